@@ -1,0 +1,72 @@
+# mlsl-b200 build: one shared library (host runtime + sm_100a kernels), the launcher, C/C++ tests and examples.
+#   make            -> mlsl_b200/lib/libmlsl_b200.so, bin/mlslrun, bin/* tests
+#   make NO_CUDA=1  -> host-only library (no nvcc needed)
+#   make sass       -> profiles/sass/*.sass listings of every kernel
+CXX      ?= g++
+NVCC     ?= /usr/local/cuda/bin/nvcc
+CUDA_HOME ?= /usr/local/cuda
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+CXXFLAGS := -O2 -g -std=c++17 -fPIC -Wall -Wextra -Wno-unused-parameter -pthread -Iinclude -Icsrc
+NVFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-parameter -Iinclude -Icsrc \
+            --expt-relaxed-constexpr -Xptxas -v
+LDFLAGS  := -shared -pthread -lrt -ldl
+ifdef DEBUG
+CXXFLAGS += -O0 -DMLSLB_DEBUG
+endif
+ifdef TSAN
+CXXFLAGS += -fsanitize=thread
+LDFLAGS  += -fsanitize=thread
+NO_CUDA := 1
+endif
+
+BUILD := build
+LIBDIR := mlsl_b200/lib
+LIB := $(LIBDIR)/libmlsl_b200.so
+
+CORE_SRC := $(wildcard csrc/core/*.cpp)
+CORE_OBJ := $(patsubst csrc/%.cpp,$(BUILD)/%.o,$(CORE_SRC))
+ifdef NO_CUDA
+CUDA_OBJ := $(BUILD)/cuda/backend_stub.o
+else
+CUDA_SRC := $(wildcard csrc/cuda/*.cu)
+CUDA_OBJ := $(patsubst csrc/%.cu,$(BUILD)/%.o,$(CUDA_SRC))
+LDFLAGS  += -L$(CUDA_HOME)/lib64 -lcudart_static
+endif
+
+TOOLS := bin/mlslrun
+TESTS := bin/mlsl_functional_test bin/cmlsl_smoke_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
+
+all: $(LIB) $(TOOLS) $(TESTS)
+
+$(BUILD)/%.o: csrc/%.cpp $(wildcard csrc/core/*.hpp) include/mlsl.hpp include/mlsl.h
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(BUILD)/%.o: csrc/%.cu $(wildcard csrc/core/*.hpp) $(wildcard csrc/cuda/*.cuh) $(wildcard csrc/cuda/*.hpp)
+	@mkdir -p $(dir $@)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/$(notdir $@).ptxas.log || (cat $(BUILD)/$(notdir $@).ptxas.log; false)
+
+$(LIB): $(CORE_OBJ) $(CUDA_OBJ)
+	@mkdir -p $(LIBDIR)
+	$(CXX) -o $@ $^ $(LDFLAGS)
+
+bin/mlslrun: csrc/tools/mlslrun.cpp
+	@mkdir -p bin
+	$(CXX) $(CXXFLAGS) -o $@ $<
+
+bin/%: csrc/tests/%.cpp $(LIB)
+	@mkdir -p bin
+	$(CXX) $(CXXFLAGS) -o $@ $< -L$(LIBDIR) -lmlsl_b200 -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+
+bin/cmlsl_smoke_test: csrc/tests/cmlsl_smoke_test.c $(LIB)
+	@mkdir -p bin
+	gcc -O2 -g -std=gnu99 -Wall -Iinclude -o $@ $< -L$(LIBDIR) -lmlsl_b200 -lm -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+
+sass: $(LIB)
+	@mkdir -p profiles/sass
+	cuobjdump -sass $(LIB) > profiles/sass/libmlsl_b200.sass
+
+clean:
+	rm -rf $(BUILD) $(LIB) bin
+
+.PHONY: all clean sass

@@ -1,0 +1,104 @@
+// Rendezvous / out-of-band control plane.
+//
+// Replaces the reference's MPI bootstrap + hydra launcher (reference src/comm_ep.cpp:1496-1750,
+// eplib/server.c:401-575) for a single NVSwitch node: ranks find each other through a POSIX shared-memory
+// control block keyed by the job id (torchrun-compatible: RANK / WORLD_SIZE / MASTER_PORT), or - for tests and
+// single-GPU loopback - live as N "virtual ranks" (threads) inside one process sharing a heap control block.
+// The control block offers: a small all-gather mailbox, a barrier, named shared regions (host heaps, signal
+// pads), file-descriptor passing (CUDA VMM / multicast handles), a poison word (fail-fast across ranks, the
+// reference only has per-process _exit) and heartbeats for the watchdog.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+
+namespace mlslb {
+
+constexpr size_t kBootSlotBytes = 1024;
+
+struct BootSlot {
+  std::atomic<uint64_t> seq[2];
+  char data[2][kBootSlotBytes];
+};
+
+constexpr size_t kGroupSlotBytes = 64;
+struct GroupSlot {
+  std::atomic<uint64_t> seq[2];
+  char data[2][kGroupSlotBytes];
+};
+
+struct alignas(64) BootCtl {
+  uint64_t magic;
+  int32_t world;
+  int32_t creator_pid;
+  uint64_t creator_start;
+  std::atomic<uint32_t> attached;
+  std::atomic<uint32_t> detached;
+  std::atomic<uint64_t> poison;        // non-zero: some rank failed; value = 1 + failing rank
+  alignas(64) std::atomic<uint64_t> heartbeat[kMaxHostRanks];
+  alignas(64) BootSlot slots[kMaxHostRanks];
+  alignas(64) GroupSlot gslots[kMaxGroupRows][kMaxHostRanks];   // per signal-row mailboxes (sub-group control plane)
+};
+
+struct InprocWorld;   // shared state of an in-process world
+
+class Bootstrap {
+ public:
+  ~Bootstrap();
+  // N virtual ranks in this process; returns one Bootstrap per rank (each to be used by its own thread).
+  static std::vector<std::unique_ptr<Bootstrap>> create_inproc(int world);
+  // Multi-process rendezvous through /dev/shm.
+  static std::unique_ptr<Bootstrap> create_shm(const std::string& job_key, int rank, int world);
+
+  int rank() const { return rank_; }
+  int size() const { return world_; }
+  bool inproc() const { return inproc_ != nullptr; }
+  const std::string& key() const { return key_; }
+
+  // in: `bytes` from every rank; out: world*bytes ordered by rank.  Any size (chunked internally).
+  void allgather(const void* in, void* out, size_t bytes);
+  void barrier();
+  // Sub-group all-gather (<= kGroupSlotBytes per rank) among `members` (global ranks) using signal row `row`;
+  // `seq` must be the same strictly increasing ticket on every member.
+  void group_allgather(const std::vector<int>& members, int row, uint64_t seq, const void* in, void* out,
+                       size_t bytes);
+
+  // Named regions.  create_region: this rank creates+maps a zero-filled region other ranks can attach to.
+  // Usage pattern: create -> barrier -> attach peers -> barrier -> seal_regions() (unlinks the names).
+  void* create_region(const std::string& name, size_t bytes);
+  void* attach_region(int owner_rank, const std::string& name, size_t bytes);
+  void release_region(void* ptr, size_t bytes, bool owner, const std::string& name);
+  void seal_regions();   // unlink every name this rank created (mappings stay valid)
+
+  // File-descriptor exchange (multi-process only): every rank contributes one fd, receives world fds
+  // (its own slot is a dup).  Used for CUDA VMM shareable handles.
+  std::vector<int> allgather_fd(int fd);
+
+  // Fail-fast: mark the job poisoned / query it / beat.
+  void poison(int code);
+  uint64_t poisoned() const;
+  void heartbeat();
+  uint64_t peer_heartbeat(int r) const;
+  BootCtl* ctl() { return ctl_; }
+
+ private:
+  Bootstrap() = default;
+  int rank_ = 0, world_ = 1;
+  std::string key_;
+  BootCtl* ctl_ = nullptr;
+  size_t ctl_bytes_ = 0;
+  uint64_t round_ = 0;
+  std::shared_ptr<InprocWorld> inproc_;
+  std::vector<std::string> created_names_;
+  int uds_fd_ = -1;
+  std::string shm_name(int owner, const std::string& name) const;
+  void wait_slots(uint64_t round);
+};
+
+}  // namespace mlslb

@@ -1,0 +1,84 @@
+#include "env.hpp"
+
+#include <cstdlib>
+#include <cstring>
+
+#include "log.hpp"
+
+namespace mlslb {
+
+static const char* ev(const char* a, const char* b = nullptr) {
+  const char* v = getenv(a);
+  if (v && *v) return v;
+  if (b) {
+    v = getenv(b);
+    if (v && *v) return v;
+  }
+  return nullptr;
+}
+static void geti(int& dst, const char* a, const char* b = nullptr) {
+  if (const char* v = ev(a, b)) dst = atoi(v);
+}
+static void getb(bool& dst, const char* a) {
+  if (const char* v = ev(a)) dst = atoi(v) != 0;
+}
+static void getz(size_t& dst, const char* a) {
+  if (const char* v = ev(a)) dst = (size_t)strtoull(v, nullptr, 10);
+}
+static void gets(std::string& dst, const char* a, const char* b = nullptr) {
+  if (const char* v = ev(a, b)) dst = v;
+}
+
+EnvConfig parse_env() {
+  EnvConfig c;
+  geti(c.log_level, "MLSL_LOG_LEVEL");
+  getb(c.stats, "MLSL_STATS");
+  getb(c.dup_group, "MLSL_DUP_GROUP");
+  geti(c.auto_config, "MLSL_AUTO_CONFIG_TYPE");
+  geti(c.num_servers, "MLSL_NUM_SERVERS", "EPLIB_MAX_EP_PER_TASK");
+  gets(c.server_affinity, "MLSL_SERVER_AFFINITY", "EPLIB_SERVER_AFFINITY");
+  geti(c.num_channels, "MLSL_NUM_CHANNELS");
+  if (const char* v = ev("MLSL_HEAP_SIZE_GB", "EPLIB_SHM_SIZE_GB")) c.heap_size_gb = atof(v);
+  getb(c.check_mem_size, "MLSL_CHECK_MEM_SIZE");
+  getz(c.max_short_msg, "MLSL_MAX_SHORT_MSG_SIZE");
+  getz(c.large_msg_mb, "MLSL_LARGE_MSG_SIZE_MB");
+  geti(c.large_msg_chunks, "MLSL_LARGE_MSG_CHUNKS");
+  geti(c.alltoall_split, "MLSL_ALLTOALL_SPLIT");
+  geti(c.alltoallv_split, "MLSL_ALLTOALLV_SPLIT");
+  getb(c.msg_priority, "MLSL_MSG_PRIORITY");
+  getz(c.msg_priority_threshold, "MLSL_MSG_PRIORITY_THRESHOLD");
+  geti(c.msg_priority_mode, "MLSL_MSG_PRIORITY_MODE");
+  getb(c.check_single_node, "MLSL_CHECK_SINGLE_NODE");
+  getb(c.pointer_check, "MLSL_POINTER_CHECK");
+  gets(c.backend, "MLSL_BACKEND");
+  gets(c.algo, "MLSL_ALGO");
+  getb(c.use_nvls, "MLSL_NVLS");
+  geti(c.one_shot_max_kb, "MLSL_ONESHOT_MAX_KB");
+  geti(c.watchdog_sec, "MLSL_WATCHDOG_SEC");
+  gets(c.wait_mode, "MLSL_WAIT_MODE");
+  gets(c.job_id, "MLSL_JOB_ID");
+  geti(c.rank, "MLSL_RANK", "RANK");
+  geti(c.world, "MLSL_WORLD_SIZE", "WORLD_SIZE");
+  geti(c.local_rank, "MLSL_LOCAL_RANK", "LOCAL_RANK");
+  geti(c.inproc_ranks, "MLSL_INPROC_RANKS");
+  geti(c.stats_iters, "MLSL_STATS_ITERS");
+  geti(c.stats_skip, "MLSL_STATS_SKIP");
+  if (c.num_servers > 16) c.num_servers = 16;
+  if (c.large_msg_chunks < 1) c.large_msg_chunks = 1;
+  return c;
+}
+
+void print_env(const EnvConfig& c) {
+  MLSLB_LOG(LOG_INFO, "MLSL_LOG_LEVEL=%d MLSL_STATS=%d MLSL_DUP_GROUP=%d MLSL_AUTO_CONFIG_TYPE=%d", c.log_level,
+            (int)c.stats, (int)c.dup_group, c.auto_config);
+  MLSLB_LOG(LOG_INFO, "MLSL_BACKEND=%s MLSL_NUM_SERVERS=%d MLSL_NUM_CHANNELS=%d MLSL_HEAP_SIZE_GB=%.2f",
+            c.backend.c_str(), c.num_servers, c.num_channels, c.heap_size_gb);
+  MLSLB_LOG(LOG_INFO, "MLSL_MAX_SHORT_MSG_SIZE=%zu MLSL_LARGE_MSG_SIZE_MB=%zu MLSL_LARGE_MSG_CHUNKS=%d",
+            c.max_short_msg, c.large_msg_mb, c.large_msg_chunks);
+  MLSLB_LOG(LOG_INFO, "MLSL_MSG_PRIORITY=%d MLSL_MSG_PRIORITY_THRESHOLD=%zu MLSL_MSG_PRIORITY_MODE=%d",
+            (int)c.msg_priority, c.msg_priority_threshold, c.msg_priority_mode);
+  MLSLB_LOG(LOG_INFO, "MLSL_NVLS=%d MLSL_ONESHOT_MAX_KB=%d MLSL_WAIT_MODE=%s MLSL_WATCHDOG_SEC=%d",
+            (int)c.use_nvls, c.one_shot_max_kb, c.wait_mode.c_str(), c.watchdog_sec);
+}
+
+}  // namespace mlslb

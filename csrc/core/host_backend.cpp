@@ -1,0 +1,570 @@
+// Host shared-memory backend: every collective of the library executed by CPU threads over POSIX shared memory
+// (or plain process memory for in-process virtual ranks).
+//
+// Role: (1) the "CPU plumbing" configuration of BASELINE.json (mlsl_sample on 2 CPU ranks), (2) makes the whole
+// graph/API layer testable without GPUs, (3) reference semantics oracle for the CUDA kernels.  It deliberately
+// uses the SAME protocol shape as the device kernels - publish buffer offsets in a per-(group,lane) signal row,
+// barrier, pull from the peers' buffers, barrier - where the reference issues MPI_I* calls on endpoint
+// communicators (reference src/comm_ep.cpp:768-1378) and stages foreign buffers through the shared heap
+// (ReplaceIn/ReplaceOut, src/comm_ep.cpp:363-566): buffers obtained from Environment::Alloc are zero-copy,
+// anything else is transparently staged.
+#include <sched.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "log.hpp"
+#include "numeric.hpp"
+#include "quant.hpp"
+#include "runtime.hpp"
+
+namespace mlslb {
+
+namespace {
+
+struct alignas(64) HostPub {
+  std::atomic<uint64_t> phase;            // 4*ticket + step
+  uint64_t send_off, recv_off;            // offsets in the owner's region (absolute pointers in-process)
+  uint64_t aux[kMaxHostRanks];            // per-destination send offsets (elements) for the *v collectives
+};
+
+constexpr int kPubRows = kMaxGroupRows * 2;
+
+struct HostReqState {
+  std::vector<float> residual;            // error-feedback residual of the quantised path (per request)
+};
+
+template <typename T>
+struct Acc { using type = T; };
+
+inline float load_as_float(const uint16_t* p, bool bf) { return bf ? bf16_to_f32(*p) : f16_to_f32(*p); }
+
+template <typename T>
+inline T apply(RedOp op, T a, T b) {
+  switch (op) {
+    case RedOp::SUM: return (T)(a + b);
+    case RedOp::MIN: return a < b ? a : b;
+    case RedOp::MAX: return a > b ? a : b;
+  }
+  return a;
+}
+
+// dst[i] = scale * reduce_p src[p][i]   (fixed p order => bitwise identical on every rank)
+template <typename T>
+void reduce_typed(T* dst, const std::vector<const void*>& srcs, size_t n, RedOp op, float scale) {
+  for (size_t i = 0; i < n; ++i) {
+    T a = ((const T*)srcs[0])[i];
+    for (size_t p = 1; p < srcs.size(); ++p) a = apply<T>(op, a, ((const T*)srcs[p])[i]);
+    if (scale != 1.0f) a = (T)(a * (T)scale);
+    dst[i] = a;
+  }
+}
+
+void reduce_half(uint16_t* dst, const std::vector<const void*>& srcs, size_t n, RedOp op, float scale, bool bf) {
+  for (size_t i = 0; i < n; ++i) {
+    float a = load_as_float((const uint16_t*)srcs[0] + i, bf);
+    for (size_t p = 1; p < srcs.size(); ++p) a = apply<float>(op, a, load_as_float((const uint16_t*)srcs[p] + i, bf));
+    a *= scale;
+    dst[i] = bf ? f32_to_bf16(a) : f32_to_f16(a);
+  }
+}
+
+void reduce_any(DType dt, void* dst, const std::vector<const void*>& srcs, size_t n, RedOp op, float scale) {
+  switch (dt) {
+    case DType::F32: reduce_typed<float>((float*)dst, srcs, n, op, scale); break;
+    case DType::F64: reduce_typed<double>((double*)dst, srcs, n, op, scale); break;
+    case DType::U8:
+    case DType::F8E4M3: reduce_typed<uint8_t>((uint8_t*)dst, srcs, n, op, 1.0f); break;
+    case DType::I32: reduce_typed<int32_t>((int32_t*)dst, srcs, n, op, 1.0f); break;
+    case DType::BF16: reduce_half((uint16_t*)dst, srcs, n, op, scale, true); break;
+    case DType::F16: reduce_half((uint16_t*)dst, srcs, n, op, scale, false); break;
+  }
+}
+
+class HostBackend final : public Backend {
+ public:
+  explicit HostBackend(RankContext* ctx) : ctx_(ctx) {
+    Bootstrap* b = ctx->boot.get();
+    inproc_ = b->inproc();
+    world_ = b->size();
+    rank_ = b->rank();
+    pub_bytes_ = round_up(sizeof(HostPub) * kPubRows, 4096);
+    if (inproc_) {
+      // all virtual ranks share the address space: only the signal rows need a shared region
+      region_bytes_ = pub_bytes_;
+    } else {
+      double gb = ctx->env.heap_size_gb;
+      region_bytes_ = pub_bytes_ + (size_t)(gb * 1024.0 * 1024.0 * 1024.0);
+    }
+    base_.assign(world_, nullptr);
+    base_[rank_] = (char*)b->create_region("hheap", region_bytes_);
+    b->barrier();
+    for (int p = 0; p < world_; ++p)
+      if (p != rank_) base_[p] = (char*)b->attach_region(p, "hheap", region_bytes_);
+    b->barrier();
+    b->seal_regions();
+    if (!inproc_) heap_.reset(pub_bytes_, region_bytes_ - pub_bytes_);
+    MLSLB_LOG(LOG_DEBUG, "host backend: world %d inproc %d region %zu bytes", world_, (int)inproc_, region_bytes_);
+  }
+
+  ~HostBackend() override {}
+
+  const char* name() const override { return "host"; }
+
+  void* alloc(size_t bytes, size_t align) override {
+    if (align == 0) align = 64;
+    void* p = nullptr;
+    if (inproc_) {
+      MLSLB_ASSERT(posix_memalign(&p, std::max<size_t>(align, 64), round_up(std::max<size_t>(bytes, 1), 64)) == 0,
+                   "host alloc of %zu bytes failed", bytes);
+      std::lock_guard<std::mutex> g(mu_);
+      inproc_live_[p] = bytes;
+    } else {
+      size_t off = heap_.alloc(bytes, align);
+      MLSLB_ASSERT(off != SIZE_MAX,
+                   "symmetric host heap exhausted (%zu bytes requested, %zu of %zu in use): raise MLSL_HEAP_SIZE_GB",
+                   bytes, heap_.bytes_in_use(), heap_.capacity());
+      p = base_[rank_] + off;
+    }
+    ctx_->ptrcheck.add(p, bytes);
+    return p;
+  }
+
+  void free(void* p) override {
+    if (!p) return;
+    ctx_->ptrcheck.remove(p);
+    if (inproc_) {
+      std::lock_guard<std::mutex> g(mu_);
+      auto it = inproc_live_.find(p);
+      MLSLB_ASSERT(it != inproc_live_.end(), "Free of a pointer that did not come from Alloc");
+      inproc_live_.erase(it);
+      ::free(p);
+    } else {
+      MLSLB_ASSERT(heap_.free((size_t)((char*)p - base_[rank_])), "Free of a pointer that did not come from Alloc");
+    }
+  }
+
+  bool owns(const void* p, size_t len) const override {
+    if (inproc_) return true;   // one address space: every buffer is directly visible to the peers
+    const char* c = (const char*)p;
+    return c >= base_[rank_] + pub_bytes_ && c + len <= base_[rank_] + region_bytes_;
+  }
+
+  void prepare(CommRequest& r) override {
+    if (!r.backend_state) r.backend_state = new HostReqState();
+  }
+  void release(CommRequest& r) override {
+    delete (HostReqState*)r.backend_state;
+    r.backend_state = nullptr;
+  }
+
+  void launch(CommRequest& r) override {
+    execute(r);
+    r.state.store(CommRequest::DONE, std::memory_order_release);
+  }
+  bool test(CommRequest& r) override { return r.state.load(std::memory_order_acquire) >= CommRequest::DONE; }
+  void wait(CommRequest& r) override {
+    uint64_t spins = 0;
+    while (r.state.load(std::memory_order_acquire) < CommRequest::DONE)
+      if ((++spins & 0xff) == 0) sched_yield();
+  }
+
+  void finalize() override {
+    Bootstrap* b = ctx_->boot.get();
+    b->barrier();
+    for (int p = 0; p < world_; ++p)
+      if (base_[p]) b->release_region(base_[p], region_bytes_, p == rank_, "hheap");
+    base_.clear();
+  }
+
+  std::string describe() const override {
+    return std::string("host shared-memory backend (") + (inproc_ ? "in-process ranks" : "POSIX shm") + ")";
+  }
+
+ private:
+  RankContext* ctx_;
+  bool inproc_ = false;
+  int world_ = 1, rank_ = 0;
+  size_t pub_bytes_ = 0, region_bytes_ = 0;
+  std::vector<char*> base_;
+  SlabAllocator heap_;
+  std::mutex mu_;
+  std::map<void*, size_t> inproc_live_;
+
+  HostPub* pub(int global_rank, int prow) const { return (HostPub*)base_[global_rank] + prow; }
+  uint64_t to_off(const void* p) const { return inproc_ ? (uint64_t)(uintptr_t)p : (uint64_t)((const char*)p - base_[rank_]); }
+  char* peer_ptr(int global_rank, uint64_t off) const {
+    return inproc_ ? (char*)(uintptr_t)off : base_[global_rank] + off;
+  }
+
+  struct Stage {
+    void* user = nullptr;
+    void* slab = nullptr;
+    size_t bytes = 0;
+  };
+
+  void wait_all(const ProcessGroup& g, int prow, uint64_t target) {
+    uint64_t spins = 0, t0 = 0;
+    for (int m : g.members) {
+      HostPub* pp = pub(m, prow);
+      while (pp->phase.load(std::memory_order_acquire) < target) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((++spins & 0x3ff) == 0) {
+          sched_yield();
+          if (ctx_->boot->poisoned())
+            MLSLB_ASSERT(false, "job poisoned by rank %d during a host collective", (int)ctx_->boot->poisoned() - 1);
+          if (!t0) t0 = now_ns();
+          int wd = ctx_->env.watchdog_sec;
+          if (wd > 0 && now_ns() - t0 > (uint64_t)wd * 1000000000ull) {
+            ctx_->boot->poison(rank_);
+            MLSLB_ASSERT(false, "watchdog: rank %d never reached phase %llu on signal row %d", m,
+                         (unsigned long long)target, prow);
+          }
+        }
+      }
+    }
+  }
+
+  void execute(CommRequest& r);
+  void exec_quantized_allreduce(CommRequest& r, const ProcessGroup& g, int prow, char* S, char* R);
+};
+
+void HostBackend::execute(CommRequest& r) {
+  const CommDesc& d = r.desc;
+  ProcessGroup* gp = d.group;
+  const size_t dt = dtype_size(d.dtype);
+  const size_t n = d.count;
+  // ---- single-rank groups: local semantics only --------------------------------------------------------
+  if (!gp || gp->size() <= 1) {
+    switch (d.kind) {
+      case OpKind::ALLREDUCE:
+      case OpKind::REDUCE:
+      case OpKind::REDUCE_SCATTER:
+      case OpKind::ALLGATHER:
+      case OpKind::GATHER:
+      case OpKind::SCATTER:
+      case OpKind::ALLTOALL:
+        if (r.recv && r.recv != r.send && n) memmove(r.recv, r.send, n * dt);
+        if (d.scale != 1.0f && r.recv && (d.kind == OpKind::ALLREDUCE || d.kind == OpKind::REDUCE_SCATTER)) {
+          std::vector<const void*> one{r.recv};
+          reduce_any(d.dtype, r.recv, one, n, RedOp::SUM, d.scale);
+        }
+        break;
+      case OpKind::ALLGATHERV:
+        if (r.recv && r.recv != r.send && n) memmove(r.recv, r.send, n * dt);
+        break;
+      case OpKind::ALLTOALLV:
+      case OpKind::SENDRECV_LIST:
+        if (!d.send_counts.empty() && d.send_counts[0])
+          memmove((char*)r.recv + d.recv_offsets[0] * dt, (char*)r.send + d.send_offsets[0] * dt, d.send_counts[0] * dt);
+        break;
+      default: break;
+    }
+    return;
+  }
+  const ProcessGroup& g = *gp;
+  const int P = g.size();
+  const int me = g.idx;
+  const int prow = g.row * 2 + r.lane;
+  const uint64_t t = r.group_seq;
+  HostPub* mine = pub(rank_, prow);
+
+  // ---- stage foreign buffers into the symmetric heap -----------------------------------------------------
+  std::vector<Stage> stages;
+  auto stage = [&](void* user, size_t bytes, bool copy_in) -> char* {
+    if (!user || bytes == 0 || owns(user, bytes)) return (char*)user;
+    Stage s;
+    s.user = user;
+    s.bytes = bytes;
+    s.slab = alloc(bytes, 64);
+    if (copy_in) memcpy(s.slab, user, bytes);
+    stages.push_back(s);
+    return (char*)s.slab;
+  };
+  size_t sbytes = r.send_bytes(), rbytes = r.recv_bytes();
+  if (d.kind == OpKind::REDUCE && me != (int)d.root) rbytes = 0;
+  if (d.kind == OpKind::GATHER && me != (int)d.root) rbytes = 0;
+  if (d.kind == OpKind::SCATTER && me != (int)d.root) sbytes = 0;
+  char* R = nullptr;
+  char* S = nullptr;
+  bool recv_staged = false;
+  if (r.recv && rbytes) {
+    size_t before = stages.size();
+    R = stage(r.recv, rbytes, true);
+    recv_staged = stages.size() != before;
+  }
+  if (r.send && sbytes) {
+    char* us = (char*)r.send;
+    char* ur = (char*)r.recv;
+    if (ur && rbytes && us >= ur && us + sbytes <= ur + rbytes) {
+      S = R + (us - ur);             // send aliases the receive buffer (in-place variants)
+    } else {
+      S = stage(r.send, sbytes, true);
+    }
+  }
+
+  auto arrive = [&](int step) { mine->phase.store(4 * t + step, std::memory_order_release); };
+  auto sync = [&](int step) {
+    arrive(step);
+    wait_all(g, prow, 4 * t + step);
+  };
+  mine->send_off = to_off(S);
+  mine->recv_off = to_off(R);
+  if (d.kind == OpKind::ALLTOALLV || d.kind == OpKind::SENDRECV_LIST)
+    for (int p = 0; p < P; ++p) mine->aux[p] = d.send_offsets[p];
+  sync(0);
+
+  auto peerS = [&](int p) { return (const char*)peer_ptr(g.members[p], pub(g.members[p], prow)->send_off); };
+  auto peerR = [&](int p) { return (const char*)peer_ptr(g.members[p], pub(g.members[p], prow)->recv_off); };
+
+  switch (d.kind) {
+    case OpKind::BARRIER: break;
+    case OpKind::ALLREDUCE: {
+      if (d.compress && d.dtype == DType::F32 && d.rop == RedOp::SUM) {
+        exec_quantized_allreduce(r, g, prow, S, R);
+        break;
+      }
+      size_t per = ceil_div(n, (size_t)P);
+      size_t lo = std::min(n, (size_t)me * per), hi = std::min(n, lo + per);
+      std::vector<const void*> srcs(P);
+      for (int p = 0; p < P; ++p) srcs[p] = peerS(p) + lo * dt;
+      if (hi > lo) reduce_any(d.dtype, R + lo * dt, srcs, hi - lo, d.rop, d.scale);
+      sync(1);
+      for (int p = 0; p < P; ++p) {
+        if (p == me) continue;
+        size_t plo = std::min(n, (size_t)p * per), phi = std::min(n, plo + per);
+        if (phi > plo) memcpy(R + plo * dt, peerR(p) + plo * dt, (phi - plo) * dt);
+      }
+      sync(2);
+      break;
+    }
+    case OpKind::REDUCE_SCATTER: {
+      std::vector<const void*> srcs(P);
+      for (int p = 0; p < P; ++p) srcs[p] = peerS(p) + (size_t)me * n * dt;
+      bool alias = R >= S && R < S + sbytes;
+      if (alias) {
+        std::vector<char> tmp(n * dt);
+        reduce_any(d.dtype, tmp.data(), srcs, n, d.rop, d.scale);
+        sync(1);
+        memcpy(R, tmp.data(), n * dt);
+      } else {
+        reduce_any(d.dtype, R, srcs, n, d.rop, d.scale);
+        sync(1);
+      }
+      break;
+    }
+    case OpKind::ALLGATHER: {
+      for (int p = 0; p < P; ++p) {
+        char* dst = R + (size_t)p * n * dt;
+        const char* src = peerS(p);
+        if (dst != src) memcpy(dst, src, n * dt);
+      }
+      sync(1);
+      break;
+    }
+    case OpKind::ALLGATHERV: {
+      size_t off = 0;
+      for (int p = 0; p < P; ++p) {
+        char* dst = R + off * dt;
+        const char* src = peerS(p);
+        if (dst != src && d.recv_counts[p]) memcpy(dst, src, d.recv_counts[p] * dt);
+        off += d.recv_counts[p];
+      }
+      sync(1);
+      break;
+    }
+    case OpKind::BCAST: {
+      // Bcast uses one buffer: it was published as the recv pointer
+      if (me != (int)d.root) memcpy(R, peerR((int)d.root), n * dt);
+      sync(1);
+      break;
+    }
+    case OpKind::REDUCE: {
+      if (me == (int)d.root) {
+        std::vector<const void*> srcs(P);
+        for (int p = 0; p < P; ++p) srcs[p] = peerS(p);
+        reduce_any(d.dtype, R, srcs, n, d.rop, d.scale);
+      }
+      sync(1);
+      break;
+    }
+    case OpKind::ALLTOALL: {
+      bool alias = R == S;
+      std::vector<char> tmp;
+      char* dstbase = R;
+      if (alias) {
+        tmp.resize((size_t)P * n * dt);
+        dstbase = tmp.data();
+      }
+      for (int p = 0; p < P; ++p) memcpy(dstbase + (size_t)p * n * dt, peerS(p) + (size_t)me * n * dt, n * dt);
+      sync(1);
+      if (alias) memcpy(R, tmp.data(), tmp.size());
+      break;
+    }
+    case OpKind::ALLTOALLV:
+    case OpKind::SENDRECV_LIST: {
+      for (int p = 0; p < P; ++p) {
+        size_t cnt = d.recv_counts[p];
+        if (!cnt) continue;
+        size_t soff = pub(g.members[p], prow)->aux[me];
+        memcpy(R + d.recv_offsets[p] * dt, peerS(p) + soff * dt, cnt * dt);
+      }
+      sync(1);
+      break;
+    }
+    case OpKind::GATHER: {
+      if (me == (int)d.root)
+        for (int p = 0; p < P; ++p) memcpy(R + (size_t)p * n * dt, peerS(p), n * dt);
+      sync(1);
+      break;
+    }
+    case OpKind::SCATTER: {
+      const char* src = peerS((int)d.root) + (size_t)me * n * dt;
+      if (R != src) memcpy(R, src, n * dt);
+      sync(1);
+      break;
+    }
+    case OpKind::FUSED_UPDATE: {
+      // reduce-scatter -> optimizer on the owned shard -> all-gather of the updated parameters.
+      // S: full gradient (P*n elements of d.dtype), d.fused.param: full parameters (P*n of out dtype).
+      MLSLB_ASSERT(d.dtype == DType::F32 || d.dtype == DType::BF16, "fused update: gradient dtype must be f32/bf16");
+      DType pdt = d.has_out_dtype ? d.out_dtype : d.dtype;
+      MLSLB_ASSERT(pdt == DType::F32 || pdt == DType::BF16, "fused update: parameter dtype must be f32/bf16");
+      const CommDesc::FusedUpdate& f = d.fused;
+      std::vector<float> gsum(n);
+      for (size_t i = 0; i < n; ++i) {
+        float a = 0.f;
+        for (int p = 0; p < P; ++p) {
+          const char* sp = peerS(p) + ((size_t)me * n + i) * dt;
+          a += d.dtype == DType::F32 ? *(const float*)sp : bf16_to_f32(*(const uint16_t*)sp);
+        }
+        gsum[i] = a * d.scale;
+      }
+      char* param = (char*)f.param;
+      size_t pdts = dtype_size(pdt);
+      float* master = (float*)f.master;
+      float* m1 = (float*)f.state1;
+      float* m2 = (float*)f.state2;
+      float bc1 = 1.f, bc2 = 1.f;
+      if (f.optimizer == 1) {
+        bc1 = 1.f - powf(f.beta1, (float)f.step);
+        bc2 = 1.f - powf(f.beta2, (float)f.step);
+      }
+      for (size_t i = 0; i < n; ++i) {
+        char* pp = param + ((size_t)me * n + i) * pdts;
+        float w = master ? master[i] : (pdt == DType::F32 ? *(float*)pp : bf16_to_f32(*(uint16_t*)pp));
+        float gr = gsum[i];
+        if (f.optimizer == 0) {
+          gr += f.weight_decay * w;
+          if (m1) {
+            m1[i] = f.momentum * m1[i] + gr;
+            gr = m1[i];
+          }
+          w -= f.lr * gr;
+        } else {
+          m1[i] = f.beta1 * m1[i] + (1.f - f.beta1) * gr;
+          m2[i] = f.beta2 * m2[i] + (1.f - f.beta2) * gr * gr;
+          float mh = m1[i] / bc1, vh = m2[i] / bc2;
+          w -= f.lr * (mh / (sqrtf(vh) + f.eps) + f.weight_decay * w);
+        }
+        if (master) master[i] = w;
+        if (pdt == DType::F32) *(float*)pp = w; else *(uint16_t*)pp = f32_to_bf16(w);
+      }
+      // publish parameter buffer for the gather step
+      mine->recv_off = to_off(param);
+      sync(1);
+      for (int p = 0; p < P; ++p) {
+        if (p == me) continue;
+        const char* src = peer_ptr(g.members[p], pub(g.members[p], prow)->recv_off) + (size_t)p * n * pdts;
+        memcpy(param + (size_t)p * n * pdts, src, n * pdts);
+      }
+      sync(2);
+      break;
+    }
+    case OpKind::GEMM_RS:
+      MLSLB_ASSERT(false, "GEMM+reduce-scatter is a device-only fused op");
+      break;
+  }
+
+  // ---- copy staged results back, drop the staging buffers -----------------------------------------------
+  for (auto& s : stages) {
+    if (recv_staged && s.user == r.recv) memcpy(s.user, s.slab, s.bytes);
+    free(s.slab);
+  }
+}
+
+// Quantised all-reduce with error feedback, CPU edition of the fused device kernel (same block format and the
+// same three steps, so both backends agree to rounding): see quant.hpp.
+void HostBackend::exec_quantized_allreduce(CommRequest& r, const ProcessGroup& g, int prow, char* S, char* R) {
+  const CommDesc& d = r.desc;
+  const size_t n = d.count;
+  const int P = g.size(), me = g.idx;
+  const uint64_t t = r.group_seq;
+  HostPub* mine = pub(rank_, prow);
+  HostReqState* st = (HostReqState*)r.backend_state;
+  if (st->residual.size() != n) st->residual.assign(n, 0.f);
+  const size_t nblk = ceil_div(n, (size_t)kQuantBlock);
+  const size_t blk_per = ceil_div(nblk, (size_t)P);
+  // staging: [q bytes | scales] x2 (own quantised input, reduced+requantised slice exchange)
+  size_t qbytes = round_up(nblk * kQuantBlock, 64), sbytes = round_up(nblk * sizeof(float), 64);
+  char* stage = (char*)alloc(2 * (qbytes + sbytes), 64);
+  uint8_t* q1 = (uint8_t*)stage;
+  float* s1 = (float*)(stage + qbytes);
+  uint8_t* q2 = (uint8_t*)(stage + qbytes + sbytes);
+  float* s2 = (float*)(stage + 2 * qbytes + sbytes);
+  const float* x = (const float*)S;
+  float* y = (float*)R;
+  // step 1: x + residual -> fp8 blocks, residual update
+  for (size_t b = 0; b < nblk; ++b) {
+    size_t lo = b * kQuantBlock, hi = std::min(n, lo + kQuantBlock);
+    float v[kQuantBlock];
+    for (size_t i = lo; i < hi; ++i) v[i - lo] = x[i] + st->residual[i];
+    for (size_t i = hi - lo; i < (size_t)kQuantBlock; ++i) v[i] = 0.f;
+    s1[b] = quant_block(v, q1 + lo);
+    for (size_t i = lo; i < hi; ++i) st->residual[i] = v[i - lo] - e4m3_to_f32(q1[i]) * s1[b];
+  }
+  mine->send_off = to_off(stage);
+  auto sync = [&](int step) {
+    mine->phase.store(4 * t + step, std::memory_order_release);
+    wait_all(g, prow, 4 * t + step);
+  };
+  sync(1);
+  // step 2: my block range: dequant-accumulate over peers in fp32, requantise
+  size_t blo = std::min(nblk, (size_t)me * blk_per), bhi = std::min(nblk, blo + blk_per);
+  for (size_t b = blo; b < bhi; ++b) {
+    float acc[kQuantBlock];
+    for (int i = 0; i < kQuantBlock; ++i) acc[i] = 0.f;
+    for (int p = 0; p < P; ++p) {
+      const char* ps = peer_ptr(g.members[p], pub(g.members[p], prow)->send_off);
+      const uint8_t* pq = (const uint8_t*)ps + b * kQuantBlock;
+      float sc = ((const float*)(ps + qbytes))[b];
+      for (int i = 0; i < kQuantBlock; ++i) acc[i] += e4m3_to_f32(pq[i]) * sc;
+    }
+    s2[b] = quant_block(acc, q2 + b * kQuantBlock);
+  }
+  sync(2);
+  // step 3: gather every slice, dequantise with the fused output scale
+  for (int p = 0; p < P; ++p) {
+    const char* ps = peer_ptr(g.members[p], pub(g.members[p], prow)->send_off);
+    const uint8_t* pq = (const uint8_t*)ps + qbytes + sbytes;
+    const float* psc = (const float*)(ps + 2 * qbytes + sbytes);
+    size_t plo = std::min(nblk, (size_t)p * blk_per), phi = std::min(nblk, plo + blk_per);
+    for (size_t b = plo; b < phi; ++b) {
+      size_t lo = b * kQuantBlock, hi = std::min(n, lo + kQuantBlock);
+      for (size_t i = lo; i < hi; ++i) y[i] = e4m3_to_f32(pq[i]) * psc[b] * d.scale;
+    }
+  }
+  sync(3);
+  free(stage);
+}
+
+}  // namespace
+
+std::unique_ptr<Backend> make_host_backend(RankContext* ctx) { return std::unique_ptr<Backend>(new HostBackend(ctx)); }
+
+}  // namespace mlslb

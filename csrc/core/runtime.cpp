@@ -1,0 +1,623 @@
+#include "runtime.hpp"
+
+#include <pthread.h>
+#include <sched.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "log.hpp"
+
+namespace mlslb {
+
+// ============================================================================================================
+// CommRequest
+// ============================================================================================================
+CommRequest::CommRequest(RankContext* c, DType dt, int64_t uid, CommDesc::CompType ct) : ctx(c) {
+  desc.dtype = dt;
+  desc.op_uid = uid;
+  desc.comp_type = ct;
+}
+
+CommRequest::~CommRequest() {
+  if (ctx && ctx->backend && backend_state) ctx->backend->release(*this);
+}
+
+// Buffer-size rules.  Same contract as the reference's CommRequestImpl::Setup (src/comm_ep.cpp:568-766): the
+// comm buffer is [send region | recv region] for ops we run out of place and just the message for in-place ops.
+// We run ReduceScatter / AlltoAll(v) / Gather out of place (what the reference does whenever endpoints are
+// active) because a peer-memory kernel cannot overwrite a slice other GPUs are still reading.
+void CommRequest::setup() {
+  const size_t dt = dtype_size(desc.dtype);
+  const size_t P = desc.group ? (size_t)desc.group->size() : 1;
+  const size_t n = desc.count;
+  oop_default_ = false;
+  switch (desc.kind) {
+    case OpKind::BARRIER:
+      send_bytes_ = recv_bytes_ = buf_bytes_ = msg_bytes_ = 0;
+      break;
+    case OpKind::BCAST:
+    case OpKind::REDUCE:
+    case OpKind::ALLREDUCE:
+      send_bytes_ = recv_bytes_ = buf_bytes_ = msg_bytes_ = n * dt;
+      break;
+    case OpKind::ALLGATHER:
+      send_bytes_ = n * dt;
+      recv_bytes_ = n * P * dt;
+      buf_bytes_ = recv_bytes_;          // in place: rank r's contribution lives at r*n
+      msg_bytes_ = recv_bytes_;
+      break;
+    case OpKind::ALLGATHERV: {
+      size_t tot = 0;
+      for (size_t c : desc.recv_counts) tot += c;
+      send_bytes_ = n * dt;
+      recv_bytes_ = buf_bytes_ = msg_bytes_ = tot * dt;
+      break;
+    }
+    case OpKind::REDUCE_SCATTER:
+      send_bytes_ = n * P * dt;
+      recv_bytes_ = n * dt;
+      buf_bytes_ = send_bytes_ + recv_bytes_;
+      msg_bytes_ = send_bytes_;
+      oop_default_ = true;
+      break;
+    case OpKind::ALLTOALL:
+      send_bytes_ = recv_bytes_ = n * P * dt;
+      buf_bytes_ = 2 * send_bytes_;
+      msg_bytes_ = send_bytes_;
+      oop_default_ = true;
+      break;
+    case OpKind::ALLTOALLV: {
+      size_t s = 0, r = 0;
+      for (size_t i = 0; i < desc.send_counts.size(); ++i)
+        s = std::max(s, desc.send_offsets[i] + desc.send_counts[i]);
+      for (size_t i = 0; i < desc.recv_counts.size(); ++i)
+        r = std::max(r, desc.recv_offsets[i] + desc.recv_counts[i]);
+      send_bytes_ = s * dt;
+      recv_bytes_ = r * dt;
+      buf_bytes_ = send_bytes_ + recv_bytes_;
+      msg_bytes_ = send_bytes_;
+      oop_default_ = true;
+      break;
+    }
+    case OpKind::GATHER:
+      send_bytes_ = n * dt;
+      recv_bytes_ = n * P * dt;
+      buf_bytes_ = 0;
+      msg_bytes_ = recv_bytes_;
+      oop_default_ = true;
+      break;
+    case OpKind::SCATTER:
+      send_bytes_ = n * P * dt;
+      recv_bytes_ = n * dt;
+      buf_bytes_ = 0;
+      msg_bytes_ = send_bytes_;
+      oop_default_ = true;
+      break;
+    case OpKind::SENDRECV_LIST: {
+      size_t s = 0, r = 0;
+      for (size_t i = 0; i < desc.send_counts.size(); ++i)
+        s = std::max(s, desc.send_offsets[i] + desc.send_counts[i]);
+      for (size_t i = 0; i < desc.recv_counts.size(); ++i)
+        r = std::max(r, desc.recv_offsets[i] + desc.recv_counts[i]);
+      send_bytes_ = s * dt;
+      recv_bytes_ = r * dt;
+      buf_bytes_ = send_bytes_ + recv_bytes_;
+      msg_bytes_ = send_bytes_;
+      oop_default_ = true;
+      break;
+    }
+    case OpKind::FUSED_UPDATE:
+      send_bytes_ = n * P * dt;          // full gradient buffer (n = owned elements)
+      recv_bytes_ = n * P * dtype_size(desc.has_out_dtype ? desc.out_dtype : desc.dtype);
+      buf_bytes_ = 0;
+      msg_bytes_ = send_bytes_;
+      break;
+    case OpKind::GEMM_RS:
+      send_bytes_ = recv_bytes_ = buf_bytes_ = msg_bytes_ = 0;
+      break;
+  }
+  // priority lane: large gradient messages of the earliest operations overtake the rest (the intent of the
+  // reference's newest-first Rabenseifner progress, eplib/allreduce_pr.c:76-79: first-layer gradients first).
+  lane = 0;
+  if (ctx->env.msg_priority && desc.comp_type == CommDesc::PARAM_GRAD && msg_bytes_ >= ctx->env.msg_priority_threshold) {
+    int ops = ctx->session_ops_hint > 0 ? ctx->session_ops_hint : 4;
+    int cut = std::max(1, ops / 4);
+    if (desc.op_uid >= 0 && (desc.op_uid % (int64_t)std::max(ops, 1)) < cut && ctx->env.msg_priority_mode == 1) lane = 1;
+  }
+  setup_done = true;
+  if (ctx->backend) ctx->backend->prepare(*this);
+}
+
+void CommRequest::start(void* s, void* r) {
+  MLSLB_ASSERT(setup_done, "request started before Setup()");
+  MLSLB_ASSERT(state.load(std::memory_order_acquire) == IDLE, "%s request started while still in flight",
+               opkind_name(desc.kind));
+  send = s;
+  recv = r;
+  // In-place all-gather convention (MPI_IN_PLACE): rank i's contribution already sits in its slot of the
+  // receive buffer.
+  if (s == r && desc.group && (desc.kind == OpKind::ALLGATHER || desc.kind == OpKind::ALLGATHERV)) {
+    size_t off = 0;
+    if (desc.kind == OpKind::ALLGATHER) off = (size_t)desc.group->idx * desc.count;
+    else for (int p = 0; p < desc.group->idx; ++p) off += desc.recv_counts[(size_t)p];
+    send = (char*)r + off * dtype_size(desc.dtype);
+  }
+  if (ctx->env.pointer_check) {
+    if (send_bytes_) ctx->check_pointer(s, send_bytes_, "send buffer");
+    if (recv_bytes_ && r) ctx->check_pointer(r, recv_bytes_, "recv buffer");
+  }
+  start_ns = now_ns();
+  ProcessGroup* g = desc.group;
+  if (!g || g->size() <= 1 || g->is_self) {
+    group_seq = 0;
+  } else {
+    group_seq = ++g->seq[lane];
+  }
+  state.store(QUEUED, std::memory_order_release);
+  ctx->progress->submit(this);
+}
+
+static void spin_until_launched(CommRequest* r) {
+  uint64_t spins = 0, t0 = 0;
+  while (r->state.load(std::memory_order_acquire) == CommRequest::QUEUED) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0xfff) == 0) {
+      sched_yield();
+      if (r->ctx->boot && r->ctx->boot->poisoned())
+        MLSLB_ASSERT(false, "job poisoned by rank %d", (int)r->ctx->boot->poisoned() - 1);
+      if (!t0) t0 = now_ns();
+      int wd = r->ctx->env.watchdog_sec;
+      if (wd > 0 && now_ns() - t0 > (uint64_t)wd * 1000000000ull) {
+        if (r->ctx->boot) r->ctx->boot->poison(r->ctx->rank);
+        MLSLB_ASSERT(false, "watchdog: %s on group row %d seq %llu was never launched (a peer is missing?)",
+                     opkind_name(r->desc.kind), r->desc.group ? r->desc.group->row : -1,
+                     (unsigned long long)r->group_seq);
+      }
+    }
+  }
+}
+
+void* CommRequest::wait() {
+  int st = state.load(std::memory_order_acquire);
+  if (st == IDLE) return recv;      // nothing in flight (already completed through Test)
+  spin_until_launched(this);
+  ctx->backend->wait(*this);
+  done_ns = now_ns();
+  state.store(IDLE, std::memory_order_release);
+  return recv;
+}
+
+void* CommRequest::test(bool* done) {
+  int st = state.load(std::memory_order_acquire);
+  if (st == IDLE) {
+    *done = true;
+    return recv;
+  }
+  if (st == QUEUED) {
+    *done = false;
+    return nullptr;
+  }
+  if (ctx->backend->test(*this)) {
+    done_ns = now_ns();
+    state.store(IDLE, std::memory_order_release);
+    *done = true;
+    return recv;
+  }
+  *done = false;
+  return nullptr;
+}
+
+// ============================================================================================================
+// ProgressEngine
+// ============================================================================================================
+static void pin_thread(const std::string& affinity, int idx) {
+  // "MLSL_SERVER_AFFINITY=5,6,7": server i runs on the i-th listed cpu.  Default (reference eplib/env.c:207-218):
+  // the last cores in reverse order.
+  int ncpu = (int)sysconf(_SC_NPROCESSORS_ONLN);
+  int cpu = -1;
+  if (!affinity.empty()) {
+    std::vector<int> list;
+    const char* p = affinity.c_str();
+    while (*p) {
+      list.push_back(atoi(p));
+      const char* c = strchr(p, ',');
+      if (!c) break;
+      p = c + 1;
+    }
+    if (!list.empty()) cpu = list[idx % list.size()];
+  }
+  if (cpu < 0 || cpu >= ncpu) return;   // unpinned by default: ranks share the node, let the OS place servers
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  CPU_SET(cpu, &set);
+  pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+}
+
+ProgressEngine::ProgressEngine(RankContext* ctx, int num_servers) : ctx_(ctx) {
+  for (int i = 0; i < num_servers; ++i) {
+    servers_.emplace_back(new Server());
+    Server* s = servers_.back().get();
+    s->th = std::thread([this, s, i] { run(s, i); });
+  }
+}
+
+ProgressEngine::~ProgressEngine() {
+  for (auto& s : servers_) {
+    Command c;
+    c.kind = Command::STOP;
+    {
+      std::lock_guard<std::mutex> g(s->mu);
+      while (!s->ring.push(c)) sched_yield();
+    }
+  }
+  for (auto& s : servers_)
+    if (s->th.joinable()) s->th.join();
+}
+
+void ProgressEngine::submit(CommRequest* r) {
+  if (servers_.empty()) {
+    ctx_->backend->launch(*r);
+    launched_.fetch_add(1, std::memory_order_relaxed);
+    return;
+  }
+  int row = r->desc.group ? std::max(r->desc.group->row, 0) : 0;
+  Server* s = servers_[(size_t)(row * 2 + r->lane) % servers_.size()].get();
+  Command c;
+  c.kind = Command::EXEC;
+  c.req = r;
+  std::lock_guard<std::mutex> g(s->mu);
+  s->submitted.fetch_add(1, std::memory_order_relaxed);
+  while (!s->ring.push(c)) sched_yield();   // back-pressure (the reference only detects overflow server-side)
+}
+
+void ProgressEngine::drain() {
+  for (auto& s : servers_)
+    while (s->completed.load(std::memory_order_acquire) < s->submitted.load(std::memory_order_acquire)) sched_yield();
+}
+
+void ProgressEngine::suspend() {
+  for (auto& s : servers_) {
+    Command c;
+    c.kind = Command::SUSPEND;
+    std::lock_guard<std::mutex> g(s->mu);
+    while (!s->ring.push(c)) sched_yield();
+  }
+}
+
+void ProgressEngine::resume() {
+  for (auto& s : servers_) s->parked.store(false, std::memory_order_release);
+}
+
+void ProgressEngine::run(Server* s, int idx) {
+  pin_thread(ctx_->env.server_affinity, idx);
+  set_log_rank(ctx_->rank);
+  uint64_t idle = 0;
+  for (;;) {
+    Command c;
+    if (!s->ring.pop(c)) {
+      if (++idle < 2000) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      } else if (idle < 20000) {
+        sched_yield();
+      } else {
+        usleep(50);
+      }
+      if (ctx_->boot && (idle & 0x3ff) == 0) ctx_->boot->heartbeat();
+      continue;
+    }
+    idle = 0;
+    if (c.kind == Command::STOP) return;
+    if (c.kind == Command::SUSPEND) {
+      s->parked.store(true, std::memory_order_release);
+      while (s->parked.load(std::memory_order_acquire)) usleep(100);
+      continue;
+    }
+    if (c.kind == Command::EXEC) {
+      try {
+        ctx_->backend->launch(*c.req);
+      } catch (const std::exception& e) {
+        fprintf(stderr, "(r%d) progress thread: %s\n", ctx_->rank, e.what());
+        if (ctx_->boot) ctx_->boot->poison(ctx_->rank);
+        c.req->state.store(CommRequest::LAUNCHED, std::memory_order_release);
+      }
+      launched_.fetch_add(1, std::memory_order_relaxed);
+      s->completed.fetch_add(1, std::memory_order_release);
+    }
+  }
+}
+
+// ============================================================================================================
+// Backend defaults
+// ============================================================================================================
+void Backend::pack_blocks(const BlockDesc* blocks, size_t nblocks, size_t local_fm_count, DType dt, const void* src,
+                          void* dst, bool unpack) {
+  const size_t es = dtype_size(dt);
+  for (size_t b = 0; b < nblocks; ++b) {
+    const BlockDesc& k = blocks[b];
+    const size_t row = k.fm_cnt * k.fm_size * es;   // one minibatch row of the block is contiguous on both sides
+    for (size_t mb = 0; mb < k.mb_cnt; ++mb) {
+      size_t local_off = ((mb + k.mb_off) * local_fm_count + k.fm_off) * k.fm_size * es;
+      size_t comm_off = (k.buf_off + mb * k.fm_cnt * k.fm_size) * es;
+      if (!unpack) memcpy((char*)dst + comm_off, (const char*)src + local_off, row);
+      else memcpy((char*)dst + local_off, (const char*)src + comm_off, row);
+    }
+  }
+}
+
+// ============================================================================================================
+// PointerChecker
+// ============================================================================================================
+void PointerChecker::add(const void* p, size_t len) {
+  std::lock_guard<std::mutex> g(mu_);
+  ranges_.insert({(uintptr_t)p, (uintptr_t)p + len});
+}
+void PointerChecker::remove(const void* p) {
+  std::lock_guard<std::mutex> g(mu_);
+  for (auto it = ranges_.begin(); it != ranges_.end(); ++it)
+    if (it->first == (uintptr_t)p) {
+      ranges_.erase(it);
+      return;
+    }
+}
+bool PointerChecker::check(const void* p, size_t len) const {
+  std::lock_guard<std::mutex> g(mu_);
+  uintptr_t a = (uintptr_t)p, b = a + len;
+  auto it = ranges_.upper_bound({a, UINTPTR_MAX});
+  if (it == ranges_.begin()) return false;
+  --it;
+  return a >= it->first && b <= it->second;
+}
+size_t PointerChecker::count() const {
+  std::lock_guard<std::mutex> g(mu_);
+  return ranges_.size();
+}
+
+// ============================================================================================================
+// RankContext: groups, request storage
+// ============================================================================================================
+// Collective over `parent`: ranks passing the same colour end up in the same new group, ordered by parent index
+// (MPI_Comm_split(parent, colour, key=rank) semantics, which is what the reference's CreateProcessGroup(colour)
+// does; reference src/comm_ep.cpp:1791-1830).  The exchange also agrees on (a) a signal row that is free on
+// every member and (b) a ticket base above anything a member has ever used, so flags on a recycled row can
+// never alias an older group's.
+ProcessGroup* RankContext::create_group_by_color(ProcessGroup* parent, int color) {
+  MLSLB_ASSERT(parent != nullptr, "null parent group");
+  struct Msg {
+    int32_t color;
+    int32_t pad;
+    uint64_t row_used;
+    uint64_t hwm;
+  } mine{color, 0, row_used, std::max(seq_hwm, parent->hwm())};
+  std::vector<Msg> all(parent->size());
+  if (parent->size() > 1) {
+    boot->group_allgather(parent->members, parent->row, ++parent->ctl_seq, &mine, all.data(), sizeof(Msg));
+  } else {
+    all[0] = mine;
+  }
+  ProcessGroup* g = new ProcessGroup();
+  g->ctx = this;
+  uint64_t used = 0, base = 0;
+  for (int i = 0; i < parent->size(); ++i)
+    if (all[i].color == color) {
+      if (parent->members[i] == rank) g->idx = (int)g->members.size();
+      g->members.push_back(parent->members[i]);
+      used |= all[i].row_used;
+      base = std::max(base, all[i].hwm);
+    }
+  MLSLB_ASSERT(!g->members.empty(), "rank not part of its own colour group");
+  g->is_self = g->members.size() == 1;
+  if (g->is_self) {
+    g->row = -1;
+  } else {
+    int row = -1;
+    for (int r = 1; r < kMaxGroupRows; ++r)
+      if (!(used & (1ull << r))) {
+        row = r;
+        break;
+      }
+    MLSLB_ASSERT(row > 0, "out of process-group rows (max %d live groups)", kMaxGroupRows);
+    g->row = row;
+    row_used |= 1ull << row;
+    g->seq[0] = g->seq[1] = g->ctl_seq = base;
+    seq_hwm = std::max(seq_hwm, base);
+  }
+  if (backend) backend->group_created(*g);
+  return g;
+}
+
+void RankContext::group_barrier(ProcessGroup* g) {
+  if (!g || g->size() <= 1) return;
+  boot->group_allgather(g->members, g->row, ++g->ctl_seq, nullptr, nullptr, 0);
+}
+
+void RankContext::free_group(ProcessGroup* g) {
+  if (!g || g == world_group || g == self_group) return;
+  if (g->size() > 1) {
+    // like MPI_Comm_free this is collective: nobody recycles the row while a peer still polls it
+    if (progress) progress->drain();
+    group_barrier(g);
+  }
+  if (backend) backend->group_destroyed(*g);
+  seq_hwm = std::max(seq_hwm, g->hwm());
+  if (g->row > 0) row_used &= ~(1ull << g->row);
+  delete g;
+}
+
+void RankContext::register_request(CommRequest* r) {
+  std::lock_guard<std::mutex> g(req_mu);
+  inflight.insert(r);
+}
+
+void RankContext::remove_request(CommRequest* r) {
+  {
+    std::lock_guard<std::mutex> g(req_mu);
+    inflight.erase(r);
+  }
+  if (r->one_shot) delete r;
+}
+
+void RankContext::check_pointer(const void* p, size_t len, const char* what) {
+  MLSLB_ASSERT(ptrcheck.check(p, len), "pointer check: %s [%p, +%zu) is not inside memory obtained from Environment::Alloc",
+               what, p, len);
+}
+
+// ============================================================================================================
+// Context lifecycle
+// ============================================================================================================
+struct InprocWorldReg {
+  std::vector<std::unique_ptr<Bootstrap>> boots;
+};
+static std::mutex g_reg_mu;
+static std::map<int, std::unique_ptr<InprocWorldReg>> g_worlds;
+static int g_next_world = 1;
+static RankContext g_process_ctx;
+static thread_local RankContext* tls_ctx = nullptr;
+static thread_local std::unique_ptr<Bootstrap> tls_boot;
+
+RankContext* process_context() { return &g_process_ctx; }
+RankContext* current_context() { return tls_ctx ? tls_ctx : &g_process_ctx; }
+bool thread_is_inproc_rank() { return tls_ctx != nullptr; }
+
+int inproc_world_create(int nranks) {
+  std::lock_guard<std::mutex> g(g_reg_mu);
+  int id = g_next_world++;
+  auto reg = std::unique_ptr<InprocWorldReg>(new InprocWorldReg());
+  reg->boots = Bootstrap::create_inproc(nranks);
+  g_worlds[id] = std::move(reg);
+  return id;
+}
+
+void inproc_world_destroy(int id) {
+  std::lock_guard<std::mutex> g(g_reg_mu);
+  g_worlds.erase(id);
+}
+
+void inproc_bind_thread(int id, int rank) {
+  std::lock_guard<std::mutex> g(g_reg_mu);
+  auto it = g_worlds.find(id);
+  MLSLB_ASSERT(it != g_worlds.end(), "unknown in-process world %d", id);
+  MLSLB_ASSERT(rank >= 0 && rank < (int)it->second->boots.size() && it->second->boots[rank],
+               "in-process rank %d unavailable", rank);
+  MLSLB_ASSERT(tls_ctx == nullptr, "thread already bound to a virtual rank");
+  tls_boot = std::move(it->second->boots[rank]);
+  tls_ctx = new RankContext();
+}
+
+void inproc_unbind_thread() {
+  if (!tls_ctx) return;
+  if (tls_ctx->initialized) context_finalize(tls_ctx);
+  delete tls_ctx;
+  tls_ctx = nullptr;
+  tls_boot.reset();
+}
+
+std::unique_ptr<Bootstrap> take_thread_bootstrap() { return std::move(tls_boot); }
+
+static std::string derive_job_key(const EnvConfig& e) {
+  if (!e.job_id.empty()) return e.job_id;
+  std::string k;
+  if (const char* v = getenv("TORCHELASTIC_RUN_ID")) k += v;
+  if (const char* v = getenv("MASTER_PORT")) k += std::string("p") + v;
+  if (k.empty()) k = "default";
+  for (auto& ch : k)
+    if (!isalnum((unsigned char)ch)) ch = '_';
+  return k;
+}
+
+static void poison_on_fail() {
+  RankContext* c = current_context();
+  if (c && c->boot) c->boot->poison(c->rank);
+}
+
+void context_init(RankContext* ctx) {
+  ctx->env = parse_env();
+  set_log_level(ctx->env.log_level);
+  ctx->init_pid = (int)getpid();
+  if (auto b = take_thread_bootstrap()) {
+    ctx->boot = std::move(b);
+  } else {
+    int world = ctx->env.world > 0 ? ctx->env.world : 1;
+    int rank = ctx->env.rank >= 0 ? ctx->env.rank : 0;
+    if (world == 1) {
+      auto v = Bootstrap::create_inproc(1);
+      ctx->boot = std::move(v[0]);
+    } else {
+      ctx->boot = Bootstrap::create_shm(derive_job_key(ctx->env), rank, world);
+    }
+  }
+  ctx->rank = ctx->boot->rank();
+  ctx->world = ctx->boot->size();
+  set_log_rank(ctx->rank);
+  set_fail_hook(poison_on_fail);
+
+  // base groups
+  ctx->world_group = new ProcessGroup();
+  ctx->world_group->ctx = ctx;
+  for (int r = 0; r < ctx->world; ++r) ctx->world_group->members.push_back(r);
+  ctx->world_group->idx = ctx->rank;
+  ctx->world_group->row = 0;
+  ctx->world_group->is_world = true;
+  ctx->world_group->is_self = ctx->world == 1;
+  ctx->row_used = 1;
+  ctx->self_group = new ProcessGroup();
+  ctx->self_group->ctx = ctx;
+  ctx->self_group->members.push_back(ctx->rank);
+  ctx->self_group->idx = 0;
+  ctx->self_group->row = -1;
+  ctx->self_group->is_self = true;
+  ctx->global_group = ctx->world_group;
+
+  // backend selection: CUDA when a GPU is usable, host shared memory otherwise (MLSL_BACKEND overrides)
+  std::string want = ctx->env.backend;
+  if (want == "auto") want = cuda_backend_available() ? "cuda" : "host";
+  if (want == "cuda") {
+    ctx->backend = make_cuda_backend(ctx);
+    MLSLB_ASSERT(ctx->backend != nullptr, "MLSL_BACKEND=cuda requested but no usable CUDA device / extension");
+  } else {
+    MLSLB_ASSERT(want == "host", "unknown MLSL_BACKEND '%s' (auto|host|cuda)", want.c_str());
+    ctx->backend = make_host_backend(ctx);
+  }
+  ctx->backend->group_created(*ctx->world_group);
+
+  // Servers: the reference switches its endpoint servers off on a single node unless MLSL_NUM_SERVERS is set
+  // (src/comm_ep.cpp:1585-1602).  Same rule for the device path (kernels are asynchronous anyway); the host
+  // path needs one server for true non-blocking progress.
+  int ns = ctx->env.num_servers;
+  if (ns < 0) ns = ctx->backend->is_device() ? 0 : (ctx->world > 1 ? 1 : 0);
+  ctx->progress.reset(new ProgressEngine(ctx, ns));
+  ctx->initialized = true;
+  ctx->boot->barrier();
+}
+
+void context_finalize(RankContext* ctx) {
+  if (!ctx->initialized) return;
+  ctx->progress->drain();
+  ctx->boot->barrier();
+  ctx->progress.reset();
+  if (ctx->global_group != ctx->world_group) {
+    ProcessGroup* g = ctx->global_group;
+    ctx->global_group = ctx->world_group;
+    ctx->free_group(g);
+  }
+  ctx->backend->group_destroyed(*ctx->world_group);
+  ctx->backend->finalize();
+  ctx->backend.reset();
+  delete ctx->world_group;
+  delete ctx->self_group;
+  ctx->world_group = ctx->self_group = ctx->global_group = nullptr;
+  ctx->boot->barrier();
+  ctx->boot.reset();
+  ctx->initialized = false;
+  ctx->row_used = 0;
+  ctx->quant = QuantConfig();
+}
+
+}  // namespace mlslb

@@ -1,0 +1,277 @@
+// Per-rank runtime: process groups, communication requests, backend interface, progress engine.
+//
+// This is the layer the reference calls "internal comm interface" (reference src/comm.hpp:48-424:
+// ProcessGroup, CommOp*, CommDesc, CommRequest, Comm* free functions) plus the endpoint-proxy runtime behind it
+// (reference eplib/cqueue.c, eplib/server.c).  B200 re-design:
+//   * a request is a POD descriptor + state word; the data plane is a Backend (host shared memory, or CUDA
+//     peer-memory kernels) instead of MPI calls;
+//   * the client<->ep_server shared-memory command ring becomes an in-process SPSC ring consumed by background
+//     progress thread(s) ("servers") that drive CUDA streams (or execute host reductions);
+//   * process groups are rank lists + a row in the symmetric signal pad - creating one allocates no transport.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "bootstrap.hpp"
+#include "common.hpp"
+#include "env.hpp"
+#include "heap.hpp"
+
+namespace mlslb {
+
+struct RankContext;
+class Backend;
+class CommRequest;
+
+// ----------------------------------------------------------------------------------------------------------
+struct ProcessGroup {
+  RankContext* ctx = nullptr;
+  std::vector<int> members;   // global ranks in group order
+  int idx = 0;                // this rank's index inside members
+  int row = -1;               // signal-pad row (-1: self group, never communicates)
+  uint64_t seq[2] = {0, 0};   // collectives issued per lane (0 normal, 1 priority); identical on every member
+  uint64_t ctl_seq = 0;       // control-plane (host mailbox) collectives issued on this group
+  bool is_world = false, is_self = false;
+  uint64_t hwm() const { return std::max(ctl_seq, std::max(seq[0], seq[1])); }
+  int size() const { return (int)members.size(); }
+};
+
+// What a request does (reference src/comm.hpp:250-366 "CommDesc" with exactly one op).
+struct CommDesc {
+  enum CompType { FPROP = 0, BPROP, PARAM_GRAD, PARAM_INC, GENERIC };
+  OpKind kind = OpKind::BARRIER;
+  DType dtype = DType::F32;
+  RedOp rop = RedOp::SUM;
+  ProcessGroup* group = nullptr;
+  size_t count = 0;   // elements: Bcast/Reduce/AllReduce total; AlltoAll/Gather/AllGather per-peer send count;
+                      // Scatter/ReduceScatter per-rank recv count
+  size_t root = 0;
+  std::vector<size_t> send_counts, send_offsets, recv_counts, recv_offsets;   // *v variants (elements)
+  CompType comp_type = GENERIC;
+  int64_t op_uid = -1;
+  // ---- B200 extensions (fused epilogues) ----
+  DType out_dtype = DType::F32;   // only honoured when has_out_dtype
+  bool has_out_dtype = false;
+  float scale = 1.0f;             // result multiplier fused into the reduction epilogue (e.g. 1/N averaging)
+  bool compress = false;          // block-scaled fp8 quantised transport with error feedback
+  // fused distributed update (OpKind::FUSED_UPDATE)
+  struct FusedUpdate {
+    int optimizer = 0;            // 0 = SGD(momentum), 1 = AdamW
+    float lr = 0.f, momentum = 0.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, weight_decay = 0.f;
+    int64_t step = 0;
+    void* param = nullptr;        // full parameter buffer (all-gathered in place, dtype = out_dtype)
+    void* master = nullptr;       // fp32 owned master shard (may be null: param is the master)
+    void* state1 = nullptr;       // momentum / exp_avg shard (fp32)
+    void* state2 = nullptr;       // exp_avg_sq shard (fp32)
+  } fused;
+};
+
+class CommRequest {
+ public:
+  enum State : int { IDLE = 0, QUEUED = 1, LAUNCHED = 2, DONE = 3 };
+  CommRequest(RankContext* ctx, DType dt, int64_t uid, CommDesc::CompType ct);
+  ~CommRequest();
+  CommDesc desc;
+  RankContext* ctx;
+  bool one_shot = false;           // freed by Environment::Wait/Test (Distribution collectives)
+  // Setup(): sizes derived from the op (reference src/comm_ep.cpp:568-766)
+  void setup();
+  size_t buf_bytes() const { return buf_bytes_; }      // bytes a comm buffer must have for Start(buf, buf+send_bytes)
+  size_t send_bytes() const { return send_bytes_; }    // bytes of the send region (== tmpBufOffset for activations)
+  size_t recv_bytes() const { return recv_bytes_; }
+  size_t msg_bytes() const { return msg_bytes_; }      // payload size used for statistics / priority
+  bool out_of_place_default() const { return oop_default_; }
+
+  void start(void* send, void* recv);
+  void* wait();                     // returns recv pointer
+  void* test(bool* done);           // returns recv pointer when done else nullptr
+  bool active() const { return state.load(std::memory_order_acquire) != IDLE; }
+
+  // runtime state
+  std::atomic<int> state{IDLE};
+  void* send = nullptr;
+  void* recv = nullptr;
+  uint64_t group_seq = 0;           // ticket in the (group, lane) collective order
+  int lane = 0;                     // 0 = normal, 1 = priority lane (own signal row + high-priority stream)
+  uint64_t start_ns = 0, done_ns = 0;
+  void* backend_state = nullptr;    // owned by the backend (events, staging buffers)
+  bool setup_done = false;
+
+ private:
+  size_t buf_bytes_ = 0, send_bytes_ = 0, recv_bytes_ = 0, msg_bytes_ = 0;
+  bool oop_default_ = false;
+};
+
+struct BlockDesc {
+  size_t mb_off, mb_cnt, fm_off, fm_cnt, fm_size, buf_off;
+};
+
+// ----------------------------------------------------------------------------------------------------------
+class Backend {
+ public:
+  virtual ~Backend() {}
+  virtual const char* name() const = 0;
+  virtual bool is_device() const { return false; }
+  virtual void* alloc(size_t bytes, size_t align) = 0;
+  virtual void free(void* p) = 0;
+  virtual bool owns(const void* p, size_t len) const = 0;       // inside this rank's symmetric heap?
+  virtual void group_created(ProcessGroup&) {}
+  virtual void group_destroyed(ProcessGroup&) {}
+  virtual void prepare(CommRequest&) {}
+  virtual void release(CommRequest&) {}
+  // Issue the collective.  Device backends return once the work is enqueued on a stream; the host backend
+  // returns when the collective has completed.  Must move r.state to LAUNCHED (or DONE).
+  virtual void launch(CommRequest& r) = 0;
+  virtual bool test(CommRequest& r) = 0;
+  virtual void wait(CommRequest& r) = 0;
+  virtual void set_user_stream(void*) {}
+  virtual void* user_stream() { return nullptr; }
+  virtual void set_wait_mode(bool /*stream_ordered*/) {}
+  // Strided (mb, fm, fmSize) gather/scatter between a local activation tensor and the comm buffer
+  // (reference: the user-side triple loop of tests/examples/mlsl_test/mlsl_test.cpp:214-254).
+  virtual void pack_blocks(const BlockDesc* blocks, size_t nblocks, size_t local_fm_count, DType dt,
+                           const void* src, void* dst, bool unpack);
+  virtual void finalize() {}
+  virtual std::string describe() const { return name(); }
+};
+
+std::unique_ptr<Backend> make_host_backend(RankContext* ctx);
+std::unique_ptr<Backend> make_cuda_backend(RankContext* ctx);   // null when no usable GPU
+bool cuda_backend_available();
+
+// ----------------------------------------------------------------------------------------------------------
+// Bounded single-producer / single-consumer ring (the descendant of reference eplib/cqueue.h:95-183: client
+// fills table[tail], server drains table[head]; ours has back-pressure and C++11 acquire/release instead of
+// volatile + x86-TSO).
+template <typename T, size_t N>
+class SpscRing {
+ public:
+  bool push(const T& v) {
+    size_t t = tail_.load(std::memory_order_relaxed);
+    if (t - head_.load(std::memory_order_acquire) >= N) return false;
+    slots_[t % N] = v;
+    tail_.store(t + 1, std::memory_order_release);
+    return true;
+  }
+  bool pop(T& v) {
+    size_t h = head_.load(std::memory_order_relaxed);
+    if (h == tail_.load(std::memory_order_acquire)) return false;
+    v = slots_[h % N];
+    head_.store(h + 1, std::memory_order_release);
+    return true;
+  }
+  size_t size() const { return tail_.load(std::memory_order_acquire) - head_.load(std::memory_order_acquire); }
+
+ private:
+  alignas(64) std::atomic<size_t> head_{0};
+  alignas(64) std::atomic<size_t> tail_{0};
+  alignas(64) T slots_[N];
+};
+
+struct Command {
+  enum Kind : int { EXEC = 0, SUSPEND, RESUME, STOP };
+  int kind = EXEC;
+  CommRequest* req = nullptr;
+};
+
+// Background "endpoint server" threads.  One ring per server; requests of one process group always go to the
+// same server so the per-group launch order is the program order on every rank.
+class ProgressEngine {
+ public:
+  ProgressEngine(RankContext* ctx, int num_servers);
+  ~ProgressEngine();
+  int servers() const { return (int)servers_.size(); }
+  void submit(CommRequest* r);        // inline launch when there are no servers
+  void drain();                       // block until every submitted command has been launched
+  void suspend();                     // park the servers (reference EPLIB_suspend/EPLIB_execute)
+  void resume();
+  uint64_t launched() const { return launched_.load(); }
+
+ private:
+  struct Server {
+    SpscRing<Command, 1024> ring;
+    std::thread th;
+    std::atomic<uint64_t> submitted{0}, completed{0};
+    std::atomic<bool> parked{false};
+    std::mutex mu;                    // producers are API threads: serialise pushes (SPSC per ring)
+  };
+  void run(Server* s, int idx);
+  RankContext* ctx_;
+  std::vector<std::unique_ptr<Server>> servers_;
+  std::atomic<uint64_t> launched_{0};
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// Registry of CommAlloc'ed ranges (reference src/pointer_checker.cpp:29-105, opt-in there at build time,
+// MLSL_POINTER_CHECK=1 here): every buffer handed to a collective must lie inside one registered range.
+class PointerChecker {
+ public:
+  void add(const void* p, size_t len);
+  void remove(const void* p);
+  // returns true when [p, p+len) is inside a registered range
+  bool check(const void* p, size_t len) const;
+  size_t count() const;
+
+ private:
+  mutable std::mutex mu_;
+  std::set<std::pair<uintptr_t, uintptr_t>> ranges_;
+};
+
+struct QuantConfig {               // deep copy of the public QuantParams (reference include/mlsl.hpp:150-158)
+  bool set = false;
+  std::string lib_path, quant_name, dequant_name, reduce_name;
+  size_t block_size = 0, elem_in_block = 0;
+};
+
+struct RankContext {
+  EnvConfig env;
+  std::unique_ptr<Bootstrap> boot;
+  int rank = 0, world = 1;
+  std::unique_ptr<Backend> backend;
+  std::unique_ptr<ProgressEngine> progress;
+  ProcessGroup* world_group = nullptr;     // all ranks of the job
+  ProcessGroup* global_group = nullptr;    // the "global" group (world, or the Configure("color=") subset)
+  ProcessGroup* self_group = nullptr;
+  uint64_t row_used = 0;                   // bitmap of signal rows in use
+  uint64_t seq_hwm = 0;                    // highest ticket this rank has used on any row (see create_group_by_color)
+  int session_ops_hint = 0;                // operations in the committed session (priority-lane rule)
+  std::mutex req_mu;
+  std::set<CommRequest*> inflight;         // RequestStorage (reference src/mlsl_impl.hpp:60-94)
+  PointerChecker ptrcheck;
+  QuantConfig quant;
+  std::atomic<int64_t> next_op_uid{0};
+  int init_pid = 0;
+  bool initialized = false;
+  void* api_env = nullptr;                 // MLSL::impl::EnvironmentImpl bound to this context
+
+  ProcessGroup* create_group_by_color(ProcessGroup* parent, int color);   // collective over parent
+  void free_group(ProcessGroup* g);
+  void group_barrier(ProcessGroup* g);      // host control-plane barrier among the members
+  void register_request(CommRequest* r);
+  void remove_request(CommRequest* r);      // also frees one-shot requests
+  void check_pointer(const void* p, size_t len, const char* what);
+};
+
+// Context lifecycle.  `bind_inproc_rank` makes the calling thread a virtual rank of an in-process world.
+RankContext* current_context();             // thread-bound context if any, else the process-wide one
+RankContext* process_context();
+int inproc_world_create(int nranks);        // returns world id
+void inproc_world_destroy(int world_id);
+void inproc_bind_thread(int world_id, int rank);
+void inproc_unbind_thread();
+bool thread_is_inproc_rank();
+std::unique_ptr<Bootstrap> take_thread_bootstrap();   // bootstrap reserved for the calling thread (or null)
+
+void context_init(RankContext* ctx);        // bootstrap + backend + progress engine + base groups
+void context_finalize(RankContext* ctx);
+
+}  // namespace mlslb
