@@ -158,6 +158,7 @@ void CommRequest::start(void* s, void* r) {
     group_seq = ++g->seq[lane];
   }
   state.store(QUEUED, std::memory_order_release);
+  ctx->backend->on_start(*this);
   ctx->progress->submit(this);
 }
 

@@ -131,6 +131,7 @@ class Backend {
   // Issue the collective.  Device backends return once the work is enqueued on a stream; the host backend
   // returns when the collective has completed.  Must move r.state to LAUNCHED (or DONE).
   virtual void launch(CommRequest& r) = 0;
+  virtual void on_start(CommRequest&) {}      // called on the API thread inside Start(), before the hand-off
   virtual bool test(CommRequest& r) = 0;
   virtual void wait(CommRequest& r) = 0;
   virtual void set_user_stream(void*) {}

@@ -1,0 +1,643 @@
+// CUDA backend: symmetric device heap + peer mappings + stream/event plumbing around the collective kernels.
+//
+// What the reference builds out of POSIX shared memory, dlmalloc and ep_server processes (reference eplib/memory.c,
+// eplib/client.c, eplib/server.c, src/comm_ep.cpp:363-566) becomes, on an NVSwitch node:
+//   * one device slab per rank, mapped by every peer (CUDA IPC between processes, plain pointers between in-process
+//     ranks) - Environment::Alloc sub-allocates from it, so user buffers are directly addressable by peer kernels;
+//   * buffers that are NOT in the slab (arbitrary cudaMalloc / host memory) are staged through slab scratch on the
+//     same stream - the GPU analogue of the reference's ReplaceIn / ReplaceOut shadow-buffer copies;
+//   * every (group, lane) has its own CUDA stream (lane 1 = high priority): Start() makes it wait for the user's
+//     stream, Wait() either blocks the host on the completion event or just orders the user's stream after it.
+#include <cuda_runtime.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "core/log.hpp"
+#include "core/quant.hpp"
+#include "core/runtime.hpp"
+#include "core/sysinfo.hpp"
+#include "cuda/kernels.hpp"
+
+namespace mlslb {
+
+namespace {
+
+constexpr size_t kPadRowBytes = (size_t)kMaxChannels * kMaxDevRanks * sizeof(PadSlot);   // per (row, lane)
+constexpr size_t kSeqRowBytes = (size_t)kMaxChannels * sizeof(unsigned long long);
+constexpr int kPadRows = kMaxGroupRows * 2;
+constexpr size_t kPadBytes = kPadRows * kPadRowBytes;
+constexpr size_t kSeqBase = kPadBytes;
+constexpr size_t kHeaderBytes = (kPadBytes + kPadRows * kSeqRowBytes + ((size_t)1 << 20) - 1) >> 20 << 20;
+
+struct StageBuf {
+  void* user;
+  void* slab;
+  size_t bytes;
+  bool copy_out;
+};
+
+struct CudaReqState {
+  cudaEvent_t ready = nullptr, done = nullptr;
+  std::vector<StageBuf> stages;
+  float* residual = nullptr;      // error-feedback residual (quantised all-reduce)
+  void* qstage = nullptr;         // fp8 staging area inside the slab
+  size_t residual_elems = 0;
+  cudaStream_t stream = nullptr;
+  bool inflight = false;
+  bool recorded = false;          // `done` was recorded for the current launch
+};
+
+struct PeerInfo {
+  cudaIpcMemHandle_t handle;
+  unsigned long long ptr;
+  int pid;
+  int device;
+  int pad;
+};
+
+class CudaBackend final : public Backend {
+ public:
+  explicit CudaBackend(RankContext* ctx) : ctx_(ctx) { init(); }
+  ~CudaBackend() override {}
+
+  const char* name() const override { return "cuda"; }
+  bool is_device() const override { return true; }
+
+  void* alloc(size_t bytes, size_t align) override {
+    size_t off = heap_.alloc(bytes, std::max<size_t>(align, 256));
+    MLSLB_ASSERT(off != SIZE_MAX,
+                 "symmetric device heap exhausted (%zu bytes requested, %zu of %zu in use): raise MLSL_HEAP_SIZE_GB",
+                 bytes, heap_.bytes_in_use(), heap_.capacity());
+    void* p = slab_ + off;
+    ctx_->ptrcheck.add(p, bytes);
+    return p;
+  }
+  void free(void* p) override {
+    if (!p) return;
+    ctx_->ptrcheck.remove(p);
+    MLSLB_ASSERT(heap_.free((size_t)((char*)p - slab_)), "Free of a pointer that did not come from Alloc");
+  }
+  bool owns(const void* p, size_t len) const override {
+    const char* c = (const char*)p;
+    return c >= slab_ + kHeaderBytes && c + len <= slab_ + slab_bytes_;
+  }
+
+  void group_created(ProcessGroup& g) override {
+    if (g.size() <= 1 || g.row < 0) return;
+    MLSLB_ASSERT(g.size() <= kMaxDevRanks, "device groups are limited to %d ranks (got %d)", kMaxDevRanks, g.size());
+    set_device();
+    // fresh row: zero my pads and ticket counters, then make sure every member has done so before anyone signals
+    MLSLB_CUDA(cudaMemsetAsync(slab_ + (size_t)g.row * 2 * kPadRowBytes, 0, 2 * kPadRowBytes, aux_stream_));
+    MLSLB_CUDA(cudaMemsetAsync(slab_ + kSeqBase + (size_t)g.row * 2 * kSeqRowBytes, 0, 2 * kSeqRowBytes, aux_stream_));
+    MLSLB_CUDA(cudaStreamSynchronize(aux_stream_));
+    if (!g.is_world) ctx_->group_barrier(&g);
+  }
+
+  void prepare(CommRequest& r) override {
+    if (r.backend_state) return;
+    r.backend_state = new CudaReqState();   // events are created on first use (none at all in inline-stream mode)
+  }
+  void ensure_events(CudaReqState* st) {
+    if (st->done) return;
+    MLSLB_CUDA(cudaEventCreateWithFlags(&st->ready, cudaEventDisableTiming));
+    MLSLB_CUDA(cudaEventCreateWithFlags(&st->done, cudaEventDisableTiming));
+  }
+  // inline-stream + stream-ordered wait: the collective is just a kernel on the user's stream, nothing to track
+  bool eventless() const { return inline_stream_ && stream_wait_; }
+  void release(CommRequest& r) override {
+    auto* st = (CudaReqState*)r.backend_state;
+    if (!st) return;
+    set_device();
+    if (st->inflight && st->recorded) cudaEventSynchronize(st->done);
+    else if (st->inflight && st->stream) cudaStreamSynchronize(st->stream);
+    // scratch that a stream-ordered (not host-waited) kernel may still be using must not be recycled early
+    if ((st->residual || st->qstage || !st->stages.empty()) && st->stream) cudaStreamSynchronize(st->stream);
+    drop_stages(st, false);
+    if (st->residual) free(st->residual);
+    if (st->qstage) free(st->qstage);
+    if (st->ready) cudaEventDestroy(st->ready);
+    if (st->done) cudaEventDestroy(st->done);
+    delete st;
+    r.backend_state = nullptr;
+  }
+
+  void on_start(CommRequest& r) override {
+    // runs on the API thread: pin the point of the user's stream the collective has to wait for
+    if (inline_stream_) return;
+    auto* st = (CudaReqState*)r.backend_state;
+    set_device();
+    ensure_events(st);
+    MLSLB_CUDA(cudaEventRecord(st->ready, user_stream_));
+  }
+
+  void launch(CommRequest& r) override;
+  bool test(CommRequest& r) override {
+    auto* st = (CudaReqState*)r.backend_state;
+    set_device();
+    cudaError_t e = st->recorded ? cudaEventQuery(st->done) : cudaStreamQuery(st->stream);
+    if (e == cudaErrorNotReady) return false;
+    MLSLB_CUDA(e);
+    finish(r, st);
+    return true;
+  }
+  void wait(CommRequest& r) override {
+    auto* st = (CudaReqState*)r.backend_state;
+    set_device();
+    if (stream_wait_ && st->stages.empty()) {
+      // stream-ordered completion: nothing blocks the host
+      if (!inline_stream_) MLSLB_CUDA(cudaStreamWaitEvent(user_stream_, st->done, 0));
+      st->inflight = false;
+      return;
+    }
+    if (st->recorded) MLSLB_CUDA(cudaEventSynchronize(st->done));
+    else MLSLB_CUDA(cudaStreamSynchronize(st->stream));
+    finish(r, st);
+  }
+
+  void set_user_stream(void* s) override { user_stream_ = (cudaStream_t)s; }
+  void* user_stream() override { return (void*)user_stream_; }
+  void set_wait_mode(bool stream_ordered) override { stream_wait_ = stream_ordered; }
+
+  void pack_blocks(const BlockDesc* blocks, size_t nblocks, size_t local_fm_count, DType dt, const void* src,
+                   void* dst, bool unpack) override {
+    set_device();
+    size_t mx = 0;
+    for (size_t i = 0; i < nblocks; ++i) mx = std::max(mx, blocks[i].mb_cnt * blocks[i].fm_cnt * blocks[i].fm_size);
+    for (size_t i = 0; i < nblocks; i += kMaxDevRanks) {
+      PackPlan plan;
+      plan.n = (int)std::min<size_t>(kMaxDevRanks, nblocks - i);
+      for (int k = 0; k < plan.n; ++k) plan.b[k] = blocks[i + k];
+      MLSLB_CUDA(launch_pack_blocks(plan, local_fm_count, (int)dtype_size(dt), src, dst, unpack, mx, user_stream_));
+    }
+  }
+
+  void finalize() override {
+    set_device();
+    cudaDeviceSynchronize();
+    ctx_->boot->barrier();
+    for (size_t p = 0; p < peer_slab_.size(); ++p)
+      if (peer_opened_[p]) cudaIpcCloseMemHandle(peer_slab_[p]);
+    ctx_->boot->barrier();
+    for (auto& s : streams_)
+      if (s) cudaStreamDestroy(s);
+    if (aux_stream_) cudaStreamDestroy(aux_stream_);
+    if (own_user_stream_) cudaStreamDestroy(own_user_stream_);
+    if (slab_) cudaFree(slab_);
+    if (err_host_) cudaFreeHost((void*)err_host_);
+    slab_ = nullptr;
+  }
+
+  std::string describe() const override {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuda peer-memory backend (device %d, %d SMs, slab %.1f GiB, %s, ranks/device %d)", device_,
+             sm_count_, slab_bytes_ / 1073741824.0, inproc_ ? "in-process ranks" : "CUDA IPC", ranks_per_device_);
+    return buf;
+  }
+
+ private:
+  RankContext* ctx_;
+  int device_ = 0, sm_count_ = 148, ranks_per_device_ = 1;
+  bool inproc_ = false;
+  char* slab_ = nullptr;
+  size_t slab_bytes_ = 0;
+  SlabAllocator heap_;
+  std::vector<char*> peer_slab_;
+  std::vector<bool> peer_opened_;
+  std::vector<cudaStream_t> streams_;
+  cudaStream_t aux_stream_ = nullptr, user_stream_ = nullptr, own_user_stream_ = nullptr;
+  bool stream_wait_ = false, inline_stream_ = false;
+  volatile int* err_host_ = nullptr;
+  int* err_dev_ = nullptr;
+  std::mutex mu_;
+
+  void set_device() { cudaSetDevice(device_); }
+  void init();
+  cudaStream_t stream_for(int row, int lane);
+  int pick_channels(size_t bytes) const;
+  DevComm make_comm(const ProcessGroup& g, int lane) const;
+  void drop_stages(CudaReqState* st, bool copied);
+  void finish(CommRequest& r, CudaReqState* st);
+  void check_error(const char* what);
+  void launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s);
+};
+
+void CudaBackend::init() {
+  Bootstrap* b = ctx_->boot.get();
+  inproc_ = b->inproc();
+  int ndev = 0;
+  MLSLB_CUDA(cudaGetDeviceCount(&ndev));
+  MLSLB_ASSERT(ndev > 0, "no CUDA device");
+  int lr = ctx_->env.local_rank >= 0 && !inproc_ ? ctx_->env.local_rank : b->rank();
+  if (const char* d = getenv("MLSL_DEVICE")) device_ = atoi(d);
+  else device_ = lr % ndev;
+  set_device();
+  cudaDeviceProp prop;
+  MLSLB_CUDA(cudaGetDeviceProperties(&prop, device_));
+  sm_count_ = prop.multiProcessorCount;
+  slab_bytes_ = (size_t)(ctx_->env.heap_size_gb * 1024.0 * 1024.0 * 1024.0);
+  if (slab_bytes_ < kHeaderBytes + ((size_t)64 << 20)) slab_bytes_ = kHeaderBytes + ((size_t)64 << 20);
+  if (ctx_->env.check_mem_size) {
+    size_t fr = 0, tot = 0;
+    MLSLB_CUDA(cudaMemGetInfo(&fr, &tot));
+    MLSLB_ASSERT(slab_bytes_ < fr, "MLSL_HEAP_SIZE_GB=%.2f does not fit in free device memory (%.2f GiB)",
+                 ctx_->env.heap_size_gb, fr / 1073741824.0);
+  }
+  cudaError_t e = cudaMalloc((void**)&slab_, slab_bytes_);
+  MLSLB_ASSERT(e == cudaSuccess, "cudaMalloc of the %.2f GiB symmetric heap failed: %s (lower MLSL_HEAP_SIZE_GB)",
+               slab_bytes_ / 1073741824.0, cudaGetErrorString(e));
+  MLSLB_CUDA(cudaMemset(slab_, 0, kHeaderBytes));
+  MLSLB_CUDA(cudaDeviceSynchronize());
+  heap_.reset(kHeaderBytes, slab_bytes_ - kHeaderBytes);
+  int lo = 0, hi = 0;
+  MLSLB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  MLSLB_CUDA(cudaStreamCreateWithPriority(&aux_stream_, cudaStreamNonBlocking, hi));
+  MLSLB_CUDA(cudaStreamCreateWithFlags(&own_user_stream_, cudaStreamNonBlocking));
+  user_stream_ = own_user_stream_;
+  streams_.assign(kPadRows, nullptr);
+  MLSLB_CUDA(cudaHostAlloc((void**)&err_host_, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+  *err_host_ = 0;
+  MLSLB_CUDA(cudaHostGetDevicePointer((void**)&err_dev_, (void*)err_host_, 0));
+  if (const char* m = getenv("MLSL_STREAM_MODE")) inline_stream_ = !strcmp(m, "inline");
+
+  // exchange slab addresses / IPC handles
+  const int W = b->size();
+  PeerInfo mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.ptr = (unsigned long long)slab_;
+  mine.pid = (int)getpid();
+  mine.device = device_;
+  if (!inproc_) MLSLB_CUDA(cudaIpcGetMemHandle(&mine.handle, slab_));
+  std::vector<PeerInfo> all(W);
+  b->allgather(&mine, all.data(), sizeof(PeerInfo));
+  peer_slab_.assign(W, nullptr);
+  peer_opened_.assign(W, false);
+  for (int p = 0; p < W; ++p) {
+    if (p == b->rank()) {
+      peer_slab_[p] = slab_;
+    } else if (all[p].pid == mine.pid) {
+      peer_slab_[p] = (char*)all[p].ptr;
+      if (all[p].device != device_) {
+        int can = 0;
+        MLSLB_CUDA(cudaDeviceCanAccessPeer(&can, device_, all[p].device));
+        MLSLB_ASSERT(can, "device %d cannot access peer device %d", device_, all[p].device);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(all[p].device, 0);
+        if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else MLSLB_CUDA(pe);
+      }
+    } else {
+      void* ptr = nullptr;
+      cudaError_t oe = cudaIpcOpenMemHandle(&ptr, all[p].handle, cudaIpcMemLazyEnablePeerAccess);
+      MLSLB_ASSERT(oe == cudaSuccess, "cudaIpcOpenMemHandle for rank %d failed: %s (are the GPUs peer-capable?)", p,
+                   cudaGetErrorString(oe));
+      peer_slab_[p] = (char*)ptr;
+      peer_opened_[p] = true;
+    }
+  }
+  // ranks sharing one physical device must all be co-resident while they spin on each other: bound the grid
+  ranks_per_device_ = 1;
+  {
+    std::map<int, int> per_dev;
+    for (int p = 0; p < W; ++p) per_dev[all[p].device]++;
+    // CUDA_VISIBLE_DEVICES may remap ordinals per process; only same-process ranks are known to share
+    if (inproc_) for (auto& kv : per_dev) ranks_per_device_ = std::max(ranks_per_device_, kv.second);
+  }
+  if (const char* v = getenv("MLSL_RANKS_PER_DEVICE")) ranks_per_device_ = std::max(1, atoi(v));
+  b->barrier();
+  MLSLB_LOG(LOG_DEBUG, "cuda backend up: device %d slab %p (%zu bytes) ranks/device %d", device_, (void*)slab_,
+            slab_bytes_, ranks_per_device_);
+}
+
+cudaStream_t CudaBackend::stream_for(int row, int lane) {
+  std::lock_guard<std::mutex> g(mu_);
+  cudaStream_t& s = streams_[row * 2 + lane];
+  if (!s) {
+    int lo = 0, hi = 0;
+    MLSLB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    // communication outranks compute so a spinning collective is never starved of SMs by queued compute kernels
+    MLSLB_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, lane ? hi : std::min(lo, hi + 1)));
+  }
+  return s;
+}
+
+// Channel ("endpoint") count as a pure function of the message size: every member must pick the same grid.
+int CudaBackend::pick_channels(size_t bytes) const {
+  int c;
+  if (bytes <= ((size_t)64 << 10)) c = 1;
+  else if (bytes <= ((size_t)256 << 10)) c = 2;
+  else if (bytes <= ((size_t)1 << 20)) c = 4;
+  else if (bytes <= ((size_t)4 << 20)) c = 8;
+  else if (bytes <= ((size_t)16 << 20)) c = 16;
+  else c = 32;
+  if (ctx_->env.num_channels > 0) c = std::min(ctx_->env.num_channels, c * 4);
+  if (ctx_->env.max_short_msg && bytes <= ctx_->env.max_short_msg * 4) c = 1;
+  int cap = std::max(1, (sm_count_ * 2) / std::max(1, ranks_per_device_) / 2);
+  c = std::min(c, std::min(cap, kMaxChannels));
+  return std::max(c, 1);
+}
+
+DevComm CudaBackend::make_comm(const ProcessGroup& g, int lane) const {
+  DevComm dc;
+  memset(&dc, 0, sizeof(dc));
+  dc.nranks = g.size();
+  dc.me = g.idx;
+  dc.pad_off = (unsigned)(((size_t)g.row * 2 + lane) * kPadRowBytes);
+  dc.seq_off = (unsigned)(kSeqBase + ((size_t)g.row * 2 + lane) * kSeqRowBytes);
+  dc.timeout_ns = ctx_->env.watchdog_sec > 0 ? (unsigned long long)ctx_->env.watchdog_sec * 1000000000ull : 0ull;
+  dc.err = err_dev_;
+  for (int i = 0; i < g.size(); ++i) dc.slab[i] = peer_slab_[g.members[i]];
+  dc.mc = nullptr;
+  return dc;
+}
+
+void CudaBackend::check_error(const char* what) {
+  int code = *err_host_;
+  if (code != 0) {
+    ctx_->boot->poison(ctx_->rank);
+    MLSLB_ASSERT(false, "device watchdog: %s: a peer never arrived (error code %d, reported by group index %d)", what,
+                 code, code - 1000);
+  }
+  if (ctx_->boot->poisoned()) MLSLB_ASSERT(false, "job poisoned by rank %d", (int)ctx_->boot->poisoned() - 1);
+}
+
+void CudaBackend::drop_stages(CudaReqState* st, bool) {
+  for (auto& s : st->stages) free(s.slab);
+  st->stages.clear();
+}
+
+void CudaBackend::finish(CommRequest& r, CudaReqState* st) {
+  st->inflight = false;
+  drop_stages(st, true);
+  check_error(opkind_name(r.desc.kind));
+}
+
+void CudaBackend::launch(CommRequest& r) {
+  set_device();
+  auto* st = (CudaReqState*)r.backend_state;
+  MLSLB_ASSERT(st != nullptr, "request was not prepared");
+  const CommDesc& d = r.desc;
+  ProcessGroup* g = d.group;
+  const bool solo = !g || g->size() <= 1;
+  cudaStream_t s = inline_stream_ ? user_stream_ : stream_for(solo ? 0 : g->row, r.lane);
+  st->stream = s;
+  if (!inline_stream_) MLSLB_CUDA(cudaStreamWaitEvent(s, st->ready, 0));
+  launch_single(r, st, s);
+  st->recorded = false;
+  if (!(eventless() && st->stages.empty())) {
+    ensure_events(st);
+    MLSLB_CUDA(cudaEventRecord(st->done, s));
+    st->recorded = true;
+  }
+  st->inflight = true;
+  r.state.store(CommRequest::LAUNCHED, std::memory_order_release);
+}
+
+void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s) {
+  const CommDesc& d = r.desc;
+  ProcessGroup* g = d.group;
+  const size_t es = dtype_size(d.dtype);
+  const size_t n = d.count;
+  // ---- single-rank groups: local semantics, no peers -------------------------------------------------------
+  if (!g || g->size() <= 1) {
+    size_t bytes = 0;
+    switch (d.kind) {
+      case OpKind::ALLREDUCE: case OpKind::REDUCE: case OpKind::REDUCE_SCATTER: case OpKind::ALLGATHER:
+      case OpKind::GATHER: case OpKind::SCATTER: case OpKind::ALLTOALL: case OpKind::ALLGATHERV:
+        bytes = n * es;
+        break;
+      default: break;
+    }
+    const bool reducing = d.kind == OpKind::ALLREDUCE || d.kind == OpKind::REDUCE_SCATTER || d.kind == OpKind::REDUCE;
+    if (reducing && bytes && r.recv && r.recv != r.send && owns(r.recv, bytes) && owns(r.send, bytes)) {
+      // one kernel: copy with the scale epilogue fused
+      MLSLB_CUDA(launch_scale_copy(d.dtype, r.recv, r.send, n, d.scale, s));
+      return;
+    }
+    if (bytes && r.recv && r.recv != r.send) MLSLB_CUDA(cudaMemcpyAsync(r.recv, r.send, bytes, cudaMemcpyDefault, s));
+    if ((d.kind == OpKind::ALLTOALLV || d.kind == OpKind::SENDRECV_LIST) && !d.send_counts.empty() && d.send_counts[0])
+      MLSLB_CUDA(cudaMemcpyAsync((char*)r.recv + d.recv_offsets[0] * es, (char*)r.send + d.send_offsets[0] * es,
+                                 d.send_counts[0] * es, cudaMemcpyDefault, s));
+    if (d.scale != 1.0f && r.recv && (d.kind == OpKind::ALLREDUCE || d.kind == OpKind::REDUCE_SCATTER))
+      MLSLB_CUDA(launch_scale(d.dtype, r.recv, n, d.scale, s));
+    return;
+  }
+  const int P = g->size(), me = g->idx;
+  DevComm dc = make_comm(*g, r.lane);
+
+  // ---- stage foreign buffers through the slab ------------------------------------------------------------------
+  size_t sbytes = r.send_bytes(), rbytes = r.recv_bytes();
+  if ((d.kind == OpKind::REDUCE || d.kind == OpKind::GATHER) && me != (int)d.root) rbytes = 0;
+  if (d.kind == OpKind::SCATTER && me != (int)d.root) sbytes = 0;
+  if (d.kind == OpKind::FUSED_UPDATE) rbytes = n * P * dtype_size(d.has_out_dtype ? d.out_dtype : d.dtype);
+  auto stage = [&](void* user, size_t bytes, bool copy_in, bool copy_out) -> char* {
+    if (!user || bytes == 0 || owns(user, bytes)) return (char*)user;
+    StageBuf sb{user, alloc(bytes, 256), bytes, copy_out};
+    if (copy_in) MLSLB_CUDA(cudaMemcpyAsync(sb.slab, user, bytes, cudaMemcpyDefault, s));
+    st->stages.push_back(sb);
+    return (char*)sb.slab;
+  };
+  char* R = nullptr;
+  char* S = nullptr;
+  const bool in_place = r.send == r.recv;
+  const bool recv_needs_input = in_place || d.kind == OpKind::BCAST || d.kind == OpKind::ALLGATHER ||
+                                d.kind == OpKind::ALLGATHERV || d.kind == OpKind::FUSED_UPDATE;
+  if (r.recv && rbytes) R = stage(r.recv, rbytes, recv_needs_input, true);
+  if (r.send && sbytes) {
+    char* us = (char*)r.send;
+    char* ur = (char*)r.recv;
+    if (ur && rbytes && us >= ur && us + sbytes <= ur + rbytes) S = R + (us - ur);
+    else S = stage(r.send, sbytes, true, false);
+  }
+  // ops whose device kernel cannot run in place get a private receive area
+  bool alias_fix = false;
+  if ((d.kind == OpKind::ALLTOALL || d.kind == OpKind::ALLTOALLV || d.kind == OpKind::SENDRECV_LIST) && S && R == S)
+    alias_fix = true;
+  if (d.kind == OpKind::REDUCE_SCATTER && S && R >= S && R < S + sbytes) alias_fix = true;
+  char* Rfinal = R;
+  if (alias_fix) {
+    StageBuf sb{R, alloc(rbytes, 256), rbytes, false};
+    st->stages.push_back(sb);
+    R = (char*)sb.slab;
+  }
+  const unsigned long long so = S ? (unsigned long long)(S - slab_) : 0ull;
+  const unsigned long long ro = R ? (unsigned long long)(R - slab_) : 0ull;
+  const int ch = pick_channels(r.msg_bytes());
+
+  switch (d.kind) {
+    case OpKind::BARRIER: MLSLB_CUDA(launch_barrier(dc, s)); break;
+    case OpKind::ALLREDUCE: {
+      const bool can_quant = d.compress && d.dtype == DType::F32 && d.rop == RedOp::SUM && ((so | ro) & 15ull) == 0;
+      if (can_quant) {
+        size_t sb = allreduce_quant_stage_bytes(n);
+        if (!st->qstage) st->qstage = alloc(sb, 256);
+        if (st->residual_elems != n) {
+          // from the slab, not cudaMalloc/cudaFree: those may synchronise the device while a peer rank of this
+          // process is spinning inside a collective that needs THIS launch to make progress
+          if (st->residual) free(st->residual);
+          st->residual = (float*)alloc(std::max<size_t>(n, 1) * sizeof(float), 256);
+          MLSLB_CUDA(cudaMemsetAsync(st->residual, 0, n * sizeof(float), s));
+          st->residual_elems = n;
+        }
+        MLSLB_CUDA(launch_allreduce_quant(dc, so, ro, (unsigned long long)((char*)st->qstage - slab_), st->residual, n,
+                                          d.scale, pick_channels(n), s));
+      } else {
+        // very large messages go out as pipelined chunks (reference MLSL_LARGE_MSG_SIZE_MB / _CHUNKS,
+        // src/comm_ep.cpp:645-656) so a higher-priority collective can slip in between them
+        size_t chunks = 1;
+        if (ctx_->env.large_msg_mb && n * es >= ctx_->env.large_msg_mb * (size_t)1048576 && ctx_->env.large_msg_chunks > 1 &&
+            ctx_->env.msg_priority)
+          chunks = (size_t)ctx_->env.large_msg_chunks;
+        size_t per = round_up(ceil_div(n, chunks), 256);
+        for (size_t off = 0; off < n; off += per) {
+          size_t cnt = std::min(per, n - off);
+          MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, so + off * es, ro + off * es, cnt, d.scale, ch, s));
+        }
+      }
+      break;
+    }
+    case OpKind::REDUCE_SCATTER:
+      MLSLB_CUDA(launch_reduce_pull(dc, d.dtype, d.rop, so, ro, (size_t)me * n, n, d.scale, true, ch, s));
+      break;
+    case OpKind::REDUCE:
+      MLSLB_CUDA(launch_reduce_pull(dc, d.dtype, d.rop, so, ro, 0, n, d.scale, me == (int)d.root, ch, s));
+      break;
+    case OpKind::ALLGATHER:
+    case OpKind::ALLGATHERV:
+    case OpKind::BCAST:
+    case OpKind::ALLTOALL:
+    case OpKind::ALLTOALLV:
+    case OpKind::SENDRECV_LIST:
+    case OpKind::GATHER:
+    case OpKind::SCATTER: {
+      CopyPlan plan;
+      memset(&plan, 0, sizeof(plan));
+      plan.elem_size = (int)es;
+      auto add = [&](int peer, unsigned long long src, unsigned long long dst, unsigned long long bytes, int aux) {
+        CopySeg& sg = plan.seg[plan.nseg++];
+        sg.peer = peer;
+        sg.src_off = src;
+        sg.dst_off = dst;
+        sg.bytes = bytes;
+        sg.use_aux = aux;
+      };
+      unsigned long long pub_send = so;
+      switch (d.kind) {
+        case OpKind::ALLGATHER:
+          for (int p = 0; p < P; ++p) add(p, 0, (unsigned long long)p * n * es, n * es, 0);
+          break;
+        case OpKind::ALLGATHERV: {
+          unsigned long long off = 0;
+          for (int p = 0; p < P; ++p) {
+            add(p, 0, off * es, d.recv_counts[p] * es, 0);
+            off += d.recv_counts[p];
+          }
+          break;
+        }
+        case OpKind::BCAST:
+          pub_send = ro;   // one buffer: publish it as the source
+          if (me != (int)d.root) add((int)d.root, 0, 0, n * es, 0);
+          break;
+        case OpKind::ALLTOALL:
+          for (int p = 0; p < P; ++p) add(p, (unsigned long long)me * n * es, (unsigned long long)p * n * es, n * es, 0);
+          break;
+        case OpKind::ALLTOALLV:
+        case OpKind::SENDRECV_LIST:
+          for (int p = 0; p < P; ++p) {
+            plan.aux_out[p] = d.send_offsets[p];
+            if (d.recv_counts[p]) add(p, 0, d.recv_offsets[p] * es, d.recv_counts[p] * es, 1);
+          }
+          break;
+        case OpKind::GATHER:
+          if (me == (int)d.root)
+            for (int p = 0; p < P; ++p) add(p, 0, (unsigned long long)p * n * es, n * es, 0);
+          break;
+        case OpKind::SCATTER:
+          add((int)d.root, (unsigned long long)me * n * es, 0, n * es, 0);
+          break;
+        default: break;
+      }
+      MLSLB_CUDA(launch_pull_copy(dc, plan, pub_send, ro, ch, s));
+      break;
+    }
+    case OpKind::FUSED_UPDATE: {
+      const CommDesc::FusedUpdate& f = d.fused;
+      FusedUpdateArgs a;
+      a.optimizer = f.optimizer;
+      a.lr = f.lr;
+      a.momentum = f.momentum;
+      a.beta1 = f.beta1;
+      a.beta2 = f.beta2;
+      a.eps = f.eps;
+      a.weight_decay = f.weight_decay;
+      a.grad_scale = d.scale;
+      a.bc1 = f.optimizer == 1 ? 1.f - powf(f.beta1, (float)f.step) : 1.f;
+      a.bc2 = f.optimizer == 1 ? 1.f - powf(f.beta2, (float)f.step) : 1.f;
+      a.master = (float*)f.master;
+      a.state1 = (float*)f.state1;
+      a.state2 = (float*)f.state2;
+      MLSLB_CUDA(launch_fused_update(dc, d.dtype, d.has_out_dtype ? d.out_dtype : d.dtype, so, ro, n, a, ch, s));
+      break;
+    }
+    case OpKind::GEMM_RS: MLSLB_ASSERT(false, "GEMM_RS is launched through the ops API"); break;
+  }
+
+  // ---- copy results out of the staging buffers -------------------------------------------------------------------
+  if (alias_fix) MLSLB_CUDA(cudaMemcpyAsync(Rfinal, R, rbytes, cudaMemcpyDefault, s));
+  for (auto& sb : st->stages)
+    if (sb.copy_out && sb.user == r.recv) MLSLB_CUDA(cudaMemcpyAsync(sb.user, sb.slab, sb.bytes, cudaMemcpyDefault, s));
+}
+
+}  // namespace
+
+std::unique_ptr<Backend> make_cuda_backend(RankContext* ctx) {
+  if (!cuda_backend_available()) return nullptr;
+  return std::unique_ptr<Backend>(new CudaBackend(ctx));
+}
+
+bool cuda_backend_available() {
+  static int cached = -1;
+  if (cached < 0) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) cudaGetLastError();
+    cached = (e == cudaSuccess && n > 0) ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+void cuda_fill_sysinfo(SysInfo& s) {
+  if (!cuda_backend_available()) return;
+  int n = 0, dev = 0;
+  cudaGetDeviceCount(&n);
+  cudaGetDevice(&dev);
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return;
+  s.gpus = n;
+  s.sms = p.multiProcessorCount;
+  s.gpu_name = p.name;
+  s.cc_major = p.major;
+  s.cc_minor = p.minor;
+  s.peer_access = n <= 1;
+  if (n > 1) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, dev, (dev + 1) % n);
+    s.peer_access = can != 0;
+  }
+  // multicast (NVLS) support: CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED = 132, queried through the driver entry point
+  typedef int (*cuDeviceGetAttribute_t)(int*, int, int);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuDeviceGetAttribute", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn) {
+    int v = 0;
+    if (((cuDeviceGetAttribute_t)fn)(&v, 132, dev) == 0) s.multicast = v != 0;
+  } else {
+    cudaGetLastError();
+  }
+}
+
+}  // namespace mlslb

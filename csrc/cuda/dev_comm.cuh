@@ -1,0 +1,281 @@
+// Device-side communication primitives shared by every collective kernel (sm_100a).
+//
+// Model: each rank owns one "slab" of device memory that every peer of the NVSwitch domain has mapped (CUDA IPC,
+// or plain pointers for in-process ranks).  The first bytes of a slab hold signal pads: for every (group row, lane)
+// an array PadSlot[channel][peer].  A collective kernel is launched with the same grid on every member of the group;
+// CTA c of rank r only ever talks to CTA c of the peers ("channel" c - the GPU analogue of the reference's endpoint
+// c, eplib/), so no grid-wide synchronisation exists anywhere:
+//
+//   begin()  : ticket = ++seq[channel]            (device resident -> kernels are CUDA-graph replayable)
+//              write {send_off, recv_off, aux, flag=4*ticket} into every peer's pad slot [c][me]  (st.release.sys)
+//              wait for every peer's slot in MY pad  (ld.acquire.sys), pick up their buffer offsets
+//   ... move / reduce data straight out of / into the peers' buffers over NVLink ...
+//   sync(k)  : flag = 4*ticket + k handshake between the same CTAs (k = 1..3), release/acquire at .sys scope
+//
+// Flags only ever grow, so nothing is reset between collectives; a new group on a recycled row starts from zeroed
+// pads (host side).  Every spin has a %globaltimer deadline: on expiry the kernel records an error word in
+// host-mapped memory and stops waiting, so a missing peer can never wedge the GPU (fail-fast).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "core/common.hpp"
+
+namespace mlslb {
+
+struct alignas(32) PadSlot {
+  unsigned long long flag, a, b, aux;
+};
+
+struct DevComm {
+  int nranks;                 // group size
+  int me;                     // my index in the group
+  unsigned pad_off;           // byte offset of this (row, lane) pad array inside every slab
+  unsigned seq_off;           // byte offset of my private per-channel ticket counters
+  unsigned long long timeout_ns;
+  int* err;                   // host-mapped error word (0 = ok)
+  char* slab[kMaxDevRanks];   // slab base of every member (group order) in MY address space
+  char* mc;                   // multicast mapping of the slabs (NVLS) or nullptr
+};
+
+struct PeerTable {            // lives in shared memory
+  char* send[kMaxDevRanks];
+  char* recv[kMaxDevRanks];
+  unsigned long long aux[kMaxDevRanks];
+  unsigned long long ticket;
+  int failed;
+};
+
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// 16-byte accesses that stay out of L1 (peer lines are only ever cached in the reader's L1, never its L2 -
+// keeping them out makes every load observe the owner's L2/HBM).
+__device__ __forceinline__ uint4 ld16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st16(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ PadSlot* pad_slot(const DevComm& dc, int owner, int channel, int writer) {
+  return reinterpret_cast<PadSlot*>(dc.slab[owner] + dc.pad_off) + channel * kMaxDevRanks + writer;
+}
+
+__device__ __forceinline__ bool spin_until(const DevComm& dc, const unsigned long long* flag, unsigned long long want) {
+  if (ld_acquire_sys(flag) >= want) return true;
+  unsigned long long t0 = globaltimer_ns();
+  unsigned spins = 0;
+  while (ld_acquire_sys(flag) < want) {
+    if ((++spins & 0x3ff) == 0) {
+      if (*(volatile int*)dc.err != 0) return false;               // another CTA / the host already gave up
+      if (dc.timeout_ns && globaltimer_ns() - t0 > dc.timeout_ns) {
+        *(volatile int*)dc.err = 1000 + dc.me;
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+// Opening handshake.  `aux_for_peer(p)` is a per-destination word (the *v collectives publish their send
+// offsets with it).  Returns the ticket; fills `pt` with the peers' buffer addresses.
+template <typename AuxFn>
+__device__ __forceinline__ unsigned long long comm_begin(const DevComm& dc, PeerTable& pt, unsigned long long send_off,
+                                                         unsigned long long recv_off, AuxFn aux_for_peer) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    unsigned long long* seq = reinterpret_cast<unsigned long long*>(dc.slab[dc.me] + dc.seq_off) + blockIdx.x;
+    unsigned long long t = *seq + 1;
+    *seq = t;
+    pt.ticket = t;
+    pt.failed = 0;
+  }
+  __syncthreads();
+  const unsigned long long t = pt.ticket;
+  if (tid < dc.nranks) {
+    PadSlot* remote = pad_slot(dc, tid, blockIdx.x, dc.me);
+    st_relaxed_sys(&remote->a, send_off);
+    st_relaxed_sys(&remote->b, recv_off);
+    st_relaxed_sys(&remote->aux, aux_for_peer(tid));
+    st_release_sys(&remote->flag, 4 * t);
+    PadSlot* local = pad_slot(dc, dc.me, blockIdx.x, tid);
+    if (spin_until(dc, &local->flag, 4 * t)) {
+      pt.send[tid] = dc.slab[tid] + ld_relaxed_sys(&local->a);
+      pt.recv[tid] = dc.slab[tid] + ld_relaxed_sys(&local->b);
+      pt.aux[tid] = ld_relaxed_sys(&local->aux);
+    } else {   // peer never showed up: keep every address valid (results are garbage, the host reports the error)
+      pt.failed = 1;
+      pt.send[tid] = dc.slab[dc.me] + send_off;
+      pt.recv[tid] = dc.slab[dc.me] + recv_off;
+      pt.aux[tid] = 0;
+    }
+  }
+  __syncthreads();
+  return t;
+}
+
+struct NoAux {
+  __device__ __forceinline__ unsigned long long operator()(int) const { return 0ull; }
+};
+
+// Handshake k (1..3) between the same channel of every member.  `published_remote_writes`: this CTA stored into
+// peer memory since the last handshake, so the writes must be performed before the flag becomes visible.
+__device__ __forceinline__ void comm_sync(const DevComm& dc, PeerTable& pt, unsigned long long t, int k,
+                                          bool published_remote_writes) {
+  __syncthreads();
+  const int tid = threadIdx.x;
+  if (tid < dc.nranks) {
+    if (published_remote_writes) __threadfence_system();
+    st_release_sys(&pad_slot(dc, tid, blockIdx.x, dc.me)->flag, 4 * t + k);
+    if (!spin_until(dc, &pad_slot(dc, dc.me, blockIdx.x, tid)->flag, 4 * t + k)) pt.failed = 1;
+  }
+  __syncthreads();
+}
+
+// ---- element math ----------------------------------------------------------------------------------------------
+struct OpSum {
+  template <typename A> __device__ __forceinline__ static A apply(A a, A b) { return a + b; }
+};
+struct OpMin {
+  template <typename A> __device__ __forceinline__ static A apply(A a, A b) { return a < b ? a : b; }
+};
+struct OpMax {
+  template <typename A> __device__ __forceinline__ static A apply(A a, A b) { return a > b ? a : b; }
+};
+
+// VecTraits<T>: how a 16-byte vector of T is unpacked to accumulators and packed back.
+template <typename T> struct VecTraits;
+template <> struct VecTraits<float> {
+  using Acc = float;
+  static constexpr int N = 4;
+  __device__ __forceinline__ static void unpack(const uint4& v, Acc* a) {
+    a[0] = __uint_as_float(v.x); a[1] = __uint_as_float(v.y); a[2] = __uint_as_float(v.z); a[3] = __uint_as_float(v.w);
+  }
+  __device__ __forceinline__ static uint4 pack(const Acc* a) {
+    return make_uint4(__float_as_uint(a[0]), __float_as_uint(a[1]), __float_as_uint(a[2]), __float_as_uint(a[3]));
+  }
+  __device__ __forceinline__ static Acc load1(const void* p) { return *(const float*)p; }
+  __device__ __forceinline__ static void store1(void* p, Acc a) { *(float*)p = a; }
+  __device__ __forceinline__ static Acc scale(Acc a, float s) { return a * s; }
+};
+template <> struct VecTraits<double> {
+  using Acc = double;
+  static constexpr int N = 2;
+  __device__ __forceinline__ static void unpack(const uint4& v, Acc* a) {
+    a[0] = __hiloint2double((int)v.y, (int)v.x); a[1] = __hiloint2double((int)v.w, (int)v.z);
+  }
+  __device__ __forceinline__ static uint4 pack(const Acc* a) {
+    return make_uint4((unsigned)__double2loint(a[0]), (unsigned)__double2hiint(a[0]), (unsigned)__double2loint(a[1]),
+                      (unsigned)__double2hiint(a[1]));
+  }
+  __device__ __forceinline__ static Acc load1(const void* p) { return *(const double*)p; }
+  __device__ __forceinline__ static void store1(void* p, Acc a) { *(double*)p = a; }
+  __device__ __forceinline__ static Acc scale(Acc a, float s) { return a * (double)s; }
+};
+template <> struct VecTraits<int> {
+  using Acc = int;
+  static constexpr int N = 4;
+  __device__ __forceinline__ static void unpack(const uint4& v, Acc* a) { a[0] = (int)v.x; a[1] = (int)v.y; a[2] = (int)v.z; a[3] = (int)v.w; }
+  __device__ __forceinline__ static uint4 pack(const Acc* a) { return make_uint4((unsigned)a[0], (unsigned)a[1], (unsigned)a[2], (unsigned)a[3]); }
+  __device__ __forceinline__ static Acc load1(const void* p) { return *(const int*)p; }
+  __device__ __forceinline__ static void store1(void* p, Acc a) { *(int*)p = a; }
+  __device__ __forceinline__ static Acc scale(Acc a, float) { return a; }
+};
+template <> struct VecTraits<unsigned char> {
+  using Acc = unsigned;   // per-byte lanes kept in 32-bit accumulators, wrap-around on pack
+  static constexpr int N = 16;
+  __device__ __forceinline__ static void unpack(const uint4& v, Acc* a) {
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+  }
+  __device__ __forceinline__ static uint4 pack(const Acc* a) {
+    unsigned w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i >> 2] |= (a[i] & 0xffu) << ((i & 3) * 8);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ __forceinline__ static Acc load1(const void* p) { return *(const unsigned char*)p; }
+  __device__ __forceinline__ static void store1(void* p, Acc a) { *(unsigned char*)p = (unsigned char)a; }
+  __device__ __forceinline__ static Acc scale(Acc a, float) { return a; }
+};
+template <> struct VecTraits<__nv_bfloat16> {
+  using Acc = float;
+  static constexpr int N = 8;
+  __device__ __forceinline__ static void unpack(const uint4& v, Acc* a) {
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[2 * i] = __uint_as_float(w[i] << 16);
+      a[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ __forceinline__ static uint4 pack(const Acc* a) {
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
+      w[i] = *reinterpret_cast<unsigned*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ __forceinline__ static Acc load1(const void* p) { return __bfloat162float(*(const __nv_bfloat16*)p); }
+  __device__ __forceinline__ static void store1(void* p, Acc a) { *(__nv_bfloat16*)p = __float2bfloat16_rn(a); }
+  __device__ __forceinline__ static Acc scale(Acc a, float s) { return a * s; }
+};
+template <> struct VecTraits<__half> {
+  using Acc = float;
+  static constexpr int N = 8;
+  __device__ __forceinline__ static void unpack(const uint4& v, Acc* a) {
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      float2 f = __half22float2(h);
+      a[2 * i] = f.x;
+      a[2 * i + 1] = f.y;
+    }
+  }
+  __device__ __forceinline__ static uint4 pack(const Acc* a) {
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = __floats2half2_rn(a[2 * i], a[2 * i + 1]);
+      w[i] = *reinterpret_cast<unsigned*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ __forceinline__ static Acc load1(const void* p) { return __half2float(*(const __half*)p); }
+  __device__ __forceinline__ static void store1(void* p, Acc a) { *(__half*)p = __float2half_rn(a); }
+  __device__ __forceinline__ static Acc scale(Acc a, float s) { return a * s; }
+};
+
+}  // namespace mlslb

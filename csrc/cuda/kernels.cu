@@ -1,0 +1,413 @@
+// Peer-memory collective kernels for sm_100a (NVLink 5 / NVSwitch).
+//
+// These replace every MPI call site of the reference (MPI_Iallreduce / Ireduce_scatter_block /
+// Iallgather(v) / Ibcast / Ireduce / Ialltoall(v) / Igather / Iscatter / Barrier in reference src/comm_ep.cpp:768-1378
+// and eplib/cqueue.c:1930-2098).  One kernel = one collective: the handshake, the data movement out of / into the
+// peers' buffers and the scale epilogue all happen inside it; channels (CTAs) play the role of the reference's
+// endpoints (a message is split across them).
+#include "cuda/kernels.hpp"
+
+namespace mlslb {
+
+// ------------------------------------------------------------------------------------------------------------
+// K8: barrier
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_barrier(DevComm dc) {
+  __shared__ PeerTable pt;
+  unsigned long long t = comm_begin(dc, pt, 0, 0, NoAux());
+  comm_sync(dc, pt, t, 1, false);
+}
+
+cudaError_t launch_barrier(const DevComm& dc, cudaStream_t s) {
+  k_barrier<<<1, 32, 0, s>>>(dc);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1: all-reduce, "fused two-shot": CTA c of rank r owns sub-slice (r, c) of the message.  It pulls that sub-slice
+// from every peer's send buffer, reduces in registers, applies the scale and pushes the result into every peer's
+// receive buffer.  Reads and writes of one 16-byte chunk are done by the same thread, so in-place operation needs
+// no extra barrier: 2 handshakes per collective, NVLink busy in both directions for the whole kernel.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, typename Op, int U>
+__global__ void __launch_bounds__(kCommThreads) k_allreduce(DevComm dc, unsigned long long send_off,
+                                                            unsigned long long recv_off, size_t count, float scale) {
+  using VT = VecTraits<T>;
+  using Acc = typename VT::Acc;
+  constexpr int N = VT::N;
+  __shared__ PeerTable pt;
+  __shared__ int s_aligned;
+  const unsigned long long t = comm_begin(dc, pt, send_off, recv_off, NoAux());
+  const int P = dc.nranks, me = dc.me;
+  if (threadIdx.x == 0) {
+    unsigned long long bits = 0;
+    for (int p = 0; p < P; ++p) bits |= (unsigned long long)pt.send[p] | (unsigned long long)pt.recv[p];
+    s_aligned = (bits & 15ull) == 0;
+  }
+  __syncthreads();
+  // slice of this rank, in elements (vector aligned so that every slice but the last is a whole number of vectors)
+  size_t per = (count + P - 1) / P;
+  per = (per + N - 1) / N * N;
+  const size_t lo = min(count, (size_t)me * per), hi = min(count, lo + per);
+  const size_t n = hi - lo;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+  const bool do_scale = scale != 1.0f;
+  if (s_aligned) {
+    const size_t nvec = n / N;
+    for (size_t base = gtid; base < nvec; base += gsz * U) {
+      Acc acc[U][N];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t i = base + (size_t)u * gsz;
+        if (i < nvec) {
+          uint4 v = ld16(pt.send[me] + (lo + i * N) * sizeof(T));
+          VT::unpack(v, acc[u]);
+        }
+      }
+      for (int q = 1; q < P; ++q) {
+        int p = me + q;
+        if (p >= P) p -= P;
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t i = base + (size_t)u * gsz;
+          if (i < nvec) v[u] = ld16(pt.send[p] + (lo + i * N) * sizeof(T));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t i = base + (size_t)u * gsz;
+          if (i < nvec) {
+            Acc b[N];
+            VT::unpack(v[u], b);
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc[u][k] = Op::apply(acc[u][k], b[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t i = base + (size_t)u * gsz;
+        if (i < nvec) {
+          if (do_scale) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc[u][k] = VT::scale(acc[u][k], scale);
+          }
+          uint4 r = VT::pack(acc[u]);
+          for (int q = 0; q < P; ++q) {
+            int p = me + q;
+            if (p >= P) p -= P;
+            st16(pt.recv[p] + (lo + i * N) * sizeof(T), r);
+          }
+        }
+      }
+    }
+    // tail elements of the last slice
+    for (size_t i = nvec * N + gtid; i < n; i += gsz) {
+      Acc a = VT::load1(pt.send[me] + (lo + i) * sizeof(T));
+      for (int q = 1; q < P; ++q) {
+        int p = me + q;
+        if (p >= P) p -= P;
+        a = Op::apply(a, VT::load1(pt.send[p] + (lo + i) * sizeof(T)));
+      }
+      if (do_scale) a = VT::scale(a, scale);
+      for (int p = 0; p < P; ++p) VT::store1(pt.recv[p] + (lo + i) * sizeof(T), a);
+    }
+  } else {
+    for (size_t i = gtid; i < n; i += gsz) {
+      Acc a = VT::load1(pt.send[me] + (lo + i) * sizeof(T));
+      for (int q = 1; q < P; ++q) {
+        int p = me + q;
+        if (p >= P) p -= P;
+        a = Op::apply(a, VT::load1(pt.send[p] + (lo + i) * sizeof(T)));
+      }
+      if (do_scale) a = VT::scale(a, scale);
+      for (int p = 0; p < P; ++p) VT::store1(pt.recv[p] + (lo + i) * sizeof(T), a);
+    }
+  }
+  comm_sync(dc, pt, t, 1, true);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2 / K5: pull-reduce.  out[i] = scale * op_p send_p[base + i] for i < count, written to MY recv buffer only.
+// ReduceScatter: every rank active with base = me * count.  Reduce: only the root is active (base 0); the
+// others just keep their send buffers alive until the closing handshake.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, typename Op, int U>
+__global__ void __launch_bounds__(kCommThreads) k_reduce_pull(DevComm dc, unsigned long long send_off,
+                                                              unsigned long long recv_off, size_t base_elems,
+                                                              size_t count, float scale, int active) {
+  using VT = VecTraits<T>;
+  using Acc = typename VT::Acc;
+  constexpr int N = VT::N;
+  __shared__ PeerTable pt;
+  __shared__ int s_aligned;
+  const unsigned long long t = comm_begin(dc, pt, send_off, recv_off, NoAux());
+  const int P = dc.nranks, me = dc.me;
+  if (active) {
+    if (threadIdx.x == 0) {
+      unsigned long long bits = (unsigned long long)pt.recv[me] | (unsigned long long)(base_elems * sizeof(T));
+      for (int p = 0; p < P; ++p) bits |= (unsigned long long)pt.send[p];
+      s_aligned = (bits & 15ull) == 0;
+    }
+    __syncthreads();
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    const bool do_scale = scale != 1.0f;
+    char* out = pt.recv[me];
+    const size_t nvec = s_aligned ? count / N : 0;
+    for (size_t b0 = gtid; b0 < nvec; b0 += gsz * U) {
+      Acc acc[U][N];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t i = b0 + (size_t)u * gsz;
+        if (i < nvec) VT::unpack(ld16(pt.send[me] + (base_elems + i * N) * sizeof(T)), acc[u]);
+      }
+      for (int q = 1; q < P; ++q) {
+        int p = me + q;
+        if (p >= P) p -= P;
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t i = b0 + (size_t)u * gsz;
+          if (i < nvec) v[u] = ld16(pt.send[p] + (base_elems + i * N) * sizeof(T));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t i = b0 + (size_t)u * gsz;
+          if (i < nvec) {
+            Acc b[N];
+            VT::unpack(v[u], b);
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc[u][k] = Op::apply(acc[u][k], b[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t i = b0 + (size_t)u * gsz;
+        if (i < nvec) {
+          if (do_scale) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc[u][k] = VT::scale(acc[u][k], scale);
+          }
+          st16(out + i * N * sizeof(T), VT::pack(acc[u]));
+        }
+      }
+    }
+    for (size_t i = nvec * N + gtid; i < count; i += gsz) {
+      Acc a = VT::load1(pt.send[me] + (base_elems + i) * sizeof(T));
+      for (int q = 1; q < P; ++q) {
+        int p = me + q;
+        if (p >= P) p -= P;
+        a = Op::apply(a, VT::load1(pt.send[p] + (base_elems + i) * sizeof(T)));
+      }
+      if (do_scale) a = VT::scale(a, scale);
+      VT::store1(out + i * sizeof(T), a);
+    }
+  }
+  comm_sync(dc, pt, t, 1, false);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3/K4/K6/K7/K9: pull-copy.  Every gather-like collective is "copy these byte ranges out of the peers' send
+// buffers into my receive buffer"; only local memory is written, so no write fence is needed before the closing
+// handshake.  For the *v collectives the source offset inside the peer's buffer comes from the peer (aux word).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCommThreads) k_pull_copy(DevComm dc, CopyPlan plan, unsigned long long send_off,
+                                                            unsigned long long recv_off) {
+  __shared__ PeerTable pt;
+  struct AuxOut {
+    const CopyPlan* pl;
+    __device__ __forceinline__ unsigned long long operator()(int p) const { return pl->aux_out[p]; }
+  } auxfn{&plan};
+  const unsigned long long t = comm_begin(dc, pt, send_off, recv_off, auxfn);
+  const int me = dc.me;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  for (int sgi = 0; sgi < plan.nseg; ++sgi) {
+    // rotate the segment order by rank so the peers are not all hammering the same source at the same time
+    int sidx = sgi + me;
+    while (sidx >= plan.nseg) sidx -= plan.nseg;
+    const CopySeg sg = plan.seg[sidx];
+    const char* src = pt.send[sg.peer] + sg.src_off + (sg.use_aux ? pt.aux[sg.peer] * (unsigned long long)plan.elem_size : 0ull);
+    char* dst = pt.recv[me] + sg.dst_off;
+    if (src == dst || sg.bytes == 0) continue;
+    const bool aligned = ((((unsigned long long)src) | ((unsigned long long)dst)) & 15ull) == 0;
+    size_t done = 0;
+    if (aligned) {
+      const size_t nvec = sg.bytes / 16;
+      for (size_t b0 = gtid; b0 < nvec; b0 += gsz * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t i = b0 + (size_t)u * gsz;
+          if (i < nvec) v[u] = ld16(src + i * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t i = b0 + (size_t)u * gsz;
+          if (i < nvec) st16(dst + i * 16, v[u]);
+        }
+      }
+      done = nvec * 16;
+    }
+    for (size_t i = done + gtid; i < sg.bytes; i += gsz) dst[i] = src[i];
+  }
+  comm_sync(dc, pt, t, 1, false);
+}
+
+cudaError_t launch_pull_copy(const DevComm& dc, const CopyPlan& plan, unsigned long long send_off,
+                             unsigned long long recv_off, int channels, cudaStream_t s) {
+  k_pull_copy<<<channels, kCommThreads, 0, s>>>(dc, plan, send_off, recv_off);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, typename Op>
+static cudaError_t launch_ar_t(const DevComm& dc, unsigned long long so, unsigned long long ro, size_t count,
+                               float scale, int channels, cudaStream_t s) {
+  // small messages: one vector per thread keeps the critical path short; big ones: more loads in flight
+  if (count * sizeof(T) <= (size_t)(1 << 20))
+    k_allreduce<T, Op, 1><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+  else
+    k_allreduce<T, Op, 2><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+  return cudaGetLastError();
+}
+template <typename T, typename Op>
+static cudaError_t launch_rp_t(const DevComm& dc, unsigned long long so, unsigned long long ro, size_t base,
+                               size_t count, float scale, bool active, int channels, cudaStream_t s) {
+  k_reduce_pull<T, Op, 2><<<channels, kCommThreads, 0, s>>>(dc, so, ro, base, count, scale, active ? 1 : 0);
+  return cudaGetLastError();
+}
+
+#define MLSLB_DISPATCH_T_OP(DT, OP, CALL)                                                     \
+  switch (DT) {                                                                               \
+    case DType::F32: MLSLB_DISPATCH_OP(float, OP, CALL) break;                                \
+    case DType::F64: MLSLB_DISPATCH_OP(double, OP, CALL) break;                               \
+    case DType::I32: MLSLB_DISPATCH_OP(int, OP, CALL) break;                                  \
+    case DType::U8:                                                                           \
+    case DType::F8E4M3: MLSLB_DISPATCH_OP(unsigned char, OP, CALL) break;                     \
+    case DType::BF16: MLSLB_DISPATCH_OP(__nv_bfloat16, OP, CALL) break;                       \
+    case DType::F16: MLSLB_DISPATCH_OP(__half, OP, CALL) break;                               \
+  }
+#define MLSLB_DISPATCH_OP(T, OP, CALL)                                                        \
+  switch (OP) {                                                                               \
+    case RedOp::SUM: { using TT = T; using OO = OpSum; return CALL; }                         \
+    case RedOp::MIN: { using TT = T; using OO = OpMin; return CALL; }                         \
+    case RedOp::MAX: { using TT = T; using OO = OpMax; return CALL; }                         \
+  }
+
+cudaError_t launch_allreduce(const DevComm& dc, DType dt, RedOp op, unsigned long long send_off,
+                             unsigned long long recv_off, size_t count, float scale, int channels, cudaStream_t s) {
+  MLSLB_DISPATCH_T_OP(dt, op, (launch_ar_t<TT, OO>(dc, send_off, recv_off, count, scale, channels, s)))
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_reduce_pull(const DevComm& dc, DType dt, RedOp op, unsigned long long send_off,
+                               unsigned long long recv_off, size_t base, size_t count, float scale, bool active,
+                               int channels, cudaStream_t s) {
+  MLSLB_DISPATCH_T_OP(dt, op, (launch_rp_t<TT, OO>(dc, send_off, recv_off, base, count, scale, active, channels, s)))
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K13: activation pack / unpack.  A block is an (mbCount x fmCount*fmSize) rectangle; one minibatch row of it is
+// contiguous on both sides, so each row is a straight vector copy.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_blocks(PackPlan plan, size_t local_fm_count, int es, const char* src,
+                                                     char* dst, int unpack) {
+  const int b = blockIdx.y;
+  if (b >= plan.n) return;
+  const BlockDesc k = plan.b[b];
+  const size_t row_bytes = k.fm_cnt * k.fm_size * (size_t)es;
+  const size_t total = k.mb_cnt * row_bytes;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+  const size_t local0 = (k.mb_off * local_fm_count + k.fm_off) * k.fm_size * (size_t)es;
+  const size_t local_stride = local_fm_count * k.fm_size * (size_t)es;
+  const size_t comm0 = k.buf_off * (size_t)es;
+  const bool vec = ((row_bytes | local0 | local_stride | comm0 | (size_t)src | (size_t)dst) & 15) == 0;
+  if (vec) {
+    const size_t rv = row_bytes / 16, nv = total / 16;
+    for (size_t i = gtid; i < nv; i += gsz) {
+      const size_t mb = i / rv, c = i - mb * rv;
+      const size_t lo = local0 + mb * local_stride + c * 16, co = comm0 + mb * row_bytes + c * 16;
+      if (!unpack) *(uint4*)(dst + co) = *(const uint4*)(src + lo);
+      else *(uint4*)(dst + lo) = *(const uint4*)(src + co);
+    }
+  } else {
+    for (size_t i = gtid; i < total; i += gsz) {
+      const size_t mb = i / row_bytes, c = i - mb * row_bytes;
+      const size_t lo = local0 + mb * local_stride + c, co = comm0 + mb * row_bytes + c;
+      if (!unpack) dst[co] = src[lo];
+      else dst[lo] = src[co];
+    }
+  }
+}
+
+cudaError_t launch_pack_blocks(const PackPlan& plan, size_t local_fm_count, int elem_size, const void* src, void* dst,
+                               bool unpack, size_t max_block_elems, cudaStream_t s) {
+  size_t bytes = max_block_elems * (size_t)elem_size;
+  int gx = (int)std::min<size_t>(148, std::max<size_t>(1, bytes / (256 * 64)));
+  dim3 grid(gx, plan.n);
+  k_pack_blocks<<<grid, 256, 0, s>>>(plan, local_fm_count, elem_size, (const char*)src, (char*)dst, unpack ? 1 : 0);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// local scale (single-rank groups keep the "result = scale * sum" contract without any peer traffic)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_scale(T* buf, size_t count, float scale) {
+  using VT = VecTraits<T>;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+    VT::store1(buf + i, VT::scale(VT::load1(buf + i), scale));
+}
+
+cudaError_t launch_scale(DType dt, void* buf, size_t count, float scale, cudaStream_t s) {
+  int grid = (int)std::min<size_t>(296, std::max<size_t>(1, count / 1024));
+  switch (dt) {
+    case DType::F32: k_scale<float><<<grid, 256, 0, s>>>((float*)buf, count, scale); break;
+    case DType::F64: k_scale<double><<<grid, 256, 0, s>>>((double*)buf, count, scale); break;
+    case DType::BF16: k_scale<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)buf, count, scale); break;
+    case DType::F16: k_scale<__half><<<grid, 256, 0, s>>>((__half*)buf, count, scale); break;
+    default: break;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace mlslb
+
+namespace mlslb {
+// dst = scale * src (single-rank groups: the whole "collective" is this one kernel)
+template <typename T>
+__global__ void __launch_bounds__(256) k_scale_copy(T* __restrict__ dst, const T* __restrict__ src, size_t count, float scale) {
+  using VT = VecTraits<T>;
+  using Acc = typename VT::Acc;
+  constexpr int N = VT::N;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+  const bool vec = ((((size_t)dst) | ((size_t)src)) & 15) == 0;
+  const size_t nvec = vec ? count / N : 0;
+  for (size_t i = gtid; i < nvec; i += gsz) {
+    Acc a[N];
+    VT::unpack(__ldcs(reinterpret_cast<const uint4*>(src) + i), a);
+#pragma unroll
+    for (int k = 0; k < N; ++k) a[k] = VT::scale(a[k], scale);
+    __stcs(reinterpret_cast<uint4*>(dst) + i, VT::pack(a));
+  }
+  for (size_t i = nvec * N + gtid; i < count; i += gsz) VT::store1(dst + i, VT::scale(VT::load1(src + i), scale));
+}
+
+cudaError_t launch_scale_copy(DType dt, void* dst, const void* src, size_t count, float scale, cudaStream_t s) {
+  int grid = (int)std::min<size_t>(148 * 8, std::max<size_t>(1, count / 2048));
+  switch (dt) {
+    case DType::F32: k_scale_copy<float><<<grid, 256, 0, s>>>((float*)dst, (const float*)src, count, scale); break;
+    case DType::F64: k_scale_copy<double><<<grid, 256, 0, s>>>((double*)dst, (const double*)src, count, scale); break;
+    case DType::BF16: k_scale_copy<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, count, scale); break;
+    case DType::F16: k_scale_copy<__half><<<grid, 256, 0, s>>>((__half*)dst, (const __half*)src, count, scale); break;
+    case DType::I32: k_scale_copy<int><<<grid, 256, 0, s>>>((int*)dst, (const int*)src, count, 1.0f); break;
+    default: k_scale_copy<unsigned char><<<grid, 256, 0, s>>>((unsigned char*)dst, (const unsigned char*)src, count, 1.0f); break;
+  }
+  return cudaGetLastError();
+}
+}  // namespace mlslb

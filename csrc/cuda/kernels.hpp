@@ -1,0 +1,66 @@
+// Host-callable launchers of the sm_100a collective kernels (implemented in csrc/cuda/*.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "core/common.hpp"
+#include "core/runtime.hpp"
+#include "cuda/dev_comm.cuh"
+
+namespace mlslb {
+
+constexpr int kCommThreads = 512;
+
+// One source segment of a gather-like collective: copy `bytes` from peer's send buffer (+src_off, + the peer's
+// published aux word * elem_size when use_aux) to my recv buffer + dst_off.
+struct CopySeg {
+  int peer;
+  int use_aux;
+  unsigned long long src_off, dst_off, bytes;
+};
+struct CopyPlan {
+  int nseg;
+  int elem_size;
+  CopySeg seg[kMaxDevRanks];
+  unsigned long long aux_out[kMaxDevRanks];   // word I publish to peer p in the opening handshake
+};
+
+// K8 barrier
+cudaError_t launch_barrier(const DevComm& dc, cudaStream_t s);
+// K1 all-reduce: fused reduce-scatter + all-gather over peer memory, scale epilogue
+cudaError_t launch_allreduce(const DevComm& dc, DType dt, RedOp op, unsigned long long send_off,
+                             unsigned long long recv_off, size_t count, float scale, int channels, cudaStream_t s);
+// K2/K5 reduce-scatter and reduce: out[i] = scale * op_p send_p[base + i], i < count (active ranks only)
+cudaError_t launch_reduce_pull(const DevComm& dc, DType dt, RedOp op, unsigned long long send_off,
+                               unsigned long long recv_off, size_t base, size_t count, float scale, bool active,
+                               int channels, cudaStream_t s);
+// K3/K4/K6/K7/K9 all-gather(v), bcast, all-to-all(v), gather, scatter, send/recv list
+cudaError_t launch_pull_copy(const DevComm& dc, const CopyPlan& plan, unsigned long long send_off,
+                             unsigned long long recv_off, int channels, cudaStream_t s);
+// K13 activation pack / unpack (strided (mb, fm, fmSize) gather/scatter), local
+struct PackPlan {
+  int n;
+  BlockDesc b[kMaxDevRanks];
+};
+cudaError_t launch_pack_blocks(const PackPlan& plan, size_t local_fm_count, int elem_size, const void* src, void* dst,
+                               bool unpack, size_t max_block_elems, cudaStream_t s);
+// K11 fused fp8 block-quantised all-reduce with error feedback (fp32 in/out)
+cudaError_t launch_allreduce_quant(const DevComm& dc, unsigned long long send_off, unsigned long long recv_off,
+                                   unsigned long long stage_off, float* residual, size_t count, float scale,
+                                   int channels, cudaStream_t s);
+size_t allreduce_quant_stage_bytes(size_t count);
+// fused distributed update: reduce-scatter + optimizer + all-gather in one kernel
+struct FusedUpdateArgs {
+  int optimizer;
+  float lr, momentum, beta1, beta2, eps, weight_decay, grad_scale, bc1, bc2;
+  float* master;
+  float* state1;
+  float* state2;
+};
+cudaError_t launch_fused_update(const DevComm& dc, DType grad_dt, DType param_dt, unsigned long long grad_off,
+                                unsigned long long param_off, size_t owned, const FusedUpdateArgs& a, int channels,
+                                cudaStream_t s);
+// local elementwise helper (scale in place) for single-rank groups
+cudaError_t launch_scale(DType dt, void* buf, size_t count, float scale, cudaStream_t s);
+cudaError_t launch_scale_copy(DType dt, void* dst, const void* src, size_t count, float scale, cudaStream_t s);
+
+}  // namespace mlslb

@@ -1,0 +1,30 @@
+"""mlsl_b200: a Blackwell-native deep-learning collective library with the capabilities of Intel MLSL.
+
+    import mlsl_b200 as mlsl
+    mlsl.init()                                   # RANK / WORLD_SIZE / LOCAL_RANK from the environment (torchrun)
+    g = mlsl.alloc_tensor(n, torch.float32)       # lives in the symmetric, peer-mapped heap
+    mlsl.allreduce(g, scale=1.0 / mlsl.world_size())
+    opt = mlsl.DistributedOptimizer(model.parameters(), lr=0.1)
+
+The object model of the reference (Environment / Session / Distribution / Operation / ...) is in `mlsl_b200.api`.
+"""
+from . import _lib, api
+from ._lib import MLSLError
+from .api import (CompressionType, DataType, GroupType, InprocWorld, MLSL, OperationType, OptimizerType, PhaseType,
+                  ReductionType, cuda_available)
+from .comm import (Work, alloc_tensor, allgather, allreduce, alltoall, barrier, bcast, bind_thread_state, env, finalize,
+                   free_tensor, init, is_device, is_initialized, rank, reduce, reduce_scatter, tensor_from_address,
+                   world_distribution, world_size)
+
+__version__ = "2026.1"
+
+
+def __getattr__(name):
+    # heavier modules are imported on demand
+    if name == "DistributedOptimizer":
+        from .optim import DistributedOptimizer
+        return DistributedOptimizer
+    if name == "DistributedDataParallel":
+        from .parallel.data_parallel import DistributedDataParallel
+        return DistributedDataParallel
+    raise AttributeError(name)

@@ -1,0 +1,267 @@
+"""Tensor-level API: `mlsl.init()`, `mlsl.allreduce(t)`, `mlsl.allgather(...)`, symmetric-heap tensors.
+
+The thin PyTorch face of the library.  Every call goes straight to the native runtime through
+the C API; on the CUDA backend the collective is ordered after the work already queued on torch's current stream and
+`Work.wait()` orders the current stream after the collective (no host blocking), like torch.distributed.
+"""
+import ctypes
+import threading
+
+import torch
+
+from . import api
+from .api import CompressionType, DataType, GroupType, ReductionType
+
+_tls = threading.local()
+_process_state = {}
+
+_TORCH2MLSL = {
+    torch.float32: DataType.FLOAT,
+    torch.float64: DataType.DOUBLE,
+    torch.uint8: DataType.BYTE,
+    torch.int8: DataType.BYTE,
+    torch.bfloat16: DataType.BF16,
+    torch.float16: DataType.FP16,
+    torch.int32: DataType.INT32,
+}
+_OPS = {"sum": ReductionType.SUM, "min": ReductionType.MIN, "max": ReductionType.MAX}
+_GROUPS = {"data": GroupType.DATA, "model": GroupType.MODEL, "global": GroupType.GLOBAL}
+
+
+def _state():
+    if getattr(_tls, "bound", False):
+        return _tls.__dict__
+    return _process_state
+
+
+def bind_thread_state():
+    """Give the calling thread its own library state (in-process virtual ranks call this before init())."""
+    _tls.bound = True
+
+
+def mlsl_dtype(t):
+    try:
+        return _TORCH2MLSL[t]
+    except KeyError:
+        raise TypeError("dtype %s is not supported by mlsl_b200" % t)
+
+
+class Work:
+    """Handle of an in-flight collective."""
+
+    def __init__(self, env, req, result=None, keep=()):
+        self._env, self._req, self.result, self._keep = env, req, result, keep
+
+    def wait(self):
+        if self._req is not None:
+            self._env.wait(self._req)
+            self._req = None
+        return self.result
+
+    def is_completed(self):
+        if self._req is None:
+            return True
+        if self._env.test(self._req):
+            self._req = None
+            return True
+        return False
+
+
+def init(wait_mode=None):
+    """Initialise the library for this process (or this virtual rank).  Returns the Environment (api.MLSL)."""
+    st = _state()
+    if st.get("env") is not None:
+        return st["env"]
+    env = api.MLSL()
+    env.init()
+    st["env"] = env
+    st["device"] = env.is_device_backend()
+    st["world_dist"] = None
+    st["live"] = {}
+    if st["device"]:
+        env.set_wait_mode(wait_mode or "stream")
+    return env
+
+
+def finalize():
+    st = _state()
+    env = st.get("env")
+    if env is None:
+        return
+    if st.get("world_dist") is not None:
+        env.delete_distribution(st["world_dist"])
+    for ptr in list(st["live"].keys()):
+        env.free(ptr)
+    st["live"].clear()
+    env.finalize()
+    st["env"] = None
+
+
+def env():
+    e = _state().get("env")
+    if e is None:
+        raise RuntimeError("mlsl_b200 is not initialised: call mlsl_b200.init() first")
+    return e
+
+
+def is_initialized():
+    return _state().get("env") is not None
+
+
+def rank():
+    return env().get_process_idx()
+
+
+def world_size():
+    return env().get_process_count()
+
+
+def is_device():
+    return bool(_state().get("device"))
+
+
+def world_distribution():
+    """Distribution(world, 1): every rank is a data-parallel replica."""
+    st = _state()
+    if st.get("world_dist") is None:
+        st["world_dist"] = env().create_distribution(world_size(), 1)
+    return st["world_dist"]
+
+
+class _CudaMem:
+    """Minimal CUDA-array-interface carrier so torch can wrap library memory without copying."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def tensor_from_address(ptr, shape, dtype, device=None):
+    """Zero-copy torch view of `numel*itemsize` bytes at `ptr` (device memory on the CUDA backend, host otherwise)."""
+    numel = 1
+    for s in shape:
+        numel *= int(s)
+    nbytes = max(numel, 1) * torch.empty((), dtype=dtype).element_size()
+    if is_device():
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        raw = torch.as_tensor(_CudaMem(ptr, nbytes), device=dev)
+    else:
+        buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+        raw = torch.frombuffer(buf, dtype=torch.uint8)
+    return raw.view(dtype)[:numel].view(*shape)
+
+
+def alloc_tensor(shape, dtype=torch.float32, zero=True):
+    """Allocate a tensor in the symmetric heap: peers' kernels read/write it directly (zero-copy collectives)."""
+    if isinstance(shape, int):
+        shape = (shape,)
+    numel = 1
+    for s in shape:
+        numel *= int(s)
+    nbytes = max(numel, 1) * torch.empty((), dtype=dtype).element_size()
+    ptr = env().alloc(nbytes, 256)
+    _state()["live"][ptr] = nbytes
+    t = tensor_from_address(ptr, tuple(shape), dtype)
+    if zero:
+        t.zero_()
+    return t
+
+
+def free_tensor(t):
+    ptr = t.data_ptr()
+    st = _state()
+    if ptr in st["live"]:
+        del st["live"][ptr]
+        env().free(ptr)
+
+
+def _sync_stream():
+    if is_device():
+        env().set_stream(torch.cuda.current_stream().cuda_stream)
+
+
+def _prep(t):
+    if not t.is_contiguous():
+        raise ValueError("mlsl_b200 collectives need contiguous tensors")
+    return t
+
+
+def _dist(distribution):
+    return distribution if distribution is not None else world_distribution()
+
+
+def _group(group):
+    return _GROUPS[group] if isinstance(group, str) else group
+
+
+def allreduce(tensor, op="sum", group="data", scale=1.0, compress=False, out=None, async_op=False, distribution=None):
+    """All-reduce `tensor` (in place unless `out` is given).  `scale` and the optional fp8 `compress`ed transport are
+    fused into the reduction kernel."""
+    _prep(tensor)
+    out = tensor if out is None else _prep(out)
+    _sync_stream()
+    req = _dist(distribution).all_reduce_ex(tensor, out, tensor.numel(), mlsl_dtype(tensor.dtype), _OPS[op],
+                                            _group(group), float(scale),
+                                            CompressionType.QUANTIZATION if compress else CompressionType.NONE)
+    w = Work(env(), req, out, (tensor, out))
+    return w if async_op else w.wait()
+
+
+def reduce_scatter(tensor, out=None, op="sum", group="data", scale=1.0, async_op=False, distribution=None):
+    """tensor: P*n elements; returns rank's n-element reduced shard."""
+    _prep(tensor)
+    d = _dist(distribution)
+    P = d.get_process_count(_group(group))
+    n = tensor.numel() // P
+    if out is None:
+        out = alloc_tensor((n,), tensor.dtype, zero=False) if is_device() else torch.empty(n, dtype=tensor.dtype)
+    _sync_stream()
+    req = d.reduce_scatter(tensor, out, n, mlsl_dtype(tensor.dtype), _OPS[op], _group(group), float(scale))
+    w = Work(env(), req, out, (tensor, out))
+    return w if async_op else w.wait()
+
+
+def allgather(tensor, out=None, group="data", async_op=False, distribution=None):
+    _prep(tensor)
+    d = _dist(distribution)
+    P = d.get_process_count(_group(group))
+    if out is None:
+        out = (alloc_tensor((P * tensor.numel(),), tensor.dtype, zero=False) if is_device()
+               else torch.empty(P * tensor.numel(), dtype=tensor.dtype))
+    _sync_stream()
+    req = d.all_gather(tensor, tensor.numel(), out, mlsl_dtype(tensor.dtype), _group(group))
+    w = Work(env(), req, out, (tensor, out))
+    return w if async_op else w.wait()
+
+
+def alltoall(tensor, out=None, group="data", async_op=False, distribution=None):
+    _prep(tensor)
+    d = _dist(distribution)
+    P = d.get_process_count(_group(group))
+    if out is None:
+        out = alloc_tensor(tuple(tensor.shape), tensor.dtype, zero=False) if is_device() else torch.empty_like(tensor)
+    _sync_stream()
+    req = d.all_to_all(tensor, tensor.numel() // P, out, mlsl_dtype(tensor.dtype), _group(group))
+    w = Work(env(), req, out, (tensor, out))
+    return w if async_op else w.wait()
+
+
+def bcast(tensor, root=0, group="data", async_op=False, distribution=None):
+    _prep(tensor)
+    _sync_stream()
+    req = _dist(distribution).bcast(tensor, tensor.numel(), mlsl_dtype(tensor.dtype), root, _group(group))
+    w = Work(env(), req, tensor, (tensor,))
+    return w if async_op else w.wait()
+
+
+def reduce(tensor, out=None, root=0, op="sum", group="data", async_op=False, distribution=None):
+    _prep(tensor)
+    out = tensor if out is None else out
+    _sync_stream()
+    req = _dist(distribution).reduce(tensor, out, tensor.numel(), mlsl_dtype(tensor.dtype), _OPS[op], root, _group(group))
+    w = Work(env(), req, out, (tensor, out))
+    return w if async_op else w.wait()
+
+
+def barrier(group="global", distribution=None):
+    _sync_stream()
+    _dist(distribution).barrier(_group(group))

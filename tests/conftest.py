@@ -1,0 +1,59 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_library():
+    """Build the in-tree native library once; the tests never run against a Python fallback."""
+    from mlsl_b200 import _lib
+    _lib.build()
+    yield
+
+
+def run_ranks(nranks, fn, backend="host", env=None, timeout=300):
+    """Run fn(rank, mlsl) on `nranks` in-process virtual ranks of the given backend; returns the per-rank results."""
+    import mlsl_b200 as mlsl
+
+    old = {}
+    new = {"MLSL_BACKEND": backend}
+    new.update(env or {})
+    for k, v in new.items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = str(v)
+    try:
+        with mlsl.InprocWorld(nranks) as world:
+            def body(r):
+                mlsl.bind_thread_state()
+                if backend == "cuda":
+                    import torch
+                    torch.cuda.set_device(0)
+                    stream = torch.cuda.Stream()
+                    ctx = torch.cuda.stream(stream)
+                    ctx.__enter__()
+                mlsl.init()
+                try:
+                    return fn(r, mlsl)
+                finally:
+                    if backend == "cuda":
+                        import torch
+                        torch.cuda.current_stream().synchronize()
+                    mlsl.finalize()
+                    if backend == "cuda":
+                        ctx.__exit__(None, None, None)
+            return world.run(body, timeout=timeout)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
