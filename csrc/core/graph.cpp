@@ -75,7 +75,12 @@ DistributionImpl::DistributionImpl(RankContext* c, size_t dParts, size_t mParts,
 
 DistributionImpl::~DistributionImpl() {
   auto drop = [&](ProcessGroup* g) {
-    if (g && g != ctx->global_group && g != ctx->self_group && g != ctx->world_group) ctx->free_group(g);
+    if (!(g && g != ctx->global_group && g != ctx->self_group && g != ctx->world_group)) return;
+    try {   // destructors must not throw: a poisoned / timed-out job is reported, not escalated to terminate()
+      ctx->free_group(g);
+    } catch (const std::exception& e) {
+      MLSLB_LOG(LOG_ERROR, "while releasing a process group: %s", e.what());
+    }
   };
   drop(modelGroup);
   drop(dataGroup);

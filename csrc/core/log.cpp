@@ -85,7 +85,13 @@ void fail(const char* file, int line, const char* func, const char* cond, const 
   base = base ? base + 1 : file;
   char full[2600];
   snprintf(full, sizeof(full), "MLSL assertion failed: (%s) at %s:%d %s: %s", cond, base, line, func, msg);
-  if (assert_throws()) throw Error(full);
+  if (assert_throws()) {
+    if (getenv("MLSL_DEBUG_ERRORS")) {
+      fprintf(stderr, "(r%d) %s\n", g_rank.load(), full);
+      fflush(stderr);
+    }
+    throw Error(full);
+  }
   fprintf(stderr, "(r%d) %s\n", g_rank.load(), full);
   void* bt[32];
   int n = backtrace(bt, 32);

@@ -8,8 +8,15 @@
 
 The object model of the reference (Environment / Session / Distribution / Operation / ...) is in `mlsl_b200.api`.
 """
-from . import _lib, api
-from ._lib import MLSLError
+import os as _os
+
+# Several ranks may share one GPU (in-process loopback used by the tests and smoke()): their kernels spin on each
+# other, so every stream needs its own hardware queue - the default of 8 connections makes unrelated streams
+# serialise behind a waiting kernel.  Must be set before the CUDA context exists; a user setting wins.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+from . import _lib, api  # noqa: E402
+from ._lib import MLSLError  # noqa: E402
 from .api import (CompressionType, DataType, GroupType, InprocWorld, MLSL, OperationType, OptimizerType, PhaseType,
                   ReductionType, cuda_available)
 from .comm import (Work, alloc_tensor, allgather, allreduce, alltoall, barrier, bcast, bind_thread_state, env, finalize,

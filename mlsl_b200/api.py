@@ -64,6 +64,16 @@ def _size_array(values):
     return arr
 
 
+# Installed by mlsl_b200.comm.init(): binds the library to torch's CURRENT stream before every call that starts or
+# waits for communication, so the raw object API is stream-ordered exactly like the tensor-level functions.
+_stream_hook = None
+
+
+def _pre():
+    if _stream_hook is not None:
+        _stream_hook()
+
+
 class _Handle:
     __slots__ = ("handle",)
 
@@ -108,15 +118,19 @@ class Activation(_Handle):
         return self._get("mlsl_activation_get_comm_buf", c_void_p)
 
     def start_comm(self, buf):
+        _pre()
         self._call("mlsl_activation_start_comm", buffer_address(buf))
 
     def wait_comm(self):
+        _pre()
         return self._get("mlsl_activation_wait_comm", c_void_p)
 
     def pack(self, local_buf, comm_buf):
+        _pre()
         self._call("mlsl_activation_pack", buffer_address(local_buf), buffer_address(comm_buf))
 
     def unpack(self, comm_buf, local_buf):
+        _pre()
         self._call("mlsl_activation_unpack", buffer_address(comm_buf), buffer_address(local_buf))
 
 
@@ -130,29 +144,36 @@ class ParameterSet(_Handle):
         return bool(self._get("mlsl_parameter_set_is_distributed_update", c_int))
 
     def start_gradient_comm(self, buf):
+        _pre()
         self._call("mlsl_parameter_set_start_gradient_comm", buffer_address(buf))
 
     def wait_gradient_comm(self):
+        _pre()
         return self._get("mlsl_parameter_set_wait_gradient_comm", c_void_p)
 
     def test_gradient_comm(self):
+        _pre()
         done, ret = c_int(), c_void_p()
         check(_lib.lib().mlsl_parameter_set_test_gradient_comm(self.handle, ctypes.byref(done), ctypes.byref(ret)))
         return ret.value, bool(done.value)
 
     def start_increment_comm(self, buf):
+        _pre()
         self._call("mlsl_parameter_set_start_increment_comm", buffer_address(buf))
 
     def wait_increment_comm(self):
+        _pre()
         return self._get("mlsl_parameter_set_wait_increment_comm", c_void_p)
 
     def start_fused_update(self, grad, param, param_type, master, state1, state2, opt_type=OptimizerType.SGD, lr=0.0,
                            momentum=0.0, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1, grad_scale=1.0):
+        _pre()
         p = _lib.FusedUpdateParams(opt_type, lr, momentum, beta1, beta2, eps, weight_decay, step, grad_scale)
         self._call("mlsl_parameter_set_start_fused_update", buffer_address(grad), buffer_address(param), param_type,
                    buffer_address(master), buffer_address(state1), buffer_address(state2), ctypes.byref(p))
 
     def wait_fused_update(self):
+        _pre()
         self._call("mlsl_parameter_set_wait_fused_update")
 
 
@@ -169,6 +190,7 @@ class Distribution(_Handle):
         return self._get("mlsl_distribution_get_process_idx", c_size_t, group_type)
 
     def _req(self, fname, *args):
+        _pre()
         req = H()
         check(getattr(_lib.lib(), fname)(self.handle, *args, ctypes.byref(req)))
         return req.value
@@ -224,6 +246,7 @@ class Distribution(_Handle):
                          recv_count, data_type, red_type, group_type, scale)
 
     def barrier(self, group_type):
+        _pre()
         self._call("mlsl_distribution_barrier", group_type)
 
 
@@ -415,9 +438,11 @@ class MLSL(_Handle):
         self._call("mlsl_environment_delete_distribution", dist.handle)
 
     def wait(self, req):
+        _pre()
         self._call("mlsl_environment_wait", req)
 
     def test(self, req):
+        _pre()
         return bool(self._get("mlsl_environment_test", c_int, req))
 
     def alloc(self, size, alignment=64):

@@ -78,8 +78,10 @@ def init(wait_mode=None):
     st["device"] = env.is_device_backend()
     st["world_dist"] = None
     st["live"] = {}
+    st["stream"] = None
     if st["device"]:
         env.set_wait_mode(wait_mode or "stream")
+        api._stream_hook = _sync_stream
     return env
 
 
@@ -175,8 +177,12 @@ def free_tensor(t):
 
 
 def _sync_stream():
-    if is_device():
-        env().set_stream(torch.cuda.current_stream().cuda_stream)
+    st = _state()
+    if st.get("device") and st.get("env") is not None:
+        cur = torch.cuda.current_stream().cuda_stream
+        if st.get("stream") != cur:
+            st["env"].set_stream(cur)
+            st["stream"] = cur
 
 
 def _prep(t):

@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # loopback ranks share one GPU (see mlsl_b200/__init__.py)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -42,14 +43,23 @@ def run_ranks(nranks, fn, backend="host", env=None, timeout=300):
                     ctx.__enter__()
                 mlsl.init()
                 try:
-                    return fn(r, mlsl)
-                finally:
-                    if backend == "cuda":
-                        import torch
-                        torch.cuda.current_stream().synchronize()
-                    mlsl.finalize()
-                    if backend == "cuda":
-                        ctx.__exit__(None, None, None)
+                    res = fn(r, mlsl)
+                except BaseException:
+                    import traceback
+                    sys.stderr.write("rank %d failed:\n%s\n" % (r, traceback.format_exc()))
+                    sys.stderr.flush()
+                    try:
+                        mlsl.finalize()
+                    except BaseException:  # noqa: BLE001 - the first error is the one that matters
+                        pass
+                    raise
+                if backend == "cuda":
+                    import torch
+                    torch.cuda.current_stream().synchronize()
+                mlsl.finalize()
+                if backend == "cuda":
+                    ctx.__exit__(None, None, None)
+                return res
             return world.run(body, timeout=timeout)
     finally:
         for k, v in old.items():
