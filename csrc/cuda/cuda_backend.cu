@@ -326,19 +326,16 @@ cudaStream_t CudaBackend::stream_for(int row, int lane) {
 }
 
 // Channel ("endpoint") count as a pure function of the message size: every member must pick the same grid.
+// `bytes` = what ONE rank produces (its slice of an all-reduce, its shard of a reduce-scatter, what it pulls in a
+// gather).  NVLink round trips are ~2-3 us, so the only way to move data fast is to have it all in flight at once:
+// one 16-byte vector per thread until the grid limit is reached, only then more vectors per thread.
 int CudaBackend::pick_channels(size_t bytes) const {
-  int c;
-  if (bytes <= ((size_t)64 << 10)) c = 1;
-  else if (bytes <= ((size_t)256 << 10)) c = 2;
-  else if (bytes <= ((size_t)1 << 20)) c = 4;
-  else if (bytes <= ((size_t)4 << 20)) c = 8;
-  else if (bytes <= ((size_t)16 << 20)) c = 16;
-  else c = 32;
-  if (ctx_->env.num_channels > 0) c = std::min(ctx_->env.num_channels, c * 4);
-  if (ctx_->env.max_short_msg && bytes <= ctx_->env.max_short_msg * 4) c = 1;
-  int cap = std::max(1, (sm_count_ * 2) / std::max(1, ranks_per_device_) / 2);
-  c = std::min(c, std::min(cap, kMaxChannels));
-  return std::max(c, 1);
+  size_t want = ceil_div(std::max<size_t>(bytes, 1), (size_t)kCommThreads * 16);
+  int cmax = ctx_->env.num_channels > 0 ? ctx_->env.num_channels : 96;
+  int cap = std::max(1, sm_count_ / std::max(1, ranks_per_device_));
+  cmax = std::min(cmax, std::min(cap, kMaxChannels));
+  if (ctx_->env.max_short_msg && bytes <= ctx_->env.max_short_msg * 4) return 1;
+  return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)cmax));
 }
 
 DevComm CudaBackend::make_comm(const ProcessGroup& g, int lane) const {
@@ -466,7 +463,15 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   }
   const unsigned long long so = S ? (unsigned long long)(S - slab_) : 0ull;
   const unsigned long long ro = R ? (unsigned long long)(R - slab_) : 0ull;
-  const int ch = pick_channels(r.msg_bytes());
+  // work one rank performs, in output bytes (see pick_channels)
+  size_t work = r.msg_bytes();
+  switch (d.kind) {
+    case OpKind::ALLREDUCE: work = ceil_div(n * es, (size_t)P); break;
+    case OpKind::REDUCE_SCATTER: case OpKind::REDUCE: case OpKind::SCATTER: work = n * es; break;
+    case OpKind::FUSED_UPDATE: work = n * 4; break;
+    default: break;   // gather-like: everything a rank pulls
+  }
+  const int ch = pick_channels(work);
 
   switch (d.kind) {
     case OpKind::BARRIER: MLSLB_CUDA(launch_barrier(dc, s)); break;
@@ -484,7 +489,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
           st->residual_elems = n;
         }
         MLSLB_CUDA(launch_allreduce_quant(dc, so, ro, (unsigned long long)((char*)st->qstage - slab_), st->residual, n,
-                                          d.scale, pick_channels(n), s));
+                                          d.scale, pick_channels(n / 2), s));
       } else {
         // very large messages go out as pipelined chunks (reference MLSL_LARGE_MSG_SIZE_MB / _CHUNKS,
         // src/comm_ep.cpp:645-656) so a higher-priority collective can slip in between them
@@ -495,7 +500,8 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
         size_t per = round_up(ceil_div(n, chunks), 256);
         for (size_t off = 0; off < n; off += per) {
           size_t cnt = std::min(per, n - off);
-          MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, so + off * es, ro + off * es, cnt, d.scale, ch, s));
+          MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, so + off * es, ro + off * es, cnt, d.scale,
+                                      chunks > 1 ? pick_channels(ceil_div(cnt * es, (size_t)P)) : ch, s));
         }
       }
       break;

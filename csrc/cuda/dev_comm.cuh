@@ -89,11 +89,14 @@ __device__ __forceinline__ PadSlot* pad_slot(const DevComm& dc, int owner, int c
   return reinterpret_cast<PadSlot*>(dc.slab[owner] + dc.pad_off) + channel * kMaxDevRanks + writer;
 }
 
-__device__ __forceinline__ bool spin_until(const DevComm& dc, const unsigned long long* flag, unsigned long long want) {
-  if (ld_acquire_sys(flag) >= want) return true;
+// A spin costs one relaxed (volatile-class) system-scope load per iteration; the deadline check only starts after
+// the first miss.
+template <typename Pred>
+__device__ __forceinline__ bool spin_on(const DevComm& dc, const unsigned long long* word, Pred ok) {
+  if (ok(ld_relaxed_sys(word))) return true;
   unsigned long long t0 = globaltimer_ns();
   unsigned spins = 0;
-  while (ld_acquire_sys(flag) < want) {
+  while (!ok(ld_relaxed_sys(word))) {
     if ((++spins & 0x3ff) == 0) {
       if (*(volatile int*)dc.err != 0) return false;               // another CTA / the host already gave up
       if (dc.timeout_ns && globaltimer_ns() - t0 > dc.timeout_ns) {
@@ -105,8 +108,14 @@ __device__ __forceinline__ bool spin_until(const DevComm& dc, const unsigned lon
   return true;
 }
 
-// Opening handshake.  `aux_for_peer(p)` is a per-destination word (the *v collectives publish their send
-// offsets with it).  Returns the ticket; fills `pt` with the peers' buffer addresses.
+constexpr unsigned long long kTagShift = 40;                       // payload: 40 bits (1 TiB of slab / 2^40 elements)
+constexpr unsigned long long kPayloadMask = (1ull << kTagShift) - 1;
+
+// Opening handshake.  Every word a rank publishes carries the low 24 bits of the ticket in its top bits, so each
+// word validates itself: three relaxed stores per peer, no release fence (= no NVLink round trip) on the critical
+// path.  The data the peers are about to read was produced by EARLIER kernels of the publishing rank, i.e. it is
+// already performed in that GPU's L2 before this kernel could start.  `aux_for_peer(p)` is a per-destination word
+// (the *v collectives publish their send offsets with it).  Returns the ticket; fills `pt`.
 template <typename AuxFn>
 __device__ __forceinline__ unsigned long long comm_begin(const DevComm& dc, PeerTable& pt, unsigned long long send_off,
                                                          unsigned long long recv_off, AuxFn aux_for_peer) {
@@ -121,16 +130,18 @@ __device__ __forceinline__ unsigned long long comm_begin(const DevComm& dc, Peer
   __syncthreads();
   const unsigned long long t = pt.ticket;
   if (tid < dc.nranks) {
+    const unsigned long long tag = (t & 0xffffffull) << kTagShift;
     PadSlot* remote = pad_slot(dc, tid, blockIdx.x, dc.me);
-    st_relaxed_sys(&remote->a, send_off);
-    st_relaxed_sys(&remote->b, recv_off);
-    st_relaxed_sys(&remote->aux, aux_for_peer(tid));
-    st_release_sys(&remote->flag, 4 * t);
+    st_relaxed_sys(&remote->a, tag | send_off);
+    st_relaxed_sys(&remote->b, tag | recv_off);
+    st_relaxed_sys(&remote->aux, tag | (aux_for_peer(tid) & kPayloadMask));
     PadSlot* local = pad_slot(dc, dc.me, blockIdx.x, tid);
-    if (spin_until(dc, &local->flag, 4 * t)) {
-      pt.send[tid] = dc.slab[tid] + ld_relaxed_sys(&local->a);
-      pt.recv[tid] = dc.slab[tid] + ld_relaxed_sys(&local->b);
-      pt.aux[tid] = ld_relaxed_sys(&local->aux);
+    auto fresh = [tag](unsigned long long w) { return (w & ~kPayloadMask) == tag; };
+    const bool ok = spin_on(dc, &local->a, fresh) && spin_on(dc, &local->b, fresh) && spin_on(dc, &local->aux, fresh);
+    if (ok) {
+      pt.send[tid] = dc.slab[tid] + (ld_relaxed_sys(&local->a) & kPayloadMask);
+      pt.recv[tid] = dc.slab[tid] + (ld_relaxed_sys(&local->b) & kPayloadMask);
+      pt.aux[tid] = ld_relaxed_sys(&local->aux) & kPayloadMask;
     } else {   // peer never showed up: keep every address valid (results are garbage, the host reports the error)
       pt.failed = 1;
       pt.send[tid] = dc.slab[dc.me] + send_off;
@@ -146,16 +157,22 @@ struct NoAux {
   __device__ __forceinline__ unsigned long long operator()(int) const { return 0ull; }
 };
 
-// Handshake k (1..3) between the same channel of every member.  `published_remote_writes`: this CTA stored into
-// peer memory since the last handshake, so the writes must be performed before the flag becomes visible.
+// Handshake k (1..3) between the same channel of every member.  `published_writes`: this CTA stored data a peer
+// will read after the handshake (into peer memory, or into local memory a peer pulls from), so those writes must be
+// performed system-wide before the flag can be seen: bar.sync (CTA-scope happens-before) + fence.sys by the
+// signalling thread (cumulative) + relaxed flag store.
 __device__ __forceinline__ void comm_sync(const DevComm& dc, PeerTable& pt, unsigned long long t, int k,
-                                          bool published_remote_writes) {
+                                          bool published_writes) {
   __syncthreads();
   const int tid = threadIdx.x;
   if (tid < dc.nranks) {
-    if (published_remote_writes) __threadfence_system();
-    st_release_sys(&pad_slot(dc, tid, blockIdx.x, dc.me)->flag, 4 * t + k);
-    if (!spin_until(dc, &pad_slot(dc, dc.me, blockIdx.x, tid)->flag, 4 * t + k)) pt.failed = 1;
+    if (published_writes) __threadfence_system();
+    const unsigned long long want = 4 * t + k;
+    st_relaxed_sys(&pad_slot(dc, tid, blockIdx.x, dc.me)->flag, want);
+    if (!spin_on(dc, &pad_slot(dc, dc.me, blockIdx.x, tid)->flag, [want](unsigned long long w) { return w >= want; }))
+      pt.failed = 1;
+    // order the data reads that follow after the flag observation
+    __threadfence_system();
   }
   __syncthreads();
 }

@@ -267,17 +267,24 @@ cudaError_t launch_pull_copy(const DevComm& dc, const CopyPlan& plan, unsigned l
 template <typename T, typename Op>
 static cudaError_t launch_ar_t(const DevComm& dc, unsigned long long so, unsigned long long ro, size_t count,
                                float scale, int channels, cudaStream_t s) {
-  // small messages: one vector per thread keeps the critical path short; big ones: more loads in flight
-  if (count * sizeof(T) <= (size_t)(1 << 20))
+  // vectors each thread has to move: keep them all in flight (unroll) up to 4 per pass
+  const size_t per_thread = (count * sizeof(T) / (size_t)dc.nranks) / ((size_t)channels * kCommThreads * 16);
+  if (per_thread <= 1)
     k_allreduce<T, Op, 1><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
-  else
+  else if (per_thread <= 3)
     k_allreduce<T, Op, 2><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+  else
+    k_allreduce<T, Op, 4><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
   return cudaGetLastError();
 }
 template <typename T, typename Op>
 static cudaError_t launch_rp_t(const DevComm& dc, unsigned long long so, unsigned long long ro, size_t base,
                                size_t count, float scale, bool active, int channels, cudaStream_t s) {
-  k_reduce_pull<T, Op, 2><<<channels, kCommThreads, 0, s>>>(dc, so, ro, base, count, scale, active ? 1 : 0);
+  const size_t per_thread = (count * sizeof(T)) / ((size_t)channels * kCommThreads * 16);
+  if (per_thread <= 1)
+    k_reduce_pull<T, Op, 1><<<channels, kCommThreads, 0, s>>>(dc, so, ro, base, count, scale, active ? 1 : 0);
+  else
+    k_reduce_pull<T, Op, 4><<<channels, kCommThreads, 0, s>>>(dc, so, ro, base, count, scale, active ? 1 : 0);
   return cudaGetLastError();
 }
 
