@@ -1,0 +1,75 @@
+"""Reference arm of bench.py: the UNMODIFIED intel/MLSL (baseline/_ref, built by baseline/install_ref.sh) running the
+same metric - fp32 SUM all-reduce bus bandwidth of the headline message through its own public API
+(Environment::Alloc + Distribution::AllReduce + Environment::Wait, stock "process" mode, N MPI ranks on this node
+launched by its bundled mpiexec.hydra).  The reference is a CPU library: its buffers live in host memory, so the
+end-to-end number equals the measured one (no device copies exist on that path).
+"""
+import json
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, "_ref")
+
+
+def _env():
+    env = dict(os.environ)
+    mp = os.path.join(REF, "mpirt")
+    env["I_MPI_ROOT"] = mp
+    env["MLSL_ROOT"] = REF
+    env["PATH"] = os.path.join(mp, "bin") + os.pathsep + env.get("PATH", "")
+    env["LD_LIBRARY_PATH"] = os.pathsep.join([os.path.join(REF, "intel64", "lib"), os.path.join(mp, "lib"),
+                                              env.get("LD_LIBRARY_PATH", "")])
+    # torchrun's variables must not leak into the MPI ranks
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "MLSL_BACKEND", "MLSL_JOB_ID"):
+        env.pop(k, None)
+    env.setdefault("I_MPI_FABRICS", "shm")
+    return env
+
+
+def _run(nranks, minb, maxb, iters, warm, factor, timeout):
+    exe = os.path.join(REF, "bin", "ref_allreduce_bench")
+    if not os.path.exists(exe):
+        raise RuntimeError("baseline/_ref is not installed (run baseline/install_ref.sh)")
+    cmd = [os.path.join(REF, "mpirt", "bin", "mpiexec.hydra"), "-n", str(nranks), exe, str(minb), str(maxb), str(iters),
+           str(warm), str(factor)]
+    res = subprocess.run(cmd, env=_env(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    rows = []
+    for line in res.stdout.splitlines():
+        line = line.strip()
+        if line.startswith("{"):
+            rows.append(json.loads(line))
+    if res.returncode != 0 or not rows:
+        raise RuntimeError("reference run failed rc=%d: %s" % (res.returncode, (res.stderr or res.stdout)[-300:]))
+    return rows
+
+
+def run(n_gpus, steps, warmup, headline_bytes):
+    n = max(int(n_gpus), 1)
+    head = _run(n, headline_bytes, headline_bytes, steps, warmup, 4, timeout=3000)[-1]
+    sweep = []
+    try:
+        for r in _run(n, 1024, min(headline_bytes, 1 << 24), 5, 2, 16, timeout=600):
+            sweep.append({"bytes": r["bytes"], "us": r["us"], "busbw_GBps": r["busbw_GBps"]})
+    except Exception:  # noqa: BLE001 - the sweep is informative only
+        pass
+    value = head["busbw_GBps"] if n > 1 else head["algbw_GBps"]
+    return {
+        "metric": "allreduce_busbw_GBps" if n > 1 else "allreduce_algbw_GBps_single_gpu",
+        "value": round(value, 4), "unit": "GB/s", "n_gpus": n, "steps": steps, "warmup": warmup,
+        "ms_per_step": round(head["us"] / 1e3, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic", "impl": "reference",
+        "config": {"model": "allreduce fp32 SUM, %d MiB per rank, in place" % (headline_bytes >> 20),
+                   "parallelism": "dp%d" % n, "message_bytes": headline_bytes,
+                   "api": "MLSL::Distribution::AllReduce + Environment::Wait (intel/MLSL process mode, Intel MPI shm)",
+                   "device": "CPU (the reference has no GPU path); host-timed, max over ranks",
+                   "launcher": "baseline/_ref/mpirt/bin/mpiexec.hydra -n %d" % n},
+        "e2e": {"value": round(value, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "note": "buffers are host resident: the measured value already is end to end"},
+        "gpu_launches": 0, "sweep": sweep,
+    }
+
+
+if __name__ == "__main__":
+    import sys
+    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 2, 3, 1, 1 << 24)))

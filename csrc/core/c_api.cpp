@@ -288,6 +288,7 @@ int mlsl_environment_set_stream(mlsl_environment e, void* s) { C_GUARD(H<Environ
 int mlsl_environment_get_stream(mlsl_environment e, void** s) { C_GUARD(*need(s) = H<Environment>(e)->GetStream()) }
 int mlsl_environment_set_wait_mode(mlsl_environment e, const char* m) { C_GUARD(H<Environment>(e)->SetWaitMode(m)) }
 int mlsl_environment_get_backend_name(mlsl_environment e, const char** n) { C_GUARD(*need(n) = H<Environment>(e)->GetBackendName()) }
+int mlsl_environment_describe_backend(mlsl_environment e, const char** n) { C_GUARD(*need(n) = H<Environment>(e)->DescribeBackend()) }
 int mlsl_environment_is_device_backend(mlsl_environment e, int* v) { C_GUARD(*need(v) = H<Environment>(e)->IsDeviceBackend() ? 1 : 0) }
 int mlsl_environment_suspend_servers(mlsl_environment e) { C_GUARD(H<Environment>(e)->SuspendServers()) }
 int mlsl_environment_resume_servers(mlsl_environment e) { C_GUARD(H<Environment>(e)->ResumeServers()) }

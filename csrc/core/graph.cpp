@@ -970,6 +970,11 @@ void Environment::SetWaitMode(const char* mode) {
   live(this)->backend->set_wait_mode(!strcmp(mode, "stream"));
 }
 const char* Environment::GetBackendName() { return live(this)->backend->name(); }
+const char* Environment::DescribeBackend() {
+  auto e = SELF(EnvironmentImpl);
+  e->backendDesc = live(this)->backend->describe();
+  return e->backendDesc.c_str();
+}
 bool Environment::IsDeviceBackend() { return live(this)->backend->is_device(); }
 void Environment::SuspendServers() { live(this)->progress->suspend(); }
 void Environment::ResumeServers() { live(this)->progress->resume(); }

@@ -220,7 +220,7 @@ class EnvironmentImpl : public Environment {
   explicit EnvironmentImpl(RankContext* c) : ctx(c) {}
   RankContext* ctx;
   QuantParams* quantView = nullptr;     // heap copy handed back by GetQuantizationParams
-  std::string waitMode;
+  std::string waitMode, backendDesc;
 };
 
 EnvironmentImpl* env_of(RankContext* ctx);

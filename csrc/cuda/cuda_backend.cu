@@ -23,6 +23,7 @@
 #include "core/runtime.hpp"
 #include "core/sysinfo.hpp"
 #include "cuda/kernels.hpp"
+#include "cuda/vmm.hpp"
 
 namespace mlslb {
 
@@ -188,15 +189,17 @@ class CudaBackend final : public Backend {
       if (s) cudaStreamDestroy(s);
     if (aux_stream_) cudaStreamDestroy(aux_stream_);
     if (own_user_stream_) cudaStreamDestroy(own_user_stream_);
-    if (slab_) cudaFree(slab_);
+    if (vmm_.ok) vmm_slab_destroy(vmm_);
+    else if (slab_) cudaFree(slab_);
     if (err_host_) cudaFreeHost((void*)err_host_);
     slab_ = nullptr;
   }
 
   std::string describe() const override {
     char buf[256];
-    snprintf(buf, sizeof(buf), "cuda peer-memory backend (device %d, %d SMs, slab %.1f GiB, %s, ranks/device %d)", device_,
-             sm_count_, slab_bytes_ / 1073741824.0, inproc_ ? "in-process ranks" : "CUDA IPC", ranks_per_device_);
+    snprintf(buf, sizeof(buf), "cuda peer-memory backend (device %d, %d SMs, slab %.1f GiB, %s%s, ranks/device %d)", device_,
+             sm_count_, slab_bytes_ / 1073741824.0, inproc_ ? "in-process ranks" : (vmm_.ok ? "VMM fd-shared" : "CUDA IPC"),
+             mc_ ? " + NVLS multicast" : "", ranks_per_device_);
     return buf;
   }
 
@@ -212,6 +215,8 @@ class CudaBackend final : public Backend {
   std::vector<cudaStream_t> streams_;
   cudaStream_t aux_stream_ = nullptr, user_stream_ = nullptr, own_user_stream_ = nullptr;
   bool stream_wait_ = false, inline_stream_ = false;
+  VmmSlab vmm_;
+  char* mc_ = nullptr;
   volatile int* err_host_ = nullptr;
   int* err_dev_ = nullptr;
   std::mutex mu_;
@@ -248,9 +253,27 @@ void CudaBackend::init() {
     MLSLB_ASSERT(slab_bytes_ < fr, "MLSL_HEAP_SIZE_GB=%.2f does not fit in free device memory (%.2f GiB)",
                  ctx_->env.heap_size_gb, fr / 1073741824.0);
   }
-  cudaError_t e = cudaMalloc((void**)&slab_, slab_bytes_);
-  MLSLB_ASSERT(e == cudaSuccess, "cudaMalloc of the %.2f GiB symmetric heap failed: %s (lower MLSL_HEAP_SIZE_GB)",
-               slab_bytes_ / 1073741824.0, cudaGetErrorString(e));
+  // Preferred: VMM slab (file-descriptor shared, NVLS multicast capable).  Fallback: cudaMalloc + CUDA IPC.
+  {
+    const char* mode = getenv("MLSL_SLAB");
+    bool want_vmm = !inproc_ && b->size() > 1 && !(mode && !strcmp(mode, "ipc"));
+    if (want_vmm) {
+      vmm_ = vmm_slab_create(b, device_, slab_bytes_, ctx_->env.use_nvls && b->size() <= kMaxDevRanks);
+      if (vmm_.ok) {
+        slab_ = vmm_.local;
+        slab_bytes_ = vmm_.bytes;
+        mc_ = vmm_.mc;
+      }
+      if (b->rank() == 0)
+        MLSLB_LOG(LOG_INFO, "symmetric heap: %s, NVLS multicast: %s%s%s", vmm_.ok ? "VMM (POSIX fd shared)" : "CUDA IPC",
+                  mc_ ? "yes" : "no", vmm_.why.empty() ? "" : " - ", vmm_.why.c_str());
+    }
+  }
+  if (!vmm_.ok) {
+    cudaError_t e = cudaMalloc((void**)&slab_, slab_bytes_);
+    MLSLB_ASSERT(e == cudaSuccess, "cudaMalloc of the %.2f GiB symmetric heap failed: %s (lower MLSL_HEAP_SIZE_GB)",
+                 slab_bytes_ / 1073741824.0, cudaGetErrorString(e));
+  }
   MLSLB_CUDA(cudaMemset(slab_, 0, kHeaderBytes));
   MLSLB_CUDA(cudaDeviceSynchronize());
   heap_.reset(kHeaderBytes, slab_bytes_ - kHeaderBytes);
@@ -272,7 +295,7 @@ void CudaBackend::init() {
   mine.ptr = (unsigned long long)slab_;
   mine.pid = (int)getpid();
   mine.device = device_;
-  if (!inproc_) MLSLB_CUDA(cudaIpcGetMemHandle(&mine.handle, slab_));
+  if (!inproc_ && !vmm_.ok) MLSLB_CUDA(cudaIpcGetMemHandle(&mine.handle, slab_));
   std::vector<PeerInfo> all(W);
   b->allgather(&mine, all.data(), sizeof(PeerInfo));
   peer_slab_.assign(W, nullptr);
@@ -280,6 +303,8 @@ void CudaBackend::init() {
   for (int p = 0; p < W; ++p) {
     if (p == b->rank()) {
       peer_slab_[p] = slab_;
+    } else if (vmm_.ok) {
+      peer_slab_[p] = vmm_.peers[p];
     } else if (all[p].pid == mine.pid) {
       peer_slab_[p] = (char*)all[p].ptr;
       if (all[p].device != device_) {
@@ -348,7 +373,13 @@ DevComm CudaBackend::make_comm(const ProcessGroup& g, int lane) const {
   dc.timeout_ns = ctx_->env.watchdog_sec > 0 ? (unsigned long long)ctx_->env.watchdog_sec * 1000000000ull : 0ull;
   dc.err = err_dev_;
   for (int i = 0; i < g.size(); ++i) dc.slab[i] = peer_slab_[g.members[i]];
+  // NVLS only for groups spanning every rank in world order (the multicast object covers exactly those devices)
   dc.mc = nullptr;
+  if (mc_ && g.size() == ctx_->world) {
+    bool ident = true;
+    for (int i = 0; i < g.size(); ++i) ident &= g.members[i] == i;
+    if (ident) dc.mc = mc_;
+  }
   return dc;
 }
 

@@ -7,6 +7,8 @@
 // endpoints (a message is split across them).
 #include "cuda/kernels.hpp"
 
+#include <type_traits>
+
 namespace mlslb {
 
 // ------------------------------------------------------------------------------------------------------------
@@ -29,7 +31,50 @@ cudaError_t launch_barrier(const DevComm& dc, cudaStream_t s) {
 // receive buffer.  Reads and writes of one 16-byte chunk are done by the same thread, so in-place operation needs
 // no extra barrier: 2 handshakes per collective, NVLink busy in both directions for the whole kernel.
 // ------------------------------------------------------------------------------------------------------------
-template <typename T, typename Op, int U>
+// NVLS flavour (kNvls): when every member passed the SAME slab offsets (symmetric buffers) the pull + reduce of a
+// 16-byte chunk is a single `multimem.ld_reduce` (the NVSwitch adds the N copies) and the push to all peers a single
+// `multimem.st` (the switch replicates it): 1 load + 1 store per chunk instead of N + N, and each GPU's links carry
+// ~S(1+1/N) bytes per direction instead of 2S(N-1)/N.
+template <typename T> struct Multimem;   // ld_reduce(.add) / st of one 16-byte vector through a multicast address
+template <> struct Multimem<float> {
+  __device__ __forceinline__ static uint4 ld_reduce_add(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ static void st(void* p, const uint4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+};
+template <> struct Multimem<__nv_bfloat16> {
+  __device__ __forceinline__ static uint4 ld_reduce_add(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ static void st(void* p, const uint4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+};
+template <> struct Multimem<__half> {
+  __device__ __forceinline__ static uint4 ld_reduce_add(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ static void st(void* p, const uint4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+};
+template <typename T> struct HasMultimem { static constexpr bool value = false; };
+template <> struct HasMultimem<float> { static constexpr bool value = true; };
+template <> struct HasMultimem<__nv_bfloat16> { static constexpr bool value = true; };
+template <> struct HasMultimem<__half> { static constexpr bool value = true; };
+
+template <typename T, typename Op, int U, bool kNvls>
 __global__ void __launch_bounds__(kCommThreads) k_allreduce(DevComm dc, unsigned long long send_off,
                                                             unsigned long long recv_off, size_t count, float scale) {
   using VT = VecTraits<T>;
@@ -37,12 +82,18 @@ __global__ void __launch_bounds__(kCommThreads) k_allreduce(DevComm dc, unsigned
   constexpr int N = VT::N;
   __shared__ PeerTable pt;
   __shared__ int s_aligned;
+  __shared__ int s_symmetric;
   const unsigned long long t = comm_begin(dc, pt, send_off, recv_off, NoAux());
   const int P = dc.nranks, me = dc.me;
   if (threadIdx.x == 0) {
     unsigned long long bits = 0;
-    for (int p = 0; p < P; ++p) bits |= (unsigned long long)pt.send[p] | (unsigned long long)pt.recv[p];
+    int sym = 1;
+    for (int p = 0; p < P; ++p) {
+      bits |= (unsigned long long)pt.send[p] | (unsigned long long)pt.recv[p];
+      sym &= (pt.send[p] - dc.slab[p]) == (long long)send_off && (pt.recv[p] - dc.slab[p]) == (long long)recv_off;
+    }
     s_aligned = (bits & 15ull) == 0;
+    s_symmetric = sym && dc.mc != nullptr && !pt.failed;
   }
   __syncthreads();
   // slice of this rank, in elements (vector aligned so that every slice but the last is a whole number of vectors)
@@ -52,6 +103,47 @@ __global__ void __launch_bounds__(kCommThreads) k_allreduce(DevComm dc, unsigned
   const size_t n = hi - lo;
   const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
   const bool do_scale = scale != 1.0f;
+  if constexpr (kNvls && HasMultimem<T>::value) {
+    if (s_aligned && s_symmetric) {
+      const size_t nvec = n / N;
+      const char* msrc = dc.mc + send_off + lo * sizeof(T);
+      char* mdst = dc.mc + recv_off + lo * sizeof(T);
+      for (size_t base = gtid; base < nvec; base += gsz * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t i = base + (size_t)u * gsz;
+          if (i < nvec) v[u] = Multimem<T>::ld_reduce_add(msrc + i * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t i = base + (size_t)u * gsz;
+          if (i < nvec) {
+            if (do_scale) {
+              Acc a[N];
+              VT::unpack(v[u], a);
+#pragma unroll
+              for (int k = 0; k < N; ++k) a[k] = VT::scale(a[k], scale);
+              v[u] = VT::pack(a);
+            }
+            Multimem<T>::st(mdst + i * 16, v[u]);
+          }
+        }
+      }
+      for (size_t i = nvec * N + gtid; i < n; i += gsz) {   // tail elements of the last slice: plain peer access
+        Acc a = VT::load1(pt.send[me] + (lo + i) * sizeof(T));
+        for (int q = 1; q < P; ++q) {
+          int p = me + q;
+          if (p >= P) p -= P;
+          a = Op::apply(a, VT::load1(pt.send[p] + (lo + i) * sizeof(T)));
+        }
+        if (do_scale) a = VT::scale(a, scale);
+        for (int p = 0; p < P; ++p) VT::store1(pt.recv[p] + (lo + i) * sizeof(T), a);
+      }
+      comm_sync(dc, pt, t, 1, true);
+      return;
+    }
+  }
   if (s_aligned) {
     const size_t nvec = n / N;
     for (size_t base = gtid; base < nvec; base += gsz * U) {
@@ -269,12 +361,22 @@ static cudaError_t launch_ar_t(const DevComm& dc, unsigned long long so, unsigne
                                float scale, int channels, cudaStream_t s) {
   // vectors each thread has to move: keep them all in flight (unroll) up to 4 per pass
   const size_t per_thread = (count * sizeof(T) / (size_t)dc.nranks) / ((size_t)channels * kCommThreads * 16);
+  constexpr bool kCanNvls = HasMultimem<T>::value && std::is_same<Op, OpSum>::value;
+  if (kCanNvls && dc.mc != nullptr) {
+    if (per_thread <= 1)
+      k_allreduce<T, Op, 1, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+    else if (per_thread <= 3)
+      k_allreduce<T, Op, 2, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+    else
+      k_allreduce<T, Op, 4, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+    return cudaGetLastError();
+  }
   if (per_thread <= 1)
-    k_allreduce<T, Op, 1><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+    k_allreduce<T, Op, 1, false><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
   else if (per_thread <= 3)
-    k_allreduce<T, Op, 2><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+    k_allreduce<T, Op, 2, false><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
   else
-    k_allreduce<T, Op, 4><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+    k_allreduce<T, Op, 4, false><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
   return cudaGetLastError();
 }
 template <typename T, typename Op>

@@ -216,6 +216,7 @@ int mlsl_environment_set_stream(mlsl_environment env, void* cuda_stream);
 int mlsl_environment_get_stream(mlsl_environment env, void** cuda_stream);
 int mlsl_environment_set_wait_mode(mlsl_environment env, const char* mode);
 int mlsl_environment_get_backend_name(mlsl_environment env, const char** name);
+int mlsl_environment_describe_backend(mlsl_environment env, const char** text);
 int mlsl_environment_is_device_backend(mlsl_environment env, int* is_device);
 int mlsl_environment_suspend_servers(mlsl_environment env);
 int mlsl_environment_resume_servers(mlsl_environment env);

@@ -291,6 +291,7 @@ class Environment {
   void* GetStream();
   void SetWaitMode(const char* mode);   // "host" | "stream"
   const char* GetBackendName();         // "host" | "cuda"
+  const char* DescribeBackend();        // human-readable: device, heap kind, NVLS availability
   bool IsDeviceBackend();
   // Park / resume the background progress threads (reference EPLIB_suspend / EPLIB_execute).
   void SuspendServers();

@@ -111,6 +111,7 @@ def _declare(l):
         "mlsl_environment_set_wait_mode": [H, c_char_p],
         "mlsl_environment_get_backend_name": [H, P(c_char_p)],
         "mlsl_environment_is_device_backend": [H, P(c_int)],
+        "mlsl_environment_describe_backend": [H, P(c_char_p)],
         "mlsl_environment_suspend_servers": [H],
         "mlsl_environment_resume_servers": [H],
         "mlsl_distribution_get_process_count": [H, c_int, P(c_size_t)],

@@ -477,6 +477,9 @@ class MLSL(_Handle):
     def get_backend_name(self):
         return self._get("mlsl_environment_get_backend_name", ctypes.c_char_p).decode()
 
+    def describe_backend(self):
+        return self._get("mlsl_environment_describe_backend", ctypes.c_char_p).decode()
+
     def is_device_backend(self):
         return bool(self._get("mlsl_environment_is_device_backend", c_int))
 
