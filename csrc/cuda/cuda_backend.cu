@@ -375,7 +375,10 @@ DevComm CudaBackend::make_comm(const ProcessGroup& g, int lane) const {
   for (int i = 0; i < g.size(); ++i) dc.slab[i] = peer_slab_[g.members[i]];
   // NVLS only for groups spanning every rank in world order (the multicast object covers exactly those devices)
   dc.mc = nullptr;
-  if (mc_ && g.size() == ctx_->world) {
+  // (and only from 4 ranks up: per direction NVLS moves S(1+1/N) bytes, the peer-to-peer kernel 2S(N-1)/N)
+  int nvls_min = 4;
+  if (const char* v = getenv("MLSL_NVLS_MIN_RANKS")) nvls_min = atoi(v);
+  if (mc_ && g.size() == ctx_->world && g.size() >= nvls_min) {
     bool ident = true;
     for (int i = 0; i < g.size(); ++i) ident &= g.members[i] == i;
     if (ident) dc.mc = mc_;

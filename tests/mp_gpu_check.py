@@ -1,0 +1,92 @@
+"""Multi-process, multi-GPU correctness check (one rank per GPU, launched by torchrun):
+    python -m torch.distributed.run --nproc-per-node N tests/mp_gpu_check.py
+Every collective over real NVLink peers (CUDA IPC / VMM mappings, NVLS multicast when N >= 4) against a reference
+computed from the deterministic per-rank inputs.  Prints one PASSED/FAILED line per check on rank 0; exit code 1 on failure."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mlsl_b200 as mlsl  # noqa: E402
+
+
+def make(rank, n, dtype, seed=0):
+    g = torch.Generator().manual_seed(999 + 13 * rank + seed)
+    if dtype == torch.int32:
+        return torch.randint(0, 9, (n,), generator=g, dtype=torch.int32)
+    return (torch.rand(n, generator=g) * 4 - 2).to(dtype)
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MLSL_HEAP_SIZE_GB", "2")
+    os.environ.setdefault("MLSL_WATCHDOG_SEC", "30")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    env = mlsl.init()
+    r, W = mlsl.rank(), mlsl.world_size()
+    fails = []
+
+    def check(name, ok):
+        t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+        mlsl.allreduce(t, op="min")
+        torch.cuda.synchronize()
+        good = bool(t.item() > 0.5)
+        if r == 0:
+            print("%s: %s" % (name, "PASSED" if good else "FAILED"), flush=True)
+        if not good:
+            fails.append(name)
+
+    if r == 0:
+        print("backend:", env.describe_backend(), flush=True)
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 5e-2), (torch.float16, 2e-2), (torch.float64, 1e-12), (torch.int32, 0)):
+        for n in (1, 1000, 262147, 8 * 1024 * 1024 + 5):
+            x = mlsl.alloc_tensor(n, dtype)
+            x.copy_(make(r, n, dtype))
+            y = mlsl.alloc_tensor(n, dtype)
+            mlsl.allreduce(x, out=y, scale=0.5 if dtype.is_floating_point else 1.0)
+            ref = sum(make(p, n, dtype).double() for p in range(W)) * (0.5 if dtype.is_floating_point else 1.0)
+            torch.cuda.synchronize()
+            err = (y.double().cpu() - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+            check("allreduce %s n=%d (err %.2e)" % (str(dtype).split(".")[-1], n, err), err <= tol)
+            mlsl.allreduce(x)   # in place
+            torch.cuda.synchronize()
+            err = (x.double().cpu() - ref / (0.5 if dtype.is_floating_point else 1.0)).abs().max().item() / max(1.0, ref.abs().max().item())
+            check("allreduce in-place %s n=%d" % (str(dtype).split(".")[-1], n), err <= 2 * tol)
+            mlsl.free_tensor(x)
+            mlsl.free_tensor(y)
+    n = 100003
+    x = mlsl.alloc_tensor(n * W, torch.float32)
+    x.copy_(make(r, n * W, torch.float32))
+    shard = mlsl.reduce_scatter(x)
+    full = mlsl.allgather(shard)
+    ref = sum(make(p, n * W, torch.float32).double() for p in range(W)).float()
+    torch.cuda.synchronize()
+    check("reduce_scatter", torch.allclose(shard.cpu(), ref[r * n:(r + 1) * n], rtol=1e-5, atol=1e-5))
+    check("allgather", torch.allclose(full.cpu(), ref, rtol=1e-5, atol=1e-5))
+    a = (torch.arange(W * n, dtype=torch.float32) + 1000 * r).cuda()
+    a2a = mlsl.alltoall(a)
+    torch.cuda.synchronize()
+    ok = all(torch.equal(a2a[p * n:(p + 1) * n].cpu(), (torch.arange(W * n, dtype=torch.float32) + 1000 * p)[r * n:(r + 1) * n]) for p in range(W))
+    check("alltoall", ok)
+    b = (make(W - 1, n, torch.float32) if r == W - 1 else torch.zeros(n)).cuda()
+    mlsl.bcast(b, root=W - 1)
+    torch.cuda.synchronize()
+    check("bcast", torch.equal(b.cpu(), make(W - 1, n, torch.float32)))
+    q = mlsl.alloc_tensor(n, torch.float32)
+    src = mlsl.alloc_tensor(n, torch.float32)
+    src.copy_(make(r, n, torch.float32))
+    mlsl.allreduce(src, out=q, compress=True)
+    refq = sum(make(p, n, torch.float32).double() for p in range(W)).float()
+    torch.cuda.synchronize()
+    check("allreduce fp8-compressed", ((q.cpu() - refq).abs().max() / refq.abs().max()).item() < 0.1)
+    mlsl.finalize()
+    if r == 0:
+        print("mp_gpu_check: %s" % ("ALL PASSED" if not fails else "FAILED: %s" % fails), flush=True)
+    sys.exit(1 if fails else 0)
+
+
+if __name__ == "__main__":
+    main()
