@@ -35,6 +35,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bytes", type=int, default=HEADLINE_BYTES, help="headline message size per rank")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--sweep-sizes", default="", help="comma separated byte sizes instead of the default 1 KiB..1 GiB x4 ladder")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--nccl", action="store_true", help="also time torch.distributed (NCCL) all_reduce for comparison")
     ap.add_argument("--compress", action="store_true", help="headline through the fp8-compressed transport")
@@ -179,6 +180,8 @@ def run_ours(args):
         sizes = [1 << k for k in range(10, 31, 2)]
         if S not in sizes:
             sizes.append(S)
+        if args.sweep_sizes:
+            sizes = [int(v) for v in args.sweep_sizes.split(",")]
         for b in sorted(sizes):
             if b > S:
                 continue

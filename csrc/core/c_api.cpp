@@ -120,6 +120,7 @@ int mlsl_parameter_set_start_fused_update(mlsl_parameter_set p, void* grad, void
           f.grad_scale = o->grad_scale; H<ParameterSet>(p)->StartFusedUpdate(grad, param, DT(pt), master, s1, s2, &f))
 }
 int mlsl_parameter_set_wait_fused_update(mlsl_parameter_set p) { C_GUARD(H<ParameterSet>(p)->WaitFusedUpdate()) }
+int mlsl_parameter_set_set_gradient_scale(mlsl_parameter_set p, float scale) { C_GUARD(H<ParameterSet>(p)->SetGradientScale(scale)) }
 
 // ---- Distribution ----
 int mlsl_distribution_get_process_count(mlsl_distribution d, mlsl_group_type g, size_t* v) { C_GUARD(*need(v) = H<Distribution>(d)->GetProcessCount(GT(g))) }

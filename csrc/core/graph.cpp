@@ -569,6 +569,10 @@ void ParameterSet::StartFusedUpdate(void* grad, void* param, DataType paramType,
   SELF(ParameterSetImpl)->start_fused(grad, param, paramType, master, state1, state2, opt);
 }
 void ParameterSet::WaitFusedUpdate() { SELF(ParameterSetImpl)->wait_fused(); }
+void ParameterSet::SetGradientScale(float scale) {
+  auto p = SELF(ParameterSetImpl);
+  if (p->gradReq) p->gradReq->desc.scale = scale;
+}
 
 // ---- Distribution ----------------------------------------------------------------------------------------------
 size_t Distribution::GetProcessIdx(GroupType gt) { return (size_t)SELF(DistributionImpl)->group(gt)->idx; }

@@ -240,7 +240,7 @@ void HostBackend::execute(CommRequest& r) {
   const size_t dt = dtype_size(d.dtype);
   const size_t n = d.count;
   // ---- single-rank groups: local semantics only --------------------------------------------------------
-  if (!gp || gp->size() <= 1) {
+  if ((!gp || gp->size() <= 1) && d.kind != OpKind::FUSED_UPDATE) {
     switch (d.kind) {
       case OpKind::ALLREDUCE:
       case OpKind::REDUCE:
@@ -270,7 +270,8 @@ void HostBackend::execute(CommRequest& r) {
   const ProcessGroup& g = *gp;
   const int P = g.size();
   const int me = g.idx;
-  const int prow = g.row * 2 + r.lane;
+  // single-rank groups have no signal row of their own: they use the reserved last one (only this rank touches it)
+  const int prow = (g.row >= 0 ? g.row : kMaxGroupRows - 1) * 2 + r.lane;
   const uint64_t t = r.group_seq;
   HostPub* mine = pub(rank_, prow);
 

@@ -419,7 +419,7 @@ ProcessGroup* RankContext::create_group_by_color(ProcessGroup* parent, int color
     g->row = -1;
   } else {
     int row = -1;
-    for (int r = 1; r < kMaxGroupRows; ++r)
+    for (int r = 1; r < kMaxGroupRows - 1; ++r)   // the last row is reserved for single-rank (self) groups
       if (!(used & (1ull << r))) {
         row = r;
         break;
@@ -595,11 +595,13 @@ void context_init(RankContext* ctx) {
   if (ns < 0) ns = ctx->backend->is_device() ? 0 : (ctx->world > 1 ? 1 : 0);
   ctx->progress.reset(new ProgressEngine(ctx, ns));
   ctx->initialized = true;
+  install_signal_handlers(ctx);
   ctx->boot->barrier();
 }
 
 void context_finalize(RankContext* ctx) {
   if (!ctx->initialized) return;
+  if (!ctx->boot->inproc()) remove_signal_handlers();
   ctx->progress->drain();
   ctx->boot->barrier();
   ctx->progress.reset();

@@ -272,6 +272,8 @@ void inproc_unbind_thread();
 bool thread_is_inproc_rank();
 std::unique_ptr<Bootstrap> take_thread_bootstrap();   // bootstrap reserved for the calling thread (or null)
 
+void install_signal_handlers(RankContext* ctx);   // sig_handler.cpp
+void remove_signal_handlers();
 void context_init(RankContext* ctx);        // bootstrap + backend + progress engine + base groups
 void context_finalize(RankContext* ctx);
 

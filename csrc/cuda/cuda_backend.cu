@@ -356,7 +356,7 @@ cudaStream_t CudaBackend::stream_for(int row, int lane) {
 // one 16-byte vector per thread until the grid limit is reached, only then more vectors per thread.
 int CudaBackend::pick_channels(size_t bytes) const {
   size_t want = ceil_div(std::max<size_t>(bytes, 1), (size_t)kCommThreads * 16);
-  int cmax = ctx_->env.num_channels > 0 ? ctx_->env.num_channels : 96;
+  int cmax = ctx_->env.num_channels > 0 ? ctx_->env.num_channels : 96;   // MLSL_NUM_CHANNELS (<= 128)
   int cap = std::max(1, sm_count_ / std::max(1, ranks_per_device_));
   cmax = std::min(cmax, std::min(cap, kMaxChannels));
   if (ctx_->env.max_short_msg && bytes <= ctx_->env.max_short_msg * 4) return 1;
@@ -368,8 +368,9 @@ DevComm CudaBackend::make_comm(const ProcessGroup& g, int lane) const {
   memset(&dc, 0, sizeof(dc));
   dc.nranks = g.size();
   dc.me = g.idx;
-  dc.pad_off = (unsigned)(((size_t)g.row * 2 + lane) * kPadRowBytes);
-  dc.seq_off = (unsigned)(kSeqBase + ((size_t)g.row * 2 + lane) * kSeqRowBytes);
+  const size_t row = g.row >= 0 ? (size_t)g.row : (size_t)kMaxGroupRows - 1;   // self groups: reserved last row
+  dc.pad_off = (unsigned)((row * 2 + lane) * kPadRowBytes);
+  dc.seq_off = (unsigned)(kSeqBase + (row * 2 + lane) * kSeqRowBytes);
   dc.timeout_ns = ctx_->env.watchdog_sec > 0 ? (unsigned long long)ctx_->env.watchdog_sec * 1000000000ull : 0ull;
   dc.err = err_dev_;
   for (int i = 0; i < g.size(); ++i) dc.slab[i] = peer_slab_[g.members[i]];
@@ -414,7 +415,7 @@ void CudaBackend::launch(CommRequest& r) {
   const CommDesc& d = r.desc;
   ProcessGroup* g = d.group;
   const bool solo = !g || g->size() <= 1;
-  cudaStream_t s = inline_stream_ ? user_stream_ : stream_for(solo ? 0 : g->row, r.lane);
+  cudaStream_t s = inline_stream_ ? user_stream_ : stream_for(solo || g->row < 0 ? kMaxGroupRows - 1 : g->row, r.lane);
   st->stream = s;
   if (!inline_stream_) MLSLB_CUDA(cudaStreamWaitEvent(s, st->ready, 0));
   launch_single(r, st, s);
@@ -434,7 +435,11 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   const size_t es = dtype_size(d.dtype);
   const size_t n = d.count;
   // ---- single-rank groups: local semantics, no peers -------------------------------------------------------
-  if (!g || g->size() <= 1) {
+  // MLSL_FORCE_KERNEL_SOLO=1: run a 1-rank group through the real collective kernels (handshake with itself,
+  // pull from / push to its own buffers).  Lets ncu profile the kernels on one GPU - under the profiler kernels
+  // are serialised, so ranks that wait for each other can never be captured.
+  static const bool force_solo = getenv("MLSL_FORCE_KERNEL_SOLO") && atoi(getenv("MLSL_FORCE_KERNEL_SOLO")) != 0;
+  if (!g || g->size() <= 1 ? !((force_solo && g && g->row >= 0) || d.kind == OpKind::FUSED_UPDATE) : false) {
     size_t bytes = 0;
     switch (d.kind) {
       case OpKind::ALLREDUCE: case OpKind::REDUCE: case OpKind::REDUCE_SCATTER: case OpKind::ALLGATHER:

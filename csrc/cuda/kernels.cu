@@ -7,6 +7,7 @@
 // endpoints (a message is split across them).
 #include "cuda/kernels.hpp"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace mlslb {
@@ -362,8 +363,11 @@ static cudaError_t launch_ar_t(const DevComm& dc, unsigned long long so, unsigne
   // vectors each thread has to move: keep them all in flight (unroll) up to 4 per pass
   const size_t per_thread = (count * sizeof(T) / (size_t)dc.nranks) / ((size_t)channels * kCommThreads * 16);
   constexpr bool kCanNvls = HasMultimem<T>::value && std::is_same<Op, OpSum>::value;
+  static int force_u = getenv("MLSL_AR_UNROLL") ? atoi(getenv("MLSL_AR_UNROLL")) : 0;   // tuning aid
   if (kCanNvls && dc.mc != nullptr) {
-    if (per_thread <= 1)
+    if ((force_u == 8) || (!force_u && per_thread >= 8))
+      k_allreduce<T, Op, 8, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+    else if (per_thread <= 1)
       k_allreduce<T, Op, 1, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
     else if (per_thread <= 3)
       k_allreduce<T, Op, 2, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);

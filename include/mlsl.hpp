@@ -151,6 +151,8 @@ class ParameterSet {
   void StartFusedUpdate(void* grad, void* param, DataType paramType, void* master, void* state1, void* state2,
                         const FusedUpdateParams* opt);
   void WaitFusedUpdate();
+  // [ext] multiplier fused into the gradient reduction (e.g. 1/world for averaging); default 1
+  void SetGradientScale(float scale);
 };
 
 class Distribution {

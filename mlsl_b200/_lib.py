@@ -202,6 +202,7 @@ def _declare(l):
         "mlsl_parameter_set_wait_increment_comm": [H, P(c_void_p)],
         "mlsl_parameter_set_start_fused_update": [H, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, P(FusedUpdateParams)],
         "mlsl_parameter_set_wait_fused_update": [H],
+        "mlsl_parameter_set_set_gradient_scale": [H, c_float],
         "mlsl_statistics_start": [H],
         "mlsl_statistics_stop": [H],
         "mlsl_statistics_reset": [H],

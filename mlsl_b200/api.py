@@ -176,6 +176,9 @@ class ParameterSet(_Handle):
         _pre()
         self._call("mlsl_parameter_set_wait_fused_update")
 
+    def set_gradient_scale(self, scale):
+        self._call("mlsl_parameter_set_set_gradient_scale", float(scale))
+
 
 _getters(ParameterSet, "mlsl_parameter_set", ["global_kernel_count", "global_kernel_offset", "local_kernel_count",
                                              "owned_kernel_count", "owned_kernel_offset", "kernel_size"])

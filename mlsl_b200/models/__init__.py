@@ -1,0 +1,8 @@
+"""Model zoo used by the benchmark configurations of BASELINE.json (ResNet-50 data parallel, BERT-large with the
+reduce-scatter + all-gather parameter path).  The reference ships no models (its tests use a synthetic two-layer
+network); these are plain PyTorch definitions with random-init weights."""
+from .bert import BertConfig, BertEncoderModel, bert_large
+from .mlp import MLP
+from .resnet import resnet50
+
+__all__ = ["BertConfig", "BertEncoderModel", "bert_large", "MLP", "resnet50"]

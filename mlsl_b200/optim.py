@@ -1,0 +1,179 @@
+"""DistributedOptimizer: data-parallel training on top of the Session / ParameterSet graph API.
+
+What a framework integration of the reference does by hand (reference tests/examples/mlsl_test/mlsl_test.cpp:
+per layer StartGradientComm during backward, WaitGradientComm before the update, optional distributed update with
+StartIncrementComm / WaitIncrementComm) packaged for PyTorch:
+
+  * parameters and gradients are flattened into buckets that live in the symmetric heap (zero-copy for the peer
+    kernels); every parameter's .data / .grad is a view into its bucket;
+  * one ParameterSet per bucket is registered in a Session (one Operation per bucket, so statistics are per bucket);
+  * a post-accumulate-grad hook counts the gradients of a bucket and starts its communication the moment the last
+    one is produced - while autograd is still computing the earlier layers (the overlap MLSL was designed for);
+  * mode "fused" (default on the CUDA backend): ReduceScatter + optimizer step on the owned shard + AllGather of the
+    new parameters is ONE kernel per bucket (ParameterSet.start_fused_update), with fp32 master weights and optimizer
+    state sharded over the data group (the reference's "distributed update", src/mlsl_impl.cpp:401-433);
+  * mode "allreduce": gradient AllReduce with the 1/N scale (and optionally the fp8 transport) fused in, followed by
+    a local torch optimizer.
+"""
+import torch
+
+from . import comm
+from .api import CompressionType, DataType, OperationType, OptimizerType
+
+
+class _Bucket:
+    __slots__ = ("params", "numel", "padded", "grad", "flat", "ps", "op", "pending", "master", "state1", "state2",
+                 "started", "offsets")
+
+
+class DistributedOptimizer:
+    def __init__(self, params, lr=0.1, momentum=0.0, weight_decay=0.0, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8,
+                 bucket_mb=64, mode=None, compress=False, distribution=None, average=True):
+        self.env = comm.env()
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        self.dist = distribution if distribution is not None else comm.world_distribution()
+        self.world = self.dist.get_process_count(0)
+        self.rank = self.dist.get_process_idx(0)
+        self.mode = mode or "fused"
+        assert self.mode in ("fused", "allreduce")
+        self.kind = optimizer
+        assert optimizer in ("sgd", "adamw")
+        self.lr, self.momentum, self.weight_decay, self.betas, self.eps = lr, momentum, weight_decay, betas, eps
+        self.compress = bool(compress) and self.mode == "allreduce"
+        self.scale = 1.0 / self.world if average else 1.0
+        self.steps = 0
+        self._build(bucket_mb)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(p)) for p in self.params]
+        if self.mode == "allreduce":
+            cls = torch.optim.AdamW if optimizer == "adamw" else torch.optim.SGD
+            kw = dict(lr=lr, weight_decay=weight_decay)
+            kw.update(dict(betas=betas, eps=eps) if optimizer == "adamw" else dict(momentum=momentum))
+            self.local = cls(self.params, **kw)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _build(self, bucket_mb):
+        dtype = self.params[0].dtype
+        assert all(p.dtype == dtype for p in self.params), "mixed parameter dtypes: create one optimizer per dtype"
+        self.dtype = dtype
+        limit = int(bucket_mb * (1 << 20)) // self.params[0].element_size()
+        # buckets are filled in REVERSE parameter order: gradients arrive last-layer-first
+        groups, cur, cur_n = [], [], 0
+        for p in reversed(self.params):
+            if cur and cur_n + p.numel() > limit:
+                groups.append(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += p.numel()
+        if cur:
+            groups.append(cur)
+        self.session = self.env.create_session()
+        self.session.set_global_minibatch_size(self.world)
+        mdt = comm.mlsl_dtype(dtype)
+        self.buckets, self._bucket_of = [], {}
+        align = 64  # elements: keeps every parameter view 16-byte aligned and the owned shards vector friendly
+        for gi, plist in enumerate(groups):
+            b = _Bucket()
+            b.params, b.offsets, off = plist, [], 0
+            for p in plist:
+                b.offsets.append(off)
+                off += (p.numel() + align - 1) // align * align
+            b.numel = off
+            b.padded = (off + self.world * align - 1) // (self.world * align) * (self.world * align)
+            ri = self.session.create_operation_reg_info(OperationType.CC)
+            ri.set_name("bucket_%d" % gi)
+            ri.add_input(1, 1, mdt)
+            ri.add_output(1, 1, mdt)
+            ri.add_parameter_set(b.padded, 1, mdt, self.mode == "fused",
+                                 CompressionType.QUANTIZATION if self.compress else CompressionType.NONE)
+            b.op = self.session.get_operation(self.session.add_operation(ri, self.dist))
+            self.session.delete_operation_reg_info(ri)
+            self.buckets.append(b)
+        self.session.commit()
+        dev = self.params[0].device
+        for b in self.buckets:
+            b.ps = b.op.get_parameter_set(0)
+            b.grad = comm.alloc_tensor(b.padded, dtype)
+            b.flat = comm.alloc_tensor(b.padded, dtype)
+            for p, off in zip(b.params, b.offsets):
+                view = b.flat[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = b.grad[off:off + p.numel()].view_as(p)
+                self._bucket_of[p] = b
+            b.pending, b.started = len(b.params), False
+            b.master = b.state1 = b.state2 = None
+            if self.mode == "fused":
+                owned = b.ps.get_owned_kernel_count() * b.ps.get_kernel_size()
+                lo = b.ps.get_owned_kernel_offset() * b.ps.get_kernel_size()
+                if dtype != torch.float32:
+                    b.master = b.flat[lo:lo + owned].float().clone()
+                if self.kind == "adamw" or self.momentum != 0.0:
+                    b.state1 = torch.zeros(owned, dtype=torch.float32, device=dev)
+                if self.kind == "adamw":
+                    b.state2 = torch.zeros(owned, dtype=torch.float32, device=dev)
+            else:
+                b.ps.set_gradient_scale(self.scale)
+
+    def _make_hook(self, p):
+        def hook(_):
+            b = self._bucket_of[p]
+            b.pending -= 1
+            if b.pending == 0:
+                self._start(b)
+        return hook
+
+    def _start(self, b):
+        if self.mode == "fused":
+            b.ps.start_fused_update(b.grad, b.flat, comm.mlsl_dtype(self.dtype), b.master, b.state1, b.state2,
+                                    OptimizerType.ADAMW if self.kind == "adamw" else OptimizerType.SGD, lr=self.lr,
+                                    momentum=self.momentum, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                                    weight_decay=self.weight_decay, step=self.steps + 1, grad_scale=self.scale)
+        else:
+            b.ps.start_gradient_comm(b.grad)
+        b.started = True
+
+    # ------------------------------------------------------------------------------------------------------------
+    def step(self):
+        """Finish the communication started during backward and apply the update."""
+        for b in self.buckets:
+            if not b.started:          # gradients that autograd never produced (unused parameters): start now
+                self._start(b)
+        for b in self.buckets:
+            if self.mode == "fused":
+                b.ps.wait_fused_update()
+            else:
+                b.ps.wait_gradient_comm()
+            b.pending, b.started = len(b.params), False
+        if self.mode == "allreduce":
+            self.local.step()
+        self.steps += 1
+
+    def zero_grad(self, set_to_none=False):
+        for b in self.buckets:
+            b.grad.zero_()
+
+    def set_lr(self, lr):
+        self.lr = lr
+        if self.mode == "allreduce":
+            for g in self.local.param_groups:
+                g["lr"] = lr
+
+    def gather_full_state(self):
+        """Checkpoint helper (the reference leaves snapshot assembly to Distribution::AllGather): returns
+        the full fp32 master weights of every bucket on every rank."""
+        out = []
+        for b in self.buckets:
+            if self.mode == "fused" and b.master is not None:
+                out.append(comm.allgather(b.master.contiguous(), distribution=self.dist))
+            else:
+                out.append(b.flat.float().clone())
+        return out
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self.env.delete_session(self.session)
+        for b in self.buckets:
+            comm.free_tensor(b.grad)
+            comm.free_tensor(b.flat)
