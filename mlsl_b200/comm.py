@@ -191,6 +191,11 @@ def _prep(t):
     return t
 
 
+def _movable(t):
+    """Pure data-movement collectives accept any dtype: unsupported ones travel as bytes."""
+    return t if t.dtype in _TORCH2MLSL else t.view(torch.uint8)
+
+
 def _dist(distribution):
     return distribution if distribution is not None else world_distribution()
 
@@ -254,8 +259,9 @@ def alltoall(tensor, out=None, group="data", async_op=False, distribution=None):
 def bcast(tensor, root=0, group="data", async_op=False, distribution=None):
     _prep(tensor)
     _sync_stream()
-    req = _dist(distribution).bcast(tensor, tensor.numel(), mlsl_dtype(tensor.dtype), root, _group(group))
-    w = Work(env(), req, tensor, (tensor,))
+    raw = _movable(tensor.view(-1))
+    req = _dist(distribution).bcast(raw, raw.numel(), mlsl_dtype(raw.dtype), root, _group(group))
+    w = Work(env(), req, tensor, (tensor, raw))
     return w if async_op else w.wait()
 
 
