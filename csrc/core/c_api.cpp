@@ -174,6 +174,10 @@ int mlsl_distribution_reduce_scatter_ex(mlsl_distribution d, void* s, void* rv, 
                                         mlsl_group_type g, float scale, mlsl_comm_req* r) {
   C_GUARD(*need(r) = U(H<Distribution>(d)->ReduceScatterEx(s, rv, n, DT(t), RT(op), GT(g), scale)))
 }
+int mlsl_distribution_gemm_reduce_scatter(mlsl_distribution d, const void* a, const void* w, void* out, size_t m, size_t n, size_t k,
+                                          mlsl_data_type ot, mlsl_group_type g, mlsl_comm_req* r) {
+  C_GUARD(*need(r) = U(H<Distribution>(d)->GemmReduceScatter(a, w, out, m, n, k, DT(ot), GT(g))))
+}
 int mlsl_distribution_barrier(mlsl_distribution d, mlsl_group_type g) { C_GUARD(H<Distribution>(d)->Barrier(GT(g))) }
 
 // ---- OperationRegInfo ----

@@ -13,7 +13,7 @@ namespace mlslb {
 constexpr int kMaxDevRanks = 16;    // ranks addressable by one device kernel (single NVSwitch domain)
 constexpr int kMaxHostRanks = 64;   // ranks supported by the host shared-memory backend
 constexpr int kMaxGroupRows = 64;   // concurrent process-group "rows" (one row per collective group creation)
-constexpr int kMaxChannels = 128;    // max CTAs ("channels", the GPU analogue of endpoints) per collective kernel
+constexpr int kMaxChannels = 152;    // max CTAs ("channels", the GPU analogue of endpoints) per collective kernel
 
 enum class DType : int { F32 = 0, F64 = 1, U8 = 2, BF16 = 3, F16 = 4, I32 = 5, F8E4M3 = 6 };
 enum class RedOp : int { SUM = 0, MIN = 1, MAX = 2 };

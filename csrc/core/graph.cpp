@@ -702,6 +702,21 @@ CommReq* Distribution::ReduceScatterEx(void* sendBuffer, void* recvBuffer, size_
   r->desc.scale = scale;
   return d->submit(r, sendBuffer, recvBuffer);
 }
+CommReq* Distribution::GemmReduceScatter(const void* a, const void* w, void* out, size_t M, size_t N, size_t K,
+                                         DataType outType, GroupType gt) {
+  auto d = SELF(DistributionImpl);
+  MLSLB_ASSERT(d->ctx->backend->is_device(), "GemmReduceScatter needs the CUDA backend");
+  MLSLB_ASSERT(outType == DT_BF16 || outType == DT_FLOAT, "GemmReduceScatter: output must be bf16 or fp32");
+  CommRequest* r = d->make_request(mlslb::OpKind::GEMM_RS, DT_BF16, gt);
+  r->desc.gemm.M = (int)M;
+  r->desc.gemm.N = (int)N;
+  r->desc.gemm.K = (int)K;
+  r->desc.gemm.a = a;
+  r->desc.gemm.w = w;
+  r->desc.has_out_dtype = true;
+  r->desc.out_dtype = to_dtype(outType);
+  return d->submit(r, const_cast<void*>(a), out);
+}
 void Distribution::Barrier(GroupType gt) {
   auto d = SELF(DistributionImpl);
   CommRequest* r = d->make_request(mlslb::OpKind::BARRIER, DT_BYTE, gt);

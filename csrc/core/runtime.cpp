@@ -117,7 +117,10 @@ void CommRequest::setup() {
       msg_bytes_ = send_bytes_;
       break;
     case OpKind::GEMM_RS:
-      send_bytes_ = recv_bytes_ = buf_bytes_ = msg_bytes_ = 0;
+      send_bytes_ = 0;
+      recv_bytes_ = (size_t)desc.gemm.M / P * (size_t)desc.gemm.N * dtype_size(desc.has_out_dtype ? desc.out_dtype : desc.dtype);
+      buf_bytes_ = 0;
+      msg_bytes_ = (size_t)desc.gemm.M * (size_t)desc.gemm.N * 2;
       break;
   }
   // priority lane: large gradient messages of the earliest operations overtake the rest (the intent of the

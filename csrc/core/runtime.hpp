@@ -73,6 +73,12 @@ struct CommDesc {
     void* state1 = nullptr;       // momentum / exp_avg shard (fp32)
     void* state2 = nullptr;       // exp_avg_sq shard (fp32)
   } fused;
+  // fused GEMM + reduce-scatter (OpKind::GEMM_RS): out[M/P, N] = reduce_scatter_rows(A[M, K] * W[N, K]^T)
+  struct GemmRs {
+    int M = 0, N = 0, K = 0;
+    const void* a = nullptr;      // [M, K] bf16, row-major (activations, K-slice of this rank)
+    const void* w = nullptr;      // [N, K] bf16, row-major (nn.Linear weight layout, K-slice of this rank)
+  } gemm;
 };
 
 class CommRequest {

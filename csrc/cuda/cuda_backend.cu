@@ -439,7 +439,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   // pull from / push to its own buffers).  Lets ncu profile the kernels on one GPU - under the profiler kernels
   // are serialised, so ranks that wait for each other can never be captured.
   static const bool force_solo = getenv("MLSL_FORCE_KERNEL_SOLO") && atoi(getenv("MLSL_FORCE_KERNEL_SOLO")) != 0;
-  if (!g || g->size() <= 1 ? !((force_solo && g && g->row >= 0) || d.kind == OpKind::FUSED_UPDATE) : false) {
+  if (!g || g->size() <= 1 ? !((force_solo && g && g->row >= 0) || d.kind == OpKind::FUSED_UPDATE || d.kind == OpKind::GEMM_RS) : false) {
     size_t bytes = 0;
     switch (d.kind) {
       case OpKind::ALLREDUCE: case OpKind::REDUCE: case OpKind::REDUCE_SCATTER: case OpKind::ALLGATHER:
@@ -470,6 +470,10 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   if ((d.kind == OpKind::REDUCE || d.kind == OpKind::GATHER) && me != (int)d.root) rbytes = 0;
   if (d.kind == OpKind::SCATTER && me != (int)d.root) sbytes = 0;
   if (d.kind == OpKind::FUSED_UPDATE) rbytes = n * P * dtype_size(d.has_out_dtype ? d.out_dtype : d.dtype);
+  if (d.kind == OpKind::GEMM_RS) {
+    sbytes = 0;   // A and W are only read by this rank's own TMA loads: any device memory will do
+    rbytes = (size_t)d.gemm.M / P * d.gemm.N * (d.has_out_dtype && d.out_dtype == DType::F32 ? 4 : 2);
+  }
   auto stage = [&](void* user, size_t bytes, bool copy_in, bool copy_out) -> char* {
     if (!user || bytes == 0 || owns(user, bytes)) return (char*)user;
     StageBuf sb{user, alloc(bytes, 256), bytes, copy_out};
@@ -628,7 +632,18 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
       MLSLB_CUDA(launch_fused_update(dc, d.dtype, d.has_out_dtype ? d.out_dtype : d.dtype, so, ro, n, a, ch, s));
       break;
     }
-    case OpKind::GEMM_RS: MLSLB_ASSERT(false, "GEMM_RS is launched through the ops API"); break;
+    case OpKind::GEMM_RS: {
+      const CommDesc::GemmRs& gm = d.gemm;
+      const char* why = gemm_rs_check(gm.M, gm.N, gm.K, P);
+      MLSLB_ASSERT(why == nullptr, "GemmReduceScatter(M=%d, N=%d, K=%d, P=%d): %s", gm.M, gm.N, gm.K, P, why);
+      MLSLB_ASSERT(d.dtype == DType::BF16, "GemmReduceScatter: inputs must be bf16");
+      size_t sb = gemm_rs_stage_bytes(gm.M, gm.N);
+      if (!st->qstage) st->qstage = alloc(sb, 1024);
+      const bool out32 = d.has_out_dtype && d.out_dtype == DType::F32;
+      const int gch = gemm_rs_channels(gm.M, gm.N, std::min(std::max(1, sm_count_ / std::max(1, ranks_per_device_)), kMaxChannels));
+      MLSLB_CUDA(launch_gemm_rs(dc, gm.a, gm.w, (unsigned long long)((char*)st->qstage - slab_), R, out32, gm.M, gm.N, gm.K, gch, s));
+      break;
+    }
   }
 
   // ---- copy results out of the staging buffers -------------------------------------------------------------------

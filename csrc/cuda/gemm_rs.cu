@@ -1,0 +1,406 @@
+// Fused GEMM + reduce-scatter for tensor (model) parallel layers - SURVEY K14.
+//
+// The reference's model parallelism (OT_CC with modelParts > 1: every rank holds a K-slice of the weights, its output
+// is a full-size PARTIAL sum that must be reduce-scattered over the model group, reference src/mlsl_impl.cpp:139-175)
+// costs a GEMM and then a collective.  Here both are ONE persistent sm_100a kernel:
+//
+//   C_r[M, N] = A_r[M, K_r] * W_r[N, K_r]^T        (bf16 inputs, fp32 accumulation)
+//   out_r[M/P, N] = sum_q C_q[rows of rank r]       (rank r owns rows [r*M/P, (r+1)*M/P))
+//
+//   * warp 0  : TMA producer  - cp.async.bulk.tensor 2D loads of A / W tiles (128B swizzle) into a 5-stage smem ring,
+//               completion on mbarriers;
+//   * warp 1  : MMA issuer    - one elected thread issues tcgen05.mma (cta_group::1, kind::f16, M128 x N128 x K16)
+//               with the accumulator in TMEM; two accumulator buffers (2 x 128 columns) so the epilogue of tile i
+//               overlaps the main loop of tile i+1; tcgen05.commit frees smem stages / publishes the accumulator;
+//   * warp 2  : TMEM allocation (256 columns) / deallocation;
+//   * warps 4-7: epilogue     - tcgen05.ld (32x32b.x32) the accumulator, convert to bf16, transpose through smem and
+//               write the tile with 128-byte row segments straight into the OWNER rank's staging slot over NVLink
+//               (peer store; local store when this rank owns the rows) while the tensor core already runs the next tile.
+//   After its last tile every CTA does the channel handshake (fence + flags) with the same CTA of the peers - the
+//   tile -> CTA map is identical on every rank, so the P partials of a tile are all produced by "its" channel - and
+//   then sums the P staged partials of the tiles it owns into the output (fp32 accumulate, bf16 or fp32 result).
+// Partials travel as bf16 (what a separate bf16 GEMM followed by a bf16 reduce-scatter would move); the order of the
+// final summation is fixed (rank 0..P-1), so results are deterministic.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "core/log.hpp"
+#include "cuda/kernels.hpp"
+
+namespace mlslb {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;          // CTA tile; BK * 2 bytes = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 5;
+constexpr int kAccBufs = 2;
+constexpr int kTmemCols = kAccBufs * BN;           // 256 (power of two >= 32)
+constexpr int kThreads = 256;                      // warps 0..3: producer / mma / tmem / idle, warps 4..7: epilogue
+constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
+constexpr uint32_t kEpiBytesPerWarp = 32 * 64 * 2; // 32 rows x 64 bf16 columns
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * (kStageBytesA + kStageBytesB) + 4 * kEpiBytesPerWarp + 256;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// K-major, 128-byte swizzled operand tile: start address, LBO = 1 (unused for swizzled K-major), SBO = 8 rows * 128 B,
+// descriptor version 1 (Blackwell), layout type SWIZZLE_128B (= 2 in bits 61..63).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N and M encoded as N>>3, M>>4.
+__device__ __forceinline__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct GemmRsArgs {
+  int M, N, K;                      // this rank's partial product: [M, N], reduction length K (= K_r)
+  unsigned long long stage_off;     // slab offset of the staging area: [P sources][M/P rows][N] bf16
+  void* out;                        // [M/P, N], bf16 or fp32
+  int out_fp32;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_gemm_rs(DevComm dc, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, GemmRsArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kStageBytesA;
+  uint8_t* sEpi = sB + kStages * kStageBytesB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * kEpiBytesPerWarp);
+  uint64_t* full = bars;                    // [kStages]  TMA -> MMA
+  uint64_t* empty = bars + kStages;         // [kStages]  MMA -> TMA
+  uint64_t* acc_full = empty + kStages;     // [kAccBufs] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + kAccBufs;// [kAccBufs] epilogue -> MMA
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + kAccBufs);
+  __shared__ PeerTable pt;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = dc.nranks, me = dc.me;
+  const int tiles_m = g.M / BM, tiles_n = g.N / BN, ntiles = tiles_m * tiles_n;
+  const int kblocks = g.K / BK;
+  const int rows_per_rank = g.M / P;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_w) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < kAccBufs; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);           // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  // Opening handshake: learn where every peer's staging area lives (and that its kernel - hence everything queued
+  // before it on its stream - has started).  All threads take part in the bar.syncs inside.
+  const unsigned long long ticket = comm_begin(dc, pt, g.stage_off, g.stage_off, NoAux());
+
+  // Tile schedule: tile t belongs to channel t % gridDim.x on EVERY rank; within a CTA the tiles are visited starting
+  // at an offset that depends on the rank, so at any moment the ranks push to different owners.
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int rot = my_tiles > 0 ? (me * ((my_tiles + P - 1) / P)) % my_tiles : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int t = (int)blockIdx.x + ((it + rot) % my_tiles) * (int)gridDim.x;
+        const int tm = t / tiles_n, tn = t % tiles_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], kStageBytesA + kStageBytesB);
+          tma_load_2d(sA + stage * kStageBytesA, &map_a, &full[stage], kb * BK, tm * BM);
+          tma_load_2d(sB + stage * kStageBytesB, &map_w, &full[stage], kb * BK, tn * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(BM, BN);
+    uint32_t stage = 0, phase = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t buf = (uint32_t)it & 1u, use = (uint32_t)it >> 1;
+      mbar_wait(&acc_empty[buf], (use & 1u) ^ 1u);       // epilogue has drained this accumulator buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + buf * BN;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t a0 = smem_u32(sA + stage * kStageBytesA), b0 = smem_u32(sB + stage * kStageBytesB);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(a0 + k * UMMA_K * 2), db = make_smem_desc(b0 + k * UMMA_K * 2);
+            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);                    // smem stage reusable once these MMAs have read it
+          if (kb == kblocks - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> bf16 -> owner's staging slot (peer memory) =====================
+    const int ew = warp - 4;                             // TMEM lanes [32*ew, 32*ew + 32)
+    uint8_t* myepi = sEpi + ew * kEpiBytesPerWarp;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int t = (int)blockIdx.x + ((it + rot) % my_tiles) * (int)gridDim.x;
+      const int tm = t / tiles_n, tn = t % tiles_n;
+      const uint32_t buf = (uint32_t)it & 1u, use = (uint32_t)it >> 1;
+      mbar_wait(&acc_full[buf], use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row0 = tm * BM + ew * 32;                // first global row handled by this warp
+      const int owner = row0 / rows_per_rank;
+      // destination: staging[src = me][row - owner*rows_per_rank][col] in the OWNER's slab
+      __nv_bfloat16* dst_base = reinterpret_cast<__nv_bfloat16*>(pt.send[owner]) +
+                                ((size_t)me * rows_per_rank + (size_t)(row0 - owner * rows_per_rank)) * g.N + (size_t)tn * BN;
+#pragma unroll 1
+      for (int half = 0; half < BN / 64; ++half) {
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * BN + half * 64;
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + 32, v + 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // lane = row: pack 64 fp32 -> 64 bf16 (128 B) and park the row in smem, 16-byte chunks XOR-swizzled by row
+        uint4* rowp = reinterpret_cast<uint4*>(myepi + lane * 128);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 q;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 0]), __uint_as_float(v[8 * c + 1]));
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 2]), __uint_as_float(v[8 * c + 3]));
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 4]), __uint_as_float(v[8 * c + 5]));
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[8 * c + 6]), __uint_as_float(v[8 * c + 7]));
+          q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+          q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+          rowp[c ^ (lane & 7)] = q;
+        }
+        __syncwarp();
+        // 8 lanes write one full 128-byte row segment: 4 rows per instruction, 8 instructions per 32 rows
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3), c = lane & 7;
+          const uint4 q = *reinterpret_cast<const uint4*>(myepi + r * 128 + ((c ^ (r & 7)) * 16));
+          st16(reinterpret_cast<char*>(dst_base + (size_t)r * g.N + half * 64) + c * 16, q);
+        }
+        __syncwarp();
+      }
+      // accumulator buffer drained: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+
+  // ---- all partial tiles of this channel are on their way: fence + flag handshake with the same channel of the peers
+  comm_sync(dc, pt, ticket, 1, true);
+
+  // ---- owner-side reduction of the tiles this channel is responsible for ---------------------------------------------
+  {
+    const __nv_bfloat16* stage_me = reinterpret_cast<const __nv_bfloat16*>(pt.send[me]);
+    const size_t slot = (size_t)rows_per_rank * g.N;      // elements per source slot
+    for (int it = 0; it < my_tiles; ++it) {
+      const int t = (int)blockIdx.x + it * (int)gridDim.x;
+      const int tm = t / tiles_n, tn = t % tiles_n;
+      const int row0 = tm * BM;
+      if (row0 / rows_per_rank != me) continue;           // tiles never straddle owners (rows_per_rank % BM == 0)
+      const int lrow0 = row0 - me * rows_per_rank;
+      // 128 x 128 tile, 8 bf16 (16 B) per thread-iteration
+      for (int idx = threadIdx.x; idx < BM * (BN / 8); idx += kThreads) {
+        const int r = idx / (BN / 8), c8 = idx % (BN / 8);
+        const size_t off = (size_t)(lrow0 + r) * g.N + (size_t)tn * BN + c8 * 8;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int q = 0; q < P; ++q) {
+          const uint4 v = __ldcg(reinterpret_cast<const uint4*>(stage_me + (size_t)q * slot + off));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[2 * j] += __uint_as_float(w[j] << 16);
+            acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+          }
+        }
+        if (g.out_fp32) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + off);
+          o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        } else {
+          uint4 o;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]), h3 = __floats2bfloat162_rn(acc[6], acc[7]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + off) = o;
+        }
+      }
+    }
+  }
+  // keep the staging area stable until every peer has finished reading... nobody reads remote staging in phase 2, but a
+  // fast peer must not start the NEXT launch's pushes into my staging while I still reduce: closing handshake.
+  comm_sync(dc, pt, ticket, 2, false);
+
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess) fn = (EncodeTiledFn)p;
+    else cudaGetLastError();
+  });
+  return fn;
+}
+
+// row-major [rows, K] bf16 matrix, box = [box_rows, 64] elements, 128-byte swizzle
+bool make_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+size_t gemm_rs_stage_bytes(int M, int N) { return (size_t)M * N * 2; }   // P slots of [M/P, N] bf16
+
+int gemm_rs_channels(int M, int N, int max_channels) {
+  int tiles = (M / BM) * (N / BN);
+  return std::max(1, std::min(tiles, max_channels));
+}
+
+const char* gemm_rs_check(int M, int N, int K, int P) {
+  if (M <= 0 || N <= 0 || K <= 0) return "empty problem";
+  if (M % (BM * P) != 0) return "M must be a multiple of 128 * group size";
+  if (N % BN != 0) return "N must be a multiple of 128";
+  if (K % BK != 0) return "K must be a multiple of 64";
+  return nullptr;
+}
+
+cudaError_t launch_gemm_rs(const DevComm& dc, const void* a, const void* w, unsigned long long stage_off, void* out,
+                           bool out_fp32, int M, int N, int K, int channels, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap ma, mw;
+  if (!make_map(&ma, a, M, K, BM) || !make_map(&mw, w, N, K, BN)) return cudaErrorInvalidValue;
+  GemmRsArgs g;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.stage_off = stage_off;
+  g.out = out;
+  g.out_fp32 = out_fp32 ? 1 : 0;
+  k_gemm_rs<<<channels, kThreads, kSmemBytes, s>>>(dc, ma, mw, g);
+  return cudaGetLastError();
+}
+
+}  // namespace mlslb

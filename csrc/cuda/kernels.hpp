@@ -59,6 +59,12 @@ struct FusedUpdateArgs {
 cudaError_t launch_fused_update(const DevComm& dc, DType grad_dt, DType param_dt, unsigned long long grad_off,
                                 unsigned long long param_off, size_t owned, const FusedUpdateArgs& a, int channels,
                                 cudaStream_t s);
+// K14: tcgen05 GEMM whose epilogue reduce-scatters the partial sums over peer memory (csrc/cuda/gemm_rs.cu)
+size_t gemm_rs_stage_bytes(int M, int N);
+int gemm_rs_channels(int M, int N, int max_channels);
+const char* gemm_rs_check(int M, int N, int K, int P);   // nullptr when the shape is supported
+cudaError_t launch_gemm_rs(const DevComm& dc, const void* a, const void* w, unsigned long long stage_off, void* out,
+                           bool out_fp32, int M, int N, int K, int channels, cudaStream_t s);
 // local elementwise helper (scale in place) for single-rank groups
 cudaError_t launch_scale(DType dt, void* buf, size_t count, float scale, cudaStream_t s);
 cudaError_t launch_scale_copy(DType dt, void* dst, const void* src, size_t count, float scale, cudaStream_t s);

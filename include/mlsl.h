@@ -229,6 +229,9 @@ int mlsl_distribution_reduce_scatter_ex(mlsl_distribution dist, void* send_buffe
 int mlsl_distribution_send_recv_list(mlsl_distribution dist, void* send_buffer, size_t* send_counts,
                                      size_t* send_offsets, void* recv_buffer, size_t* recv_counts, size_t* recv_offsets,
                                      mlsl_data_type dtype, mlsl_group_type group_type, mlsl_comm_req* req);
+int mlsl_distribution_gemm_reduce_scatter(mlsl_distribution dist, const void* a, const void* w, void* out, size_t m,
+                                          size_t n, size_t k, mlsl_data_type out_type, mlsl_group_type group_type,
+                                          mlsl_comm_req* req);
 int mlsl_activation_pack(mlsl_activation act, const void* local_buf, void* comm_buf);
 int mlsl_activation_unpack(mlsl_activation act, const void* comm_buf, void* local_buf);
 int mlsl_parameter_set_start_fused_update(mlsl_parameter_set param_set, void* grad, void* param,

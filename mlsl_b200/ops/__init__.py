@@ -1,0 +1,4 @@
+"""Fused compute + collective ops (hand-written sm_100a kernels, see csrc/cuda)."""
+from .gemm_rs import gemm_reduce_scatter
+
+__all__ = ["gemm_reduce_scatter"]
