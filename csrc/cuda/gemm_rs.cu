@@ -7,13 +7,13 @@
 //   C_r[M, N] = A_r[M, K_r] * W_r[N, K_r]^T        (bf16 inputs, fp32 accumulation)
 //   out_r[M/P, N] = sum_q C_q[rows of rank r]       (rank r owns rows [r*M/P, (r+1)*M/P))
 //
-//   * warp 0  : TMA producer  - cp.async.bulk.tensor 2D loads of A / W tiles (128B swizzle) into a 5-stage smem ring,
+//   * warp 0  : TMA producer  - cp.async.bulk.tensor 2D loads of A / W tiles (128B swizzle) into a 4-stage smem ring,
 //               completion on mbarriers;
-//   * warp 1  : MMA issuer    - one elected thread issues tcgen05.mma (cta_group::1, kind::f16, M128 x N128 x K16)
-//               with the accumulator in TMEM; two accumulator buffers (2 x 128 columns) so the epilogue of tile i
+//   * warp 1  : MMA issuer    - one elected thread issues tcgen05.mma (cta_group::1, kind::f16, M128 x N256 x K16)
+//               with the accumulator in TMEM; two accumulator buffers (2 x 256 columns = all of TMEM) so the epilogue of tile i
 //               overlaps the main loop of tile i+1; tcgen05.commit frees smem stages / publishes the accumulator;
-//   * warp 2  : TMEM allocation (256 columns) / deallocation;
-//   * warps 4-7: epilogue     - tcgen05.ld (32x32b.x32) the accumulator, convert to bf16, transpose through smem and
+//   * warp 2  : TMEM allocation (512 columns) / deallocation;
+//   * warps 4-11: epilogue    - tcgen05.ld (32x32b.x32) the accumulator, convert to bf16, transpose through smem and
 //               write the tile with 128-byte row segments straight into the OWNER rank's staging slot over NVLink
 //               (peer store; local store when this rank owns the rows) while the tensor core already runs the next tile.
 //   After its last tile every CTA does the channel handshake (fence + flags) with the same CTA of the peers - the
@@ -36,15 +36,17 @@ namespace mlslb {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;          // CTA tile; BK * 2 bytes = one 128-byte swizzle row
+constexpr int BM = 128, BN = 256, BK = 64;          // CTA tile; BK * 2 bytes = one 128-byte swizzle row.  N = 256 keeps the
+                                                    // smem operand traffic (A 4 KB + B 8 KB per 128-cycle MMA) under 128 B/clk
 constexpr int UMMA_K = 16;
-constexpr int kStages = 5;
+constexpr int kStages = 4;
 constexpr int kAccBufs = 2;
-constexpr int kTmemCols = kAccBufs * BN;           // 256 (power of two >= 32)
-constexpr int kThreads = 256;                      // warps 0..3: producer / mma / tmem / idle, warps 4..7: epilogue
+constexpr int kTmemCols = kAccBufs * BN;           // 512: the whole tensor memory, double-buffered accumulator
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int kThreads = 128 + kEpiWarps * 32;     // warps 0..3: producer / mma / tmem / idle, warps 4..11: epilogue
 constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
 constexpr uint32_t kEpiBytesPerWarp = 32 * 64 * 2; // 32 rows x 64 bf16 columns
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * (kStageBytesA + kStageBytesB) + 4 * kEpiBytesPerWarp + 256;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + kStages * (kStageBytesA + kStageBytesB) + kEpiWarps * kEpiBytesPerWarp + 256;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,7 +144,7 @@ k_gemm_rs(DevComm dc, const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kStageBytesA;
   uint8_t* sEpi = sB + kStages * kStageBytesB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * kEpiBytesPerWarp);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + kEpiWarps * kEpiBytesPerWarp);
   uint64_t* full = bars;                    // [kStages]  TMA -> MMA
   uint64_t* empty = bars + kStages;         // [kStages]  MMA -> TMA
   uint64_t* acc_full = empty + kStages;     // [kAccBufs] MMA -> epilogue
@@ -167,7 +169,7 @@ k_gemm_rs(DevComm dc, const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
     for (int i = 0; i < kAccBufs; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);           // one arrival per epilogue warp
+      mbar_init(&acc_empty[i], kEpiWarps);   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -234,8 +236,9 @@ k_gemm_rs(DevComm dc, const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> bf16 -> owner's staging slot (peer memory) =====================
-    const int ew = warp - 4;                             // TMEM lanes [32*ew, 32*ew + 32)
-    uint8_t* myepi = sEpi + ew * kEpiBytesPerWarp;
+    const int ew = (warp - 4) & 3;                       // TMEM lane quarter [32*ew, 32*ew + 32) (= warp id % 4)
+    const int ch = (warp - 4) >> 2;                      // which half of the tile's columns this warp drains
+    uint8_t* myepi = sEpi + (warp - 4) * kEpiBytesPerWarp;
     for (int it = 0; it < my_tiles; ++it) {
       const int t = (int)blockIdx.x + ((it + rot) % my_tiles) * (int)gridDim.x;
       const int tm = t / tiles_n, tn = t % tiles_n;
@@ -248,7 +251,8 @@ k_gemm_rs(DevComm dc, const __grid_constant__ CUtensorMap map_a, const __grid_co
       __nv_bfloat16* dst_base = reinterpret_cast<__nv_bfloat16*>(pt.send[owner]) +
                                 ((size_t)me * rows_per_rank + (size_t)(row0 - owner * rows_per_rank)) * g.N + (size_t)tn * BN;
 #pragma unroll 1
-      for (int half = 0; half < BN / 64; ++half) {
+      for (int hh = 0; hh < BN / 128; ++hh) {
+        const int half = ch * (BN / 128) + hh;           // 64-column chunk index inside the tile
         uint32_t v[64];
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * BN + half * 64;
         tmem_ld32(taddr, v);
@@ -296,31 +300,49 @@ k_gemm_rs(DevComm dc, const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int row0 = tm * BM;
       if (row0 / rows_per_rank != me) continue;           // tiles never straddle owners (rows_per_rank % BM == 0)
       const int lrow0 = row0 - me * rows_per_rank;
-      // 128 x 128 tile, 8 bf16 (16 B) per thread-iteration
-      for (int idx = threadIdx.x; idx < BM * (BN / 8); idx += kThreads) {
-        const int r = idx / (BN / 8), c8 = idx % (BN / 8);
-        const size_t off = (size_t)(lrow0 + r) * g.N + (size_t)tn * BN + c8 * 8;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int q = 0; q < P; ++q) {
-          const uint4 v = __ldcg(reinterpret_cast<const uint4*>(stage_me + (size_t)q * slot + off));
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      // 128 x 256 tile, 8 bf16 (16 B) per item; kU independent items per thread in flight (the loop is latency bound)
+      constexpr int kU = 4, kItems = BM * (BN / 8);
+      for (int idx0 = threadIdx.x; idx0 < kItems; idx0 += kThreads * kU) {
+        float acc[kU][8];
+        size_t off[kU];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            acc[2 * j] += __uint_as_float(w[j] << 16);
-            acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+        for (int u = 0; u < kU; ++u) {
+          const int idx = idx0 + u * kThreads;
+          const int r = idx / (BN / 8), c8 = idx % (BN / 8);
+          off[u] = (size_t)(lrow0 + r) * g.N + (size_t)tn * BN + c8 * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[u][j] = 0.f;
+        }
+        for (int q = 0; q < P; ++q) {
+          uint4 v[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u)
+            if (idx0 + u * kThreads < kItems) v[u] = __ldcg(reinterpret_cast<const uint4*>(stage_me + (size_t)q * slot + off[u]));
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[u][2 * j] += __uint_as_float(w[j] << 16);
+              acc[u][2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+            }
           }
         }
-        if (g.out_fp32) {
-          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + off);
-          o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-          o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        } else {
-          uint4 o;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]), h3 = __floats2bfloat162_rn(acc[6], acc[7]);
-          o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-          o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + off) = o;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          if (idx0 + u * kThreads >= kItems) continue;
+          if (g.out_fp32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + off[u]);
+            o[0] = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+            o[1] = make_float4(acc[u][4], acc[u][5], acc[u][6], acc[u][7]);
+          } else {
+            uint4 o;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[u][0], acc[u][1]), h1 = __floats2bfloat162_rn(acc[u][2], acc[u][3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[u][4], acc[u][5]), h3 = __floats2bfloat162_rn(acc[u][6], acc[u][7]);
+            o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+            o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(g.out) + off[u]) = o;
+          }
         }
       }
     }
@@ -377,7 +399,7 @@ int gemm_rs_channels(int M, int N, int max_channels) {
 const char* gemm_rs_check(int M, int N, int K, int P) {
   if (M <= 0 || N <= 0 || K <= 0) return "empty problem";
   if (M % (BM * P) != 0) return "M must be a multiple of 128 * group size";
-  if (N % BN != 0) return "N must be a multiple of 128";
+  if (N % BN != 0) return "N must be a multiple of 256";
   if (K % BK != 0) return "K must be a multiple of 64";
   return nullptr;
 }

@@ -191,7 +191,7 @@ class Distribution {
                         size_t* recvCounts, size_t* recvOffsets, DataType dataType, GroupType groupType);
   // [ext] tensor-parallel GEMM fused with the reduce-scatter of its partial sums (CUDA backend, one tcgen05 kernel):
   // out[M/P, N] (rows of this rank) = sum over the group of A_r[M, K] * W_r[N, K]^T; A, W bf16 row-major;
-  // out bf16 or fp32 (outType).  M % (128 * P) == 0, N % 128 == 0, K % 64 == 0.
+  // out bf16 or fp32 (outType).  M % (128 * P) == 0, N % 256 == 0, K % 64 == 0.
   CommReq* GemmReduceScatter(const void* a, const void* w, void* out, size_t M, size_t N, size_t K, DataType outType,
                              GroupType groupType);
 };

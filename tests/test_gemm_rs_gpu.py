@@ -14,7 +14,7 @@ def _mats(rank, M, N, K):
     return a, w
 
 
-@pytest.mark.parametrize("world,M,N,K", [(1, 128, 128, 64), (1, 256, 384, 512), (2, 512, 256, 256), (4, 1024, 512, 320),
+@pytest.mark.parametrize("world,M,N,K", [(1, 128, 256, 64), (1, 256, 768, 512), (2, 512, 256, 256), (4, 1024, 512, 320),
                                          (2, 2048, 1024, 1024)])
 @pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
 def test_gemm_reduce_scatter(world, M, N, K, out_dtype):
