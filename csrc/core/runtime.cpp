@@ -286,16 +286,19 @@ void ProgressEngine::drain() {
 }
 
 void ProgressEngine::suspend() {
+  const uint64_t gen = suspend_gen_.fetch_add(1) + 1;
   for (auto& s : servers_) {
     Command c;
     c.kind = Command::SUSPEND;
+    c.arg = gen;
     std::lock_guard<std::mutex> g(s->mu);
     while (!s->ring.push(c)) sched_yield();
   }
 }
 
 void ProgressEngine::resume() {
-  for (auto& s : servers_) s->parked.store(false, std::memory_order_release);
+  // generation based: a resume that overtakes a not-yet-processed SUSPEND still cancels it
+  resume_gen_.store(suspend_gen_.load(std::memory_order_acquire), std::memory_order_release);
 }
 
 void ProgressEngine::run(Server* s, int idx) {
@@ -321,7 +324,8 @@ void ProgressEngine::run(Server* s, int idx) {
     if (c.kind == Command::STOP) return;
     if (c.kind == Command::SUSPEND) {
       s->parked.store(true, std::memory_order_release);
-      while (s->parked.load(std::memory_order_acquire)) usleep(100);
+      while (resume_gen_.load(std::memory_order_acquire) < c.arg) usleep(100);
+      s->parked.store(false, std::memory_order_release);
       continue;
     }
     if (c.kind == Command::EXEC) {

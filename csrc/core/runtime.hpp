@@ -188,6 +188,7 @@ struct Command {
   enum Kind : int { EXEC = 0, SUSPEND, RESUME, STOP };
   int kind = EXEC;
   CommRequest* req = nullptr;
+  uint64_t arg = 0;                   // SUSPEND: generation to wait for
 };
 
 // Background "endpoint server" threads.  One ring per server; requests of one process group always go to the
@@ -215,6 +216,7 @@ class ProgressEngine {
   RankContext* ctx_;
   std::vector<std::unique_ptr<Server>> servers_;
   std::atomic<uint64_t> launched_{0};
+  std::atomic<uint64_t> suspend_gen_{0}, resume_gen_{0};   // a server stays parked while resume_gen_ < its SUSPEND's generation
 };
 
 // ----------------------------------------------------------------------------------------------------------

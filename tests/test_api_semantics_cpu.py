@@ -1,0 +1,310 @@
+"""Behavioural checks of the graph / environment API on the host backend: the rules of SURVEY 7.4 and the error
+paths the reference asserts on, plus features its own tests never touch (colours, Configure, statistics, pointer
+checker, priority lanes, server suspend/resume, golden layouts)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT, run_ranks
+
+
+def _session_two_layers(mlsl, world, model_parts, dist_update, mb=16):
+    from mlsl_b200.api import DataType, OperationType
+    e = mlsl.env()
+    sess = e.create_session()
+    sess.set_global_minibatch_size(mb)
+    dist = e.create_distribution(world // model_parts, model_parts)
+    ops = []
+    for l, (ifm, ofm) in enumerate([(128, 256), (256, 256)]):
+        ri = sess.create_operation_reg_info(OperationType.CC)
+        ri.set_name("layer_%d" % l)
+        ri.add_input(ifm, 144, DataType.FLOAT)
+        ri.add_output(ofm, 144, DataType.FLOAT)
+        ri.add_parameter_set(ifm * ofm, 9, DataType.FLOAT, dist_update)
+        ops.append(sess.get_operation(sess.add_operation(ri, dist)))
+        sess.delete_operation_reg_info(ri)   # reg info may be dropped right after AddOperation (ref-counted)
+    ops[1].set_prev(ops[0], 0, 0)
+    sess.commit()
+    return sess, dist, ops
+
+
+def test_golden_layout_2x2_distributed_update():
+    """The layout the reference prints for 4 ranks, 2x2, distUpdate=1, rank 0 (SURVEY 2.6 golden dump)."""
+    def body(r, mlsl):
+        sess, dist, ops = _session_two_layers(mlsl, 4, 2, True)
+        oa, ia, ps = ops[0].get_output(0), ops[1].get_input(0), ops[0].get_parameter_set(0)
+        blocks = [(b.get_mb_offset(), b.get_mb_count(), b.get_fm_offset(), b.get_fm_count(), b.get_fm_size(), b.get_buf_offset())
+                  for b in (oa.get_pack_block(i) for i in range(oa.get_pack_block_count()))]
+        res = dict(out_global=oa.get_global_fm_count(), out_local=oa.get_local_fm_count(), blocks=blocks,
+                   out_buf=oa.get_comm_buf_size(), in_local=ia.get_local_fm_count(), in_pack=ia.get_pack_block_count(),
+                   in_unpack=ia.get_unpack_block_count(), in_buf=ia.get_comm_buf_size(),
+                   kernels=(ps.get_global_kernel_count(), ps.get_local_kernel_count(), ps.get_owned_kernel_count(),
+                            ps.get_owned_kernel_offset()), lmb=ops[0].get_local_minibatch_size(),
+                   mb_off=ops[0].get_global_minibatch_offset())
+        mlsl.env().delete_session(sess)
+        mlsl.env().delete_distribution(dist)
+        return res
+
+    outs = run_ranks(4, body)
+    r0 = outs[0]
+    assert (r0["out_global"], r0["out_local"]) == (256, 256)
+    assert r0["blocks"] == [(0, 8, 0, 128, 144, 0), (0, 8, 128, 128, 144, 147456)]
+    assert r0["in_local"] == 128 and r0["in_pack"] == 1 and r0["in_unpack"] == 1
+    # reduce-scatter runs out of place here: send region (the reference's tmp_size 1179648) + the receive shard
+    assert r0["out_buf"] == 1179648 + 147456 * 4
+    assert r0["in_buf"] == 147456 * 2 * 4
+    assert r0["kernels"] == (32768, 16384, 8192, 0)
+    assert outs[2]["kernels"][3] == 8192 and outs[2]["mb_off"] == 8 and r0["lmb"] == 8
+
+
+def test_owned_count_is_padded_for_distributed_update():
+    def body(r, mlsl):
+        from mlsl_b200.api import DataType, OperationType
+        e = mlsl.env()
+        sess = e.create_session()
+        sess.set_global_minibatch_size(3)
+        dist = e.create_distribution(3, 1)
+        ri = sess.create_operation_reg_info(OperationType.CC)
+        ri.add_input(4, 1, DataType.FLOAT)
+        ri.add_output(4, 1, DataType.FLOAT)
+        ri.add_parameter_set(10, 7, DataType.DOUBLE, True)     # 10 kernels over 3 ranks -> owned 4, local padded to 12
+        op = sess.get_operation(sess.add_operation(ri, dist))
+        sess.commit()
+        ps = op.get_parameter_set(0)
+        out = (ps.get_local_kernel_count(), ps.get_owned_kernel_count(), ps.get_owned_kernel_offset(), ps.is_distributed_update())
+        e.delete_session(sess)
+        e.delete_distribution(dist)
+        return out
+
+    outs = run_ranks(3, body)
+    assert [o[:3] for o in outs] == [(12, 4, 0), (12, 4, 4), (12, 4, 8)] and all(o[3] for o in outs)
+
+
+def test_error_paths_raise():
+    def body(r, mlsl):
+        from mlsl_b200 import MLSLError
+        from mlsl_b200.api import DataType, OperationType
+        e = mlsl.env()
+        errs = []
+
+        def expect(fn, what):
+            try:
+                fn()
+                errs.append("no error for " + what)
+            except MLSLError as ex:
+                assert "assertion" in str(ex).lower() or "null" in str(ex).lower(), str(ex)
+
+        expect(lambda: e.init(), "double init")
+        sess = e.create_session()
+        expect(lambda: sess.set_global_minibatch_size(0), "zero minibatch")
+        sess.set_global_minibatch_size(8)
+        expect(lambda: sess.set_global_minibatch_size(8), "minibatch set twice")
+        expect(lambda: e.create_distribution(0, 1), "zero partitions")
+        expect(lambda: e.create_distribution(3, 3), "more partitions than ranks")
+        d = mlsl.world_distribution()
+        expect(lambda: d.bcast(torch.zeros(4), 4, DataType.FLOAT, 99, 0), "root outside group")
+        ri = sess.create_operation_reg_info(OperationType.SPLIT)
+        expect(lambda: sess.add_operation(ri, d), "unsupported op type")
+        ri2 = sess.create_operation_reg_info(OperationType.CC)
+        expect(lambda: ri2.add_input(0, 4, DataType.FLOAT), "zero feature maps")
+        ri2.add_input(4, 4, DataType.FLOAT)
+        ri2.add_output(4, 4, DataType.FLOAT)
+        op = sess.get_operation(sess.add_operation(ri2, d))
+        expect(lambda: op.set_distribution(d), "distribution set twice")
+        expect(lambda: op.get_input(5), "input index out of range")
+        sess.commit()
+        expect(lambda: sess.commit(), "commit twice")
+        e.delete_session(sess)
+        return errs
+
+    assert run_ranks(2, body) == [[], []]
+
+
+def test_distribution_with_colors_and_configure():
+    def body(r, mlsl):
+        e = mlsl.env()
+        # rows of a 2x3 grid as data groups, columns as model groups
+        d = e.create_distribution_with_colors(r // 3, r % 3)
+        info = (d.get_process_count(0), d.get_process_idx(0), d.get_process_count(1), d.get_process_idx(1))
+        t = torch.full((8,), float(r))
+        mlsl.allreduce(t, group="data", distribution=d)
+        u = torch.full((8,), float(r))
+        mlsl.allreduce(u, group="model", distribution=d)
+        e.delete_distribution(d)
+        # Configure("color=N"): the global group itself is split
+        e.configure("color=%d" % (r % 2))
+        g = (e.get_process_count(), e.get_process_idx())
+        d2 = e.create_distribution(e.get_process_count(), 1)
+        v = torch.full((4,), float(r))
+        mlsl.allreduce(v, group="global", distribution=d2)
+        e.delete_distribution(d2)
+        return info, float(t[0]), float(u[0]), g, float(v[0])
+
+    outs = run_ranks(6, body)
+    for r, (info, t, u, g, v) in enumerate(outs):
+        assert info == (3, r % 3, 2, r // 3)
+        assert t == sum(q for q in range(6) if q // 3 == r // 3)
+        assert u == sum(q for q in range(6) if q % 3 == r % 3)
+        assert g == (3, r // 2)
+        assert v == sum(q for q in range(6) if q % 2 == r % 2)
+
+
+def test_statistics_counters():
+    def body(r, mlsl):
+        sess, dist, ops = _session_two_layers(mlsl, 2, 1, False, mb=4)
+        st = sess.get_stats()
+        assert st.is_enabled() and not st.is_started()
+        iso = st.get_total_isolation_comm_cycles()
+        st.start()
+        ps = ops[0].get_parameter_set(0)
+        n = ps.get_local_kernel_count() * ps.get_kernel_size()
+        g = mlsl.alloc_tensor(n, torch.float32)
+        for _ in range(3):
+            ps.start_gradient_comm(g)
+            ps.wait_gradient_comm()
+        st.stop()
+        res = (iso, st.get_comm_size(0), st.get_comm_cycles(0), st.get_compute_cycles(0), st.get_comm_size(1),
+               st.get_total_comm_size(), st.get_comm_nanos(0), n)
+        st.print()
+        st.reset()
+        assert st.get_total_comm_cycles() == 0
+        mlsl.env().delete_session(sess)
+        mlsl.env().delete_distribution(dist)
+        return res
+
+    outs = run_ranks(2, body, env={"MLSL_STATS": "1", "MLSL_STATS_ITERS": "3", "MLSL_STATS_SKIP": "1"})
+    for iso, size0, comm0, comp0, size1, total, ns0, n in outs:
+        assert iso > 0 and comm0 > 0 and ns0 > 0
+        assert size0 == 3 * n * 4 and size1 == 0 and total == size0
+    if os.path.exists("mlsl_stats.log"):
+        os.remove("mlsl_stats.log")
+
+
+def test_pointer_checker_rejects_foreign_buffers():
+    def body(r, mlsl):
+        from mlsl_b200 import MLSLError
+        ok = mlsl.alloc_tensor(16, torch.float32)
+        mlsl.allreduce(ok)
+        try:
+            mlsl.allreduce(torch.zeros(16))
+            return "foreign buffer accepted"
+        except MLSLError as ex:
+            return "pointer check" in str(ex)
+
+    assert run_ranks(2, body, env={"MLSL_POINTER_CHECK": "1"}) == [True, True]
+
+
+@pytest.mark.parametrize("servers", ["0", "2"])
+def test_servers_priority_lane_and_suspend_resume(servers):
+    """Inline execution (no servers) and two progress threads with the priority lane: same results."""
+    def body(r, mlsl):
+        sess, dist, ops = _session_two_layers(mlsl, 2, 1, False, mb=4)
+        e = mlsl.env()
+        grads = []
+        for op in ops:
+            ps = op.get_parameter_set(0)
+            g = mlsl.alloc_tensor(ps.get_local_kernel_count() * ps.get_kernel_size(), torch.float32)
+            g.fill_(r + 1.0)
+            grads.append((ps, g))
+        if servers != "0":
+            e.suspend_servers()
+        for ps, g in reversed(grads):        # backward order: last layer first
+            ps.start_gradient_comm(g)
+        if servers != "0":
+            e.resume_servers()
+        for ps, g in grads:
+            ps.wait_gradient_comm()
+        ok = all(float(g[0]) == 3.0 and float(g[-1]) == 3.0 for _, g in grads)
+        e.delete_session(sess)
+        e.delete_distribution(dist)
+        return ok
+
+    env = {"MLSL_NUM_SERVERS": servers, "MLSL_MSG_PRIORITY": "1", "MLSL_MSG_PRIORITY_THRESHOLD": "1000"}
+    assert run_ranks(2, body, env=env) == [True, True]
+
+
+def test_test_returns_pointer_again_after_completion():
+    def body(r, mlsl):
+        sess, dist, ops = _session_two_layers(mlsl, 2, 1, False, mb=4)
+        ps = ops[0].get_parameter_set(0)
+        g = mlsl.alloc_tensor(ps.get_local_kernel_count() * ps.get_kernel_size(), torch.float32)
+        ps.start_gradient_comm(g)
+        ptr, done = None, False
+        while not done:
+            ptr, done = ps.test_gradient_comm()
+        again, done2 = ps.test_gradient_comm()
+        mlsl.env().delete_session(sess)
+        mlsl.env().delete_distribution(dist)
+        return ptr == g.data_ptr() and again == ptr and done2
+
+    assert run_ranks(2, body) == [True, True]
+
+
+def test_quantization_params_roundtrip_and_version():
+    def body(r, mlsl):
+        e = mlsl.env()
+        e.set_quantization_params("libdl_comp.so", "q", "d", "rs", 0, 0)
+        q = e.get_quantization_params()
+        return q["block_size"], q["elem_in_block"], e.get_version()
+
+    assert run_ranks(1, body) == [(132, 128, (1 << 16) | 0)]
+
+
+# ---- native test programs through the launcher (multi-process, POSIX shared memory) --------------------------------
+def _bin(name):
+    p = os.path.join(ROOT, "bin", name)
+    if not os.path.exists(p):
+        subprocess.run(["make", "-C", ROOT, "-j8"], check=True, stdout=subprocess.DEVNULL)
+    return p
+
+
+@pytest.mark.parametrize("args", [["1", "0", "0", "0"], ["2", "1", "1", "1"], ["4", "1", "0", "0"], ["1", "0", "0", "0", "1"]])
+def test_cpp_functional_test_multiprocess(args):
+    env = dict(os.environ, MLSL_BACKEND="host", MLSL_HEAP_SIZE_GB="0.25")
+    res = subprocess.run([_bin("mlslrun"), "-n", "4", "--timeout", "120", _bin("mlsl_functional_test")] + args,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=180)
+    assert res.returncode == 0, res.stdout[-2000:]
+    assert ": FAILED" not in res.stdout and res.stdout.count("summary: ") == 4 and "0 FAILED" in res.stdout
+
+
+def test_c_binding_and_sample_multiprocess():
+    env = dict(os.environ, MLSL_BACKEND="host", MLSL_HEAP_SIZE_GB="0.25")
+    for prog, n in (("cmlsl_smoke_test", 3), ("mlsl_sample", 2), ("mlsl_example", 4)):
+        res = subprocess.run([_bin("mlslrun"), "-n", str(n), "--timeout", "60", _bin(prog)], stdout=subprocess.PIPE,
+                             stderr=subprocess.STDOUT, text=True, env=env, timeout=120)
+        assert res.returncode == 0 and "FAILED" not in res.stdout, res.stdout[-2000:]
+
+
+def test_poison_makes_peers_fail_fast():
+    """A rank that dies with a fatal signal poisons the shared control block: the survivor errors out at once instead
+    of waiting for the watchdog (the reference can only _exit the failing process)."""
+    code = r'''
+import os, sys, signal, time
+sys.path.insert(0, %r)
+import torch, mlsl_b200 as mlsl
+mlsl.init()
+t = torch.ones(8)
+mlsl.allreduce(t)
+if mlsl.rank() == 1:
+    os.kill(os.getpid(), signal.SIGSEGV)
+time.sleep(0.5)
+t0 = time.time()
+try:
+    mlsl.allreduce(t)
+    print("survived")
+except Exception as e:
+    print("FAILFAST %%.1f %%s" %% (time.time() - t0, "poisoned" in str(e)))
+''' % ROOT
+    procs = []
+    job = "pz%d" % os.getpid()
+    for r in range(2):
+        env = dict(os.environ, MLSL_BACKEND="host", MLSL_RANK=str(r), MLSL_WORLD_SIZE="2", MLSL_JOB_ID=job,
+                   MLSL_HEAP_SIZE_GB="0.1", MLSL_WATCHDOG_SEC="60")
+        procs.append(subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env))
+    out0 = procs[0].communicate(timeout=120)[0]
+    procs[1].communicate(timeout=120)
+    assert "FAILFAST" in out0 and "True" in out0, out0
+    assert float(out0.split("FAILFAST")[1].split()[0]) < 30
