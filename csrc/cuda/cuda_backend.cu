@@ -215,6 +215,14 @@ class CudaBackend final : public Backend {
   std::vector<cudaStream_t> streams_;
   cudaStream_t aux_stream_ = nullptr, user_stream_ = nullptr, own_user_stream_ = nullptr;
   bool stream_wait_ = false, inline_stream_ = false;
+  // host-buffer pipeline (see launch_host_pipelined)
+  static constexpr int kPipeBufs = 3;
+  size_t pipe_chunk_ = (size_t)32 << 20;
+  char* pipe_buf_[kPipeBufs] = {nullptr, nullptr, nullptr};
+  cudaEvent_t pipe_h2d_[kPipeBufs] = {}, pipe_ar_[kPipeBufs] = {}, pipe_d2h_[kPipeBufs] = {}, pipe_start_ = nullptr;
+  cudaStream_t h2d_stream_ = nullptr, d2h_stream_ = nullptr;
+  bool pipe_used_[kPipeBufs] = {false, false, false};
+  bool launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaStream_t s);
   VmmSlab vmm_;
   char* mc_ = nullptr;
   volatile int* err_host_ = nullptr;
@@ -465,6 +473,9 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   const int P = g->size(), me = g->idx;
   DevComm dc = make_comm(*g, r.lane);
 
+  // ---- host-resident all-reduce: chunked H2D -> kernel -> D2H pipeline instead of staging the whole message ------
+  if (d.kind == OpKind::ALLREDUCE && !d.compress && launch_host_pipelined(r, dc, s)) return;
+
   // ---- stage foreign buffers through the slab ------------------------------------------------------------------
   size_t sbytes = r.send_bytes(), rbytes = r.recv_bytes();
   if ((d.kind == OpKind::REDUCE || d.kind == OpKind::GATHER) && me != (int)d.root) rbytes = 0;
@@ -650,6 +661,62 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   if (alias_fix) MLSLB_CUDA(cudaMemcpyAsync(Rfinal, R, rbytes, cudaMemcpyDefault, s));
   for (auto& sb : st->stages)
     if (sb.copy_out && sb.user == r.recv) MLSLB_CUDA(cudaMemcpyAsync(sb.user, sb.slab, sb.bytes, cudaMemcpyDefault, s));
+}
+
+// End-to-end path for buffers that live in HOST memory (the reference's only kind of buffer): the message is cut
+// into chunks that flow through three slab buffers - chunk i+1 is on its way up over PCIe while chunk i is being
+// all-reduced over NVLink and chunk i-1 travels back down, so a step costs ~max(H2D, D2H) instead of their sum.
+// Every rank derives the same chunking from the message size, so the per-chunk kernels pair up across ranks.
+bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaStream_t s) {
+  const CommDesc& d = r.desc;
+  const size_t es = dtype_size(d.dtype), bytes = d.count * es;
+  if (bytes < 2 * pipe_chunk_ || !r.send || !r.recv) return false;
+  cudaPointerAttributes as, ar;
+  if (cudaPointerGetAttributes(&as, r.send) != cudaSuccess || cudaPointerGetAttributes(&ar, r.recv) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  auto is_host = [](const cudaPointerAttributes& a) { return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeUnregistered; };
+  // the decision must be identical on every rank: only taken when BOTH buffers are host memory (SPMD programs pass
+  // the same kind of buffer everywhere)
+  if (!is_host(as) || !is_host(ar)) return false;
+  if (!pipe_buf_[0]) {
+    for (int b = 0; b < kPipeBufs; ++b) {
+      pipe_buf_[b] = (char*)alloc(pipe_chunk_, 4096);
+      MLSLB_CUDA(cudaEventCreateWithFlags(&pipe_h2d_[b], cudaEventDisableTiming));
+      MLSLB_CUDA(cudaEventCreateWithFlags(&pipe_ar_[b], cudaEventDisableTiming));
+      MLSLB_CUDA(cudaEventCreateWithFlags(&pipe_d2h_[b], cudaEventDisableTiming));
+    }
+    MLSLB_CUDA(cudaEventCreateWithFlags(&pipe_start_, cudaEventDisableTiming));
+    int lo = 0, hi = 0;
+    MLSLB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    MLSLB_CUDA(cudaStreamCreateWithPriority(&h2d_stream_, cudaStreamNonBlocking, hi));
+    MLSLB_CUDA(cudaStreamCreateWithPriority(&d2h_stream_, cudaStreamNonBlocking, hi));
+  }
+  const int P = dc.nranks;
+  MLSLB_CUDA(cudaEventRecord(pipe_start_, s));
+  MLSLB_CUDA(cudaStreamWaitEvent(h2d_stream_, pipe_start_, 0));
+  const size_t chunk_elems = pipe_chunk_ / es;
+  int i = 0;
+  for (size_t off = 0; off < d.count; off += chunk_elems, ++i) {
+    const int b = i % kPipeBufs;
+    const size_t cnt = std::min(chunk_elems, d.count - off);
+    if (pipe_used_[b]) MLSLB_CUDA(cudaStreamWaitEvent(h2d_stream_, pipe_d2h_[b], 0));   // buffer drained by its last user
+    MLSLB_CUDA(cudaMemcpyAsync(pipe_buf_[b], (const char*)r.send + off * es, cnt * es, cudaMemcpyHostToDevice, h2d_stream_));
+    MLSLB_CUDA(cudaEventRecord(pipe_h2d_[b], h2d_stream_));
+    MLSLB_CUDA(cudaStreamWaitEvent(s, pipe_h2d_[b], 0));
+    const unsigned long long o = (unsigned long long)(pipe_buf_[b] - slab_);
+    MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, o, o, cnt, d.scale, pick_channels(ceil_div(cnt * es, (size_t)P)), s));
+    MLSLB_CUDA(cudaEventRecord(pipe_ar_[b], s));
+    MLSLB_CUDA(cudaStreamWaitEvent(d2h_stream_, pipe_ar_[b], 0));
+    MLSLB_CUDA(cudaMemcpyAsync((char*)r.recv + off * es, pipe_buf_[b], cnt * es, cudaMemcpyDeviceToHost, d2h_stream_));
+    MLSLB_CUDA(cudaEventRecord(pipe_d2h_[b], d2h_stream_));
+    pipe_used_[b] = true;
+  }
+  // completion of the request = the last copies down
+  for (int b = 0; b < kPipeBufs; ++b)
+    if (pipe_used_[b]) MLSLB_CUDA(cudaStreamWaitEvent(s, pipe_d2h_[b], 0));
+  return true;
 }
 
 }  // namespace

@@ -313,3 +313,21 @@ def test_session_graph_on_device_hybrid():
         assert torch.equal(inp, (M * (mb * lfm * fs * M + (off + fm) * fs + s)).float())
         assert torch.equal(dout, torch.arange(dout.numel(), dtype=torch.float32))
         assert torch.equal(g, D * (own_off + torch.arange(g.numel(), dtype=torch.float32)))
+
+
+def test_host_resident_allreduce_is_pipelined_and_correct():
+    """Pinned host buffers straight through the public call: chunked H2D -> all-reduce -> D2H pipeline."""
+    world, n = 2, (80 << 20) // 4 + 1031          # > 2 chunks of 32 MiB, odd tail
+
+    def body(r, mlsl):
+        hin = (torch.arange(n, dtype=torch.float32) % 1000 + r).pin_memory()
+        hout = torch.empty(n, dtype=torch.float32).pin_memory()
+        mlsl.allreduce(hin, out=hout, scale=0.5)
+        torch.cuda.current_stream().synchronize()
+        return hout[::4099].clone(), hout[-5:].clone()
+
+    outs = run_ranks(world, body, backend="cuda", env={"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20"})
+    base = torch.arange(n, dtype=torch.float32) % 1000
+    ref = (base * 2 + 1) * 0.5
+    for a, b in outs:
+        assert torch.equal(a, ref[::4099]) and torch.equal(b, ref[-5:])
