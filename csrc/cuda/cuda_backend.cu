@@ -233,6 +233,13 @@ class CudaBackend final : public Backend {
   void init();
   cudaStream_t stream_for(int row, int lane);
   int pick_channels(size_t bytes) const;
+  // fp8 all-reduce: one warp per 128-element block and pass; HBM-bound local phases -> up to one 1024-thread CTA per SM
+  int quant_channels(size_t elems) const {
+    size_t blocks = ceil_div(std::max<size_t>(elems, 1), (size_t)128);
+    size_t want = ceil_div(blocks, (size_t)32 * 2);
+    int cap = std::min(kMaxChannels, std::max(1, sm_count_ / std::max(1, ranks_per_device_)));
+    return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)cap));
+  }
   DevComm make_comm(const ProcessGroup& g, int lane) const;
   void drop_stages(CudaReqState* st, bool copied);
   void finish(CommRequest& r, CudaReqState* st);
@@ -543,7 +550,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
           st->residual_elems = n;
         }
         MLSLB_CUDA(launch_allreduce_quant(dc, so, ro, (unsigned long long)((char*)st->qstage - slab_), st->residual, n,
-                                          d.scale, pick_channels(n / 2), s));
+                                          d.scale, quant_channels(n), s));
       } else {
         // very large messages go out as pipelined chunks (reference MLSL_LARGE_MSG_SIZE_MB / _CHUNKS,
         // src/comm_ep.cpp:645-656) so a higher-priority collective can slip in between them

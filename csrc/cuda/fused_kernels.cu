@@ -53,7 +53,10 @@ __device__ __forceinline__ float quant_warp_block(const float4& v, unsigned& pac
   return scale;
 }
 
-__global__ void __launch_bounds__(kCommThreads) k_allreduce_quant(DevComm dc, unsigned long long send_off,
+// The local phases (quantise / dequantise) are HBM bound, so unlike the pure NVLink kernels this one wants the whole
+// GPU: 1024-thread CTAs, up to one per SM.
+constexpr int kQuantThreads = 1024;
+__global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, unsigned long long send_off,
                                                                   unsigned long long recv_off,
                                                                   unsigned long long stage_off, float* residual,
                                                                   size_t count, float out_scale) {
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(kCommThreads) k_allreduce_quant(DevComm dc, un
 cudaError_t launch_allreduce_quant(const DevComm& dc, unsigned long long send_off, unsigned long long recv_off,
                                    unsigned long long stage_off, float* residual, size_t count, float scale,
                                    int channels, cudaStream_t s) {
-  k_allreduce_quant<<<channels, kCommThreads, 0, s>>>(dc, send_off, recv_off, stage_off, residual, count, scale);
+  k_allreduce_quant<<<channels, kQuantThreads, 0, s>>>(dc, send_off, recv_off, stage_off, residual, count, scale);
   return cudaGetLastError();
 }
 
