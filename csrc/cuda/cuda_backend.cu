@@ -558,6 +558,11 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
         if (ctx_->env.large_msg_mb && n * es >= ctx_->env.large_msg_mb * (size_t)1048576 && ctx_->env.large_msg_chunks > 1 &&
             ctx_->env.msg_priority)
           chunks = (size_t)ctx_->env.large_msg_chunks;
+        // NVLS: measured on 8xB200 the multimem kernel sustains 767 GB/s bus bandwidth on 256 MiB launches but only
+        // ~580 GB/s on a single 1 GiB launch; giant messages therefore go out as back-to-back 256 MiB launches
+        // (same stream, the next handshake overlaps the previous launch's tail).  MLSL_NVLS_CHUNK_MB=0 disables.
+        static const size_t nvls_chunk = (size_t)(getenv("MLSL_NVLS_CHUNK_MB") ? atoi(getenv("MLSL_NVLS_CHUNK_MB")) : 256) << 20;
+        if (dc.mc && nvls_chunk && n * es >= nvls_chunk + nvls_chunk / 2) chunks = std::max(chunks, ceil_div(n * es, nvls_chunk));
         size_t per = round_up(ceil_div(n, chunks), 256);
         for (size_t off = 0; off < n; off += per) {
           size_t cnt = std::min(per, n - off);
