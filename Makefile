@@ -66,7 +66,14 @@ sass: $(LIB)
 	@mkdir -p profiles/sass
 	cuobjdump -sass $(LIB) > profiles/sass/libmlsl_b200.sass
 
+# ThreadSanitizer run of the host runtime (ring, progress threads, shm protocol): 4 in-process ranks, hybrid 2x2
+tsan:
+	$(MAKE) CXX=/usr/bin/g++ TSAN=1 BUILD=/tmp/mlsl_tsan/build LIBDIR=/tmp/mlsl_tsan/lib LIB=/tmp/mlsl_tsan/lib/libmlsl_b200.so /tmp/mlsl_tsan/lib/libmlsl_b200.so
+	/usr/bin/g++ -O1 -g -std=c++17 -fsanitize=thread -pthread -Iinclude -Icsrc csrc/tests/mlsl_functional_test.cpp -o /tmp/mlsl_tsan/ftest -L/tmp/mlsl_tsan/lib -lmlsl_b200 -Wl,-rpath,/tmp/mlsl_tsan/lib
+	cd /tmp/mlsl_tsan && TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" ./ftest 2 1 0 1 --inproc 4 | tail -1
+	cd /tmp/mlsl_tsan && MLSL_NUM_SERVERS=2 MLSL_MSG_PRIORITY=1 TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" ./ftest 1 0 1 0 --inproc 4 | tail -1
+
 clean:
 	rm -rf $(BUILD) $(LIB) bin
 
-.PHONY: all clean sass
+.PHONY: all clean sass tsan

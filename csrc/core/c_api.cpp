@@ -303,6 +303,23 @@ int mlsl_inproc_world_create(int nranks, int* world_id) { C_GUARD(*need(world_id
 int mlsl_inproc_world_destroy(int world_id) { C_GUARD(mlslb::inproc_world_destroy(world_id)) }
 int mlsl_inproc_bind_thread(int world_id, int rank) { C_GUARD(mlslb::inproc_bind_thread(world_id, rank)) }
 int mlsl_inproc_unbind_thread(void) { C_GUARD(mlslb::inproc_unbind_thread()) }
+// ---- file-IO offload ----
+static mlslb::RankContext* io_ctx() {
+  mlslb::RankContext* c = mlslb::current_context();
+  if (!c->initialized) throw mlslb::Error("MLSL is not initialized");
+  return c;
+}
+int mlsl_io_open(mlsl_environment, const char* path, mlsl_handle_t* f) { C_GUARD(*need(f) = U(mlslb::io_open(io_ctx(), path))) }
+int mlsl_io_size(mlsl_handle_t f, size_t* n) { C_GUARD(*need(n) = mlslb::io_size(H<mlslb::IoFile>(f))) }
+int mlsl_io_read_nb(mlsl_handle_t f, void* dst, size_t bytes, long long off, mlsl_handle_t* r) {
+  C_GUARD(*need(r) = U(mlslb::io_read_nb(H<mlslb::IoFile>(f), dst, bytes, off)))
+}
+int mlsl_io_open_read_close_nb(mlsl_environment, const char* path, void* dst, size_t bytes, long long off, mlsl_handle_t* r) {
+  C_GUARD(*need(r) = U(mlslb::io_open_read_close_nb(io_ctx(), path, dst, bytes, off)))
+}
+int mlsl_io_test(mlsl_handle_t r, int* done, size_t* n) { C_GUARD(size_t v = 0; *need(done) = mlslb::io_test(H<mlslb::IoRequest>(r), &v) ? 1 : 0; if (n) *n = v) }
+int mlsl_io_wait(mlsl_handle_t r, size_t* n) { C_GUARD(size_t v = mlslb::io_wait(H<mlslb::IoRequest>(r)); if (n) *n = v) }
+int mlsl_io_close(mlsl_handle_t f) { C_GUARD(mlslb::io_close(H<mlslb::IoFile>(f))) }
 int mlsl_set_assert_throws(int on) { C_GUARD(mlslb::set_assert_throws(on != 0)) }
 int mlsl_cuda_available(int* available) { C_GUARD(*need(available) = mlslb::cuda_backend_available() ? 1 : 0) }
 

@@ -17,7 +17,7 @@ namespace mlslb {
 static std::atomic<int> g_level{-1};
 static std::atomic<int> g_throw{-1};
 static std::atomic<int> g_rank{-1};
-static void (*g_fail_hook)() = nullptr;
+static std::atomic<void (*)()> g_fail_hook{nullptr};
 
 int log_level() {
   int l = g_level.load(std::memory_order_relaxed);
@@ -43,7 +43,7 @@ bool assert_throws() {
   return t == 1;
 }
 void set_assert_throws(bool on) { g_throw.store(on ? 1 : 0); }
-void set_fail_hook(void (*hook)()) { g_fail_hook = hook; }
+void set_fail_hook(void (*hook)()) { g_fail_hook.store(hook); }
 
 static const char* lvl_name(int l) {
   switch (l) {
@@ -98,7 +98,8 @@ void fail(const char* file, int line, const char* func, const char* cond, const 
   backtrace_symbols_fd(bt, n, 2);
   fflush(stderr);
   static std::atomic<int> once{0};
-  if (g_fail_hook && once.fetch_add(1) == 0) g_fail_hook();
+  auto hook = g_fail_hook.load();
+  if (hook && once.fetch_add(1) == 0) hook();
   _exit(1);
 }
 

@@ -360,6 +360,8 @@ void Backend::pack_blocks(const BlockDesc* blocks, size_t nblocks, size_t local_
   }
 }
 
+void Backend::copy_from_host(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
+
 // ============================================================================================================
 // PointerChecker
 // ============================================================================================================
@@ -609,6 +611,7 @@ void context_init(RankContext* ctx) {
 void context_finalize(RankContext* ctx) {
   if (!ctx->initialized) return;
   if (!ctx->boot->inproc()) remove_signal_handlers();
+  io_shutdown(ctx);
   ctx->progress->drain();
   ctx->boot->barrier();
   ctx->progress.reset();

@@ -147,6 +147,8 @@ class Backend {
   // (reference: the user-side triple loop of tests/examples/mlsl_test/mlsl_test.cpp:214-254).
   virtual void pack_blocks(const BlockDesc* blocks, size_t nblocks, size_t local_fm_count, DType dt,
                            const void* src, void* dst, bool unpack);
+  virtual bool is_device_pointer(const void*) const { return false; }
+  virtual void copy_from_host(void* dst, const void* src, size_t bytes);   // blocking; default memcpy
   virtual void finalize() {}
   virtual std::string describe() const { return name(); }
 };
@@ -260,6 +262,7 @@ struct RankContext {
   std::atomic<int64_t> next_op_uid{0};
   int init_pid = 0;
   bool initialized = false;
+  void* io_service = nullptr;              // file-IO offload thread (fileio.cpp), created on first use
   void* api_env = nullptr;                 // MLSL::impl::EnvironmentImpl bound to this context
 
   ProcessGroup* create_group_by_color(ProcessGroup* parent, int color);   // collective over parent
@@ -280,6 +283,17 @@ void inproc_unbind_thread();
 bool thread_is_inproc_rank();
 std::unique_ptr<Bootstrap> take_thread_bootstrap();   // bootstrap reserved for the calling thread (or null)
 
+// file-IO offload (fileio.cpp)
+struct IoFile;
+struct IoRequest;
+IoFile* io_open(RankContext* ctx, const char* path);
+size_t io_size(IoFile* f);
+void io_close(IoFile* f);
+IoRequest* io_read_nb(IoFile* f, void* dst, size_t bytes, long long offset);
+IoRequest* io_open_read_close_nb(RankContext* ctx, const char* path, void* dst, size_t bytes, long long offset);
+bool io_test(IoRequest* r, size_t* bytes_read);
+size_t io_wait(IoRequest* r);          // frees the request
+void io_shutdown(RankContext* ctx);
 void install_signal_handlers(RankContext* ctx);   // sig_handler.cpp
 void remove_signal_handlers();
 void context_init(RankContext* ctx);        // bootstrap + backend + progress engine + base groups

@@ -161,6 +161,19 @@ class CudaBackend final : public Backend {
     finish(r, st);
   }
 
+  bool is_device_pointer(const void* p) const override {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+  }
+  void copy_from_host(void* dst, const void* src, size_t bytes) override {
+    cudaSetDevice(device_);
+    MLSLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, aux_stream_));
+    MLSLB_CUDA(cudaStreamSynchronize(aux_stream_));
+  }
   void set_user_stream(void* s) override { user_stream_ = (cudaStream_t)s; }
   void* user_stream() override { return (void*)user_stream_; }
   void set_wait_mode(bool stream_ordered) override { stream_wait_ = stream_ordered; }

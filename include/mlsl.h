@@ -247,6 +247,16 @@ int mlsl_inproc_world_create(int nranks, int* world_id);
 int mlsl_inproc_world_destroy(int world_id);
 int mlsl_inproc_bind_thread(int world_id, int rank);
 int mlsl_inproc_unbind_thread(void);
+/* File-IO offload (the reference's EPLIB_fopen / fread_nb / forc_nb / fwait / fclose): reads run on a background thread;
+ * dst may be host memory or, on the CUDA backend, device memory. */
+int mlsl_io_open(mlsl_environment env, const char* path, mlsl_handle_t* file);
+int mlsl_io_size(mlsl_handle_t file, size_t* bytes);
+int mlsl_io_read_nb(mlsl_handle_t file, void* dst, size_t bytes, long long offset, mlsl_handle_t* req);
+int mlsl_io_open_read_close_nb(mlsl_environment env, const char* path, void* dst, size_t bytes, long long offset,
+                               mlsl_handle_t* req);
+int mlsl_io_test(mlsl_handle_t req, int* done, size_t* bytes_read);
+int mlsl_io_wait(mlsl_handle_t req, size_t* bytes_read);
+int mlsl_io_close(mlsl_handle_t file);
 int mlsl_set_assert_throws(int on);                      /* 1: failures return CMLSL_FAILURE instead of exiting */
 int mlsl_cuda_available(int* available);
 

@@ -224,6 +224,13 @@ def _declare(l):
         "mlsl_inproc_world_destroy": [c_int],
         "mlsl_inproc_bind_thread": [c_int, c_int],
         "mlsl_inproc_unbind_thread": [],
+        "mlsl_io_open": [H, c_char_p, P(H)],
+        "mlsl_io_size": [H, P(c_size_t)],
+        "mlsl_io_read_nb": [H, c_void_p, c_size_t, ctypes.c_longlong, P(H)],
+        "mlsl_io_open_read_close_nb": [H, c_char_p, c_void_p, c_size_t, ctypes.c_longlong, P(H)],
+        "mlsl_io_test": [H, P(c_int), P(c_size_t)],
+        "mlsl_io_wait": [H, P(c_size_t)],
+        "mlsl_io_close": [H],
         "mlsl_set_assert_throws": [c_int],
         "mlsl_cuda_available": [P(c_int)],
     }

@@ -78,6 +78,7 @@ def init(wait_mode=None):
     st["device"] = env.is_device_backend()
     st["world_dist"] = None
     st["live"] = {}
+    st["deferred"] = []
     st["stream"] = None
     if st["device"]:
         env.set_wait_mode(wait_mode or "stream")
@@ -92,6 +93,11 @@ def finalize():
         return
     if st.get("world_dist") is not None:
         env.delete_distribution(st["world_dist"])
+    if st.get("device"):
+        torch.cuda.synchronize()
+    for _, ptr in st.get("deferred", []):
+        env.free(ptr)
+    st["deferred"] = []
     for ptr in list(st["live"].keys()):
         env.free(ptr)
     st["live"].clear()
@@ -131,13 +137,42 @@ def world_distribution():
 
 
 class _CudaMem:
-    """Minimal CUDA-array-interface carrier so torch can wrap library memory without copying."""
+    """Minimal CUDA-array-interface carrier so torch can wrap library memory without copying.  torch keeps this object
+    alive for as long as any tensor / view uses the storage; when `owner` is given, dropping the last of them returns
+    the block to the symmetric heap - deferred until the work queued on the stream at that moment has finished."""
 
-    def __init__(self, ptr, nbytes):
+    def __init__(self, ptr, nbytes, owner=None):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        self._ptr, self._owner = ptr, owner
+
+    def __del__(self):
+        st = self._owner
+        if st is None or st.get("env") is None or self._ptr not in st.get("live", {}):
+            return
+        try:
+            del st["live"][self._ptr]
+            ev = torch.cuda.Event()
+            ev.record()
+            st["deferred"].append((ev, self._ptr))
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
 
 
-def tensor_from_address(ptr, shape, dtype, device=None):
+def _sweep_deferred(st):
+    """Free heap blocks whose last user has been garbage collected and whose stream work has completed."""
+    pend = st.get("deferred")
+    if not pend:
+        return
+    keep = []
+    for ev, ptr in pend:
+        if ev.query():
+            st["env"].free(ptr)
+        else:
+            keep.append((ev, ptr))
+    st["deferred"] = keep
+
+
+def tensor_from_address(ptr, shape, dtype, device=None, _owner=None):
     """Zero-copy torch view of `numel*itemsize` bytes at `ptr` (device memory on the CUDA backend, host otherwise)."""
     numel = 1
     for s in shape:
@@ -145,7 +180,7 @@ def tensor_from_address(ptr, shape, dtype, device=None):
     nbytes = max(numel, 1) * torch.empty((), dtype=dtype).element_size()
     if is_device():
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        raw = torch.as_tensor(_CudaMem(ptr, nbytes), device=dev)
+        raw = torch.as_tensor(_CudaMem(ptr, nbytes, _owner), device=dev)
     else:
         buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
         raw = torch.frombuffer(buf, dtype=torch.uint8)
@@ -160,9 +195,11 @@ def alloc_tensor(shape, dtype=torch.float32, zero=True):
     for s in shape:
         numel *= int(s)
     nbytes = max(numel, 1) * torch.empty((), dtype=dtype).element_size()
+    st = _state()
+    _sweep_deferred(st)
     ptr = env().alloc(nbytes, 256)
-    _state()["live"][ptr] = nbytes
-    t = tensor_from_address(ptr, tuple(shape), dtype)
+    st["live"][ptr] = nbytes
+    t = tensor_from_address(ptr, tuple(shape), dtype, _owner=st if st.get("device") else None)
     if zero:
         t.zero_()
     return t

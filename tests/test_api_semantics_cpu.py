@@ -308,3 +308,27 @@ except Exception as e:
     procs[1].communicate(timeout=120)
     assert "FAILFAST" in out0 and "True" in out0, out0
     assert float(out0.split("FAILFAST")[1].split()[0]) < 30
+
+
+def test_file_io_offload(tmp_path):
+    import numpy as np
+    data = np.arange(100000, dtype=np.float32)
+    path = str(tmp_path / "blob.bin")
+    data.tofile(path)
+
+    def body(r, mlsl):
+        from mlsl_b200.utils.fileio import File, read_file_nb
+        f = File(path)
+        assert f.size() == data.nbytes
+        a = torch.zeros(1000)
+        b = torch.zeros(500)
+        ra = f.read_nb(a, offset=4 * 1000 * r)
+        rb = read_file_nb(path, b, offset=4 * 50000)
+        na, nb = ra.wait(), rb.wait()
+        f.close()
+        return na, nb, a.clone(), b.clone()
+
+    for r, (na, nb, a, b) in enumerate(run_ranks(2, body)):
+        assert (na, nb) == (4000, 2000)
+        assert torch.equal(a, torch.arange(1000 * r, 1000 * r + 1000, dtype=torch.float32))
+        assert torch.equal(b, torch.arange(50000, 50500, dtype=torch.float32))

@@ -1,0 +1,72 @@
+"""Column/Row-parallel linear layers (model parallelism of the reference, activation exchange case 1) vs a single
+process MLP: forward values and all gradients.  CPU (host backend) always; CUDA (fused GEMM+RS forward) marked gpu."""
+import threading
+
+import pytest
+import torch
+
+from conftest import run_ranks
+
+_lock = threading.Lock()
+D_IN, D_HID, D_OUT, M = 64, 512, 256, 256
+
+
+def _full_weights():
+    g = torch.Generator().manual_seed(5)
+    w1 = torch.randn(D_HID, D_IN, generator=g) * 0.1
+    w2 = torch.randn(D_OUT, D_HID, generator=g) * 0.1
+    x = torch.randn(M, D_IN, generator=g)
+    t = torch.randn(M, D_OUT, generator=g)
+    return w1, w2, x, t
+
+
+def _run(world, backend, dtype, tol):
+    def body(r, mlsl):
+        from mlsl_b200.parallel.tensor_parallel import ColumnParallelLinear, RowParallelLinear, gather_rows
+        dev = "cuda" if backend == "cuda" else "cpu"
+        w1, w2, x, t = _full_weights()
+        e = mlsl.env()
+        dist = e.create_distribution(1, world)          # pure model parallelism
+        with _lock:
+            col = ColumnParallelLinear(D_IN, D_HID, bias=False, distribution=dist, dtype=dtype, device=dev)
+            row = RowParallelLinear(D_HID, D_OUT, bias=False, distribution=dist, dtype=dtype, device=dev)
+        hs = D_HID // world
+        with torch.no_grad():
+            col.weight.copy_(w1[r * hs:(r + 1) * hs].to(dtype))
+            row.weight.copy_(w2[:, r * hs:(r + 1) * hs].to(dtype))
+        xin = x.to(dev).to(dtype).requires_grad_(True)
+        h = torch.relu(col(xin))
+        y_rows = row(h)                                  # [M / world, D_OUT]
+        y = gather_rows(y_rows, distribution=dist)       # [M, D_OUT]
+        loss = ((y.float() - t.to(dev)) ** 2).mean()
+        loss.backward()
+        if backend == "cuda":
+            torch.cuda.current_stream().synchronize()
+        out = (y.detach().float().cpu(), xin.grad.float().cpu(), col.weight.grad.float().cpu(), row.weight.grad.float().cpu())
+        e.delete_distribution(dist)
+        return out
+
+    env = {"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20"} if backend == "cuda" else None
+    outs = run_ranks(world, body, backend=backend, env=env)
+    w1, w2, x, t = _full_weights()
+    w1r, w2r, xr = (v.to(dtype).float().requires_grad_(True) for v in (w1, w2, x))
+    yr = torch.relu(xr @ w1r.t()) @ w2r.t()
+    ((yr - t) ** 2).mean().backward()
+    hs = D_HID // world
+    for r, (y, gx, gw1, gw2) in enumerate(outs):
+        s = max(1.0, yr.abs().max().item())
+        assert (y - yr.detach()).abs().max().item() <= tol * s
+        assert (gx - xr.grad).abs().max().item() <= tol * max(1e-3, xr.grad.abs().max().item()) * 4
+        assert (gw1 - w1r.grad[r * hs:(r + 1) * hs]).abs().max().item() <= tol * max(1e-3, w1r.grad.abs().max().item()) * 4
+        assert (gw2 - w2r.grad[:, r * hs:(r + 1) * hs]).abs().max().item() <= tol * max(1e-3, w2r.grad.abs().max().item()) * 4
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_tensor_parallel_mlp_cpu(world):
+    _run(world, "host", torch.float32, 1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2])
+def test_tensor_parallel_mlp_gpu_fused_gemm_rs(world):
+    _run(world, "cuda", torch.bfloat16, 3e-2)
