@@ -34,7 +34,8 @@ constexpr size_t kSeqRowBytes = (size_t)kMaxChannels * sizeof(unsigned long long
 constexpr int kPadRows = kMaxGroupRows * 2;
 constexpr size_t kPadBytes = kPadRows * kPadRowBytes;
 constexpr size_t kSeqBase = kPadBytes;
-constexpr size_t kHeaderBytes = (kPadBytes + kPadRows * kSeqRowBytes + ((size_t)1 << 20) - 1) >> 20 << 20;
+constexpr size_t kLLBase = (kPadBytes + kPadRows * kSeqRowBytes + 4095) & ~(size_t)4095;   // low-latency arenas, one per row
+constexpr size_t kHeaderBytes = (kLLBase + kLLRows * kLLRowBytes + ((size_t)1 << 20) - 1) >> 20 << 20;
 
 struct StageBuf {
   void* user;
@@ -96,6 +97,7 @@ class CudaBackend final : public Backend {
     // fresh row: zero my pads and ticket counters, then make sure every member has done so before anyone signals
     MLSLB_CUDA(cudaMemsetAsync(slab_ + (size_t)g.row * 2 * kPadRowBytes, 0, 2 * kPadRowBytes, aux_stream_));
     MLSLB_CUDA(cudaMemsetAsync(slab_ + kSeqBase + (size_t)g.row * 2 * kSeqRowBytes, 0, 2 * kSeqRowBytes, aux_stream_));
+    if (g.row < kLLRows) MLSLB_CUDA(cudaMemsetAsync(slab_ + kLLBase + (size_t)g.row * kLLRowBytes, 0, kLLRowBytes, aux_stream_));
     MLSLB_CUDA(cudaStreamSynchronize(aux_stream_));
     if (!g.is_world) ctx_->group_barrier(&g);
   }
@@ -402,6 +404,7 @@ DevComm CudaBackend::make_comm(const ProcessGroup& g, int lane) const {
   dc.timeout_ns = ctx_->env.watchdog_sec > 0 ? (unsigned long long)ctx_->env.watchdog_sec * 1000000000ull : 0ull;
   dc.err = err_dev_;
   for (int i = 0; i < g.size(); ++i) dc.slab[i] = peer_slab_[g.members[i]];
+  dc.ll_off = (lane == 0 && g.row >= 0 && g.row < kLLRows) ? (unsigned)(kLLBase + (size_t)g.row * kLLRowBytes) : 0u;
   // NVLS only for groups spanning every rank in world order (the multicast object covers exactly those devices)
   dc.mc = nullptr;
   // (and only from 4 ranks up: per direction NVLS moves S(1+1/N) bytes, the peer-to-peer kernel 2S(N-1)/N)
@@ -492,6 +495,15 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   }
   const int P = g->size(), me = g->idx;
   DevComm dc = make_comm(*g, r.lane);
+
+  // ---- tiny all-reduce: low-latency push path, works on any device-accessible buffers (no staging) ---------------
+  static const bool ll_enabled = !(getenv("MLSL_LL") && atoi(getenv("MLSL_LL")) == 0);
+  if (d.kind == OpKind::ALLREDUCE && !d.compress && ll_enabled && dc.ll_off && n * es <= kLLMaxBytes && n > 0 &&
+      (((uintptr_t)r.send | (uintptr_t)r.recv) & 7) == 0 && (d.dtype != DType::F64 || true) &&
+      (owns(r.send, n * es) || is_device_pointer(r.send)) && (owns(r.recv, n * es) || is_device_pointer(r.recv))) {
+    MLSLB_CUDA(launch_allreduce_ll(dc, d.dtype, d.rop, r.send, r.recv, n, d.scale, s));
+    return;
+  }
 
   // ---- host-resident all-reduce: chunked H2D -> kernel -> D2H pipeline instead of staging the whole message ------
   if (d.kind == OpKind::ALLREDUCE && !d.compress && launch_host_pipelined(r, dc, s)) return;

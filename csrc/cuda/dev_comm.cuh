@@ -38,6 +38,7 @@ struct DevComm {
   int* err;                   // host-mapped error word (0 = ok)
   char* slab[kMaxDevRanks];   // slab base of every member (group order) in MY address space
   char* mc;                   // multicast mapping of the slabs (NVLS) or nullptr
+  unsigned ll_off;            // byte offset of this row's low-latency arena inside every slab (0 = none)
 };
 
 struct PeerTable {            // lives in shared memory

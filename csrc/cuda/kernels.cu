@@ -221,6 +221,107 @@ __global__ void __launch_bounds__(kCommThreads) k_allreduce(DevComm dc, unsigned
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// K1, latency path ("LL"): one CTA; thread i owns bytes [8i, 8i+8) of the message.  It stores {d0, flag, d1, flag}
+// (16 bytes, each (data, flag) half is one atomic 8-byte unit) into slot [parity][me][i] of EVERY member's arena, then
+// polls the P slots of its own arena until both flags carry the current ticket, reduces in fixed rank order and
+// writes the result.  No opening handshake, no fence, no closing handshake: the critical path is one NVLink one-way
+// trip.  Two parities suffice: a rank can enter collective t+2 only after it has received every peer's t+1 data,
+// which a peer sends only after it finished reading t.  Send/recv may be ANY device-accessible pointers (the data
+// goes through registers), so small foreign tensors need no staging either.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T, typename Op>
+__global__ void __launch_bounds__(1024) k_allreduce_ll(DevComm dc, const char* send, char* recv, size_t bytes, float scale) {
+  using VT = VecTraits<T>;
+  using Acc = typename VT::Acc;
+  constexpr int N = VT::N, H = N / 2 > 0 ? N / 2 : 1;          // elements per 8 bytes
+  __shared__ unsigned long long s_ticket;
+  if (threadIdx.x == 0) {
+    unsigned long long* seq = reinterpret_cast<unsigned long long*>(dc.slab[dc.me] + dc.seq_off);   // channel 0
+    s_ticket = *seq + 1;
+    *seq = s_ticket;
+  }
+  __syncthreads();
+  const unsigned flag = (unsigned)s_ticket;
+  const int P = dc.nranks, me = dc.me;
+  const size_t n8 = (bytes + 7) / 8;
+  const size_t par = (size_t)(s_ticket & 1ull) * kMaxDevRanks * kLLSlotBytes;
+  for (size_t i = threadIdx.x; i < n8; i += blockDim.x) {
+    // my 8 bytes (zero padded at the tail)
+    unsigned d0 = 0, d1 = 0;
+    if (i * 8 + 8 <= bytes) {
+      const uint2 v = *reinterpret_cast<const uint2*>(send + i * 8);
+      d0 = v.x;
+      d1 = v.y;
+    } else {
+      unsigned char tmp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (size_t b = i * 8; b < bytes; ++b) tmp[b - i * 8] = (unsigned char)send[b];
+      d0 = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((unsigned)tmp[3] << 24);
+      d1 = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((unsigned)tmp[7] << 24);
+    }
+    for (int q = 0; q < P; ++q) {
+      int p = me + q;
+      if (p >= P) p -= P;
+      char* slot = dc.slab[p] + dc.ll_off + par + (size_t)me * kLLSlotBytes + i * 16;
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(slot), "r"(d0), "r"(flag), "r"(d1), "r"(flag) : "memory");
+    }
+    // collect
+    Acc acc[N];
+    bool first = true, ok = true;
+    unsigned long long t0 = 0;
+    for (int p = 0; p < P && ok; ++p) {
+      const char* slot = dc.slab[me] + dc.ll_off + par + (size_t)p * kLLSlotBytes + i * 16;
+      uint4 v;
+      unsigned spins = 0;
+      for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(slot) : "memory");
+        if (v.y == flag && v.w == flag) break;
+        if ((++spins & 0x3ff) == 0) {
+          if (!t0) t0 = globaltimer_ns();
+          if (*(volatile int*)dc.err != 0 || (dc.timeout_ns && globaltimer_ns() - t0 > dc.timeout_ns)) {
+            *(volatile int*)dc.err = 1000 + dc.me;
+            ok = false;
+            break;
+          }
+        }
+      }
+      Acc b[N];
+      VT::unpack(make_uint4(v.x, v.z, 0u, 0u), b);
+      if (first) {
+#pragma unroll
+        for (int k = 0; k < H; ++k) acc[k] = b[k];
+        first = false;
+      } else {
+#pragma unroll
+        for (int k = 0; k < H; ++k) acc[k] = Op::apply(acc[k], b[k]);
+      }
+    }
+    if (!ok) break;
+    if (scale != 1.0f) {
+#pragma unroll
+      for (int k = 0; k < H; ++k) acc[k] = VT::scale(acc[k], scale);
+    }
+#pragma unroll
+    for (int k = H; k < N; ++k) acc[k] = acc[0];
+    const uint4 r = VT::pack(acc);
+    if (i * 8 + 8 <= bytes) {
+      *reinterpret_cast<uint2*>(recv + i * 8) = make_uint2(r.x, r.y);
+    } else {
+      const unsigned w[2] = {r.x, r.y};
+      for (size_t b = i * 8; b < bytes; ++b) recv[b] = (char)((w[(b - i * 8) >> 2] >> (((b - i * 8) & 3) * 8)) & 0xff);
+    }
+  }
+}
+
+template <typename T, typename Op>
+static cudaError_t launch_ll_t(const DevComm& dc, const void* send, void* recv, size_t count, float scale, cudaStream_t s) {
+  const size_t bytes = count * sizeof(T);
+  const size_t n8 = (bytes + 7) / 8;
+  int threads = (int)std::min<size_t>(1024, std::max<size_t>(32, (n8 + 31) / 32 * 32));
+  k_allreduce_ll<T, Op><<<1, threads, 0, s>>>(dc, (const char*)send, (char*)recv, bytes, scale);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K2 / K5: pull-reduce.  out[i] = scale * op_p send_p[base + i] for i < count, written to MY recv buffer only.
 // ReduceScatter: every rank active with base = me * count.  Reduce: only the root is active (base 0); the
 // others just keep their send buffers alive until the closing handshake.
@@ -414,6 +515,12 @@ static cudaError_t launch_rp_t(const DevComm& dc, unsigned long long so, unsigne
 cudaError_t launch_allreduce(const DevComm& dc, DType dt, RedOp op, unsigned long long send_off,
                              unsigned long long recv_off, size_t count, float scale, int channels, cudaStream_t s) {
   MLSLB_DISPATCH_T_OP(dt, op, (launch_ar_t<TT, OO>(dc, send_off, recv_off, count, scale, channels, s)))
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_allreduce_ll(const DevComm& dc, DType dt, RedOp op, const void* send, void* recv, size_t count,
+                                float scale, cudaStream_t s) {
+  MLSLB_DISPATCH_T_OP(dt, op, (launch_ll_t<TT, OO>(dc, send, recv, count, scale, s)))
   return cudaErrorInvalidValue;
 }
 

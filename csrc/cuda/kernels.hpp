@@ -29,6 +29,14 @@ cudaError_t launch_barrier(const DevComm& dc, cudaStream_t s);
 // K1 all-reduce: fused reduce-scatter + all-gather over peer memory, scale epilogue
 cudaError_t launch_allreduce(const DevComm& dc, DType dt, RedOp op, unsigned long long send_off,
                              unsigned long long recv_off, size_t count, float scale, int channels, cudaStream_t s);
+// K1, latency path: messages <= kLLMaxBytes travel as (data, flag) pairs pushed straight into every peer's arena -
+// one NVLink one-way trip, no handshake, no fence (csrc/cuda/kernels.cu: k_allreduce_ll)
+constexpr size_t kLLMaxBytes = 8192;                                   // payload per rank
+constexpr size_t kLLSlotBytes = 2 * kLLMaxBytes;                       // packed: 8 B data -> 16 B
+constexpr size_t kLLRowBytes = 2 * (size_t)kMaxDevRanks * kLLSlotBytes;   // two parities x sources
+constexpr int kLLRows = 32;                                            // group rows that own an arena
+cudaError_t launch_allreduce_ll(const DevComm& dc, DType dt, RedOp op, const void* send, void* recv, size_t count,
+                                float scale, cudaStream_t s);
 // K2/K5 reduce-scatter and reduce: out[i] = scale * op_p send_p[base + i], i < count (active ranks only)
 cudaError_t launch_reduce_pull(const DevComm& dc, DType dt, RedOp op, unsigned long long send_off,
                                unsigned long long recv_off, size_t base, size_t count, float scale, bool active,

@@ -331,3 +331,41 @@ def test_host_resident_allreduce_is_pipelined_and_correct():
     ref = (base * 2 + 1) * 0.5
     for a, b in outs:
         assert torch.equal(a, ref[::4099]) and torch.equal(b, ref[-5:])
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16, torch.float64, torch.int32, torch.uint8])
+def test_allreduce_low_latency_path(world, dtype):
+    """<= 8 KiB: the flag-in-data (LL) kernel, on heap and on foreign buffers, several calls in a row (parity reuse)."""
+    sizes = [1, 3, 257, 8192 // max(1, torch.empty((), dtype=dtype).element_size())]
+
+    def body(r, mlsl):
+        res = []
+        for n in sizes:
+            for op in ("sum", "max"):
+                x = _make(r, n, dtype).cuda()
+                y = torch.empty_like(x)
+                mlsl.allreduce(x, out=y, op=op, scale=0.5 if (dtype.is_floating_point and op == "sum") else 1.0)
+                h = mlsl.alloc_tensor(n, dtype)
+                h.copy_(x)
+                mlsl.allreduce(h, op=op)
+                torch.cuda.current_stream().synchronize()
+                res.append((y.cpu(), h.cpu()))
+        return res
+
+    outs = _gpu(body, world)
+    k = 0
+    for n in sizes:
+        for op in ("sum", "max"):
+            ins = [_make(r, n, dtype) for r in range(world)]
+            ref = _ref_reduce(ins, op)
+            if dtype == torch.uint8 and op == "sum":
+                ref = ref % 256
+            sc = 0.5 if (dtype.is_floating_point and op == "sum") else 1.0
+            tol = 0 if not dtype.is_floating_point else {torch.float32: 1e-6, torch.float64: 1e-12}.get(dtype, 4e-2)
+            for r in range(world):
+                y, h = outs[r][k]
+                assert torch.allclose(y.to(ref.dtype), ref * sc, rtol=tol, atol=tol * 4), (n, op)
+                assert torch.allclose(h.to(ref.dtype), ref, rtol=tol, atol=tol * 4), (n, op)
+                assert torch.equal(y, outs[0][k][0]) and torch.equal(h, outs[0][k][1])
+            k += 1
