@@ -174,7 +174,10 @@ class HostBackend final : public Backend {
 
   void finalize() override {
     Bootstrap* b = ctx_->boot.get();
-    b->barrier();
+    try {
+      b->barrier();
+    } catch (const std::exception&) {   // poisoned job: still unmap
+    }
     for (int p = 0; p < world_; ++p)
       if (base_[p]) b->release_region(base_[p], region_bytes_, p == rank_, "hheap");
     base_.clear();

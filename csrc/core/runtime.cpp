@@ -610,27 +610,40 @@ void context_init(RankContext* ctx) {
 
 void context_finalize(RankContext* ctx) {
   if (!ctx->initialized) return;
+  ctx->initialized = false;   // never torn down twice, also when a step below fails
+  // Every step runs even when an earlier one failed (a poisoned job throws at the first barrier): a failing rank must
+  // still stop its threads and give its memory back; the first error is re-thrown at the end.
+  std::string first_error;
+  auto step = [&](auto&& fn) {
+    try {
+      fn();
+    } catch (const std::exception& e) {
+      if (first_error.empty()) first_error = e.what();
+    }
+  };
   if (!ctx->boot->inproc()) remove_signal_handlers();
-  io_shutdown(ctx);
-  ctx->progress->drain();
-  ctx->boot->barrier();
-  ctx->progress.reset();
+  step([&] { io_shutdown(ctx); });
+  step([&] { if (ctx->progress) ctx->progress->drain(); });
+  step([&] { ctx->boot->barrier(); });
+  step([&] { ctx->progress.reset(); });
   if (ctx->global_group != ctx->world_group) {
     ProcessGroup* g = ctx->global_group;
     ctx->global_group = ctx->world_group;
-    ctx->free_group(g);
+    step([&] { ctx->free_group(g); });
   }
-  ctx->backend->group_destroyed(*ctx->world_group);
-  ctx->backend->finalize();
-  ctx->backend.reset();
+  if (ctx->backend) {
+    step([&] { ctx->backend->group_destroyed(*ctx->world_group); });
+    step([&] { ctx->backend->finalize(); });
+    step([&] { ctx->backend.reset(); });
+  }
   delete ctx->world_group;
   delete ctx->self_group;
   ctx->world_group = ctx->self_group = ctx->global_group = nullptr;
-  ctx->boot->barrier();
+  step([&] { ctx->boot->barrier(); });
   ctx->boot.reset();
-  ctx->initialized = false;
   ctx->row_used = 0;
   ctx->quant = QuantConfig();
+  MLSLB_ASSERT(first_error.empty(), "finalize after a failure: %s", first_error.c_str());
 }
 
 }  // namespace mlslb

@@ -95,10 +95,13 @@ class CudaBackend final : public Backend {
     MLSLB_ASSERT(g.size() <= kMaxDevRanks, "device groups are limited to %d ranks (got %d)", kMaxDevRanks, g.size());
     set_device();
     // fresh row: zero my pads and ticket counters, then make sure every member has done so before anyone signals
-    MLSLB_CUDA(cudaMemsetAsync(slab_ + (size_t)g.row * 2 * kPadRowBytes, 0, 2 * kPadRowBytes, aux_stream_));
-    MLSLB_CUDA(cudaMemsetAsync(slab_ + kSeqBase + (size_t)g.row * 2 * kSeqRowBytes, 0, 2 * kSeqRowBytes, aux_stream_));
-    if (g.row < kLLRows) MLSLB_CUDA(cudaMemsetAsync(slab_ + kLLBase + (size_t)g.row * kLLRowBytes, 0, kLLRowBytes, aux_stream_));
-    MLSLB_CUDA(cudaStreamSynchronize(aux_stream_));
+    // (on the row's own stream: every extra stream is one more hardware queue that loop-back ranks sharing a GPU
+    // compete for, and two spinning kernels falsely serialised on one queue dead-lock each other)
+    cudaStream_t zs = stream_for(g.row, 0);
+    MLSLB_CUDA(cudaMemsetAsync(slab_ + (size_t)g.row * 2 * kPadRowBytes, 0, 2 * kPadRowBytes, zs));
+    MLSLB_CUDA(cudaMemsetAsync(slab_ + kSeqBase + (size_t)g.row * 2 * kSeqRowBytes, 0, 2 * kSeqRowBytes, zs));
+    if (g.row < kLLRows) MLSLB_CUDA(cudaMemsetAsync(slab_ + kLLBase + (size_t)g.row * kLLRowBytes, 0, kLLRowBytes, zs));
+    MLSLB_CUDA(cudaStreamSynchronize(zs));
     if (!g.is_world) ctx_->group_barrier(&g);
   }
 
@@ -136,7 +139,7 @@ class CudaBackend final : public Backend {
     auto* st = (CudaReqState*)r.backend_state;
     set_device();
     ensure_events(st);
-    MLSLB_CUDA(cudaEventRecord(st->ready, user_stream_));
+    MLSLB_CUDA(cudaEventRecord(st->ready, ustream()));
   }
 
   void launch(CommRequest& r) override;
@@ -154,8 +157,9 @@ class CudaBackend final : public Backend {
     set_device();
     if (stream_wait_ && st->stages.empty()) {
       // stream-ordered completion: nothing blocks the host
-      if (!inline_stream_) MLSLB_CUDA(cudaStreamWaitEvent(user_stream_, st->done, 0));
+      if (!inline_stream_) MLSLB_CUDA(cudaStreamWaitEvent(ustream(), st->done, 0));
       st->inflight = false;
+      check_error(opkind_name(r.desc.kind));   // a device watchdog hit of an EARLIER operation surfaces here
       return;
     }
     if (st->recorded) MLSLB_CUDA(cudaEventSynchronize(st->done));
@@ -173,10 +177,13 @@ class CudaBackend final : public Backend {
   }
   void copy_from_host(void* dst, const void* src, size_t bytes) override {
     cudaSetDevice(device_);
-    MLSLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, aux_stream_));
-    MLSLB_CUDA(cudaStreamSynchronize(aux_stream_));
+    MLSLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, aux_stream()));
+    MLSLB_CUDA(cudaStreamSynchronize(aux_stream()));
   }
-  void set_user_stream(void* s) override { user_stream_ = (cudaStream_t)s; }
+  void set_user_stream(void* s) override {
+    user_stream_ = (cudaStream_t)s;
+    user_stream_set_ = true;   // null is a valid choice: the legacy default stream
+  }
   void* user_stream() override { return (void*)user_stream_; }
   void set_wait_mode(bool stream_ordered) override { stream_wait_ = stream_ordered; }
 
@@ -189,17 +196,24 @@ class CudaBackend final : public Backend {
       PackPlan plan;
       plan.n = (int)std::min<size_t>(kMaxDevRanks, nblocks - i);
       for (int k = 0; k < plan.n; ++k) plan.b[k] = blocks[i + k];
-      MLSLB_CUDA(launch_pack_blocks(plan, local_fm_count, (int)dtype_size(dt), src, dst, unpack, mx, user_stream_));
+      MLSLB_CUDA(launch_pack_blocks(plan, local_fm_count, (int)dtype_size(dt), src, dst, unpack, mx, ustream()));
     }
   }
 
   void finalize() override {
     set_device();
+    // a poisoned job cannot synchronise any more: release the resources anyway (kernels have watchdog deadlines)
+    auto quiet_barrier = [&] {
+      try {
+        ctx_->boot->barrier();
+      } catch (const std::exception&) {
+      }
+    };
     cudaDeviceSynchronize();
-    ctx_->boot->barrier();
+    quiet_barrier();
     for (size_t p = 0; p < peer_slab_.size(); ++p)
       if (peer_opened_[p]) cudaIpcCloseMemHandle(peer_slab_[p]);
-    ctx_->boot->barrier();
+    quiet_barrier();
     for (auto& s : streams_)
       if (s) cudaStreamDestroy(s);
     if (aux_stream_) cudaStreamDestroy(aux_stream_);
@@ -229,6 +243,18 @@ class CudaBackend final : public Backend {
   std::vector<bool> peer_opened_;
   std::vector<cudaStream_t> streams_;
   cudaStream_t aux_stream_ = nullptr, user_stream_ = nullptr, own_user_stream_ = nullptr;
+  int stream_prio_hi_ = 0;
+  bool user_stream_set_ = false;
+  // both created on first use only (see group_created for why streams are rationed)
+  cudaStream_t aux_stream() {
+    if (!aux_stream_) MLSLB_CUDA(cudaStreamCreateWithPriority(&aux_stream_, cudaStreamNonBlocking, stream_prio_hi_));
+    return aux_stream_;
+  }
+  cudaStream_t ustream() {
+    if (user_stream_set_) return user_stream_;
+    if (!own_user_stream_) MLSLB_CUDA(cudaStreamCreateWithFlags(&own_user_stream_, cudaStreamNonBlocking));
+    return own_user_stream_;
+  }
   bool stream_wait_ = false, inline_stream_ = false;
   // host-buffer pipeline (see launch_host_pipelined)
   static constexpr int kPipeBufs = 3;
@@ -309,9 +335,7 @@ void CudaBackend::init() {
   heap_.reset(kHeaderBytes, slab_bytes_ - kHeaderBytes);
   int lo = 0, hi = 0;
   MLSLB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  MLSLB_CUDA(cudaStreamCreateWithPriority(&aux_stream_, cudaStreamNonBlocking, hi));
-  MLSLB_CUDA(cudaStreamCreateWithFlags(&own_user_stream_, cudaStreamNonBlocking));
-  user_stream_ = own_user_stream_;
+  stream_prio_hi_ = hi;
   streams_.assign(kPadRows, nullptr);
   MLSLB_CUDA(cudaHostAlloc((void**)&err_host_, 64, cudaHostAllocMapped | cudaHostAllocPortable));
   *err_host_ = 0;
@@ -446,7 +470,7 @@ void CudaBackend::launch(CommRequest& r) {
   const CommDesc& d = r.desc;
   ProcessGroup* g = d.group;
   const bool solo = !g || g->size() <= 1;
-  cudaStream_t s = inline_stream_ ? user_stream_ : stream_for(solo || g->row < 0 ? kMaxGroupRows - 1 : g->row, r.lane);
+  cudaStream_t s = inline_stream_ ? ustream() : stream_for(solo || g->row < 0 ? kMaxGroupRows - 1 : g->row, r.lane);
   st->stream = s;
   if (!inline_stream_) MLSLB_CUDA(cudaStreamWaitEvent(s, st->ready, 0));
   launch_single(r, st, s);

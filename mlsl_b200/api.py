@@ -532,9 +532,11 @@ class InprocWorld:
             t.join(timeout)
             if t.is_alive():
                 raise TimeoutError("in-process rank did not finish within %s s" % timeout)
-        for e in errors:
-            if e is not None:
-                raise e
+        failed = [e for e in errors if e is not None]
+        if failed:
+            # the root cause first: peers of a failing rank only report "poisoned" / watchdog follow-up errors
+            root = [e for e in failed if "poisoned" not in str(e) and "watchdog" not in str(e)]
+            raise (root or failed)[0]
         return results
 
     def close(self):

@@ -289,8 +289,9 @@ mlsl.init()
 t = torch.ones(8)
 mlsl.allreduce(t)
 if mlsl.rank() == 1:
+    time.sleep(0.3)          # let the peer leave the first collective
     os.kill(os.getpid(), signal.SIGSEGV)
-time.sleep(0.5)
+time.sleep(1.0)
 t0 = time.time()
 try:
     mlsl.allreduce(t)
@@ -332,3 +333,28 @@ def test_file_io_offload(tmp_path):
         assert (na, nb) == (4000, 2000)
         assert torch.equal(a, torch.arange(1000 * r, 1000 * r + 1000, dtype=torch.float32))
         assert torch.equal(b, torch.arange(50000, 50500, dtype=torch.float32))
+
+
+def test_failing_inproc_rank_tears_down_cleanly():
+    """A rank that raises in the middle of a job: its peers fail fast (poison), every context is torn down without
+    crashing the process, the root cause is what the caller sees, and the next world works."""
+    import torch
+    from conftest import run_ranks
+
+    def body(r, mlsl):
+        x = torch.ones(1000)
+        mlsl.allreduce(x)
+        if r == 1:
+            raise ValueError("boom")
+        mlsl.allreduce(x)
+        return x[0].item()
+
+    with pytest.raises(ValueError, match="boom"):
+        run_ranks(2, body, backend="host", env={"MLSL_WATCHDOG_SEC": "3"})
+
+    def body2(r, mlsl):
+        x = torch.ones(10)
+        mlsl.allreduce(x)
+        return x[0].item()
+
+    assert run_ranks(2, body2, backend="host") == [2.0, 2.0]

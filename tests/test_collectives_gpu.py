@@ -365,7 +365,7 @@ def test_allreduce_low_latency_path(world, dtype):
             tol = 0 if not dtype.is_floating_point else {torch.float32: 1e-6, torch.float64: 1e-12}.get(dtype, 4e-2)
             for r in range(world):
                 y, h = outs[r][k]
-                assert torch.allclose(y.to(ref.dtype), ref * sc, rtol=tol, atol=tol * 4), (n, op)
+                assert torch.allclose(y.to(ref.dtype), ref * sc if sc != 1.0 else ref, rtol=tol, atol=tol * 4), (n, op)
                 assert torch.allclose(h.to(ref.dtype), ref, rtol=tol, atol=tol * 4), (n, op)
                 assert torch.equal(y, outs[0][k][0]) and torch.equal(h, outs[0][k][1])
             k += 1
