@@ -338,7 +338,7 @@ void CudaBackend::init() {
   stream_prio_hi_ = hi;
   streams_.assign(kPadRows, nullptr);
   MLSLB_CUDA(cudaHostAlloc((void**)&err_host_, 64, cudaHostAllocMapped | cudaHostAllocPortable));
-  *err_host_ = 0;
+  for (int i = 0; i < 16; ++i) err_host_[i] = 0;
   MLSLB_CUDA(cudaHostGetDevicePointer((void**)&err_dev_, (void*)err_host_, 0));
   if (const char* m = getenv("MLSL_STREAM_MODE")) inline_stream_ = !strcmp(m, "inline");
 
@@ -387,6 +387,10 @@ void CudaBackend::init() {
     if (inproc_) for (auto& kv : per_dev) ranks_per_device_ = std::max(ranks_per_device_, kv.second);
   }
   if (const char* v = getenv("MLSL_RANKS_PER_DEVICE")) ranks_per_device_ = std::max(1, atoi(v));
+  // Loop-back ranks that share a GPU also share its (at most 32) hardware queues with torch's stream pool.  A kernel
+  // that spins for a peer dead-locks as soon as that peer's next kernel is falsely serialised behind it on one queue,
+  // so unless told otherwise every collective runs in line on the caller's stream: one stream per rank, program order.
+  if (!getenv("MLSL_STREAM_MODE") && ranks_per_device_ > 1) inline_stream_ = true;
   b->barrier();
   MLSLB_LOG(LOG_DEBUG, "cuda backend up: device %d slab %p (%zu bytes) ranks/device %d", device_, (void*)slab_,
             slab_bytes_, ranks_per_device_);
@@ -446,8 +450,12 @@ void CudaBackend::check_error(const char* what) {
   int code = *err_host_;
   if (code != 0) {
     ctx_->boot->poison(ctx_->rank);
-    MLSLB_ASSERT(false, "device watchdog: %s: a peer never arrived (error code %d, reported by group index %d)", what,
-                 code, code - 1000);
+    const unsigned long long off = ((unsigned long long)(unsigned)err_host_[4] << 32) | (unsigned)err_host_[3];
+    const unsigned long long seen = ((unsigned long long)(unsigned)err_host_[6] << 32) | (unsigned)err_host_[5];
+    MLSLB_ASSERT(false,
+                 "device watchdog: %s: a peer never arrived (error code %d, reported by group index %d; channel %d, "
+                 "waiting on peer index %d, signal word at slab offset 0x%llx held 0x%llx)",
+                 what, code, code - 1000, err_host_[1], err_host_[2], off, seen);
   }
   if (ctx_->boot->poisoned()) MLSLB_ASSERT(false, "job poisoned by rank %d", (int)ctx_->boot->poisoned() - 1);
 }
@@ -519,13 +527,40 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   }
   const int P = g->size(), me = g->idx;
   DevComm dc = make_comm(*g, r.lane);
+  static const bool trace = getenv("MLSL_TRACE_LAUNCH") && atoi(getenv("MLSL_TRACE_LAUNCH")) != 0;
+  if (trace) {
+    fprintf(stderr, "[launch %.6f] r%d %s row %d lane %d idx %d/%d count %zu send %p recv %p stream %p\n", now_ns() * 1e-9,
+            ctx_->rank, opkind_name(d.kind), g->row, r.lane, me, P, n, r.send, r.recv, (void*)s);
+    fflush(stderr);
+  }
 
-  // ---- tiny all-reduce: low-latency push path, works on any device-accessible buffers (no staging) ---------------
+  // ---- tiny all-reduce: low-latency push path -------------------------------------------------------------------
+  // The choice of kernel must be the same on every member, so it only looks at (kind, size, group).  The kernel reads
+  // and writes any device-accessible memory at any alignment (torch tensors are used in place, no staging copy); a
+  // buffer the GPU cannot address (pageable host memory) goes through a small slab scratch block first.
   static const bool ll_enabled = !(getenv("MLSL_LL") && atoi(getenv("MLSL_LL")) == 0);
-  if (d.kind == OpKind::ALLREDUCE && !d.compress && ll_enabled && dc.ll_off && n * es <= kLLMaxBytes && n > 0 &&
-      (((uintptr_t)r.send | (uintptr_t)r.recv) & 7) == 0 && (d.dtype != DType::F64 || true) &&
-      (owns(r.send, n * es) || is_device_pointer(r.send)) && (owns(r.recv, n * es) || is_device_pointer(r.recv))) {
-    MLSLB_CUDA(launch_allreduce_ll(dc, d.dtype, d.rop, r.send, r.recv, n, d.scale, s));
+  if (d.kind == OpKind::ALLREDUCE && !d.compress && ll_enabled && dc.ll_off && n > 0 && n * es <= kLLMaxBytes) {
+    const size_t bytes = n * es;
+    auto dev_ok = [&](const void* p) { return owns(p, bytes) || is_device_pointer(p); };
+    const void* sp = r.send;
+    void* rp = r.recv;
+    const bool in_place = r.send == r.recv;
+    if (!dev_ok(rp)) {
+      StageBuf sb{r.recv, alloc(bytes, 256), bytes, true};
+      if (in_place) MLSLB_CUDA(cudaMemcpyAsync(sb.slab, r.recv, bytes, cudaMemcpyDefault, s));
+      st->stages.push_back(sb);
+      rp = sb.slab;
+      if (in_place) sp = rp;
+    }
+    if (!in_place && !dev_ok(sp)) {
+      StageBuf sb{(void*)r.send, alloc(bytes, 256), bytes, false};
+      MLSLB_CUDA(cudaMemcpyAsync(sb.slab, r.send, bytes, cudaMemcpyDefault, s));
+      st->stages.push_back(sb);
+      sp = sb.slab;
+    }
+    MLSLB_CUDA(launch_allreduce_ll(dc, d.dtype, d.rop, sp, rp, n, d.scale, s));
+    for (auto& sb : st->stages)
+      if (sb.copy_out) MLSLB_CUDA(cudaMemcpyAsync(sb.user, sb.slab, sb.bytes, cudaMemcpyDefault, s));
     return;
   }
 

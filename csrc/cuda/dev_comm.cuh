@@ -101,7 +101,18 @@ __device__ __forceinline__ bool spin_on(const DevComm& dc, const unsigned long l
     if ((++spins & 0x3ff) == 0) {
       if (*(volatile int*)dc.err != 0) return false;               // another CTA / the host already gave up
       if (dc.timeout_ns && globaltimer_ns() - t0 > dc.timeout_ns) {
-        *(volatile int*)dc.err = 1000 + dc.me;
+        // post-mortem for the host: which word (slab offset), what it held, which CTA / waiting thread
+        volatile int* e = (volatile int*)dc.err;
+        const unsigned long long off = (unsigned long long)((const char*)word - dc.slab[dc.me]);
+        const unsigned long long seen = ld_relaxed_sys(word);
+        e[1] = (int)blockIdx.x;
+        e[2] = (int)threadIdx.x;
+        e[3] = (int)(off & 0xffffffffull);
+        e[4] = (int)(off >> 32);
+        e[5] = (int)(seen & 0xffffffffull);
+        e[6] = (int)(seen >> 32);
+        __threadfence_system();
+        e[0] = 1000 + dc.me;
         return false;
       }
     }

@@ -245,16 +245,17 @@ __global__ void __launch_bounds__(1024) k_allreduce_ll(DevComm dc, const char* s
   const int P = dc.nranks, me = dc.me;
   const size_t n8 = (bytes + 7) / 8;
   const size_t par = (size_t)(s_ticket & 1ull) * kMaxDevRanks * kLLSlotBytes;
+  const bool al_in = ((unsigned long long)send & 7ull) == 0, al_out = ((unsigned long long)recv & 7ull) == 0;
   for (size_t i = threadIdx.x; i < n8; i += blockDim.x) {
-    // my 8 bytes (zero padded at the tail)
+    // my 8 bytes (zero padded at the tail; byte by byte when the user's view is not 8-byte aligned)
     unsigned d0 = 0, d1 = 0;
-    if (i * 8 + 8 <= bytes) {
+    if (al_in && i * 8 + 8 <= bytes) {
       const uint2 v = *reinterpret_cast<const uint2*>(send + i * 8);
       d0 = v.x;
       d1 = v.y;
     } else {
       unsigned char tmp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (size_t b = i * 8; b < bytes; ++b) tmp[b - i * 8] = (unsigned char)send[b];
+      for (size_t b = i * 8; b < bytes && b < i * 8 + 8; ++b) tmp[b - i * 8] = (unsigned char)send[b];
       d0 = tmp[0] | (tmp[1] << 8) | (tmp[2] << 16) | ((unsigned)tmp[3] << 24);
       d1 = tmp[4] | (tmp[5] << 8) | (tmp[6] << 16) | ((unsigned)tmp[7] << 24);
     }
@@ -303,11 +304,11 @@ __global__ void __launch_bounds__(1024) k_allreduce_ll(DevComm dc, const char* s
 #pragma unroll
     for (int k = H; k < N; ++k) acc[k] = acc[0];
     const uint4 r = VT::pack(acc);
-    if (i * 8 + 8 <= bytes) {
+    if (al_out && i * 8 + 8 <= bytes) {
       *reinterpret_cast<uint2*>(recv + i * 8) = make_uint2(r.x, r.y);
     } else {
       const unsigned w[2] = {r.x, r.y};
-      for (size_t b = i * 8; b < bytes; ++b) recv[b] = (char)((w[(b - i * 8) >> 2] >> (((b - i * 8) & 3) * 8)) & 0xff);
+      for (size_t b = i * 8; b < bytes && b < i * 8 + 8; ++b) recv[b] = (char)((w[(b - i * 8) >> 2] >> (((b - i * 8) & 3) * 8)) & 0xff);
     }
   }
 }

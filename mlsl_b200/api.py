@@ -504,9 +504,16 @@ def cuda_available():
 
 
 class InprocWorld:
-    """N virtual ranks inside this process (threads).  Used by the tests and for single-GPU loopback."""
+    """N virtual ranks inside this process (threads).  Used by the tests and for single-GPU loopback.
+
+    Loop-back ranks on the CUDA backend are threads of ONE CUDA context whose kernels wait for each other, so nothing
+    may synchronise that context behind their back: set CUDA_MODULE_LOADING=EAGER (lazy loading synchronises on the
+    first launch of every kernel) and CUDA_DEVICE_MAX_CONNECTIONS=32 before CUDA is initialised.  Both are set here
+    when the process has not chosen otherwise, which only helps if no CUDA call was made yet."""
 
     def __init__(self, nranks):
+        import os
+        os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
         wid = c_int()
         check(_lib.lib().mlsl_inproc_world_create(nranks, ctypes.byref(wid)))
         self.world_id, self.nranks = wid.value, nranks

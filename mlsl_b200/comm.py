@@ -29,9 +29,29 @@ _GROUPS = {"data": GroupType.DATA, "model": GroupType.MODEL, "global": GroupType
 
 
 def _state():
+    ov = getattr(_tls, "override", None)
+    if ov is not None:
+        return ov
     if getattr(_tls, "bound", False):
         return _tls.__dict__
     return _process_state
+
+
+class use_state:
+    """Run a block with the library state captured on another thread (`comm._state()` there).  Autograd executes the
+    backward of CUDA functions on its own device thread, which is not bound to any in-process virtual rank."""
+
+    def __init__(self, state):
+        self.state = state
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "override", None)
+        _tls.override = self.state
+        return self
+
+    def __exit__(self, *exc):
+        _tls.override = self.prev
+        return False
 
 
 def bind_thread_state():

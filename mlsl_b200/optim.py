@@ -30,6 +30,7 @@ class DistributedOptimizer:
     def __init__(self, params, lr=0.1, momentum=0.0, weight_decay=0.0, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8,
                  bucket_mb=64, mode=None, compress=False, distribution=None, average=True):
         self.env = comm.env()
+        self._state = comm._state()   # gradient hooks fire on autograd's device thread
         self.params = [p for p in params if p.requires_grad]
         assert self.params, "no trainable parameters"
         self.dist = distribution if distribution is not None else comm.world_distribution()
@@ -120,7 +121,8 @@ class DistributedOptimizer:
             b = self._bucket_of[p]
             b.pending -= 1
             if b.pending == 0:
-                self._start(b)
+                with comm.use_state(self._state):
+                    self._start(b)
         return hook
 
     def _start(self, b):

@@ -29,6 +29,7 @@ class _RowParallelMatmul(torch.autograd.Function):
         d, g, P, idx = _group_info(distribution, group)
         ctx.save_for_backward(x, w)
         ctx.cfg = (distribution, group)
+        ctx.mlsl_state = comm._state()
         M, N = x.shape[0], w.shape[0]
         use_fused = (fused and comm.is_device() and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and
                      M % (128 * P) == 0 and N % 256 == 0 and x.shape[1] % 64 == 0)
@@ -46,12 +47,13 @@ class _RowParallelMatmul(torch.autograd.Function):
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         distribution, group = ctx.cfg
-        d, g, P, idx = _group_info(distribution, group)
         gy = gy.contiguous()
-        if P > 1:
-            full = comm.allgather(gy.view(-1), group=group, distribution=distribution).view(gy.shape[0] * P, gy.shape[1])
-        else:
-            full = gy
+        with comm.use_state(ctx.mlsl_state):
+            d, g, P, idx = _group_info(distribution, group)
+            if P > 1:
+                full = comm.allgather(gy.view(-1), group=group, distribution=distribution).view(gy.shape[0] * P, gy.shape[1])
+            else:
+                full = gy
         gx = full.to(w.dtype) @ w             # [M, K_local]
         gw = full.to(x.dtype).t() @ x         # [N, K_local]
         return gx, gw, None, None, None
@@ -63,15 +65,17 @@ class _CopyToModelGroup(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, distribution, group):
         ctx.cfg = (distribution, group)
+        ctx.mlsl_state = comm._state()
         return x
 
     @staticmethod
     def backward(ctx, gx):
         distribution, group = ctx.cfg
-        d, g, P, idx = _group_info(distribution, group)
-        if P > 1:
-            gx = gx.contiguous().clone()
-            comm.allreduce(gx.view(-1), group=group, distribution=distribution)
+        with comm.use_state(ctx.mlsl_state):
+            d, g, P, idx = _group_info(distribution, group)
+            if P > 1:
+                gx = gx.contiguous().clone()
+                comm.allreduce(gx.view(-1), group=group, distribution=distribution)
         return gx, None, None
 
 
@@ -120,6 +124,7 @@ class _GatherRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, distribution, group, replicated):
         ctx.cfg = (distribution, group, replicated)
+        ctx.mlsl_state = comm._state()
         d, g, P, idx = _group_info(distribution, group)
         if P == 1:
             return x
@@ -129,11 +134,12 @@ class _GatherRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         distribution, group, replicated = ctx.cfg
-        d, g, P, idx = _group_info(distribution, group)
-        if P == 1:
-            return gy, None, None, None
-        rows = gy.shape[0] // P
-        if replicated:
-            return gy[idx * rows:(idx + 1) * rows].contiguous(), None, None, None
-        out = comm.reduce_scatter(gy.contiguous().view(-1), group=group, distribution=distribution)
-        return out.view(rows, *gy.shape[1:]).clone(), None, None, None
+        with comm.use_state(ctx.mlsl_state):
+            d, g, P, idx = _group_info(distribution, group)
+            if P == 1:
+                return gy, None, None, None
+            rows = gy.shape[0] // P
+            if replicated:
+                return gy[idx * rows:(idx + 1) * rows].contiguous(), None, None, None
+            out = comm.reduce_scatter(gy.contiguous().view(-1), group=group, distribution=distribution)
+            return out.view(rows, *gy.shape[1:]).clone(), None, None, None

@@ -4,6 +4,10 @@ import sys
 import pytest
 
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # loopback ranks share one GPU (see mlsl_b200/__init__.py)
+# Loop-back ranks are threads of ONE CUDA context.  With lazy module loading the first launch of any kernel (ours or
+# torch's) synchronises the context while holding its lock; if a peer rank's kernel is spinning for a third rank whose
+# launch now waits for that lock, the job dead-locks until the watchdog fires.  Load every kernel up front instead.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -82,20 +82,28 @@ def test_allreduce_sizes_scale_out_of_place(n):
         assert torch.allclose(y.double(), ref, rtol=1e-6, atol=1e-6)
 
 
-def test_unaligned_buffers_take_the_scalar_path():
-    world, n = 2, 1001
+@pytest.mark.parametrize("n", [1001, 5001])
+def test_unaligned_buffers(n):
+    """4-byte aligned views: <= 8 KiB the LL kernel goes byte-wise, above it the handshake kernel takes its scalar path.
+    Rank 1 passes a 16-byte aligned view instead - the choice of kernel may not depend on a rank's own alignment."""
+    world = 2
 
     def body(r, mlsl):
         base = mlsl.alloc_tensor(n + 8, torch.float32)
-        v = base[1:n + 1]                           # 4-byte aligned only
+        v = base[1:n + 1] if r == 0 else base[4:n + 4]
         v.copy_(_make(r, n, torch.float32))
         mlsl.allreduce(v)
+        f = torch.zeros(n + 3, device="cuda")[3:]       # foreign (torch-owned) view, 4-byte aligned
+        f.copy_(_make(r, n, torch.float32))
+        mlsl.allreduce(f)
         torch.cuda.current_stream().synchronize()
-        return v.cpu()
+        return v.cpu(), f.cpu()
 
     outs = _gpu(body, world)
     ref = _ref_reduce([_make(r, n, torch.float32) for r in range(world)], "sum").float()
-    assert torch.allclose(outs[0], ref, rtol=1e-6, atol=1e-6) and torch.equal(outs[0], outs[1])
+    for v, f in outs:
+        assert torch.allclose(v, ref, rtol=1e-6, atol=1e-6) and torch.equal(v, outs[0][0])
+        assert torch.allclose(f, ref, rtol=1e-6, atol=1e-6) and torch.equal(f, outs[0][1])
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])
