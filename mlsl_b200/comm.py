@@ -164,11 +164,13 @@ class _CudaMem:
     def __init__(self, ptr, nbytes, owner=None):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
         self._ptr, self._owner = ptr, owner
+        if owner is not None:
+            owner["live"][ptr] = id(self)     # the block belongs to THIS carrier (the address may be recycled later)
 
     def __del__(self):
         st = self._owner
-        if st is None or st.get("env") is None or self._ptr not in st.get("live", {}):
-            return
+        if st is None or st.get("env") is None or st.get("live", {}).get(self._ptr) != id(self):
+            return                            # freed explicitly (free_tensor) or the library is already finalised
         try:
             del st["live"][self._ptr]
             ev = torch.cuda.Event()
@@ -218,7 +220,7 @@ def alloc_tensor(shape, dtype=torch.float32, zero=True):
     st = _state()
     _sweep_deferred(st)
     ptr = env().alloc(nbytes, 256)
-    st["live"][ptr] = nbytes
+    st["live"][ptr] = 0
     t = tensor_from_address(ptr, tuple(shape), dtype, _owner=st if st.get("device") else None)
     if zero:
         t.zero_()

@@ -358,3 +358,25 @@ def test_failing_inproc_rank_tears_down_cleanly():
         return x[0].item()
 
     assert run_ranks(2, body2, backend="host") == [2.0, 2.0]
+
+
+def test_heap_tensor_lifetime_explicit_free_then_recycled_address():
+    """free_tensor() followed by an allocation that recycles the address: the old tensor object dying later must not
+    release the new owner's block (the carrier, not the address, owns the block)."""
+    import torch
+    from conftest import run_ranks
+
+    def body(r, mlsl):
+        from mlsl_b200 import comm
+        st = comm._state()
+        x = mlsl.alloc_tensor(1000, torch.float32)
+        p0 = x.data_ptr()
+        mlsl.free_tensor(x)
+        x2 = mlsl.alloc_tensor(1000, torch.float32)       # recycles p0 while the old `x` object is still alive
+        same = x2.data_ptr() == p0
+        del x                                             # old object dies now
+        y = mlsl.alloc_tensor(1000, torch.float32)
+        return same, y.data_ptr() != x2.data_ptr(), x2.data_ptr() in st["live"]
+
+    for same, distinct, live in run_ranks(1, body, backend="host"):
+        assert distinct and live

@@ -377,3 +377,24 @@ def test_allreduce_low_latency_path(world, dtype):
                 assert torch.allclose(h.to(ref.dtype), ref, rtol=tol, atol=tol * 4), (n, op)
                 assert torch.equal(y, outs[0][k][0]) and torch.equal(h, outs[0][k][1])
             k += 1
+
+
+def test_heap_tensor_explicit_free_then_recycled_address():
+    """free_tensor() + an allocation that recycles the address while the old tensor object is still alive: its later
+    garbage collection must not release the new owner's block (this made two live tensors alias)."""
+    def body(r, mlsl):
+        outs = []
+        for it in range(3):
+            x = mlsl.alloc_tensor(1000, torch.float32)
+            x.fill_(float(r + 1))
+            y = mlsl.alloc_tensor(1000, torch.float32)
+            mlsl.allreduce(x, out=y)
+            torch.cuda.current_stream().synchronize()
+            outs.append((x.data_ptr() != y.data_ptr(), float(y[0]), float(x[0])))
+            mlsl.free_tensor(x)
+            mlsl.free_tensor(y)
+        return outs
+
+    for r, outs in enumerate(_gpu(body, 2)):
+        for distinct, ysum, xval in outs:
+            assert distinct and ysum == 3.0 and xval == float(r + 1)
