@@ -34,7 +34,7 @@ LDFLAGS  += -L$(CUDA_HOME)/lib64 -lcudart_static
 endif
 
 TOOLS := bin/mlslrun
-TESTS := bin/mlsl_functional_test bin/cmlsl_smoke_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
+TESTS := bin/libmlsl_quant_sample.so bin/mlsl_functional_test bin/cmlsl_smoke_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
 
 all: $(LIB) $(TOOLS) $(TESTS)
 
@@ -57,6 +57,10 @@ bin/mlslrun: csrc/tools/mlslrun.cpp
 bin/%: csrc/tests/%.cpp $(LIB)
 	@mkdir -p bin
 	$(CXX) $(CXXFLAGS) -o $@ $< -L$(LIBDIR) -lmlsl_b200 -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
+
+bin/libmlsl_quant_sample.so: csrc/tests/quant_plugin_sample.c
+	@mkdir -p bin
+	gcc -O2 -g -std=gnu99 -Wall -shared -fPIC -o $@ $< -lm
 
 bin/cmlsl_smoke_test: csrc/tests/cmlsl_smoke_test.c $(LIB)
 	@mkdir -p bin

@@ -979,6 +979,10 @@ void Environment::SetQuantizationParams(QuantParams* params) {
   e->quantView->reduce_sum_func_name = strdup(c->quant.reduce_name.c_str());
   e->quantView->block_size = c->quant.block_size;
   e->quantView->elem_in_block = c->quant.elem_in_block;
+  if (!c->quant.lib_path.empty() && c->backend->is_device())
+    MLSLB_LOG(mlslb::LOG_INFO,
+              "quantization library %s: host functions cannot run inside the device kernels - the CUDA backend uses its "
+              "built-in fused fp8 block format (the host backend calls the library)", c->quant.lib_path.c_str());
 }
 QuantParams* Environment::GetQuantizationParams() { return SELF(EnvironmentImpl)->quantView; }
 

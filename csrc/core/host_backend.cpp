@@ -18,6 +18,8 @@
 
 #include "log.hpp"
 #include "numeric.hpp"
+#include <dlfcn.h>
+
 #include "quant.hpp"
 #include "runtime.hpp"
 
@@ -235,6 +237,16 @@ class HostBackend final : public Backend {
 
   void execute(CommRequest& r);
   void exec_quantized_allreduce(CommRequest& r, const ProcessGroup& g, int prow, char* S, char* R);
+  void exec_plugin_allreduce(CommRequest& r, const ProcessGroup& g, int prow, char* S, char* R);
+  void load_quant_plugin();
+  // user-supplied compression library (Environment::SetQuantizationParams with a lib_path)
+  typedef int (*PluginQuant)(void* src, void* dst, size_t count, void* diff, int src_dtype, size_t comp_ratio, int method);
+  typedef int (*PluginDequant)(void* src, void* dst, size_t count);
+  typedef int (*PluginReduce)(const void* in, void* inout, size_t block_count);
+  void* plugin_lib_ = nullptr;
+  PluginQuant plugin_quant_ = nullptr;
+  PluginDequant plugin_dequant_ = nullptr;
+  PluginReduce plugin_reduce_ = nullptr;
 };
 
 void HostBackend::execute(CommRequest& r) {
@@ -330,7 +342,8 @@ void HostBackend::execute(CommRequest& r) {
     case OpKind::BARRIER: break;
     case OpKind::ALLREDUCE: {
       if (d.compress && d.dtype == DType::F32 && d.rop == RedOp::SUM) {
-        exec_quantized_allreduce(r, g, prow, S, R);
+        if (ctx_->quant.set && !ctx_->quant.lib_path.empty()) exec_plugin_allreduce(r, g, prow, S, R);
+        else exec_quantized_allreduce(r, g, prow, S, R);
         break;
       }
       size_t per = ceil_div(n, (size_t)P);
@@ -564,6 +577,82 @@ void HostBackend::exec_quantized_allreduce(CommRequest& r, const ProcessGroup& g
     }
   }
   sync(3);
+  free(stage);
+}
+
+// Quantised all-reduce through a USER compression library, the reference's only flavour (reference quant/quant.c:
+// dlopen + three dlsym'ed functions, quantise in place with a per-buffer error-feedback residual, all-reduce of
+// ceil(count / elem_in_block) opaque blocks of block_size bytes with the library's own block sum, dequantise in place;
+// hook-up in eplib/cqueue.c:1977-1994, 2283-2284).  Here the block range is split over the ranks: every rank sums its
+// slice of blocks over all peers in a fixed order with the plugin's reduce function, then the slices are gathered, so
+// the result is bitwise identical everywhere.
+void HostBackend::load_quant_plugin() {
+  if (plugin_lib_) return;
+  const QuantConfig& q = ctx_->quant;
+  plugin_lib_ = dlopen(q.lib_path.c_str(), RTLD_NOW | RTLD_LOCAL);
+  MLSLB_ASSERT(plugin_lib_ != nullptr, "quantization library can't be loaded: %s", dlerror());
+  plugin_quant_ = (PluginQuant)dlsym(plugin_lib_, q.quant_name.c_str());
+  MLSLB_ASSERT(plugin_quant_ != nullptr, "quantization function can't be loaded: %s", q.quant_name.c_str());
+  plugin_dequant_ = (PluginDequant)dlsym(plugin_lib_, q.dequant_name.c_str());
+  MLSLB_ASSERT(plugin_dequant_ != nullptr, "dequantization function can't be loaded: %s", q.dequant_name.c_str());
+  plugin_reduce_ = (PluginReduce)dlsym(plugin_lib_, q.reduce_name.c_str());
+  MLSLB_ASSERT(plugin_reduce_ != nullptr, "reduce function can't be loaded: %s", q.reduce_name.c_str());
+  MLSLB_ASSERT(q.block_size > 0 && q.elem_in_block > 0, "quantization block_size / elem_in_block must be positive");
+  MLSLB_LOG(LOG_INFO, "quantization plugin %s: block %zu bytes / %zu elements", q.lib_path.c_str(), q.block_size,
+            q.elem_in_block);
+}
+
+void HostBackend::exec_plugin_allreduce(CommRequest& r, const ProcessGroup& g, int prow, char* S, char* R) {
+  load_quant_plugin();
+  const CommDesc& d = r.desc;
+  const QuantConfig& q = ctx_->quant;
+  const size_t n = d.count;
+  const int P = g.size(), me = g.idx;
+  const uint64_t t = r.group_seq;
+  HostPub* mine = pub(rank_, prow);
+  HostReqState* st = (HostReqState*)r.backend_state;
+  if (st->residual.size() != n) st->residual.assign(n, 0.f);
+  const size_t nblk = ceil_div(n, q.elem_in_block);
+  const size_t blk_per = ceil_div(nblk, (size_t)P);
+  // the plugin works in place on a buffer of `count` floats (compressed data occupies its head) and may touch whole
+  // blocks, so both areas are sized for max(count floats, nblk blocks)
+  const size_t area = round_up(std::max(n * sizeof(float), nblk * q.block_size) + q.block_size, 64);
+  char* stage = (char*)alloc(2 * area, 64);
+  char* mineq = stage;          // my quantised input
+  char* red = stage + area;     // my slice of reduced blocks (at its global block position)
+  memcpy(mineq, S, n * sizeof(float));
+  // DL_COMP_FLOAT32 = 2, compression ratio 4, DL_COMP_DFP = 1: the constants the reference passes (quant/quant.c:201)
+  int rc = plugin_quant_(mineq, mineq, n, st->residual.data(), 2, 4, 1);
+  MLSLB_ASSERT(rc == 0, "quantization failed: error code %d", rc);
+  mine->send_off = to_off(stage);
+  auto sync = [&](int step) {
+    mine->phase.store(4 * t + step, std::memory_order_release);
+    wait_all(g, prow, 4 * t + step);
+  };
+  sync(1);
+  const size_t blo = std::min(nblk, (size_t)me * blk_per), bhi = std::min(nblk, blo + blk_per);
+  if (bhi > blo) {
+    const char* p0 = peer_ptr(g.members[0], pub(g.members[0], prow)->send_off);
+    memcpy(red + blo * q.block_size, p0 + blo * q.block_size, (bhi - blo) * q.block_size);
+    for (int p = 1; p < P; ++p) {
+      const char* ps = peer_ptr(g.members[p], pub(g.members[p], prow)->send_off);
+      rc = plugin_reduce_(ps + blo * q.block_size, red + blo * q.block_size, bhi - blo);
+      MLSLB_ASSERT(rc == 0, "quantized reduction failed: error code %d", rc);
+    }
+  }
+  sync(2);
+  // gather the reduced slices into my first area (everyone is past reading it), dequantise in place
+  for (int p = 0; p < P; ++p) {
+    const char* ps = peer_ptr(g.members[p], pub(g.members[p], prow)->send_off) + area;
+    size_t plo = std::min(nblk, (size_t)p * blk_per), phi = std::min(nblk, plo + blk_per);
+    if (phi > plo) memcpy(mineq + plo * q.block_size, ps + plo * q.block_size, (phi - plo) * q.block_size);
+  }
+  sync(3);
+  rc = plugin_dequant_(mineq, mineq, n);
+  MLSLB_ASSERT(rc == 0, "dequantization failed: error code %d", rc);
+  const float* v = (const float*)mineq;
+  float* y = (float*)R;
+  for (size_t i = 0; i < n; ++i) y[i] = v[i] * d.scale;
   free(stage);
 }
 

@@ -217,3 +217,51 @@ def test_quantized_allreduce_matches_definition():
         assert err < 0.08, err
     # a request created per call has a fresh residual, so every iteration gives the same answer
     assert torch.equal(outs[0][0], outs[0][1])
+
+
+def test_quantized_allreduce_through_user_plugin():
+    """Environment::SetQuantizationParams with a lib_path: the host backend dlopen()s the user's library and runs the
+    all-reduce on its opaque blocks (268-byte blocks of 256 int8 + header, the geometry of the reference's test)."""
+    import os
+    from conftest import ROOT
+    plugin = os.path.join(ROOT, "bin", "libmlsl_quant_sample.so")
+    assert os.path.exists(plugin), "make builds bin/libmlsl_quant_sample.so"
+    world, n = 4, 3000      # 11.7 blocks: a partial tail block, more ranks than evenly divides
+
+    def body(r, mlsl):
+        env = mlsl.env()
+        env.set_quantization_params(plugin, "sample_compress", "sample_decompress", "sample_reduce_sum", 268, 256)
+        assert env.get_quantization_params()["block_size"] == 268
+        x = _make(r, n, torch.float32) * 3
+        y = torch.zeros(n)
+        mlsl.allreduce(x, out=y, compress=True, scale=0.5)
+        # persistent request (ParameterSet with compression): the error-feedback residual carries over
+        from mlsl_b200.api import CompressionType, DataType, OperationType
+        sess = env.create_session()
+        sess.set_global_minibatch_size(world)
+        dist = env.create_distribution(world, 1)
+        ri = sess.create_operation_reg_info(OperationType.CC)
+        ri.add_input(1, 1, DataType.FLOAT)
+        ri.add_output(1, 1, DataType.FLOAT)
+        ri.add_parameter_set(n, 1, DataType.FLOAT, False, CompressionType.QUANTIZATION)
+        op = sess.get_operation(sess.add_operation(ri, dist))
+        sess.commit()
+        ps = op.get_parameter_set(0)
+        g = mlsl.alloc_tensor(n, torch.float32)
+        acc = torch.zeros(n)
+        for _ in range(8):
+            g.copy_(x)
+            ps.start_gradient_comm(g)
+            ps.wait_gradient_comm()
+            acc += g
+        return y, acc / 8
+
+    outs = run_ranks(world, body)
+    ref = _ref_reduce([_make(r, n, torch.float32) * 3 for r in range(world)], "sum").float()
+    for r in range(world):
+        assert torch.equal(outs[r][0], outs[0][0]) and torch.equal(outs[r][1], outs[0][1])
+    err1 = (outs[0][0] - 0.5 * ref).abs().max() / ref.abs().max()
+    assert err1 < 0.03, err1
+    # with error feedback the time average converges towards the exact sum
+    err8 = (outs[0][1] - ref).abs().max() / ref.abs().max()
+    assert err8 < err1 * 2 and err8 < 0.02, (err1, err8)
