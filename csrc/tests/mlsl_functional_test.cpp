@@ -233,6 +233,16 @@ struct Net {
     if (cfg.quant) {
       QuantParams qp;
       memset(&qp, 0, sizeof(qp));
+      // MLSL_TEST_QUANT_LIB=<path to bin/libmlsl_quant_sample.so>: go through the user plug-in interface instead of
+      // the built-in fp8 block format (host backend; the CUDA backend always uses its fused kernel)
+      if (const char* lib = getenv("MLSL_TEST_QUANT_LIB")) {
+        qp.lib_path = (char*)lib;
+        qp.quant_buffer_func_name = (char*)"sample_compress";
+        qp.dequant_buffer_func_name = (char*)"sample_decompress";
+        qp.reduce_sum_func_name = (char*)"sample_reduce_sum";
+        qp.block_size = 268;
+        qp.elem_in_block = 256;
+      }
       env->SetQuantizationParams(&qp);
     }
     Session* session = env->CreateSession(PT_TRAIN);
