@@ -172,6 +172,63 @@ class DistributedOptimizer:
                 out.append(b.flat.float().clone())
         return out
 
+    # ---- checkpoint / resume (the reference has none; SURVEY 5.4 leaves snapshot assembly to AllGather) ------------
+    def state_dict(self):
+        """Collective.  The COMPLETE optimizer state on every rank: fp32 master weights and moments are all-gathered
+        from their owners and stripped of the world-size dependent padding, so a checkpoint written by one rank can be
+        resumed on a different number of ranks (the shards are re-cut in load_state_dict)."""
+        sd = {"version": 1, "mode": self.mode, "optimizer": self.kind, "steps": self.steps, "lr": self.lr, "buckets": []}
+        for b in self.buckets:
+            e = {"numel": b.numel, "shapes": [tuple(p.shape) for p in b.params]}
+
+            def full(shard):
+                if shard is None:
+                    return None
+                return comm.allgather(shard.contiguous(), distribution=self.dist)[:b.numel].float().cpu().clone()
+
+            if self.mode == "fused":
+                e["master"] = full(b.master) if b.master is not None else b.flat[:b.numel].float().cpu().clone()
+                e["state1"], e["state2"] = full(b.state1), full(b.state2)
+            else:
+                e["master"] = b.flat[:b.numel].float().cpu().clone()
+            sd["buckets"].append(e)
+        if self.mode == "allreduce":
+            import copy
+            sd["local"] = copy.deepcopy(self.local.state_dict())   # torch hands out references to the live moments
+        return sd
+
+    def load_state_dict(self, sd):
+        """Restore parameters (they are views of the buckets) and optimizer state; works across world sizes."""
+        assert sd.get("version") == 1 and sd["mode"] == self.mode and sd["optimizer"] == self.kind, \
+            "checkpoint was written by a different optimizer configuration"
+        assert len(sd["buckets"]) == len(self.buckets), "different bucket layout (bucket_mb / parameter list changed)"
+        self.steps = int(sd["steps"])
+        self.set_lr(sd["lr"])
+        dev = self.params[0].device
+        for b, e in zip(self.buckets, sd["buckets"]):
+            assert e["numel"] == b.numel and e["shapes"] == [tuple(p.shape) for p in b.params], "parameter shapes changed"
+            with torch.no_grad():
+                b.flat[:b.numel].copy_(e["master"].to(self.dtype))
+            if self.mode != "fused":
+                continue
+            owned = b.ps.get_owned_kernel_count() * b.ps.get_kernel_size()
+            lo = b.ps.get_owned_kernel_offset() * b.ps.get_kernel_size()
+
+            def shard(full):
+                if full is None:
+                    return None
+                padded = torch.zeros(b.padded, dtype=torch.float32)
+                padded[:b.numel] = full
+                return padded[lo:lo + owned].to(dev).contiguous()
+
+            if b.master is not None:
+                b.master = shard(e["master"])
+            b.state1 = shard(e["state1"]) if b.state1 is not None else None
+            b.state2 = shard(e["state2"]) if b.state2 is not None else None
+        if self.mode == "allreduce" and "local" in sd:
+            import copy
+            self.local.load_state_dict(copy.deepcopy(sd["local"]))   # torch keeps references when dtype/device match
+
     def close(self):
         for h in self._hooks:
             h.remove()
