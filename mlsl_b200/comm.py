@@ -315,6 +315,26 @@ def alltoall(tensor, out=None, group="data", async_op=False, distribution=None):
     return w if async_op else w.wait()
 
 
+def ring_shift(tensor, shift=1, out=None, group="data", async_op=False, distribution=None):
+    """out on rank i = tensor of rank (i - shift) mod P: every rank sends its block `shift` positions up the ring.
+    One SendRecvList operation (the reference declares that op but never wires it up, src/comm.hpp:212-248); this is the
+    KV rotation of ring attention and the neighbour exchange of pipeline schedules."""
+    _prep(tensor)
+    d = _dist(distribution)
+    g = _group(group)
+    P, idx = d.get_process_count(g), d.get_process_idx(g)
+    n = tensor.numel()
+    if out is None:
+        out = alloc_tensor(tuple(tensor.shape), tensor.dtype, zero=False) if is_device() else torch.empty_like(tensor)
+    dst, src = (idx + shift) % P, (idx - shift) % P
+    sc = [n if p == dst else 0 for p in range(P)]
+    rc = [n if p == src else 0 for p in range(P)]
+    _sync_stream()
+    req = d.send_recv_list(tensor, sc, [0] * P, out, rc, [0] * P, mlsl_dtype(tensor.dtype), g)
+    w = Work(env(), req, out, (tensor, out))
+    return w if async_op else w.wait()
+
+
 def bcast(tensor, root=0, group="data", async_op=False, distribution=None):
     _prep(tensor)
     _sync_stream()
