@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 
 #include "log.hpp"
 #include "numeric.hpp"
@@ -93,7 +94,8 @@ class HostBackend final : public Backend {
     inproc_ = b->inproc();
     world_ = b->size();
     rank_ = b->rank();
-    pub_bytes_ = round_up(sizeof(HostPub) * kPubRows, 4096);
+    dir_off_ = round_up(sizeof(HostPub) * kPubRows, 4096);
+    pub_bytes_ = dir_off_ + round_up(sizeof(RegionDir), 4096);   // [signal rows | region directory | heap ...]
     if (inproc_) {
       // all virtual ranks share the address space: only the signal rows need a shared region
       region_bytes_ = pub_bytes_;
@@ -108,7 +110,14 @@ class HostBackend final : public Backend {
       if (p != rank_) base_[p] = (char*)b->attach_region(p, "hheap", region_bytes_);
     b->barrier();
     b->seal_regions();
-    if (!inproc_) heap_.reset(pub_bytes_, region_bytes_ - pub_bytes_);
+    regions_.assign(world_, {});
+    for (int p = 0; p < world_; ++p) regions_[p].push_back(Region{base_[p], region_bytes_});
+    if (!inproc_) {
+      heaps_.emplace_back(new SlabAllocator());
+      heaps_[0]->reset(pub_bytes_, region_bytes_ - pub_bytes_);
+      dir(rank_)->bytes[0] = region_bytes_;
+      dir(rank_)->count.store(1, std::memory_order_release);
+    }
     MLSLB_LOG(LOG_DEBUG, "host backend: world %d inproc %d region %zu bytes", world_, (int)inproc_, region_bytes_);
   }
 
@@ -125,11 +134,7 @@ class HostBackend final : public Backend {
       std::lock_guard<std::mutex> g(mu_);
       inproc_live_[p] = bytes;
     } else {
-      size_t off = heap_.alloc(bytes, align);
-      MLSLB_ASSERT(off != SIZE_MAX,
-                   "symmetric host heap exhausted (%zu bytes requested, %zu of %zu in use): raise MLSL_HEAP_SIZE_GB",
-                   bytes, heap_.bytes_in_use(), heap_.capacity());
-      p = base_[rank_] + off;
+      p = heap_alloc(bytes, align);
     }
     ctx_->ptrcheck.add(p, bytes);
     return p;
@@ -145,14 +150,17 @@ class HostBackend final : public Backend {
       inproc_live_.erase(it);
       ::free(p);
     } else {
-      MLSLB_ASSERT(heap_.free((size_t)((char*)p - base_[rank_])), "Free of a pointer that did not come from Alloc");
+      std::lock_guard<std::mutex> g(mu_);
+      int k = own_region_of(p, 1);
+      MLSLB_ASSERT(k >= 0 && heaps_[k]->free((size_t)((char*)p - regions_[rank_][k].base)),
+                   "Free of a pointer that did not come from Alloc");
     }
   }
 
   bool owns(const void* p, size_t len) const override {
     if (inproc_) return true;   // one address space: every buffer is directly visible to the peers
-    const char* c = (const char*)p;
-    return c >= base_[rank_] + pub_bytes_ && c + len <= base_[rank_] + region_bytes_;
+    std::lock_guard<std::mutex> g(mu_);
+    return own_region_of(p, len) >= 0;
   }
 
   void prepare(CommRequest& r) override {
@@ -181,7 +189,9 @@ class HostBackend final : public Backend {
     } catch (const std::exception&) {   // poisoned job: still unmap
     }
     for (int p = 0; p < world_; ++p)
-      if (base_[p]) b->release_region(base_[p], region_bytes_, p == rank_, "hheap");
+      for (size_t k = 0; k < regions_[p].size(); ++k)
+        if (regions_[p][k].base) b->release_region(regions_[p][k].base, regions_[p][k].bytes, p == rank_, region_name((int)k));
+    regions_.clear();
     base_.clear();
   }
 
@@ -195,14 +205,94 @@ class HostBackend final : public Backend {
   int world_ = 1, rank_ = 0;
   size_t pub_bytes_ = 0, region_bytes_ = 0;
   std::vector<char*> base_;
-  SlabAllocator heap_;
-  std::mutex mu_;
+  // The heap grows on demand like the reference's (eplib/memory.c:396-410: when the mspace is full another shared
+  // region, at least twice as large, is registered on the client and on every server; at most 99 of them).  Region 0
+  // carries a directory of the region sizes; peers attach a new region the first time an offset points into it.
+  // Offsets that travel between ranks are (region index << 48) | byte offset.
+  static constexpr int kMaxRegions = 100;
+  static constexpr int kRegionShift = 48;
+  struct RegionDir {
+    std::atomic<uint32_t> count;
+    uint32_t pad;
+    uint64_t bytes[kMaxRegions];
+  };
+  struct Region {
+    char* base;
+    size_t bytes;
+  };
+  size_t dir_off_ = 0;
+  mutable std::vector<std::vector<Region>> regions_;   // [rank][region]: what this process has mapped so far
+  std::vector<std::unique_ptr<SlabAllocator>> heaps_;  // my regions
+  mutable std::mutex mu_;
+
+  RegionDir* dir(int global_rank) const { return (RegionDir*)(base_[global_rank] + dir_off_); }
+  static std::string region_name(int k) { return k == 0 ? std::string("hheap") : "hheap" + std::to_string(k); }
+  // index of my region that contains [p, p+len), -1 if none (mu_ held)
+  int own_region_of(const void* p, size_t len) const {
+    const char* c = (const char*)p;
+    const auto& mine = regions_[rank_];
+    for (size_t k = 0; k < mine.size(); ++k) {
+      const char* lo = mine[k].base + (k == 0 ? pub_bytes_ : 0);
+      if (c >= lo && c + len <= mine[k].base + mine[k].bytes) return (int)k;
+    }
+    return -1;
+  }
+  void* heap_alloc(size_t bytes, size_t align) {
+    std::lock_guard<std::mutex> g(mu_);
+    for (size_t k = 0; k < heaps_.size(); ++k) {
+      size_t off = heaps_[k]->alloc(bytes, align);
+      if (off != SIZE_MAX) return regions_[rank_][k].base + off;
+    }
+    const int k = (int)heaps_.size();
+    size_t in_use = 0, cap = 0;
+    for (auto& h : heaps_) in_use += h->bytes_in_use(), cap += h->capacity();
+    MLSLB_ASSERT(k < kMaxRegions,
+                 "symmetric host heap exhausted (%zu bytes requested, %zu of %zu in use in %d regions): raise "
+                 "MLSL_HEAP_SIZE_GB", bytes, in_use, cap, k);
+    size_t want = std::max(2 * regions_[rank_].back().bytes, round_up(bytes + align + 4096, (size_t)1 << 20));
+    char* base = (char*)ctx_->boot->create_region(region_name(k), want);
+    regions_[rank_].push_back(Region{base, want});
+    heaps_.emplace_back(new SlabAllocator());
+    heaps_[k]->reset(0, want);
+    dir(rank_)->bytes[k] = want;
+    dir(rank_)->count.store((uint32_t)k + 1, std::memory_order_release);
+    MLSLB_LOG(LOG_INFO, "host heap grown: region %d of %.1f MiB (%zu of %zu bytes were in use)", k, want / 1048576.0,
+              in_use, cap);
+    size_t off = heaps_[k]->alloc(bytes, align);
+    MLSLB_ASSERT(off != SIZE_MAX, "allocation of %zu bytes failed in a fresh region of %zu bytes", bytes, want);
+    return base + off;
+  }
+  char* peer_region(int global_rank, int k) const {
+    std::lock_guard<std::mutex> g(mu_);
+    auto& v = regions_[global_rank];
+    while ((int)v.size() <= k) {
+      const int kk = (int)v.size();
+      RegionDir* d = dir(global_rank);
+      MLSLB_ASSERT(d->count.load(std::memory_order_acquire) > (uint32_t)kk, "rank %d published an offset into region %d it never created",
+                   global_rank, kk);
+      size_t bytes = d->bytes[kk];
+      v.push_back(Region{(char*)ctx_->boot->attach_region(global_rank, region_name(kk), bytes), bytes});
+    }
+    return v[k].base;
+  }
   std::map<void*, size_t> inproc_live_;
 
   HostPub* pub(int global_rank, int prow) const { return (HostPub*)base_[global_rank] + prow; }
-  uint64_t to_off(const void* p) const { return inproc_ ? (uint64_t)(uintptr_t)p : (uint64_t)((const char*)p - base_[rank_]); }
+  uint64_t to_off(const void* p) const {
+    if (inproc_) return (uint64_t)(uintptr_t)p;
+    if (!p) return 0;   // barrier, non-root sides of rooted collectives
+    const char* c = (const char*)p;
+    if (c >= base_[rank_] && c < base_[rank_] + region_bytes_) return (uint64_t)(c - base_[rank_]);
+    std::lock_guard<std::mutex> g(mu_);
+    int k = own_region_of(p, 1);
+    MLSLB_ASSERT(k > 0, "buffer %p is not in the symmetric heap", p);
+    return ((uint64_t)k << kRegionShift) | (uint64_t)(c - regions_[rank_][k].base);
+  }
   char* peer_ptr(int global_rank, uint64_t off) const {
-    return inproc_ ? (char*)(uintptr_t)off : base_[global_rank] + off;
+    if (inproc_) return (char*)(uintptr_t)off;
+    const int k = (int)(off >> kRegionShift);
+    if (k == 0) return base_[global_rank] + off;
+    return peer_region(global_rank, k) + (off & (((uint64_t)1 << kRegionShift) - 1));
   }
 
   struct Stage {

@@ -380,3 +380,47 @@ def test_heap_tensor_lifetime_explicit_free_then_recycled_address():
 
     for same, distinct, live in run_ranks(1, body, backend="host"):
         assert distinct and live
+
+
+def test_host_heap_grows_on_demand():
+    """MLSL_HEAP_SIZE_GB far too small for what the program allocates: the heap registers further shared regions
+    (each at least twice the last) and peers attach them lazily when a collective first points into one - the
+    reference's EPLIB heap expansion (eplib/memory.c:396-410)."""
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import torch, mlsl_b200 as mlsl
+mlsl.init()
+r, W = mlsl.rank(), mlsl.world_size()
+n = 3 << 20                                   # 12 MiB each, the heap starts with 8 MiB
+ts = []
+for i in range(4):
+    t = mlsl.alloc_tensor(n, torch.float32)
+    t.fill_(float(r + 1 + i))
+    ts.append(t)
+ptrs = [t.data_ptr() for t in ts]
+ok = True
+for i, t in enumerate(ts):
+    out = mlsl.alloc_tensor(n, torch.float32)
+    mlsl.allreduce(t, out=out)               # zero copy: peers read this rank's expansion regions directly
+    want = sum(p + 1 + i for p in range(W))
+    ok = ok and bool((out == want).all()) and float(t[0]) == r + 1 + i
+    mlsl.free_tensor(out)
+sh = mlsl.reduce_scatter(ts[3])              # library-allocated result in a grown region
+ok = ok and bool((sh == sum(p + 1 + 3 for p in range(W))).all())
+for t in ts:
+    mlsl.free_tensor(t)
+t = mlsl.alloc_tensor(n, torch.float32)      # freed space is reused, no further growth needed
+ok = ok and t.data_ptr() in ptrs
+print("GROW %%s" %% ("OK" if ok else "BAD"), flush=True)
+del t, ts, sh, out
+mlsl.finalize()
+''' % ROOT
+    env = dict(os.environ, MLSL_BACKEND="host", MLSL_HEAP_SIZE_GB=str(8.0 / 1024), MLSL_WATCHDOG_SEC="60",
+               MLSL_JOB_ID="grow%d" % os.getpid(), MLSL_LOG_LEVEL="1")
+    p = subprocess.run([os.path.join(ROOT, "bin", "mlslrun"), "-n", "3", sys.executable, "-c", code], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
+    assert p.returncode == 0 and p.stdout.count("GROW OK") == 3, p.stdout[-3000:]
+    assert "host heap grown" in p.stdout
+    leftovers = [f for f in os.listdir("/dev/shm") if "grow%d" % os.getpid() in f]
+    assert not leftovers, leftovers
