@@ -77,7 +77,22 @@ tsan:
 	cd /tmp/mlsl_tsan && TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" ./ftest 2 1 0 1 --inproc 4 | tail -1
 	cd /tmp/mlsl_tsan && MLSL_NUM_SERVERS=2 MLSL_MSG_PRIORITY=1 TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" ./ftest 1 0 1 0 --inproc 4 | tail -1
 
-clean:
-	rm -rf $(BUILD) $(LIB) bin
+# make install PREFIX=/opt/mlsl_b200: the layout of the reference's package (intel64/{bin,lib,include}, doc, examples,
+# the environment script), plus the Python package
+PREFIX ?= $(CURDIR)/_install
+install: all
+	@mkdir -p $(PREFIX)/intel64/bin $(PREFIX)/intel64/lib $(PREFIX)/intel64/include/mlsl $(PREFIX)/doc $(PREFIX)/examples $(PREFIX)/python
+	cp $(LIB) $(PREFIX)/intel64/lib/
+	cp bin/mlslrun bin/libmlsl_quant_sample.so $(PREFIX)/intel64/bin/
+	cp include/mlsl.hpp include/mlsl.h $(PREFIX)/intel64/include/
+	cp -r mlsl_b200 $(PREFIX)/python/ && rm -rf $(PREFIX)/python/mlsl_b200/__pycache__ $(PREFIX)/python/mlsl_b200/*/__pycache__
+	cp README.md DESIGN.md docs/*.md $(PREFIX)/doc/
+	cp examples/*.py csrc/tests/mlsl_example.cpp csrc/tests/mlsl_sample.cpp csrc/tests/mlsl_functional_test.cpp \
+	   csrc/tests/cmlsl_smoke_test.c csrc/tests/quant_plugin_sample.c $(PREFIX)/examples/
+	cp scripts/mlslvars.sh $(PREFIX)/intel64/bin/mlslvars.sh
+	@echo "installed into $(PREFIX); source $(PREFIX)/intel64/bin/mlslvars.sh"
 
-.PHONY: all clean sass tsan
+clean:
+	rm -rf $(BUILD) $(LIB) bin _install
+
+.PHONY: all clean sass tsan install

@@ -9,6 +9,7 @@
 //   * every (group, lane) has its own CUDA stream (lane 1 = high priority): Start() makes it wait for the user's
 //     stream, Wait() either blocks the host on the completion event or just orders the user's stream after it.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -481,6 +482,13 @@ void CudaBackend::launch(CommRequest& r) {
   cudaStream_t s = inline_stream_ ? ustream() : stream_for(solo || g->row < 0 ? kMaxGroupRows - 1 : g->row, r.lane);
   st->stream = s;
   if (!inline_stream_) MLSLB_CUDA(cudaStreamWaitEvent(s, st->ready, 0));
+  // NVTX range per collective launch (header-only NVTX3: a no-op unless a profiler is attached), SURVEY 5.1
+  static const bool nvtx = !(getenv("MLSL_NVTX") && atoi(getenv("MLSL_NVTX")) == 0);
+  if (nvtx) nvtxRangePushA(opkind_name(d.kind));
+  struct NvtxPop {
+    bool on;
+    ~NvtxPop() { if (on) nvtxRangePop(); }
+  } nvtx_pop{nvtx};
   launch_single(r, st, s);
   st->recorded = false;
   if (!(eventless() && st->stages.empty())) {

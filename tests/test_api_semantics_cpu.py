@@ -424,3 +424,22 @@ mlsl.finalize()
     assert "host heap grown" in p.stdout
     leftovers = [f for f in os.listdir("/dev/shm") if "grow%d" % os.getpid() in f]
     assert not leftovers, leftovers
+
+
+def test_make_install_layout_is_usable(tmp_path):
+    """`make install PREFIX=...` + `source intel64/bin/mlslvars.sh`: a C++ program builds with -lmlsl_b200 and runs under
+    mlslrun, the Python package imports from the prefix (the reference's packaged layout, scripts/mlslvars.sh)."""
+    prefix = str(tmp_path / "inst")
+    r = subprocess.run(["make", "-C", ROOT, "install", "PREFIX=" + prefix], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    src = tmp_path / "t.cpp"
+    src.write_text('#include <mlsl.hpp>\n#include <cstdio>\nint main(int c, char** v) { MLSL::Environment& e = '
+                   'MLSL::Environment::GetEnv(); e.Init(&c, &v); printf("rank %zu of %zu\\n", e.GetProcessIdx(), '
+                   'e.GetProcessCount()); e.Finalize(); return 0; }\n')
+    script = ("source %s/intel64/bin/mlslvars.sh && cd %s && g++ -std=c++17 t.cpp -o t -lmlsl_b200 && mlslrun -n 2 ./t && "
+              "python -c 'import mlsl_b200, os; print(os.path.dirname(mlsl_b200.__file__))'") % (prefix, tmp_path)
+    env = {k: v for k, v in os.environ.items() if k not in ("PYTHONPATH", "LD_LIBRARY_PATH")}
+    env.update(MLSL_BACKEND="host", MLSL_JOB_ID="inst%d" % os.getpid(), MLSL_HEAP_SIZE_GB="0.05")
+    r = subprocess.run(["bash", "-c", script], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "rank 0 of 2" in r.stdout and "rank 1 of 2" in r.stdout and prefix + "/python/mlsl_b200" in r.stdout
