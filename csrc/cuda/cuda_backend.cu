@@ -74,6 +74,10 @@ class CudaBackend final : public Backend {
 
   void* alloc(size_t bytes, size_t align) override {
     size_t off = heap_.alloc(bytes, std::max<size_t>(align, 256));
+    if (off == SIZE_MAX) {   // scratch of finished stream-ordered requests may still be parked
+      sweep_parked();
+      off = heap_.alloc(bytes, std::max<size_t>(align, 256));
+    }
     MLSLB_ASSERT(off != SIZE_MAX,
                  "symmetric device heap exhausted (%zu bytes requested, %zu of %zu in use): raise MLSL_HEAP_SIZE_GB",
                  bytes, heap_.bytes_in_use(), heap_.capacity());
@@ -156,9 +160,13 @@ class CudaBackend final : public Backend {
   void wait(CommRequest& r) override {
     auto* st = (CudaReqState*)r.backend_state;
     set_device();
-    if (stream_wait_ && st->stages.empty()) {
-      // stream-ordered completion: nothing blocks the host
+    if (stream_wait_) {
+      // stream-ordered completion: nothing blocks the host.  Staged (foreign) buffers were copied back on the
+      // collective's stream right behind the kernel; only their slab scratch has to outlive the kernel, so it is
+      // parked with an event and recycled by a later call.
       if (!inline_stream_) MLSLB_CUDA(cudaStreamWaitEvent(ustream(), st->done, 0));
+      if (!st->stages.empty()) park_stages(st);
+      sweep_parked();
       st->inflight = false;
       check_error(opkind_name(r.desc.kind));   // a device watchdog hit of an EARLIER operation surfaces here
       return;
@@ -211,6 +219,9 @@ class CudaBackend final : public Backend {
       }
     };
     cudaDeviceSynchronize();
+    sweep_parked(true);
+    for (cudaEvent_t ev : event_pool_) cudaEventDestroy(ev);
+    event_pool_.clear();
     quiet_barrier();
     for (size_t p = 0; p < peer_slab_.size(); ++p)
       if (peer_opened_[p]) cudaIpcCloseMemHandle(peer_slab_[p]);
@@ -284,6 +295,52 @@ class CudaBackend final : public Backend {
   }
   DevComm make_comm(const ProcessGroup& g, int lane) const;
   void drop_stages(CudaReqState* st, bool copied);
+  // scratch blocks of stream-ordered requests: freed once the event recorded behind their last use has fired
+  struct Parked {
+    cudaEvent_t ev;
+    void* slab;
+  };
+  std::vector<Parked> parked_;
+  std::vector<cudaEvent_t> event_pool_;
+  std::mutex park_mu_;
+  void park_stages(CudaReqState* st) {
+    std::lock_guard<std::mutex> g(park_mu_);
+    cudaEvent_t ev;
+    if (!event_pool_.empty()) {
+      ev = event_pool_.back();
+      event_pool_.pop_back();
+    } else {
+      MLSLB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    MLSLB_CUDA(cudaEventRecord(ev, st->stream));
+    // one event guards all blocks of the request: the first entry owns it, the others piggy-back (null event)
+    bool first = true;
+    for (auto& sb : st->stages) {
+      parked_.push_back(Parked{first ? ev : nullptr, sb.slab});
+      first = false;
+    }
+    st->stages.clear();
+  }
+  void sweep_parked(bool all = false) {
+    std::vector<void*> to_free;
+    {
+      std::lock_guard<std::mutex> g(park_mu_);
+      size_t i = 0;
+      while (i < parked_.size()) {
+        // entries come in groups [event, null, null...]; a group is released as a whole
+        size_t j = i + 1;
+        while (j < parked_.size() && parked_[j].ev == nullptr) ++j;
+        if (all || cudaEventQuery(parked_[i].ev) == cudaSuccess) {
+          event_pool_.push_back(parked_[i].ev);
+          for (size_t k = i; k < j; ++k) to_free.push_back(parked_[k].slab);
+          parked_.erase(parked_.begin() + i, parked_.begin() + j);
+        } else {
+          i = j;
+        }
+      }
+    }
+    for (void* p : to_free) free(p);
+  }
   void finish(CommRequest& r, CudaReqState* st);
   void check_error(const char* what);
   void launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s);
