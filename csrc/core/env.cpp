@@ -51,9 +51,7 @@ EnvConfig parse_env() {
   getb(c.check_single_node, "MLSL_CHECK_SINGLE_NODE");
   getb(c.pointer_check, "MLSL_POINTER_CHECK");
   gets(c.backend, "MLSL_BACKEND");
-  gets(c.algo, "MLSL_ALGO");
   getb(c.use_nvls, "MLSL_NVLS");
-  geti(c.one_shot_max_kb, "MLSL_ONESHOT_MAX_KB");
   geti(c.watchdog_sec, "MLSL_WATCHDOG_SEC");
   gets(c.wait_mode, "MLSL_WAIT_MODE");
   gets(c.job_id, "MLSL_JOB_ID");
@@ -77,8 +75,8 @@ void print_env(const EnvConfig& c) {
             c.max_short_msg, c.large_msg_mb, c.large_msg_chunks);
   MLSLB_LOG(LOG_INFO, "MLSL_MSG_PRIORITY=%d MLSL_MSG_PRIORITY_THRESHOLD=%zu MLSL_MSG_PRIORITY_MODE=%d",
             (int)c.msg_priority, c.msg_priority_threshold, c.msg_priority_mode);
-  MLSLB_LOG(LOG_INFO, "MLSL_NVLS=%d MLSL_ONESHOT_MAX_KB=%d MLSL_WAIT_MODE=%s MLSL_WATCHDOG_SEC=%d",
-            (int)c.use_nvls, c.one_shot_max_kb, c.wait_mode.c_str(), c.watchdog_sec);
+  MLSLB_LOG(LOG_INFO, "MLSL_NVLS=%d MLSL_WAIT_MODE=%s MLSL_WATCHDOG_SEC=%d MLSL_CHECK_SINGLE_NODE=%d",
+            (int)c.use_nvls, c.wait_mode.c_str(), c.watchdog_sec, (int)c.check_single_node);
 }
 
 }  // namespace mlslb

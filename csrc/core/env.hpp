@@ -36,9 +36,7 @@ struct EnvConfig {
   bool check_single_node = true; // MLSL_CHECK_SINGLE_NODE
   bool pointer_check = false;    // MLSL_POINTER_CHECK (reference: build-time ENABLE_CHKP_INT)
   std::string backend = "auto";  // MLSL_BACKEND: auto | host | cuda
-  std::string algo;              // MLSL_ALGO: force device algorithm (oneshot|twoshot|nvls)
   bool use_nvls = true;          // MLSL_NVLS: allow multicast path when available
-  int one_shot_max_kb = 256;     // MLSL_ONESHOT_MAX_KB: allreduce one-shot/two-shot crossover
   int watchdog_sec = 120;        // MLSL_WATCHDOG_SEC: flag-wait timeout before poison+abort (0=off)
   std::string wait_mode = "host";// MLSL_WAIT_MODE: host (block the CPU) | stream (order the user stream)
   std::string job_id;            // MLSL_JOB_ID (else derived from MASTER_PORT / TORCHELASTIC_RUN_ID)

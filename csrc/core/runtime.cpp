@@ -600,8 +600,12 @@ void context_init(RankContext* ctx) {
   // Servers: the reference switches its endpoint servers off on a single node unless MLSL_NUM_SERVERS is set
   // (src/comm_ep.cpp:1585-1602).  Same rule for the device path (kernels are asynchronous anyway); the host
   // path needs one server for true non-blocking progress.
+  // MLSL_CHECK_SINGLE_NODE=0 switches that rule off: the reference's default of 4 servers applies (host path).
   int ns = ctx->env.num_servers;
-  if (ns < 0) ns = ctx->backend->is_device() ? 0 : (ctx->world > 1 ? 1 : 0);
+  if (ns < 0) {
+    if (ctx->backend->is_device() || ctx->world <= 1) ns = 0;
+    else ns = ctx->env.check_single_node ? 1 : 4;
+  }
   ctx->progress.reset(new ProgressEngine(ctx, ns));
   ctx->initialized = true;
   install_signal_handlers(ctx);
