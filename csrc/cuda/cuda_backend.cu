@@ -812,8 +812,16 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
       size_t sb = gemm_rs_stage_bytes(gm.M, gm.N);
       if (!st->qstage) st->qstage = alloc(sb, 1024);
       const bool out32 = d.has_out_dtype && d.out_dtype == DType::F32;
-      const int gch = gemm_rs_channels(gm.M, gm.N, std::min(std::max(1, sm_count_ / std::max(1, ranks_per_device_)), kMaxChannels));
-      MLSLB_CUDA(launch_gemm_rs(dc, gm.a, gm.w, (unsigned long long)((char*)st->qstage - slab_), R, out32, gm.M, gm.N, gm.K, gch, s));
+      const int gcap = std::min(std::max(1, sm_count_ / std::max(1, ranks_per_device_)), kMaxChannels);
+      // MLSL_GEMM_2CTA=1: experimental cta_group::2 kernel (256 x 256 tiles on CTA pairs); same choice on every rank
+      const bool two_cta = getenv("MLSL_GEMM_2CTA") && atoi(getenv("MLSL_GEMM_2CTA")) != 0;
+      if (two_cta && gcap >= 2 && gemm_rs2_check(gm.M, gm.N, gm.K, P) == nullptr) {
+        const int gch = gemm_rs2_channels(gm.M, gm.N, gcap);
+        MLSLB_CUDA(launch_gemm_rs2(dc, gm.a, gm.w, (unsigned long long)((char*)st->qstage - slab_), R, out32, gm.M, gm.N, gm.K, gch, s));
+      } else {
+        const int gch = gemm_rs_channels(gm.M, gm.N, gcap);
+        MLSLB_CUDA(launch_gemm_rs(dc, gm.a, gm.w, (unsigned long long)((char*)st->qstage - slab_), R, out32, gm.M, gm.N, gm.K, gch, s));
+      }
       break;
     }
   }

@@ -71,6 +71,11 @@ cudaError_t launch_fused_update(const DevComm& dc, DType grad_dt, DType param_dt
 size_t gemm_rs_stage_bytes(int M, int N);
 int gemm_rs_channels(int M, int N, int max_channels);
 const char* gemm_rs_check(int M, int N, int K, int P);   // nullptr when the shape is supported
+// experimental cta_group::2 form (MLSL_GEMM_2CTA=1): 256 x 256 tiles on CTA pairs
+const char* gemm_rs2_check(int M, int N, int K, int P);
+int gemm_rs2_channels(int M, int N, int max_channels);
+cudaError_t launch_gemm_rs2(const DevComm& dc, const void* a, const void* w, unsigned long long stage_off, void* out,
+                            bool out_fp32, int M, int N, int K, int channels, cudaStream_t s);
 cudaError_t launch_gemm_rs(const DevComm& dc, const void* a, const void* w, unsigned long long stage_off, void* out,
                            bool out_fp32, int M, int N, int K, int channels, cudaStream_t s);
 // local elementwise helper (scale in place) for single-rank groups
