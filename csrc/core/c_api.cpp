@@ -179,6 +179,14 @@ int mlsl_distribution_gemm_reduce_scatter(mlsl_distribution d, const void* a, co
   C_GUARD(*need(r) = U(H<Distribution>(d)->GemmReduceScatter(a, w, out, m, n, k, DT(ot), GT(g))))
 }
 int mlsl_distribution_barrier(mlsl_distribution d, mlsl_group_type g) { C_GUARD(H<Distribution>(d)->Barrier(GT(g))) }
+int mlsl_distribution_create_window(mlsl_distribution d, void* base, size_t bytes, mlsl_group_type g, mlsl_window* w) {
+  C_GUARD(*need(w) = (mlsl_window)H<Distribution>(d)->CreateWindow(base, bytes, GT(g)))
+}
+int mlsl_distribution_free_window(mlsl_distribution d, mlsl_window w) { C_GUARD(H<Distribution>(d)->FreeWindow((MLSL::Window*)w)) }
+int mlsl_window_put(mlsl_window w, const void* o, size_t n, size_t t, size_t disp) { C_GUARD(((MLSL::Window*)w)->Put(o, n, t, disp)) }
+int mlsl_window_get(mlsl_window w, void* o, size_t n, size_t t, size_t disp) { C_GUARD(((MLSL::Window*)w)->Get(o, n, t, disp)) }
+int mlsl_window_fence(mlsl_window w) { C_GUARD(((MLSL::Window*)w)->Fence()) }
+int mlsl_window_get_size(mlsl_window w, size_t i, size_t* bytes) { C_GUARD(*need(bytes) = ((MLSL::Window*)w)->GetSize(i)) }
 
 // ---- OperationRegInfo ----
 int mlsl_operation_reg_info_set_name(mlsl_operation_reg_info i, const char* name) { C_GUARD(H<OperationRegInfo>(i)->SetName(name)) }

@@ -717,6 +717,62 @@ CommReq* Distribution::GemmReduceScatter(const void* a, const void* w, void* out
   r->desc.out_dtype = to_dtype(outType);
   return d->submit(r, const_cast<void*>(a), out);
 }
+// ---- [ext] RMA windows -----------------------------------------------------------------------------------------
+Window* Distribution::CreateWindow(void* base, size_t bytes, GroupType gt) {
+  auto d = SELF(DistributionImpl);
+  ProcessGroup* g = d->group(gt);
+  MLSLB_ASSERT(base != nullptr && bytes > 0, "CreateWindow: empty window");
+  MLSLB_ASSERT(d->ctx->backend->owns(base, bytes), "CreateWindow: the memory must come from Environment::Alloc");
+  auto* w = new WindowImpl();
+  w->dist = d;
+  w->groupType = gt;
+  w->group = g;
+  const size_t P = (size_t)g->size();
+  struct Msg {
+    uint64_t off, bytes;
+  } mine{d->ctx->backend->heap_offset(base), (uint64_t)bytes};
+  std::vector<Msg> all(P);
+  if (P > 1) d->ctx->boot->group_allgather(g->members, g->row, ++g->ctl_seq, &mine, all.data(), sizeof(Msg));
+  else all[0] = mine;
+  for (size_t i = 0; i < P; ++i) {
+    w->offsets.push_back(all[i].off);
+    w->sizes.push_back(all[i].bytes);
+  }
+  return w;
+}
+void Distribution::FreeWindow(Window* window) {
+  if (!window) return;
+  auto* w = static_cast<WindowImpl*>(window);
+  w->Fence();   // nobody unmaps or reuses the memory while a peer may still access it
+  delete w;
+}
+static void window_range_check(WindowImpl* w, size_t bytes, size_t idx, size_t disp) {
+  MLSLB_ASSERT(idx < w->sizes.size(), "window target index %zu out of range (group size %zu)", idx, w->sizes.size());
+  MLSLB_ASSERT(disp + bytes <= w->sizes[idx], "window access [%zu, %zu) exceeds the %zu bytes member %zu exposed", disp,
+               disp + bytes, (size_t)w->sizes[idx], idx);
+}
+void Window::Put(const void* origin, size_t bytes, size_t targetIdx, size_t targetDisp) {
+  auto* w = SELF(WindowImpl);
+  window_range_check(w, bytes, targetIdx, targetDisp);
+  mlslb::Backend* b = w->dist->ctx->backend.get();
+  b->rma_copy((char*)b->peer_heap_ptr(w->group->members[targetIdx], w->offsets[targetIdx]) + targetDisp, origin, bytes);
+}
+void Window::Get(void* origin, size_t bytes, size_t targetIdx, size_t targetDisp) {
+  auto* w = SELF(WindowImpl);
+  window_range_check(w, bytes, targetIdx, targetDisp);
+  mlslb::Backend* b = w->dist->ctx->backend.get();
+  b->rma_copy(origin, (const char*)b->peer_heap_ptr(w->group->members[targetIdx], w->offsets[targetIdx]) + targetDisp, bytes);
+}
+void Window::Fence() {
+  auto* w = SELF(WindowImpl);
+  w->dist->Barrier(w->groupType);   // ordered behind the copies; its handshake makes them visible at the targets
+}
+size_t Window::GetSize(size_t memberIdx) {
+  auto* w = SELF(WindowImpl);
+  MLSLB_ASSERT(memberIdx < w->sizes.size(), "window member index out of range");
+  return (size_t)w->sizes[memberIdx];
+}
+
 void Distribution::Barrier(GroupType gt) {
   auto d = SELF(DistributionImpl);
   CommRequest* r = d->make_request(mlslb::OpKind::BARRIER, DT_BYTE, gt);

@@ -119,6 +119,14 @@ class ParameterSetImpl : public ParameterSet {
   size_t inc_msg_bytes() const;
 };
 
+class WindowImpl : public Window {
+ public:
+  DistributionImpl* dist = nullptr;
+  GroupType groupType = GT_GLOBAL;
+  ProcessGroup* group = nullptr;
+  std::vector<uint64_t> offsets, sizes;   // per group member: heap offset and size of the exposed memory
+};
+
 class DistributionImpl : public Distribution {
  public:
   DistributionImpl(RankContext* ctx, size_t dataParts, size_t modelParts, bool replicate, int dataColor,

@@ -163,6 +163,9 @@ class HostBackend final : public Backend {
     return own_region_of(p, len) >= 0;
   }
 
+  uint64_t heap_offset(const void* p) const override { return to_off(p); }
+  void* peer_heap_ptr(int global_rank, uint64_t offset) override { return peer_ptr(global_rank, offset); }
+
   void prepare(CommRequest& r) override {
     if (!r.backend_state) r.backend_state = new HostReqState();
   }

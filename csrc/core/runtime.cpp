@@ -360,6 +360,7 @@ void Backend::pack_blocks(const BlockDesc* blocks, size_t nblocks, size_t local_
   }
 }
 
+void Backend::rma_copy(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 void Backend::copy_from_host(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 
 // ============================================================================================================

@@ -149,6 +149,11 @@ class Backend {
                            const void* src, void* dst, bool unpack);
   virtual bool is_device_pointer(const void*) const { return false; }
   virtual void copy_from_host(void* dst, const void* src, size_t bytes);   // blocking; default memcpy
+  // One-sided access (RMA windows): heap pointers travel between ranks as offsets; every rank can address every
+  // peer's heap.  rma_copy is ordered like any other work of the caller (stream order on the device, immediate on the host).
+  virtual uint64_t heap_offset(const void* p) const = 0;
+  virtual void* peer_heap_ptr(int global_rank, uint64_t offset) = 0;
+  virtual void rma_copy(void* dst, const void* src, size_t bytes);         // default memcpy
   virtual void finalize() {}
   virtual std::string describe() const { return name(); }
 };

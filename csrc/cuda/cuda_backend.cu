@@ -189,6 +189,12 @@ class CudaBackend final : public Backend {
     MLSLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, aux_stream()));
     MLSLB_CUDA(cudaStreamSynchronize(aux_stream()));
   }
+  uint64_t heap_offset(const void* p) const override { return (uint64_t)((const char*)p - slab_); }
+  void* peer_heap_ptr(int global_rank, uint64_t offset) override { return peer_slab_[global_rank] + offset; }
+  void rma_copy(void* dst, const void* src, size_t bytes) override {
+    set_device();
+    MLSLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ustream()));   // peers are mapped: a plain copy
+  }
   void set_user_stream(void* s) override {
     user_stream_ = (cudaStream_t)s;
     user_stream_set_ = true;   // null is a valid choice: the legacy default stream

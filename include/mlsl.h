@@ -229,6 +229,15 @@ int mlsl_distribution_reduce_scatter_ex(mlsl_distribution dist, void* send_buffe
 int mlsl_distribution_send_recv_list(mlsl_distribution dist, void* send_buffer, size_t* send_counts,
                                      size_t* send_offsets, void* recv_buffer, size_t* recv_counts, size_t* recv_offsets,
                                      mlsl_data_type dtype, mlsl_group_type group_type, mlsl_comm_req* req);
+/* [ext] RMA windows (one-sided put / get into memory a group member exposed; fence is collective) */
+typedef void* mlsl_window;
+int mlsl_distribution_create_window(mlsl_distribution dist, void* base, size_t bytes, mlsl_group_type group_type,
+                                    mlsl_window* window);
+int mlsl_distribution_free_window(mlsl_distribution dist, mlsl_window window);
+int mlsl_window_put(mlsl_window window, const void* origin, size_t bytes, size_t target_idx, size_t target_disp);
+int mlsl_window_get(mlsl_window window, void* origin, size_t bytes, size_t target_idx, size_t target_disp);
+int mlsl_window_fence(mlsl_window window);
+int mlsl_window_get_size(mlsl_window window, size_t member_idx, size_t* bytes);
 int mlsl_distribution_gemm_reduce_scatter(mlsl_distribution dist, const void* a, const void* w, void* out, size_t m,
                                           size_t n, size_t k, mlsl_data_type out_type, mlsl_group_type group_type,
                                           mlsl_comm_req* req);

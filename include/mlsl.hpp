@@ -155,6 +155,8 @@ class ParameterSet {
   void SetGradientScale(float scale);
 };
 
+class Window;
+
 class Distribution {
   MLSL_FACTORY_ONLY(Distribution)
  public:
@@ -194,6 +196,23 @@ class Distribution {
   // out bf16 or fp32 (outType).  M % (128 * P) == 0, N % 256 == 0, K % 64 == 0.
   CommReq* GemmReduceScatter(const void* a, const void* w, void* out, size_t M, size_t N, size_t K, DataType outType,
                              GroupType groupType);
+  // [ext] one-sided access (the reference keeps its RMA window table behind ENABLE_MPIRMA_ENDPOINTS,
+  // eplib/window.c).  Collective over the group: every member exposes `bytes` at `base` (memory from
+  // Environment::Alloc).  FreeWindow is collective too.
+  Window* CreateWindow(void* base, size_t bytes, GroupType groupType);
+  void FreeWindow(Window* window);
+};
+
+// [ext] RMA window: Put / Get address a member by its index in the window's group and a byte displacement inside
+// the memory it exposed; they are ordered like the caller's other work (stream order on the CUDA backend) and
+// complete - locally and at the target - at the next Fence(), which is collective.
+class Window {
+  MLSL_FACTORY_ONLY(Window)
+ public:
+  void Put(const void* origin, size_t bytes, size_t targetIdx, size_t targetDisp);
+  void Get(void* origin, size_t bytes, size_t targetIdx, size_t targetDisp);
+  void Fence();
+  size_t GetSize(size_t memberIdx);
 };
 
 class OperationRegInfo {

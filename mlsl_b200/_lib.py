@@ -130,6 +130,12 @@ def _declare(l):
         "mlsl_distribution_reduce_scatter": [H, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, P(H)],
         "mlsl_distribution_reduce_scatter_ex": [H, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_float, P(H)],
         "mlsl_distribution_barrier": [H, c_int],
+        "mlsl_distribution_create_window": [H, c_void_p, c_size_t, c_int, P(H)],
+        "mlsl_distribution_free_window": [H, H],
+        "mlsl_window_put": [H, c_void_p, c_size_t, c_size_t, c_size_t],
+        "mlsl_window_get": [H, c_void_p, c_size_t, c_size_t, c_size_t],
+        "mlsl_window_fence": [H],
+        "mlsl_window_get_size": [H, c_size_t, P(c_size_t)],
         "mlsl_distribution_gemm_reduce_scatter": [H, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_int, P(H)],
         "mlsl_session_set_global_minibatch_size": [H, c_size_t],
         "mlsl_session_get_global_minibatch_size": [H, P(c_size_t)],

@@ -252,9 +252,48 @@ class Distribution(_Handle):
         return self._req("mlsl_distribution_gemm_reduce_scatter", buffer_address(a), buffer_address(w), buffer_address(out),
                          m, n, k, out_type, group_type)
 
+    def create_window(self, tensor, group_type=GroupType.GLOBAL):
+        """Collective: expose `tensor` (heap memory: mlsl_b200.alloc_tensor / Environment.alloc) to the group."""
+        _pre()
+        h = self._get("mlsl_distribution_create_window", H, buffer_address(tensor), tensor.numel() * tensor.element_size(),
+                      group_type)
+        return Window(h, self, tensor)
+
     def barrier(self, group_type):
         _pre()
         self._call("mlsl_distribution_barrier", group_type)
+
+
+class Window(_Handle):
+    """[ext] RMA window over memory every member of a group exposed (Distribution.create_window).  `put` / `get`
+    address a member by group index and an ELEMENT displacement of the tensor's dtype; both are ordered like the caller's
+    other work and complete at the next `fence()` (collective)."""
+
+    def __init__(self, handle, dist, keepalive):
+        super().__init__(handle)
+        self._dist, self._keep = dist, keepalive
+
+    def put(self, tensor, target_idx, target_disp=0):
+        _pre()
+        self._call("mlsl_window_put", buffer_address(tensor), tensor.numel() * tensor.element_size(), target_idx,
+                   target_disp * tensor.element_size())
+
+    def get(self, tensor, target_idx, target_disp=0):
+        _pre()
+        self._call("mlsl_window_get", buffer_address(tensor), tensor.numel() * tensor.element_size(), target_idx,
+                   target_disp * tensor.element_size())
+
+    def fence(self):
+        _pre()
+        self._call("mlsl_window_fence")
+
+    def get_size(self, member_idx):
+        return self._get("mlsl_window_get_size", c_size_t, member_idx)
+
+    def free(self):
+        if self.handle:
+            check(_lib.lib().mlsl_distribution_free_window(self._dist.handle, self.handle))
+            self.handle, self._keep = None, None
 
 
 class OperationRegInfo(_Handle):

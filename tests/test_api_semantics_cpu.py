@@ -443,3 +443,35 @@ def test_make_install_layout_is_usable(tmp_path):
     r = subprocess.run(["bash", "-c", script], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=120)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "rank 0 of 2" in r.stdout and "rank 1 of 2" in r.stdout and prefix + "/python/mlsl_b200" in r.stdout
+
+
+def test_rma_window_multiprocess_shared_memory():
+    """Windows across real processes: offsets are translated into every peer's mapping of the owner's region."""
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import torch, mlsl_b200 as mlsl
+from mlsl_b200.api import GroupType
+mlsl.init()
+r, W = mlsl.rank(), mlsl.world_size()
+mem = mlsl.alloc_tensor(32, torch.float32)
+mem.fill_(float(r))
+win = mlsl.world_distribution().create_window(mem, GroupType.GLOBAL)
+win.fence()
+win.put(torch.full((8,), 50.0 + r), (r + 1) %% W, target_disp=8)
+win.fence()
+got = torch.zeros(16)
+win.get(got, (r + 2) %% W, target_disp=0)
+win.fence()
+ok = bool((mem[8:16] == 50.0 + (r - 1) %% W).all()) and float(mem[0]) == r
+o = (r + 2) %% W
+ok = ok and bool((got[:8] == o).all()) and bool((got[8:] == 50.0 + (o - 1) %% W).all())
+print("RMA %%s" %% ("OK" if ok else "BAD %%s %%s" %% (mem, got)), flush=True)
+win.free()
+del mem
+mlsl.finalize()
+''' % ROOT
+    env = dict(os.environ, MLSL_BACKEND="host", MLSL_HEAP_SIZE_GB="0.05", MLSL_WATCHDOG_SEC="60", MLSL_JOB_ID="rma%d" % os.getpid())
+    p = subprocess.run([os.path.join(ROOT, "bin", "mlslrun"), "-n", "3", sys.executable, "-c", code], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert p.returncode == 0 and p.stdout.count("RMA OK") == 3, p.stdout[-2000:]

@@ -265,3 +265,36 @@ def test_quantized_allreduce_through_user_plugin():
     # with error feedback the time average converges towards the exact sum
     err8 = (outs[0][1] - ref).abs().max() / ref.abs().max()
     assert err8 < err1 * 2 and err8 < 0.02, (err1, err8)
+
+
+@pytest.mark.parametrize("world", [1, 4])
+def test_rma_window_put_get_fence(world):
+    """[ext] one-sided windows: every rank puts a tagged block into its right neighbour, fences, then gets a block back
+    from its left neighbour's window; range errors are reported."""
+    n = 64
+
+    def body(r, mlsl):
+        from mlsl_b200.api import GroupType
+        from mlsl_b200._lib import MLSLError
+        d = mlsl.world_distribution()
+        mem = mlsl.alloc_tensor(2 * n, torch.float32)
+        mem[:n] = float(r)                      # first half: my own data; second half: filled by my left neighbour
+        win = d.create_window(mem, GroupType.GLOBAL)
+        assert win.get_size((r + 1) % world) == 2 * n * 4
+        win.fence()
+        src = torch.full((n,), 100.0 + r)
+        win.put(src, (r + 1) % world, target_disp=n)
+        win.fence()
+        got_put = mem[n:].clone()               # what my left neighbour put here
+        fetched = torch.zeros(n)
+        win.get(fetched, (r - 1) % world, target_disp=0)
+        win.fence()
+        with pytest.raises(MLSLError, match="exceeds"):
+            win.put(src, (r + 1) % world, target_disp=2 * n - 1)
+        win.free()
+        return got_put, fetched
+
+    for r, (got_put, fetched) in enumerate(run_ranks(world, body)):
+        left = (r - 1) % world
+        assert torch.equal(got_put, torch.full((n,), 100.0 + left))
+        assert torch.equal(fetched, torch.full((n,), float(left)))
