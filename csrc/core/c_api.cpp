@@ -178,6 +178,10 @@ int mlsl_distribution_gemm_reduce_scatter(mlsl_distribution d, const void* a, co
                                           mlsl_data_type ot, mlsl_group_type g, mlsl_comm_req* r) {
   C_GUARD(*need(r) = U(H<Distribution>(d)->GemmReduceScatter(a, w, out, m, n, k, DT(ot), GT(g))))
 }
+int mlsl_distribution_all_gather_gemm(mlsl_distribution d, const void* x, const void* w, void* gathered, void* out, size_t m, size_t n,
+                                       size_t k, mlsl_data_type ot, mlsl_group_type g, mlsl_comm_req* r) {
+  C_GUARD(*need(r) = U(H<Distribution>(d)->AllGatherGemm(x, w, gathered, out, m, n, k, DT(ot), GT(g))))
+}
 int mlsl_distribution_barrier(mlsl_distribution d, mlsl_group_type g) { C_GUARD(H<Distribution>(d)->Barrier(GT(g))) }
 int mlsl_distribution_create_window(mlsl_distribution d, void* base, size_t bytes, mlsl_group_type g, mlsl_window* w) {
   C_GUARD(*need(w) = (mlsl_window)H<Distribution>(d)->CreateWindow(base, bytes, GT(g)))

@@ -59,12 +59,13 @@ enum class OpKind : int {
   SENDRECV_LIST,   // ring-shift style point-to-point list (the reference declares it but never wires it up)
   FUSED_UPDATE,    // B200 extension: reduce-scatter + optimizer step + all-gather in one kernel
   GEMM_RS,         // B200 extension: tcgen05 GEMM whose epilogue reduce-scatters over peer memory
+  AG_GEMM,         // B200 extension (experimental): all-gather of the row shards overlapped with the GEMM that eats them
 };
 
 inline const char* opkind_name(OpKind k) {
   static const char* n[] = {"Barrier", "Bcast", "Reduce", "AllReduce", "AlltoAll", "AlltoAllv", "Gather",
                             "AllGather", "AllGatherv", "Scatter", "ReduceScatter", "SendRecvList",
-                            "FusedUpdate", "GemmRS"};
+                            "FusedUpdate", "GemmRS", "AllGatherGemm"};
   return n[(int)k];
 }
 

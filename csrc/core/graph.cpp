@@ -717,6 +717,23 @@ CommReq* Distribution::GemmReduceScatter(const void* a, const void* w, void* out
   r->desc.out_dtype = to_dtype(outType);
   return d->submit(r, const_cast<void*>(a), out);
 }
+CommReq* Distribution::AllGatherGemm(const void* xShard, const void* w, void* gathered, void* out, size_t M, size_t N, size_t K,
+                                     DataType outType, GroupType gt) {
+  auto d = SELF(DistributionImpl);
+  MLSLB_ASSERT(d->ctx->backend->is_device(), "AllGatherGemm needs the CUDA backend");
+  MLSLB_ASSERT(outType == DT_BF16 || outType == DT_FLOAT, "AllGatherGemm: output must be bf16 or fp32");
+  MLSLB_ASSERT(xShard && w && gathered && out, "AllGatherGemm: NULL buffer");
+  CommRequest* r = d->make_request(mlslb::OpKind::AG_GEMM, DT_BF16, gt);
+  r->desc.gemm.M = (int)M;
+  r->desc.gemm.N = (int)N;
+  r->desc.gemm.K = (int)K;
+  r->desc.gemm.a = xShard;
+  r->desc.gemm.w = w;
+  r->desc.gathered = gathered;
+  r->desc.has_out_dtype = true;
+  r->desc.out_dtype = to_dtype(outType);
+  return d->submit(r, const_cast<void*>(xShard), out);
+}
 // ---- [ext] RMA windows -----------------------------------------------------------------------------------------
 Window* Distribution::CreateWindow(void* base, size_t bytes, GroupType gt) {
   auto d = SELF(DistributionImpl);

@@ -599,6 +599,9 @@ void HostBackend::execute(CommRequest& r) {
     case OpKind::GEMM_RS:
       MLSLB_ASSERT(false, "GEMM+reduce-scatter is a device-only fused op");
       break;
+    case OpKind::AG_GEMM:
+      MLSLB_ASSERT(false, "all-gather+GEMM is a device-only fused op");
+      break;
   }
 
   // ---- copy staged results back, drop the staging buffers -----------------------------------------------

@@ -122,6 +122,12 @@ void CommRequest::setup() {
       buf_bytes_ = 0;
       msg_bytes_ = (size_t)desc.gemm.M * (size_t)desc.gemm.N * 2;
       break;
+    case OpKind::AG_GEMM:
+      send_bytes_ = (size_t)desc.gemm.M / P * (size_t)desc.gemm.K * 2;   // this rank's shard, read by every peer
+      recv_bytes_ = 0;                                                     // Y and the gathered X are local only
+      buf_bytes_ = 0;
+      msg_bytes_ = (size_t)desc.gemm.M * (size_t)desc.gemm.K * 2;
+      break;
   }
   // priority lane: large gradient messages of the earliest operations overtake the rest (the intent of the
   // reference's newest-first Rabenseifner progress, eplib/allreduce_pr.c:76-79: first-layer gradients first).

@@ -79,6 +79,9 @@ struct CommDesc {
     const void* a = nullptr;      // [M, K] bf16, row-major (activations, K-slice of this rank)
     const void* w = nullptr;      // [N, K] bf16, row-major (nn.Linear weight layout, K-slice of this rank)
   } gemm;
+  // fused all-gather + GEMM (OpKind::AG_GEMM): Y[M, N] = concat_rows(X_0..X_{P-1}) * W[N, K]^T; gemm.M/N/K, gemm.a = this
+  // rank's shard X_r [M/P, K], gemm.w = W; `gathered` receives the full X [M, K] (kept for backward)
+  void* gathered = nullptr;
 };
 
 class CommRequest {

@@ -127,11 +127,17 @@ class CudaBackend final : public Backend {
     set_device();
     if (st->inflight && st->recorded) cudaEventSynchronize(st->done);
     else if (st->inflight && st->stream) cudaStreamSynchronize(st->stream);
-    // scratch that a stream-ordered (not host-waited) kernel may still be using must not be recycled early
-    if ((st->residual || st->qstage || !st->stages.empty()) && st->stream) cudaStreamSynchronize(st->stream);
-    drop_stages(st, false);
-    if (st->residual) free(st->residual);
-    if (st->qstage) free(st->qstage);
+    // Scratch that a stream-ordered (not host-waited) kernel may still be using must not be recycled early.  It is
+    // parked behind an event instead of synchronising the stream: one-shot requests (Distribution::*, the fused GEMM
+    // ops) are released inside Environment::Wait, which must not block the CPU in stream-ordered mode.
+    if (st->residual) st->stages.push_back(StageBuf{nullptr, st->residual, 0, false});
+    if (st->qstage) st->stages.push_back(StageBuf{nullptr, st->qstage, 0, false});
+    st->residual = nullptr;
+    st->qstage = nullptr;
+    if (!st->stages.empty()) {
+      if (st->stream) park_stages(st);
+      else drop_stages(st, false);
+    }
     if (st->ready) cudaEventDestroy(st->ready);
     if (st->done) cudaEventDestroy(st->done);
     delete st;
@@ -311,14 +317,22 @@ class CudaBackend final : public Backend {
   std::mutex park_mu_;
   void park_stages(CudaReqState* st) {
     std::lock_guard<std::mutex> g(park_mu_);
-    cudaEvent_t ev;
+    cudaEvent_t ev = nullptr;
     if (!event_pool_.empty()) {
       ev = event_pool_.back();
       event_pool_.pop_back();
-    } else {
-      MLSLB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    } else if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+      ev = nullptr;
     }
-    MLSLB_CUDA(cudaEventRecord(ev, st->stream));
+    // never throws (also runs from destructors): if the event cannot be recorded - e.g. the stream is already gone at
+    // teardown, after a device synchronise - the blocks are simply released
+    if (!ev || cudaEventRecord(ev, st->stream) != cudaSuccess) {
+      cudaGetLastError();
+      if (ev) event_pool_.push_back(ev);
+      for (auto& sb : st->stages) heap_.free((size_t)((char*)sb.slab - slab_)), ctx_->ptrcheck.remove(sb.slab);
+      st->stages.clear();
+      return;
+    }
     // one event guards all blocks of the request: the first entry owns it, the others piggy-back (null event)
     bool first = true;
     for (auto& sb : st->stages) {
@@ -573,7 +587,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   // pull from / push to its own buffers).  Lets ncu profile the kernels on one GPU - under the profiler kernels
   // are serialised, so ranks that wait for each other can never be captured.
   static const bool force_solo = getenv("MLSL_FORCE_KERNEL_SOLO") && atoi(getenv("MLSL_FORCE_KERNEL_SOLO")) != 0;
-  if (!g || g->size() <= 1 ? !((force_solo && g && g->row >= 0) || d.kind == OpKind::FUSED_UPDATE || d.kind == OpKind::GEMM_RS) : false) {
+  if (!g || g->size() <= 1 ? !((force_solo && g && g->row >= 0) || d.kind == OpKind::FUSED_UPDATE || d.kind == OpKind::GEMM_RS || d.kind == OpKind::AG_GEMM) : false) {
     size_t bytes = 0;
     switch (d.kind) {
       case OpKind::ALLREDUCE: case OpKind::REDUCE: case OpKind::REDUCE_SCATTER: case OpKind::ALLGATHER:
@@ -643,6 +657,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   if ((d.kind == OpKind::REDUCE || d.kind == OpKind::GATHER) && me != (int)d.root) rbytes = 0;
   if (d.kind == OpKind::SCATTER && me != (int)d.root) sbytes = 0;
   if (d.kind == OpKind::FUSED_UPDATE) rbytes = n * P * dtype_size(d.has_out_dtype ? d.out_dtype : d.dtype);
+  if (d.kind == OpKind::AG_GEMM) rbytes = 0;   // Y and the gathered X are local: any device memory; the shard is staged if foreign
   if (d.kind == OpKind::GEMM_RS) {
     sbytes = 0;   // A and W are only read by this rank's own TMA loads: any device memory will do
     rbytes = (size_t)d.gemm.M / P * d.gemm.N * (d.has_out_dtype && d.out_dtype == DType::F32 ? 4 : 2);
@@ -808,6 +823,24 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
       a.state1 = (float*)f.state1;
       a.state2 = (float*)f.state2;
       MLSLB_CUDA(launch_fused_update(dc, d.dtype, d.has_out_dtype ? d.out_dtype : d.dtype, so, ro, n, a, ch, s));
+      break;
+    }
+    case OpKind::AG_GEMM: {
+      const CommDesc::GemmRs& gm = d.gemm;
+      const char* why = ag_gemm_check(gm.M, gm.N, gm.K, P);
+      MLSLB_ASSERT(why == nullptr, "AllGatherGemm(M=%d, N=%d, K=%d, P=%d): %s", gm.M, gm.N, gm.K, P, why);
+      MLSLB_ASSERT(is_device_pointer(gm.w) && is_device_pointer(d.gathered) && is_device_pointer(r.recv),
+                   "AllGatherGemm: W, the gathered buffer and the output must be device memory");
+      const int cap = std::min(std::max(1, sm_count_ / std::max(1, ranks_per_device_)), kMaxChannels);
+      int copy_ctas = 0, total_ctas = 0;
+      ag_gemm_grid(gm.M, gm.N, P, cap, &copy_ctas, &total_ctas);
+      if (!st->qstage) {   // launch counters + tile flags: zero once, the kernel keeps them consistent afterwards
+        const size_t sb = ag_gemm_scratch_bytes(gm.M, kMaxChannels);
+        st->qstage = alloc(sb, 256);
+        MLSLB_CUDA(cudaMemsetAsync(st->qstage, 0, sb, s));
+      }
+      const bool out32 = d.has_out_dtype && d.out_dtype == DType::F32;
+      MLSLB_CUDA(launch_ag_gemm(dc, so, gm.w, d.gathered, r.recv, out32, gm.M, gm.N, gm.K, copy_ctas, total_ctas, st->qstage, s));
       break;
     }
     case OpKind::GEMM_RS: {

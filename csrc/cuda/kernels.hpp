@@ -71,6 +71,12 @@ cudaError_t launch_fused_update(const DevComm& dc, DType grad_dt, DType param_dt
 size_t gemm_rs_stage_bytes(int M, int N);
 int gemm_rs_channels(int M, int N, int max_channels);
 const char* gemm_rs_check(int M, int N, int K, int P);   // nullptr when the shape is supported
+// experimental: all-gather of row shards fused with the GEMM that consumes them (csrc/cuda/ag_gemm.cu)
+const char* ag_gemm_check(int M, int N, int K, int P);
+size_t ag_gemm_scratch_bytes(int M, int max_ctas);
+void ag_gemm_grid(int M, int N, int P, int max_ctas, int* copy_ctas, int* total_ctas);
+cudaError_t launch_ag_gemm(const DevComm& dc, unsigned long long x_off, const void* w, void* gathered, void* out, bool out_fp32,
+                           int M, int N, int K, int copy_ctas, int total_ctas, void* scratch, cudaStream_t s);
 // experimental cta_group::2 form (MLSL_GEMM_2CTA=1): 256 x 256 tiles on CTA pairs
 const char* gemm_rs2_check(int M, int N, int K, int P);
 int gemm_rs2_channels(int M, int N, int max_channels);

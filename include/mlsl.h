@@ -229,6 +229,9 @@ int mlsl_distribution_reduce_scatter_ex(mlsl_distribution dist, void* send_buffe
 int mlsl_distribution_send_recv_list(mlsl_distribution dist, void* send_buffer, size_t* send_counts,
                                      size_t* send_offsets, void* recv_buffer, size_t* recv_counts, size_t* recv_offsets,
                                      mlsl_data_type dtype, mlsl_group_type group_type, mlsl_comm_req* req);
+int mlsl_distribution_all_gather_gemm(mlsl_distribution dist, const void* x_shard, const void* w, void* gathered, void* out,
+                                       size_t m, size_t n, size_t k, mlsl_data_type out_type, mlsl_group_type group_type,
+                                       mlsl_comm_req* req);
 /* [ext] RMA windows (one-sided put / get into memory a group member exposed; fence is collective) */
 typedef void* mlsl_window;
 int mlsl_distribution_create_window(mlsl_distribution dist, void* base, size_t bytes, mlsl_group_type group_type,

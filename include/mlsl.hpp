@@ -196,6 +196,12 @@ class Distribution {
   // out bf16 or fp32 (outType).  M % (128 * P) == 0, N % 256 == 0, K % 64 == 0.
   CommReq* GemmReduceScatter(const void* a, const void* w, void* out, size_t M, size_t N, size_t K, DataType outType,
                              GroupType groupType);
+  // [ext, experimental] all-gather fused with the GEMM that consumes it (CUDA backend, one kernel: copy CTAs stream the
+  // peers' row shards into `gathered` while tensor-core CTAs already multiply the rows that have landed):
+  // out[M, N] = concat_rows(X_0 .. X_{P-1}) * W[N, K]^T, xShard = X_r [M/P, K] bf16, gathered [M, K] bf16 (kept for
+  // backward), out bf16 or fp32.  Same shape rules as GemmReduceScatter.
+  CommReq* AllGatherGemm(const void* xShard, const void* w, void* gathered, void* out, size_t M, size_t N, size_t K,
+                         DataType outType, GroupType groupType);
   // [ext] one-sided access (the reference keeps its RMA window table behind ENABLE_MPIRMA_ENDPOINTS,
   // eplib/window.c).  Collective over the group: every member exposes `bytes` at `base` (memory from
   // Environment::Alloc).  FreeWindow is collective too.

@@ -137,6 +137,7 @@ def _declare(l):
         "mlsl_window_fence": [H],
         "mlsl_window_get_size": [H, c_size_t, P(c_size_t)],
         "mlsl_distribution_gemm_reduce_scatter": [H, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_int, P(H)],
+        "mlsl_distribution_all_gather_gemm": [H, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_int, P(H)],
         "mlsl_session_set_global_minibatch_size": [H, c_size_t],
         "mlsl_session_get_global_minibatch_size": [H, P(c_size_t)],
         "mlsl_session_get_phase_type": [H, P(c_int)],

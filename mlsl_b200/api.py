@@ -248,6 +248,10 @@ class Distribution(_Handle):
         return self._req("mlsl_distribution_reduce_scatter_ex", buffer_address(send_buf), buffer_address(recv_buf),
                          recv_count, data_type, red_type, group_type, scale)
 
+    def all_gather_gemm(self, x_shard, w, gathered, out, m, n, k, out_type, group_type):
+        return self._req("mlsl_distribution_all_gather_gemm", buffer_address(x_shard), buffer_address(w),
+                         buffer_address(gathered), buffer_address(out), m, n, k, out_type, group_type)
+
     def gemm_reduce_scatter(self, a, w, out, m, n, k, out_type, group_type):
         return self._req("mlsl_distribution_gemm_reduce_scatter", buffer_address(a), buffer_address(w), buffer_address(out),
                          m, n, k, out_type, group_type)

@@ -70,3 +70,48 @@ def test_tensor_parallel_mlp_cpu(world):
 @pytest.mark.parametrize("world", [1, 2])
 def test_tensor_parallel_mlp_gpu_fused_gemm_rs(world):
     _run(world, "cuda", torch.bfloat16, 3e-2)
+
+
+def _ag_gemm_case(world, backend, fused, dtype, tol, M=512, N=256, K=128):
+    def body(r, mlsl):
+        from mlsl_b200.ops import allgather_gemm
+        dev = "cuda" if backend == "cuda" else "cpu"
+        e = mlsl.env()
+        dist = e.create_distribution(1, world)
+        g = torch.Generator().manual_seed(31)
+        x = (torch.randn(M, K, generator=g) * 0.5).to(dtype)
+        w = (torch.randn(N, K, generator=g) * 0.5).to(dtype)
+        rows = M // world
+        outs = []
+        for _ in range(2):      # twice: flag epochs / staging reuse
+            y, full = allgather_gemm(x[r * rows:(r + 1) * rows].to(dev), w.to(dev), out_dtype=torch.float32,
+                                     group="model", distribution=dist, fused=fused)
+            if backend == "cuda":
+                torch.cuda.current_stream().synchronize()
+            outs.append((y.float().cpu(), full.float().cpu()))
+        e.delete_distribution(dist)
+        assert torch.equal(outs[0][0], outs[1][0])
+        return outs[0]
+
+    env = {"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20"} if backend == "cuda" else None
+    outs = run_ranks(world, body, backend=backend, env=env)
+    g = torch.Generator().manual_seed(31)
+    x = (torch.randn(M, K, generator=g) * 0.5).to(dtype).float()
+    w = (torch.randn(N, K, generator=g) * 0.5).to(dtype).float()
+    ref = x @ w.t()
+    for y, full in outs:
+        assert torch.equal(full, x)
+        assert (y - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_allgather_gemm_unfused_cpu(world):
+    _ag_gemm_case(world, "host", False, torch.float32, 1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("MLSL_TEST_AGGEMM") != "1",
+                    reason="experimental fused all-gather + GEMM kernel: opt in with MLSL_TEST_AGGEMM=1 (not yet run on hardware)")
+@pytest.mark.parametrize("world,M,N,K", [(1, 256, 256, 64), (2, 512, 512, 256), (4, 1024, 768, 512)])
+def test_allgather_gemm_fused_gpu(world, M, N, K):
+    _ag_gemm_case(world, "cuda", True, torch.bfloat16, 2e-2, M, N, K)
