@@ -79,10 +79,56 @@ class _CopyToModelGroup(torch.autograd.Function):
         return gx, None, None
 
 
+class _SeqParallelColumnMatmul(torch.autograd.Function):
+    """y[M, N/P] = all_gather_rows(x[M/P, K]) @ w[N/P, K]^T   (Megatron-style sequence parallelism in front of a column
+    parallel layer).  Forward: all-gather + GEMM (one kernel when the fused op is enabled, mlsl_b200.ops.allgather_gemm);
+    backward: dX[M/P, K] = reduce_scatter_rows(dY @ w) - the same shape of problem as the row-parallel forward, so it
+    runs on the fused GEMM + reduce-scatter kernel - and dW = dY^T @ X_full with the gathered X kept from forward."""
+
+    @staticmethod
+    def forward(ctx, x, w, distribution, group, fused):
+        from ..ops import allgather_gemm
+        ctx.cfg = (distribution, group, fused)
+        ctx.mlsl_state = comm._state()
+        y, full = allgather_gemm(x, w, group=group, distribution=distribution, fused=fused)
+        ctx.save_for_backward(full, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        full, w = ctx.saved_tensors
+        distribution, group, fused = ctx.cfg
+        gy = gy.contiguous()
+        with comm.use_state(ctx.mlsl_state):
+            d, g, P, idx = _group_info(distribution, group)
+            M, Nl = gy.shape
+            K = w.shape[1]
+            use_fused = (fused is not False and comm.is_device() and gy.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and
+                         P > 1 and M % (128 * P) == 0 and K % 256 == 0 and Nl % 64 == 0)
+            if use_fused:
+                from ..ops import gemm_reduce_scatter
+                gx = gemm_reduce_scatter(gy, w.t().contiguous(), group=group, distribution=distribution).clone()
+            else:
+                partial = (gy.to(w.dtype) @ w).contiguous()                 # [M, K]: this rank's share of dX for ALL rows
+                if P == 1:
+                    gx = partial
+                else:
+                    gx = comm.reduce_scatter(partial.view(-1), group=group, distribution=distribution).view(M // P, K).clone()
+        gw = gy.to(full.dtype).t() @ full                                   # [N/P, K]
+        return gx, gw, None, None, None
+
+
 class ColumnParallelLinear(torch.nn.Module):
-    def __init__(self, in_features, out_features, bias=True, distribution=None, group="model", dtype=None, device=None):
+    """Output features are split over the model group.  sequence_parallel=False: the input is replicated, [M, in] ->
+    [M, out/P] (all-reduce of dX in backward).  sequence_parallel=True: the input arrives split over the token rows,
+    [M/P, in] -> [M, out/P]: all-gather + GEMM forward, GEMM + reduce-scatter backward - together with
+    RowParallelLinear (whose output is row-split again) no activation is ever replicated between the two layers' ends."""
+
+    def __init__(self, in_features, out_features, bias=True, distribution=None, group="model", dtype=None, device=None,
+                 sequence_parallel=False, fused=None):
         super().__init__()
         self.distribution, self.group = distribution, group
+        self.sequence_parallel, self.fused = sequence_parallel, fused
         _, _, P, idx = _group_info(distribution, group)
         assert out_features % P == 0
         self.weight = torch.nn.Parameter(torch.empty(out_features // P, in_features, dtype=dtype, device=device))
@@ -90,6 +136,9 @@ class ColumnParallelLinear(torch.nn.Module):
         torch.nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
 
     def forward(self, x):
+        if self.sequence_parallel:
+            y = _SeqParallelColumnMatmul.apply(x, self.weight, self.distribution, self.group, self.fused)
+            return y if self.bias is None else y + self.bias
         x = _CopyToModelGroup.apply(x, self.distribution, self.group)
         return torch.nn.functional.linear(x, self.weight, self.bias)
 

@@ -115,3 +115,40 @@ def test_allgather_gemm_unfused_cpu(world):
 @pytest.mark.parametrize("world,M,N,K", [(1, 256, 256, 64), (2, 512, 512, 256), (4, 1024, 768, 512)])
 def test_allgather_gemm_fused_gpu(world, M, N, K):
     _ag_gemm_case(world, "cuda", True, torch.bfloat16, 2e-2, M, N, K)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_sequence_parallel_mlp_block_cpu(world):
+    """Megatron-SP MLP: tokens split over the model group at both ends ([M/P, D] -> [M/P, D_OUT]); fc1 = all-gather +
+    GEMM, fc2 = GEMM + reduce-scatter; values and every gradient against the single-process MLP."""
+    def body(r, mlsl):
+        from mlsl_b200.parallel.tensor_parallel import ColumnParallelLinear, RowParallelLinear
+        w1, w2, x, t = _full_weights()
+        e = mlsl.env()
+        dist = e.create_distribution(1, world)
+        with _lock:
+            col = ColumnParallelLinear(D_IN, D_HID, bias=False, distribution=dist, sequence_parallel=True)
+            row = RowParallelLinear(D_HID, D_OUT, bias=False, distribution=dist)
+        hs, rows = D_HID // world, M // world
+        with torch.no_grad():
+            col.weight.copy_(w1[r * hs:(r + 1) * hs])
+            row.weight.copy_(w2[:, r * hs:(r + 1) * hs])
+        xin = x[r * rows:(r + 1) * rows].clone().requires_grad_(True)
+        y = row(torch.relu(col(xin)))                      # [M/P, D_OUT]
+        loss = ((y - t[r * rows:(r + 1) * rows]) ** 2).sum() / (M * D_OUT)
+        loss.backward()
+        out = (y.detach(), xin.grad, col.weight.grad, row.weight.grad)
+        e.delete_distribution(dist)
+        return out
+
+    outs = run_ranks(world, body)
+    w1, w2, x, t = _full_weights()
+    w1r, w2r, xr = (v.clone().requires_grad_(True) for v in (w1, w2, x))
+    yr = torch.relu(xr @ w1r.t()) @ w2r.t()
+    ((yr - t) ** 2).mean().backward()
+    hs, rows = D_HID // world, M // world
+    for r, (y, gx, gw1, gw2) in enumerate(outs):
+        assert torch.allclose(y, yr.detach()[r * rows:(r + 1) * rows], rtol=1e-4, atol=1e-5)
+        assert torch.allclose(gx, xr.grad[r * rows:(r + 1) * rows], rtol=1e-4, atol=1e-6)
+        assert torch.allclose(gw1, w1r.grad[r * hs:(r + 1) * hs], rtol=1e-4, atol=1e-6)
+        assert torch.allclose(gw2, w2r.grad[:, r * hs:(r + 1) * hs], rtol=1e-4, atol=1e-6)
