@@ -398,32 +398,3 @@ def test_heap_tensor_explicit_free_then_recycled_address():
     for r, outs in enumerate(_gpu(body, 2)):
         for distinct, ysum, xval in outs:
             assert distinct and ysum == 3.0 and xval == float(r + 1)
-
-
-def test_rma_window_put_get_fence_device():
-    """[ext] one-sided windows on peer-mapped device memory: put into the right neighbour, get from the left one."""
-    world, n = 2, 256
-
-    def body(r, mlsl):
-        from mlsl_b200.api import GroupType
-        d = mlsl.world_distribution()
-        mem = mlsl.alloc_tensor(2 * n, torch.float32)
-        mem[:n] = float(r)
-        win = d.create_window(mem, GroupType.GLOBAL)
-        win.fence()
-        src = torch.full((n,), 100.0 + r, device="cuda")
-        win.put(src, (r + 1) % world, target_disp=n)
-        win.fence()
-        got_put = mem[n:].clone()
-        fetched = torch.zeros(n, device="cuda")
-        win.get(fetched, (r - 1) % world, target_disp=0)
-        win.fence()
-        torch.cuda.current_stream().synchronize()
-        out = (got_put.cpu(), fetched.cpu())
-        win.free()
-        return out
-
-    for r, (got_put, fetched) in enumerate(_gpu(body, world)):
-        left = (r - 1) % world
-        assert torch.equal(got_put, torch.full((n,), 100.0 + left))
-        assert torch.equal(fetched, torch.full((n,), float(left)))
