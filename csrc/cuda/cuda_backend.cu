@@ -287,7 +287,7 @@ class CudaBackend final : public Backend {
   cudaEvent_t pipe_h2d_[kPipeBufs] = {}, pipe_ar_[kPipeBufs] = {}, pipe_d2h_[kPipeBufs] = {}, pipe_start_ = nullptr;
   cudaStream_t h2d_stream_ = nullptr, d2h_stream_ = nullptr;
   bool pipe_used_[kPipeBufs] = {false, false, false};
-  bool launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaStream_t s);
+  bool launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaStream_t s, bool solo = false);
   VmmSlab vmm_;
   char* mc_ = nullptr;
   volatile int* err_host_ = nullptr;
@@ -596,6 +596,9 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
         break;
       default: break;
     }
+    // host-resident all-reduce on one rank (the 1-GPU end-to-end case): same chunked H2D / D2H pipeline as with
+    // peers, so the two PCIe directions overlap instead of one device-driven host-to-host copy
+    if (d.kind == OpKind::ALLREDUCE && !d.compress && r.send != r.recv && launch_host_pipelined(r, DevComm{}, s, true)) return;
     const bool reducing = d.kind == OpKind::ALLREDUCE || d.kind == OpKind::REDUCE_SCATTER || d.kind == OpKind::REDUCE;
     if (reducing && bytes && r.recv && r.recv != r.send && owns(r.recv, bytes) && owns(r.send, bytes)) {
       // one kernel: copy with the scale epilogue fused
@@ -875,10 +878,12 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
 // into chunks that flow through three slab buffers - chunk i+1 is on its way up over PCIe while chunk i is being
 // all-reduced over NVLink and chunk i-1 travels back down, so a step costs ~max(H2D, D2H) instead of their sum.
 // Every rank derives the same chunking from the message size, so the per-chunk kernels pair up across ranks.
-bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaStream_t s) {
+bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaStream_t s, bool solo) {
   const CommDesc& d = r.desc;
   const size_t es = dtype_size(d.dtype), bytes = d.count * es;
   if (bytes < 2 * pipe_chunk_ || !r.send || !r.recv) return false;
+  static const bool enabled = !(getenv("MLSL_HOST_PIPELINE") && atoi(getenv("MLSL_HOST_PIPELINE")) == 0);
+  if (!enabled) return false;
   cudaPointerAttributes as, ar;
   if (cudaPointerGetAttributes(&as, r.send) != cudaSuccess || cudaPointerGetAttributes(&ar, r.recv) != cudaSuccess) {
     cudaGetLastError();
@@ -901,7 +906,7 @@ bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaS
     MLSLB_CUDA(cudaStreamCreateWithPriority(&h2d_stream_, cudaStreamNonBlocking, hi));
     MLSLB_CUDA(cudaStreamCreateWithPriority(&d2h_stream_, cudaStreamNonBlocking, hi));
   }
-  const int P = dc.nranks;
+  const int P = solo ? 1 : dc.nranks;
   MLSLB_CUDA(cudaEventRecord(pipe_start_, s));
   MLSLB_CUDA(cudaStreamWaitEvent(h2d_stream_, pipe_start_, 0));
   const size_t chunk_elems = pipe_chunk_ / es;
@@ -914,7 +919,11 @@ bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaS
     MLSLB_CUDA(cudaEventRecord(pipe_h2d_[b], h2d_stream_));
     MLSLB_CUDA(cudaStreamWaitEvent(s, pipe_h2d_[b], 0));
     const unsigned long long o = (unsigned long long)(pipe_buf_[b] - slab_);
-    MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, o, o, cnt, d.scale, pick_channels(ceil_div(cnt * es, (size_t)P)), s));
+    if (solo) {   // single-rank group: nothing to reduce, the chunk only passes through the GPU (scaled if asked for)
+      if (d.scale != 1.0f) MLSLB_CUDA(launch_scale(d.dtype, pipe_buf_[b], cnt, d.scale, s));
+    } else {
+      MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, o, o, cnt, d.scale, pick_channels(ceil_div(cnt * es, (size_t)P)), s));
+    }
     MLSLB_CUDA(cudaEventRecord(pipe_ar_[b], s));
     MLSLB_CUDA(cudaStreamWaitEvent(d2h_stream_, pipe_ar_[b], 0));
     MLSLB_CUDA(cudaMemcpyAsync((char*)r.recv + off * es, pipe_buf_[b], cnt * es, cudaMemcpyDeviceToHost, d2h_stream_));
