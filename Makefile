@@ -92,7 +92,17 @@ install: all
 	cp scripts/mlslvars.sh $(PREFIX)/intel64/bin/mlslvars.sh
 	@echo "installed into $(PREFIX); source $(PREFIX)/intel64/bin/mlslvars.sh"
 
+# AddressSanitizer + UBSan run of the host runtime: in-process and multi-process functional test, user plug-in path
+asan: bin/mlslrun bin/libmlsl_quant_sample.so
+	$(MAKE) CXX=/usr/bin/g++ NO_CUDA=1 BUILD=/tmp/mlsl_asan/build LIBDIR=/tmp/mlsl_asan/lib LIB=/tmp/mlsl_asan/lib/libmlsl_b200.so \
+	  CXXFLAGS="-O1 -g -std=c++17 -fPIC -pthread -Iinclude -Icsrc -fsanitize=address,undefined -fno-omit-frame-pointer" \
+	  LDFLAGS="-shared -pthread -lrt -ldl -fsanitize=address,undefined" /tmp/mlsl_asan/lib/libmlsl_b200.so
+	/usr/bin/g++ -O1 -g -std=c++17 -fsanitize=address,undefined -pthread -Iinclude -Icsrc csrc/tests/mlsl_functional_test.cpp -o /tmp/mlsl_asan/ftest -L/tmp/mlsl_asan/lib -lmlsl_b200 -Wl,-rpath,/tmp/mlsl_asan/lib
+	cd /tmp/mlsl_asan && MLSL_BACKEND=host ./ftest 2 1 0 1 --inproc 4 | tail -1
+	cd /tmp/mlsl_asan && MLSL_BACKEND=host MLSL_TEST_QUANT_LIB=$(CURDIR)/bin/libmlsl_quant_sample.so ./ftest 1 0 0 0 1 --inproc 4 | tail -1
+	cd /tmp/mlsl_asan && MLSL_BACKEND=host MLSL_HEAP_SIZE_GB=0.2 $(CURDIR)/bin/mlslrun -n 4 ./ftest 2 1 | grep -c "0 FAILED"
+
 clean:
 	rm -rf $(BUILD) $(LIB) bin _install
 
-.PHONY: all clean sass tsan install
+.PHONY: all clean sass tsan asan install

@@ -509,7 +509,10 @@ SessionImpl::~SessionImpl() {
 }
 
 EnvironmentImpl* env_of(RankContext* ctx) {
-  if (!ctx->api_env) ctx->api_env = new EnvironmentImpl(ctx);
+  if (!ctx->api_env) {
+    ctx->api_env = new EnvironmentImpl(ctx);
+    ctx->api_env_free = [](void* p) { delete (EnvironmentImpl*)p; };
+  }
   return (EnvironmentImpl*)ctx->api_env;
 }
 

@@ -272,6 +272,10 @@ struct RankContext {
   bool initialized = false;
   void* io_service = nullptr;              // file-IO offload thread (fileio.cpp), created on first use
   void* api_env = nullptr;                 // MLSL::impl::EnvironmentImpl bound to this context
+  void (*api_env_free)(void*) = nullptr;   // its deleter (the type lives in graph.cpp)
+  ~RankContext() {
+    if (api_env && api_env_free) api_env_free(api_env);
+  }
 
   ProcessGroup* create_group_by_color(ProcessGroup* parent, int color);   // collective over parent
   void free_group(ProcessGroup* g);
