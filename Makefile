@@ -33,6 +33,9 @@ CUDA_OBJ := $(patsubst csrc/%.cu,$(BUILD)/%.o,$(CUDA_SRC))
 LDFLAGS  += -L$(CUDA_HOME)/lib64 -lcudart_static
 endif
 
+# the host reduction loops are written to be auto-vectorised
+$(BUILD)/core/host_backend.o: CXXFLAGS += -O3
+
 TOOLS := bin/mlslrun
 TESTS := bin/libmlsl_quant_sample.so bin/mlsl_functional_test bin/cmlsl_smoke_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
 

@@ -56,15 +56,59 @@ inline T apply(RedOp op, T a, T b) {
 }
 
 // dst[i] = scale * reduce_p src[p][i]   (fixed p order => bitwise identical on every rank)
-template <typename T>
-void reduce_typed(T* dst, const std::vector<const void*>& srcs, size_t n, RedOp op, float scale) {
-  for (size_t i = 0; i < n; ++i) {
-    T a = ((const T*)srcs[0])[i];
-    for (size_t p = 1; p < srcs.size(); ++p) a = apply<T>(op, a, ((const T*)srcs[p])[i]);
-    if (scale != 1.0f) a = (T)(a * (T)scale);
-    dst[i] = a;
+// Blocked so that every pass is a plain two-array loop the compiler vectorises: a block of the first source is copied
+// into a small accumulator, the other sources are folded in one after the other, then the block is written out - dst
+// may alias one of the sources (in-place all-reduce), every block is read completely before it is written.
+struct SumOp {
+  template <typename T> static inline T f(T a, T b) { return (T)(a + b); }
+};
+struct MinOp {
+  template <typename T> static inline T f(T a, T b) { return a < b ? a : b; }
+};
+struct MaxOp {
+  template <typename T> static inline T f(T a, T b) { return a > b ? a : b; }
+};
+
+template <typename T, typename Op>
+static inline void reduce_blocked(T* dst, const void* const* srcs, size_t nsrc, size_t n, float scale) {
+  constexpr size_t B = 8192 / sizeof(T);
+  T acc[B];
+  const bool do_scale = scale != 1.0f;
+  const T sc = (T)scale;
+  for (size_t b0 = 0; b0 < n; b0 += B) {
+    const size_t m = n - b0 < B ? n - b0 : B;
+    const T* __restrict__ s0 = (const T*)srcs[0] + b0;
+    for (size_t i = 0; i < m; ++i) acc[i] = s0[i];
+    for (size_t p = 1; p < nsrc; ++p) {
+      const T* __restrict__ sp = (const T*)srcs[p] + b0;
+      for (size_t i = 0; i < m; ++i) acc[i] = Op::f(acc[i], sp[i]);
+    }
+    if (do_scale)
+      for (size_t i = 0; i < m; ++i) acc[i] = (T)(acc[i] * sc);
+    T* d = dst + b0;
+    for (size_t i = 0; i < m; ++i) d[i] = acc[i];
   }
 }
+
+template <typename T>
+static inline void reduce_by_op(T* dst, const void* const* srcs, size_t nsrc, size_t n, RedOp op, float scale) {
+  switch (op) {
+    case RedOp::SUM: reduce_blocked<T, SumOp>(dst, srcs, nsrc, n, scale); break;
+    case RedOp::MIN: reduce_blocked<T, MinOp>(dst, srcs, nsrc, n, scale); break;
+    case RedOp::MAX: reduce_blocked<T, MaxOp>(dst, srcs, nsrc, n, scale); break;
+  }
+}
+
+// one entry point per element type, cloned for the vector ISAs of the machine it runs on (resolved at load time)
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define MLSLB_SIMD_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define MLSLB_SIMD_CLONES
+#endif
+MLSLB_SIMD_CLONES void reduce_f32(float* d, const void* const* s, size_t ns, size_t n, RedOp op, float sc) { reduce_by_op<float>(d, s, ns, n, op, sc); }
+MLSLB_SIMD_CLONES void reduce_f64(double* d, const void* const* s, size_t ns, size_t n, RedOp op, float sc) { reduce_by_op<double>(d, s, ns, n, op, sc); }
+MLSLB_SIMD_CLONES void reduce_i32(int32_t* d, const void* const* s, size_t ns, size_t n, RedOp op) { reduce_by_op<int32_t>(d, s, ns, n, op, 1.0f); }
+MLSLB_SIMD_CLONES void reduce_u8(uint8_t* d, const void* const* s, size_t ns, size_t n, RedOp op) { reduce_by_op<uint8_t>(d, s, ns, n, op, 1.0f); }
 
 void reduce_half(uint16_t* dst, const std::vector<const void*>& srcs, size_t n, RedOp op, float scale, bool bf) {
   for (size_t i = 0; i < n; ++i) {
@@ -77,11 +121,11 @@ void reduce_half(uint16_t* dst, const std::vector<const void*>& srcs, size_t n, 
 
 void reduce_any(DType dt, void* dst, const std::vector<const void*>& srcs, size_t n, RedOp op, float scale) {
   switch (dt) {
-    case DType::F32: reduce_typed<float>((float*)dst, srcs, n, op, scale); break;
-    case DType::F64: reduce_typed<double>((double*)dst, srcs, n, op, scale); break;
+    case DType::F32: reduce_f32((float*)dst, srcs.data(), srcs.size(), n, op, scale); break;
+    case DType::F64: reduce_f64((double*)dst, srcs.data(), srcs.size(), n, op, scale); break;
     case DType::U8:
-    case DType::F8E4M3: reduce_typed<uint8_t>((uint8_t*)dst, srcs, n, op, 1.0f); break;
-    case DType::I32: reduce_typed<int32_t>((int32_t*)dst, srcs, n, op, 1.0f); break;
+    case DType::F8E4M3: reduce_u8((uint8_t*)dst, srcs.data(), srcs.size(), n, op); break;
+    case DType::I32: reduce_i32((int32_t*)dst, srcs.data(), srcs.size(), n, op); break;
     case DType::BF16: reduce_half((uint16_t*)dst, srcs, n, op, scale, true); break;
     case DType::F16: reduce_half((uint16_t*)dst, srcs, n, op, scale, false); break;
   }

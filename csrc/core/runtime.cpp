@@ -605,13 +605,21 @@ void context_init(RankContext* ctx) {
   ctx->backend->group_created(*ctx->world_group);
 
   // Servers: the reference switches its endpoint servers off on a single node unless MLSL_NUM_SERVERS is set
-  // (src/comm_ep.cpp:1585-1602).  Same rule for the device path (kernels are asynchronous anyway); the host
-  // path needs one server for true non-blocking progress.
+  // (src/comm_ep.cpp:1585-1602).  Same rule here, for both backends.
   // MLSL_CHECK_SINGLE_NODE=0 switches that rule off: the reference's default of 4 servers applies (host path).
   int ns = ctx->env.num_servers;
   if (ns < 0) {
-    if (ctx->backend->is_device() || ctx->world <= 1) ns = 0;
-    else ns = ctx->env.check_single_node ? 1 : 4;
+    if (ctx->backend->is_device() || ctx->world <= 1) {
+      ns = 0;
+    } else if (!ctx->env.check_single_node) {
+      ns = 4;
+    } else {
+      // the reference's own single-node rule (src/comm_ep.cpp:1585-1602): no servers unless asked for.  A collective
+      // then runs inside Start() on the calling thread - 2 us for a small all-reduce on 4 ranks; a hop through a
+      // progress thread costs 20-400 us on a busy or virtualised node (measured, profiles/host_backend_vs_reference_cpu.txt).
+      // MLSL_NUM_SERVERS=1 buys true asynchronous progress when there are cores to spare.
+      ns = 0;
+    }
   }
   ctx->progress.reset(new ProgressEngine(ctx, ns));
   ctx->initialized = true;

@@ -1,12 +1,16 @@
 // mlslrun: single-node process launcher (the role mpiexec.hydra plays for the reference:
 // `mpiexec.hydra -n 4 -ppn 1 ./mlsl_test ...`, reference tests/examples/mlsl_test/Makefile:58-106).
 //
-//   mlslrun -n N [-g] [-e NAME=VALUE]... [--timeout SEC] program [args...]
+//   mlslrun -n N [-g] [-e NAME=VALUE]... [--timeout SEC] [--bind core|none] program [args...]
 //
 // Starts N copies of `program` with MLSL_RANK / MLSL_WORLD_SIZE / MLSL_LOCAL_RANK and a fresh MLSL_JOB_ID
 // (plus the torchrun-style RANK / WORLD_SIZE / LOCAL_RANK), -g additionally pins rank r to GPU r through
-// CUDA_VISIBLE_DEVICES.  The first non-zero exit (or the timeout) terminates the whole process group and
+// CUDA_VISIBLE_DEVICES.  Like hydra, the launcher binds every rank to its own slice of the cores it may use (rank r
+// gets cpus [r*C/N, (r+1)*C/N) when C >= N; --bind none or MLSL_BIND=0 switches that off): ranks spin on each other
+// through shared memory, and two of them time-sharing one core cost ~100 us per synchronisation.
+// The first non-zero exit (or the timeout) terminates the whole process group and
 // becomes the launcher's exit code - fail-fast like the reference's abort-on-assert.
+#include <sched.h>
 #include <signal.h>
 #include <sys/time.h>
 #include <sys/wait.h>
@@ -34,6 +38,7 @@ static void on_signal(int) {
 int main(int argc, char** argv) {
   int n = 1, timeout = 0;
   bool gpus = false;
+  bool bind = !(getenv("MLSL_BIND") && atoi(getenv("MLSL_BIND")) == 0);
   std::vector<std::string> envs;
   int i = 1;
   for (; i < argc; ++i) {
@@ -41,11 +46,12 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-g")) gpus = true;
     else if (!strcmp(argv[i], "-e") && i + 1 < argc) envs.push_back(argv[++i]);
     else if (!strcmp(argv[i], "--timeout") && i + 1 < argc) timeout = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--bind") && i + 1 < argc) bind = strcmp(argv[++i], "none") != 0;
     else if (!strcmp(argv[i], "--")) { ++i; break; }
     else break;
   }
   if (i >= argc || n < 1) {
-    fprintf(stderr, "usage: mlslrun -n N [-g] [-e NAME=VALUE]... [--timeout SEC] program [args...]\n");
+    fprintf(stderr, "usage: mlslrun -n N [-g] [-e NAME=VALUE]... [--timeout SEC] [--bind core|none] program [args...]\n");
     return 2;
   }
   timeval tv;
@@ -55,6 +61,15 @@ int main(int argc, char** argv) {
   signal(SIGINT, on_signal);
   signal(SIGTERM, on_signal);
   g_kids.assign(n, -1);
+  std::vector<int> cpus;   // what the launcher itself may run on (cgroup / taskset aware)
+  {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (bind && sched_getaffinity(0, sizeof(set), &set) == 0)
+      for (int c = 0; c < CPU_SETSIZE; ++c)
+        if (CPU_ISSET(c, &set)) cpus.push_back(c);
+    if ((int)cpus.size() < n) cpus.clear();   // fewer cores than ranks: let the kernel place them
+  }
   for (int r = 0; r < n; ++r) {
     pid_t p = fork();
     if (p < 0) {
@@ -63,6 +78,13 @@ int main(int argc, char** argv) {
       return 1;
     }
     if (p == 0) {
+      if (!cpus.empty()) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        const size_t lo = (size_t)r * cpus.size() / n, hi = (size_t)(r + 1) * cpus.size() / n;
+        for (size_t k = lo; k < hi; ++k) CPU_SET(cpus[k], &set);
+        sched_setaffinity(0, sizeof(set), &set);
+      }
       char buf[32];
       snprintf(buf, sizeof(buf), "%d", r);
       setenv("MLSL_RANK", buf, 1);
