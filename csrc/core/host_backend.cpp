@@ -110,12 +110,34 @@ MLSLB_SIMD_CLONES void reduce_f64(double* d, const void* const* s, size_t ns, si
 MLSLB_SIMD_CLONES void reduce_i32(int32_t* d, const void* const* s, size_t ns, size_t n, RedOp op) { reduce_by_op<int32_t>(d, s, ns, n, op, 1.0f); }
 MLSLB_SIMD_CLONES void reduce_u8(uint8_t* d, const void* const* s, size_t ns, size_t n, RedOp op) { reduce_by_op<uint8_t>(d, s, ns, n, op, 1.0f); }
 
-void reduce_half(uint16_t* dst, const std::vector<const void*>& srcs, size_t n, RedOp op, float scale, bool bf) {
-  for (size_t i = 0; i < n; ++i) {
-    float a = load_as_float((const uint16_t*)srcs[0] + i, bf);
-    for (size_t p = 1; p < srcs.size(); ++p) a = apply<float>(op, a, load_as_float((const uint16_t*)srcs[p] + i, bf));
-    a *= scale;
-    dst[i] = bf ? f32_to_bf16(a) : f32_to_f16(a);
+template <typename Op, bool BF>
+static inline void reduce_half_blocked(uint16_t* dst, const void* const* srcs, size_t nsrc, size_t n, float scale) {
+  constexpr size_t B = 2048;
+  float acc[B];
+  for (size_t b0 = 0; b0 < n; b0 += B) {
+    const size_t m = n - b0 < B ? n - b0 : B;
+    const uint16_t* s0 = (const uint16_t*)srcs[0] + b0;
+    for (size_t i = 0; i < m; ++i) acc[i] = BF ? bf16_to_f32(s0[i]) : f16_to_f32(s0[i]);
+    for (size_t p = 1; p < nsrc; ++p) {
+      const uint16_t* sp = (const uint16_t*)srcs[p] + b0;
+      for (size_t i = 0; i < m; ++i) acc[i] = Op::f(acc[i], BF ? bf16_to_f32(sp[i]) : f16_to_f32(sp[i]));
+    }
+    uint16_t* d = dst + b0;
+    for (size_t i = 0; i < m; ++i) d[i] = BF ? f32_to_bf16(acc[i] * scale) : f32_to_f16(acc[i] * scale);
+  }
+}
+
+MLSLB_SIMD_CLONES void reduce_half(uint16_t* dst, const void* const* srcs, size_t nsrc, size_t n, RedOp op, float scale, bool bf) {
+  switch (op) {
+    case RedOp::SUM:
+      bf ? reduce_half_blocked<SumOp, true>(dst, srcs, nsrc, n, scale) : reduce_half_blocked<SumOp, false>(dst, srcs, nsrc, n, scale);
+      break;
+    case RedOp::MIN:
+      bf ? reduce_half_blocked<MinOp, true>(dst, srcs, nsrc, n, scale) : reduce_half_blocked<MinOp, false>(dst, srcs, nsrc, n, scale);
+      break;
+    case RedOp::MAX:
+      bf ? reduce_half_blocked<MaxOp, true>(dst, srcs, nsrc, n, scale) : reduce_half_blocked<MaxOp, false>(dst, srcs, nsrc, n, scale);
+      break;
   }
 }
 
@@ -126,8 +148,8 @@ void reduce_any(DType dt, void* dst, const std::vector<const void*>& srcs, size_
     case DType::U8:
     case DType::F8E4M3: reduce_u8((uint8_t*)dst, srcs.data(), srcs.size(), n, op); break;
     case DType::I32: reduce_i32((int32_t*)dst, srcs.data(), srcs.size(), n, op); break;
-    case DType::BF16: reduce_half((uint16_t*)dst, srcs, n, op, scale, true); break;
-    case DType::F16: reduce_half((uint16_t*)dst, srcs, n, op, scale, false); break;
+    case DType::BF16: reduce_half((uint16_t*)dst, srcs.data(), srcs.size(), n, op, scale, true); break;
+    case DType::F16: reduce_half((uint16_t*)dst, srcs.data(), srcs.size(), n, op, scale, false); break;
   }
 }
 
