@@ -73,9 +73,10 @@ enum OpType {
 
 enum CompressionType { CT_NONE = 0, CT_QUANTIZATION = 1 };
 
-// Kept for API compatibility: the reference dlopen()s a user quantisation library described by this struct.
-// Here quantisation is built in (block-scaled FP8 E4M3, fused into the all-reduce kernel); the values are
-// recorded and returned, block_size/elem_in_block are reported as 132/128 when left zero.
+// The reference dlopen()s a user quantisation library described by this struct (three function names + block
+// geometry).  The host backend does the same when lib_path is set (csrc/tests/quant_plugin_sample.c is a complete
+// plug-in); the CUDA backend always uses its built-in block-scaled FP8 E4M3 format fused into the all-reduce kernel.
+// With an empty lib_path the built-in format is used everywhere; block_size / elem_in_block then report 132 / 128.
 typedef struct {
   char* lib_path;
   char* quant_buffer_func_name;
