@@ -37,7 +37,7 @@ endif
 $(BUILD)/core/host_backend.o: CXXFLAGS += -O3
 
 TOOLS := bin/mlslrun
-TESTS := bin/libmlsl_quant_sample.so bin/mlsl_functional_test bin/cmlsl_smoke_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
+TESTS := bin/libmlsl_quant_sample.so bin/mlsl_functional_test bin/cmlsl_smoke_test bin/cmlsl_functional_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
 
 all: $(LIB) $(TOOLS) $(TESTS)
 
@@ -65,7 +65,7 @@ bin/libmlsl_quant_sample.so: csrc/tests/quant_plugin_sample.c
 	@mkdir -p bin
 	gcc -O2 -g -std=gnu99 -Wall -shared -fPIC -o $@ $< -lm
 
-bin/cmlsl_smoke_test: csrc/tests/cmlsl_smoke_test.c $(LIB)
+bin/cmlsl_%: csrc/tests/cmlsl_%.c $(LIB)
 	@mkdir -p bin
 	gcc -O2 -g -std=gnu99 -Wall -Iinclude -o $@ $< -L$(LIBDIR) -lmlsl_b200 -lm -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
 

@@ -475,3 +475,12 @@ mlsl.finalize()
     p = subprocess.run([os.path.join(ROOT, "bin", "mlslrun"), "-n", "3", sys.executable, "-c", code], env=env,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert p.returncode == 0 and p.stdout.count("RMA OK") == 3, p.stdout[-2000:]
+
+
+@pytest.mark.parametrize("args", [["1"], ["4"], ["2", "1"], ["2", "1", "1"]])
+def test_c_functional_test_multiprocess(args):
+    """The two-layer scenario through the C binding (data / model / hybrid parallel, distributed update, Test polling)."""
+    env = dict(os.environ, MLSL_BACKEND="host", MLSL_HEAP_SIZE_GB="0.25")
+    res = subprocess.run([_bin("mlslrun"), "-n", "4", "--timeout", "90", _bin("cmlsl_functional_test"), *args],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=150)
+    assert res.returncode == 0 and ": FAILED" not in res.stdout and res.stdout.count("0 FAILED") == 4, res.stdout[-2000:]
