@@ -592,9 +592,11 @@ void context_init(RankContext* ctx) {
   ctx->self_group->is_self = true;
   ctx->global_group = ctx->world_group;
 
-  // backend selection: CUDA when a GPU is usable, host shared memory otherwise (MLSL_BACKEND overrides)
+  // Backend selection.  MLSL_BACKEND=cuda | host; unset ("auto") means host for native programs: sources written
+  // against the reference fill Environment::Alloc memory and the communication buffers with CPU code, which only the
+  // host backend's memory allows.  The Python layer picks cuda itself when a GPU is visible (mlsl_b200/api.py).
   std::string want = ctx->env.backend;
-  if (want == "auto") want = cuda_backend_available() ? "cuda" : "host";
+  if (want == "auto") want = "host";
   if (want == "cuda") {
     ctx->backend = make_cuda_backend(ctx);
     MLSLB_ASSERT(ctx->backend != nullptr, "MLSL_BACKEND=cuda requested but no usable CUDA device / extension");

@@ -458,6 +458,17 @@ class MLSL(_Handle):
         self._call("mlsl_environment_configure", config.encode())
 
     def init(self):
+        # Native programs get the host backend unless they ask for MLSL_BACKEND=cuda (Environment::Alloc must keep
+        # returning CPU-addressable memory for sources written against the reference).  From Python the tensors say where
+        # the data lives, so a visible GPU selects the CUDA backend.
+        import os
+        if "MLSL_BACKEND" not in os.environ:
+            try:
+                import torch
+                use_cuda = torch.cuda.is_available() and cuda_available()
+            except Exception:  # noqa: BLE001
+                use_cuda = False
+            os.environ["MLSL_BACKEND"] = "cuda" if use_cuda else "host"
         self._call("mlsl_environment_init", None, None)
 
     def finalize(self):
