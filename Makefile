@@ -37,7 +37,10 @@ endif
 $(BUILD)/core/host_backend.o: CXXFLAGS += -O3
 
 TOOLS := bin/mlslrun
-TESTS := bin/libmlsl_quant_sample.so bin/mlsl_functional_test bin/cmlsl_smoke_test bin/cmlsl_functional_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
+ifndef NO_CUDA
+CUDA_EXAMPLES := bin/mlsl_example_cuda
+endif
+TESTS := $(CUDA_EXAMPLES) bin/libmlsl_quant_sample.so bin/mlsl_functional_test bin/cmlsl_smoke_test bin/cmlsl_functional_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
 
 all: $(LIB) $(TOOLS) $(TESTS)
 
@@ -64,6 +67,10 @@ bin/%: csrc/tests/%.cpp $(LIB)
 bin/libmlsl_quant_sample.so: csrc/tests/quant_plugin_sample.c
 	@mkdir -p bin
 	gcc -O2 -g -std=gnu99 -Wall -shared -fPIC -o $@ $< -lm
+
+bin/mlsl_example_cuda: csrc/tests/mlsl_example_cuda.cu $(LIB)
+	@mkdir -p bin
+	$(NVCC) -O2 -std=c++17 $(ARCH) -Iinclude -o $@ $< -L$(LIBDIR) -lmlsl_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(LIBDIR)'
 
 bin/cmlsl_%: csrc/tests/cmlsl_%.c $(LIB)
 	@mkdir -p bin
