@@ -1,6 +1,6 @@
 // The native path from C++: MLSL_BACKEND=cuda, device memory from Environment::Alloc, collectives ordered on the
 // caller's CUDA stream.  One rank per GPU:
-//     MLSL_BACKEND=cuda bin/mlslrun -g -n 8 bin/mlsl_example_cuda
+//     bin/mlslrun -n 8 bin/mlsl_example_cuda          (rank r uses GPU LOCAL_RANK = r; every GPU stays visible to every rank)
 // Each rank fills a gradient buffer on its GPU, the fused all-reduce averages it over the data group (one kernel: pull
 // from the peers over NVLink, reduce, scale by 1/N, push), a second all-reduce moves the same data as block-scaled FP8.
 #include <cuda_runtime.h>
