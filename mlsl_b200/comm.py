@@ -260,16 +260,32 @@ def _dist(distribution):
 
 
 def _group(group):
-    return _GROUPS[group] if isinstance(group, str) else group
+    if isinstance(group, str):
+        if group not in _GROUPS:
+            raise ValueError("unknown group %r (expected one of %s)" % (group, ", ".join(sorted(_GROUPS))))
+        return _GROUPS[group]
+    return group
+
+
+def _op(op):
+    if op not in _OPS:
+        raise ValueError("unknown reduction %r (expected sum, min or max)" % (op,))
+    return _OPS[op]
+
+
+def _check_out(what, out, numel, dtype):
+    if out.numel() != numel or out.dtype != dtype:
+        raise ValueError("%s: `out` must hold %d elements of %s (got %d of %s)" % (what, numel, dtype, out.numel(), out.dtype))
+    return _prep(out)
 
 
 def allreduce(tensor, op="sum", group="data", scale=1.0, compress=False, out=None, async_op=False, distribution=None):
     """All-reduce `tensor` (in place unless `out` is given).  `scale` and the optional fp8 `compress`ed transport are
     fused into the reduction kernel."""
     _prep(tensor)
-    out = tensor if out is None else _prep(out)
+    out = tensor if out is None else _check_out("allreduce", out, tensor.numel(), tensor.dtype)
     _sync_stream()
-    req = _dist(distribution).all_reduce_ex(tensor, out, tensor.numel(), mlsl_dtype(tensor.dtype), _OPS[op],
+    req = _dist(distribution).all_reduce_ex(tensor, out, tensor.numel(), mlsl_dtype(tensor.dtype), _op(op),
                                             _group(group), float(scale),
                                             CompressionType.QUANTIZATION if compress else CompressionType.NONE)
     w = Work(env(), req, out, (tensor, out))
@@ -281,11 +297,15 @@ def reduce_scatter(tensor, out=None, op="sum", group="data", scale=1.0, async_op
     _prep(tensor)
     d = _dist(distribution)
     P = d.get_process_count(_group(group))
+    if tensor.numel() % P:
+        raise ValueError("reduce_scatter: %d elements cannot be split over %d ranks" % (tensor.numel(), P))
     n = tensor.numel() // P
     if out is None:
         out = alloc_tensor((n,), tensor.dtype, zero=False) if is_device() else torch.empty(n, dtype=tensor.dtype)
+    else:
+        _check_out("reduce_scatter", out, n, tensor.dtype)
     _sync_stream()
-    req = d.reduce_scatter(tensor, out, n, mlsl_dtype(tensor.dtype), _OPS[op], _group(group), float(scale))
+    req = d.reduce_scatter(tensor, out, n, mlsl_dtype(tensor.dtype), _op(op), _group(group), float(scale))
     w = Work(env(), req, out, (tensor, out))
     return w if async_op else w.wait()
 
@@ -297,6 +317,8 @@ def allgather(tensor, out=None, group="data", async_op=False, distribution=None)
     if out is None:
         out = (alloc_tensor((P * tensor.numel(),), tensor.dtype, zero=False) if is_device()
                else torch.empty(P * tensor.numel(), dtype=tensor.dtype))
+    else:
+        _check_out("allgather", out, P * tensor.numel(), tensor.dtype)
     _sync_stream()
     req = d.all_gather(tensor, tensor.numel(), out, mlsl_dtype(tensor.dtype), _group(group))
     w = Work(env(), req, out, (tensor, out))
@@ -307,8 +329,12 @@ def alltoall(tensor, out=None, group="data", async_op=False, distribution=None):
     _prep(tensor)
     d = _dist(distribution)
     P = d.get_process_count(_group(group))
+    if tensor.numel() % P:
+        raise ValueError("alltoall: %d elements cannot be split over %d ranks" % (tensor.numel(), P))
     if out is None:
         out = alloc_tensor(tuple(tensor.shape), tensor.dtype, zero=False) if is_device() else torch.empty_like(tensor)
+    else:
+        _check_out("alltoall", out, tensor.numel(), tensor.dtype)
     _sync_stream()
     req = d.all_to_all(tensor, tensor.numel() // P, out, mlsl_dtype(tensor.dtype), _group(group))
     w = Work(env(), req, out, (tensor, out))
@@ -346,9 +372,9 @@ def bcast(tensor, root=0, group="data", async_op=False, distribution=None):
 
 def reduce(tensor, out=None, root=0, op="sum", group="data", async_op=False, distribution=None):
     _prep(tensor)
-    out = tensor if out is None else out
+    out = tensor if out is None else _check_out("reduce", out, tensor.numel(), tensor.dtype)
     _sync_stream()
-    req = _dist(distribution).reduce(tensor, out, tensor.numel(), mlsl_dtype(tensor.dtype), _OPS[op], root, _group(group))
+    req = _dist(distribution).reduce(tensor, out, tensor.numel(), mlsl_dtype(tensor.dtype), _op(op), root, _group(group))
     w = Work(env(), req, out, (tensor, out))
     return w if async_op else w.wait()
 

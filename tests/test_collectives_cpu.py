@@ -298,3 +298,33 @@ def test_rma_window_put_get_fence(world):
         left = (r - 1) % world
         assert torch.equal(got_put, torch.full((n,), 100.0 + left))
         assert torch.equal(fetched, torch.full((n,), float(left)))
+
+
+def test_tensor_api_rejects_inconsistent_arguments():
+    """Shapes / dtypes / names that would make the native call read or write out of bounds are refused up front."""
+    def body(r, mlsl):
+        bad = []
+
+        def refused(fn, exc=ValueError):
+            try:
+                fn()
+                bad.append("accepted")
+            except exc:
+                pass
+
+        refused(lambda: mlsl.allreduce(torch.arange(12.).view(3, 4).t()))                       # not contiguous
+        refused(lambda: mlsl.allreduce(torch.ones(4), out=torch.ones(3)))                       # too small
+        refused(lambda: mlsl.allreduce(torch.ones(4), out=torch.ones(4, dtype=torch.float64)))  # other dtype
+        refused(lambda: mlsl.reduce_scatter(torch.ones(5)))
+        refused(lambda: mlsl.alltoall(torch.ones(5)))
+        refused(lambda: mlsl.allgather(torch.ones(4), out=torch.ones(4)))
+        refused(lambda: mlsl.reduce(torch.ones(4), out=torch.ones(2)))
+        refused(lambda: mlsl.allreduce(torch.ones(4), op="prod"))
+        refused(lambda: mlsl.allreduce(torch.ones(4), group="nobody"))
+        refused(lambda: mlsl.allreduce(torch.ones(4, dtype=torch.int64)), TypeError)
+        x = torch.ones(4)
+        mlsl.allreduce(x)            # still consistent on every rank after the refused calls
+        return bad, float(x[0])
+
+    for bad, v in run_ranks(2, body):
+        assert bad == [] and v == 2.0
