@@ -15,6 +15,7 @@
 #include <cstring>
 
 #include "log.hpp"
+#include "tcp_control.hpp"
 
 namespace mlslb {
 
@@ -55,6 +56,11 @@ static uint64_t proc_start_time(int pid) {
 }
 
 Bootstrap::~Bootstrap() {
+  if (tcp_) {
+    tcp_->goodbye();
+    tcp_.reset();
+    return;
+  }
   if (uds_fd_ >= 0) close(uds_fd_);
   if (!inproc_ && ctl_) {
     seal_regions();
@@ -195,7 +201,24 @@ void Bootstrap::wait_slots(uint64_t round) {
   }
 }
 
+std::unique_ptr<Bootstrap> Bootstrap::create_tcp(const std::string& master_addr, int master_port, int rank, int world) {
+  MLSLB_ASSERT(world >= 1 && rank >= 0 && rank < world, "bad rank %d / world %d", rank, world);
+  std::unique_ptr<Bootstrap> b(new Bootstrap());
+  b->rank_ = rank;
+  b->world_ = world;
+  b->key_ = master_addr + ":" + std::to_string(master_port);
+  b->tcp_ = std::make_shared<TcpControl>(master_addr, master_port, rank, world);
+  b->barrier();   // everybody is connected before anyone proceeds
+  return b;
+}
+
 void Bootstrap::allgather(const void* in, void* out, size_t bytes) {
+  if (tcp_) {
+    std::vector<int> all(world_);
+    for (int r = 0; r < world_; ++r) all[r] = r;
+    tcp_->gather(~0ull, ++round_, all, rank_, in, out, bytes);
+    return;
+  }
   size_t off = 0;
   do {
     size_t n = bytes - off < kBootSlotBytes ? bytes - off : kBootSlotBytes;
@@ -216,6 +239,14 @@ void Bootstrap::group_allgather(const std::vector<int>& members, int row, uint64
                                 size_t bytes) {
   MLSLB_ASSERT(bytes <= kGroupSlotBytes, "group_allgather payload too large");
   MLSLB_ASSERT(row >= 0 && row < kMaxGroupRows, "bad signal row %d", row);
+  if (tcp_) {
+    int idx = -1;
+    for (size_t i = 0; i < members.size(); ++i)
+      if (members[i] == rank_) idx = (int)i;
+    MLSLB_ASSERT(idx >= 0, "group_allgather: this rank is not a member");
+    tcp_->gather((uint64_t)row, seq, members, idx, in, out, bytes);
+    return;
+  }
   int par = (int)(seq & 1);
   GroupSlot* slots = ctl_->gslots[row];
   if (bytes) memcpy(slots[rank_].data[par], in, bytes);
@@ -239,6 +270,7 @@ void Bootstrap::group_allgather(const std::vector<int>& members, int row, uint64
 }
 
 void* Bootstrap::create_region(const std::string& name, size_t bytes) {
+  MLSLB_ASSERT(!tcp_, "shared regions do not exist across nodes");
   bytes = round_up(bytes, 4096);
   if (inproc_) {
     void* p = nullptr;
@@ -262,6 +294,7 @@ void* Bootstrap::create_region(const std::string& name, size_t bytes) {
 }
 
 void* Bootstrap::attach_region(int owner, const std::string& name, size_t bytes) {
+  MLSLB_ASSERT(!tcp_, "shared regions do not exist across nodes");
   bytes = round_up(bytes, 4096);
   if (inproc_) {
     std::string k = std::to_string(owner) + "/" + name;
@@ -365,11 +398,17 @@ std::vector<int> Bootstrap::allgather_fd(int fd) {
 }
 
 void Bootstrap::poison(int code) {
+  if (tcp_) {
+    tcp_->poison(code);
+    return;
+  }
   uint64_t expect = 0;
   ctl_->poison.compare_exchange_strong(expect, (uint64_t)code + 1);
 }
-uint64_t Bootstrap::poisoned() const { return ctl_->poison.load(std::memory_order_relaxed); }
-void Bootstrap::heartbeat() { ctl_->heartbeat[rank_].fetch_add(1, std::memory_order_relaxed); }
-uint64_t Bootstrap::peer_heartbeat(int r) const { return ctl_->heartbeat[r].load(std::memory_order_relaxed); }
+uint64_t Bootstrap::poisoned() const { return tcp_ ? tcp_->poisoned() : ctl_->poison.load(std::memory_order_relaxed); }
+void Bootstrap::heartbeat() {
+  if (!tcp_) ctl_->heartbeat[rank_].fetch_add(1, std::memory_order_relaxed);
+}
+uint64_t Bootstrap::peer_heartbeat(int r) const { return tcp_ ? 0 : ctl_->heartbeat[r].load(std::memory_order_relaxed); }
 
 }  // namespace mlslb

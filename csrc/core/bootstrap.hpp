@@ -47,6 +47,7 @@ struct alignas(64) BootCtl {
 };
 
 struct InprocWorld;   // shared state of an in-process world
+class TcpControl;     // control plane of a job that spans nodes (tcp_control.hpp)
 
 class Bootstrap {
  public:
@@ -55,6 +56,10 @@ class Bootstrap {
   static std::vector<std::unique_ptr<Bootstrap>> create_inproc(int world);
   // Multi-process rendezvous through /dev/shm.
   static std::unique_ptr<Bootstrap> create_shm(const std::string& job_key, int rank, int world);
+  // Multi-node rendezvous: rank 0 serves the control plane on master_addr:master_port (net backend).  All-gather,
+  // barrier, the sub-group mailbox and poison work as above; regions and fd passing do not exist across nodes.
+  static std::unique_ptr<Bootstrap> create_tcp(const std::string& master_addr, int master_port, int rank, int world);
+  bool is_tcp() const { return tcp_ != nullptr; }
 
   int rank() const { return rank_; }
   int size() const { return world_; }
@@ -95,6 +100,7 @@ class Bootstrap {
   size_t ctl_bytes_ = 0;
   uint64_t round_ = 0;
   std::shared_ptr<InprocWorld> inproc_;
+  std::shared_ptr<TcpControl> tcp_;
   std::vector<std::string> created_names_;
   int uds_fd_ = -1;
   std::string shm_name(int owner, const std::string& name) const;

@@ -59,6 +59,10 @@ EnvConfig parse_env() {
   geti(c.world, "MLSL_WORLD_SIZE", "WORLD_SIZE");
   geti(c.local_rank, "MLSL_LOCAL_RANK", "LOCAL_RANK");
   geti(c.inproc_ranks, "MLSL_INPROC_RANKS");
+  gets(c.master_addr, "MLSL_MASTER_ADDR", "MASTER_ADDR");
+  if (const char* v = ev("MLSL_MASTER_PORT")) c.master_port = atoi(v);
+  else if (const char* t = ev("MASTER_PORT")) c.master_port = atoi(t) + 1;   // torch's own store owns MASTER_PORT itself
+  else c.master_port = 29571;
   geti(c.stats_iters, "MLSL_STATS_ITERS");
   geti(c.stats_skip, "MLSL_STATS_SKIP");
   if (c.num_servers > 16) c.num_servers = 16;

@@ -41,6 +41,8 @@ struct EnvConfig {
   std::string wait_mode = "host";// MLSL_WAIT_MODE: host (block the CPU) | stream (order the user stream)
   std::string job_id;            // MLSL_JOB_ID (else derived from MASTER_PORT / TORCHELASTIC_RUN_ID)
   int rank = -1, world = -1, local_rank = -1;  // MLSL_RANK/RANK, MLSL_WORLD_SIZE/WORLD_SIZE, LOCAL_RANK
+  std::string master_addr = "127.0.0.1";   // MLSL_MASTER_ADDR / MASTER_ADDR: where rank 0's control server listens (net backend)
+  int master_port = 0;                      // MLSL_MASTER_PORT, else MASTER_PORT + 1, else 29571
   int inproc_ranks = 0;          // MLSL_INPROC_RANKS: >0 -> N virtual ranks inside this process (tests/loopback)
   int stats_iters = 10, stats_skip = 4;  // isolation statistics iterations (reference: 10 / skip 4)
 };

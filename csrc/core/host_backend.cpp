@@ -623,34 +623,7 @@ void HostBackend::execute(CommRequest& r) {
       }
       char* param = (char*)f.param;
       size_t pdts = dtype_size(pdt);
-      float* master = (float*)f.master;
-      float* m1 = (float*)f.state1;
-      float* m2 = (float*)f.state2;
-      float bc1 = 1.f, bc2 = 1.f;
-      if (f.optimizer == 1) {
-        bc1 = 1.f - powf(f.beta1, (float)f.step);
-        bc2 = 1.f - powf(f.beta2, (float)f.step);
-      }
-      for (size_t i = 0; i < n; ++i) {
-        char* pp = param + ((size_t)me * n + i) * pdts;
-        float w = master ? master[i] : (pdt == DType::F32 ? *(float*)pp : bf16_to_f32(*(uint16_t*)pp));
-        float gr = gsum[i];
-        if (f.optimizer == 0) {
-          gr += f.weight_decay * w;
-          if (m1) {
-            m1[i] = f.momentum * m1[i] + gr;
-            gr = m1[i];
-          }
-          w -= f.lr * gr;
-        } else {
-          m1[i] = f.beta1 * m1[i] + (1.f - f.beta1) * gr;
-          m2[i] = f.beta2 * m2[i] + (1.f - f.beta2) * gr * gr;
-          float mh = m1[i] / bc1, vh = m2[i] / bc2;
-          w -= f.lr * (mh / (sqrtf(vh) + f.eps) + f.weight_decay * w);
-        }
-        if (master) master[i] = w;
-        if (pdt == DType::F32) *(float*)pp = w; else *(uint16_t*)pp = f32_to_bf16(w);
-      }
+      host_optimizer_step(f, pdt, param + (size_t)me * n * pdts, gsum.data(), n);
       // publish parameter buffer for the gather step
       mine->recv_off = to_off(param);
       sync(1);
@@ -819,6 +792,46 @@ void HostBackend::exec_plugin_allreduce(CommRequest& r, const ProcessGroup& g, i
 }
 
 }  // namespace
+
+// ---- shared with the net backend ---------------------------------------------------------------------------------------
+void host_reduce(DType dt, void* dst, const std::vector<const void*>& srcs, size_t n, RedOp op, float scale) {
+  reduce_any(dt, dst, srcs, n, op, scale);
+}
+
+// SGD(momentum) / AdamW on one shard: `param_owned` points at the first owned element of the (fp32 or bf16) parameters,
+// gsum holds the reduced, already scaled gradient of the shard (same arithmetic as the fused device kernel).
+void host_optimizer_step(const CommDesc::FusedUpdate& f, DType pdt, char* param_owned, const float* gsum, size_t n) {
+  const size_t pdts = dtype_size(pdt);
+  float* master = (float*)f.master;
+  float* m1 = (float*)f.state1;
+  float* m2 = (float*)f.state2;
+  float bc1 = 1.f, bc2 = 1.f;
+  if (f.optimizer == 1) {
+    bc1 = 1.f - powf(f.beta1, (float)f.step);
+    bc2 = 1.f - powf(f.beta2, (float)f.step);
+  }
+  for (size_t i = 0; i < n; ++i) {
+    char* pp = param_owned + i * pdts;
+    float w = master ? master[i] : (pdt == DType::F32 ? *(float*)pp : bf16_to_f32(*(uint16_t*)pp));
+    float gr = gsum[i];
+    if (f.optimizer == 0) {
+      gr += f.weight_decay * w;
+      if (m1) {
+        m1[i] = f.momentum * m1[i] + gr;
+        gr = m1[i];
+      }
+      w -= f.lr * gr;
+    } else {
+      m1[i] = f.beta1 * m1[i] + (1.f - f.beta1) * gr;
+      m2[i] = f.beta2 * m2[i] + (1.f - f.beta2) * gr * gr;
+      float mh = m1[i] / bc1, vh = m2[i] / bc2;
+      w -= f.lr * (mh / (sqrtf(vh) + f.eps) + f.weight_decay * w);
+    }
+    if (master) master[i] = w;
+    if (pdt == DType::F32) *(float*)pp = w;
+    else *(uint16_t*)pp = f32_to_bf16(w);
+  }
+}
 
 std::unique_ptr<Backend> make_host_backend(RankContext* ctx) { return std::unique_ptr<Backend>(new HostBackend(ctx)); }
 

@@ -1,0 +1,570 @@
+// Net backend: collectives between ranks that share nothing but a network (MLSL_BACKEND=net).
+//
+// The reference reaches other nodes through MPI (src/comm_ep.cpp issues MPI_I* calls on endpoint communicators); this
+// backend is the self-contained counterpart for CPU clusters and for the control-plane-only parts of a multi-node job:
+// a full mesh of TCP connections between the ranks, one generic primitive - every member sends at most one byte range to
+// and receives at most one from every other member, all of them progressed together with non-blocking sockets - and
+// every collective expressed as one or two such exchanges plus a local, fixed-order reduction (so results are bitwise
+// identical on all ranks):
+//   all-gather(v), all-to-all(v), gather, scatter, bcast, send/recv list, barrier : one exchange
+//   reduce-scatter : exchange of slices, then reduce          reduce : gather to the root, then reduce
+//   all-reduce     : reduce-scatter + all-gather              fused update : reduce-scatter + optimizer + all-gather
+// Messages carry a tag (signal row, lane, sequence number, step), so collectives of different groups may be in flight on
+// the same connection; an early message is parked until its collective asks for it.  Buffers are ordinary host memory.
+#include <fcntl.h>
+#include <poll.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+
+#include "log.hpp"
+#include "numeric.hpp"
+#include "runtime.hpp"
+#include "tcp_control.hpp"
+
+namespace mlslb {
+
+namespace {
+
+struct Seg {
+  int peer;      // global rank
+  char* ptr;
+  size_t bytes;
+};
+
+struct WireHdr {
+  uint64_t tag, bytes;
+};
+
+class Mesh {
+ public:
+  void init(RankContext* ctx) {
+    ctx_ = ctx;
+    rank_ = ctx->rank;
+    world_ = ctx->world;
+    fds_.assign(world_, -1);
+    peers_.resize(world_);
+    if (world_ == 1) return;
+    int port = 0;
+    int lfd = tcp_listen("*", 0, world_ + 8, &port);
+    struct Addr {
+      char ip[48];
+      int port;
+    } mine, zero;
+    memset(&zero, 0, sizeof(zero));
+    mine = zero;
+    const std::string& key = ctx->boot->key();                  // "master:port"
+    const size_t colon = key.rfind(':');
+    std::string my_ip = tcp_local_address_towards(key.substr(0, colon), atoi(key.c_str() + colon + 1));
+    if (const char* v = getenv("MLSL_NET_ADDR")) my_ip = v;       // explicit address of this rank's interface
+    snprintf(mine.ip, sizeof(mine.ip), "%s", my_ip.c_str());
+    mine.port = port;
+    std::vector<Addr> all(world_);
+    ctx->boot->allgather(&mine, all.data(), sizeof(Addr));
+    // connect to every lower rank (the listen backlog completes the handshake even before the peer accepts) ...
+    for (int p = 0; p < rank_; ++p) {
+      int fd = tcp_connect_retry(all[p].ip, all[p].port, 60);
+      uint32_t me = (uint32_t)rank_;
+      try {
+        tcp_send_all(fd, &me, sizeof(me));
+      } catch (const Error& e) {
+        MLSLB_ASSERT(false, "data mesh: hello to rank %d failed: %s", p, e.what());
+      }
+      fds_[p] = fd;
+    }
+    // ... and accept every higher one
+    for (int k = rank_ + 1; k < world_; ++k) {
+      int fd = accept4(lfd, nullptr, nullptr, SOCK_CLOEXEC);
+      MLSLB_ASSERT(fd >= 0, "accept(): %s", strerror(errno));
+      tcp_tune(fd);
+      uint32_t who = 0;
+      try {
+        tcp_recv_all(fd, &who, sizeof(who));
+      } catch (const Error& e) {
+        MLSLB_ASSERT(false, "data mesh: a peer connected and vanished: %s", e.what());
+      }
+      MLSLB_ASSERT((int)who > rank_ && (int)who < world_ && fds_[who] < 0, "unexpected peer %u on the data mesh", who);
+      fds_[who] = fd;
+    }
+    close(lfd);
+    for (int p = 0; p < world_; ++p)
+      if (fds_[p] >= 0) {
+        int fl = fcntl_nonblock(fds_[p]);
+        (void)fl;
+      }
+    ctx->boot->barrier();
+  }
+
+  void shutdown_all() {
+    for (int& fd : fds_)
+      if (fd >= 0) {
+        close(fd);
+        fd = -1;
+      }
+  }
+
+  // Every entry of `sends` / `recvs` names a distinct peer.  Returns when all of them have completed.
+  void exchange(uint64_t tag, const std::vector<Seg>& sends, const std::vector<Seg>& recvs) {
+    std::lock_guard<std::mutex> g(mu_);
+    struct Out {
+      int peer;
+      WireHdr hdr;
+      size_t hdr_sent = 0, sent = 0;
+      const char* ptr;
+    };
+    std::vector<Out> outs;
+    for (const Seg& s : sends) {
+      Out o;
+      o.peer = s.peer;
+      o.hdr.tag = tag;
+      o.hdr.bytes = s.bytes;
+      o.ptr = s.ptr;
+      outs.push_back(o);
+    }
+    // expected arrivals; something that came early is already parked
+    size_t pending_in = 0;
+    for (const Seg& r : recvs) {
+      Peer& P = peers_[r.peer];
+      auto it = P.parked.find(tag);
+      if (it != P.parked.end()) {
+        MLSLB_ASSERT(it->second.size() == r.bytes, "message of %zu bytes from rank %d where %zu were expected", it->second.size(),
+                     r.peer, r.bytes);
+        if (r.bytes) memcpy(r.ptr, it->second.data(), r.bytes);
+        P.parked.erase(it);
+      } else {
+        MLSLB_ASSERT(P.expect.find(tag) == P.expect.end(), "two receives from rank %d in one exchange", r.peer);
+        P.expect[tag] = Expect{r.ptr, r.bytes, false};
+        ++pending_in;
+      }
+    }
+    size_t pending_out = outs.size();
+    const uint64_t t0 = now_ns();
+    // first try without sleeping: small messages usually go out and come in at once
+    for (Out& o : outs) {
+      push(o.peer, o.hdr, o.hdr_sent, o.ptr, o.sent);
+      if (o.hdr_sent == sizeof(WireHdr) && o.sent == o.hdr.bytes) --pending_out;
+    }
+    for (int spin = 0; spin < 200 && pending_in; ++spin)
+      for (const Seg& r : recvs)
+        if (peers_[r.peer].expect.count(tag)) pending_in -= drain(r.peer, tag);
+    std::vector<pollfd> pfds;
+    while (pending_in || pending_out) {
+      pfds.clear();
+      // always listen on every connection: a peer may already be sending for a later collective
+      for (int p = 0; p < world_; ++p)
+        if (fds_[p] >= 0) pfds.push_back(pollfd{fds_[p], POLLIN, 0});
+      for (Out& o : outs)
+        if (o.sent < o.hdr.bytes || o.hdr_sent < sizeof(WireHdr))
+          for (pollfd& pf : pfds)
+            if (pf.fd == fds_[o.peer]) pf.events |= POLLOUT;
+      int rc = poll(pfds.data(), (nfds_t)pfds.size(), 100);
+      if (rc < 0 && errno != EINTR) MLSLB_ASSERT(false, "poll(): %s", strerror(errno));
+      if (ctx_->boot->poisoned()) MLSLB_ASSERT(false, "job poisoned by rank %d during a network collective", (int)ctx_->boot->poisoned() - 1);
+      const int wd = ctx_->env.watchdog_sec;
+      if (wd > 0 && now_ns() - t0 > (uint64_t)wd * 1000000000ull) {
+        ctx_->boot->poison(rank_);
+        MLSLB_ASSERT(false, "watchdog: network collective (tag %llx) did not complete in %d s", (unsigned long long)tag, wd);
+      }
+      if (rc <= 0) continue;
+      for (pollfd& pf : pfds) {
+        if (pf.revents & (POLLERR | POLLHUP | POLLNVAL)) {
+          if (!(pf.revents & POLLIN)) MLSLB_ASSERT(false, "connection to a peer broke during a collective");
+        }
+        int peer = -1;
+        for (int p = 0; p < world_; ++p)
+          if (fds_[p] == pf.fd) peer = p;
+        if (pf.revents & POLLIN) pending_in -= drain(peer, tag);
+        if (pf.revents & POLLOUT)
+          for (Out& o : outs)
+            if (o.peer == peer && (o.hdr_sent < sizeof(WireHdr) || o.sent < o.hdr.bytes)) {
+              push(o.peer, o.hdr, o.hdr_sent, o.ptr, o.sent);
+              if (o.hdr_sent == sizeof(WireHdr) && o.sent == o.hdr.bytes) --pending_out;
+            }
+      }
+    }
+  }
+
+ private:
+  struct Expect {
+    char* ptr;
+    size_t bytes;
+    bool done;
+  };
+  struct Peer {
+    // incoming parser
+    WireHdr hdr;
+    size_t hdr_got = 0, got = 0;
+    char* dst = nullptr;                  // where the current payload goes (user buffer or parking space)
+    std::vector<char> stash;              // parking space of the message being read, if nobody waits for it yet
+    bool to_stash = false;
+    std::map<uint64_t, Expect> expect;    // tag -> waiting receive of the running exchange
+    std::map<uint64_t, std::vector<char>> parked;
+  };
+
+  static int fcntl_nonblock(int fd);
+
+  void push(int peer, const WireHdr& h, size_t& hdr_sent, const char* ptr, size_t& sent) {
+    const int fd = fds_[peer];
+    while (hdr_sent < sizeof(WireHdr)) {
+      ssize_t n = send(fd, (const char*)&h + hdr_sent, sizeof(WireHdr) - hdr_sent, MSG_NOSIGNAL);
+      if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return;
+      if (n < 0 && errno == EINTR) continue;
+      MLSLB_ASSERT(n > 0, "send() to rank %d: %s", peer, strerror(errno));
+      hdr_sent += (size_t)n;
+    }
+    while (sent < h.bytes) {
+      ssize_t n = send(fd, ptr + sent, h.bytes - sent, MSG_NOSIGNAL);
+      if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return;
+      if (n < 0 && errno == EINTR) continue;
+      MLSLB_ASSERT(n > 0, "send() to rank %d: %s", peer, strerror(errno));
+      sent += (size_t)n;
+    }
+  }
+
+  // read what is available from `peer`; returns how many receives of the running exchange completed
+  size_t drain(int peer, uint64_t /*running_tag*/) {
+    Peer& P = peers_[peer];
+    const int fd = fds_[peer];
+    size_t completed = 0;
+    for (;;) {
+      if (P.hdr_got < sizeof(WireHdr)) {
+        ssize_t n = recv(fd, (char*)&P.hdr + P.hdr_got, sizeof(WireHdr) - P.hdr_got, 0);
+        if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return completed;
+        if (n < 0 && errno == EINTR) continue;
+        MLSLB_ASSERT(n > 0, "rank %d closed its connection in the middle of a job", peer);
+        P.hdr_got += (size_t)n;
+        if (P.hdr_got < sizeof(WireHdr)) continue;
+        P.got = 0;
+        auto it = P.expect.find(P.hdr.tag);
+        if (it != P.expect.end()) {
+          MLSLB_ASSERT(it->second.bytes == P.hdr.bytes, "message of %llu bytes from rank %d where %zu were expected",
+                       (unsigned long long)P.hdr.bytes, peer, it->second.bytes);
+          P.dst = it->second.ptr;
+          P.to_stash = false;
+        } else {
+          P.stash.assign(P.hdr.bytes, 0);
+          P.dst = P.stash.data();
+          P.to_stash = true;
+        }
+      }
+      while (P.got < P.hdr.bytes) {
+        ssize_t n = recv(fd, P.dst + P.got, P.hdr.bytes - P.got, 0);
+        if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return completed;
+        if (n < 0 && errno == EINTR) continue;
+        MLSLB_ASSERT(n > 0, "rank %d closed its connection in the middle of a message", peer);
+        P.got += (size_t)n;
+      }
+      // message complete
+      if (P.to_stash) {
+        // its collective may have started while the payload was still trickling in
+        auto it = P.expect.find(P.hdr.tag);
+        if (it != P.expect.end()) {
+          MLSLB_ASSERT(it->second.bytes == P.hdr.bytes, "message of %llu bytes from rank %d where %zu were expected",
+                       (unsigned long long)P.hdr.bytes, peer, it->second.bytes);
+          if (P.hdr.bytes) memcpy(it->second.ptr, P.stash.data(), P.hdr.bytes);
+          P.expect.erase(it);
+          ++completed;
+        } else {
+          P.parked[P.hdr.tag] = std::move(P.stash);
+        }
+        P.stash.clear();
+      } else {
+        P.expect.erase(P.hdr.tag);
+        ++completed;
+      }
+      P.hdr_got = 0;
+      P.dst = nullptr;
+    }
+  }
+
+  RankContext* ctx_ = nullptr;
+  int rank_ = 0, world_ = 1;
+  std::vector<int> fds_;
+  std::vector<Peer> peers_;
+  std::mutex mu_;
+};
+
+int Mesh::fcntl_nonblock(int fd) {
+  int fl = fcntl(fd, F_GETFL, 0);
+  return fcntl(fd, F_SETFL, fl | O_NONBLOCK);
+}
+
+class NetBackend final : public Backend {
+ public:
+  explicit NetBackend(RankContext* ctx) : ctx_(ctx) { mesh_.init(ctx); }
+  const char* name() const override { return "net"; }
+  void* alloc(size_t bytes, size_t align) override {
+    void* p = nullptr;
+    MLSLB_ASSERT(posix_memalign(&p, std::max<size_t>(align ? align : 64, 64), round_up(std::max<size_t>(bytes, 1), 64)) == 0,
+                 "allocation of %zu bytes failed", bytes);
+    ctx_->ptrcheck.add(p, bytes);
+    return p;
+  }
+  void free(void* p) override {
+    if (!p) return;
+    ctx_->ptrcheck.remove(p);
+    ::free(p);
+  }
+  bool owns(const void*, size_t) const override { return true; }   // any host buffer can go on the wire
+  void prepare(CommRequest&) override {}
+  void release(CommRequest&) override {}
+  void launch(CommRequest& r) override {
+    execute(r);
+    r.state.store(CommRequest::DONE, std::memory_order_release);
+  }
+  bool test(CommRequest& r) override { return r.state.load(std::memory_order_acquire) >= CommRequest::DONE; }
+  void wait(CommRequest& r) override {
+    uint64_t spins = 0;
+    while (r.state.load(std::memory_order_acquire) < CommRequest::DONE)
+      if ((++spins & 0xff) == 0) sched_yield();
+  }
+  uint64_t heap_offset(const void*) const override {
+    MLSLB_ASSERT(false, "RMA windows need a shared address space: not available on the net backend");
+    return 0;
+  }
+  void* peer_heap_ptr(int, uint64_t) override {
+    MLSLB_ASSERT(false, "RMA windows need a shared address space: not available on the net backend");
+    return nullptr;
+  }
+  void finalize() override {
+    try {
+      ctx_->boot->barrier();
+    } catch (const std::exception&) {
+    }
+    mesh_.shutdown_all();
+  }
+  std::string describe() const override { return "net backend (TCP mesh, " + std::to_string(ctx_->world) + " ranks)"; }
+
+ private:
+  RankContext* ctx_;
+  Mesh mesh_;
+  void execute(CommRequest& r);
+};
+
+void NetBackend::execute(CommRequest& r) {
+  const CommDesc& d = r.desc;
+  ProcessGroup* gp = d.group;
+  const size_t dt = dtype_size(d.dtype), n = d.count;
+  char* S = (char*)r.send;
+  char* R = (char*)r.recv;
+  if (!gp || gp->size() <= 1) {   // local semantics, like the other backends
+    size_t bytes = 0;
+    switch (d.kind) {
+      case OpKind::ALLREDUCE: case OpKind::REDUCE: case OpKind::REDUCE_SCATTER: case OpKind::ALLGATHER: case OpKind::GATHER:
+      case OpKind::SCATTER: case OpKind::ALLTOALL: case OpKind::ALLGATHERV:
+        bytes = n * dt;
+        break;
+      default: break;
+    }
+    if (bytes && R && R != S) memcpy(R, S, bytes);
+    if ((d.kind == OpKind::ALLTOALLV || d.kind == OpKind::SENDRECV_LIST) && !d.send_counts.empty() && d.send_counts[0])
+      memmove(R + d.recv_offsets[0] * dt, S + d.send_offsets[0] * dt, d.send_counts[0] * dt);
+    if (d.kind == OpKind::FUSED_UPDATE) {
+      const DType pdt = d.has_out_dtype ? d.out_dtype : d.dtype;
+      std::vector<float> gs(n);
+      for (size_t i = 0; i < n; ++i) gs[i] = (d.dtype == DType::F32 ? ((const float*)S)[i] : bf16_to_f32(((const uint16_t*)S)[i])) * d.scale;
+      host_optimizer_step(d.fused, pdt, (char*)d.fused.param, gs.data(), n);
+    } else if (d.scale != 1.0f && R && (d.kind == OpKind::ALLREDUCE || d.kind == OpKind::REDUCE_SCATTER)) {
+      std::vector<const void*> one{R};
+      host_reduce(d.dtype, R, one, n, RedOp::SUM, d.scale);
+    }
+    return;
+  }
+  const ProcessGroup& g = *gp;
+  const int P = g.size(), me = g.idx;
+  auto tag = [&](int step) {
+    return ((uint64_t)(uint8_t)g.row << 56) | ((uint64_t)(r.lane & 0xff) << 48) | ((r.group_seq & 0xffffffffffull) << 8) |
+           (uint64_t)(step & 0xff);
+  };
+  auto peer = [&](int p) { return g.members[p]; };
+  std::vector<Seg> snd, rcv;
+  auto go = [&](int step) {
+    mesh_.exchange(tag(step), snd, rcv);
+    snd.clear();
+    rcv.clear();
+  };
+  // reduce `P` equally sized slices sitting in tmp (slice p from member p; my own contribution read from `own`)
+  auto reduce_slices = [&](char* dst, const char* own, std::vector<char>& tmp, size_t elems, float scale) {
+    std::vector<const void*> srcs(P);
+    for (int p = 0; p < P; ++p) srcs[p] = p == me ? (const void*)own : (const void*)(tmp.data() + (size_t)p * elems * dt);
+    if (elems) host_reduce(d.dtype, dst, srcs, elems, d.rop, scale);
+  };
+
+  switch (d.kind) {
+    case OpKind::BARRIER:
+      for (int p = 0; p < P; ++p)
+        if (p != me) {
+          snd.push_back(Seg{peer(p), nullptr, 0});
+          rcv.push_back(Seg{peer(p), nullptr, 0});
+        }
+      go(0);
+      break;
+    case OpKind::BCAST:
+      if (me == (int)d.root) {
+        for (int p = 0; p < P; ++p)
+          if (p != me) snd.push_back(Seg{peer(p), R, n * dt});
+      } else {
+        rcv.push_back(Seg{peer((int)d.root), R, n * dt});
+      }
+      go(0);
+      break;
+    case OpKind::ALLGATHER:
+    case OpKind::ALLGATHERV: {
+      std::vector<size_t> cnt(P, n), off(P, 0);
+      if (d.kind == OpKind::ALLGATHERV) cnt.assign(d.recv_counts.begin(), d.recv_counts.end());
+      for (int p = 1; p < P; ++p) off[p] = off[p - 1] + cnt[p - 1];
+      if (R + off[me] * dt != S) memmove(R + off[me] * dt, S, cnt[me] * dt);
+      for (int p = 0; p < P; ++p)
+        if (p != me) {
+          snd.push_back(Seg{peer(p), R + off[me] * dt, cnt[me] * dt});
+          rcv.push_back(Seg{peer(p), R + off[p] * dt, cnt[p] * dt});
+        }
+      go(0);
+      break;
+    }
+    case OpKind::ALLTOALL:
+    case OpKind::ALLTOALLV:
+    case OpKind::SENDRECV_LIST: {
+      const bool v = d.kind != OpKind::ALLTOALL;
+      auto sc = [&](int p) { return v ? d.send_counts[p] : n; };
+      auto so = [&](int p) { return v ? d.send_offsets[p] : (size_t)p * n; };
+      auto rc = [&](int p) { return v ? d.recv_counts[p] : n; };
+      auto ro = [&](int p) { return v ? d.recv_offsets[p] : (size_t)p * n; };
+      std::vector<char> stage;   // in place: outgoing data must survive the incoming writes
+      const char* src = S;
+      if (S == R) {
+        size_t total = 0;
+        for (int p = 0; p < P; ++p) total = std::max(total, so(p) + sc(p));
+        stage.assign(S, S + total * dt);
+        src = stage.data();
+      }
+      if (sc(me)) memmove(R + ro(me) * dt, src + so(me) * dt, sc(me) * dt);
+      for (int p = 0; p < P; ++p)
+        if (p != me) {
+          if (sc(p) || !v) snd.push_back(Seg{peer(p), (char*)src + so(p) * dt, sc(p) * dt});
+          if (rc(p) || !v) rcv.push_back(Seg{peer(p), R + ro(p) * dt, rc(p) * dt});
+        }
+      go(0);
+      break;
+    }
+    case OpKind::GATHER:
+      if (me == (int)d.root) {
+        memmove(R + (size_t)me * n * dt, S, n * dt);
+        for (int p = 0; p < P; ++p)
+          if (p != me) rcv.push_back(Seg{peer(p), R + (size_t)p * n * dt, n * dt});
+      } else {
+        snd.push_back(Seg{peer((int)d.root), S, n * dt});
+      }
+      go(0);
+      break;
+    case OpKind::SCATTER:
+      if (me == (int)d.root) {
+        for (int p = 0; p < P; ++p)
+          if (p != me) snd.push_back(Seg{peer(p), S + (size_t)p * n * dt, n * dt});
+        memmove(R, S + (size_t)me * n * dt, n * dt);
+      } else {
+        rcv.push_back(Seg{peer((int)d.root), R, n * dt});
+      }
+      go(0);
+      break;
+    case OpKind::REDUCE_SCATTER: {
+      std::vector<char> tmp((size_t)P * n * dt);
+      for (int p = 0; p < P; ++p)
+        if (p != me) {
+          snd.push_back(Seg{peer(p), S + (size_t)p * n * dt, n * dt});
+          rcv.push_back(Seg{peer(p), tmp.data() + (size_t)p * n * dt, n * dt});
+        }
+      go(0);
+      std::vector<char> own(S + (size_t)me * n * dt, S + (size_t)(me + 1) * n * dt);   // R may alias S
+      reduce_slices(R, own.data(), tmp, n, d.scale);
+      break;
+    }
+    case OpKind::REDUCE: {
+      if (me == (int)d.root) {
+        std::vector<char> tmp((size_t)P * n * dt);
+        for (int p = 0; p < P; ++p)
+          if (p != me) rcv.push_back(Seg{peer(p), tmp.data() + (size_t)p * n * dt, n * dt});
+        go(0);
+        std::vector<char> own(S, S + n * dt);
+        reduce_slices(R, own.data(), tmp, n, 1.0f);
+      } else {
+        snd.push_back(Seg{peer((int)d.root), S, n * dt});
+        go(0);
+      }
+      break;
+    }
+    case OpKind::ALLREDUCE: {
+      // reduce-scatter over ceil(n / P) sized slices, then all-gather of the reduced slices
+      const size_t per = ceil_div(n, (size_t)P);
+      auto lo = [&](int p) { return std::min(n, (size_t)p * per); };
+      auto len = [&](int p) { return std::min(n, lo(p) + per) - lo(p); };
+      std::vector<char> tmp((size_t)P * per * dt);
+      for (int p = 0; p < P; ++p)
+        if (p != me) {
+          snd.push_back(Seg{peer(p), S + lo(p) * dt, len(p) * dt});
+          rcv.push_back(Seg{peer(p), tmp.data() + (size_t)p * per * dt, len(me) * dt});
+        }
+      go(0);
+      std::vector<char> own(S + lo(me) * dt, S + (lo(me) + len(me)) * dt);
+      {
+        std::vector<const void*> srcs(P);
+        for (int p = 0; p < P; ++p) srcs[p] = p == me ? (const void*)own.data() : (const void*)(tmp.data() + (size_t)p * per * dt);
+        if (len(me)) host_reduce(d.dtype, R + lo(me) * dt, srcs, len(me), d.rop, d.scale);
+      }
+      for (int p = 0; p < P; ++p)
+        if (p != me) {
+          snd.push_back(Seg{peer(p), R + lo(me) * dt, len(me) * dt});
+          rcv.push_back(Seg{peer(p), R + lo(p) * dt, len(p) * dt});
+        }
+      go(1);
+      break;
+    }
+    case OpKind::FUSED_UPDATE: {
+      MLSLB_ASSERT(d.dtype == DType::F32 || d.dtype == DType::BF16, "fused update: gradient dtype must be f32/bf16");
+      const DType pdt = d.has_out_dtype ? d.out_dtype : d.dtype;
+      MLSLB_ASSERT(pdt == DType::F32 || pdt == DType::BF16, "fused update: parameter dtype must be f32/bf16");
+      const size_t pdts = dtype_size(pdt);
+      std::vector<char> tmp((size_t)P * n * dt);
+      for (int p = 0; p < P; ++p)
+        if (p != me) {
+          snd.push_back(Seg{peer(p), S + (size_t)p * n * dt, n * dt});
+          rcv.push_back(Seg{peer(p), tmp.data() + (size_t)p * n * dt, n * dt});
+        }
+      go(0);
+      std::vector<float> gsum(n);
+      for (size_t i = 0; i < n; ++i) {
+        float a = 0.f;
+        for (int p = 0; p < P; ++p) {
+          const char* sp = (p == me ? S + (size_t)me * n * dt : tmp.data() + (size_t)p * n * dt) + i * dt;
+          a += d.dtype == DType::F32 ? *(const float*)sp : bf16_to_f32(*(const uint16_t*)sp);
+        }
+        gsum[i] = a * d.scale;
+      }
+      char* param = (char*)d.fused.param;
+      host_optimizer_step(d.fused, pdt, param + (size_t)me * n * pdts, gsum.data(), n);
+      for (int p = 0; p < P; ++p)
+        if (p != me) {
+          snd.push_back(Seg{peer(p), param + (size_t)me * n * pdts, n * pdts});
+          rcv.push_back(Seg{peer(p), param + (size_t)p * n * pdts, n * pdts});
+        }
+      go(1);
+      break;
+    }
+    case OpKind::GEMM_RS:
+    case OpKind::AG_GEMM:
+      MLSLB_ASSERT(false, "%s is a device-only fused op", opkind_name(d.kind));
+      break;
+  }
+}
+
+}  // namespace
+
+std::unique_ptr<Backend> make_net_backend(RankContext* ctx) { return std::unique_ptr<Backend>(new NetBackend(ctx)); }
+
+}  // namespace mlslb

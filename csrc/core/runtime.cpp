@@ -563,9 +563,12 @@ void context_init(RankContext* ctx) {
   } else {
     int world = ctx->env.world > 0 ? ctx->env.world : 1;
     int rank = ctx->env.rank >= 0 ? ctx->env.rank : 0;
+    const bool net = ctx->env.backend == "net" || ctx->env.backend == "tcp";
     if (world == 1) {
       auto v = Bootstrap::create_inproc(1);
       ctx->boot = std::move(v[0]);
+    } else if (net) {
+      ctx->boot = Bootstrap::create_tcp(ctx->env.master_addr, ctx->env.master_port, rank, world);
     } else {
       ctx->boot = Bootstrap::create_shm(derive_job_key(ctx->env), rank, world);
     }
@@ -600,9 +603,11 @@ void context_init(RankContext* ctx) {
   if (want == "cuda") {
     ctx->backend = make_cuda_backend(ctx);
     MLSLB_ASSERT(ctx->backend != nullptr, "MLSL_BACKEND=cuda requested but no usable CUDA device / extension");
+  } else if ((want == "net" || want == "tcp") && ctx->boot->is_tcp()) {
+    ctx->backend = make_net_backend(ctx);
   } else {
-    MLSLB_ASSERT(want == "host", "unknown MLSL_BACKEND '%s' (auto|host|cuda)", want.c_str());
-    ctx->backend = make_host_backend(ctx);
+    MLSLB_ASSERT(want == "host" || want == "net" || want == "tcp", "unknown MLSL_BACKEND '%s' (host|cuda|net)", want.c_str());
+    ctx->backend = make_host_backend(ctx);   // also a single-rank or in-process "net" job: nothing crosses a wire
   }
   ctx->backend->group_created(*ctx->world_group);
 
@@ -623,6 +628,7 @@ void context_init(RankContext* ctx) {
       ns = 0;
     }
   }
+  if (ctx->boot->is_tcp() && ns > 1) ns = 1;   // one queue keeps the issue order of collectives that share connections
   ctx->progress.reset(new ProgressEngine(ctx, ns));
   ctx->initialized = true;
   install_signal_handlers(ctx);

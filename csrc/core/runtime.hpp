@@ -162,6 +162,10 @@ class Backend {
 };
 
 std::unique_ptr<Backend> make_host_backend(RankContext* ctx);
+std::unique_ptr<Backend> make_net_backend(RankContext* ctx);   // TCP mesh between nodes (net_backend.cpp)
+// CPU building blocks shared by the host and net backends (host_backend.cpp)
+void host_reduce(DType dt, void* dst, const std::vector<const void*>& srcs, size_t n, RedOp op, float scale);
+void host_optimizer_step(const CommDesc::FusedUpdate& f, DType pdt, char* param_owned, const float* gsum, size_t n);
 std::unique_ptr<Backend> make_cuda_backend(RankContext* ctx);   // null when no usable GPU
 bool cuda_backend_available();
 

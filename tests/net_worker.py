@@ -1,0 +1,42 @@
+"""One rank of a multi-node (net backend, TCP) job: the randomised collective program of test_fuzz_cpu.py, a fused
+distributed update and a failure-free finalize.  Started by bin/mlslrun --nnodes ... from test_net_backend_cpu.py."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import mlsl_b200 as mlsl  # noqa: E402
+from test_fuzz_cpu import check_rank, make_program, run_program  # noqa: E402
+
+
+def main():
+    seed = int(sys.argv[1])
+    mlsl.init()
+    r, world = mlsl.rank(), mlsl.world_size()
+    assert mlsl.env().get_backend_name() == "net", mlsl.env().describe_backend()
+    D, M, program = make_program(world, seed)
+    results = run_program(r, mlsl, world, D, M, program)
+    check_rank(r, world, D, M, program, results)
+    # sharded optimizer over the wire: two steps of AdamW must leave every replica with identical weights
+    torch.manual_seed(5)
+    model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4))
+    opt = mlsl.DistributedOptimizer(model.parameters(), lr=1e-2, optimizer="adamw", mode="fused", bucket_mb=0.002)
+    g = torch.Generator().manual_seed(100 + r)
+    for _ in range(2):
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(model(torch.randn(8, 16, generator=g)), torch.randn(8, 4, generator=g)).backward()
+        opt.step()
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).contiguous()
+    ref = flat.clone()
+    mlsl.bcast(ref, root=0)
+    assert torch.equal(flat, ref)
+    opt.close()
+    mlsl.finalize()
+    print("NET OK rank %d of %d (D=%d M=%d, %d ops)" % (r, world, D, M, len(program)), flush=True)
+
+
+if __name__ == "__main__":
+    main()

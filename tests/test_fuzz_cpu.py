@@ -34,9 +34,8 @@ def test_random_collective_sequences(world, seed):
     run_fuzz(world, seed, "host")
 
 
-def run_fuzz(world, seed, backend):
+def make_program(world, seed):
     rng = random.Random(seed)
-    dev = "cuda" if backend == "cuda" else "cpu"
     facts = [(d, m) for d in range(1, world + 1) for m in range(1, world + 1) if d * m == world]
     D, M = rng.choice(facts)
     program = []
@@ -47,8 +46,11 @@ def run_fuzz(world, seed, backend):
                             dtype=rng.choice(list(DT)), red=rng.choice(["sum", "min", "max"]), root=rng.randrange(64),
                             heap=rng.random() < 0.5, seed=seed * 100 + step,
                             cnts=[rng.randrange(0, 9) for _ in range(64)]))
+    return D, M, program
 
-    def body(r, mlsl):
+
+def run_program(r, mlsl, world, D, M, program, dev="cpu"):
+    if True:
         e = mlsl.env()
         dist = e.create_distribution(D, M)
         res = []
@@ -121,9 +123,18 @@ def run_fuzz(world, seed, backend):
         e.delete_distribution(dist)
         return res
 
-    env = {"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20"} if backend == "cuda" else None
-    outs = run_ranks(world, body, backend=backend, env=env)
 
+def run_fuzz(world, seed, backend):
+    D, M, program = make_program(world, seed)
+    dev = "cuda" if backend == "cuda" else "cpu"
+    env = {"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20"} if backend == "cuda" else None
+    outs = run_ranks(world, lambda r, mlsl: run_program(r, mlsl, world, D, M, program, dev), backend=backend, env=env)
+    for r in range(world):
+        check_rank(r, world, D, M, program, outs[r])
+
+
+def check_rank(r, world, D, M, program, results):
+    """compare what rank r got with the closed-form expectation (depends on the deterministic inputs only)"""
     def red(ts, how, dt):
         acc = ts[0].double() if dt != torch.uint8 else ts[0].to(torch.int64)
         for t in ts[1:]:
@@ -136,11 +147,11 @@ def run_fuzz(world, seed, backend):
     for k, st in enumerate(program):
         dt, n, op = st["dtype"], st["n"], st["op"]
         tol = {torch.float32: 1e-5, torch.float64: 1e-12}.get(dt, 0)
-        for r in range(world):
+        if True:
             mem = _members(world, D, M, r, st["group"])
             P, idx = len(mem), mem.index(r)
             root = st["root"] % P
-            got = outs[r][k]
+            got = results[k]
 
             def same(a, b):
                 assert a is not None and a.shape == b.shape, (op, k, r)

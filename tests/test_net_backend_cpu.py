@@ -1,0 +1,57 @@
+"""The net backend (TCP control plane + TCP data mesh) on one machine playing several nodes: every "node" is its own
+mlslrun with --nnodes / --node-rank, exactly how a real multi-node job is started."""
+import os
+import random
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+MLSLRUN = os.path.join(ROOT, "bin", "mlslrun")
+
+
+def _launch(nnodes, per_node, cmd, extra_env=None, timeout=240):
+    port = str(random.Random().randrange(20000, 50000))
+    env = dict(os.environ, MLSL_WATCHDOG_SEC="60")
+    env.pop("MLSL_BACKEND", None)
+    env.update(extra_env or {})
+    procs = [subprocess.Popen([MLSLRUN, "-n", str(per_node), "--nnodes", str(nnodes), "--node-rank", str(i), "--master-addr",
+                               "127.0.0.1", "--master-port", port, "--timeout", str(timeout - 20)] + cmd,
+                              cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for i in range(nnodes)]
+    outs = [p.communicate(timeout=timeout)[0] for p in procs]
+    return [p.returncode for p in procs], "\n".join(outs)
+
+
+@pytest.mark.parametrize("nnodes,per_node,args", [(2, 2, ["2", "1"]), (2, 2, ["1"]), (4, 1, ["4", "0", "1"]), (2, 2, ["2", "1", "0", "1"]), (2, 4, ["4", "1"])])
+def test_cpp_functional_test_across_nodes(nnodes, per_node, args):
+    rcs, out = _launch(nnodes, per_node, [os.path.join(ROOT, "bin", "mlsl_functional_test")] + args)
+    assert all(rc == 0 for rc in rcs), out[-3000:]
+    assert out.count("0 FAILED") == nnodes * per_node and ": FAILED" not in out
+
+
+@pytest.mark.parametrize("nnodes,per_node,seed", [(2, 2, 3), (3, 2, 4), (2, 1, 7)])
+def test_random_collectives_and_fused_update_across_nodes(nnodes, per_node, seed):
+    rcs, out = _launch(nnodes, per_node, [sys.executable, os.path.join(ROOT, "tests", "net_worker.py"), str(seed)])
+    assert all(rc == 0 for rc in rcs), out[-3000:]
+    assert out.count("NET OK") == nnodes * per_node
+
+
+def test_a_dying_rank_fails_the_whole_multi_node_job_fast():
+    """One rank exits without finalizing: its control connection drops, rank 0's server poisons everyone, the surviving
+    ranks leave their collective with an error instead of waiting for the watchdog."""
+    code = ("import sys, os, time; sys.path.insert(0, %r); import torch, mlsl_b200 as mlsl; mlsl.init(); t = torch.ones(4); "
+            "mlsl.allreduce(t); r = mlsl.rank();\n"
+            "if r == 3: os._exit(7)\n"
+            "t0 = time.time()\n"
+            "try:\n"
+            "    mlsl.allreduce(t); print('survived')\n"
+            "except Exception as e:\n"
+            "    print('FAILFAST %%.1f %%s' %% (time.time() - t0, 'poisoned' in str(e) or 'closed' in str(e) or 'broke' in str(e)))\n") % ROOT
+    rcs, out = _launch(2, 2, [sys.executable, "-c", code], timeout=120)
+    import re
+    hits = re.findall(r"FAILFAST ([0-9.]+) (True|False)", out)       # ranks share a pipe: lines may run together
+    assert hits and "survived" not in out, out[-2000:]
+    assert all(float(t) < 30 and ok == "True" for t, ok in hits), hits
