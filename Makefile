@@ -81,11 +81,14 @@ sass: $(LIB)
 	cuobjdump -sass $(LIB) > profiles/sass/libmlsl_b200.sass
 
 # ThreadSanitizer run of the host runtime (ring, progress threads, shm protocol): 4 in-process ranks, hybrid 2x2
-tsan:
+tsan: bin/mlslrun
 	$(MAKE) CXX=/usr/bin/g++ TSAN=1 BUILD=/tmp/mlsl_tsan/build LIBDIR=/tmp/mlsl_tsan/lib LIB=/tmp/mlsl_tsan/lib/libmlsl_b200.so /tmp/mlsl_tsan/lib/libmlsl_b200.so
 	/usr/bin/g++ -O1 -g -std=c++17 -fsanitize=thread -pthread -Iinclude -Icsrc csrc/tests/mlsl_functional_test.cpp -o /tmp/mlsl_tsan/ftest -L/tmp/mlsl_tsan/lib -lmlsl_b200 -Wl,-rpath,/tmp/mlsl_tsan/lib
 	cd /tmp/mlsl_tsan && TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" ./ftest 2 1 0 1 --inproc 4 | tail -1
 	cd /tmp/mlsl_tsan && MLSL_NUM_SERVERS=2 MLSL_MSG_PRIORITY=1 TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" ./ftest 1 0 1 0 --inproc 4 | tail -1
+	# net backend (control server, receiver thread, TCP mesh): two launchers playing two nodes
+	cd /tmp/mlsl_tsan && (TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" $(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 1 --master-addr 127.0.0.1 --master-port 29877 ./ftest 2 1 > node1.out 2>&1 &) ; \
+	  TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" $(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 0 --master-addr 127.0.0.1 --master-port 29877 ./ftest 2 1 | grep -c "0 FAILED"
 
 # make install PREFIX=/opt/mlsl_b200: the layout of the reference's package (intel64/{bin,lib,include}, doc, examples,
 # the environment script), plus the Python package

@@ -100,7 +100,8 @@ static inline void reduce_by_op(T* dst, const void* const* srcs, size_t nsrc, si
 }
 
 // one entry point per element type, cloned for the vector ISAs of the machine it runs on (resolved at load time)
-#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+// (not under ThreadSanitizer: ifunc resolvers run before its runtime is up)
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__) && !defined(__SANITIZE_THREAD__)
 #define MLSLB_SIMD_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
 #else
 #define MLSLB_SIMD_CLONES
