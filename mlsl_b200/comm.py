@@ -247,6 +247,9 @@ def _sync_stream():
 def _prep(t):
     if not t.is_contiguous():
         raise ValueError("mlsl_b200 collectives need contiguous tensors")
+    if t.is_cuda and not is_device():
+        raise TypeError("a CUDA tensor was passed but the %s backend works on host memory: initialise with "
+                        "MLSL_BACKEND=cuda, or move the tensor to the CPU" % env().get_backend_name())
     return t
 
 
