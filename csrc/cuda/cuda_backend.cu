@@ -158,7 +158,10 @@ class CudaBackend final : public Backend {
     auto* st = (CudaReqState*)r.backend_state;
     set_device();
     cudaError_t e = st->recorded ? cudaEventQuery(st->done) : cudaStreamQuery(st->stream);
-    if (e == cudaErrorNotReady) return false;
+    if (e == cudaErrorNotReady) {
+      cudaGetLastError();   // not an error, but it would be picked up by the next launch check
+      return false;
+    }
     MLSLB_CUDA(e);
     finish(r, st);
     return true;
@@ -350,7 +353,9 @@ class CudaBackend final : public Backend {
         // entries come in groups [event, null, null...]; a group is released as a whole
         size_t j = i + 1;
         while (j < parked_.size() && parked_[j].ev == nullptr) ++j;
-        if (all || cudaEventQuery(parked_[i].ev) == cudaSuccess) {
+        cudaError_t qe = all ? cudaSuccess : cudaEventQuery(parked_[i].ev);
+        if (qe == cudaErrorNotReady) cudaGetLastError();   // "not ready" is recorded as the thread's last error: clear it
+        if (qe == cudaSuccess) {
           event_pool_.push_back(parked_[i].ev);
           for (size_t k = i; k < j; ++k) to_free.push_back(parked_[k].slab);
           parked_.erase(parked_.begin() + i, parked_.begin() + j);
