@@ -125,6 +125,8 @@ ActivationImpl::ActivationImpl(OperationImpl* o, size_t fmCount, size_t fmSz, Da
     globalFmOffset = 0;
     needReduce = M > 1;
   } else {
+    // the reference divides silently (src/mlsl_impl.cpp:49) and then exchanges the wrong elements; say so instead
+    MLSLB_ASSERT(globalFmCount % M == 0, "%zu feature maps cannot be split over a model group of %zu ranks", globalFmCount, M);
     localFmCount = globalFmCount / M;
     globalFmOffset = localFmCount * (size_t)dist->modelGroup->idx;
     needReduce = false;
@@ -310,6 +312,7 @@ ParameterSetImpl::ParameterSetImpl(OperationImpl* o, size_t kCount, size_t kSize
   RankContext* ctx = o->session->ctx;
   const size_t M = (size_t)dist->modelGroup->size();
   const size_t D = (size_t)dist->dataGroup->size();
+  MLSLB_ASSERT(globalKernelCount % M == 0, "%zu kernels cannot be split over a model group of %zu ranks", globalKernelCount, M);
   localKernelCount = globalKernelCount / M;
   globalKernelOffset = localKernelCount * (size_t)dist->modelGroup->idx;
   needComm = D > 1;
