@@ -32,7 +32,7 @@ def main():
     args = ap.parse_args()
     if args.lr is None:
         args.lr = 1e-3 if args.optimizer == "adamw" else 0.05
-    use_cuda = torch.cuda.is_available() and os.environ.get("MLSL_BACKEND", "cuda") != "host"
+    use_cuda = torch.cuda.is_available() and os.environ.get("MLSL_BACKEND", "cuda") == "cuda"
     if use_cuda:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     mlsl.init()

@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--width", type=int, default=128)
     ap.add_argument("--hidden", type=int, default=512)
     args = ap.parse_args()
-    use_cuda = torch.cuda.is_available() and os.environ.get("MLSL_BACKEND", "cuda") != "host"
+    use_cuda = torch.cuda.is_available() and os.environ.get("MLSL_BACKEND", "cuda") == "cuda"
     if use_cuda:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     env = mlsl.init()
