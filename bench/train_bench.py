@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 
 
 def build(model, batch, seq):
-    from mlsl_b200.models import MLP, bert_large, resnet50
+    from mlsl_b200.models import MLP, resnet50
     from mlsl_b200.models.bert import BertConfig, BertEncoderModel
     if model == "resnet50":
         m = resnet50().cuda().to(memory_format=torch.channels_last)

@@ -18,7 +18,7 @@ StartIncrementComm / WaitIncrementComm) packaged for PyTorch:
 import torch
 
 from . import comm
-from .api import CompressionType, DataType, OperationType, OptimizerType
+from .api import CompressionType, OperationType, OptimizerType
 
 
 class _Bucket:

@@ -12,7 +12,6 @@ pushes the partial tiles to their owner over NVLink); everywhere else it is matm
 import torch
 
 from .. import comm
-from ..api import GroupType
 
 
 def _group_info(distribution, group):
