@@ -199,6 +199,7 @@ void* CommRequest::wait() {
   spin_until_launched(this);
   ctx->backend->wait(*this);
   done_ns = now_ns();
+  if (!ctx->trace_prefix.empty()) ctx->trace_request(*this);
   state.store(IDLE, std::memory_order_release);
   return recv;
 }
@@ -215,6 +216,7 @@ void* CommRequest::test(bool* done) {
   }
   if (ctx->backend->test(*this)) {
     done_ns = now_ns();
+    if (!ctx->trace_prefix.empty()) ctx->trace_request(*this);
     state.store(IDLE, std::memory_order_release);
     *done = true;
     return recv;
@@ -468,6 +470,38 @@ void RankContext::free_group(ProcessGroup* g) {
   delete g;
 }
 
+void RankContext::trace_request(const CommRequest& r) {
+  TraceEvent e{r.start_ns, r.done_ns, (int)r.desc.kind, r.desc.group ? r.desc.group->row : -1, r.lane, r.msg_bytes()};
+  std::lock_guard<std::mutex> g(trace_mu);
+  if (trace.size() < (size_t)1 << 20) trace.push_back(e);   // bounded: ~32 MB per rank
+}
+
+void RankContext::trace_dump() {
+  if (trace_prefix.empty()) return;
+  std::vector<TraceEvent> ev;
+  {
+    std::lock_guard<std::mutex> g(trace_mu);
+    ev.swap(trace);
+  }
+  const std::string path = trace_prefix + "." + std::to_string(rank) + ".json";
+  FILE* f = fopen(path.c_str(), "w");
+  if (!f) {
+    MLSLB_LOG(LOG_ERROR, "cannot write trace file %s", path.c_str());
+    return;
+  }
+  // Chrome trace event format ("X" = complete event, microseconds); one process per rank, one thread per (row, lane)
+  fprintf(f, "{\"traceEvents\":[\n");
+  fprintf(f, "{\"ph\":\"M\",\"pid\":%d,\"name\":\"process_name\",\"args\":{\"name\":\"mlsl rank %d (%s)\"}}", rank, rank,
+          backend ? backend->name() : "finalized");
+  for (const TraceEvent& e : ev)
+    fprintf(f, ",\n{\"ph\":\"X\",\"pid\":%d,\"tid\":%d,\"ts\":%.3f,\"dur\":%.3f,\"name\":\"%s\",\"args\":{\"bytes\":%zu,\"row\":%d,\"lane\":%d}}",
+            rank, (e.row < 0 ? 0 : e.row) * 2 + e.lane, e.t0 / 1000.0, (e.t1 > e.t0 ? e.t1 - e.t0 : 0) / 1000.0,
+            opkind_name((OpKind)e.kind), e.bytes, e.row, e.lane);
+  fprintf(f, "\n]}\n");
+  fclose(f);
+  MLSLB_LOG(LOG_INFO, "wrote %zu trace events to %s", ev.size(), path.c_str());
+}
+
 void RankContext::register_request(CommRequest* r) {
   std::lock_guard<std::mutex> g(req_mu);
   inflight.insert(r);
@@ -558,6 +592,7 @@ void context_init(RankContext* ctx) {
   ctx->env = parse_env();
   set_log_level(ctx->env.log_level);
   ctx->init_pid = (int)getpid();
+  if (const char* t = getenv("MLSL_TRACE_FILE")) ctx->trace_prefix = t;
   if (auto b = take_thread_bootstrap()) {
     ctx->boot = std::move(b);
   } else {
@@ -649,6 +684,7 @@ void context_finalize(RankContext* ctx) {
     }
   };
   if (!ctx->boot->inproc()) remove_signal_handlers();
+  step([&] { ctx->trace_dump(); });
   step([&] { io_shutdown(ctx); });
   step([&] { if (ctx->progress) ctx->progress->drain(); });
   step([&] { ctx->boot->barrier(); });

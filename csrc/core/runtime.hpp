@@ -275,6 +275,18 @@ struct RankContext {
   int init_pid = 0;
   bool initialized = false;
   void* io_service = nullptr;              // file-IO offload thread (fileio.cpp), created on first use
+  // MLSL_TRACE_FILE=<prefix>: every completed request becomes one slice of a Chrome / Perfetto trace
+  // (<prefix>.<rank>.json, written at Finalize): start = Start() on the API thread, end = Wait/Test saw it complete
+  struct TraceEvent {
+    uint64_t t0, t1;
+    int kind, row, lane;
+    size_t bytes;
+  };
+  std::string trace_prefix;
+  std::mutex trace_mu;
+  std::vector<TraceEvent> trace;
+  void trace_request(const CommRequest& r);
+  void trace_dump();
   void* api_env = nullptr;                 // MLSL::impl::EnvironmentImpl bound to this context
   void (*api_env_free)(void*) = nullptr;   // its deleter (the type lives in graph.cpp)
   ~RankContext() {

@@ -484,3 +484,27 @@ def test_c_functional_test_multiprocess(args):
     res = subprocess.run([_bin("mlslrun"), "-n", "4", "--timeout", "90", _bin("cmlsl_functional_test"), *args],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=150)
     assert res.returncode == 0 and ": FAILED" not in res.stdout and res.stdout.count("0 FAILED") == 4, res.stdout[-2000:]
+
+
+def test_trace_file_is_valid_chrome_trace(tmp_path):
+    """MLSL_TRACE_FILE=<prefix>: every completed request is one slice of <prefix>.<rank>.json (Chrome trace format)."""
+    import json
+    prefix = str(tmp_path / "trace")
+
+    def body(r, mlsl):
+        import torch
+        for n in (8, 1000):
+            mlsl.allreduce(torch.ones(n))
+        mlsl.allgather(torch.ones(16))
+        mlsl.barrier()
+        return True
+
+    from conftest import run_ranks as rr
+    assert rr(2, body, env={"MLSL_TRACE_FILE": prefix}) == [True, True]
+    for rank in range(2):
+        doc = json.load(open("%s.%d.json" % (prefix, rank)))
+        ev = [e for e in doc["traceEvents"] if e["ph"] == "X"]
+        names = [e["name"] for e in ev]
+        assert names.count("AllReduce") == 2 and "AllGather" in names and "Barrier" in names
+        assert all(e["dur"] >= 0 and e["pid"] == rank for e in ev)
+        assert sorted(e["args"]["bytes"] for e in ev if e["name"] == "AllReduce") == [32, 4000]
