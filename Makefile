@@ -105,6 +105,10 @@ install: all
 	cp scripts/mlslvars.sh $(PREFIX)/intel64/bin/mlslvars.sh
 	@echo "installed into $(PREFIX); source $(PREFIX)/intel64/bin/mlslvars.sh"
 
+# the reference's `make testing`: the functional matrix on 4 local ranks (C++, C, Python, quantisation, net backend)
+testing: all
+	bash scripts/run_matrix.sh
+
 # AddressSanitizer + UBSan run of the host runtime: in-process and multi-process functional test, user plug-in path
 asan: bin/mlslrun bin/libmlsl_quant_sample.so
 	$(MAKE) CXX=/usr/bin/g++ NO_CUDA=1 BUILD=/tmp/mlsl_asan/build LIBDIR=/tmp/mlsl_asan/lib LIB=/tmp/mlsl_asan/lib/libmlsl_b200.so \
@@ -118,4 +122,4 @@ asan: bin/mlslrun bin/libmlsl_quant_sample.so
 clean:
 	rm -rf $(BUILD) $(LIB) bin _install
 
-.PHONY: all clean sass tsan asan install
+.PHONY: all clean sass tsan asan install testing
