@@ -227,6 +227,10 @@ def main():
 
     def body(r):
         mlsl.bind_thread_state()
+        if torch.cuda.is_available() and os.environ.get("MLSL_BACKEND") == "cuda":
+            # loop-back ranks share the GPU: each needs its own stream (kernels of different ranks wait for each other)
+            torch.cuda.set_device(0)
+            torch.cuda.set_stream(torch.cuda.Stream())
         return Net(*cfg).run()
 
     with mlsl.InprocWorld(inproc) as world:
