@@ -58,6 +58,9 @@ def main():
 
         def body(r):
             mlsl.bind_thread_state()
+            if torch.cuda.is_available() and os.environ.get("MLSL_BACKEND") == "cuda":
+                torch.cuda.set_device(0)                    # loop-back ranks share the GPU: one stream per rank
+                torch.cuda.set_stream(torch.cuda.Stream())
             return run()
 
         with mlsl.InprocWorld(n) as world:
