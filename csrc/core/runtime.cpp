@@ -599,6 +599,13 @@ void context_init(RankContext* ctx) {
     int world = ctx->env.world > 0 ? ctx->env.world : 1;
     int rank = ctx->env.rank >= 0 ? ctx->env.rank : 0;
     const bool net = ctx->env.backend == "net" || ctx->env.backend == "tcp";
+    // torchrun tells how many ranks share this node: a job that spans nodes cannot meet in /dev/shm
+    if (const char* lws = getenv("LOCAL_WORLD_SIZE")) {
+      const int local_world = atoi(lws);
+      MLSLB_ASSERT(net || local_world <= 0 || local_world >= world,
+                   "this job spans nodes (%d of %d ranks are local): the %s backend covers one node - use MLSL_BACKEND=net "
+                   "(TCP, host memory) across nodes", local_world, world, ctx->env.backend == "cuda" ? "cuda" : "host");
+    }
     if (world == 1) {
       auto v = Bootstrap::create_inproc(1);
       ctx->boot = std::move(v[0]);
