@@ -60,3 +60,29 @@ def test_python_classes_and_methods():
         missing = sorted(m for m in methods if m not in mine[cls] and not (m.startswith("get_") and m[4:] in generated)
                          and not (m.startswith("is_") and m[3:] in generated))
         assert not missing, (cls, missing)
+
+
+def test_enum_values():
+    def enums(path):
+        s = open(path, errors="ignore").read()
+        s = re.sub(r"/\*.*?\*/", "", s, flags=re.S)
+        s = re.sub(r"//[^\n]*", "", s)
+        out = {}
+        for m in re.finditer(r"enum\s+(\w+)\s*\{(.*?)\}", s, flags=re.S):
+            vals, nxt = {}, 0
+            for item in (i.strip() for i in m.group(2).split(",")):
+                if not item:
+                    continue
+                if "=" in item:
+                    item, v = (x.strip() for x in item.split("="))
+                    nxt = int(v, 0)
+                vals[item] = nxt
+                nxt += 1
+            out[m.group(1)] = vals
+        return out
+
+    ref, mine = enums(os.path.join(REF, "include", "mlsl.hpp")), enums(os.path.join(ROOT, "include", "mlsl.hpp"))
+    assert len(ref) >= 6
+    for name, vals in ref.items():
+        for k, v in vals.items():
+            assert mine.get(name, {}).get(k) == v, (name, k, v, mine.get(name, {}).get(k))
