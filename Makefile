@@ -96,6 +96,7 @@ PREFIX ?= $(CURDIR)/_install
 install: all
 	@mkdir -p $(PREFIX)/intel64/bin $(PREFIX)/intel64/lib $(PREFIX)/intel64/include/mlsl $(PREFIX)/doc $(PREFIX)/examples $(PREFIX)/python
 	cp $(LIB) $(PREFIX)/intel64/lib/
+	ln -sf libmlsl_b200.so $(PREFIX)/intel64/lib/libmlsl.so   # drop-in name: -lmlsl and the reference's Python binding find it
 	cp bin/mlslrun bin/libmlsl_quant_sample.so $(PREFIX)/intel64/bin/
 	cp include/mlsl.hpp include/mlsl.h $(PREFIX)/intel64/include/
 	cp -r mlsl_b200 $(PREFIX)/python/ && rm -rf $(PREFIX)/python/mlsl_b200/__pycache__ $(PREFIX)/python/mlsl_b200/*/__pycache__

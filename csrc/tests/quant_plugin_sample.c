@@ -92,3 +92,13 @@ int sample_reduce_sum(const void* in, void* inout, size_t block_count) {
   }
   return 0;
 }
+
+/* The same three entry points under the names the reference's own functional test asks for (it was written against
+ * Intel's dl_comp library, tests/examples/mlsl_test/mlsl_test.cpp:590-592), so that test can run with this plug-in. */
+int dl_comp_compress_buffer(void* src, void* dst, size_t count, void* diff, int src_dtype, size_t comp_ratio, int method) {
+  return sample_compress(src, dst, count, diff, src_dtype, comp_ratio, method);
+}
+int dl_comp_decompress_buffer(void* src, void* dst, size_t count) { return sample_decompress(src, dst, count); }
+int dl_comp_compressed_buffer_reduce_sum(const void* in, void* inout, size_t block_count) {
+  return sample_reduce_sum(in, inout, block_count);
+}

@@ -14,6 +14,17 @@
 extern "C" {
 #endif
 
+/* API version of this header; mlsl_environment_get_version() returns the library's (same encoding) */
+#define CMLSL_MAJOR_VERSION 1
+#define CMLSL_MINOR_VERSION 0
+#define CMLSL_VERSION(major, minor) (((major) << 16) | (minor))
+#define CMLSL_MAJOR(version) ((version) >> 16)
+#define CMLSL_MINOR(version) ((version)&0xFFFF)
+#define CMLSL_VERSION_GE(v1, v2) \
+  ((CMLSL_MAJOR(v1) > CMLSL_MAJOR(v2)) || (CMLSL_MAJOR(v1) == CMLSL_MAJOR(v2) && CMLSL_MINOR(v1) >= CMLSL_MINOR(v2)))
+#define CMLSL_VERSION_LT(v1, v2) \
+  ((CMLSL_MAJOR(v1) < CMLSL_MAJOR(v2)) || (CMLSL_MAJOR(v1) == CMLSL_MAJOR(v2) && CMLSL_MINOR(v1) < CMLSL_MINOR(v2)))
+
 #define CMLSL_SUCCESS 0
 #define CMLSL_FAILURE -1
 
