@@ -234,6 +234,14 @@ def run_ours(args):
         except Exception as ex:  # noqa: BLE001 - the device-timed headline must still be reported
             e2e = {"error": repr(ex)[:300]}
 
+    # kernels per timed step: giant messages on the multicast (NVLS) path are issued as several launches
+    # (csrc/cuda/cuda_backend.cu: >= 1.5 x MLSL_NVLS_CHUNK_MB on a group that spans the multicast object)
+    launches_per_step = 1
+    chunk = int(os.environ.get("MLSL_NVLS_CHUNK_MB", "256")) << 20
+    nvls = ("NVLS" in mlsl.env().describe_backend() and world >= int(os.environ.get("MLSL_NVLS_MIN_RANKS", "4"))
+            and os.environ.get("MLSL_NVLS", "1") != "0" and not args.compress)
+    if nvls and chunk and S >= chunk + chunk // 2:
+        launches_per_step = -(-S // chunk)
     out = {
         "metric": "allreduce_busbw_GBps" if world > 1 else "allreduce_algbw_GBps_single_gpu",
         "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -245,7 +253,7 @@ def run_ours(args):
                    "api": "mlsl_b200.allreduce -> Distribution::AllReduceEx -> Environment::Wait",
                    "backend": env.get_backend_name(), "backend_detail": env.describe_backend(), "stream_mode": os.environ.get("MLSL_STREAM_MODE"),
                    "correct": ok},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * launches_per_step,
         "sweep": sweep, "nccl": nccl,
     }
     mlsl.free_tensor(x)
