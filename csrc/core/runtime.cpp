@@ -279,7 +279,9 @@ void ProgressEngine::submit(CommRequest* r) {
     return;
   }
   int row = r->desc.group ? std::max(r->desc.group->row, 0) : 0;
-  Server* s = servers_[(size_t)(row * 2 + r->lane) % servers_.size()].get();
+  // rows spread over the servers first (different groups progress independently), the priority lane of a row goes to
+  // the neighbouring server
+  Server* s = servers_[(size_t)(row + r->lane) % servers_.size()].get();
   Command c;
   c.kind = Command::EXEC;
   c.req = r;

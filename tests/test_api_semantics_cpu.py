@@ -508,3 +508,22 @@ def test_trace_file_is_valid_chrome_trace(tmp_path):
         assert names.count("AllReduce") == 2 and "AllGather" in names and "Barrier" in names
         assert all(e["dur"] >= 0 and e["pid"] == rank for e in ev)
         assert sorted(e["args"]["bytes"] for e in ev if e["name"] == "AllReduce") == [32, 4000]
+
+
+def test_out_of_order_starts_on_different_groups_need_servers():
+    """Ranks that start collectives of two groups in opposite orders: fine with one progress server per group in flight
+    (rows are spread over the servers), a dead-lock the watchdog reports when collectives run inside Start()."""
+    import torch
+
+    def body(r, mlsl):
+        a, b = torch.ones(1000), torch.ones(1000) * 2
+        first, second = (("global", a), ("data", b)) if r == 0 else (("data", b), ("global", a))
+        w1 = mlsl.allreduce(first[1], group=first[0], async_op=True)
+        w2 = mlsl.allreduce(second[1], group=second[0], async_op=True)
+        w1.wait()
+        w2.wait()
+        return float(a[0]), float(b[0])
+
+    assert run_ranks(2, body, env={"MLSL_NUM_SERVERS": "2"}) == [(2.0, 4.0), (2.0, 4.0)]
+    with pytest.raises(Exception, match="watchdog|poisoned"):
+        run_ranks(2, body, env={"MLSL_NUM_SERVERS": "0", "MLSL_WATCHDOG_SEC": "3"})
