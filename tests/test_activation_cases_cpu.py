@@ -108,3 +108,54 @@ def run_case(case, ptype, pdist, cdist, backend):
         assert fwd_ok, (case, r, "forward")
         assert bwd_ok, (case, r, "backward")
         assert npack >= 1 and nunpack >= 1
+
+
+def test_operation_with_two_outputs_feeding_two_consumers():
+    """A small DAG: op0 has two outputs, wired with SetPrev (to op1) and SetNext (to op2); both edges are model-parallel
+    exchanges (case 1) that run concurrently; inputs / outputs that are not wired stay communication-free."""
+    def body(r, mlsl):
+        from mlsl_test import Net
+        from mlsl_b200.api import DataType, OperationType
+        e = mlsl.env()
+        dist = e.create_distribution(2, 2)
+        sess = e.create_session()
+        sess.set_global_minibatch_size(GMB)
+
+        def reg(n_out):
+            ri = sess.create_operation_reg_info(OperationType.CC)
+            ri.add_input(FM, FS, DataType.FLOAT)
+            for _ in range(n_out):
+                ri.add_output(FM, FS, DataType.FLOAT)
+            ri.add_parameter_set(FM * FM, 1, DataType.FLOAT)
+            return ri
+
+        op0 = sess.get_operation(sess.add_operation(reg(2), dist))
+        op1 = sess.get_operation(sess.add_operation(reg(1), dist))
+        op2 = sess.get_operation(sess.add_operation(reg(1), dist))
+        op1.set_prev(op0, 0, 0)          # op0.out0 -> op1.in0
+        op0.set_next(op2, 1, 0)          # op0.out1 -> op2.in0
+        sess.commit()
+        view = lambda addr, nbytes: mlsl.tensor_from_address(addr, (nbytes // 4,), torch.float32)     # noqa: E731
+        mb, off = op0.get_local_minibatch_size(), op0.get_global_minibatch_offset()
+        oks = []
+        outs = [op0.get_output(0), op0.get_output(1)]
+        for k, oa in enumerate(outs):    # start both transfers before waiting for either
+            out = (k + 1) * _f(off, mb, 0, FM)
+            comm = view(oa.get_comm_buf(), oa.get_comm_buf_size())
+            Net.move_blocks(oa, comm, out, False)
+            oa.start_comm(comm)
+        for k, cons in enumerate((op1, op2)):
+            ia = cons.get_input(0)
+            got = ia.wait_comm()
+            inp = torch.zeros(mb * ia.get_local_fm_count() * FS)
+            Net.move_blocks(ia, view(got, mb * ia.get_local_fm_count() * FS * 4), inp, True)
+            want = 2 * (k + 1) * _f(off, mb, ia.get_global_fm_offset(), ia.get_local_fm_count())   # 2 partial sums
+            oks.append(torch.equal(inp, want))
+        unwired = (op0.get_input(0).get_comm_buf_size(), op1.get_output(0).get_comm_buf_size(), op0.get_input(0).wait_comm())
+        e.delete_session(sess)
+        e.delete_distribution(dist)
+        return oks, unwired
+
+    for oks, unwired in run_ranks(WORLD, body):
+        assert oks == [True, True]
+        assert unwired == (0, 0, None)
