@@ -284,6 +284,14 @@ int mlsl_environment_delete_session(mlsl_environment e, mlsl_session s) { C_GUAR
 int mlsl_environment_create_distribution(mlsl_environment e, size_t dp, size_t mp, mlsl_distribution* d) {
   C_GUARD(*need(d) = U(H<Environment>(e)->CreateDistribution(dp, mp)))
 }
+int mlsl_environment_get_group_state(mlsl_environment e, unsigned long long* rows, unsigned long long* mark) {
+  C_GUARD(H<Environment>(e)->GetGroupState(need(rows), need(mark)))
+}
+int mlsl_environment_create_distribution_from_ranks(mlsl_environment e, const size_t* ranks, size_t count,
+                                                    unsigned long long rows, unsigned long long mark,
+                                                    mlsl_distribution* d) {
+  C_GUARD(*need(d) = U(H<Environment>(e)->CreateDistributionFromRanks(ranks, count, rows, mark)))
+}
 int mlsl_environment_create_distribution_with_colors(mlsl_environment e, int dc, int mc, mlsl_distribution* d) {
   C_GUARD(*need(d) = U(H<Environment>(e)->CreateDistributionWithColors(dc, mc)))
 }

@@ -73,6 +73,10 @@ DistributionImpl::DistributionImpl(RankContext* c, size_t dParts, size_t mParts,
   }
 }
 
+DistributionImpl::DistributionImpl(RankContext* c, ProcessGroup* data)
+    : ctx(c), dataParts((size_t)data->size()), modelParts(1), replicaCount(1), dataGroup(data),
+      modelGroup(c->self_group), replicaGroup(c->self_group) {}
+
 DistributionImpl::~DistributionImpl() {
   auto drop = [&](ProcessGroup* g) {
     if (!(g && g != ctx->global_group && g != ctx->self_group && g != ctx->world_group)) return;
@@ -1021,6 +1025,24 @@ Distribution* Environment::CreateDistribution(size_t dataPartitions, size_t mode
 Distribution* Environment::CreateDistributionWithColors(int dataColor, int modelColor) {
   MLSLB_ASSERT(dataColor >= 0 && modelColor >= 0, "colors must be non-negative");
   return new DistributionImpl(live(this), 0, 0, false, dataColor, modelColor);
+}
+void Environment::GetGroupState(unsigned long long* rowsInUse, unsigned long long* ticketMark) {
+  mlslb::RankContext* c = live(this);
+  MLSLB_ASSERT(rowsInUse != nullptr && ticketMark != nullptr, "output pointers are NULL");
+  *rowsInUse = c->row_used;
+  *ticketMark = std::max(c->seq_hwm, c->global_group->hwm());
+}
+Distribution* Environment::CreateDistributionFromRanks(const size_t* ranks, size_t count, unsigned long long rowsInUse,
+                                                       unsigned long long ticketMark) {
+  mlslb::RankContext* c = live(this);
+  MLSLB_ASSERT(ranks != nullptr && count > 0, "the rank list is empty");
+  std::vector<int> members(count);
+  for (size_t i = 0; i < count; ++i) {
+    MLSLB_ASSERT(ranks[i] < (size_t)c->global_group->size(), "rank %zu is outside the global group (%d processes)",
+                 ranks[i], c->global_group->size());
+    members[i] = c->global_group->members[ranks[i]];
+  }
+  return new DistributionImpl(c, c->create_group_from_members(members, rowsInUse, ticketMark));
 }
 void Environment::DeleteDistribution(Distribution* distribution) { delete static_cast<DistributionImpl*>(distribution); }
 void Environment::Wait(CommReq* req) {

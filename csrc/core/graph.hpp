@@ -131,6 +131,7 @@ class DistributionImpl : public Distribution {
  public:
   DistributionImpl(RankContext* ctx, size_t dataParts, size_t modelParts, bool replicate, int dataColor,
                    int modelColor);
+  DistributionImpl(RankContext* ctx, ProcessGroup* data);   // `data` as the data group, no model parallelism
   ~DistributionImpl();
   ProcessGroup* group(GroupType gt);
   CommRequest* make_request(mlslb::OpKind kind, DataType dt, GroupType gt);

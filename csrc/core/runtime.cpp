@@ -423,30 +423,46 @@ ProcessGroup* RankContext::create_group_by_color(ProcessGroup* parent, int color
   } else {
     all[0] = mine;
   }
-  ProcessGroup* g = new ProcessGroup();
-  g->ctx = this;
+  std::vector<int> members;
   uint64_t used = 0, base = 0;
   for (int i = 0; i < parent->size(); ++i)
     if (all[i].color == color) {
-      if (parent->members[i] == rank) g->idx = (int)g->members.size();
-      g->members.push_back(parent->members[i]);
+      members.push_back(parent->members[i]);
       used |= all[i].row_used;
       base = std::max(base, all[i].hwm);
     }
-  MLSLB_ASSERT(!g->members.empty(), "rank not part of its own colour group");
+  return create_group_from_members(members, used, base);
+}
+
+ProcessGroup* RankContext::create_group_from_members(const std::vector<int>& members, uint64_t used, uint64_t base) {
+  ProcessGroup* g = new ProcessGroup();
+  g->ctx = this;
+  g->members = members;
+  g->idx = -1;
+  for (size_t i = 0; i < members.size(); ++i) {
+    for (size_t j = 0; j < i; ++j) MLSLB_ASSERT(members[j] != members[i], "rank %d is listed twice in a group", members[i]);
+    if (members[i] == rank) g->idx = (int)i;
+  }
+  if (g->idx < 0) {
+    delete g;
+    MLSLB_ASSERT(false, "rank %d is not a member of the group it is creating", rank);
+  }
   g->is_self = g->members.size() == 1;
   if (g->is_self) {
     g->row = -1;
   } else {
+    used |= row_used;
     int row = -1;
     for (int r = 1; r < kMaxGroupRows - 1; ++r)   // the last row is reserved for single-rank (self) groups
       if (!(used & (1ull << r))) {
         row = r;
         break;
       }
+    if (row < 0) delete g;
     MLSLB_ASSERT(row > 0, "out of process-group rows (max %d live groups)", kMaxGroupRows);
     g->row = row;
     row_used |= 1ull << row;
+    base = std::max(base, seq_hwm);
     g->seq[0] = g->seq[1] = g->ctl_seq = base;
     seq_hwm = std::max(seq_hwm, base);
   }

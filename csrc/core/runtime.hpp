@@ -294,6 +294,8 @@ struct RankContext {
   }
 
   ProcessGroup* create_group_by_color(ProcessGroup* parent, int color);   // collective over parent
+  // members only: `used` = OR of the members' row bitmaps, `base` = max of their ticket marks (exchanged by the caller)
+  ProcessGroup* create_group_from_members(const std::vector<int>& members, uint64_t used, uint64_t base);
   void free_group(ProcessGroup* g);
   void group_barrier(ProcessGroup* g);      // host control-plane barrier among the members
   void register_request(CommRequest* r);

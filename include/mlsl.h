@@ -231,6 +231,12 @@ int mlsl_environment_describe_backend(mlsl_environment env, const char** text);
 int mlsl_environment_is_device_backend(mlsl_environment env, int* is_device);
 int mlsl_environment_suspend_servers(mlsl_environment env);
 int mlsl_environment_resume_servers(mlsl_environment env);
+/* members-only group creation over a caller-provided rendezvous (see Environment::CreateDistributionFromRanks) */
+int mlsl_environment_get_group_state(mlsl_environment env, unsigned long long* rows_in_use,
+                                     unsigned long long* ticket_mark);
+int mlsl_environment_create_distribution_from_ranks(mlsl_environment env, const size_t* ranks, size_t count,
+                                                    unsigned long long rows_in_use, unsigned long long ticket_mark,
+                                                    mlsl_distribution* dist);
 int mlsl_distribution_all_reduce_ex(mlsl_distribution dist, void* send_buffer, void* recv_buffer, size_t count,
                                     mlsl_data_type dtype, mlsl_reduction_type red_type, mlsl_group_type group_type,
                                     float scale, mlsl_compression_type compress, mlsl_comm_req* req);

@@ -329,6 +329,13 @@ class Environment {
   // Park / resume the background progress threads (reference EPLIB_suspend / EPLIB_execute).
   void SuspendServers();
   void ResumeServers();
+  // Group creation by its members only, for hosts that bring their own rendezvous (the torch.distributed backend
+  // uses the job's store): every member reads GetGroupState(), the members exchange the two words, and each calls
+  // CreateDistributionFromRanks with the OR of the row bitmaps and the maximum of the ticket marks.  `ranks` are
+  // process indices of the global group in group order; the new distribution has them as its data group.
+  void GetGroupState(unsigned long long* rowsInUse, unsigned long long* ticketMark);
+  Distribution* CreateDistributionFromRanks(const size_t* ranks, size_t count, unsigned long long rowsInUse,
+                                            unsigned long long ticketMark);
 };
 
 }  // namespace MLSL

@@ -114,6 +114,9 @@ def _declare(l):
         "mlsl_environment_describe_backend": [H, P(c_char_p)],
         "mlsl_environment_suspend_servers": [H],
         "mlsl_environment_resume_servers": [H],
+        "mlsl_environment_get_group_state": [H, P(ctypes.c_ulonglong), P(ctypes.c_ulonglong)],
+        "mlsl_environment_create_distribution_from_ranks": [H, P(c_size_t), c_size_t, ctypes.c_ulonglong,
+                                                            ctypes.c_ulonglong, P(H)],
         "mlsl_distribution_get_process_count": [H, c_int, P(c_size_t)],
         "mlsl_distribution_get_process_idx": [H, c_int, P(c_size_t)],
         "mlsl_distribution_bcast": [H, c_void_p, c_size_t, c_int, c_size_t, c_int, P(H)],

@@ -495,6 +495,21 @@ class MLSL(_Handle):
     def create_distribution_with_colors(self, data_color, model_color):
         return Distribution(self._get("mlsl_environment_create_distribution_with_colors", H, data_color, model_color))
 
+    def get_group_state(self):
+        """(rows in use, ticket mark) of this rank: the two words the members of a new group exchange before
+        create_distribution_from_ranks."""
+        rows, mark = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        self._call("mlsl_environment_get_group_state", ctypes.byref(rows), ctypes.byref(mark))
+        return rows.value, mark.value
+
+    def create_distribution_from_ranks(self, ranks, rows_in_use, ticket_mark):
+        """Members-only creation of a distribution whose data group is `ranks` (global process indices, the same list
+        in the same order on every member).  `rows_in_use` is the OR and `ticket_mark` the maximum of the members'
+        get_group_state() words, exchanged over the caller's own rendezvous (mlsl_b200.torch_backend uses the
+        torch.distributed store)."""
+        return Distribution(self._get("mlsl_environment_create_distribution_from_ranks", H, _size_array(ranks),
+                                      len(ranks), rows_in_use, ticket_mark))
+
     def delete_distribution(self, dist):
         self._call("mlsl_environment_delete_distribution", dist.handle)
 

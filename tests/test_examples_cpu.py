@@ -50,3 +50,8 @@ def test_data_parallel_training_example(mode):
 def test_tensor_parallel_training_example():
     out = _run([MLSLRUN, "-n", "4", sys.executable, "examples/train_tensor_parallel.py", "--model-parts", "2", "--steps", "6"])
     assert out.count("PASSED") == 4
+
+
+def test_torch_ddp_example():
+    out = _run([MLSLRUN, "-n", "4", sys.executable, "examples/torch_ddp.py"])
+    assert out.count("PASSED") == 4 and "FAILED" not in out

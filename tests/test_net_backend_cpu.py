@@ -55,3 +55,10 @@ def test_a_dying_rank_fails_the_whole_multi_node_job_fast():
     hits = re.findall(r"FAILFAST ([0-9.]+) (True|False)", out)       # ranks share a pipe: lines may run together
     assert hits and "survived" not in out, out[-2000:]
     assert all(float(t) < 30 and ok == "True" for t, ok in hits), hits
+
+
+def test_torch_distributed_backend_across_nodes(tmp_path):
+    """The torch.distributed "mlsl" backend (collectives, member-made sub-groups, DDP) with the ranks spread over two
+    "nodes": the same worker as tests/test_torch_backend_cpu.py, traffic on the TCP mesh."""
+    rcs, out = _launch(2, 2, [sys.executable, os.path.join(ROOT, "tests", "torch_backend_worker.py"), str(tmp_path / "store")])
+    assert all(rc == 0 for rc in rcs) and "torch backend OK" in out, out[-3000:]
