@@ -10,15 +10,15 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(n, tmp_path, extra_env=None):
+def _run(n, tmp_path, extra_env=None, worker="torch_backend_worker.py", expect="torch backend OK"):
     env = dict(os.environ, MLSL_BACKEND="host")
     env.update(extra_env or {})
     store = str(tmp_path / "store")
     res = subprocess.run([os.path.join(ROOT, "bin", "mlslrun"), "-n", str(n), "--timeout", "150", sys.executable,
-                          os.path.join(ROOT, "tests", "torch_backend_worker.py"), store], env=env,
+                          os.path.join(ROOT, "tests", worker), store], env=env,
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=240)
     out = res.stdout.decode(errors="replace")
-    assert res.returncode == 0 and "torch backend OK" in out, out[-3000:]
+    assert res.returncode == 0 and expect in out, out[-3000:]
 
 
 @pytest.mark.parametrize("n", [1, 2, 4])
@@ -30,6 +30,13 @@ def test_torch_distributed_on_mlsl_with_progress_servers(tmp_path):
     """The same traffic when requests go through the progress servers (DDP issues its all-reduces from autograd's
     threads while the main thread is inside backward)."""
     _run(3, tmp_path, {"MLSL_NUM_SERVERS": "2"})
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_fsdp2_and_hybrid_sharding_on_mlsl(n, tmp_path):
+    """`fully_shard` on a 1-D mesh and (4 ranks) replicate x shard on a 2-D DeviceMesh - the mesh dimensions are sub-groups
+    made by their members - must train exactly like one process on the whole batch."""
+    _run(n, tmp_path, worker="torch_fsdp_worker.py", expect="torch fsdp OK")
 
 
 def test_members_only_group_creation_api():
