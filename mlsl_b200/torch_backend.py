@@ -391,6 +391,26 @@ def _create(opts, pg_options=None):
     return MLSLProcessGroup(rank, size, env.create_distribution_from_ranks(ranks, rows, mark), True, owns_lib)
 
 
+def compressed_allreduce_hook(process_group, bucket):
+    """DDP communication hook: average the gradient bucket with the library's quantised all-reduce (block-scaled FP8 with
+    error feedback on the CUDA backend, the QuantParams plug-in or the built-in codec on the host backend - the
+    reference's CT_QUANTIZATION, src/quant/quant.cpp:1-200), scale fused into the same operation.
+
+        ddp.register_comm_hook(None, mlsl_b200.torch_backend.compressed_allreduce_hook)
+    """
+    pg = process_group if process_group is not None else dist.group.WORLD
+    if not isinstance(pg, MLSLProcessGroup):
+        raise TypeError("compressed_allreduce_hook needs a process group of the mlsl backend")
+    buf = bucket.buffer()
+    with comm.use_state(pg._state):
+        if pg.size() > 1:
+            comm.allreduce(buf, scale=1.0 / pg.size(), compress=buf.dtype == torch.float32, group="data",
+                           distribution=pg._d, async_op=True).wait()
+    fut = torch.futures.Future(devices=[buf.device]) if buf.is_cuda else torch.futures.Future()
+    fut.set_result(buf)
+    return fut
+
+
 def register():
     if BACKEND_NAME.upper() not in getattr(dist.Backend, "_plugins", {}):
         dist.Backend.register_backend(BACKEND_NAME, _create, extended_api=True, devices=["cpu", "cuda"])

@@ -151,6 +151,35 @@ for p, q in zip(model.parameters(), ref.parameters()):
     if not torch.allclose(p, q, atol=1e-5 if DEV.type == "cpu" else 1e-3, rtol=1e-4 if DEV.type == "cpu" else 1e-2):
         print("rank %d: DDP diverged from the single-process reference" % rank, flush=True)
         sys.exit(1)
+
+# the same training with the quantised all-reduce as DDP communication hook: replicas stay identical, the result is close
+torch.manual_seed(4321)
+qmodel = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4)).to(DEV)
+qddp = torch.nn.parallel.DistributedDataParallel(qmodel, device_ids=[DEV.index] if DEV.type == "cuda" else None)
+qddp.register_comm_hook(None, mlsl_b200.torch_backend.compressed_allreduce_hook)
+qref = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4)).to(DEV)
+qref.load_state_dict(qmodel.state_dict())
+qopt, qropt = torch.optim.SGD(qddp.parameters(), lr=0.1), torch.optim.SGD(qref.parameters(), lr=0.1)
+for step in range(3):
+    torch.manual_seed(11 * step)
+    x_all, y_all = torch.randn(world, 8, 16).to(DEV), torch.randn(world, 8, 4).to(DEV)
+    qopt.zero_grad()
+    torch.nn.functional.mse_loss(qddp(x_all[rank]), y_all[rank]).backward()
+    qopt.step()
+    qropt.zero_grad()
+    sum(torch.nn.functional.mse_loss(qref(x_all[r]), y_all[r]) for r in range(world)).div(world).backward()
+    qropt.step()
+flat = torch.cat([p.detach().reshape(-1) for p in qmodel.parameters()])
+want = torch.cat([p.detach().reshape(-1) for p in qref.parameters()])
+lo, hi = flat.clone(), flat.clone()
+dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+err = ((flat - want).norm() / want.norm()).item()
+if os.environ.get("MLSL_TEST_VERBOSE") and rank == 0:
+    print("quantised hook relative error %g" % err, flush=True)
+if not torch.equal(lo, hi) or not err < 2e-2:
+    print("rank %d: quantised DDP hook: replicas identical %s, relative error %g" % (rank, torch.equal(lo, hi), err), flush=True)
+    sys.exit(1)
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:
