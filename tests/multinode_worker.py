@@ -10,13 +10,17 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from mlsl_b200 import comm  # noqa: E402
 from mlsl_b200.parallel import multinode  # noqa: E402
 
+DEV = torch.device("cpu")
+if len(sys.argv) > 1 and sys.argv[1] == "cuda":     # one GPU per rank; CUDA_VISIBLE_DEVICES selects the "node's" GPUs
+    DEV = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    torch.cuda.set_device(DEV)
 hc = multinode.init_hybrid()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 assert hc.rank == rank and hc.world_size == world and comm.world_size() == int(os.environ["LOCAL_WORLD_SIZE"])
 
 
 def inp(r, n):
-    return torch.arange(n, dtype=torch.float32) % 17 + r + 1
+    return (torch.arange(n, dtype=torch.float32) % 17 + r + 1).to(DEV)
 
 
 for n in (1, 5, 1000, 4099, 1 << 16):
@@ -30,7 +34,7 @@ for n in (1, 5, 1000, 4099, 1 << 16):
     hc.allreduce(t, op="max")
     assert torch.equal(t, inp(world - 1, n)), ("allreduce max", n)
     for root in (0, world - 1, world // 2):
-        t = inp(100 + root, n) if rank == root else torch.zeros(n)
+        t = inp(100 + root, n) if rank == root else torch.zeros(n, device=DEV)
         hc.bcast(t, root=root)
         assert torch.equal(t, inp(100 + root, n)), ("bcast", n, root)
     out = hc.allgather(inp(rank, n))
@@ -39,13 +43,13 @@ hc.barrier()
 
 # data-parallel SGD over both levels against a single-process model on the whole batch
 torch.manual_seed(3)
-model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 2))
-ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 2))
+model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 2)).to(DEV)
+ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 2)).to(DEV)
 ref.load_state_dict(model.state_dict())
 opt, ropt = torch.optim.SGD(model.parameters(), lr=0.1), torch.optim.SGD(ref.parameters(), lr=0.1)
 for step in range(3):
     torch.manual_seed(50 + step)
-    x, y = torch.randn(world, 4, 8), torch.randn(world, 4, 2)
+    x, y = torch.randn(world, 4, 8).to(DEV), torch.randn(world, 4, 2).to(DEV)
     opt.zero_grad()
     torch.nn.functional.mse_loss(model(x[rank]), y[rank]).backward()
     flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
@@ -59,7 +63,7 @@ for step in range(3):
     sum(torch.nn.functional.mse_loss(ref(x[r]), y[r]) for r in range(world)).div(world).backward()
     ropt.step()
 for p, q in zip(model.parameters(), ref.parameters()):
-    assert torch.allclose(p, q, atol=1e-5, rtol=1e-4), "two-level data parallel training diverged"
+    assert torch.allclose(p, q, atol=1e-5 if DEV.type == "cpu" else 1e-3, rtol=1e-4 if DEV.type == "cpu" else 1e-2), "two-level data parallel training diverged"
 hc.barrier()
 dist.destroy_process_group()
 hc.finalize()
