@@ -28,7 +28,7 @@ class _Bucket:
 
 class DistributedOptimizer:
     def __init__(self, params, lr=0.1, momentum=0.0, weight_decay=0.0, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8,
-                 bucket_mb=64, mode=None, compress=False, distribution=None, average=True):
+                 bucket_mb=64, mode=None, compress=False, distribution=None, average=True, hybrid=None):
         self.env = comm.env()
         self._state = comm._state()   # gradient hooks fire on autograd's device thread
         self.params = [p for p in params if p.requires_grad]
@@ -36,13 +36,17 @@ class DistributedOptimizer:
         self.dist = distribution if distribution is not None else comm.world_distribution()
         self.world = self.dist.get_process_count(0)
         self.rank = self.dist.get_process_idx(0)
-        self.mode = mode or "fused"
+        # hybrid: a parallel.multinode.HybridComm - gradients are averaged over ALL nodes by the two-level all-reduce
+        # (reduce-scatter in the node, shard all-reduce between nodes, all-gather in the node), the update is local
+        self.hybrid = hybrid
+        self.mode = mode or ("allreduce" if hybrid is not None else "fused")
         assert self.mode in ("fused", "allreduce")
+        assert hybrid is None or self.mode == "allreduce", "hybrid (multi-node) training uses mode='allreduce'"
         self.kind = optimizer
         assert optimizer in ("sgd", "adamw")
         self.lr, self.momentum, self.weight_decay, self.betas, self.eps = lr, momentum, weight_decay, betas, eps
         self.compress = bool(compress) and self.mode == "allreduce"
-        self.scale = 1.0 / self.world if average else 1.0
+        self.scale = 1.0 / (hybrid.world_size if hybrid is not None else self.world) if average else 1.0
         self.steps = 0
         self._build(bucket_mb)
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(p)) for p in self.params]
@@ -131,6 +135,8 @@ class DistributedOptimizer:
                                     OptimizerType.ADAMW if self.kind == "adamw" else OptimizerType.SGD, lr=self.lr,
                                     momentum=self.momentum, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
                                     weight_decay=self.weight_decay, step=self.steps + 1, grad_scale=self.scale)
+        elif self.hybrid is not None:
+            self.hybrid.allreduce(b.grad, scale=self.scale)
         else:
             b.ps.start_gradient_comm(b.grad)
         b.started = True
@@ -144,7 +150,7 @@ class DistributedOptimizer:
         for b in self.buckets:
             if self.mode == "fused":
                 b.ps.wait_fused_update()
-            else:
+            elif self.hybrid is None:
                 b.ps.wait_gradient_comm()
             b.pending, b.started = len(b.params), False
         if self.mode == "allreduce":

@@ -64,6 +64,29 @@ for step in range(3):
     ropt.step()
 for p, q in zip(model.parameters(), ref.parameters()):
     assert torch.allclose(p, q, atol=1e-5 if DEV.type == "cpu" else 1e-3, rtol=1e-4 if DEV.type == "cpu" else 1e-2), "two-level data parallel training diverged"
+
+# the packaged form: DistributedOptimizer with bucketed gradients in the symmetric heap, hooks, two-level all-reduce
+import mlsl_b200 as mlsl  # noqa: E402
+torch.manual_seed(8)
+m2 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 2)).to(DEV)
+r2 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 2)).to(DEV)
+r2.load_state_dict(m2.state_dict())
+dopt = mlsl.DistributedOptimizer(m2.parameters(), lr=0.05, momentum=0.9, hybrid=hc, bucket_mb=0.0005)
+ropt2 = torch.optim.SGD(r2.parameters(), lr=0.05, momentum=0.9)
+for step in range(4):
+    torch.manual_seed(90 + step)
+    x, y = torch.randn(world, 4, 8).to(DEV), torch.randn(world, 4, 2).to(DEV)
+    dopt.zero_grad()
+    torch.nn.functional.mse_loss(m2(x[rank]), y[rank]).backward()
+    dopt.step()
+    ropt2.zero_grad()
+    sum(torch.nn.functional.mse_loss(r2(x[r]), y[r]) for r in range(world)).div(world).backward()
+    ropt2.step()
+for p, q in zip(m2.parameters(), r2.parameters()):
+    assert torch.allclose(p, q, atol=1e-5 if DEV.type == "cpu" else 1e-3, rtol=1e-4 if DEV.type == "cpu" else 1e-2), \
+        "DistributedOptimizer(hybrid=...) diverged"
+assert len(dopt.buckets) > 1
+dopt.close()
 hc.barrier()
 dist.destroy_process_group()
 hc.finalize()
