@@ -24,6 +24,8 @@ def _env():
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "MLSL_BACKEND", "MLSL_JOB_ID"):
         env.pop(k, None)
     env.setdefault("I_MPI_FABRICS", "shm")
+    # the form bench.py times on the GPU: separate send and receive buffers (harness option, the library is untouched)
+    env["MLSL_BENCH_OUT_OF_PLACE"] = "1"
     return env
 
 
@@ -66,7 +68,7 @@ def run(n_gpus, steps, warmup, headline_bytes):
         "value": round(value, 4), "unit": "GB/s", "n_gpus": n, "steps": steps, "warmup": warmup,
         "ms_per_step": round(head["us"] / 1e3, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic", "impl": "reference",
-        "config": {"model": "allreduce fp32 SUM, %d MiB per rank, in place" % (headline_bytes >> 20),
+        "config": {"model": "allreduce fp32 SUM, %d MiB per rank, out of place" % (headline_bytes >> 20),
                    "parallelism": "dp%d" % n, "message_bytes": headline_bytes,
                    "api": "MLSL::Distribution::AllReduce + Environment::Wait (intel/MLSL process mode, Intel MPI shm)",
                    "device": "CPU (the reference has no GPU path); host-timed, max over ranks",

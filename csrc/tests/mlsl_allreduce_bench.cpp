@@ -1,5 +1,6 @@
-// Host-pointer AllReduce bandwidth sweep through the public API (Environment::Alloc buffers, in-place fp32 SUM,
-// Distribution::AllReduce + Environment::Wait).  Uses only calls that exist in the reference API, so the SAME source
+// Host-pointer AllReduce bandwidth sweep through the public API (Environment::Alloc buffers, fp32 SUM,
+// Distribution::AllReduce + Environment::Wait; in place, or send -> recv with MLSL_BENCH_OUT_OF_PLACE=1 - the form
+// bench.py times on the GPU).  Uses only calls that exist in the reference API, so the SAME source
 // is compiled against the reference's headers/library for the `--impl reference` arm of bench.py and against ours
 // for the CPU-plumbing comparison.  Host-timed (both are CPU libraries on this path), max over ranks.
 //   mlsl_allreduce_bench <min_bytes> <max_bytes> <iters> <warmup> [factor=4] [exact_bytes...]
@@ -30,6 +31,9 @@ int main(int argc, char** argv) {
   size_t rank = env.GetProcessIdx(), P = env.GetProcessCount();
   Distribution* dist = env.CreateDistribution(P, 1);
   float* buf = (float*)env.Alloc(maxb, 4096);
+  const char* oop = getenv("MLSL_BENCH_OUT_OF_PLACE");
+  float* out = (oop && atoi(oop)) ? (float*)env.Alloc(maxb, 4096) : buf;
+  if (out != buf) memset(out, 0, maxb);
   double* tbuf = (double*)env.Alloc(64, 64);
   for (size_t i = 0; i < maxb / 4; ++i) buf[i] = 1.0f;
   std::vector<size_t> sizes;
@@ -38,10 +42,10 @@ int main(int argc, char** argv) {
   for (size_t bytes : sizes) {
     size_t count = bytes / 4;
     if (!count) continue;
-    for (int i = 0; i < warm; ++i) env.Wait(dist->AllReduce(buf, buf, count, DT_FLOAT, RT_SUM, GT_DATA));
+    for (int i = 0; i < warm; ++i) env.Wait(dist->AllReduce(buf, out, count, DT_FLOAT, RT_SUM, GT_DATA));
     dist->Barrier(GT_DATA);
     double t0 = now_s();
-    for (int i = 0; i < iters; ++i) env.Wait(dist->AllReduce(buf, buf, count, DT_FLOAT, RT_SUM, GT_DATA));
+    for (int i = 0; i < iters; ++i) env.Wait(dist->AllReduce(buf, out, count, DT_FLOAT, RT_SUM, GT_DATA));
     double dt = (now_s() - t0) / iters;
     tbuf[0] = dt;
     env.Wait(dist->AllReduce(tbuf, tbuf, 1, DT_DOUBLE, RT_MAX, GT_DATA));
@@ -55,6 +59,10 @@ int main(int argc, char** argv) {
              dt * 1e6, algbw, busbw, P);
       fflush(stdout);
     }
+  }
+  if (out != buf) {
+    if (out[0] != (float)P) fprintf(stderr, "rank %zu: unexpected result %f (expected %zu)\n", rank, out[0], P);
+    env.Free(out);
   }
   env.Free(buf);
   env.Free(tbuf);
