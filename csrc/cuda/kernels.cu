@@ -609,12 +609,31 @@ __global__ void __launch_bounds__(256) k_scale_copy(T* __restrict__ dst, const T
   const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
   const bool vec = ((((size_t)dst) | ((size_t)src)) & 15) == 0;
   const size_t nvec = vec ? count / N : 0;
-  for (size_t i = gtid; i < nvec; i += gsz) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  // four independent 16-byte loads in flight per thread before the first store: a single load per iteration leaves
+  // ~32 KB outstanding per SM, short of what HBM3e needs to stay busy (82 % of the copy peak measured that way)
+  constexpr int U = 4;
+  const size_t nblk = nvec / (U * gsz) * (U * gsz);
+  for (size_t base = gtid; base < nblk; base += U * gsz) {
+    uint4 v[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) v[j] = __ldcs(s4 + base + (size_t)j * gsz);
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      Acc a[N];
+      VT::unpack(v[j], a);
+#pragma unroll
+      for (int k = 0; k < N; ++k) a[k] = VT::scale(a[k], scale);
+      __stcs(d4 + base + (size_t)j * gsz, VT::pack(a));
+    }
+  }
+  for (size_t i = nblk + gtid; i < nvec; i += gsz) {
     Acc a[N];
-    VT::unpack(__ldcs(reinterpret_cast<const uint4*>(src) + i), a);
+    VT::unpack(__ldcs(s4 + i), a);
 #pragma unroll
     for (int k = 0; k < N; ++k) a[k] = VT::scale(a[k], scale);
-    __stcs(reinterpret_cast<uint4*>(dst) + i, VT::pack(a));
+    __stcs(d4 + i, VT::pack(a));
   }
   for (size_t i = nvec * N + gtid; i < count; i += gsz) VT::store1(dst + i, VT::scale(VT::load1(src + i), scale));
 }
