@@ -55,3 +55,8 @@ def test_tensor_parallel_training_example():
 def test_torch_ddp_example():
     out = _run([MLSLRUN, "-n", "4", sys.executable, "examples/torch_ddp.py"])
     assert out.count("PASSED") == 4 and "FAILED" not in out
+
+
+def test_pipeline_parallel_training_example():
+    out = _run([MLSLRUN, "-n", "4", sys.executable, "examples/train_pipeline_parallel.py", "--stages", "2"])
+    assert out.count("PASSED") == 4 and "FAILED" not in out
