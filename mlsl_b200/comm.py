@@ -344,6 +344,38 @@ def alltoall(tensor, out=None, group="data", async_op=False, distribution=None):
     return w if async_op else w.wait()
 
 
+def alltoallv(tensor, send_counts, recv_counts=None, out=None, group="data", async_op=False, distribution=None):
+    """Variable all-to-all (Distribution::AlltoAllv): `send_counts[p]` consecutive elements of `tensor` go to rank p;
+    returns the concatenation of what the ranks sent here, in rank order.  `recv_counts` are exchanged first when the
+    caller does not know them (one small all-to-all)."""
+    _prep(tensor)
+    d = _dist(distribution)
+    g = _group(group)
+    P = d.get_process_count(g)
+    send_counts = [int(c) for c in send_counts]
+    if len(send_counts) != P or sum(send_counts) > tensor.numel():
+        raise ValueError("alltoallv: need %d send counts that fit the %d elements of the tensor" % (P, tensor.numel()))
+    if recv_counts is None:
+        mine = torch.tensor(send_counts, dtype=torch.int32)
+        theirs = torch.empty(P, dtype=torch.int32)
+        if is_device():
+            mine, theirs = mine.to(tensor.device), theirs.to(tensor.device)
+        alltoall(mine, out=theirs, group=group, distribution=distribution)
+        recv_counts = theirs.tolist()
+    recv_counts = [int(c) for c in recv_counts]
+    total = sum(recv_counts)
+    if out is None:
+        out = torch.empty(max(total, 1), dtype=tensor.dtype, device=tensor.device)[:total]
+    elif out.numel() < total or out.dtype != tensor.dtype:
+        raise ValueError("alltoallv: `out` must hold %d elements of %s" % (total, tensor.dtype))
+    so = [sum(send_counts[:p]) for p in range(P)]
+    ro = [sum(recv_counts[:p]) for p in range(P)]
+    _sync_stream()
+    req = d.all_to_allv(tensor, send_counts, so, out, recv_counts, ro, mlsl_dtype(tensor.dtype), g)
+    w = Work(env(), req, out, (tensor, out))
+    return w if async_op else w.wait()
+
+
 def ring_shift(tensor, shift=1, out=None, group="data", async_op=False, distribution=None):
     """out on rank i = tensor of rank (i - shift) mod P: every rank sends its block `shift` positions up the ring.
     One SendRecvList operation (the reference declares that op but never wires it up, src/comm.hpp:212-248); this is the
