@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--width", type=int, default=64)
     ap.add_argument("--micro-batch", type=int, default=16)
     ap.add_argument("--layers-per-stage", type=int, default=2)
+    ap.add_argument("--schedule", default="1f1b", choices=["gpipe", "1f1b"])
     args = ap.parse_args()
     use_cuda = torch.cuda.is_available() and os.environ.get("MLSL_BACKEND", "cuda") == "cuda"
     if use_cuda:
@@ -53,7 +54,7 @@ def main():
     for step in range(args.steps):
         opt.zero_grad()
         loss = st.step(xs if st.is_first else None, loss_fn=torch.nn.functional.mse_loss if st.is_last else None,
-                       targets=ys if st.is_last else None, num_micro=args.micro)
+                       targets=ys if st.is_last else None, num_micro=args.micro, schedule=args.schedule)
         for p in block.parameters():                      # average this stage's gradients over the replicas
             g = p.grad.contiguous().view(-1)
             mlsl.allreduce(g, group="data", distribution=dist, scale=1.0 / replicas)

@@ -8,8 +8,12 @@ stage s hands its output to stage s+1 (backward: its input gradient to stage s-1
 order of communication identical on all ranks by construction - the rule every collective of the library relies on -
 and on the CUDA backend the exchange is a single peer-memory kernel ordered on the compute stream.
 
-Schedule: GPipe (all forwards, then all backwards), M micro-batches over S stages = M + S - 1 ticks each way, bubble
-fraction (S - 1) / (M + S - 1); activations of the M micro-batches are kept for the backward pass.
+Schedules (both give the gradients of the unsplit model, mean over the micro-batches):
+  "gpipe" : all forwards, then all backwards; M + S - 1 ticks each way, the activations of all M micro-batches are alive;
+  "1f1b"  : a stage runs the forward of micro-batch t - s and the backward of micro-batch t - 2(S-1) + s in the same tick,
+            and BOTH directions travel in the one exchange of that tick (activation to s+1, gradient to s-1);
+            M + 2(S-1) ticks, at most 2(S-1-s) + 1 micro-batches alive on stage s.
+Bubble fraction (S - 1) / (M + S - 1) in both.
 """
 import torch
 
@@ -30,6 +34,24 @@ def _neighbour_shift(tensor, out, direction, dist, group):
     req = dist.send_recv_list(tensor, sc, [0] * P, out, rc, [0] * P, comm.mlsl_dtype(tensor.dtype), g)
     comm.Work(comm.env(), req, out, (tensor, out)).wait()
     return out
+
+
+def _both_ways(send, recv, n_fwd_out, n_bwd_out, n_fwd_in, n_bwd_in, dist, group):
+    """One exchange, two directions: send = [activation for s+1 | gradient for s-1], recv = [activation from s-1 |
+    gradient from s+1]."""
+    g = comm._group(group)
+    P, idx = dist.get_process_count(g), dist.get_process_idx(g)
+    sc, so, rc, ro = [0] * P, [0] * P, [0] * P, [0] * P
+    if idx + 1 < P:
+        sc[idx + 1], so[idx + 1] = n_fwd_out, 0
+        rc[idx + 1], ro[idx + 1] = n_bwd_in, n_fwd_in
+    if idx - 1 >= 0:
+        sc[idx - 1], so[idx - 1] = n_bwd_out, n_fwd_out
+        rc[idx - 1], ro[idx - 1] = n_fwd_in, 0
+    comm._prep(send), comm._prep(recv)
+    comm._sync_stream()
+    req = dist.send_recv_list(send, sc, so, recv, rc, ro, comm.mlsl_dtype(send.dtype), g)
+    comm.Work(comm.env(), req, recv, (send, recv)).wait()
 
 
 class PipelineStage:
@@ -57,7 +79,7 @@ class PipelineStage:
             return comm.alloc_tensor(shape, self.dtype, zero=True)
         return torch.zeros(shape, dtype=self.dtype, device=self.device)
 
-    def step(self, micro_inputs=None, loss_fn=None, targets=None, num_micro=None):
+    def step(self, micro_inputs=None, loss_fn=None, targets=None, num_micro=None, schedule="gpipe"):
         """One training step over M micro-batches: forward through all stages, backward through all stages.  Gradients
         accumulate into the parameters' .grad (mean over the micro-batches).  Returns the mean loss on the last stage,
         None elsewhere.  `num_micro` must be given on stages that see neither inputs nor targets."""
@@ -67,6 +89,10 @@ class PipelineStage:
             raise ValueError("the first stage needs the %d micro-batch inputs" % M)
         if self.is_last and (loss_fn is None or targets is None or len(targets) != M):
             raise ValueError("the last stage needs loss_fn and the %d micro-batch targets" % M)
+        if schedule == "1f1b":
+            return self._step_1f1b(micro_inputs, loss_fn, targets, M)
+        if schedule != "gpipe":
+            raise ValueError("unknown schedule %r (expected 'gpipe' or '1f1b')" % (schedule,))
         recv_act, send_act = self._buf(self.in_shape), self._buf(self.out_shape)
         recv_grad, send_grad = self._buf(self.out_shape), self._buf(self.in_shape)
         saved = [None] * M
@@ -104,6 +130,40 @@ class PipelineStage:
         if comm.is_device():
             for b in (recv_act, send_act, recv_grad, send_grad):
                 comm.free_tensor(b)
+        return total
+
+    def _step_1f1b(self, micro_inputs, loss_fn, targets, M):
+        S, s = self.stages, self.stage
+        n_in = int(torch.Size(self.in_shape).numel())
+        n_out = int(torch.Size(self.out_shape).numel())
+        # send = [my output | my input gradient], recv = [my input | my output gradient]
+        send, recv = self._buf((n_out + n_in,)), self._buf((n_in + n_out,))
+        saved, total = {}, None
+        self.max_alive = 0
+        for t in range(M + 2 * (S - 1)):
+            f, b = t - s, t - 2 * (S - 1) + s
+            if 0 <= f < M:
+                x = micro_inputs[f] if self.is_first else recv[:n_in].view(self.in_shape).clone().requires_grad_(True)
+                y = self.module(x)
+                saved[f] = (x, y)
+                self.max_alive = max(self.max_alive, len(saved))
+                if not self.is_last:
+                    send[:n_out].copy_(y.detach().reshape(-1))
+            if 0 <= b < M:
+                x, y = saved.pop(b)
+                if self.is_last:
+                    loss = loss_fn(y, targets[b]) / M
+                    total = loss.detach() if total is None else total + loss.detach()
+                    loss.backward()
+                else:
+                    torch.autograd.backward(y, recv[n_in:].view_as(y).clone())
+                if not self.is_first:
+                    send[n_out:].copy_(x.grad.reshape(-1))
+            if S > 1:
+                _both_ways(send, recv, n_out, n_in, n_in, n_out, self.dist, self.group)
+        if comm.is_device():
+            comm.free_tensor(send)
+            comm.free_tensor(recv)
         return total
 
 

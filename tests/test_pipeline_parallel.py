@@ -38,8 +38,9 @@ def _reference(stages, m, replicas=1):
     return total.item(), [[p.grad.clone() for p in b.parameters()] for b in blocks]
 
 
-@pytest.mark.parametrize("stages,micro", [(1, 3), (2, 1), (3, 4), (4, 2)])
-def test_pipeline_matches_unsplit_model(stages, micro):
+@pytest.mark.parametrize("schedule", ["gpipe", "1f1b"])
+@pytest.mark.parametrize("stages,micro", [(1, 3), (2, 1), (3, 4), (4, 2), (3, 7)])
+def test_pipeline_matches_unsplit_model(stages, micro, schedule):
     want_loss, want_grads = _reference(stages, micro)
 
     def body(r, mlsl):
@@ -53,7 +54,9 @@ def test_pipeline_matches_unsplit_model(stages, micro):
         for _ in range(2):      # a second step reuses nothing from the first (buffers are per step)
             block.zero_grad()
             loss = st.step(xs if st.is_first else None, loss_fn=torch.nn.functional.mse_loss if st.is_last else None,
-                           targets=ys if st.is_last else None, num_micro=micro)
+                           targets=ys if st.is_last else None, num_micro=micro, schedule=schedule)
+        if schedule == "1f1b":      # the point of the schedule: live activations are bounded by the depth, not by M
+            assert st.max_alive <= min(micro, 2 * (stages - 1 - r) + 1), (r, st.max_alive)
         assert abs(bubble_fraction(stages, micro) - (stages - 1) / (micro + stages - 1)) < 1e-12
         mlsl.env().delete_distribution(dist)
         return (loss.item() if loss is not None else None), [p.grad.clone() for p in block.parameters()]
