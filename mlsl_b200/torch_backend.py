@@ -65,11 +65,10 @@ class _MLSLWork(dist._Work):
         return True
 
     def is_completed(self):
-        if self._finish is None and all(w.test() for w in self._pending):
+        if all(w.is_completed() for w in self._pending):
+            self.wait()          # nothing left to wait for: run the copy-backs
             return True
         return False
-
-    test = is_completed
 
     def is_success(self):
         return True
