@@ -252,7 +252,10 @@ def run_ours(args):
                    "l2": "inputs (1 GiB) larger than L2, no flush needed", "transport": "fp8" if args.compress else "fp32",
                    "api": "mlsl_b200.allreduce -> Distribution::AllReduceEx -> Environment::Wait",
                    "backend": env.get_backend_name(), "backend_detail": env.describe_backend(), "stream_mode": os.environ.get("MLSL_STREAM_MODE"),
-                   "correct": ok},
+                   "correct": ok,
+                   "value_definition": "bus bandwidth in the nccl-tests sense: S / t x 2(N-1)/N, a per-link figure that stays "
+                                       "CONSTANT under ideal weak scaling (S per rank fixed); total bytes reduced per second = "
+                                       "N x S / t.  N = 1 has no link: the value is S / t of the on-device scale-copy"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * launches_per_step,
         "sweep": sweep, "nccl": nccl,
     }
