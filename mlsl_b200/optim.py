@@ -48,6 +48,7 @@ class DistributedOptimizer:
         self.compress = bool(compress) and self.mode == "allreduce"
         self.scale = 1.0 / (hybrid.world_size if hybrid is not None else self.world) if average else 1.0
         self.steps = 0
+        self._sync = True
         self._build(bucket_mb)
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(p)) for p in self.params]
         if self.mode == "allreduce":
@@ -125,9 +126,27 @@ class DistributedOptimizer:
             b = self._bucket_of[p]
             b.pending -= 1
             if b.pending == 0:
+                if not self._sync:          # gradient accumulation: keep adding into the bucket, exchange later
+                    b.pending = len(b.params)
+                    return
                 with comm.use_state(self._state):
                     self._start(b)
         return hook
+
+    def no_sync(self):
+        """Context manager for gradient accumulation: backward passes inside it only accumulate into the buckets; the
+        exchange of the accumulated gradients starts in the first backward after it (or in step())."""
+        opt = self
+
+        class _NoSync:
+            def __enter__(self):
+                opt._sync = False
+
+            def __exit__(self, *exc):
+                opt._sync = True
+                return False
+
+        return _NoSync()
 
     def _start(self, b):
         if self.mode == "fused":

@@ -159,3 +159,47 @@ def test_checkpoint_resume_and_reshard(mode, kind, kw):
     other_world = run_ranks(4, resumed)
     for o in other_world:
         assert torch.allclose(o, ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["fused", "allreduce"])
+def test_gradient_accumulation_with_no_sync(mode):
+    """Two micro-batches per step: the first backward runs under no_sync() (no exchange, the bucket only accumulates), the
+    second starts the exchange of the sum.  Reference: one process, the mean over ranks of the summed micro-batch gradients."""
+    world, steps, kw = 2, 3, dict(lr=0.05, momentum=0.9)
+
+    def body(r, mlsl):
+        m = _model()
+        opt = mlsl.DistributedOptimizer(m.parameters(), lr=kw["lr"], momentum=kw["momentum"], mode=mode, bucket_mb=0.004)
+        started = []
+        orig = opt._start
+        opt._start = lambda b: (started.append(1), orig(b))[1]
+        for s in range(steps):
+            opt.zero_grad()
+            with opt.no_sync():
+                x, y = _batch(r, 2 * s)
+                torch.nn.functional.mse_loss(m(x), y).backward()
+                assert not started, "no_sync() must not start any exchange"
+            x, y = _batch(r, 2 * s + 1)
+            torch.nn.functional.mse_loss(m(x), y).backward()
+            assert len(started) == len(opt.buckets)
+            opt.step()
+            started.clear()
+        out = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+        opt.close()
+        return out
+
+    outs = run_ranks(world, body)
+    m = _model()
+    ref_opt = torch.optim.SGD(m.parameters(), **kw)
+    for s in range(steps):
+        ref_opt.zero_grad()
+        loss = 0
+        for r in range(world):
+            for micro in (2 * s, 2 * s + 1):
+                x, y = _batch(r, micro)
+                loss = loss + torch.nn.functional.mse_loss(m(x), y) / world
+        loss.backward()
+        ref_opt.step()
+    ref = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+    for o in outs:
+        assert torch.allclose(o, ref, rtol=2e-4, atol=2e-5), (o - ref).abs().max()
