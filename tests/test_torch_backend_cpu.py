@@ -43,7 +43,7 @@ def test_members_only_group_creation_api():
     """Environment.get_group_state / create_distribution_from_ranks without torch: the members exchange the two words over
     an all-gather on the world and build overlapping groups; non-members never take part."""
     code = r'''
-import os, sys, torch
+import os, struct, sys, torch
 sys.path.insert(0, %r)
 import mlsl_b200 as mlsl
 from mlsl_b200 import comm
@@ -51,13 +51,14 @@ env = mlsl.init()
 rank, world = comm.rank(), comm.world_size()
 def make(ranks):
     rows, mark = env.get_group_state()
-    words = comm.allgather(torch.tensor([rows, mark], dtype=torch.float64), group="global").view(world, 2)
+    mine = torch.frombuffer(bytearray(struct.pack("<QQ", rows, mark)), dtype=torch.uint8)      # 64-bit words travel as bytes
+    words = [struct.unpack("<QQ", bytes(w.tolist())) for w in comm.allgather(mine, group="global").view(world, 16)]
     if rank not in ranks:
         return None
     r = 0
     for p in ranks:
-        r |= int(words[p, 0])
-    return env.create_distribution_from_ranks(ranks, r, int(max(words[p, 1] for p in ranks)))
+        r |= words[p][0]
+    return env.create_distribution_from_ranks(ranks, r, max(words[p][1] for p in ranks))
 groups = [(l, make(l)) for l in ([0, 2], [1, 2], [0, 1, 2])]
 for l, d in groups:
     if d is None:
