@@ -4,6 +4,8 @@
 // is compiled against the reference's headers/library for the `--impl reference` arm of bench.py and against ours
 // for the CPU-plumbing comparison.  Host-timed (both are CPU libraries on this path), max over ranks.
 //   mlsl_allreduce_bench <min_bytes> <max_bytes> <iters> <warmup> [factor=4] [exact_bytes...]
+// MLSL_BENCH_OP=allreduce (default) | allgather | reducescatter | alltoall | bcast selects the collective; `bytes` is
+// always the size of the LARGER of the two buffers (the gathered / scattered / exchanged whole), algbw = bytes / t.
 // Prints one JSON object per size on rank 0.
 #include <chrono>
 #include <cstdio>
@@ -32,8 +34,20 @@ int main(int argc, char** argv) {
   Distribution* dist = env.CreateDistribution(P, 1);
   float* buf = (float*)env.Alloc(maxb, 4096);
   const char* oop = getenv("MLSL_BENCH_OUT_OF_PLACE");
-  float* out = (oop && atoi(oop)) ? (float*)env.Alloc(maxb, 4096) : buf;
+  const char* opname = getenv("MLSL_BENCH_OP") ? getenv("MLSL_BENCH_OP") : "allreduce";
+  enum { AR, AG, RS, A2A, BC } op = !strcmp(opname, "allgather") ? AG : !strcmp(opname, "reducescatter") ? RS
+                                    : !strcmp(opname, "alltoall") ? A2A : !strcmp(opname, "bcast") ? BC : AR;
+  float* out = ((oop && atoi(oop)) || op == AG || op == RS || op == A2A) ? (float*)env.Alloc(maxb, 4096) : buf;
   if (out != buf) memset(out, 0, maxb);
+  auto run = [&](size_t count) -> CommReq* {   // count = elements of the whole
+    switch (op) {
+      case AG: return dist->AllGather(buf, count / P, out, DT_FLOAT, GT_DATA);
+      case RS: return dist->ReduceScatter(buf, out, count / P, DT_FLOAT, RT_SUM, GT_DATA);
+      case A2A: return dist->AlltoAll(buf, count / P, out, DT_FLOAT, GT_DATA);
+      case BC: return dist->Bcast(buf, count, DT_FLOAT, 0, GT_DATA);
+      default: return dist->AllReduce(buf, out, count, DT_FLOAT, RT_SUM, GT_DATA);
+    }
+  };
   double* tbuf = (double*)env.Alloc(64, 64);
   for (size_t i = 0; i < maxb / 4; ++i) buf[i] = 1.0f;
   std::vector<size_t> sizes;
@@ -42,10 +56,11 @@ int main(int argc, char** argv) {
   for (size_t bytes : sizes) {
     size_t count = bytes / 4;
     if (!count) continue;
-    for (int i = 0; i < warm; ++i) env.Wait(dist->AllReduce(buf, out, count, DT_FLOAT, RT_SUM, GT_DATA));
+    if (count < P) continue;
+    for (int i = 0; i < warm; ++i) env.Wait(run(count));
     dist->Barrier(GT_DATA);
     double t0 = now_s();
-    for (int i = 0; i < iters; ++i) env.Wait(dist->AllReduce(buf, out, count, DT_FLOAT, RT_SUM, GT_DATA));
+    for (int i = 0; i < iters; ++i) env.Wait(run(count));
     double dt = (now_s() - t0) / iters;
     tbuf[0] = dt;
     env.Wait(dist->AllReduce(tbuf, tbuf, 1, DT_DOUBLE, RT_MAX, GT_DATA));
@@ -55,13 +70,13 @@ int main(int argc, char** argv) {
     if (rank == 0) {
       double algbw = bytes / dt / 1e9;
       double busbw = algbw * (P > 1 ? 2.0 * (P - 1) / P : 1.0);
-      printf("{\"bytes\": %zu, \"us\": %.3f, \"algbw_GBps\": %.4f, \"busbw_GBps\": %.4f, \"ranks\": %zu}\n", bytes,
+      printf("{\"op\": \"%s\", \"bytes\": %zu, \"us\": %.3f, \"algbw_GBps\": %.4f, \"busbw_GBps\": %.4f, \"ranks\": %zu}\n", opname, bytes,
              dt * 1e6, algbw, busbw, P);
       fflush(stdout);
     }
   }
   if (out != buf) {
-    if (out[0] != (float)P) fprintf(stderr, "rank %zu: unexpected result %f (expected %zu)\n", rank, out[0], P);
+    if (op == AR && out[0] != (float)P) fprintf(stderr, "rank %zu: unexpected result %f (expected %zu)\n", rank, out[0], P);
     env.Free(out);
   }
   env.Free(buf);
