@@ -14,6 +14,7 @@
 #include <fcntl.h>
 #include <poll.h>
 #include <sys/socket.h>
+#include <sys/uio.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -21,6 +22,7 @@
 #include <cstring>
 #include <deque>
 #include <map>
+#include <memory>
 #include <mutex>
 
 #include "log.hpp"
@@ -37,6 +39,14 @@ struct Seg {
   char* ptr;
   size_t bytes;
 };
+
+constexpr size_t kOneShotBytes = 32 << 10;   // all-reduce up to this size: one exchange of whole vectors
+// A message nobody waits for yet is read into parking space only up to this size (eager); a larger one stays in the
+// socket until its receive is posted and is then read straight into the user's buffer (rendezvous by TCP flow control).
+// Safe because a pair of ranks starts its common collectives in the same order: nothing this rank needs first can be
+// queued behind the held message on that connection.
+constexpr size_t kEagerBytes = 32 << 10;
+constexpr size_t kBcastSplitBytes = 128 << 10;   // broadcast from this size on: scatter + all-gather
 
 struct WireHdr {
   uint64_t tag, bytes;
@@ -158,7 +168,11 @@ class Mesh {
       pfds.clear();
       // always listen on every connection: a peer may already be sending for a later collective
       for (int p = 0; p < world_; ++p)
-        if (fds_[p] >= 0) pfds.push_back(pollfd{fds_[p], POLLIN, 0});
+        if (fds_[p] >= 0) {
+          const Peer& P = peers_[p];
+          const bool idle_hold = P.held && !P.expect.count(P.hdr.tag);   // readable, but nobody to read for: don't spin
+          pfds.push_back(pollfd{fds_[p], (short)(idle_hold ? 0 : POLLIN), 0});
+        }
       for (Out& o : outs)
         if (o.sent < o.hdr.bytes || o.hdr_sent < sizeof(WireHdr))
           for (pollfd& pf : pfds)
@@ -203,27 +217,40 @@ class Mesh {
     char* dst = nullptr;                  // where the current payload goes (user buffer or parking space)
     std::vector<char> stash;              // parking space of the message being read, if nobody waits for it yet
     bool to_stash = false;
+    bool held = false;                    // header read, large payload left in the socket until its receive is posted
     std::map<uint64_t, Expect> expect;    // tag -> waiting receive of the running exchange
     std::map<uint64_t, std::vector<char>> parked;
   };
 
   static int fcntl_nonblock(int fd);
+  static size_t eager_bytes() {
+    static const size_t v = getenv("MLSL_NET_EAGER_KB") ? (size_t)atol(getenv("MLSL_NET_EAGER_KB")) << 10 : kEagerBytes;
+    return v;
+  }
 
   void push(int peer, const WireHdr& h, size_t& hdr_sent, const char* ptr, size_t& sent) {
     const int fd = fds_[peer];
-    while (hdr_sent < sizeof(WireHdr)) {
-      ssize_t n = send(fd, (const char*)&h + hdr_sent, sizeof(WireHdr) - hdr_sent, MSG_NOSIGNAL);
+    while (hdr_sent < sizeof(WireHdr) || sent < h.bytes) {
+      // header and payload leave in one call (one segment for small messages instead of a 16-byte packet of its own)
+      iovec iov[2];
+      int niov = 0;
+      if (hdr_sent < sizeof(WireHdr)) iov[niov++] = iovec{(char*)&h + hdr_sent, sizeof(WireHdr) - hdr_sent};
+      if (sent < h.bytes) iov[niov++] = iovec{(char*)ptr + sent, (size_t)(h.bytes - sent)};
+      msghdr mh;
+      memset(&mh, 0, sizeof(mh));
+      mh.msg_iov = iov;
+      mh.msg_iovlen = (size_t)niov;
+      ssize_t n = sendmsg(fd, &mh, MSG_NOSIGNAL);
       if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return;
       if (n < 0 && errno == EINTR) continue;
       MLSLB_ASSERT(n > 0, "send() to rank %d: %s", peer, strerror(errno));
-      hdr_sent += (size_t)n;
-    }
-    while (sent < h.bytes) {
-      ssize_t n = send(fd, ptr + sent, h.bytes - sent, MSG_NOSIGNAL);
-      if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return;
-      if (n < 0 && errno == EINTR) continue;
-      MLSLB_ASSERT(n > 0, "send() to rank %d: %s", peer, strerror(errno));
-      sent += (size_t)n;
+      size_t k = (size_t)n;
+      if (hdr_sent < sizeof(WireHdr)) {
+        const size_t h_part = std::min(k, sizeof(WireHdr) - hdr_sent);
+        hdr_sent += h_part;
+        k -= h_part;
+      }
+      sent += k;
     }
   }
 
@@ -247,11 +274,22 @@ class Mesh {
                        (unsigned long long)P.hdr.bytes, peer, it->second.bytes);
           P.dst = it->second.ptr;
           P.to_stash = false;
+        } else if (P.hdr.bytes > eager_bytes()) {
+          P.held = true;
         } else {
-          P.stash.assign(P.hdr.bytes, 0);
+          P.stash.resize(P.hdr.bytes);
           P.dst = P.stash.data();
           P.to_stash = true;
         }
+      }
+      if (P.held) {
+        auto it = P.expect.find(P.hdr.tag);
+        if (it == P.expect.end()) return completed;
+        MLSLB_ASSERT(it->second.bytes == P.hdr.bytes, "message of %llu bytes from rank %d where %zu were expected",
+                     (unsigned long long)P.hdr.bytes, peer, it->second.bytes);
+        P.dst = it->second.ptr;
+        P.to_stash = false;
+        P.held = false;
       }
       while (P.got < P.hdr.bytes) {
         ssize_t n = recv(fd, P.dst + P.got, P.hdr.bytes - P.got, 0);
@@ -347,6 +385,18 @@ class NetBackend final : public Backend {
   void execute(CommRequest& r);
 };
 
+// Receive space for the slices of a reduction: grow-only and uninitialised (a fresh std::vector would zero-fill and
+// page-fault the whole message size on every call).
+static char* net_scratch(size_t bytes) {
+  thread_local std::unique_ptr<char[]> buf;
+  thread_local size_t cap = 0;
+  if (bytes > cap) {
+    cap = bytes + bytes / 4;
+    buf.reset(new char[cap]);
+  }
+  return buf.get();
+}
+
 void NetBackend::execute(CommRequest& r) {
   const CommDesc& d = r.desc;
   ProcessGroup* gp = d.group;
@@ -390,9 +440,10 @@ void NetBackend::execute(CommRequest& r) {
     rcv.clear();
   };
   // reduce `P` equally sized slices sitting in tmp (slice p from member p; my own contribution read from `own`)
-  auto reduce_slices = [&](char* dst, const char* own, std::vector<char>& tmp, size_t elems, float scale) {
+  // (host_reduce works element by element in a fixed member order: `dst` may be the same memory as `own`)
+  auto reduce_slices = [&](char* dst, const char* own, const char* tmp, size_t elems, float scale) {
     std::vector<const void*> srcs(P);
-    for (int p = 0; p < P; ++p) srcs[p] = p == me ? (const void*)own : (const void*)(tmp.data() + (size_t)p * elems * dt);
+    for (int p = 0; p < P; ++p) srcs[p] = p == me ? (const void*)own : (const void*)(tmp + (size_t)p * elems * dt);
     if (elems) host_reduce(d.dtype, dst, srcs, elems, d.rop, scale);
   };
 
@@ -405,15 +456,38 @@ void NetBackend::execute(CommRequest& r) {
         }
       go(0);
       break;
-    case OpKind::BCAST:
-      if (me == (int)d.root) {
+    case OpKind::BCAST: {
+      const int root = (int)d.root;
+      if (n * dt < kBcastSplitBytes || P < 3) {   // small: the root sends the whole buffer to everybody
+        if (me == root) {
+          for (int p = 0; p < P; ++p)
+            if (p != me) snd.push_back(Seg{peer(p), R, n * dt});
+        } else {
+          rcv.push_back(Seg{peer(root), R, n * dt});
+        }
+        go(0);
+        break;
+      }
+      // large: the root scatters 1/P slices, then the owners all-gather them - every link carries (P-1)/P of the
+      // message instead of the root's link carrying P-1 copies
+      const size_t per = ceil_div(n, (size_t)P);
+      auto lo = [&](int p) { return std::min(n, (size_t)p * per); };
+      auto len = [&](int p) { return std::min(n, lo(p) + per) - lo(p); };
+      if (me == root) {
         for (int p = 0; p < P; ++p)
-          if (p != me) snd.push_back(Seg{peer(p), R, n * dt});
-      } else {
-        rcv.push_back(Seg{peer((int)d.root), R, n * dt});
+          if (p != me && len(p)) snd.push_back(Seg{peer(p), R + lo(p) * dt, len(p) * dt});
+      } else if (len(me)) {
+        rcv.push_back(Seg{peer(root), R + lo(me) * dt, len(me) * dt});
       }
       go(0);
+      for (int p = 0; p < P; ++p)
+        if (p != me) {
+          if (p != root && len(me)) snd.push_back(Seg{peer(p), R + lo(me) * dt, len(me) * dt});
+          if (me != root && len(p)) rcv.push_back(Seg{peer(p), R + lo(p) * dt, len(p) * dt});
+        }
+      go(1);
       break;
+    }
     case OpKind::ALLGATHER:
     case OpKind::ALLGATHERV: {
       std::vector<size_t> cnt(P, n), off(P, 0);
@@ -474,25 +548,25 @@ void NetBackend::execute(CommRequest& r) {
       go(0);
       break;
     case OpKind::REDUCE_SCATTER: {
-      std::vector<char> tmp((size_t)P * n * dt);
+      char* tmp = net_scratch((size_t)P * n * dt);
       for (int p = 0; p < P; ++p)
         if (p != me) {
           snd.push_back(Seg{peer(p), S + (size_t)p * n * dt, n * dt});
-          rcv.push_back(Seg{peer(p), tmp.data() + (size_t)p * n * dt, n * dt});
+          rcv.push_back(Seg{peer(p), tmp + (size_t)p * n * dt, n * dt});
         }
       go(0);
-      std::vector<char> own(S + (size_t)me * n * dt, S + (size_t)(me + 1) * n * dt);   // R may alias S
-      reduce_slices(R, own.data(), tmp, n, d.scale);
+      // in place (R == S) the result lands on slice 0 of the send buffer: either exactly on my input slice (me == 0) or
+      // on a slice that has already been sent and is not an input of this reduction
+      reduce_slices(R, S + (size_t)me * n * dt, tmp, n, d.scale);
       break;
     }
     case OpKind::REDUCE: {
       if (me == (int)d.root) {
-        std::vector<char> tmp((size_t)P * n * dt);
+        char* tmp = net_scratch((size_t)P * n * dt);
         for (int p = 0; p < P; ++p)
-          if (p != me) rcv.push_back(Seg{peer(p), tmp.data() + (size_t)p * n * dt, n * dt});
+          if (p != me) rcv.push_back(Seg{peer(p), tmp + (size_t)p * n * dt, n * dt});
         go(0);
-        std::vector<char> own(S, S + n * dt);
-        reduce_slices(R, own.data(), tmp, n, 1.0f);
+        reduce_slices(R, S, tmp, n, 1.0f);
       } else {
         snd.push_back(Seg{peer((int)d.root), S, n * dt});
         go(0);
@@ -500,21 +574,34 @@ void NetBackend::execute(CommRequest& r) {
       break;
     }
     case OpKind::ALLREDUCE: {
+      static const size_t one_shot = getenv("MLSL_NET_ONESHOT_KB") ? (size_t)atol(getenv("MLSL_NET_ONESHOT_KB")) << 10 : kOneShotBytes;
+      if (n * dt <= one_shot) {
+        // small message: everybody sends the whole vector to everybody and reduces locally in member order (bitwise
+        // identical everywhere) - one exchange instead of two
+        char* tmp = net_scratch((size_t)P * n * dt);
+        for (int p = 0; p < P; ++p)
+          if (p != me) {
+            snd.push_back(Seg{peer(p), S, n * dt});
+            rcv.push_back(Seg{peer(p), tmp + (size_t)p * n * dt, n * dt});
+          }
+        go(0);
+        reduce_slices(R, S, tmp, n, d.scale);
+        break;
+      }
       // reduce-scatter over ceil(n / P) sized slices, then all-gather of the reduced slices
       const size_t per = ceil_div(n, (size_t)P);
       auto lo = [&](int p) { return std::min(n, (size_t)p * per); };
       auto len = [&](int p) { return std::min(n, lo(p) + per) - lo(p); };
-      std::vector<char> tmp((size_t)P * per * dt);
+      char* tmp = net_scratch((size_t)P * per * dt);
       for (int p = 0; p < P; ++p)
         if (p != me) {
           snd.push_back(Seg{peer(p), S + lo(p) * dt, len(p) * dt});
-          rcv.push_back(Seg{peer(p), tmp.data() + (size_t)p * per * dt, len(me) * dt});
+          rcv.push_back(Seg{peer(p), tmp + (size_t)p * per * dt, len(me) * dt});
         }
       go(0);
-      std::vector<char> own(S + lo(me) * dt, S + (lo(me) + len(me)) * dt);
       {
         std::vector<const void*> srcs(P);
-        for (int p = 0; p < P; ++p) srcs[p] = p == me ? (const void*)own.data() : (const void*)(tmp.data() + (size_t)p * per * dt);
+        for (int p = 0; p < P; ++p) srcs[p] = p == me ? (const void*)(S + lo(me) * dt) : (const void*)(tmp + (size_t)p * per * dt);
         if (len(me)) host_reduce(d.dtype, R + lo(me) * dt, srcs, len(me), d.rop, d.scale);
       }
       for (int p = 0; p < P; ++p)
@@ -530,18 +617,18 @@ void NetBackend::execute(CommRequest& r) {
       const DType pdt = d.has_out_dtype ? d.out_dtype : d.dtype;
       MLSLB_ASSERT(pdt == DType::F32 || pdt == DType::BF16, "fused update: parameter dtype must be f32/bf16");
       const size_t pdts = dtype_size(pdt);
-      std::vector<char> tmp((size_t)P * n * dt);
+      char* tmp = net_scratch((size_t)P * n * dt);
       for (int p = 0; p < P; ++p)
         if (p != me) {
           snd.push_back(Seg{peer(p), S + (size_t)p * n * dt, n * dt});
-          rcv.push_back(Seg{peer(p), tmp.data() + (size_t)p * n * dt, n * dt});
+          rcv.push_back(Seg{peer(p), tmp + (size_t)p * n * dt, n * dt});
         }
       go(0);
       std::vector<float> gsum(n);
       for (size_t i = 0; i < n; ++i) {
         float a = 0.f;
         for (int p = 0; p < P; ++p) {
-          const char* sp = (p == me ? S + (size_t)me * n * dt : tmp.data() + (size_t)p * n * dt) + i * dt;
+          const char* sp = (p == me ? S + (size_t)me * n * dt : tmp + (size_t)p * n * dt) + i * dt;
           a += d.dtype == DType::F32 ? *(const float*)sp : bf16_to_f32(*(const uint16_t*)sp);
         }
         gsum[i] = a * d.scale;
