@@ -414,6 +414,53 @@ def reduce(tensor, out=None, root=0, op="sum", group="data", async_op=False, dis
     return w if async_op else w.wait()
 
 
+def gather(tensor, out=None, root=0, group="data", async_op=False, distribution=None):
+    """Distribution::Gather: rank `root` receives the concatenation of every member's `tensor` (in member order) in `out`
+    (allocated when missing); the other ranks get None."""
+    _prep(tensor)
+    d = _dist(distribution)
+    g = _group(group)
+    P, idx = d.get_process_count(g), d.get_process_idx(g)
+    raw = _movable(tensor.view(-1))
+    if idx == root:
+        if out is None:
+            out = torch.empty(P * tensor.numel(), dtype=tensor.dtype, device=tensor.device)
+        else:
+            _check_out("gather", out, P * tensor.numel(), tensor.dtype)
+        raw_out = _movable(out.view(-1))
+    else:
+        out, raw_out = None, raw          # not written on the other ranks; a valid address keeps the pointer checks quiet
+    _sync_stream()
+    req = d.gather(raw, raw.numel(), raw_out, mlsl_dtype(raw.dtype), root, g)
+    w = Work(env(), req, out, (tensor, raw, raw_out))
+    return w if async_op else w.wait()
+
+
+def scatter(tensor, out=None, root=0, group="data", async_op=False, distribution=None):
+    """Distribution::Scatter: member i receives block i of rank `root`'s `tensor` (P equal blocks).  On the other ranks
+    `tensor` only tells the block's dtype / device; pass `out` (or a tensor shaped like one block)."""
+    d = _dist(distribution)
+    g = _group(group)
+    P, idx = d.get_process_count(g), d.get_process_idx(g)
+    if idx == root:
+        _prep(tensor)
+        if tensor.numel() % P:
+            raise ValueError("scatter: %d elements cannot be split over %d ranks" % (tensor.numel(), P))
+        n = tensor.numel() // P
+    else:
+        n = out.numel() if out is not None else tensor.numel()
+    if out is None:
+        out = torch.empty(n, dtype=tensor.dtype, device=tensor.device)
+    else:
+        _check_out("scatter", out, n, tensor.dtype)
+    raw_out = _movable(out.view(-1))
+    raw_in = _movable(tensor.view(-1)) if idx == root else raw_out
+    _sync_stream()
+    req = d.scatter(raw_in, raw_out, raw_out.numel(), mlsl_dtype(raw_out.dtype), root, g)
+    w = Work(env(), req, out, (tensor, raw_in, raw_out))
+    return w if async_op else w.wait()
+
+
 def barrier(group="global", distribution=None):
     _sync_stream()
     _dist(distribution).barrier(_group(group))

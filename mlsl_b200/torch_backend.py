@@ -312,33 +312,32 @@ class MLSLProcessGroup(dist.ProcessGroup):
     def gather(self, output_tensors, input_tensors, opts=None):
         root = opts.rootRank if opts is not None else 0
         with comm.use_state(self._state):
-            fins = []
+            pending, fins = [], []
             for k, inp in enumerate(input_tensors):
-                full = self._gather_flat(inp.contiguous().view(-1))
+                flat = inp.contiguous().view(-1)
+                if self.size() == 1:
+                    output_tensors[k][0].copy_(inp)
+                    continue
+                w = comm.gather(flat, root=root, **self._kw())
+                pending.append(w)
                 if self.rank() == root:
-                    for r, o in enumerate(output_tensors[k]):
-                        o.copy_(full[r].view(o.shape))
-            return self._done([], [list(o) for o in output_tensors], fins)
+                    fins.append(lambda w=w, outs=output_tensors[k], n=flat.numel(): [
+                        o.copy_(w.result[r * n:(r + 1) * n].view(o.shape)) for r, o in enumerate(outs)])
+            return self._done(pending, [list(o) for o in output_tensors], fins)
 
     def scatter(self, output_tensors, input_tensors, opts=None):
         root = opts.rootRank if opts is not None else 0
-        P = self.size()
-        works = []
-        for k, out in enumerate(output_tensors):
-            n = out.numel()
-            if self.rank() == root:
-                src = torch.cat([t.reshape(-1) for t in input_tensors[k]])
-                splits_in = [n] * P
-            else:
-                src = torch.empty(0, dtype=out.dtype, device=out.device)
-                splits_in = [0] * P
-            flat = out if out.is_contiguous() else torch.empty_like(out, memory_format=torch.contiguous_format)
-            w = self.alltoall_base(flat.view(-1), src, [n if r == root else 0 for r in range(P)], splits_in)
-            if flat is not out:
-                works.append(self._done([w], out, [lambda out=out, flat=flat: out.copy_(flat)]))
-            else:
-                works.append(w)
-        return self._done(works, list(output_tensors))
+        with comm.use_state(self._state):
+            pending, fins = [], []
+            for k, out in enumerate(output_tensors):
+                if self.size() == 1:
+                    out.copy_(input_tensors[k][0])
+                    continue
+                o, back = self._staged(out)
+                src = torch.cat([t.reshape(-1) for t in input_tensors[k]]) if self.rank() == root else o.view(-1)
+                pending.append(comm.scatter(src, out=o.view(-1), root=root, **self._kw()))
+                fins.append(back)
+            return self._done(pending, list(output_tensors), fins)
 
     def barrier(self, opts=None):
         with comm.use_state(self._state):

@@ -328,3 +328,26 @@ def test_tensor_api_rejects_inconsistent_arguments():
 
     for bad, v in run_ranks(2, body):
         assert bad == [] and v == 2.0
+
+
+def test_gather_and_scatter_tensor_api():
+    """mlsl.gather / mlsl.scatter (Distribution::Gather / Scatter) for every root, a dtype the library reduces and one that
+    only travels as bytes."""
+    def body(r, mlsl):
+        P = mlsl.world_size()
+        for dtype in (torch.float32, torch.int64):
+            for root in range(P):
+                mine = (torch.arange(5) + 10 * r).to(dtype)
+                got = mlsl.gather(mine, root=root, group="global")
+                if r == root:
+                    assert torch.equal(got, torch.cat([(torch.arange(5) + 10 * p).to(dtype) for p in range(P)]))
+                else:
+                    assert got is None
+                whole = (torch.arange(3 * P) + 100 * root).to(dtype)
+                part = mlsl.scatter(whole if r == root else torch.empty(3, dtype=dtype), root=root, group="global")
+                assert torch.equal(part, whole[3 * r:3 * r + 3]), (r, root, part)
+        with pytest.raises(ValueError):
+            mlsl.scatter(torch.zeros(3 * P + 1), root=r, group="global") if P > 1 else (_ for _ in ()).throw(ValueError())
+        return True
+
+    assert run_ranks(3, body) == [True] * 3
