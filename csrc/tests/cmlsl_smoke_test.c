@@ -103,6 +103,37 @@ int main(int argc, char** argv) {
       if (fabsf(g[i] - (float)(size * i)) > 1e-3f) fails++;
   }
   CHECK(mlsl_environment_delete_session(env, session));
+
+  /* [ext] a group made by its members only: ranks 0 and size-1 exchange their group-state words (here through a byte
+   * all-gather on the world - any rendezvous will do) and build a two-rank distribution; the other ranks do nothing */
+  if (size >= 2) {
+    unsigned long long mine[2], *all;
+    mlsl_comm_req req;
+    CHECK(mlsl_environment_alloc(env, 2 * sizeof(unsigned long long) * size, 64, (void**)&all));
+    CHECK(mlsl_environment_get_group_state(env, &mine[0], &mine[1]));
+    CHECK(mlsl_distribution_all_gather(dist, mine, sizeof(mine), all, DT_BYTE, GT_GLOBAL, &req));
+    CHECK(mlsl_environment_wait(env, req));
+    if (rank == 0 || rank == size - 1) {
+      size_t members[2] = {0, size - 1}, cnt = 0, idx = 99;
+      unsigned long long rows = all[0] | all[2 * (size - 1)];
+      unsigned long long mark = all[1] > all[2 * (size - 1) + 1] ? all[1] : all[2 * (size - 1) + 1];
+      mlsl_distribution pair;
+      float* v;
+      CHECK(mlsl_environment_create_distribution_from_ranks(env, members, 2, rows, mark, &pair));
+      CHECK(mlsl_distribution_get_process_count(pair, GT_DATA, &cnt));
+      CHECK(mlsl_distribution_get_process_idx(pair, GT_DATA, &idx));
+      if (cnt != 2 || idx != (rank == 0 ? 0u : 1u)) fails++;
+      CHECK(mlsl_environment_alloc(env, 16 * sizeof(float), 64, (void**)&v));
+      for (i = 0; i < 16; ++i) v[i] = (float)(rank + 1);
+      CHECK(mlsl_distribution_all_reduce(pair, v, v, 16, DT_FLOAT, RT_SUM, GT_DATA, &req));
+      CHECK(mlsl_environment_wait(env, req));
+      for (i = 0; i < 16; ++i)
+        if (fabsf(v[i] - (float)(1 + size)) > 1e-5f) fails++;
+      CHECK(mlsl_environment_free(env, v));
+      CHECK(mlsl_environment_delete_distribution(env, pair));
+    }
+    CHECK(mlsl_environment_free(env, all));
+  }
   CHECK(mlsl_environment_free(env, a));
   CHECK(mlsl_environment_free(env, b));
   CHECK(mlsl_environment_delete_distribution(env, dist));
