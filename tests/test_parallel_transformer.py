@@ -11,7 +11,7 @@ from conftest import run_ranks
 D, H, FF, M = 32, 4, 64, 16
 
 
-def _full():
+def _full(D=D, H=H, FF=FF, M=M):
     g = torch.Generator().manual_seed(17)
     r = lambda *s: torch.randn(*s, generator=g)
     return dict(x=r(M, D), t=r(M, D), ln1w=1 + 0.1 * r(D), ln1b=0.1 * r(D), ln2w=1 + 0.1 * r(D), ln2b=0.1 * r(D),
@@ -20,9 +20,12 @@ def _full():
                 w2=r(D, FF) / math.sqrt(FF), b2=0.1 * r(D))
 
 
-def _reference():
-    p = {k: v.clone().requires_grad_(True) for k, v in _full().items() if k != "t"}
-    t = _full()["t"]
+def _reference(D=D, H=H, FF=FF, M=M, cast=None):
+    full = _full(D, H, FF, M)
+    if cast is not None:      # what a reduced-precision run starts from
+        full = {k: v.to(cast).float() for k, v in full.items()}
+    p = {k: v.clone().requires_grad_(True) for k, v in full.items() if k != "t"}
+    t = full["t"]
     hd = D // H
     x = p["x"]
     h = torch.nn.functional.layer_norm(x, (D,), p["ln1w"], p["ln1b"])

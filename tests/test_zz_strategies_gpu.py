@@ -79,3 +79,40 @@ def test_expert_parallel_device():
         assert torch.allclose(gx, want[r][1], atol=1e-3, rtol=1e-2)
         assert torch.allclose(gw1, w1.grad[r * El:(r + 1) * El], atol=1e-3, rtol=1e-2)
         assert torch.allclose(gw2, w2.grad[r * El:(r + 1) * El], atol=1e-3, rtol=1e-2)
+
+
+def test_parallel_transformer_block_device():
+    """bf16 block on the fused kernels' shapes (GEMM + reduce-scatter always; all-gather + GEMM with MLSL_AG_GEMM=1)."""
+    from test_parallel_transformer import _full, _reference
+    D, H, FF, M, world = 512, 8, 2048, 512, 2
+    want_y, want = _reference(D, H, FF, M, cast=torch.bfloat16)
+
+    def body(r, mlsl):
+        from mlsl_b200.models.gpt import ParallelTransformerBlock
+        f = {k: v.cuda() for k, v in _full(D, H, FF, M).items()}
+        dist = mlsl.env().create_distribution(1, world)
+        with _lock:
+            blk = ParallelTransformerBlock(D, H, d_ff=FF, distribution=dist, group="model", dtype=torch.bfloat16, device="cuda")
+        dl, fl, rows = D // world, FF // world, M // world
+        sl, fs, rs = slice(r * dl, (r + 1) * dl), slice(r * fl, (r + 1) * fl), slice(r * rows, (r + 1) * rows)
+        with torch.no_grad():
+            blk.ln1.weight.copy_(f["ln1w"]), blk.ln1.bias.copy_(f["ln1b"])
+            blk.ln2.weight.copy_(f["ln2w"]), blk.ln2.bias.copy_(f["ln2b"])
+            blk.qkv.weight.copy_(torch.cat([f["wq"][sl], f["wk"][sl], f["wv"][sl]]))
+            blk.qkv.bias.copy_(torch.cat([f["bq"][sl], f["bk"][sl], f["bv"][sl]]))
+            blk.proj.weight.copy_(f["wo"][:, sl]), blk.proj.bias.copy_(f["bo"])
+            blk.fc1.weight.copy_(f["w1"][fs]), blk.fc1.bias.copy_(f["b1"][fs])
+            blk.fc2.weight.copy_(f["w2"][:, fs]), blk.fc2.bias.copy_(f["b2"])
+        x = f["x"][rs].to(torch.bfloat16).requires_grad_(True)
+        y = blk(x)
+        ((y.float() - f["t"][rs]) ** 2).sum().backward()
+        torch.cuda.current_stream().synchronize()
+        mlsl.env().delete_distribution(dist)
+        return y.detach().float().cpu(), x.grad.float().cpu(), blk.fc2.weight.grad.float().cpu()
+
+    res = run_ranks(world, body, backend="cuda", env=ENV)
+    for r, (y, gx, gw2) in enumerate(res):
+        rows, fl = M // world, FF // world
+        for got, ref in ((y, want_y[r * rows:(r + 1) * rows]), (gx, want["x"][r * rows:(r + 1) * rows]),
+                         (gw2, want["w2"][:, r * fl:(r + 1) * fl])):
+            assert (got - ref).abs().max().item() <= 6e-2 * max(1.0, ref.abs().max().item())
