@@ -3,6 +3,7 @@
 //
 //   mlslrun -n N [-g] [-e NAME=VALUE]... [--timeout SEC] [--bind core|none] program [args...]
 //   mlslrun -n N --nnodes M --node-rank I --master-addr HOST [--master-port P] program [args...]     (run on every node)
+//   mlslrun -n N --hosts H0,H1,... [--rsh "ssh -o BatchMode=yes"] program [args...]                   (run once, anywhere)
 //
 // Starts N copies of `program` with MLSL_RANK / MLSL_WORLD_SIZE / MLSL_LOCAL_RANK and a fresh MLSL_JOB_ID
 // (plus the torchrun-style RANK / WORLD_SIZE / LOCAL_RANK), -g additionally pins rank r to GPU r through
@@ -12,6 +13,9 @@
 // With --nnodes the job spans M nodes: this launcher starts the N local ranks I*N .. I*N+N-1 of a world of M*N, points
 // them at rank 0's control server (MLSL_MASTER_ADDR / MLSL_MASTER_PORT) and selects the net (TCP) backend unless
 // MLSL_BACKEND says otherwise.
+// With --hosts the launcher is the head of the job (hydra's -hosts): it starts `mlslrun --nnodes M --node-rank I ...` on
+// every listed host through the remote shell (--rsh / MLSL_RSH, default ssh; the command runs in the current directory,
+// MLSL_* variables and every -e are forwarded), H0 hosts the control server, and the first node that fails stops the rest.
 // The first non-zero exit (or the timeout) terminates the whole process group and
 // becomes the launcher's exit code - fail-fast like the reference's abort-on-assert.
 #include <sched.h>
@@ -39,11 +43,104 @@ static void on_signal(int) {
   _exit(130);
 }
 
+static std::string sh_quote(const std::string& a) {
+  std::string q = "'";
+  for (char c : a) {
+    if (c == '\'') q += "'\\''";
+    else q += c;
+  }
+  return q + "'";
+}
+
+extern char** environ;
+
+// head of a multi-host job: one remote mlslrun per host
+static int run_hosts(const std::vector<std::string>& hosts, const std::string& rsh, int n, bool gpus, bool bind, int timeout,
+                     std::string master_port, const std::vector<std::string>& envs, char** prog) {
+  char self[4096];
+  ssize_t len = readlink("/proc/self/exe", self, sizeof(self) - 1);
+  if (len <= 0) {
+    perror("readlink(/proc/self/exe)");
+    return 1;
+  }
+  self[len] = 0;
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof(cwd))) cwd[0] = 0;
+  if (master_port.empty()) {
+    timeval tv;
+    gettimeofday(&tv, nullptr);
+    master_port = std::to_string(20000 + (int)((tv.tv_usec ^ getpid()) % 30000));
+  }
+  std::vector<std::string> rsh_argv;   // the remote shell command may carry its own options
+  {
+    size_t b = 0;
+    while (b < rsh.size()) {
+      size_t e = rsh.find(' ', b);
+      if (e == std::string::npos) e = rsh.size();
+      if (e > b) rsh_argv.push_back(rsh.substr(b, e - b));
+      b = e + 1;
+    }
+  }
+  g_kids.assign(hosts.size(), -1);
+  for (size_t h = 0; h < hosts.size(); ++h) {
+    std::string cmd = cwd[0] ? "cd " + sh_quote(cwd) + " && " : std::string();
+    cmd += "exec " + sh_quote(self) + " -n " + std::to_string(n) + " --nnodes " + std::to_string(hosts.size()) + " --node-rank " +
+           std::to_string(h) + " --master-addr " + sh_quote(hosts[0]) + " --master-port " + master_port;
+    if (gpus) cmd += " -g";
+    if (!bind) cmd += " --bind none";
+    if (timeout > 0) cmd += " --timeout " + std::to_string(timeout);
+    for (char** e = environ; *e; ++e)
+      if (!strncmp(*e, "MLSL_", 5) && strncmp(*e, "MLSL_RANK=", 10) && strncmp(*e, "MLSL_JOB_ID=", 12)) cmd += " -e " + sh_quote(*e);
+    for (const std::string& e : envs) cmd += " -e " + sh_quote(e);
+    cmd += " --";
+    for (char** a = prog; *a; ++a) cmd += " " + sh_quote(*a);
+    pid_t p = fork();
+    if (p < 0) {
+      perror("fork");
+      kill_all(SIGKILL);
+      return 1;
+    }
+    if (p == 0) {
+      std::vector<char*> av;
+      for (std::string& a : rsh_argv) av.push_back(&a[0]);
+      av.push_back(const_cast<char*>(hosts[h].c_str()));
+      av.push_back(&cmd[0]);
+      av.push_back(nullptr);
+      execvp(av[0], av.data());
+      fprintf(stderr, "mlslrun: cannot start the remote shell '%s': %s\n", av[0], strerror(errno));
+      _exit(127);
+    }
+    g_kids[h] = p;
+  }
+  int rc = 0;
+  size_t left = hosts.size();
+  while (left) {
+    int st = 0;
+    pid_t p = wait(&st);
+    if (p < 0) {
+      if (errno == EINTR) continue;
+      break;
+    }
+    for (size_t h = 0; h < g_kids.size(); ++h)
+      if (g_kids[h] == p) {
+        g_kids[h] = -1;
+        --left;
+        const int code = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + WTERMSIG(st);
+        if (code != 0 && rc == 0) {
+          rc = code;
+          fprintf(stderr, "mlslrun: node %zu (%s) exited with code %d, stopping the job\n", h, hosts[h].c_str(), code);
+          kill_all(SIGTERM);
+        }
+      }
+  }
+  return rc;
+}
+
 int main(int argc, char** argv) {
   int n = 1, timeout = 0;
   bool gpus = false;
   int nnodes = 1, node_rank = 0;
-  std::string master_addr, master_port;
+  std::string master_addr, master_port, hosts_arg, rsh = getenv("MLSL_RSH") ? getenv("MLSL_RSH") : "ssh";
   bool bind = !(getenv("MLSL_BIND") && atoi(getenv("MLSL_BIND")) == 0);
   std::vector<std::string> envs;
   int i = 1;
@@ -57,12 +154,33 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--master-addr") && i + 1 < argc) master_addr = argv[++i];
     else if (!strcmp(argv[i], "--master-port") && i + 1 < argc) master_port = argv[++i];
     else if (!strcmp(argv[i], "--bind") && i + 1 < argc) bind = strcmp(argv[++i], "none") != 0;
+    else if (!strcmp(argv[i], "--hosts") && i + 1 < argc) hosts_arg = argv[++i];
+    else if (!strcmp(argv[i], "--rsh") && i + 1 < argc) rsh = argv[++i];
     else if (!strcmp(argv[i], "--")) { ++i; break; }
     else break;
   }
   if (i >= argc || n < 1 || nnodes < 1 || node_rank < 0 || node_rank >= nnodes) {
-    fprintf(stderr, "usage: mlslrun -n N [-g] [-e NAME=VALUE]... [--timeout SEC] [--bind core|none] program [args...]\n");
+    fprintf(stderr, "usage: mlslrun -n N [-g] [-e NAME=VALUE]... [--timeout SEC] [--bind core|none] program [args...]\n"
+                    "       mlslrun -n N --nnodes M --node-rank I --master-addr HOST [--master-port P] program [args...]\n"
+                    "       mlslrun -n N --hosts H0,H1,... [--rsh CMD] program [args...]\n");
     return 2;
+  }
+  if (!hosts_arg.empty()) {
+    std::vector<std::string> hosts;
+    size_t b = 0;
+    while (b <= hosts_arg.size()) {
+      size_t e = hosts_arg.find(',', b);
+      if (e == std::string::npos) e = hosts_arg.size();
+      if (e > b) hosts.push_back(hosts_arg.substr(b, e - b));
+      b = e + 1;
+    }
+    if (hosts.empty()) {
+      fprintf(stderr, "mlslrun: --hosts needs a comma separated list of host names\n");
+      return 2;
+    }
+    signal(SIGINT, on_signal);
+    signal(SIGTERM, on_signal);
+    return run_hosts(hosts, rsh, n, gpus, bind, timeout, master_port, envs, argv + i);
   }
   timeval tv;
   gettimeofday(&tv, nullptr);

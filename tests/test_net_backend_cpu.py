@@ -62,3 +62,24 @@ def test_torch_distributed_backend_across_nodes(tmp_path):
     "nodes": the same worker as tests/test_torch_backend_cpu.py, traffic on the TCP mesh."""
     rcs, out = _launch(2, 2, [sys.executable, os.path.join(ROOT, "tests", "torch_backend_worker.py"), str(tmp_path / "store")])
     assert all(rc == 0 for rc in rcs) and "torch backend OK" in out, out[-3000:]
+
+
+def test_hosts_launcher_starts_every_node_through_the_remote_shell():
+    """`mlslrun --hosts a,b` is the head of the job (mpiexec.hydra -hosts): it starts one mlslrun per host through the remote
+    shell - here a stand-in for ssh that runs the command locally - and forwards -e variables; a failing node stops the job."""
+    rsh = os.path.join(ROOT, "tests", "fake_rsh.sh")
+    env = dict(os.environ, MLSL_WATCHDOG_SEC="60")
+    env.pop("MLSL_BACKEND", None)
+    p = subprocess.run([MLSLRUN, "-n", "2", "--hosts", "127.0.0.1,127.0.0.1", "--rsh", rsh, "--timeout", "120", "-e", "MARK=from head",
+                        sys.executable, "-c",
+                        "import os, sys; sys.path.insert(0, %r); import torch, mlsl_b200 as mlsl; mlsl.init(); t = torch.ones(3); "
+                        "mlsl.allreduce(t); sys.stdout.write('rank %%d of %%d sum %%d %%s %%s\\n' %% (mlsl.rank(), mlsl.world_size(), int(t[0]), "
+                        "os.environ['MARK'], mlsl.env().get_backend_name())); sys.stdout.flush(); mlsl.finalize()" % ROOT],
+                       cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=200)
+    assert p.returncode == 0, p.stdout[-2000:]
+    for r in range(4):
+        assert "rank %d of 4 sum 4 from head net" % r in p.stdout, p.stdout[-2000:]
+    bad = subprocess.run([MLSLRUN, "-n", "1", "--hosts", "127.0.0.1,127.0.0.1", "--rsh", rsh, "--timeout", "60", sys.executable, "-c",
+                          "import os, sys, time; sys.exit(5) if os.environ['RANK'] == '1' else time.sleep(30)"],
+                         cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=100)
+    assert bad.returncode == 5 and "stopping the job" in bad.stdout, bad.stdout[-1500:]
