@@ -37,6 +37,7 @@ else
   step torch_bench_mlsl 300 $TR --master-port 29615 bench/torch_backend_bench.py --backend mlsl --device cuda --max-mb 256
   step torch_bench_nccl 300 $TR --master-port 29616 bench/torch_backend_bench.py --backend nccl --device cuda --max-mb 256
   step pipeline 200 $TR --master-port 29617 examples/train_pipeline_parallel.py --stages 2
+  step collectives_vs_nccl 400 $TR --master-port 29618 bench/collectives_bench.py --max-mb 256
   step example_cuda 120 bin/mlslrun -n $N bin/mlsl_example_cuda
   if [ "$N" -ge 4 ]; then   # two "nodes" of N/2 GPUs each on one box: two-level collectives with NCCL between them
     H=$((N / 2))
