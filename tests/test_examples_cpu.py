@@ -60,3 +60,8 @@ def test_torch_ddp_example():
 def test_pipeline_parallel_training_example():
     out = _run([MLSLRUN, "-n", "4", sys.executable, "examples/train_pipeline_parallel.py", "--stages", "2"])
     assert out.count("PASSED") == 4 and "FAILED" not in out
+
+
+def test_parallel_transformer_training_example():
+    out = _run([MLSLRUN, "-n", "4", sys.executable, "examples/train_parallel_transformer.py", "--model-parts", "2"])
+    assert out.count("PASSED") == 4 and "FAILED" not in out
