@@ -35,6 +35,7 @@ endif
 
 # the host reduction loops are written to be auto-vectorised
 $(BUILD)/core/host_backend.o: CXXFLAGS += -O3
+$(BUILD)/core/net_backend.o: CXXFLAGS += -O3
 
 TOOLS := bin/mlslrun
 ifndef NO_CUDA

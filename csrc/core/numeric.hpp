@@ -73,7 +73,8 @@ inline uint16_t f32_to_f16(float f) {
 }
 
 // OCP FP8 E4M3 (finite-only variant "e4m3fn": max 448, no infinities, NaN = 0x7f/0xff), satfinite conversion.
-inline float e4m3_to_f32(uint8_t v) {
+// definition of the format (slow: libm calls); the hot paths use the table / bit-twiddling versions below
+inline float e4m3_to_f32_ref(uint8_t v) {
   uint32_t sign = v >> 7;
   uint32_t exp = (v >> 3) & 0xfu;
   uint32_t man = v & 0x7u;
@@ -87,7 +88,7 @@ inline float e4m3_to_f32(uint8_t v) {
   }
   return sign ? -r : r;
 }
-inline uint8_t f32_to_e4m3(float f) {
+inline uint8_t f32_to_e4m3_ref(float f) {
   uint8_t sign = std::signbit(f) ? 0x80 : 0;
   float a = fabsf(f);
   if (std::isnan(f)) return (uint8_t)(sign | 0x7f);
@@ -114,6 +115,37 @@ inline uint8_t f32_to_e4m3(float f) {
   }
   if (be > 15 || (be == 15 && mi == 7)) return (uint8_t)(sign | 0x7e);
   return (uint8_t)(sign | (be << 3) | mi);
+}
+
+struct E4M3Table {
+  float v[256];
+  E4M3Table() {
+    for (int i = 0; i < 256; ++i) v[i] = e4m3_to_f32_ref((uint8_t)i);
+  }
+};
+inline const E4M3Table kE4M3Table{};   // built while the library loads; a function-local static would cost a guard per call
+inline float e4m3_to_f32(uint8_t v) { return kE4M3Table.v[v]; }
+// Round-to-nearest-even conversion on the bit pattern; identical to f32_to_e4m3_ref for every float
+// (csrc/tests/quant_codec_check.cpp compares all 2^32 inputs).
+inline uint8_t f32_to_e4m3(float f) {
+  // straight-line code (selects, no branches): loops over it vectorise
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 24) & 0x80u;
+  u &= 0x7fffffffu;
+  float a;
+  memcpy(&a, &u, 4);
+  const float t = a * 512.0f + 12582912.0f;              // |f| < 2^-6: subnormal grid, quantum 2^-9; 1.5 * 2^23 makes the
+  uint32_t ti;                                            // sum round to an integer (RNE): 0 .. 8, 8 = smallest normal
+  memcpy(&ti, &t, 4);
+  const uint32_t sub = ti - 0x4b400000u;
+  const uint32_t r = u + 0x7ffffu + ((u >> 20) & 1u);     // RNE at bit 20: 3 mantissa bits survive
+  uint32_t code = (r >> 20) - 0x3c0u;                     // (exponent - 120) << 3 | mantissa
+  code = code > 0x7eu ? 0x7eu : code;                     // also covers |f| >= 448: saturate to the largest finite value
+  code = u < 0x3c800000u ? sub : code;
+  code = u >= 0x43e00000u ? 0x7eu : code;
+  code = u > 0x7f800000u ? 0x7fu : code;                  // NaN
+  return (uint8_t)(sign | code);
 }
 
 }  // namespace mlslb

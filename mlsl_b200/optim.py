@@ -255,9 +255,15 @@ class DistributedOptimizer:
             self.local.load_state_dict(copy.deepcopy(sd["local"]))   # torch keeps references when dtype/device match
 
     def close(self):
+        """Release the session and the buckets.  The parameters get storage of their own back (they were views into the
+        buckets), so the model stays usable - e.g. for another optimizer."""
         for h in self._hooks:
             h.remove()
         self.env.delete_session(self.session)
+        with torch.no_grad():
+            for p in self.params:
+                p.data = p.data.clone()
+                p.grad = None
         for b in self.buckets:
             comm.free_tensor(b.grad)
             comm.free_tensor(b.flat)

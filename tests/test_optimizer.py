@@ -203,3 +203,34 @@ def test_gradient_accumulation_with_no_sync(mode):
     ref = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
     for o in outs:
         assert torch.allclose(o, ref, rtol=2e-4, atol=2e-5), (o - ref).abs().max()
+
+
+def test_model_stays_usable_after_close():
+    """close() frees the buckets the parameters were views of: they must own their values again, and a second optimizer on
+    the same model must continue from them."""
+    def body(r, mlsl):
+        m = _model()
+        opt = mlsl.DistributedOptimizer(m.parameters(), lr=0.05, mode="fused", bucket_mb=0.004)
+        x, y = _batch(r, 0)
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(m(x), y).backward()
+        opt.step()
+        before = torch.cat([p.detach().reshape(-1).clone() for p in m.parameters()])
+        opt.close()
+        junk = [mlsl.alloc_tensor(4096, torch.float32) for _ in range(8)]      # recycle the freed blocks
+        for j in junk:
+            j.fill_(123.0)
+        after = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+        assert torch.equal(before, after) and all(p.grad is None for p in m.parameters())
+        opt2 = mlsl.DistributedOptimizer(m.parameters(), lr=0.05, mode="allreduce", bucket_mb=0.004)
+        opt2.zero_grad()
+        torch.nn.functional.mse_loss(m(x), y).backward()
+        opt2.step()
+        out = torch.cat([p.detach().reshape(-1).clone() for p in m.parameters()])
+        opt2.close()
+        for j in junk:
+            mlsl.free_tensor(j)
+        return out
+
+    outs = run_ranks(2, body)
+    assert torch.equal(outs[0], outs[1]) and torch.isfinite(outs[0]).all()
