@@ -41,7 +41,7 @@ TOOLS := bin/mlslrun
 ifndef NO_CUDA
 CUDA_EXAMPLES := bin/mlsl_example_cuda
 endif
-TESTS := $(CUDA_EXAMPLES) bin/libmlsl_quant_sample.so bin/mlsl_functional_test bin/cmlsl_smoke_test bin/cmlsl_functional_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
+TESTS := $(CUDA_EXAMPLES) bin/libmlsl_quant_sample.so bin/quant_codec_check bin/mlsl_functional_test bin/cmlsl_smoke_test bin/cmlsl_functional_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
 
 all: $(LIB) $(TOOLS) $(TESTS)
 

@@ -351,3 +351,13 @@ def test_gather_and_scatter_tensor_api():
         return True
 
     assert run_ranks(3, body) == [True] * 3
+
+
+def test_fp8_codec_matches_its_definition():
+    """The table / bit-pattern FP8 (E4M3) codec of the quantised all-reduce against the libm definition on every 1021st
+    float bit pattern (the whole 2^32 range takes 15 s: bin/quant_codec_check 1)."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    p = subprocess.run([os.path.join(ROOT, "bin", "quant_codec_check"), "1021"], stdout=subprocess.PIPE, text=True, timeout=120)
+    assert p.returncode == 0 and " 0 mismatches" in p.stdout, p.stdout
