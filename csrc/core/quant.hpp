@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 
 #include "numeric.hpp"
 
@@ -20,9 +21,18 @@ constexpr size_t kQuantBlockBytes = kQuantBlock + 4;   // payload + fp32 scale
 
 // Quantise one block (exactly kQuantBlock floats, zero padded by the caller); returns the scale.
 inline float quant_block(const float* v, uint8_t* q) {
-  float amax = 0.f;
-  for (int i = 0; i < kQuantBlock; ++i) amax = fmaxf(amax, fabsf(v[i]));
-  if (!(amax > 0.f) || !std::isfinite(amax)) {
+  // largest magnitude through the bit patterns (an integer max reduction vectorises; NaN / inf patterns sort above every
+  // finite value, so one comparison afterwards finds them)
+  uint32_t umax = 0;
+  for (int i = 0; i < kQuantBlock; ++i) {
+    uint32_t u;
+    memcpy(&u, &v[i], 4);
+    u &= 0x7fffffffu;
+    umax = u > umax ? u : umax;
+  }
+  float amax;
+  memcpy(&amax, &umax, 4);
+  if (umax == 0 || umax >= 0x7f800000u) {
     for (int i = 0; i < kQuantBlock; ++i) q[i] = 0;
     return 0.f;
   }

@@ -11,7 +11,11 @@ int main(int argc, char** argv) {
   unsigned long long bad = 0, n = 0;
   for (int i = 0; i < 256; ++i) {
     const float a = mlslb::e4m3_to_f32((uint8_t)i), b = mlslb::e4m3_to_f32_ref((uint8_t)i);
-    if (memcmp(&a, &b, 4) != 0 && !(a != a && b != b)) ++bad;
+    const float t = mlslb::kE4M3Table.v[i];
+    if ((memcmp(&a, &b, 4) != 0 && !(a != a && b != b)) || (memcmp(&t, &b, 4) != 0 && !(t != t && b != b))) {
+      printf("decode mismatch at code %02x: %g vs %g\n", i, a, b);
+      ++bad;
+    }
   }
   for (unsigned long long u = 0; u <= 0xffffffffull; u += stride, ++n) {
     const uint32_t bits = (uint32_t)u;
