@@ -154,6 +154,11 @@ class Mesh {
         ++pending_in;
       }
     }
+    // start with the next rank, not with rank 0: if everybody served the peers in index order, all first messages would
+    // converge on the same receiver
+    std::sort(outs.begin(), outs.end(), [&](const Out& a, const Out& b) {
+      return (a.peer - rank_ + world_) % world_ < (b.peer - rank_ + world_) % world_;
+    });
     size_t pending_out = outs.size();
     const uint64_t t0 = now_ns();
     // first try without sleeping: small messages usually go out and come in at once
