@@ -328,6 +328,27 @@ def allgather(tensor, out=None, group="data", async_op=False, distribution=None)
     return w if async_op else w.wait()
 
 
+def allgatherv(tensor, recv_counts, out=None, group="data", async_op=False, distribution=None):
+    """Distribution::AllGatherv: member p contributes `recv_counts[p]` elements (this rank: all of `tensor`); returns the
+    concatenation in member order."""
+    _prep(tensor)
+    d = _dist(distribution)
+    g = _group(group)
+    P, idx = d.get_process_count(g), d.get_process_idx(g)
+    recv_counts = [int(c) for c in recv_counts]
+    if len(recv_counts) != P or recv_counts[idx] != tensor.numel():
+        raise ValueError("allgatherv: need %d counts and counts[%d] == %d (this rank's elements)" % (P, idx, tensor.numel()))
+    total = sum(recv_counts)
+    if out is None:
+        out = torch.empty(max(total, 1), dtype=tensor.dtype, device=tensor.device)[:total]
+    else:
+        _check_out("allgatherv", out, total, tensor.dtype)
+    _sync_stream()
+    req = d.all_gatherv(tensor, tensor.numel(), out, recv_counts, mlsl_dtype(tensor.dtype), g)
+    w = Work(env(), req, out, (tensor, out))
+    return w if async_op else w.wait()
+
+
 def alltoall(tensor, out=None, group="data", async_op=False, distribution=None):
     _prep(tensor)
     d = _dist(distribution)

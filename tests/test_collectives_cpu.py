@@ -361,3 +361,17 @@ def test_fp8_codec_matches_its_definition():
     from conftest import ROOT
     p = subprocess.run([os.path.join(ROOT, "bin", "quant_codec_check"), "1021"], stdout=subprocess.PIPE, text=True, timeout=120)
     assert p.returncode == 0 and " 0 mismatches" in p.stdout, p.stdout
+
+
+def test_allgatherv_tensor_api():
+    def body(r, mlsl):
+        P = mlsl.world_size()
+        counts = [(p * 3) % 5 + 1 for p in range(P)]
+        mine = torch.full((counts[r],), float(r + 1))
+        got = mlsl.allgatherv(mine, counts, group="global")
+        assert torch.equal(got, torch.cat([torch.full((counts[p],), float(p + 1)) for p in range(P)]))
+        with pytest.raises(ValueError):
+            mlsl.allgatherv(mine, counts[:-1], group="global")
+        return True
+
+    assert run_ranks(4, body) == [True] * 4
