@@ -67,7 +67,7 @@ def test_torch_distributed_backend_across_nodes(tmp_path):
 def test_hosts_launcher_starts_every_node_through_the_remote_shell():
     """`mlslrun --hosts a,b` is the head of the job (mpiexec.hydra -hosts): it starts one mlslrun per host through the remote
     shell - here a stand-in for ssh that runs the command locally - and forwards -e variables; a failing node stops the job."""
-    rsh = os.path.join(ROOT, "tests", "fake_rsh.sh")
+    rsh = "sh " + os.path.join(ROOT, "tests", "fake_rsh.sh")     # a remote shell command with an argument of its own
     env = dict(os.environ, MLSL_WATCHDOG_SEC="60")
     env.pop("MLSL_BACKEND", None)
     p = subprocess.run([MLSLRUN, "-n", "2", "--hosts", "127.0.0.1,127.0.0.1", "--rsh", rsh, "--timeout", "120", "-e", "MARK=from head",
