@@ -102,7 +102,7 @@ class CudaBackend final : public Backend {
     // fresh row: zero my pads and ticket counters, then make sure every member has done so before anyone signals
     // (on the row's own stream: every extra stream is one more hardware queue that loop-back ranks sharing a GPU
     // compete for, and two spinning kernels falsely serialised on one queue dead-lock each other)
-    cudaStream_t zs = stream_for(g.row, 0);
+    cudaStream_t zs = inline_stream_ && user_stream_set_ ? user_stream_ : stream_for(g.row, 0);
     MLSLB_CUDA(cudaMemsetAsync(slab_ + (size_t)g.row * 2 * kPadRowBytes, 0, 2 * kPadRowBytes, zs));
     MLSLB_CUDA(cudaMemsetAsync(slab_ + kSeqBase + (size_t)g.row * 2 * kSeqRowBytes, 0, 2 * kSeqRowBytes, zs));
     if (g.row < kLLRows) MLSLB_CUDA(cudaMemsetAsync(slab_ + kLLBase + (size_t)g.row * kLLRowBytes, 0, kLLRowBytes, zs));
@@ -114,10 +114,31 @@ class CudaBackend final : public Backend {
     if (r.backend_state) return;
     r.backend_state = new CudaReqState();   // events are created on first use (none at all in inline-stream mode)
   }
+  // Events come from a pool filled at start-up and are never destroyed before finalize: cuEventCreate / cuEventDestroy
+  // need the writer side of a driver lock that a host thread sitting in a pageable device-to-host copy behind a
+  // spinning kernel holds for the whole copy (csrc/tools/probe_blocking.cu) - with loop-back ranks that is a dead-lock.
+  cudaEvent_t take_event() {
+    {
+      std::lock_guard<std::mutex> g(park_mu_);
+      if (!event_pool_.empty()) {
+        cudaEvent_t ev = event_pool_.back();
+        event_pool_.pop_back();
+        return ev;
+      }
+    }
+    cudaEvent_t ev = nullptr;
+    MLSLB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    return ev;
+  }
+  void give_event(cudaEvent_t ev) {
+    if (!ev) return;
+    std::lock_guard<std::mutex> g(park_mu_);
+    event_pool_.push_back(ev);
+  }
   void ensure_events(CudaReqState* st) {
     if (st->done) return;
-    MLSLB_CUDA(cudaEventCreateWithFlags(&st->ready, cudaEventDisableTiming));
-    MLSLB_CUDA(cudaEventCreateWithFlags(&st->done, cudaEventDisableTiming));
+    st->ready = take_event();
+    st->done = take_event();
   }
   // inline-stream + stream-ordered wait: the collective is just a kernel on the user's stream, nothing to track
   bool eventless() const { return inline_stream_ && stream_wait_; }
@@ -138,8 +159,8 @@ class CudaBackend final : public Backend {
       if (st->stream) park_stages(st);
       else drop_stages(st, false);
     }
-    if (st->ready) cudaEventDestroy(st->ready);
-    if (st->done) cudaEventDestroy(st->done);
+    give_event(st->ready);
+    give_event(st->done);
     delete st;
     r.backend_state = nullptr;
   }
@@ -185,6 +206,21 @@ class CudaBackend final : public Backend {
     finish(r, st);
   }
 
+  // A device-to-host copy into PAGEABLE memory blocks the calling thread until the stream has drained and holds a driver
+  // lock all that time (no event / stream / allocation call of any other thread gets through, probe_blocking.cu).
+  // Drain the stream first - the call blocks either way - so the lock is only held for the copy itself.
+  bool is_pageable_host(const void* p) const {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+  }
+  void copy_out(const StageBuf& sb, cudaStream_t s) {
+    if (is_pageable_host(sb.user)) MLSLB_CUDA(cudaStreamSynchronize(s));
+    MLSLB_CUDA(cudaMemcpyAsync(sb.user, sb.slab, sb.bytes, cudaMemcpyDefault, s));
+  }
   bool is_device_pointer(const void* p) const override {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -235,6 +271,14 @@ class CudaBackend final : public Backend {
     };
     cudaDeviceSynchronize();
     sweep_parked(true);
+    for (int b = 0; b < kPipeBufs; ++b) {
+      give_event(pipe_h2d_[b]);
+      give_event(pipe_ar_[b]);
+      give_event(pipe_d2h_[b]);
+      pipe_h2d_[b] = pipe_ar_[b] = pipe_d2h_[b] = nullptr;
+    }
+    give_event(pipe_start_);
+    pipe_start_ = nullptr;
     for (cudaEvent_t ev : event_pool_) cudaEventDestroy(ev);
     event_pool_.clear();
     quiet_barrier();
@@ -246,7 +290,8 @@ class CudaBackend final : public Backend {
     if (aux_stream_) cudaStreamDestroy(aux_stream_);
     if (own_user_stream_) cudaStreamDestroy(own_user_stream_);
     if (vmm_.ok) vmm_slab_destroy(vmm_);
-    else if (slab_) cudaFree(slab_);
+    else if (slab_ && !(inproc_ && ctx_->boot->poisoned())) cudaFree(slab_);   // failed loop-back job: a peer thread's kernel
+                                                                              // may still touch it - leak rather than fault
     if (err_host_) cudaFreeHost((void*)err_host_);
     slab_ = nullptr;
   }
@@ -424,6 +469,11 @@ void CudaBackend::init() {
   for (int i = 0; i < 16; ++i) err_host_[i] = 0;
   MLSLB_CUDA(cudaHostGetDevicePointer((void**)&err_dev_, (void*)err_host_, 0));
   if (const char* m = getenv("MLSL_STREAM_MODE")) inline_stream_ = !strcmp(m, "inline");
+  for (int i = 0; i < 256; ++i) {
+    cudaEvent_t ev = nullptr;
+    MLSLB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    event_pool_.push_back(ev);
+  }
 
   // exchange slab addresses / IPC handles
   const int W = b->size();
@@ -572,6 +622,10 @@ void CudaBackend::launch(CommRequest& r) {
     ~NvtxPop() { if (on) nvtxRangePop(); }
   } nvtx_pop{nvtx};
   launch_single(r, st, s);
+  if (getenv("MLSL_TRACE_LAUNCH")) {
+    fprintf(stderr, "[launched %.6f] r%d %s\n", now_ns() * 1e-9, ctx_->rank, opkind_name(d.kind));
+    fflush(stderr);
+  }
   st->recorded = false;
   if (!(eventless() && st->stages.empty())) {
     ensure_events(st);
@@ -653,7 +707,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
     }
     MLSLB_CUDA(launch_allreduce_ll(dc, d.dtype, d.rop, sp, rp, n, d.scale, s));
     for (auto& sb : st->stages)
-      if (sb.copy_out) MLSLB_CUDA(cudaMemcpyAsync(sb.user, sb.slab, sb.bytes, cudaMemcpyDefault, s));
+      if (sb.copy_out) copy_out(sb, s);
     return;
   }
 
@@ -876,7 +930,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   // ---- copy results out of the staging buffers -------------------------------------------------------------------
   if (alias_fix) MLSLB_CUDA(cudaMemcpyAsync(Rfinal, R, rbytes, cudaMemcpyDefault, s));
   for (auto& sb : st->stages)
-    if (sb.copy_out && sb.user == r.recv) MLSLB_CUDA(cudaMemcpyAsync(sb.user, sb.slab, sb.bytes, cudaMemcpyDefault, s));
+    if (sb.copy_out && sb.user == r.recv) copy_out(sb, s);
 }
 
 // End-to-end path for buffers that live in HOST memory (the reference's only kind of buffer): the message is cut
@@ -901,11 +955,11 @@ bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaS
   if (!pipe_buf_[0]) {
     for (int b = 0; b < kPipeBufs; ++b) {
       pipe_buf_[b] = (char*)alloc(pipe_chunk_, 4096);
-      MLSLB_CUDA(cudaEventCreateWithFlags(&pipe_h2d_[b], cudaEventDisableTiming));
-      MLSLB_CUDA(cudaEventCreateWithFlags(&pipe_ar_[b], cudaEventDisableTiming));
-      MLSLB_CUDA(cudaEventCreateWithFlags(&pipe_d2h_[b], cudaEventDisableTiming));
+      pipe_h2d_[b] = take_event();
+      pipe_ar_[b] = take_event();
+      pipe_d2h_[b] = take_event();
     }
-    MLSLB_CUDA(cudaEventCreateWithFlags(&pipe_start_, cudaEventDisableTiming));
+    pipe_start_ = take_event();
     int lo = 0, hi = 0;
     MLSLB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     MLSLB_CUDA(cudaStreamCreateWithPriority(&h2d_stream_, cudaStreamNonBlocking, hi));

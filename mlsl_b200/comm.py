@@ -103,6 +103,9 @@ def init(wait_mode=None):
     if st["device"]:
         env.set_wait_mode(wait_mode or "stream")
         api._stream_hook = _sync_stream
+        st["ev_pool"] = [torch.cuda.Event() for _ in range(64)]
+        for ev in st["ev_pool"]:
+            ev.record()          # torch creates the CUDA event lazily, on the first record
     return env
 
 
@@ -173,7 +176,10 @@ class _CudaMem:
             return                            # freed explicitly (free_tensor) or the library is already finalised
         try:
             del st["live"][self._ptr]
-            ev = torch.cuda.Event()
+            # pooled event (created at init): cuEventCreate can block behind another in-process rank's pending
+            # pageable copy (class 4) - recording an existing event never does
+            pool = st.get("ev_pool")
+            ev = pool.pop() if pool else torch.cuda.Event()
             ev.record()
             st["deferred"].append((ev, self._ptr))
         except Exception:  # noqa: BLE001 - interpreter shutdown
@@ -189,6 +195,7 @@ def _sweep_deferred(st):
     for ev, ptr in pend:
         if ev.query():
             st["env"].free(ptr)
+            st.setdefault("ev_pool", []).append(ev)
         else:
             keep.append((ev, ptr))
     st["deferred"] = keep

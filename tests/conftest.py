@@ -14,6 +14,22 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    # MLSL_TEST_DUMP_AFTER=<sec>: dump every thread's Python stack after <sec> seconds of a test (hang diagnosis)
+    if os.environ.get("MLSL_TEST_DUMP_AFTER"):
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["MLSL_TEST_DUMP_AFTER"]), repeat=True, file=sys.stderr)
+
+        def _native_dumps():
+            import threading
+            import time
+
+            def loop():
+                from mlsl_b200 import _lib
+                while True:
+                    time.sleep(float(os.environ["MLSL_TEST_DUMP_AFTER"]))
+                    _lib.lib().mlsl_debug_dump_stacks()
+            threading.Thread(target=loop, daemon=True).start()
+        _native_dumps()
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
 
 
@@ -25,8 +41,13 @@ def _native_library():
     yield
 
 
-def run_ranks(nranks, fn, backend="host", env=None, timeout=300):
-    """Run fn(rank, mlsl) on `nranks` in-process virtual ranks of the given backend; returns the per-rank results."""
+def run_ranks(nranks, fn, backend="host", env=None, timeout=300, wait_mode=None):
+    """Run fn(rank, mlsl) on `nranks` in-process virtual ranks of the given backend; returns the per-rank results.
+
+    wait_mode="host" (CUDA backend): Wait blocks the calling thread in cudaEventSynchronize / cudaStreamSynchronize until
+    the collective is done, so the `.cpu()` / `.item()` that follows never sits in a pageable copy behind a kernel that
+    still spins for a peer (such a copy holds a driver lock that blocks the peers' next calls: DESIGN 5b, class 4).
+    Tests that start collectives from autograd hooks keep the stream-ordered default (one shared autograd thread)."""
     import mlsl_b200 as mlsl
 
     old = {}
@@ -45,7 +66,7 @@ def run_ranks(nranks, fn, backend="host", env=None, timeout=300):
                     stream = torch.cuda.Stream()
                     ctx = torch.cuda.stream(stream)
                     ctx.__enter__()
-                mlsl.init()
+                mlsl.init(wait_mode=wait_mode) if wait_mode else mlsl.init()
                 try:
                     res = fn(r, mlsl)
                 except BaseException:

@@ -128,7 +128,8 @@ def run_fuzz(world, seed, backend):
     D, M, program = make_program(world, seed)
     dev = "cuda" if backend == "cuda" else "cpu"
     env = {"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20"} if backend == "cuda" else None
-    outs = run_ranks(world, lambda r, mlsl: run_program(r, mlsl, world, D, M, program, dev), backend=backend, env=env)
+    outs = run_ranks(world, lambda r, mlsl: run_program(r, mlsl, world, D, M, program, dev), backend=backend, env=env,
+                     wait_mode="host" if backend == "cuda" else None)
     for r in range(world):
         check_rank(r, world, D, M, program, outs[r])
 

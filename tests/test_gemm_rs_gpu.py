@@ -30,7 +30,7 @@ def test_gemm_reduce_scatter(world, M, N, K, out_dtype):
         assert torch.equal(outs[0], outs[1])
         return outs[0]
 
-    outs = run_ranks(world, body, backend="cuda", env={"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20"})
+    outs = run_ranks(world, body, backend="cuda", env={"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20"}, wait_mode="host")
     ref = torch.zeros(M, N, dtype=torch.float32)
     for r in range(world):
         a, w = _mats(r, M, N, K)
@@ -61,7 +61,7 @@ def test_gemm_reduce_scatter_two_cta(world, M, N, K):
         assert torch.equal(outs[0], outs[1])
         return outs[0]
 
-    outs = run_ranks(world, body, backend="cuda", env={"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20", "MLSL_GEMM_2CTA": "1"})
+    outs = run_ranks(world, body, backend="cuda", env={"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20", "MLSL_GEMM_2CTA": "1"}, wait_mode="host")
     ref = torch.zeros(M, N, dtype=torch.float32)
     for r in range(world):
         a, w = _mats(r, M, N, K)

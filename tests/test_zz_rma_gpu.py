@@ -8,6 +8,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _gpu(fn, world, **kw):
+    kw.setdefault("wait_mode", "host")     # no autograd hooks here: blocking waits keep `.cpu()` off spinning streams
     return run_ranks(world, fn, backend="cuda", env={"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20", **kw.pop("env", {})}, **kw)
 
 
