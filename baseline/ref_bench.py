@@ -72,10 +72,12 @@ def run(n_gpus, steps, warmup, headline_bytes):
             sweep.append({"bytes": r["bytes"], "us": r["us"], "busbw_GBps": r["busbw_GBps"]})
     except Exception:  # noqa: BLE001 - the sweep is informative only
         pass
-    value = head["busbw_GBps"] if n > 1 else head["algbw_GBps"]
+    # same definition as the other arm: whole-job aggregate bus bandwidth N x S / t x f(N), f(1) = 1
+    per_rank = head["busbw_GBps"] if n > 1 else head["algbw_GBps"]
+    value = per_rank * n
     return {
-        "metric": "allreduce_busbw_GBps" if n > 1 else "allreduce_algbw_GBps_single_gpu",
-        "value": round(value, 4), "unit": "GB/s", "n_gpus": n, "steps": steps, "warmup": warmup,
+        "metric": "allreduce_busbw_GBps",
+        "value": round(value, 4), "busbw_per_gpu_GBps": round(per_rank, 4), "algbw_GBps": round(head["algbw_GBps"], 4), "unit": "GB/s", "n_gpus": n, "steps": steps, "warmup": warmup,
         "ms_per_step": round(head["us"] / 1e3, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic", "impl": "reference",
         "config": {"model": "allreduce fp32 SUM, %d MiB per rank, out of place" % (headline_bytes >> 20),

@@ -44,6 +44,9 @@ struct alignas(64) BootCtl {
   alignas(64) std::atomic<uint64_t> heartbeat[kMaxHostRanks];
   alignas(64) BootSlot slots[kMaxHostRanks];
   alignas(64) GroupSlot gslots[kMaxGroupRows][kMaxHostRanks];   // per signal-row mailboxes (sub-group control plane)
+  // collectives launched so far per (signal row, lane) and rank: loop-back ranks (several ranks on one GPU) use it to
+  // launch a collective's kernels together instead of letting the first one spin on the device (cuda_backend.cu)
+  alignas(64) std::atomic<uint64_t> launch_seq[kMaxGroupRows * 2][kMaxHostRanks];
 };
 
 struct InprocWorld;   // shared state of an in-process world

@@ -29,8 +29,59 @@ static void gets(std::string& dst, const char* a, const char* b = nullptr) {
   if (const char* v = ev(a, b)) dst = v;
 }
 
+static const TuneDesc kTune[] = {
+    {"ll", "MLSL_LL", &Tunables::ll, "flag-in-data latency kernels for small all-reduces"},
+    {"mid_max_kb", "MLSL_MID_MAX_KB", &Tunables::mid_max_kb, "largest all-reduce on the multi-CTA flag-in-data kernel"},
+    {"mid_oneshot_kb", "MLSL_MID_ONESHOT_KB", &Tunables::mid_oneshot_kb, "one-shot while (P-1)*bytes <= this"},
+    {"nvls_min_ranks", "MLSL_NVLS_MIN_RANKS", &Tunables::nvls_min_ranks, "multicast kernels from this group size up"},
+    {"ar_unroll", "MLSL_AR_UNROLL", &Tunables::ar_unroll, "vectors per thread and pass of the large all-reduce"},
+    {"ar_channels", "MLSL_AR_CHANNELS", &Tunables::ar_channels, "CTAs of the large all-reduce"},
+    {"nvls_chunk_mb", "MLSL_NVLS_CHUNK_MB", &Tunables::nvls_chunk_mb, "split giant multicast all-reduces"},
+    {"bulk_copy_kb", "MLSL_BULK_COPY_KB", &Tunables::bulk_copy_kb, "cp.async.bulk rings for segments >= this"},
+    {"nvls_collectives", "MLSL_NVLS_COLLECTIVES", &Tunables::nvls_collectives, "multimem reduce-scatter / bcast"},
+    {"host_pipeline", "MLSL_HOST_PIPELINE", &Tunables::host_pipeline, "H2D / all-reduce / D2H pipeline for host buffers"},
+    {"pipe_chunk_mb", "MLSL_PIPE_CHUNK_MB", &Tunables::pipe_chunk_mb, "chunk size of the host pipeline"},
+    {"pipe_bufs", "MLSL_PIPE_BUFS", &Tunables::pipe_bufs, "device buffers of the host pipeline"},
+    {"numa_bind", "MLSL_NUMA_BIND", &Tunables::numa_bind, "bind the process to the GPU's NUMA node"},
+    {"gemm_2cta", "MLSL_GEMM_2CTA", &Tunables::gemm_2cta, "cta_group::2 GEMM + reduce-scatter"},
+    {"ag_gemm", "MLSL_AG_GEMM", &Tunables::ag_gemm, "fused all-gather + GEMM"},
+    {"nvtx", "MLSL_NVTX", &Tunables::nvtx, "NVTX ranges"},
+    {"trace_launch", "MLSL_TRACE_LAUNCH", &Tunables::trace_launch, "stderr line per launch"},
+    {"force_kernel_solo", "MLSL_FORCE_KERNEL_SOLO", &Tunables::force_kernel_solo, "1-rank groups run the peer kernels"},
+    {"quant_mx", "MLSL_QUANT_MX", &Tunables::quant_mx, "fp8 transport with per-32 ue8m0 scales"},
+    {"zero_copy", "MLSL_ZERO_COPY", &Tunables::zero_copy, "register foreign allocations instead of staging"},
+    {"dev_timestamps", "MLSL_DEV_TIMESTAMPS", &Tunables::dev_timestamps, "device timestamps in statistics / trace"},
+    {"loopback_rendezvous_ms", "MLSL_LOOPBACK_RENDEZVOUS_MS", &Tunables::loopback_rendezvous_ms,
+     "ranks sharing a GPU wait this long on the host for their peers before launching"},
+};
+const TuneDesc* tune_table(size_t* n) {
+  *n = sizeof(kTune) / sizeof(kTune[0]);
+  return kTune;
+}
+bool tune_set(Tunables& t, const char* key, long value) {
+  for (const TuneDesc& d : kTune)
+    if (!strcmp(d.key, key) || !strcmp(d.env, key)) {
+      t.*(d.field) = value;
+      return true;
+    }
+  return false;
+}
+bool tune_get(const Tunables& t, const char* key, long* value) {
+  for (const TuneDesc& d : kTune)
+    if (!strcmp(d.key, key) || !strcmp(d.env, key)) {
+      *value = t.*(d.field);
+      return true;
+    }
+  return false;
+}
+void parse_tunables(Tunables& t) {
+  for (const TuneDesc& d : kTune)
+    if (const char* v = ev(d.env)) t.*(d.field) = strtol(v, nullptr, 10);
+}
+
 EnvConfig parse_env() {
   EnvConfig c;
+  parse_tunables(c.tune);
   geti(c.log_level, "MLSL_LOG_LEVEL");
   getb(c.stats, "MLSL_STATS");
   getb(c.dup_group, "MLSL_DUP_GROUP");
@@ -81,6 +132,8 @@ void print_env(const EnvConfig& c) {
             (int)c.msg_priority, c.msg_priority_threshold, c.msg_priority_mode);
   MLSLB_LOG(LOG_INFO, "MLSL_NVLS=%d MLSL_WAIT_MODE=%s MLSL_WATCHDOG_SEC=%d MLSL_CHECK_SINGLE_NODE=%d",
             (int)c.use_nvls, c.wait_mode.c_str(), c.watchdog_sec, (int)c.check_single_node);
+  MLSLB_LOG(LOG_INFO, "MLSL_ALLTOALL_SPLIT=%d MLSL_ALLTOALLV_SPLIT=%d", c.alltoall_split, c.alltoallv_split);
+  for (const TuneDesc& d : kTune) MLSLB_LOG(LOG_INFO, "%s=%ld  (%s)", d.env, c.tune.*(d.field), d.help);
 }
 
 }  // namespace mlslb

@@ -15,6 +15,46 @@
 
 namespace mlslb {
 
+// Tuning knobs of the device path: read once from the environment, listed by print_env, and changeable at run time
+// through Environment::SetTuning(key, value) (all ranks must apply the same change at the same point of the program -
+// most of them select kernels or grids, which have to agree across a group).  Replaces ad-hoc getenv() calls in the
+// launch paths.
+struct Tunables {
+  long ll = 1;                  // MLSL_LL: flag-in-data latency kernels for small all-reduces
+  long mid_max_kb = 1024;       // MLSL_MID_MAX_KB: largest all-reduce that takes the multi-CTA flag-in-data kernel
+  long mid_oneshot_kb = 512;    // MLSL_MID_ONESHOT_KB: one-shot while (P-1) * bytes <= this, two-shot above
+  long nvls_min_ranks = 4;      // MLSL_NVLS_MIN_RANKS: multicast kernels from this group size up
+  long ar_unroll = 0;           // MLSL_AR_UNROLL: 16-byte vectors per thread and pass of the large all-reduce (0 = by size)
+  long ar_channels = 0;         // MLSL_AR_CHANNELS: CTAs of the large all-reduce (0 = MLSL_NUM_CHANNELS / auto)
+  long nvls_chunk_mb = 0;       // MLSL_NVLS_CHUNK_MB: split giant multicast all-reduces into launches of this size (0 = one launch)
+  long bulk_copy_kb = 256;      // MLSL_BULK_COPY_KB: gather-like collectives move segments >= this with cp.async.bulk rings
+  long nvls_collectives = 1;    // MLSL_NVLS_COLLECTIVES: multimem reduce-scatter / bcast when buffers are symmetric
+  long host_pipeline = 1;       // MLSL_HOST_PIPELINE: chunked H2D / all-reduce / D2H pipeline for host-resident buffers
+  long pipe_chunk_mb = 16;      // MLSL_PIPE_CHUNK_MB: chunk size of that pipeline
+  long pipe_bufs = 4;           // MLSL_PIPE_BUFS: device buffers of that pipeline (2..8)
+  long numa_bind = 1;           // MLSL_NUMA_BIND: bind the process to the NUMA node of its GPU at init (one rank per process)
+  long gemm_2cta = 1;           // MLSL_GEMM_2CTA: cta_group::2 GEMM + reduce-scatter kernel when the shape allows
+  long ag_gemm = 1;             // MLSL_AG_GEMM: fused all-gather + GEMM kernel when the shape allows
+  long nvtx = 1;                // MLSL_NVTX: NVTX range per collective launch
+  long trace_launch = 0;        // MLSL_TRACE_LAUNCH: one stderr line per kernel launch
+  long force_kernel_solo = 0;   // MLSL_FORCE_KERNEL_SOLO: single-rank groups run the peer kernels against themselves
+  long quant_mx = 0;            // MLSL_QUANT_MX: fp8 transport with per-32 ue8m0 (MX) scales instead of per-128 fp32
+  long zero_copy = 1;           // MLSL_ZERO_COPY: register foreign device allocations with the peers instead of staging
+  long dev_timestamps = 1;      // MLSL_DEV_TIMESTAMPS: statistics / trace use device event timestamps
+  long loopback_rendezvous_ms = 20;   // MLSL_LOOPBACK_RENDEZVOUS_MS: ranks sharing a GPU wait this long on the HOST for their
+                                      // peers before launching a collective (0 = launch at once and spin on the device)
+};
+struct TuneDesc {
+  const char* key;
+  const char* env;
+  long Tunables::*field;
+  const char* help;
+};
+const TuneDesc* tune_table(size_t* n);
+bool tune_set(Tunables& t, const char* key, long value);   // false: unknown key
+bool tune_get(const Tunables& t, const char* key, long* value);
+void parse_tunables(Tunables& t);
+
 struct EnvConfig {
   int log_level = 0;
   bool stats = false;            // MLSL_STATS
@@ -45,6 +85,7 @@ struct EnvConfig {
   int master_port = 0;                      // MLSL_MASTER_PORT, else MASTER_PORT + 1, else 29571
   int inproc_ranks = 0;          // MLSL_INPROC_RANKS: >0 -> N virtual ranks inside this process (tests/loopback)
   int stats_iters = 10, stats_skip = 4;  // isolation statistics iterations (reference: 10 / skip 4)
+  Tunables tune;                 // device-path knobs (see below)
 };
 
 EnvConfig parse_env();

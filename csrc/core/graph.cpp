@@ -1093,6 +1093,14 @@ void Environment::SetWaitMode(const char* mode) {
   MLSLB_ASSERT(mode && (!strcmp(mode, "host") || !strcmp(mode, "stream")), "wait mode must be 'host' or 'stream'");
   live(this)->backend->set_wait_mode(!strcmp(mode, "stream"));
 }
+void Environment::SetTuning(const char* key, long value) {
+  MLSLB_ASSERT(key && tune_set(live(this)->env.tune, key, value), "unknown tuning key '%s'", key ? key : "(null)");
+}
+long Environment::GetTuning(const char* key) {
+  long v = 0;
+  MLSLB_ASSERT(key && tune_get(live(this)->env.tune, key, &v), "unknown tuning key '%s'", key ? key : "(null)");
+  return v;
+}
 const char* Environment::GetBackendName() { return live(this)->backend->name(); }
 const char* Environment::DescribeBackend() {
   auto e = SELF(EnvironmentImpl);

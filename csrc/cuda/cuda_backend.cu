@@ -10,6 +10,7 @@
 //     stream, Wait() either blocks the host on the completion event or just orders the user's stream after it.
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
+#include <sched.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -107,6 +108,8 @@ class CudaBackend final : public Backend {
     MLSLB_CUDA(cudaMemsetAsync(slab_ + kSeqBase + (size_t)g.row * 2 * kSeqRowBytes, 0, 2 * kSeqRowBytes, zs));
     if (g.row < kLLRows) MLSLB_CUDA(cudaMemsetAsync(slab_ + kLLBase + (size_t)g.row * kLLRowBytes, 0, kLLRowBytes, zs));
     MLSLB_CUDA(cudaStreamSynchronize(zs));
+    if (BootCtl* c = ctx_->boot->ctl())
+      for (int l = 0; l < 2; ++l) c->launch_seq[g.row * 2 + l][ctx_->rank].store(0, std::memory_order_release);
     if (!g.is_world) ctx_->group_barrier(&g);
   }
 
@@ -175,6 +178,30 @@ class CudaBackend final : public Backend {
   }
 
   void launch(CommRequest& r) override;
+  // Loop-back ranks (several ranks on ONE GPU: the single-GPU test mode): a kernel that spins on the device for a peer
+  // that has not launched yet starves every host call that needs the device idle for a moment - a first kernel with a
+  // bigger stack, cudaFree, cublasCreate, any allocation while a thread sits in a pageable copy (probe_blocking.cu) -
+  // and if the late peer is inside such a call the job dead-locks.  So the members first meet on the HOST: each counts
+  // its launch on the (row, lane) and waits until every member has counted the same one; then all launch within
+  // microseconds of each other.  A bounded wait: ranks whose collectives are started from ONE shared thread (PyTorch's
+  // autograd thread runs the hooks of all in-process ranks) can never meet, they fall through and spin as before.
+  void loopback_rendezvous(const ProcessGroup& g, int lane) {
+    const long ms = ctx_->env.tune.loopback_rendezvous_ms;
+    BootCtl* c = ctx_->boot->ctl();
+    if (ranks_per_device_ <= 1 || ms <= 0 || !c || g.row < 0 || g.size() <= 1) return;
+    std::atomic<uint64_t>* row = c->launch_seq[g.row * 2 + lane];
+    const uint64_t v = row[ctx_->rank].fetch_add(1, std::memory_order_acq_rel) + 1;
+    const uint64_t deadline = now_ns() + (uint64_t)ms * 1000000ull;
+    for (int m : g.members) {
+      unsigned spins = 0;
+      while (row[m].load(std::memory_order_acquire) < v) {
+        if ((++spins & 63) == 0) {
+          if (now_ns() > deadline || ctx_->boot->poisoned()) return;
+          sched_yield();
+        }
+      }
+    }
+  }
   bool test(CommRequest& r) override {
     auto* st = (CudaReqState*)r.backend_state;
     set_device();
@@ -621,11 +648,8 @@ void CudaBackend::launch(CommRequest& r) {
     bool on;
     ~NvtxPop() { if (on) nvtxRangePop(); }
   } nvtx_pop{nvtx};
+  if (!solo) loopback_rendezvous(*g, r.lane);
   launch_single(r, st, s);
-  if (getenv("MLSL_TRACE_LAUNCH")) {
-    fprintf(stderr, "[launched %.6f] r%d %s\n", now_ns() * 1e-9, ctx_->rank, opkind_name(d.kind));
-    fflush(stderr);
-  }
   st->recorded = false;
   if (!(eventless() && st->stages.empty())) {
     ensure_events(st);

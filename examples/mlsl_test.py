@@ -33,6 +33,7 @@ class Net:
     def __init__(self, model_parts, dist_update, user_buf, use_test):
         self.model_parts, self.dist_update, self.user_buf, self.use_test = model_parts, dist_update, user_buf, use_test
         self.passed = self.failed = 0
+        self.loopback = False
 
     def check(self, ok, what, layer):
         if ok:
@@ -147,7 +148,9 @@ class Net:
         ps.start_increment_comm(L.w)
 
     def run(self):
-        env = mlsl.init()
+        # loop-back ranks (several ranks of ONE process on one GPU): Wait blocks the host until the collective is done,
+        # so the `.cpu()` checks below never sit in a pageable copy behind a kernel that still spins for a peer
+        env = mlsl.init(wait_mode="host" if self.loopback else None)
         self.rank, world = env.get_process_idx(), env.get_process_count()
         M = min(max(self.model_parts, 1), world)
         if world % M:
@@ -231,6 +234,9 @@ def main():
             # loop-back ranks share the GPU: each needs its own stream (kernels of different ranks wait for each other)
             torch.cuda.set_device(0)
             torch.cuda.set_stream(torch.cuda.Stream())
+            net = Net(*cfg)
+            net.loopback = True
+            return net.run()
         return Net(*cfg).run()
 
     with mlsl.InprocWorld(inproc) as world:

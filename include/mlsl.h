@@ -226,6 +226,8 @@ const char* mlsl_last_error(void);                       /* message of the last 
 int mlsl_environment_set_stream(mlsl_environment env, void* cuda_stream);
 int mlsl_environment_get_stream(mlsl_environment env, void** cuda_stream);
 int mlsl_environment_set_wait_mode(mlsl_environment env, const char* mode);
+int mlsl_environment_set_tuning(mlsl_environment env, const char* key, long long value);      /* [ext] */
+int mlsl_environment_get_tuning(mlsl_environment env, const char* key, long long* value);     /* [ext] */
 int mlsl_environment_get_backend_name(mlsl_environment env, const char** name);
 int mlsl_environment_describe_backend(mlsl_environment env, const char** text);
 int mlsl_environment_is_device_backend(mlsl_environment env, int* is_device);

@@ -323,6 +323,10 @@ class Environment {
   void SetStream(void* cudaStream);
   void* GetStream();
   void SetWaitMode(const char* mode);   // "host" | "stream"
+  // [ext] device-path tuning knobs by name ("ar_channels", "mid_max_kb", ... or their MLSL_* environment names; the
+  // list is printed at MLSL_LOG_LEVEL=1).  Every rank must apply the same change at the same point of the program.
+  void SetTuning(const char* key, long value);
+  long GetTuning(const char* key);
   const char* GetBackendName();         // "host" | "cuda"
   const char* DescribeBackend();        // human-readable: device, heap kind, NVLS availability
   bool IsDeviceBackend();

@@ -109,6 +109,8 @@ def _declare(l):
         "mlsl_environment_set_stream": [H, c_void_p],
         "mlsl_environment_get_stream": [H, P(c_void_p)],
         "mlsl_environment_set_wait_mode": [H, c_char_p],
+        "mlsl_environment_set_tuning": [H, c_char_p, ctypes.c_longlong],
+        "mlsl_environment_get_tuning": [H, c_char_p, ctypes.POINTER(ctypes.c_longlong)],
         "mlsl_environment_get_backend_name": [H, P(c_char_p)],
         "mlsl_environment_is_device_backend": [H, P(c_int)],
         "mlsl_environment_describe_backend": [H, P(c_char_p)],

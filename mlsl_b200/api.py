@@ -550,6 +550,13 @@ class MLSL(_Handle):
     def set_wait_mode(self, mode):
         self._call("mlsl_environment_set_wait_mode", mode.encode())
 
+    def set_tuning(self, key, value):
+        """Device-path tuning knob by name (see MLSL_LOG_LEVEL=1 for the list); same change on every rank."""
+        self._call("mlsl_environment_set_tuning", key.encode(), int(value))
+
+    def get_tuning(self, key):
+        return int(self._get("mlsl_environment_get_tuning", ctypes.c_longlong, key.encode()))
+
     def get_backend_name(self):
         return self._get("mlsl_environment_get_backend_name", ctypes.c_char_p).decode()
 
@@ -612,7 +619,8 @@ class InprocWorld:
         if failed:
             # the root cause first: peers of a failing rank only report "poisoned" / watchdog follow-up errors
             root = [e for e in failed if "poisoned" not in str(e) and "watchdog" not in str(e)]
-            raise (root or failed)[0]
+            dog = [e for e in failed if "watchdog" in str(e)]        # names the signal word a kernel gave up on
+            raise (root or dog or failed)[0]
         return results
 
     def close(self):

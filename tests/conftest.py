@@ -66,6 +66,13 @@ def run_ranks(nranks, fn, backend="host", env=None, timeout=300, wait_mode=None)
                     stream = torch.cuda.Stream()
                     ctx = torch.cuda.stream(stream)
                     ctx.__enter__()
+                    # torch creates one cuBLAS handle per thread on the first matmul; cublasCreate synchronises the
+                    # device, which dead-locks behind a peer rank's spinning kernel (scripts/probe_blocking_torch.py):
+                    # create it now, before the library's init barrier, i.e. before any collective can be in flight
+                    for wdt in (torch.float32, torch.bfloat16):
+                        wa = torch.ones(16, 16, device="cuda", dtype=wdt)
+                        torch.mm(wa, wa)
+                    stream.synchronize()
                 mlsl.init(wait_mode=wait_mode) if wait_mode else mlsl.init()
                 try:
                     res = fn(r, mlsl)
