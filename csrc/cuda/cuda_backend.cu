@@ -37,7 +37,10 @@ constexpr int kPadRows = kMaxGroupRows * 2;
 constexpr size_t kPadBytes = kPadRows * kPadRowBytes;
 constexpr size_t kSeqBase = kPadBytes;
 constexpr size_t kLLBase = (kPadBytes + kPadRows * kSeqRowBytes + 4095) & ~(size_t)4095;   // low-latency arenas, one per row
-constexpr size_t kHeaderBytes = (kLLBase + kLLRows * kLLRowBytes + ((size_t)1 << 20) - 1) >> 20 << 20;
+constexpr size_t kMidSeqBase = kLLBase + kLLRows * kLLRowBytes;                      // launch counters of the mid kernel, per row
+constexpr size_t kMidSeqRowBytes = (size_t)kMidCtas * sizeof(unsigned long long);
+constexpr size_t kMidBase = (kMidSeqBase + kMidRows * kMidSeqRowBytes + 4095) & ~(size_t)4095;   // mid-size arenas
+constexpr size_t kHeaderBytes = (kMidBase + kMidRows * kMidRowBytes + ((size_t)1 << 20) - 1) >> 20 << 20;
 
 struct StageBuf {
   void* user;
@@ -107,6 +110,10 @@ class CudaBackend final : public Backend {
     MLSLB_CUDA(cudaMemsetAsync(slab_ + (size_t)g.row * 2 * kPadRowBytes, 0, 2 * kPadRowBytes, zs));
     MLSLB_CUDA(cudaMemsetAsync(slab_ + kSeqBase + (size_t)g.row * 2 * kSeqRowBytes, 0, 2 * kSeqRowBytes, zs));
     if (g.row < kLLRows) MLSLB_CUDA(cudaMemsetAsync(slab_ + kLLBase + (size_t)g.row * kLLRowBytes, 0, kLLRowBytes, zs));
+    if (g.row < kMidRows) {
+      MLSLB_CUDA(cudaMemsetAsync(slab_ + kMidBase + (size_t)g.row * kMidRowBytes, 0, kMidRowBytes, zs));
+      MLSLB_CUDA(cudaMemsetAsync(slab_ + kMidSeqBase + (size_t)g.row * kMidSeqRowBytes, 0, kMidSeqRowBytes, zs));
+    }
     MLSLB_CUDA(cudaStreamSynchronize(zs));
     if (BootCtl* c = ctx_->boot->ctl())
       for (int l = 0; l < 2; ++l) c->launch_seq[g.row * 2 + l][ctx_->rank].store(0, std::memory_order_release);
@@ -373,6 +380,13 @@ class CudaBackend final : public Backend {
   void init();
   cudaStream_t stream_for(int row, int lane);
   int pick_channels(size_t bytes) const;
+  int ar_channels(size_t bytes) const {   // large all-reduce: MLSL_AR_CHANNELS caps / raises the grid of that kernel only
+    const long c = ctx_->env.tune.ar_channels;
+    if (c <= 0) return pick_channels(bytes);
+    size_t want = ceil_div(std::max<size_t>(bytes, 1), (size_t)kCommThreads * 16);
+    int cap = std::min(kMaxChannels, std::max(1, sm_count_ / std::max(1, ranks_per_device_)));
+    return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)std::min<long>(c, cap)));
+  }
   // fp8 all-reduce: one warp per 128-element block and pass; HBM-bound local phases -> up to one 1024-thread CTA per SM
   int quant_channels(size_t elems) const {
     size_t blocks = ceil_div(std::max<size_t>(elems, 1), (size_t)128);
@@ -496,6 +510,7 @@ void CudaBackend::init() {
   for (int i = 0; i < 16; ++i) err_host_[i] = 0;
   MLSLB_CUDA(cudaHostGetDevicePointer((void**)&err_dev_, (void*)err_host_, 0));
   if (const char* m = getenv("MLSL_STREAM_MODE")) inline_stream_ = !strcmp(m, "inline");
+  MLSLB_CUDA(init_kernel_attributes());
   for (int i = 0; i < 256; ++i) {
     cudaEvent_t ev = nullptr;
     MLSLB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -593,11 +608,13 @@ DevComm CudaBackend::make_comm(const ProcessGroup& g, int lane) const {
   dc.err = err_dev_;
   for (int i = 0; i < g.size(); ++i) dc.slab[i] = peer_slab_[g.members[i]];
   dc.ll_off = (lane == 0 && g.row >= 0 && g.row < kLLRows) ? (unsigned)(kLLBase + (size_t)g.row * kLLRowBytes) : 0u;
+  const bool mid = lane == 0 && g.row >= 0 && g.row < kMidRows;
+  dc.mid_off = mid ? (unsigned)(kMidBase + (size_t)g.row * kMidRowBytes) : 0u;
+  dc.mid_seq_off = mid ? (unsigned)(kMidSeqBase + (size_t)g.row * kMidSeqRowBytes) : 0u;
   // NVLS only for groups spanning every rank in world order (the multicast object covers exactly those devices)
   dc.mc = nullptr;
   // (and only from 4 ranks up: per direction NVLS moves S(1+1/N) bytes, the peer-to-peer kernel 2S(N-1)/N)
-  int nvls_min = 4;
-  if (const char* v = getenv("MLSL_NVLS_MIN_RANKS")) nvls_min = atoi(v);
+  const int nvls_min = (int)ctx_->env.tune.nvls_min_ranks;
   if (mc_ && g.size() == ctx_->world && g.size() >= nvls_min) {
     bool ident = true;
     for (int i = 0; i < g.size(); ++i) ident &= g.members[i] == i;
@@ -642,7 +659,7 @@ void CudaBackend::launch(CommRequest& r) {
   st->stream = s;
   if (!inline_stream_) MLSLB_CUDA(cudaStreamWaitEvent(s, st->ready, 0));
   // NVTX range per collective launch (header-only NVTX3: a no-op unless a profiler is attached), SURVEY 5.1
-  static const bool nvtx = !(getenv("MLSL_NVTX") && atoi(getenv("MLSL_NVTX")) == 0);
+  const bool nvtx = ctx_->env.tune.nvtx != 0;
   if (nvtx) nvtxRangePushA(opkind_name(d.kind));
   struct NvtxPop {
     bool on;
@@ -669,7 +686,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   // MLSL_FORCE_KERNEL_SOLO=1: run a 1-rank group through the real collective kernels (handshake with itself,
   // pull from / push to its own buffers).  Lets ncu profile the kernels on one GPU - under the profiler kernels
   // are serialised, so ranks that wait for each other can never be captured.
-  static const bool force_solo = getenv("MLSL_FORCE_KERNEL_SOLO") && atoi(getenv("MLSL_FORCE_KERNEL_SOLO")) != 0;
+  const bool force_solo = ctx_->env.tune.force_kernel_solo != 0;
   if (!g || g->size() <= 1 ? !((force_solo && g && g->row >= 0) || d.kind == OpKind::FUSED_UPDATE || d.kind == OpKind::GEMM_RS || d.kind == OpKind::AG_GEMM) : false) {
     size_t bytes = 0;
     switch (d.kind) {
@@ -698,7 +715,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   }
   const int P = g->size(), me = g->idx;
   DevComm dc = make_comm(*g, r.lane);
-  static const bool trace = getenv("MLSL_TRACE_LAUNCH") && atoi(getenv("MLSL_TRACE_LAUNCH")) != 0;
+  const bool trace = ctx_->env.tune.trace_launch != 0;
   if (trace) {
     fprintf(stderr, "[launch %.6f] r%d %s row %d lane %d idx %d/%d count %zu send %p recv %p stream %p\n", now_ns() * 1e-9,
             ctx_->rank, opkind_name(d.kind), g->row, r.lane, me, P, n, r.send, r.recv, (void*)s);
@@ -709,8 +726,12 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   // The choice of kernel must be the same on every member, so it only looks at (kind, size, group).  The kernel reads
   // and writes any device-accessible memory at any alignment (torch tensors are used in place, no staging copy); a
   // buffer the GPU cannot address (pageable host memory) goes through a small slab scratch block first.
-  static const bool ll_enabled = !(getenv("MLSL_LL") && atoi(getenv("MLSL_LL")) == 0);
-  if (d.kind == OpKind::ALLREDUCE && !d.compress && ll_enabled && dc.ll_off && n > 0 && n * es <= kLLMaxBytes) {
+  const bool ll_enabled = ctx_->env.tune.ll != 0;
+  const size_t mid_max = std::min<size_t>(kMidMaxBytes, (size_t)std::max<long>(0, ctx_->env.tune.mid_max_kb) << 10);
+  const bool take_ll = d.kind == OpKind::ALLREDUCE && !d.compress && ll_enabled && dc.ll_off && n > 0 && n * es <= kLLMaxBytes;
+  const bool take_mid = !take_ll && d.kind == OpKind::ALLREDUCE && !d.compress && ll_enabled && dc.mid_off && n > 0 &&
+                        n * es <= mid_max;
+  if (take_ll || take_mid) {
     const size_t bytes = n * es;
     auto dev_ok = [&](const void* p) { return owns(p, bytes) || is_device_pointer(p); };
     const void* sp = r.send;
@@ -729,7 +750,14 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
       st->stages.push_back(sb);
       sp = sb.slab;
     }
-    MLSLB_CUDA(launch_allreduce_ll(dc, d.dtype, d.rop, sp, rp, n, d.scale, s));
+    if (take_ll) {
+      MLSLB_CUDA(launch_allreduce_ll(dc, d.dtype, d.rop, sp, rp, n, d.scale, s));
+    } else {
+      // one-shot while the (P-1) copies every rank sends and receives stay small, two-shot (reduce-scatter + all-gather,
+      // both flag-in-data) above; the grid is fixed (every launch counts on all kMidCtas launch counters)
+      const bool two_shot = (size_t)(P - 1) * bytes > ((size_t)std::max<long>(0, ctx_->env.tune.mid_oneshot_kb) << 10);
+      MLSLB_CUDA(launch_allreduce_mid(dc, d.dtype, d.rop, sp, rp, n, d.scale, two_shot, kMidCtas, s));
+    }
     for (auto& sb : st->stages)
       if (sb.copy_out) copy_out(sb, s);
     return;
@@ -814,26 +842,30 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
         if (ctx_->env.large_msg_mb && n * es >= ctx_->env.large_msg_mb * (size_t)1048576 && ctx_->env.large_msg_chunks > 1 &&
             ctx_->env.msg_priority)
           chunks = (size_t)ctx_->env.large_msg_chunks;
-        // NVLS: measured on 8xB200 the multimem kernel sustains 767 GB/s bus bandwidth on 256 MiB launches but only
-        // ~580 GB/s on a single 1 GiB launch; giant messages therefore go out as back-to-back 256 MiB launches
-        // (same stream, the next handshake overlaps the previous launch's tail).  MLSL_NVLS_CHUNK_MB=0 disables.
-        static const size_t nvls_chunk = (size_t)(getenv("MLSL_NVLS_CHUNK_MB") ? atoi(getenv("MLSL_NVLS_CHUNK_MB")) : 256) << 20;
+        // The kernel walks the message pass by pass with all ranks in step (kernels.cu), so one launch covers any size;
+        // MLSL_NVLS_CHUNK_MB > 0 brings back the round-1 split of giant multicast messages into several launches.
+        const size_t nvls_chunk = (size_t)std::max<long>(0, ctx_->env.tune.nvls_chunk_mb) << 20;
         if (dc.mc && nvls_chunk && n * es >= nvls_chunk + nvls_chunk / 2) chunks = std::max(chunks, ceil_div(n * es, nvls_chunk));
         size_t per = round_up(ceil_div(n, chunks), 256);
+        const int unroll = (int)ctx_->env.tune.ar_unroll;
         for (size_t off = 0; off < n; off += per) {
           size_t cnt = std::min(per, n - off);
           MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, so + off * es, ro + off * es, cnt, d.scale,
-                                      chunks > 1 ? pick_channels(ceil_div(cnt * es, (size_t)P)) : ch, s));
+                                      ar_channels(ceil_div(cnt * es, (size_t)P)), unroll, s));
         }
       }
       break;
     }
     case OpKind::REDUCE_SCATTER:
-      MLSLB_CUDA(launch_reduce_pull(dc, d.dtype, d.rop, so, ro, (size_t)me * n, n, d.scale, true, ch, s));
+    case OpKind::REDUCE: {
+      DevComm rdc = dc;
+      if (!(ctx_->env.tune.nvls_collectives & 1)) rdc.mc = nullptr;   // multimem.ld_reduce flavour off
+      if (d.kind == OpKind::REDUCE_SCATTER)
+        MLSLB_CUDA(launch_reduce_pull(rdc, d.dtype, d.rop, so, ro, (size_t)me * n, n, d.scale, true, ch, s));
+      else
+        MLSLB_CUDA(launch_reduce_pull(rdc, d.dtype, d.rop, so, ro, 0, n, d.scale, me == (int)d.root, ch, s));
       break;
-    case OpKind::REDUCE:
-      MLSLB_CUDA(launch_reduce_pull(dc, d.dtype, d.rop, so, ro, 0, n, d.scale, me == (int)d.root, ch, s));
-      break;
+    }
     case OpKind::ALLGATHER:
     case OpKind::ALLGATHERV:
     case OpKind::BCAST:
@@ -889,7 +921,23 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
           break;
         default: break;
       }
-      MLSLB_CUDA(launch_pull_copy(dc, plan, pub_send, ro, ch, s));
+      // NVLS push where it pays: the root of a bcast sends the message once instead of P-1 times (all-gather: opt-in,
+      // bit 4 - every byte still has to arrive at every member, the push only saves outbound traffic)
+      const long nv = ctx_->env.tune.nvls_collectives;
+      if (dc.mc && d.kind == OpKind::BCAST && (nv & 2)) {
+        plan.mc_mode = 1;
+        plan.mc_root = (int)d.root;
+        plan.mc_bytes = n * es;
+      } else if (dc.mc && d.kind == OpKind::ALLGATHER && (nv & 4)) {
+        plan.mc_mode = 2;
+        plan.mc_bytes = n * es;
+      }
+      // big messages: the copy engine (cp.async.bulk rings) moves the segments instead of the threads
+      unsigned long long pulled = 0;
+      for (int i = 0; i < plan.nseg; ++i) pulled += plan.seg[i].bytes;
+      const long bk = ctx_->env.tune.bulk_copy_kb;
+      const bool bulk = bk > 0 && pulled >= ((unsigned long long)bk << 10);
+      MLSLB_CUDA(launch_pull_copy(dc, plan, pub_send, ro, ch, bulk, s));
       break;
     }
     case OpKind::FUSED_UPDATE: {
@@ -939,7 +987,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
       const bool out32 = d.has_out_dtype && d.out_dtype == DType::F32;
       const int gcap = std::min(std::max(1, sm_count_ / std::max(1, ranks_per_device_)), kMaxChannels);
       // MLSL_GEMM_2CTA=1: experimental cta_group::2 kernel (256 x 256 tiles on CTA pairs); same choice on every rank
-      const bool two_cta = getenv("MLSL_GEMM_2CTA") && atoi(getenv("MLSL_GEMM_2CTA")) != 0;
+      const bool two_cta = ctx_->env.tune.gemm_2cta != 0;
       if (two_cta && gcap >= 2 && gemm_rs2_check(gm.M, gm.N, gm.K, P) == nullptr) {
         const int gch = gemm_rs2_channels(gm.M, gm.N, gcap);
         MLSLB_CUDA(launch_gemm_rs2(dc, gm.a, gm.w, (unsigned long long)((char*)st->qstage - slab_), R, out32, gm.M, gm.N, gm.K, gch, s));
@@ -965,8 +1013,7 @@ bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaS
   const CommDesc& d = r.desc;
   const size_t es = dtype_size(d.dtype), bytes = d.count * es;
   if (bytes < 2 * pipe_chunk_ || !r.send || !r.recv) return false;
-  static const bool enabled = !(getenv("MLSL_HOST_PIPELINE") && atoi(getenv("MLSL_HOST_PIPELINE")) == 0);
-  if (!enabled) return false;
+  if (!ctx_->env.tune.host_pipeline) return false;
   cudaPointerAttributes as, ar;
   if (cudaPointerGetAttributes(&as, r.send) != cudaSuccess || cudaPointerGetAttributes(&ar, r.recv) != cudaSuccess) {
     cudaGetLastError();
@@ -1005,7 +1052,8 @@ bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaS
     if (solo) {   // single-rank group: nothing to reduce, the chunk only passes through the GPU (scaled if asked for)
       if (d.scale != 1.0f) MLSLB_CUDA(launch_scale(d.dtype, pipe_buf_[b], cnt, d.scale, s));
     } else {
-      MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, o, o, cnt, d.scale, pick_channels(ceil_div(cnt * es, (size_t)P)), s));
+      MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, o, o, cnt, d.scale, ar_channels(ceil_div(cnt * es, (size_t)P)),
+                                  (int)ctx_->env.tune.ar_unroll, s));
     }
     MLSLB_CUDA(cudaEventRecord(pipe_ar_[b], s));
     MLSLB_CUDA(cudaStreamWaitEvent(d2h_stream_, pipe_ar_[b], 0));

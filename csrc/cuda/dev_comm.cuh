@@ -39,6 +39,8 @@ struct DevComm {
   char* slab[kMaxDevRanks];   // slab base of every member (group order) in MY address space
   char* mc;                   // multicast mapping of the slabs (NVLS) or nullptr
   unsigned ll_off;            // byte offset of this row's low-latency arena inside every slab (0 = none)
+  unsigned mid_off;           // byte offset of this row's mid-size flag-in-data arena (0 = none)
+  unsigned mid_seq_off;       // byte offset of my launch counters of the mid kernel (one per CTA)
 };
 
 struct PeerTable {            // lives in shared memory

@@ -20,6 +20,10 @@ struct CopySeg {
 struct CopyPlan {
   int nseg;
   int elem_size;
+  int mc_mode;       // NVLS push instead of the pull, when the members' buffers turn out symmetric: 0 = never,
+                     // 1 = bcast (mc_root multimem.st's mc_bytes of its buffer), 2 = all-gather (everyone pushes its shard)
+  int mc_root;
+  unsigned long long mc_bytes;
   CopySeg seg[kMaxDevRanks];
   unsigned long long aux_out[kMaxDevRanks];   // word I publish to peer p in the opening handshake
 };
@@ -28,7 +32,7 @@ struct CopyPlan {
 cudaError_t launch_barrier(const DevComm& dc, cudaStream_t s);
 // K1 all-reduce: fused reduce-scatter + all-gather over peer memory, scale epilogue
 cudaError_t launch_allreduce(const DevComm& dc, DType dt, RedOp op, unsigned long long send_off,
-                             unsigned long long recv_off, size_t count, float scale, int channels, cudaStream_t s);
+                             unsigned long long recv_off, size_t count, float scale, int channels, int unroll, cudaStream_t s);
 // K1, latency path: messages <= kLLMaxBytes travel as (data, flag) pairs pushed straight into every peer's arena -
 // one NVLink one-way trip, no handshake, no fence (csrc/cuda/kernels.cu: k_allreduce_ll)
 constexpr size_t kLLMaxBytes = 8192;                                   // payload per rank
@@ -37,13 +41,26 @@ constexpr size_t kLLRowBytes = 2 * (size_t)kMaxDevRanks * kLLSlotBytes;   // two
 constexpr int kLLRows = 32;                                            // group rows that own an arena
 cudaError_t launch_allreduce_ll(const DevComm& dc, DType dt, RedOp op, const void* send, void* recv, size_t count,
                                 float scale, cudaStream_t s);
+// K1, mid sizes: multi-CTA flag-in-data kernel, one-shot or two-shot (csrc/cuda/kernels.cu: k_allreduce_mid).  The arena
+// of a row holds two parities; one parity fits the larger of a one-shot (P copies of 2 x bytes) and a two-shot
+// (reduce area + gather area, 2 x bytes each, slices rounded up) of the largest message.
+constexpr int kMidThreads = 512;
+constexpr int kMidCtas = 32;                                           // fixed grid: every launch counts on all of them
+constexpr size_t kMidMaxBytes = (size_t)1 << 20;                       // largest message on this path
+constexpr size_t kMidParityBytes = 4 * kMidMaxBytes + ((size_t)64 << 10);
+constexpr size_t kMidRowBytes = 2 * kMidParityBytes;
+constexpr int kMidRows = 8;                                            // group rows that own a mid arena
+cudaError_t launch_allreduce_mid(const DevComm& dc, DType dt, RedOp op, const void* send, void* recv, size_t count,
+                                 float scale, bool two_shot, int ctas, cudaStream_t s);
 // K2/K5 reduce-scatter and reduce: out[i] = scale * op_p send_p[base + i], i < count (active ranks only)
 cudaError_t launch_reduce_pull(const DevComm& dc, DType dt, RedOp op, unsigned long long send_off,
                                unsigned long long recv_off, size_t base, size_t count, float scale, bool active,
                                int channels, cudaStream_t s);
 // K3/K4/K6/K7/K9 all-gather(v), bcast, all-to-all(v), gather, scatter, send/recv list
 cudaError_t launch_pull_copy(const DevComm& dc, const CopyPlan& plan, unsigned long long send_off,
-                             unsigned long long recv_off, int channels, cudaStream_t s);
+                             unsigned long long recv_off, int channels, bool bulk, cudaStream_t s);
+// one-time kernel attributes (dynamic shared memory of the bulk-copy ring); call once per process before the first launch
+cudaError_t init_kernel_attributes();
 // K13 activation pack / unpack (strided (mb, fm, fmSize) gather/scatter), local
 struct PackPlan {
   int n;

@@ -82,6 +82,74 @@ def main():
     refq = sum(make(p, n, torch.float32).double() for p in range(W)).float()
     torch.cuda.synchronize()
     check("allreduce fp8-compressed", ((q.cpu() - refq).abs().max() / refq.abs().max()).item() < 0.1)
+    # ---- mid sizes: the multi-CTA flag-in-data kernel (one-shot / two-shot), changing sizes back to back -------------
+    for k, nb in enumerate((8200, 65536, 300004, 1 << 20, 70004, 1 << 19)):
+        n = nb // 4
+        x = make(r, n, torch.float32, seed=k).cuda()                     # foreign buffer: read in place by the kernel
+        y = mlsl.alloc_tensor(n, torch.float32)
+        mlsl.allreduce(x, out=y, scale=1.0 / W)
+        ref = sum(make(p, n, torch.float32, seed=k).double() for p in range(W)) / W
+        torch.cuda.synchronize()
+        err = (y.double().cpu() - ref).abs().max().item()
+        check("allreduce mid %d B (err %.1e)" % (nb, err), err <= 1e-5)
+        mlsl.free_tensor(y)
+    # ---- large symmetric buffers: NVLS flavours (multimem ld_reduce reduce-scatter, multimem.st bcast) and the bulk-copy
+    #      (cp.async.bulk) gather-like collectives, random data, in place and out of place -------------------------------
+    n = (4 << 20) // 4 + 12
+    x = mlsl.alloc_tensor(n * W, torch.float32)
+    x.copy_(make(r, n * W, torch.float32, seed=7))
+    shard = mlsl.alloc_tensor(n, torch.float32)
+    mlsl.reduce_scatter(x, out=shard, scale=0.25)
+    ref = (sum(make(p, n * W, torch.float32, seed=7).double() for p in range(W)) * 0.25).float()
+    torch.cuda.synchronize()
+    check("reduce_scatter 4 MiB shards (symmetric heap)", torch.allclose(shard.cpu(), ref[r * n:(r + 1) * n], rtol=1e-5, atol=1e-5))
+    full = mlsl.alloc_tensor(n * W, torch.float32)
+    mlsl.allgather(shard, out=full)
+    torch.cuda.synchronize()
+    check("allgather 4 MiB shards (bulk copy)", torch.allclose(full.cpu(), ref, rtol=1e-5, atol=1e-5))
+    full[r * n:(r + 1) * n].mul_(2.0)
+    mlsl.allgather(full[r * n:(r + 1) * n], out=full)                    # in place: my shard already sits at r * n
+    torch.cuda.synchronize()
+    check("allgather in place", torch.allclose(full.cpu(), ref * 2, rtol=1e-5, atol=1e-5))
+    a2a = mlsl.alloc_tensor(n * W, torch.float32)
+    mlsl.alltoall(x, out=a2a)
+    torch.cuda.synchronize()
+    ok = all(torch.equal(a2a[p * n:(p + 1) * n].cpu(), make(p, n * W, torch.float32, seed=7)[r * n:(r + 1) * n]) for p in range(W))
+    check("alltoall 4 MiB blocks (bulk copy)", ok)
+    for root in (0, W - 1):
+        b = mlsl.alloc_tensor(n * 4 + 3, torch.float32)
+        b.copy_(make(r, n * 4 + 3, torch.float32, seed=11))
+        mlsl.bcast(b, root=root)
+        torch.cuda.synchronize()
+        check("bcast 16 MiB from %d (symmetric heap)" % root, torch.equal(b.cpu(), make(root, n * 4 + 3, torch.float32, seed=11)))
+        mlsl.free_tensor(b)
+    g = mlsl.gather(shard, root=W - 1)
+    torch.cuda.synchronize()
+    check("gather", r != W - 1 or torch.allclose(g.cpu(), ref, rtol=1e-5, atol=1e-5))
+    # ---- sub-groups (data x model), the randomised collective programs and the Session graph twin ----------------------
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_fuzz_cpu import check_rank, make_program, run_program
+    for seed in (2, 4, 5):
+        D, M, program = make_program(W, seed)
+        res = run_program(r, mlsl, W, D, M, program, "cuda")
+        ok = True
+        try:
+            check_rank(r, W, D, M, program, res)
+        except AssertionError as e:
+            ok = False
+            print("rank %d fuzz seed %d: %r" % (r, seed, e), flush=True)
+        check("random collective program seed %d (%d x %d)" % (seed, D, M), ok)
+    for (D, M) in ((2, W // 2), (W // 2, 2)) if W >= 4 else ():
+        dist = env.create_distribution(D, M)
+        for grp, P in (("data", D), ("model", M)):
+            t = mlsl.alloc_tensor(200003, torch.float32)
+            t.fill_(float(r + 1))
+            mlsl.allreduce(t, group=grp, distribution=dist)
+            mem = [q for q in range(W) if (q % M == r % M if grp == "data" else q // M == r // M)]
+            torch.cuda.synchronize()
+            check("sub-group allreduce %dx%d %s" % (D, M, grp), bool((t == float(sum(q + 1 for q in mem))).all().item()) and len(mem) == P)
+            mlsl.free_tensor(t)
+        env.delete_distribution(dist)
     mlsl.finalize()
     if r == 0:
         print("mp_gpu_check: %s" % ("ALL PASSED" if not fails else "FAILED: %s" % fails), flush=True)

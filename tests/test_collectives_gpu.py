@@ -83,6 +83,42 @@ def test_allreduce_sizes_scale_out_of_place(n):
         assert torch.allclose(y.double(), ref, rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("dtype,op", [(torch.float32, "sum"), (torch.bfloat16, "sum"), (torch.float64, "max"), (torch.uint8, "min")])
+def test_allreduce_mid_flag_in_data_kernel(world, dtype, op):
+    """8 KiB .. 1 MiB: the multi-CTA flag-in-data kernel, one-shot and two-shot, back to back with changing sizes (the
+    arena is reused with alternating parity), in place and out of place, heap and foreign buffers, fused scale."""
+    es = torch.empty((), dtype=dtype).element_size()
+    sizes = [8200 // es + 1, 65536 // es, 300000 // es + 3, (1 << 20) // es, 70000 // es + 1]
+
+    def body(r, mlsl):
+        outs = []
+        for k, n in enumerate(sizes):
+            x = _make(r + k, n, dtype).cuda()
+            if k % 2 == 0:
+                heap = mlsl.alloc_tensor(n, dtype)
+                heap.copy_(x)
+                mlsl.allreduce(heap, op=op)
+                outs.append(heap.clone())
+            else:
+                y = torch.empty_like(x)
+                mlsl.allreduce(x, out=y, op=op, scale=0.5 if dtype.is_floating_point and op == "sum" else 1.0)
+                outs.append(y)
+        torch.cuda.current_stream().synchronize()
+        return [o.cpu() for o in outs]
+
+    res = _gpu(body, world)
+    tol = 0 if not dtype.is_floating_point else {torch.float32: 1e-6, torch.float64: 1e-12}.get(dtype, 4e-2)
+    for k, n in enumerate(sizes):
+        ref = _ref_reduce([_make(r + k, n, dtype) for r in range(world)], op)
+        if k % 2 == 1 and dtype.is_floating_point and op == "sum":
+            ref = ref * 0.5
+        for r in range(world):
+            got = res[r][k]
+            assert torch.allclose(got.to(ref.dtype), ref, rtol=tol, atol=tol * 4), (k, n, r)
+            assert torch.equal(got, res[0][k])          # bit-identical on every rank
+
+
 @pytest.mark.parametrize("n", [1001, 5001])
 def test_unaligned_buffers(n):
     """4-byte aligned views: <= 8 KiB the LL kernel goes byte-wise, above it the handshake kernel takes its scalar path.

@@ -44,8 +44,6 @@ def test_gemm_reduce_scatter(world, M, N, K, out_dtype):
         assert (o - exp).abs().max().item() <= tol, (o - exp).abs().max().item()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MLSL_TEST_2CTA") != "1",
-                    reason="experimental cta_group::2 kernel: opt in with MLSL_TEST_2CTA=1 (not yet validated on hardware)")
 @pytest.mark.parametrize("world,M,N,K", [(1, 256, 256, 64), (1, 512, 768, 512), (2, 1024, 512, 384), (2, 2048, 1024, 1024)])
 def test_gemm_reduce_scatter_two_cta(world, M, N, K):
     """Same check for the CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tiles, MLSL_GEMM_2CTA=1)."""

@@ -110,8 +110,6 @@ def test_allgather_gemm_unfused_cpu(world):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("MLSL_TEST_AGGEMM") != "1",
-                    reason="experimental fused all-gather + GEMM kernel: opt in with MLSL_TEST_AGGEMM=1 (not yet run on hardware)")
 @pytest.mark.parametrize("world,M,N,K", [(1, 256, 256, 64), (2, 512, 512, 256), (4, 1024, 768, 512)])
 def test_allgather_gemm_fused_gpu(world, M, N, K):
     _ag_gemm_case(world, "cuda", True, torch.bfloat16, 2e-2, M, N, K)

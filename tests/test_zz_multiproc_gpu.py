@@ -1,0 +1,31 @@
+"""One rank per GPU over real NVLink: spawns `torchrun tests/mp_gpu_check.py` at every N in {2, 4, 8} the box offers (VMM slab,
+NVLS multicast from 4 ranks, peer-to-peer below).  Skipped on single-GPU boxes - there the loop-back tests of this
+directory exercise the same kernels with N ranks sharing the GPU."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_one_rank_per_gpu(n):
+    if _ngpus() < n:
+        pytest.skip("needs %d GPUs, %d visible" % (n, _ngpus()))
+    env = dict(os.environ)
+    for k in ("CUDA_MODULE_LOADING", "MLSL_BACKEND", "MLSL_HEAP_SIZE_GB", "MLSL_WATCHDOG_SEC"):
+        env.pop(k, None)
+    env["MLSL_BACKEND"] = "cuda"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", str(29610 + n), os.path.join(ROOT, "tests", "mp_gpu_check.py")]
+    res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    tail = res.stdout[-6000:]
+    assert res.returncode == 0 and "ALL PASSED" in res.stdout and "FAILED" not in res.stdout.replace("0 FAILED", ""), tail
