@@ -11,9 +11,11 @@
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
 #include <sched.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -363,12 +365,14 @@ class CudaBackend final : public Backend {
   }
   bool stream_wait_ = false, inline_stream_ = false;
   // host-buffer pipeline (see launch_host_pipelined)
-  static constexpr int kPipeBufs = 3;
-  size_t pipe_chunk_ = (size_t)32 << 20;
-  char* pipe_buf_[kPipeBufs] = {nullptr, nullptr, nullptr};
+  static constexpr int kPipeBufs = 8;          // upper bound; MLSL_PIPE_BUFS of them are used
+  int pipe_bufs_ = 4;
+  size_t pipe_chunk_ = (size_t)16 << 20;
+  char* pipe_buf_[kPipeBufs] = {};
   cudaEvent_t pipe_h2d_[kPipeBufs] = {}, pipe_ar_[kPipeBufs] = {}, pipe_d2h_[kPipeBufs] = {}, pipe_start_ = nullptr;
   cudaStream_t h2d_stream_ = nullptr, d2h_stream_ = nullptr;
-  bool pipe_used_[kPipeBufs] = {false, false, false};
+  bool pipe_used_[kPipeBufs] = {};
+  void bind_to_gpu_numa_node();
   bool launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaStream_t s, bool solo = false);
   VmmSlab vmm_;
   char* mc_ = nullptr;
@@ -457,6 +461,60 @@ class CudaBackend final : public Backend {
   void launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s);
 };
 
+// One process per GPU: run the process (and place the memory it allocates from now on - pinned staging buffers, the
+// user's pinned tensors) on the NUMA node the GPU hangs off, unless the launcher already chose CPUs.  PCIe traffic that
+// crosses the socket interconnect was the suspect for the end-to-end bandwidth halving from 1 to 2 ranks in round 1.
+void CudaBackend::bind_to_gpu_numa_node() {
+  if (inproc_ || !ctx_->env.tune.numa_bind) return;
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device_) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  auto slurp = [](const std::string& path) {
+    std::string out;
+    if (FILE* f = fopen(path.c_str(), "r")) {
+      char buf[4096];
+      size_t n = fread(buf, 1, sizeof(buf) - 1, f);
+      buf[n] = 0;
+      out = buf;
+      fclose(f);
+    }
+    return out;
+  };
+  const std::string dir = std::string("/sys/bus/pci/devices/") + bus;
+  const std::string node_s = slurp(dir + "/numa_node");
+  const int node = node_s.empty() ? -1 : atoi(node_s.c_str());
+  if (node < 0) return;
+  const std::string cpus = slurp("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+  cpu_set_t want, cur, both;
+  CPU_ZERO(&want);
+  for (const char* p = cpus.c_str(); *p && *p != '\n';) {          // "0-31,64-95"
+    char* e = nullptr;
+    long a = strtol(p, &e, 10), z = a;
+    if (e == p) break;
+    if (*e == '-') z = strtol(e + 1, &e, 10);
+    for (long c = a; c <= z && c < CPU_SETSIZE; ++c) CPU_SET((int)c, &want);
+    p = *e == ',' ? e + 1 : e;
+  }
+  if (CPU_COUNT(&want) == 0 || sched_getaffinity(0, sizeof(cur), &cur) != 0) return;
+  CPU_AND(&both, &want, &cur);
+  // already narrowed by the launcher (numactl, taskset, cgroup) to a subset - of this node or of another: leave it alone
+  if (CPU_COUNT(&both) == 0 || CPU_COUNT(&cur) <= CPU_COUNT(&want)) {
+    MLSLB_LOG(LOG_INFO, "NUMA: GPU %s is on node %d; affinity left as set by the launcher (%d CPUs)", bus, node, CPU_COUNT(&cur));
+    return;
+  }
+  if (sched_setaffinity(0, sizeof(both), &both) == 0) {
+    unsigned long mask[16] = {0};
+    if (node < (int)(sizeof(mask) * 8)) {
+      mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+      syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof(mask) * 8);
+    }
+    MLSLB_LOG(LOG_INFO, "NUMA: rank %d bound to node %d (%d CPUs) next to GPU %s", ctx_->rank, node, CPU_COUNT(&both), bus);
+  }
+}
+
 void CudaBackend::init() {
   Bootstrap* b = ctx_->boot.get();
   inproc_ = b->inproc();
@@ -467,6 +525,7 @@ void CudaBackend::init() {
   if (const char* d = getenv("MLSL_DEVICE")) device_ = atoi(d);
   else device_ = lr % ndev;
   set_device();
+  bind_to_gpu_numa_node();
   cudaDeviceProp prop;
   MLSLB_CUDA(cudaGetDeviceProperties(&prop, device_));
   sm_count_ = prop.multiProcessorCount;
@@ -1012,7 +1071,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
 bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaStream_t s, bool solo) {
   const CommDesc& d = r.desc;
   const size_t es = dtype_size(d.dtype), bytes = d.count * es;
-  if (bytes < 2 * pipe_chunk_ || !r.send || !r.recv) return false;
+  if (bytes < ((size_t)64 << 20) || !r.send || !r.recv) return false;
   if (!ctx_->env.tune.host_pipeline) return false;
   cudaPointerAttributes as, ar;
   if (cudaPointerGetAttributes(&as, r.send) != cudaSuccess || cudaPointerGetAttributes(&ar, r.recv) != cudaSuccess) {
@@ -1024,7 +1083,9 @@ bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaS
   // the same kind of buffer everywhere)
   if (!is_host(as) || !is_host(ar)) return false;
   if (!pipe_buf_[0]) {
-    for (int b = 0; b < kPipeBufs; ++b) {
+    pipe_bufs_ = (int)std::min<long>(kPipeBufs, std::max<long>(2, ctx_->env.tune.pipe_bufs));
+    pipe_chunk_ = (size_t)std::max<long>(1, ctx_->env.tune.pipe_chunk_mb) << 20;
+    for (int b = 0; b < pipe_bufs_; ++b) {
       pipe_buf_[b] = (char*)alloc(pipe_chunk_, 4096);
       pipe_h2d_[b] = take_event();
       pipe_ar_[b] = take_event();
@@ -1042,7 +1103,7 @@ bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaS
   const size_t chunk_elems = pipe_chunk_ / es;
   int i = 0;
   for (size_t off = 0; off < d.count; off += chunk_elems, ++i) {
-    const int b = i % kPipeBufs;
+    const int b = i % pipe_bufs_;
     const size_t cnt = std::min(chunk_elems, d.count - off);
     if (pipe_used_[b]) MLSLB_CUDA(cudaStreamWaitEvent(h2d_stream_, pipe_d2h_[b], 0));   // buffer drained by its last user
     MLSLB_CUDA(cudaMemcpyAsync(pipe_buf_[b], (const char*)r.send + off * es, cnt * es, cudaMemcpyHostToDevice, h2d_stream_));
@@ -1062,7 +1123,7 @@ bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaS
     pipe_used_[b] = true;
   }
   // completion of the request = the last copies down
-  for (int b = 0; b < kPipeBufs; ++b)
+  for (int b = 0; b < pipe_bufs_; ++b)
     if (pipe_used_[b]) MLSLB_CUDA(cudaStreamWaitEvent(s, pipe_d2h_[b], 0));
   return true;
 }
