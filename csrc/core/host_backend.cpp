@@ -247,9 +247,20 @@ class HostBackend final : public Backend {
   }
   bool test(CommRequest& r) override { return r.state.load(std::memory_order_acquire) >= CommRequest::DONE; }
   void wait(CommRequest& r) override {
-    uint64_t spins = 0;
-    while (r.state.load(std::memory_order_acquire) < CommRequest::DONE)
+    uint64_t spins = 0, t0 = 0;
+    while (r.state.load(std::memory_order_acquire) < CommRequest::DONE) {
       if ((++spins & 0xff) == 0) sched_yield();
+      if ((spins & 0xffff) == 0) {   // a progress thread that died or a peer that failed must not leave the waiter spinning
+        if (ctx_->boot && ctx_->boot->poisoned())
+          MLSLB_ASSERT(false, "job poisoned by rank %d", (int)ctx_->boot->poisoned() - 1);
+        if (!t0) t0 = now_ns();
+        const int wd = ctx_->env.watchdog_sec;
+        if (wd > 0 && now_ns() - t0 > (uint64_t)wd * 1000000000ull) {
+          if (ctx_->boot) ctx_->boot->poison(ctx_->rank);
+          MLSLB_ASSERT(false, "watchdog: %s never completed on the progress thread", opkind_name(r.desc.kind));
+        }
+      }
+    }
   }
 
   void finalize() override {

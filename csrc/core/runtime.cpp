@@ -193,10 +193,17 @@ static void spin_until_launched(CommRequest* r) {
   }
 }
 
+static void rethrow_failed(CommRequest* r) {
+  const std::string msg = r->error;
+  r->state.store(CommRequest::IDLE, std::memory_order_release);
+  MLSLB_ASSERT(false, "%s failed on the progress thread: %s", opkind_name(r->desc.kind), msg.c_str());
+}
+
 void* CommRequest::wait() {
   int st = state.load(std::memory_order_acquire);
   if (st == IDLE) return recv;      // nothing in flight (already completed through Test)
   spin_until_launched(this);
+  if (state.load(std::memory_order_acquire) == FAILED) rethrow_failed(this);
   ctx->backend->wait(*this);
   done_ns = now_ns();
   if (!ctx->trace_prefix.empty()) ctx->trace_request(*this);
@@ -214,6 +221,7 @@ void* CommRequest::test(bool* done) {
     *done = false;
     return nullptr;
   }
+  if (st == FAILED) rethrow_failed(this);
   if (ctx->backend->test(*this)) {
     done_ns = now_ns();
     if (!ctx->trace_prefix.empty()) ctx->trace_request(*this);
@@ -342,9 +350,12 @@ void ProgressEngine::run(Server* s, int idx) {
       try {
         ctx_->backend->launch(*c.req);
       } catch (const std::exception& e) {
+        // the error belongs to the caller of Wait / Test: keep it on the request and fail it (a LAUNCHED state would
+        // leave host / net waiters spinning for a completion that never comes)
         fprintf(stderr, "(r%d) progress thread: %s\n", ctx_->rank, e.what());
         if (ctx_->boot) ctx_->boot->poison(ctx_->rank);
-        c.req->state.store(CommRequest::LAUNCHED, std::memory_order_release);
+        c.req->error = e.what();
+        c.req->state.store(CommRequest::FAILED, std::memory_order_release);
       }
       launched_.fetch_add(1, std::memory_order_relaxed);
       s->completed.fetch_add(1, std::memory_order_release);

@@ -86,7 +86,8 @@ struct CommDesc {
 
 class CommRequest {
  public:
-  enum State : int { IDLE = 0, QUEUED = 1, LAUNCHED = 2, DONE = 3 };
+  enum State : int { IDLE = 0, QUEUED = 1, LAUNCHED = 2, DONE = 3, FAILED = 4 };   // FAILED: launch threw on a progress thread
+  std::string error;     // what the launch said (valid once state == FAILED); re-thrown by wait() / test()
   CommRequest(RankContext* ctx, DType dt, int64_t uid, CommDesc::CompType ct);
   ~CommRequest();
   CommDesc desc;

@@ -23,7 +23,7 @@ from .api import CompressionType, OperationType, OptimizerType
 
 class _Bucket:
     __slots__ = ("params", "numel", "padded", "grad", "flat", "ps", "op", "pending", "master", "state1", "state2",
-                 "started", "offsets")
+                 "started", "offsets", "accumulating")
 
 
 class DistributedOptimizer:
@@ -76,7 +76,7 @@ class DistributedOptimizer:
         self.session = self.env.create_session()
         self.session.set_global_minibatch_size(self.world)
         mdt = comm.mlsl_dtype(dtype)
-        self.buckets, self._bucket_of = [], {}
+        self.buckets, self._bucket_of, self._offset_of = [], {}, {}
         align = 64  # elements: keeps every parameter view 16-byte aligned and the owned shards vector friendly
         for gi, plist in enumerate(groups):
             b = _Bucket()
@@ -107,7 +107,8 @@ class DistributedOptimizer:
                 p.data = view
                 p.grad = b.grad[off:off + p.numel()].view_as(p)
                 self._bucket_of[p] = b
-            b.pending, b.started = len(b.params), False
+                self._offset_of[p] = off
+            b.pending, b.started, b.accumulating = len(b.params), False, False
             b.master = b.state1 = b.state2 = None
             if self.mode == "fused":
                 owned = b.ps.get_owned_kernel_count() * b.ps.get_kernel_size()
@@ -121,14 +122,32 @@ class DistributedOptimizer:
             else:
                 b.ps.set_gradient_scale(self.scale)
 
+    def _reattach(self, p, b):
+        """`model.zero_grad()` (set_to_none=True by default) or `p.grad = None` makes autograd allocate a fresh gradient
+        outside the bucket; the exchange would then ship a stale bucket and the replicas would silently diverge.  Move
+        the gradient into the bucket (accumulating under no_sync, where the bucket holds earlier micro-batches) and
+        point p.grad at its bucket view again."""
+        off = self._offset_of[p]
+        view = b.grad[off:off + p.numel()].view_as(p)
+        g = p.grad
+        if g is not None and g.data_ptr() != view.data_ptr():
+            if getattr(b, "accumulating", False):
+                view.add_(g.to(view.dtype))
+            else:
+                view.copy_(g)
+            p.grad = view
+
     def _make_hook(self, p):
         def hook(_):
             b = self._bucket_of[p]
+            self._reattach(p, b)
             b.pending -= 1
             if b.pending == 0:
                 if not self._sync:          # gradient accumulation: keep adding into the bucket, exchange later
                     b.pending = len(b.params)
+                    b.accumulating = True
                     return
+                b.accumulating = False
                 with comm.use_state(self._state):
                     self._start(b)
         return hook
@@ -177,8 +196,15 @@ class DistributedOptimizer:
         self.steps += 1
 
     def zero_grad(self, set_to_none=False):
+        """Zero the gradient buckets and (re)point every p.grad at its bucket view - also after a `model.zero_grad()`
+        that set the gradients to None."""
         for b in self.buckets:
             b.grad.zero_()
+            b.accumulating = False
+            for p, off in zip(b.params, b.offsets):
+                view = b.grad[off:off + p.numel()].view_as(p)
+                if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                    p.grad = view
 
     def set_lr(self, lr):
         self.lr = lr

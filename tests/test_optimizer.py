@@ -39,7 +39,7 @@ def _reference(world, steps, kind, kw):
     return torch.cat([p.detach().reshape(-1) for p in m.parameters()])
 
 
-def _train(world, steps, kind, mode, backend, kw, bucket_mb=0.004, compress=False):
+def _train(world, steps, kind, mode, backend, kw, bucket_mb=0.004, compress=False, model_zero_grad=False):
     def body(r, mlsl):
         dev = "cuda" if backend == "cuda" else "cpu"
         m = _model().to(dev)
@@ -50,7 +50,10 @@ def _train(world, steps, kind, mode, backend, kw, bucket_mb=0.004, compress=Fals
         opt = mlsl.DistributedOptimizer(m.parameters(), **okw)
         assert len(opt.buckets) > 1            # several buckets: exercises per-bucket overlap bookkeeping
         for s in range(steps):
-            opt.zero_grad()
+            if model_zero_grad:
+                m.zero_grad()                  # set_to_none=True: autograd allocates fresh gradients outside the buckets
+            else:
+                opt.zero_grad()
             x, y = _batch(r, s)
             torch.nn.functional.mse_loss(m(x.to(dev)), y.to(dev)).backward()
             opt.step()
@@ -74,6 +77,15 @@ def test_distributed_optimizer_cpu(mode, kind, kw):
     for o in outs:
         assert torch.allclose(o, ref, rtol=2e-4, atol=2e-5), (o - ref).abs().max()
         assert torch.equal(o, outs[0])
+
+
+@pytest.mark.parametrize("mode", ["fused", "allreduce"])
+def test_model_zero_grad_set_to_none_keeps_replicas_in_sync(mode):
+    """The usual `model.zero_grad()` detaches p.grad from the bucket; the hooks move the fresh gradients back in."""
+    kw = dict(lr=0.05, momentum=0.9, weight_decay=0.01)
+    ref = _reference(2, 3, "sgd", kw)
+    for out in _train(2, 3, "sgd", mode, "host", kw, model_zero_grad=True):
+        assert torch.allclose(out, ref, rtol=1e-4, atol=1e-5)
 
 
 @pytest.mark.gpu
