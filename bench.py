@@ -346,7 +346,10 @@ def run_ours(args):
             e2e = {"error": repr(ex)[:300]}
 
     # kernels per timed step: giant messages on the multicast (NVLS) path may be issued as several launches
-    launches_per_step = int(env.get_tuning("last_launches")) if hasattr(env, "get_tuning") else 1
+    launches_per_step = 1                     # one persistent kernel walks the whole message ...
+    chunk = int(env.get_tuning("nvls_chunk_mb")) << 20
+    if nvls and chunk and S >= chunk + chunk // 2:
+        launches_per_step = -(-S // chunk)    # ... unless MLSL_NVLS_CHUNK_MB splits giant multicast messages
     out = {
         "metric": "allreduce_busbw_GBps",
         "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": warm + extra,

@@ -246,6 +246,7 @@ int mlsl_statistics_get_total_comm_size(mlsl_statistics s, size_t* v) { C_GUARD(
 int mlsl_statistics_get_total_comm_cycles(mlsl_statistics s, unsigned long long* v) { C_GUARD(*need(v) = H<Statistics>(s)->GetTotalCommCycles()) }
 int mlsl_statistics_get_total_compute_cycles(mlsl_statistics s, unsigned long long* v) { C_GUARD(*need(v) = H<Statistics>(s)->GetTotalComputeCycles()) }
 int mlsl_statistics_get_comm_nanos(mlsl_statistics s, size_t i, unsigned long long* v) { C_GUARD(*need(v) = H<Statistics>(s)->GetCommNanos(i)) }
+int mlsl_statistics_get_device_comm_nanos(mlsl_statistics s, size_t i, unsigned long long* v) { C_GUARD(*need(v) = H<Statistics>(s)->GetDeviceCommNanos(i)) }
 int mlsl_statistics_get_compute_nanos(mlsl_statistics s, size_t i, unsigned long long* v) { C_GUARD(*need(v) = H<Statistics>(s)->GetComputeNanos(i)) }
 
 // ---- Session ----

@@ -269,7 +269,7 @@ void ActivationImpl::start(void* buf) {
   st->enter(op->opIndex, kind, index, StatisticsImpl::START);
   if (needComm && req && req->desc.kind != OpKind::BARRIER)
     req->start(buf, req->out_of_place_default() ? (char*)buf + sendRegionBytes : buf);
-  st->leave(op->opIndex, kind, index, StatisticsImpl::START);
+  st->leave(op->opIndex, kind, index, StatisticsImpl::START, needComm ? req : nullptr);
 }
 
 void* ActivationImpl::wait() {
@@ -279,7 +279,7 @@ void* ActivationImpl::wait() {
   void* ret = nullptr;
   // the data we consume was sent by the PEER activation (reference src/mlsl_impl.cpp:366-386)
   if (needComm && peer && peer->req && peer->req->desc.kind != OpKind::BARRIER) ret = peer->req->wait();
-  st->leave(op->opIndex, kind, index, StatisticsImpl::WAIT);
+  st->leave(op->opIndex, kind, index, StatisticsImpl::WAIT, needComm && peer ? peer->req : nullptr);
   return ret;
 }
 
@@ -363,14 +363,14 @@ void ParameterSetImpl::start_gradient(void* buf) {
     if (distributedUpdate) commBuf.allocate();
     gradReq->start(buf, distributedUpdate ? commBuf.ptr : buf);
   }
-  st->leave(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::START);
+  st->leave(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::START, needComm ? gradReq : nullptr);
 }
 
 void* ParameterSetImpl::wait_gradient() {
   StatisticsImpl* st = op->session->stats;
   st->enter(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::WAIT);
   void* p = needComm ? gradReq->wait() : nullptr;
-  st->leave(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::WAIT);
+  st->leave(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::WAIT, needComm ? gradReq : nullptr);
   return p;
 }
 
@@ -380,7 +380,7 @@ void* ParameterSetImpl::test_gradient(bool* done) {
   void* p = nullptr;
   if (needComm) p = gradReq->test(done);
   else *done = true;
-  st->leave(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::TEST);
+  st->leave(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::TEST, needComm ? gradReq : nullptr);
   return p;
 }
 
@@ -389,14 +389,14 @@ void ParameterSetImpl::start_increment(void* buf) {
   st->enter(op->opIndex, StatisticsImpl::PARAM_INC, index, StatisticsImpl::START);
   // in-place all-gather: rank r's owned shard already sits at buf + r*owned*kernelSize
   if (needComm && distributedUpdate) incReq->start(buf, buf);
-  st->leave(op->opIndex, StatisticsImpl::PARAM_INC, index, StatisticsImpl::START);
+  st->leave(op->opIndex, StatisticsImpl::PARAM_INC, index, StatisticsImpl::START, needComm && distributedUpdate ? incReq : nullptr);
 }
 
 void* ParameterSetImpl::wait_increment() {
   StatisticsImpl* st = op->session->stats;
   st->enter(op->opIndex, StatisticsImpl::PARAM_INC, index, StatisticsImpl::WAIT);
   void* p = (needComm && distributedUpdate) ? incReq->wait() : nullptr;
-  st->leave(op->opIndex, StatisticsImpl::PARAM_INC, index, StatisticsImpl::WAIT);
+  st->leave(op->opIndex, StatisticsImpl::PARAM_INC, index, StatisticsImpl::WAIT, needComm && distributedUpdate ? incReq : nullptr);
   return p;
 }
 
@@ -432,7 +432,7 @@ void ParameterSetImpl::start_fused(void* grad, void* param, DataType paramType, 
   StatisticsImpl* st = op->session->stats;
   st->enter(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::START);
   fusedReq->start(grad, param);
-  st->leave(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::START);
+  st->leave(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::START, fusedReq);
 }
 
 void ParameterSetImpl::wait_fused() {
@@ -440,7 +440,7 @@ void ParameterSetImpl::wait_fused() {
   StatisticsImpl* st = op->session->stats;
   st->enter(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::WAIT);
   fusedReq->wait();
-  st->leave(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::WAIT);
+  st->leave(op->opIndex, StatisticsImpl::PARAM_GRAD, index, StatisticsImpl::WAIT, fusedReq);
 }
 
 size_t ParameterSetImpl::grad_msg_bytes() const { return gradReq ? gradReq->msg_bytes() : 0; }

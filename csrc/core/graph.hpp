@@ -183,6 +183,7 @@ class OperationImpl : public Operation {
 struct EntityStat {
   unsigned long long commCycles = 0, computeCycles = 0, isolationCycles = 0;
   unsigned long long commNs = 0, computeNs = 0;
+  unsigned long long devCommNs = 0, devRuns = 0, isolationDevNs = 0;   // device-timed duration of the collective itself
   size_t commBytes = 0, bytesPerIter = 0;
 };
 struct OpStat {
@@ -199,7 +200,8 @@ class StatisticsImpl : public Statistics {
   // Bracket an API call: enter() books the time since the previous MLSL call as compute, leave() books the
   // call itself as communication.
   void enter(size_t opIdx, Kind k, size_t entIdx, Action a);
-  void leave(size_t opIdx, Kind k, size_t entIdx, Action a);
+  void leave(size_t opIdx, Kind k, size_t entIdx, Action a, mlslb::CommRequest* req = nullptr);
+  static double cycles_per_ns();
   void start();
   void stop();
   void reset();

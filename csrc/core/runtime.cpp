@@ -500,7 +500,7 @@ void RankContext::free_group(ProcessGroup* g) {
 }
 
 void RankContext::trace_request(const CommRequest& r) {
-  TraceEvent e{r.start_ns, r.done_ns, (int)r.desc.kind, r.desc.group ? r.desc.group->row : -1, r.lane, r.msg_bytes()};
+  TraceEvent e{r.start_ns, r.done_ns, (int)r.desc.kind, r.desc.group ? r.desc.group->row : -1, r.lane, r.msg_bytes(), r.device_ns_last};
   std::lock_guard<std::mutex> g(trace_mu);
   if (trace.size() < (size_t)1 << 20) trace.push_back(e);   // bounded: ~32 MB per rank
 }
@@ -523,9 +523,9 @@ void RankContext::trace_dump() {
   fprintf(f, "{\"ph\":\"M\",\"pid\":%d,\"name\":\"process_name\",\"args\":{\"name\":\"mlsl rank %d (%s)\"}}", rank, rank,
           backend ? backend->name() : "finalized");
   for (const TraceEvent& e : ev)
-    fprintf(f, ",\n{\"ph\":\"X\",\"pid\":%d,\"tid\":%d,\"ts\":%.3f,\"dur\":%.3f,\"name\":\"%s\",\"args\":{\"bytes\":%zu,\"row\":%d,\"lane\":%d}}",
+    fprintf(f, ",\n{\"ph\":\"X\",\"pid\":%d,\"tid\":%d,\"ts\":%.3f,\"dur\":%.3f,\"name\":\"%s\",\"args\":{\"bytes\":%zu,\"row\":%d,\"lane\":%d,\"device_us\":%.3f}}",
             rank, (e.row < 0 ? 0 : e.row) * 2 + e.lane, e.t0 / 1000.0, (e.t1 > e.t0 ? e.t1 - e.t0 : 0) / 1000.0,
-            opkind_name((OpKind)e.kind), e.bytes, e.row, e.lane);
+            opkind_name((OpKind)e.kind), e.bytes, e.row, e.lane, e.device_ns / 1000.0);
   fprintf(f, "\n]}\n");
   fclose(f);
   MLSLB_LOG(LOG_INFO, "wrote %zu trace events to %s", ev.size(), path.c_str());

@@ -88,6 +88,15 @@ class CommRequest {
  public:
   enum State : int { IDLE = 0, QUEUED = 1, LAUNCHED = 2, DONE = 3, FAILED = 4 };   // FAILED: launch threw on a progress thread
   std::string error;     // what the launch said (valid once state == FAILED); re-thrown by wait() / test()
+  // device-measured duration of completed runs that nobody has read yet (CUDA backend: an event pair around the kernel,
+  // harvested when the run is known to be complete); statistics and the trace take it with take_device_ns()
+  uint64_t device_ns_pending = 0;
+  uint64_t device_ns_last = 0;
+  uint64_t take_device_ns() {
+    uint64_t v = device_ns_pending;
+    device_ns_pending = 0;
+    return v;
+  }
   CommRequest(RankContext* ctx, DType dt, int64_t uid, CommDesc::CompType ct);
   ~CommRequest();
   CommDesc desc;
@@ -130,6 +139,8 @@ class Backend {
  public:
   virtual ~Backend() {}
   virtual const char* name() const = 0;
+  virtual bool stream_ordered_wait() const { return false; }   // Wait only orders a stream (the host never blocks)
+  virtual void harvest_device_time(CommRequest&) {}             // fold finished device timings into the request
   virtual bool is_device() const { return false; }
   virtual void* alloc(size_t bytes, size_t align) = 0;
   virtual void free(void* p) = 0;
@@ -282,6 +293,7 @@ struct RankContext {
     uint64_t t0, t1;
     int kind, row, lane;
     size_t bytes;
+    uint64_t device_ns;   // duration of the kernel on the device (0 = not measured)
   };
   std::string trace_prefix;
   std::mutex trace_mu;

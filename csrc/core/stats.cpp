@@ -49,7 +49,7 @@ void StatisticsImpl::stop() { started = false; }
 void StatisticsImpl::reset() {
   for (auto& o : ops)
     for (auto& e : o.ent) {
-      e.commCycles = e.computeCycles = e.commNs = e.computeNs = 0;
+      e.commCycles = e.computeCycles = e.commNs = e.computeNs = e.devCommNs = e.devRuns = 0;
       e.commBytes = 0;
     }
   batches = 0;
@@ -83,16 +83,42 @@ void StatisticsImpl::enter(size_t opIdx, Kind k, size_t entIdx, Action a) {
   lastNs = n;
 }
 
-void StatisticsImpl::leave(size_t opIdx, Kind k, size_t entIdx, Action a) {
+void StatisticsImpl::leave(size_t opIdx, Kind k, size_t entIdx, Action a, CommRequest* req) {
   if (!enabled || !started || collecting) return;
   if (!resolve(this, opIdx, k, entIdx, a)) return;
   unsigned long long c = cycles_now(), n = now_ns();
   EntityStat& e = ops[opIdx].ent[slot(opIdx, k, entIdx)];
   e.commCycles += c - lastCycles;
   e.commNs += n - lastNs;
+  // Device timestamps: what the collective took ON THE DEVICE, from the event pair the backend records
+  // around the kernel.  With stream-ordered waits the host calls above only bracket a launch, so the device duration is
+  // what the comm counters have to carry; with host-blocking waits the bracket already contains it.
+  if (req) {
+    RankContext* ctx = session->ctx;
+    ctx->backend->harvest_device_time(*req);
+    if (unsigned long long d = req->take_device_ns()) {
+      e.devCommNs += d;
+      e.devRuns++;
+      if (ctx->backend->stream_ordered_wait()) {
+        e.commNs += d;
+        e.commCycles += (unsigned long long)((double)d * cycles_per_ns());
+      }
+    }
+  }
   if (a == START) e.commBytes += e.bytesPerIter;
   lastCycles = c;
   lastNs = n;
+}
+
+double StatisticsImpl::cycles_per_ns() {
+  static double ratio = 0.0;
+  if (ratio == 0.0) {
+    const unsigned long long c0 = cycles_now(), n0 = now_ns();
+    while (now_ns() - n0 < 2000000ull) {}
+    ratio = (double)(cycles_now() - c0) / (double)(now_ns() - n0);
+    if (!(ratio > 0.0)) ratio = 1.0;
+  }
+  return ratio;
 }
 
 void StatisticsImpl::collect_isolation() {
@@ -110,6 +136,8 @@ void StatisticsImpl::collect_isolation() {
   RankContext* ctx = session->ctx;
   const int iters = ctx->env.stats_iters, skip = ctx->env.stats_skip;
   collecting = true;
+  const bool was_stream = ctx->backend->stream_ordered_wait();
+  if (was_stream) ctx->backend->set_wait_mode(false);      // dry runs block the host: the bracket holds the whole collective
   size_t maxParam = 64;
   for (auto o : session->ops)
     for (auto p : o->params)
@@ -153,6 +181,7 @@ void StatisticsImpl::collect_isolation() {
     }
   }
   ctx->backend->free(scratch);
+  if (was_stream) ctx->backend->set_wait_mode(true);
   collecting = false;
   reset();
 }
@@ -175,16 +204,16 @@ void StatisticsImpl::print() {
   for (FILE* o : outs) {
     if (!o) continue;
     fprintf(o, "MLSL statistics (batches %llu, global minibatch %zu)\n", batches, session->globalMb);
-    fprintf(o, "%-24s %-5s %12s %16s %16s %16s %14s\n", "operation", "ent", "KB/iter", "isol Kcyc/img", "comm Kcyc/img",
-            "comp Kcyc/img", "comm us/iter");
+    fprintf(o, "%-24s %-5s %12s %16s %16s %16s %14s %14s\n", "operation", "ent", "KB/iter", "isol Kcyc/img", "comm Kcyc/img",
+            "comp Kcyc/img", "comm us/iter", "device us/run");
     for (size_t i = 0; i < ops.size(); ++i) {
       OperationImpl* op = session->ops[i];
       for (size_t s = 0; s < ops[i].ent.size(); ++s) {
         const EntityStat& e = ops[i].ent[s];
         if (!e.bytesPerIter && !e.commCycles) continue;
-        fprintf(o, "%-24s %-5s %12.1f %16.2f %16.2f %16.2f %14.1f\n", op->name.c_str(), kind_name(s, op),
+        fprintf(o, "%-24s %-5s %12.1f %16.2f %16.2f %16.2f %14.1f %14.1f\n", op->name.c_str(), kind_name(s, op),
                 e.bytesPerIter / 1024.0, e.isolationCycles / 1000.0 / iters / mb, e.commCycles / 1000.0 / nb / mb,
-                e.computeCycles / 1000.0 / nb / mb, e.commNs / 1000.0 / nb);
+                e.computeCycles / 1000.0 / nb / mb, e.commNs / 1000.0 / nb, e.devRuns ? e.devCommNs / 1000.0 / e.devRuns : 0.0);
       }
     }
     fprintf(o, "TOTAL: comm size %zu bytes, isolation %llu cycles, comm %llu cycles, compute %llu cycles\n",
@@ -232,6 +261,11 @@ unsigned long long Statistics::GetComputeCycles(size_t opIdx) {
 unsigned long long Statistics::GetCommNanos(size_t opIdx) {
   unsigned long long t = 0;
   for (auto& e : opstat(this, opIdx).ent) t += e.commNs;
+  return t;
+}
+unsigned long long Statistics::GetDeviceCommNanos(size_t opIdx) {
+  unsigned long long t = 0;
+  for (auto& e : opstat(this, opIdx).ent) t += e.devCommNs;
   return t;
 }
 unsigned long long Statistics::GetComputeNanos(size_t opIdx) {

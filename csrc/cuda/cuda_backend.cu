@@ -60,6 +60,8 @@ struct CudaReqState {
   cudaStream_t stream = nullptr;
   bool inflight = false;
   bool recorded = false;          // `done` was recorded for the current launch
+  cudaEvent_t t0 = nullptr, t1 = nullptr;   // timing pair around the kernel (statistics / trace), from the timing pool
+  bool timed = false;             // t0 / t1 were recorded for a run whose duration has not been read yet
 };
 
 struct PeerInfo {
@@ -147,6 +149,43 @@ class CudaBackend final : public Backend {
     std::lock_guard<std::mutex> g(park_mu_);
     event_pool_.push_back(ev);
   }
+  // device timestamps: one timing-enabled event pair per request brackets the kernel on its stream
+  bool want_timing() const { return ctx_->env.tune.dev_timestamps && (ctx_->env.stats || !ctx_->trace_prefix.empty()); }
+  cudaEvent_t take_timing_event() {
+    {
+      std::lock_guard<std::mutex> g(park_mu_);
+      if (!tevent_pool_.empty()) {
+        cudaEvent_t ev = tevent_pool_.back();
+        tevent_pool_.pop_back();
+        return ev;
+      }
+    }
+    cudaEvent_t ev = nullptr;
+    MLSLB_CUDA(cudaEventCreate(&ev));
+    return ev;
+  }
+  void harvest(CommRequest& r, CudaReqState* st, bool complete_for_sure) {
+    if (!st->timed) return;
+    if (!complete_for_sure) {
+      cudaError_t q = cudaEventQuery(st->t1);
+      if (q == cudaErrorNotReady) {
+        cudaGetLastError();
+        return;
+      }
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, st->t0, st->t1) == cudaSuccess) {
+      r.device_ns_last = (uint64_t)((double)ms * 1e6);
+      r.device_ns_pending += r.device_ns_last;
+    } else {
+      cudaGetLastError();
+    }
+    st->timed = false;
+  }
+  void harvest_device_time(CommRequest& r) override {
+    if (auto* st = (CudaReqState*)r.backend_state) harvest(r, st, false);
+  }
+  bool stream_ordered_wait() const override { return stream_wait_; }
   void ensure_events(CudaReqState* st) {
     if (st->done) return;
     st->ready = take_event();
@@ -173,6 +212,11 @@ class CudaBackend final : public Backend {
     }
     give_event(st->ready);
     give_event(st->done);
+    if (st->t0) {
+      std::lock_guard<std::mutex> g(park_mu_);
+      tevent_pool_.push_back(st->t0);
+      tevent_pool_.push_back(st->t1);
+    }
     delete st;
     r.backend_state = nullptr;
   }
@@ -317,6 +361,8 @@ class CudaBackend final : public Backend {
     pipe_start_ = nullptr;
     for (cudaEvent_t ev : event_pool_) cudaEventDestroy(ev);
     event_pool_.clear();
+    for (cudaEvent_t ev : tevent_pool_) cudaEventDestroy(ev);
+    tevent_pool_.clear();
     quiet_barrier();
     for (size_t p = 0; p < peer_slab_.size(); ++p)
       if (peer_opened_[p]) cudaIpcCloseMemHandle(peer_slab_[p]);
@@ -407,6 +453,7 @@ class CudaBackend final : public Backend {
   };
   std::vector<Parked> parked_;
   std::vector<cudaEvent_t> event_pool_;
+  std::vector<cudaEvent_t> tevent_pool_;    // timing-enabled events (device timestamps)
   std::mutex park_mu_;
   void park_stages(CudaReqState* st) {
     std::lock_guard<std::mutex> g(park_mu_);
@@ -570,6 +617,12 @@ void CudaBackend::init() {
   MLSLB_CUDA(cudaHostGetDevicePointer((void**)&err_dev_, (void*)err_host_, 0));
   if (const char* m = getenv("MLSL_STREAM_MODE")) inline_stream_ = !strcmp(m, "inline");
   MLSLB_CUDA(init_kernel_attributes());
+  if (ctx_->env.stats || !ctx_->trace_prefix.empty())
+    for (int i = 0; i < 128; ++i) {
+      cudaEvent_t ev = nullptr;
+      MLSLB_CUDA(cudaEventCreate(&ev));
+      tevent_pool_.push_back(ev);
+    }
   for (int i = 0; i < 256; ++i) {
     cudaEvent_t ev = nullptr;
     MLSLB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -702,6 +755,7 @@ void CudaBackend::drop_stages(CudaReqState* st, bool) {
 }
 
 void CudaBackend::finish(CommRequest& r, CudaReqState* st) {
+  harvest(r, st, true);
   st->inflight = false;
   drop_stages(st, true);
   check_error(opkind_name(r.desc.kind));
@@ -725,7 +779,22 @@ void CudaBackend::launch(CommRequest& r) {
     ~NvtxPop() { if (on) nvtxRangePop(); }
   } nvtx_pop{nvtx};
   if (!solo) loopback_rendezvous(*g, r.lane);
+  const bool timing = want_timing();
+  if (timing) {
+    harvest(r, st, false);           // the previous run of a persistent request, if nobody asked in between
+    if (!st->timed) {
+      if (!st->t0) {
+        st->t0 = take_timing_event();
+        st->t1 = take_timing_event();
+      }
+      MLSLB_CUDA(cudaEventRecord(st->t0, s));
+    }
+  }
   launch_single(r, st, s);
+  if (timing && !st->timed) {
+    MLSLB_CUDA(cudaEventRecord(st->t1, s));
+    st->timed = true;
+  }
   st->recorded = false;
   if (!(eventless() && st->stages.empty())) {
     ensure_events(st);

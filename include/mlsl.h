@@ -271,6 +271,7 @@ int mlsl_parameter_set_start_fused_update(mlsl_parameter_set param_set, void* gr
 int mlsl_parameter_set_wait_fused_update(mlsl_parameter_set param_set);
 int mlsl_parameter_set_set_gradient_scale(mlsl_parameter_set param_set, float scale);
 int mlsl_statistics_get_comm_nanos(mlsl_statistics stat, size_t op_idx, unsigned long long* ns);
+int mlsl_statistics_get_device_comm_nanos(mlsl_statistics stat, size_t op_idx, unsigned long long* ns);   /* [ext] */
 int mlsl_statistics_get_compute_nanos(mlsl_statistics stat, size_t op_idx, unsigned long long* ns);
 /* N virtual ranks inside one process (tests, single-GPU loopback): create a world, then every rank thread binds
  * itself before calling mlsl_environment_get_env()/init() and unbinds after finalize. */

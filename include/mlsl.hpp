@@ -277,6 +277,9 @@ class Statistics {
   // [ext] same counters in nanoseconds (cycle counters are TSC ticks as in the reference)
   unsigned long long GetCommNanos(size_t opIdx);
   unsigned long long GetComputeNanos(size_t opIdx);
+  // [ext] duration of the operation's collectives measured ON THE DEVICE (CUDA event pair around each kernel); 0 on
+  // host backends.  With stream-ordered waits this is also what GetCommCycles / GetCommNanos carry.
+  unsigned long long GetDeviceCommNanos(size_t opIdx);
 };
 
 class Session {

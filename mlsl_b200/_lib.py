@@ -231,6 +231,7 @@ def _declare(l):
         "mlsl_statistics_get_total_comm_cycles": [H, P(c_ull)],
         "mlsl_statistics_get_total_compute_cycles": [H, P(c_ull)],
         "mlsl_statistics_get_comm_nanos": [H, c_size_t, P(c_ull)],
+        "mlsl_statistics_get_device_comm_nanos": [H, c_size_t, P(c_ull)],
         "mlsl_statistics_get_compute_nanos": [H, c_size_t, P(c_ull)],
         "mlsl_inproc_world_create": [c_int, P(c_int)],
         "mlsl_inproc_world_destroy": [c_int],

@@ -393,6 +393,10 @@ class Statistics(_Handle):
     def get_comm_nanos(self, op_idx):
         return self._get("mlsl_statistics_get_comm_nanos", c_ull, op_idx)
 
+    def get_device_comm_nanos(self, op_idx):
+        """Duration of the operation's collectives measured on the device (event pair around each kernel)."""
+        return self._get("mlsl_statistics_get_device_comm_nanos", c_ull, op_idx)
+
     def get_compute_nanos(self, op_idx):
         return self._get("mlsl_statistics_get_compute_nanos", c_ull, op_idx)
 
