@@ -249,13 +249,13 @@ def run_ours(args):
     if sampler:
         sampler.start()
     warm = max(args.warmup, 3)
-    # warm-up: at least `warm` steps AND ~0.4 s of load, so the clocks have settled when the timed region starts
-    t_w = time.perf_counter()
-    extra = 0
-    while time.perf_counter() - t_w < 0.4 and extra < 2000:
+    # warm-up: at least `warm` steps AND ~0.4 s of load, so the clocks have settled when the timed region starts.  The
+    # number of extra steps must be the SAME on every rank (it is a collective): agree on the slowest rank's step time
+    est = timed(lambda: step_device(x, y, n), 3, 1)
+    extra = max(0, min(2000, int(400.0 / max(est, 1e-3))))
+    for k in range(extra):
         step_device(x, y, n)
-        extra += 1
-        if extra % 8 == 0:
+        if k % 8 == 7:
             torch.cuda.synchronize()
     ms, h0, h1 = timed(lambda: step_device(x, y, n), args.steps, warm, want_window=True)
     clocks = sampler.stop(h0, h1) if sampler else None
@@ -352,7 +352,7 @@ def run_ours(args):
         launches_per_step = -(-S // chunk)    # ... unless MLSL_NVLS_CHUNK_MB splits giant multicast messages
     out = {
         "metric": "allreduce_busbw_GBps",
-        "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": warm + extra,
+        "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": warm + extra + 4,
         "ms_per_step": round(ms, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic", "impl": "ours",
         "busbw_per_gpu_GBps": round(busbw, 3), "algbw_GBps": round(algbw, 3), "roofline": roofline(world, S, ms, nvls),

@@ -36,6 +36,8 @@ static const TuneDesc kTune[] = {
     {"nvls_min_ranks", "MLSL_NVLS_MIN_RANKS", &Tunables::nvls_min_ranks, "multicast kernels from this group size up"},
     {"ar_unroll", "MLSL_AR_UNROLL", &Tunables::ar_unroll, "vectors per thread and pass of the large all-reduce"},
     {"ar_channels", "MLSL_AR_CHANNELS", &Tunables::ar_channels, "CTAs of the large all-reduce"},
+    {"ar_p2p_pct", "MLSL_AR_P2P_PCT", &Tunables::ar_p2p_pct, "multicast all-reduce: % of the message moved peer-to-peer concurrently"},
+    {"ar_p2p_cta_pct", "MLSL_AR_P2P_CTA_PCT", &Tunables::ar_p2p_cta_pct, "... on this % of the CTAs"},
     {"nvls_chunk_mb", "MLSL_NVLS_CHUNK_MB", &Tunables::nvls_chunk_mb, "split giant multicast all-reduces"},
     {"bulk_copy_kb", "MLSL_BULK_COPY_KB", &Tunables::bulk_copy_kb, "cp.async.bulk rings for segments >= this"},
     {"nvls_collectives", "MLSL_NVLS_COLLECTIVES", &Tunables::nvls_collectives, "multimem reduce-scatter / bcast"},

@@ -26,9 +26,12 @@ struct Tunables {
   long nvls_min_ranks = 4;      // MLSL_NVLS_MIN_RANKS: multicast kernels from this group size up
   long ar_unroll = 0;           // MLSL_AR_UNROLL: 16-byte vectors per thread and pass of the large all-reduce (0 = by size)
   long ar_channels = 0;         // MLSL_AR_CHANNELS: CTAs of the large all-reduce (0 = MLSL_NUM_CHANNELS / auto)
+  long ar_p2p_pct = 0;          // MLSL_AR_P2P_PCT: multicast all-reduce - this % of a large message goes peer-to-peer at the same time
+  long ar_p2p_cta_pct = 33;     // MLSL_AR_P2P_CTA_PCT: ... on this % of the CTAs
   long nvls_chunk_mb = 0;       // MLSL_NVLS_CHUNK_MB: split giant multicast all-reduces into launches of this size (0 = one launch)
   long bulk_copy_kb = 256;      // MLSL_BULK_COPY_KB: gather-like collectives move segments >= this with cp.async.bulk rings
-  long nvls_collectives = 1;    // MLSL_NVLS_COLLECTIVES: multimem reduce-scatter / bcast when buffers are symmetric
+  long nvls_collectives = 3;    // MLSL_NVLS_COLLECTIVES: bit 0 multimem.ld_reduce reduce-scatter / reduce, bit 1 multimem.st bcast,
+                                // bit 2 multimem.st all-gather - taken when the members' buffers are symmetric
   long host_pipeline = 1;       // MLSL_HOST_PIPELINE: chunked H2D / all-reduce / D2H pipeline for host-resident buffers
   long pipe_chunk_mb = 16;      // MLSL_PIPE_CHUNK_MB: chunk size of that pipeline
   long pipe_bufs = 4;           // MLSL_PIPE_BUFS: device buffers of that pipeline (2..8)

@@ -978,8 +978,15 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
         const int unroll = (int)ctx_->env.tune.ar_unroll;
         for (size_t off = 0; off < n; off += per) {
           size_t cnt = std::min(per, n - off);
-          MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, so + off * es, ro + off * es, cnt, d.scale,
-                                      ar_channels(ceil_div(cnt * es, (size_t)P)), unroll, s));
+          const int chn = ar_channels(ceil_div(cnt * es, (size_t)P));
+          // hybrid (multicast + peer-to-peer at once) only where it can pay: big messages on a full grid
+          int p2p_cta = 0;
+          float p2p_frac = 0.f;
+          if (dc.mc && ctx_->env.tune.ar_p2p_pct > 0 && cnt * es >= ((size_t)32 << 20) && chn >= 8) {
+            p2p_cta = std::max(1, (int)(chn * ctx_->env.tune.ar_p2p_cta_pct / 100));
+            p2p_frac = (float)ctx_->env.tune.ar_p2p_pct / 100.f;
+          }
+          MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, so + off * es, ro + off * es, cnt, d.scale, chn, unroll, p2p_cta, p2p_frac, s));
         }
       }
       break;
@@ -1183,7 +1190,7 @@ bool CudaBackend::launch_host_pipelined(CommRequest& r, const DevComm& dc, cudaS
       if (d.scale != 1.0f) MLSLB_CUDA(launch_scale(d.dtype, pipe_buf_[b], cnt, d.scale, s));
     } else {
       MLSLB_CUDA(launch_allreduce(dc, d.dtype, d.rop, o, o, cnt, d.scale, ar_channels(ceil_div(cnt * es, (size_t)P)),
-                                  (int)ctx_->env.tune.ar_unroll, s));
+                                  (int)ctx_->env.tune.ar_unroll, 0, 0.f, s));
     }
     MLSLB_CUDA(cudaEventRecord(pipe_ar_[b], s));
     MLSLB_CUDA(cudaStreamWaitEvent(d2h_stream_, pipe_ar_[b], 0));

@@ -18,9 +18,15 @@ static_assert(kQuantBlock == 128, "one warp handles one 128-element block (32 la
 
 __host__ __device__ __forceinline__ size_t ru256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// stage layout (per rank): [q1 | s1 | q2 | s2], block counts rounded up to whole superblocks (4 blocks = 512 elements:
+// one warp pass with 16 bytes per lane)
+__host__ __device__ __forceinline__ size_t quant_nblk4(size_t count) {
+  const size_t nblk = (count + kQuantBlock - 1) / kQuantBlock;
+  return (nblk + 3) & ~(size_t)3;
+}
 size_t allreduce_quant_stage_bytes(size_t count) {
-  size_t nblk = (count + kQuantBlock - 1) / kQuantBlock;
-  return 2 * (ru256(nblk * kQuantBlock) + ru256(nblk * sizeof(float)));
+  const size_t nb = quant_nblk4(count);
+  return 2 * (ru256(nb * kQuantBlock) + ru256(nb * sizeof(float)));
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -61,20 +67,28 @@ __global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, u
                                                                   unsigned long long stage_off, float* residual,
                                                                   size_t count, float out_scale) {
   __shared__ PeerTable pt;
+  __shared__ int s_symmetric;
   // peers need my staging area only; x / y are touched by this rank alone
   const unsigned long long t = comm_begin(dc, pt, stage_off, stage_off, NoAux());
   const int P = dc.nranks, me = dc.me;
+  if (threadIdx.x == 0) {
+    int sym = dc.mc != nullptr && !pt.failed;
+    for (int p = 0; p < P; ++p) sym &= (pt.send[p] - dc.slab[p]) == (long long)stage_off;
+    s_symmetric = sym;
+  }
   const float* x = reinterpret_cast<const float*>(dc.slab[me] + send_off);
   float* y = reinterpret_cast<float*>(dc.slab[me] + recv_off);
   const size_t nblk = (count + kQuantBlock - 1) / kQuantBlock;
-  const size_t qbytes = ru256(nblk * kQuantBlock), sbytes = ru256(nblk * sizeof(float));
-  const size_t blk_per = (nblk + P - 1) / P;
+  const size_t nblk4 = quant_nblk4(count), nsb = nblk4 / 4;
+  const size_t qbytes = ru256(nblk4 * kQuantBlock), sbytes = ru256(nblk4 * sizeof(float));
+  const size_t q2_off = qbytes + sbytes, s2_off = 2 * qbytes + sbytes;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const size_t C = gridDim.x, c = blockIdx.x;
   char* mystage = pt.send[me];
 
-  // ---- phase 1: (x + residual) -> fp8 blocks in my staging area; residual <- quantisation error ---------------
-  for (size_t b = c + (size_t)warp * C; b < nblk; b += C * nwarp) {
+  // ---- phase 1: (x + residual) -> fp8 blocks in my staging area; residual <- quantisation error.  The only pass over
+  //      the fp32 input: 4 + 4 bytes read, 4 + 1 written per element, one warp per 128-element block. --------------------
+  for (size_t b = c + (size_t)warp * C; b < nblk4; b += C * nwarp) {
     const size_t e0 = b * kQuantBlock + (size_t)lane * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f), r = v;
     if (e0 + 3 < count) {
@@ -103,47 +117,95 @@ __global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, u
   }
   comm_sync(dc, pt, t, 1, true);
 
-  // ---- phase 2: my slice: pull the peers' fp8 blocks, accumulate in fp32 (fixed peer order), re-quantise --------
-  const size_t blo = min(nblk, (size_t)me * blk_per), bhi = min(nblk, blo + blk_per);
-  // first block of my slice that belongs to this channel (block b is handled by channel b % C everywhere)
-  size_t bstart = blo + ((c + C - blo % C) % C);
-  for (size_t b = bstart + (size_t)warp * C; b < bhi; b += C * nwarp) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // ---- phase 2: my slice of superblocks (4 blocks = 512 elements per warp pass, SIXTEEN bytes per lane on the wire):
+  //      pull the peers' fp8, accumulate in fp32 in fixed peer order, re-quantise, PUSH the result into every member's
+  //      gather area (one multimem.st when the staging areas are symmetric, P plain stores otherwise). -------------------
+  const size_t sb_per = (nsb + P - 1) / P;
+  const size_t slo = min(nsb, (size_t)me * sb_per), shi = min(nsb, slo + sb_per);
+  const int sub = lane >> 3, l8 = lane & 7;                     // block inside the superblock, 16-byte piece inside the block
+  const bool mcast = s_symmetric != 0;
+  for (size_t sb = slo + c + (size_t)warp * C; sb < shi; sb += C * nwarp) {
+    const size_t b = sb * 4 + sub;
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     for (int p = 0; p < P; ++p) {
       const char* ps = pt.send[p];
-      const unsigned w = __ldcg(reinterpret_cast<const unsigned*>(ps + b * kQuantBlock + lane * 4));
+      const uint4 w = ld16(ps + b * kQuantBlock + l8 * 16);
       const float sc = __ldcg(reinterpret_cast<const float*>(ps + qbytes + b * sizeof(float)));
-      const float4 dq = unpack_e4m3x4(w);
-      acc.x = __fadd_rn(acc.x, __fmul_rn(dq.x, sc)); acc.y = __fadd_rn(acc.y, __fmul_rn(dq.y, sc));
-      acc.z = __fadd_rn(acc.z, __fmul_rn(dq.z, sc)); acc.w = __fadd_rn(acc.w, __fmul_rn(dq.w, sc));
+      const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 dq = unpack_e4m3x4(ww[k]);
+        acc[4 * k] = __fadd_rn(acc[4 * k], __fmul_rn(dq.x, sc));
+        acc[4 * k + 1] = __fadd_rn(acc[4 * k + 1], __fmul_rn(dq.y, sc));
+        acc[4 * k + 2] = __fadd_rn(acc[4 * k + 2], __fmul_rn(dq.z, sc));
+        acc[4 * k + 3] = __fadd_rn(acc[4 * k + 3], __fmul_rn(dq.w, sc));
+      }
     }
-    unsigned packed;
-    const float sc2 = quant_warp_block(acc, packed);
-    *reinterpret_cast<unsigned*>(mystage + qbytes + sbytes + b * kQuantBlock + lane * 4) = packed;
-    if (lane == 0) *reinterpret_cast<float*>(mystage + 2 * qbytes + sbytes + b * sizeof(float)) = sc2;
+    // block amax over the 8 lanes that share the block (same arithmetic as quant_warp_block / quant_block())
+    float amax = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) amax = fmaxf(amax, fabsf(acc[k]));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    float sc2 = 0.f;
+    if (amax > 0.f && isfinite(amax)) {
+      sc2 = __fdiv_rn(amax, 448.0f);
+      const float inv = __fdiv_rn(448.0f, amax);
+      q.x = pack_e4m3x4(__fmul_rn(acc[0], inv), __fmul_rn(acc[1], inv), __fmul_rn(acc[2], inv), __fmul_rn(acc[3], inv));
+      q.y = pack_e4m3x4(__fmul_rn(acc[4], inv), __fmul_rn(acc[5], inv), __fmul_rn(acc[6], inv), __fmul_rn(acc[7], inv));
+      q.z = pack_e4m3x4(__fmul_rn(acc[8], inv), __fmul_rn(acc[9], inv), __fmul_rn(acc[10], inv), __fmul_rn(acc[11], inv));
+      q.w = pack_e4m3x4(__fmul_rn(acc[12], inv), __fmul_rn(acc[13], inv), __fmul_rn(acc[14], inv), __fmul_rn(acc[15], inv));
+    }
+    // the four block scales of the superblock travel as one 16-byte store from lane 0
+    uint4 s4;
+    s4.x = __float_as_uint(__shfl_sync(0xffffffffu, sc2, 0));
+    s4.y = __float_as_uint(__shfl_sync(0xffffffffu, sc2, 8));
+    s4.z = __float_as_uint(__shfl_sync(0xffffffffu, sc2, 16));
+    s4.w = __float_as_uint(__shfl_sync(0xffffffffu, sc2, 24));
+    const size_t qo = q2_off + b * kQuantBlock + l8 * 16, so = s2_off + sb * 16;
+    if (mcast) {
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dc.mc + stage_off + qo), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+      if (lane == 0)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dc.mc + stage_off + so), "r"(s4.x), "r"(s4.y), "r"(s4.z), "r"(s4.w) : "memory");
+    } else {
+      for (int k = 0; k < P; ++k) {
+        int p = me + k;
+        if (p >= P) p -= P;
+        st16(pt.send[p] + qo, q);
+        if (lane == 0) st16(pt.send[p] + so, s4);
+      }
+    }
   }
   comm_sync(dc, pt, t, 2, true);
 
-  // ---- phase 3: gather every slice's reduced blocks from their owners, dequantise * out_scale -> y -------------
-  for (size_t b = c + (size_t)warp * C; b < nblk; b += C * nwarp) {
-    const int owner = (int)min((size_t)(P - 1), b / blk_per);
-    const char* ps = pt.send[owner];
-    const unsigned w = __ldcg(reinterpret_cast<const unsigned*>(ps + qbytes + sbytes + b * kQuantBlock + lane * 4));
-    const float sc = __ldcg(reinterpret_cast<const float*>(ps + 2 * qbytes + sbytes + b * sizeof(float)));
-    const float4 dq = unpack_e4m3x4(w);
-    float4 o;
-    o.x = __fmul_rn(__fmul_rn(dq.x, sc), out_scale); o.y = __fmul_rn(__fmul_rn(dq.y, sc), out_scale);
-    o.z = __fmul_rn(__fmul_rn(dq.z, sc), out_scale); o.w = __fmul_rn(__fmul_rn(dq.w, sc), out_scale);
-    const size_t e0 = b * kQuantBlock + (size_t)lane * 4;
-    if (e0 + 3 < count) {
-      *reinterpret_cast<float4*>(y + e0) = o;
-    } else {
-      if (e0 < count) y[e0] = o.x;
-      if (e0 + 1 < count) y[e0 + 1] = o.y;
-      if (e0 + 2 < count) y[e0 + 2] = o.z;
+  // ---- phase 3: every slice's reduced blocks now sit in MY gather area: dequantise * out_scale -> y (local only).
+  //      No closing handshake: after sync 2 nobody reads remote memory any more, and a peer can only write my gather area
+  //      again in the NEXT launch's phase 2, which waits for my next sync 1 - i.e. for the end of this phase. ------------
+  for (size_t sb = c + (size_t)warp * C; sb < nsb; sb += C * nwarp) {
+    const size_t b = sb * 4 + sub;
+    const uint4 w = *reinterpret_cast<const uint4*>(mystage + q2_off + b * kQuantBlock + l8 * 16);
+    const float sc = *reinterpret_cast<const float*>(mystage + s2_off + b * sizeof(float));
+    const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+    const size_t e0 = b * kQuantBlock + (size_t)l8 * 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 dq = unpack_e4m3x4(ww[k]);
+      float4 o;
+      o.x = __fmul_rn(__fmul_rn(dq.x, sc), out_scale); o.y = __fmul_rn(__fmul_rn(dq.y, sc), out_scale);
+      o.z = __fmul_rn(__fmul_rn(dq.z, sc), out_scale); o.w = __fmul_rn(__fmul_rn(dq.w, sc), out_scale);
+      const size_t e = e0 + 4 * k;
+      if (e + 3 < count) {
+        *reinterpret_cast<float4*>(y + e) = o;
+      } else {
+        if (e < count) y[e] = o.x;
+        if (e + 1 < count) y[e + 1] = o.y;
+        if (e + 2 < count) y[e + 2] = o.z;
+      }
     }
   }
-  comm_sync(dc, pt, t, 3, false);
 }
 
 cudaError_t launch_allreduce_quant(const DevComm& dc, unsigned long long send_off, unsigned long long recv_off,

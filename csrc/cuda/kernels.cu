@@ -170,9 +170,41 @@ struct ArPass {
   }
 };
 
+// the pass loop over vectors [v0, v1) of the message, run by a sub-grid of `gsz` threads (this thread: `gtid`)
+template <typename T, typename Op, int U, bool kNvls>
+__device__ __forceinline__ void ar_run_passes(const DevComm& dc, const PeerTable& pt, const char* msrc, char* mdst, size_t v0, size_t v1,
+                                              size_t gtid, size_t gsz, float scale) {
+  using AP = ArPass<T, Op, U, kNvls>;
+  const int P = dc.nranks, me = dc.me;
+  const size_t nvec = v1 - v0;
+  const size_t pass_vecs = (size_t)P * gsz * U;
+  const size_t npass = (nvec + pass_vecs - 1) / pass_vecs;
+  typename AP::Regs ra, rb;
+  size_t lo_a = 0, hi_a = 0, lo_b = 0, hi_b = 0;
+  if (npass) {
+    AP::range(nvec, pass_vecs, 0, P, me, lo_a, hi_a);
+    AP::load(ra, dc, pt, msrc, v0 + lo_a, v0 + hi_a, gtid, gsz);
+  }
+  for (size_t p = 0; p < npass; p += 2) {
+    if (p + 1 < npass) {
+      AP::range(nvec, pass_vecs, p + 1, P, me, lo_b, hi_b);
+      AP::load(rb, dc, pt, msrc, v0 + lo_b, v0 + hi_b, gtid, gsz);
+    }
+    AP::store(ra, dc, pt, mdst, v0 + lo_a, gtid, gsz, scale);
+    if (p + 1 < npass) {
+      if (p + 2 < npass) {
+        AP::range(nvec, pass_vecs, p + 2, P, me, lo_a, hi_a);
+        AP::load(ra, dc, pt, msrc, v0 + lo_a, v0 + hi_a, gtid, gsz);
+      }
+      AP::store(rb, dc, pt, mdst, v0 + lo_b, gtid, gsz, scale);
+    }
+  }
+}
+
 template <typename T, typename Op, int U, bool kNvls>
 __global__ void __launch_bounds__(kCommThreads) k_allreduce(DevComm dc, unsigned long long send_off,
-                                                            unsigned long long recv_off, size_t count, float scale) {
+                                                            unsigned long long recv_off, size_t count, float scale,
+                                                            int p2p_cta, float p2p_frac) {
   using VT = VecTraits<T>;
   using Acc = typename VT::Acc;
   constexpr int N = VT::N;
@@ -196,60 +228,27 @@ __global__ void __launch_bounds__(kCommThreads) k_allreduce(DevComm dc, unsigned
   const bool do_scale = scale != 1.0f;
   if (s_aligned) {
     const size_t nvec = count / N;
-    const size_t pass_vecs = (size_t)P * gsz * U;
-    const size_t npass = (nvec + pass_vecs - 1) / pass_vecs;
     bool done = false;
     if constexpr (kNvls && HasMultimem<T>::value) {
       if (s_symmetric) {
-        using AP = ArPass<T, Op, U, true>;
-        const char* msrc = dc.mc + send_off;
-        char* mdst = dc.mc + recv_off;
-        typename AP::Regs ra, rb;
-        size_t lo_a = 0, hi_a = 0, lo_b = 0, hi_b = 0;
-        if (npass) {
-          AP::range(nvec, pass_vecs, 0, P, me, lo_a, hi_a);
-          AP::load(ra, dc, pt, msrc, lo_a, hi_a, gtid, gsz);
-        }
-        for (size_t p = 0; p < npass; p += 2) {
-          if (p + 1 < npass) {
-            AP::range(nvec, pass_vecs, p + 1, P, me, lo_b, hi_b);
-            AP::load(rb, dc, pt, msrc, lo_b, hi_b, gtid, gsz);
-          }
-          AP::store(ra, dc, pt, mdst, lo_a, gtid, gsz, scale);
-          if (p + 1 < npass) {
-            if (p + 2 < npass) {
-              AP::range(nvec, pass_vecs, p + 2, P, me, lo_a, hi_a);
-              AP::load(ra, dc, pt, msrc, lo_a, hi_a, gtid, gsz);
-            }
-            AP::store(rb, dc, pt, mdst, lo_b, gtid, gsz, scale);
-          }
+        // Hybrid: the multicast path of an 8-GPU NVSwitch domain levels off at ~540 GB/s of link traffic per GPU and
+        // direction whatever the grid (measured: 48..148 CTAs, 1..4 vectors per thread all land on 478 GB/s algorithm
+        // bandwidth) - below what the links carry for plain peer traffic (770 GB/s).  So the last `p2p_cta` CTAs move the
+        // tail `p2p_vecs` vectors of the message with the peer-to-peer two-shot code at the same time.
+        const size_t p2p_vecs = p2p_cta > 0 && (unsigned)p2p_cta < gridDim.x ? min(nvec, (size_t)((double)nvec * p2p_frac)) : 0;
+        const size_t mc_vecs = nvec - p2p_vecs;
+        const unsigned mc_cta = gridDim.x - (p2p_vecs ? p2p_cta : 0);
+        if (blockIdx.x < mc_cta) {
+          ar_run_passes<T, Op, U, true>(dc, pt, dc.mc + send_off, dc.mc + recv_off, 0, mc_vecs,
+                                        (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)mc_cta * blockDim.x, scale);
+        } else {
+          ar_run_passes<T, Op, U, false>(dc, pt, nullptr, nullptr, mc_vecs, nvec,
+                                         (size_t)(blockIdx.x - mc_cta) * blockDim.x + threadIdx.x, (size_t)p2p_cta * blockDim.x, scale);
         }
         done = true;
       }
     }
-    if (!done) {
-      using AP = ArPass<T, Op, U, false>;
-      typename AP::Regs ra, rb;
-      size_t lo_a = 0, hi_a = 0, lo_b = 0, hi_b = 0;
-      if (npass) {
-        AP::range(nvec, pass_vecs, 0, P, me, lo_a, hi_a);
-        AP::load(ra, dc, pt, nullptr, lo_a, hi_a, gtid, gsz);
-      }
-      for (size_t p = 0; p < npass; p += 2) {
-        if (p + 1 < npass) {
-          AP::range(nvec, pass_vecs, p + 1, P, me, lo_b, hi_b);
-          AP::load(rb, dc, pt, nullptr, lo_b, hi_b, gtid, gsz);
-        }
-        AP::store(ra, dc, pt, nullptr, lo_a, gtid, gsz, scale);
-        if (p + 1 < npass) {
-          if (p + 2 < npass) {
-            AP::range(nvec, pass_vecs, p + 2, P, me, lo_a, hi_a);
-            AP::load(ra, dc, pt, nullptr, lo_a, hi_a, gtid, gsz);
-          }
-          AP::store(rb, dc, pt, nullptr, lo_b, gtid, gsz, scale);
-        }
-      }
-    }
+    if (!done) ar_run_passes<T, Op, U, false>(dc, pt, nullptr, nullptr, 0, nvec, gtid, gsz, scale);
     // tail elements (less than one vector): the last rank's first threads, plain peer accesses
     if (me == P - 1) {
       for (size_t i = nvec * N + gtid; i < count; i += gsz) {
@@ -931,20 +930,20 @@ cudaError_t launch_pull_copy(const DevComm& dc, const CopyPlan& plan, unsigned l
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, typename Op>
 static cudaError_t launch_ar_t(const DevComm& dc, unsigned long long so, unsigned long long ro, size_t count,
-                               float scale, int channels, int unroll, cudaStream_t s) {
+                               float scale, int channels, int unroll, int p2p_cta, float p2p_frac, cudaStream_t s) {
   // vectors each thread moves per pass: all in flight at once (U), two register sets (software pipeline) -> U <= 4
   const size_t per_thread = (count * sizeof(T) / (size_t)dc.nranks) / ((size_t)channels * kCommThreads * 16);
   constexpr bool kCanNvls = HasMultimem<T>::value && std::is_same<Op, OpSum>::value;
   int U = unroll > 0 ? unroll : (per_thread <= 1 ? 1 : (per_thread <= 3 ? 2 : 4));
   if (kCanNvls && dc.mc != nullptr) {
-    if (U >= 4) k_allreduce<T, Op, 4, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
-    else if (U >= 2) k_allreduce<T, Op, 2, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
-    else k_allreduce<T, Op, 1, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+    if (U >= 4) k_allreduce<T, Op, 4, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale, p2p_cta, p2p_frac);
+    else if (U >= 2) k_allreduce<T, Op, 2, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale, p2p_cta, p2p_frac);
+    else k_allreduce<T, Op, 1, kCanNvls><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale, p2p_cta, p2p_frac);
     return cudaGetLastError();
   }
-  if (U >= 4) k_allreduce<T, Op, 4, false><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
-  else if (U >= 2) k_allreduce<T, Op, 2, false><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
-  else k_allreduce<T, Op, 1, false><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale);
+  if (U >= 4) k_allreduce<T, Op, 4, false><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale, 0, 0.f);
+  else if (U >= 2) k_allreduce<T, Op, 2, false><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale, 0, 0.f);
+  else k_allreduce<T, Op, 1, false><<<channels, kCommThreads, 0, s>>>(dc, so, ro, count, scale, 0, 0.f);
   return cudaGetLastError();
 }
 template <typename T, typename Op>
@@ -984,8 +983,9 @@ static cudaError_t launch_rp_t(const DevComm& dc, unsigned long long so, unsigne
   }
 
 cudaError_t launch_allreduce(const DevComm& dc, DType dt, RedOp op, unsigned long long send_off,
-                             unsigned long long recv_off, size_t count, float scale, int channels, int unroll, cudaStream_t s) {
-  MLSLB_DISPATCH_T_OP(dt, op, (launch_ar_t<TT, OO>(dc, send_off, recv_off, count, scale, channels, unroll, s)))
+                             unsigned long long recv_off, size_t count, float scale, int channels, int unroll, int p2p_cta,
+                             float p2p_frac, cudaStream_t s) {
+  MLSLB_DISPATCH_T_OP(dt, op, (launch_ar_t<TT, OO>(dc, send_off, recv_off, count, scale, channels, unroll, p2p_cta, p2p_frac, s)))
   return cudaErrorInvalidValue;
 }
 

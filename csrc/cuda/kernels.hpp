@@ -31,8 +31,11 @@ struct CopyPlan {
 // K8 barrier
 cudaError_t launch_barrier(const DevComm& dc, cudaStream_t s);
 // K1 all-reduce: fused reduce-scatter + all-gather over peer memory, scale epilogue
+// p2p_cta / p2p_frac: hybrid for multicast groups - the last p2p_cta CTAs move the tail p2p_frac of the message with the
+// peer-to-peer code while the others use multimem (0 = multicast only)
 cudaError_t launch_allreduce(const DevComm& dc, DType dt, RedOp op, unsigned long long send_off,
-                             unsigned long long recv_off, size_t count, float scale, int channels, int unroll, cudaStream_t s);
+                             unsigned long long recv_off, size_t count, float scale, int channels, int unroll, int p2p_cta,
+                             float p2p_frac, cudaStream_t s);
 // K1, latency path: messages <= kLLMaxBytes travel as (data, flag) pairs pushed straight into every peer's arena -
 // one NVLink one-way trip, no handshake, no fence (csrc/cuda/kernels.cu: k_allreduce_ll)
 constexpr size_t kLLMaxBytes = 8192;                                   // payload per rank
