@@ -28,6 +28,7 @@ struct BootSlot {
 };
 
 constexpr size_t kGroupSlotBytes = 64;
+constexpr size_t kOrderLogDepth = 256;
 struct GroupSlot {
   std::atomic<uint64_t> seq[2];
   char data[2][kGroupSlotBytes];
@@ -47,6 +48,12 @@ struct alignas(64) BootCtl {
   // collectives launched so far per (signal row, lane) and rank: loop-back ranks (several ranks on one GPU) use it to
   // launch a collective's kernels together instead of letting the first one spin on the device (cuda_backend.cu)
   alignas(64) std::atomic<uint64_t> launch_seq[kMaxGroupRows * 2][kMaxHostRanks];
+  // Launch-order log of a (signal row, lane): with message prioritisation on, the group's first member decides in which
+  // order queued collectives go out (newest big gradient first) and publishes the decision here; the other members
+  // replay it, so every rank launches the row's collectives in the same order (runtime.cpp: ProgressEngine).
+  alignas(64) std::atomic<uint64_t> order_head[kMaxGroupRows * 2];
+  alignas(64) std::atomic<uint64_t> order_pos[kMaxGroupRows * 2][kMaxHostRanks];
+  alignas(64) std::atomic<uint64_t> order_log[kMaxGroupRows * 2][kOrderLogDepth];
 };
 
 struct InprocWorld;   // shared state of an in-process world

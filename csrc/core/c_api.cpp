@@ -313,6 +313,7 @@ int mlsl_environment_get_quantization_params(mlsl_environment e, mlsl_quant_para
 int mlsl_environment_set_stream(mlsl_environment e, void* s) { C_GUARD(H<Environment>(e)->SetStream(s)) }
 int mlsl_environment_get_stream(mlsl_environment e, void** s) { C_GUARD(*need(s) = H<Environment>(e)->GetStream()) }
 int mlsl_environment_set_wait_mode(mlsl_environment e, const char* m) { C_GUARD(H<Environment>(e)->SetWaitMode(m)) }
+int mlsl_environment_get_launch_order(mlsl_environment e, long long* uids, size_t cap, size_t* n) { C_GUARD(*need(n) = H<Environment>(e)->GetLaunchOrder(uids, cap)) }
 int mlsl_environment_set_tuning(mlsl_environment e, const char* k, long long v) { C_GUARD(H<Environment>(e)->SetTuning(k, (long)v)) }
 int mlsl_environment_get_tuning(mlsl_environment e, const char* k, long long* v) { C_GUARD(*need(v) = H<Environment>(e)->GetTuning(k)) }
 int mlsl_environment_get_backend_name(mlsl_environment e, const char** n) { C_GUARD(*need(n) = H<Environment>(e)->GetBackendName()) }

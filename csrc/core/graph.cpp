@@ -1093,6 +1093,12 @@ void Environment::SetWaitMode(const char* mode) {
   MLSLB_ASSERT(mode && (!strcmp(mode, "host") || !strcmp(mode, "stream")), "wait mode must be 'host' or 'stream'");
   live(this)->backend->set_wait_mode(!strcmp(mode, "stream"));
 }
+size_t Environment::GetLaunchOrder(long long* uids, size_t capacity) {
+  std::vector<int64_t> v = live(this)->progress->recent_launches();
+  const size_t n = std::min(capacity, v.size());
+  for (size_t i = 0; i < n; ++i) uids[i] = v[v.size() - n + i];
+  return n;
+}
 void Environment::SetTuning(const char* key, long value) {
   MLSLB_ASSERT(key && tune_set(live(this)->env.tune, key, value), "unknown tuning key '%s'", key ? key : "(null)");
 }

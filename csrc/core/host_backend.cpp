@@ -246,6 +246,7 @@ class HostBackend final : public Backend {
     r.state.store(CommRequest::DONE, std::memory_order_release);
   }
   bool test(CommRequest& r) override { return r.state.load(std::memory_order_acquire) >= CommRequest::DONE; }
+  bool peek_done(CommRequest& r) override { return r.state.load(std::memory_order_acquire) != CommRequest::LAUNCHED; }
   void wait(CommRequest& r) override {
     uint64_t spins = 0, t0 = 0;
     while (r.state.load(std::memory_order_acquire) < CommRequest::DONE) {

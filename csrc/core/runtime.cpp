@@ -131,8 +131,11 @@ void CommRequest::setup() {
   }
   // priority lane: large gradient messages of the earliest operations overtake the rest (the intent of the
   // reference's newest-first Rabenseifner progress, eplib/allreduce_pr.c:76-79: first-layer gradients first).
+  // With progress threads the launch ORDER is prioritised instead (ProgressEngine::choose: newest big gradient first,
+  // the same order on every rank); the static lane is the fallback when collectives are launched by the caller.
   lane = 0;
-  if (ctx->env.msg_priority && desc.comp_type == CommDesc::PARAM_GRAD && msg_bytes_ >= ctx->env.msg_priority_threshold) {
+  const bool dynamic_order = ctx->progress && ctx->progress->servers() > 0;
+  if (!dynamic_order && ctx->env.msg_priority && desc.comp_type == CommDesc::PARAM_GRAD && msg_bytes_ >= ctx->env.msg_priority_threshold) {
     int ops = ctx->session_ops_hint > 0 ? ctx->session_ops_hint : 4;
     int cut = std::max(1, ops / 4);
     if (desc.op_uid >= 0 && (desc.op_uid % (int64_t)std::max(ops, 1)) < cut && ctx->env.msg_priority_mode == 1) lane = 1;
@@ -160,12 +163,8 @@ void CommRequest::start(void* s, void* r) {
     if (recv_bytes_ && r) ctx->check_pointer(r, recv_bytes_, "recv buffer");
   }
   start_ns = now_ns();
-  ProcessGroup* g = desc.group;
-  if (!g || g->size() <= 1 || g->is_self) {
-    group_seq = 0;
-  } else {
-    group_seq = ++g->seq[lane];
-  }
+  group_seq = 0;            // the ticket on the group's row is drawn when the command is LAUNCHED (ProgressEngine): message
+                            // prioritisation may launch in another order than the program started, on every rank alike
   state.store(QUEUED, std::memory_order_release);
   ctx->backend->on_start(*this);
   ctx->progress->submit(this);
@@ -259,6 +258,11 @@ static void pin_thread(const std::string& affinity, int idx) {
   pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
 }
 
+static void draw_ticket(CommRequest* r) {
+  ProcessGroup* g = r->desc.group;
+  r->group_seq = (!g || g->size() <= 1 || g->is_self) ? 0 : ++g->seq[r->lane];
+}
+
 ProgressEngine::ProgressEngine(RankContext* ctx, int num_servers) : ctx_(ctx) {
   for (int i = 0; i < num_servers; ++i) {
     servers_.emplace_back(new Server());
@@ -282,6 +286,7 @@ ProgressEngine::~ProgressEngine() {
 
 void ProgressEngine::submit(CommRequest* r) {
   if (servers_.empty()) {
+    draw_ticket(r);
     ctx_->backend->launch(*r);
     launched_.fetch_add(1, std::memory_order_relaxed);
     return;
@@ -319,47 +324,176 @@ void ProgressEngine::resume() {
   resume_gen_.store(suspend_gen_.load(std::memory_order_acquire), std::memory_order_release);
 }
 
+std::vector<int64_t> ProgressEngine::recent_launches() {
+  std::lock_guard<std::mutex> g(recent_mu_);
+  return recent_;
+}
+
+void ProgressEngine::exec(Server* s, CommRequest* r) {
+  draw_ticket(r);
+  {
+    std::lock_guard<std::mutex> g(recent_mu_);
+    if (recent_.size() >= 256) recent_.erase(recent_.begin());
+    recent_.push_back(r->desc.op_uid);
+  }
+  try {
+    ctx_->backend->launch(*r);
+  } catch (const std::exception& e) {
+    // the error belongs to the caller of Wait / Test: keep it on the request and fail it (a LAUNCHED state would
+    // leave host / net waiters spinning for a completion that never comes)
+    fprintf(stderr, "(r%d) progress thread: %s\n", ctx_->rank, e.what());
+    if (ctx_->boot) ctx_->boot->poison(ctx_->rank);
+    r->error = e.what();
+    r->state.store(CommRequest::FAILED, std::memory_order_release);
+  }
+  launched_.fetch_add(1, std::memory_order_relaxed);
+  s->completed.fetch_add(1, std::memory_order_release);
+}
+
+// Message prioritisation (reference eplib/allreduce_pr.c:76-79 progresses its big all-reduces newest first, so the
+// gradients of the FIRST layers - produced last by the backward pass, needed first by the next forward pass - overtake
+// the bulk; selected at eplib/cqueue.c:1999-2012 by size).  On a GPU the order is fixed once kernels sit in a stream, so
+// the choice is made here, before the launch: big gradient messages are held back while the row already has
+// kPrioWindow of them in flight, and when a slot frees up the NEWEST queued one goes next; everything else (activations,
+// small messages) is launched at once, oldest first.  All members must launch a row's collectives in the same order:
+// the group's first member decides and appends the choice to the row's order log in the shared control block, the
+// others replay the log.  SPMD programs start the same collectives before they wait, so a follower always finds the
+// logged command in its own queue eventually.
+constexpr size_t kPrioWindow = 2;
+
+static uint64_t order_key(const CommRequest* r) {
+  uint64_t k = (uint64_t)(r->desc.op_uid + 1) * 0x9e3779b97f4a7c15ull;
+  k ^= ((uint64_t)r->desc.kind << 56) ^ ((uint64_t)r->desc.comp_type << 48) ^ (uint64_t)r->desc.count;
+  return k | 1ull;   // never 0
+}
+
+bool ProgressEngine::prioritised(const CommRequest* r) const {
+  return ctx_->env.msg_priority && r->desc.comp_type == CommDesc::PARAM_GRAD && r->msg_bytes() >= ctx_->env.msg_priority_threshold &&
+         r->desc.group && r->desc.group->size() > 1 && r->desc.group->row >= 0;
+}
+
+CommRequest* ProgressEngine::choose(Server* s) {
+  if (s->pending.empty()) return nullptr;
+  BootCtl* c = ctx_->boot ? ctx_->boot->ctl() : nullptr;
+  if (!ctx_->env.msg_priority || !c) {          // plain FIFO
+    CommRequest* r = s->pending.front();
+    s->pending.erase(s->pending.begin());
+    return r;
+  }
+  // retire finished prioritised launches from the in-flight windows
+  for (size_t i = 0; i < s->inflight.size();) {
+    if (ctx_->backend->peek_done(*s->inflight[i])) s->inflight.erase(s->inflight.begin() + i);
+    else ++i;
+  }
+  // one ordering domain per (row, lane); walk the domains that have something queued, oldest command first
+  for (size_t qi = 0; qi < s->pending.size(); ++qi) {
+    CommRequest* first = s->pending[qi];
+    ProcessGroup* g = first->desc.group;
+    if (!g || g->size() <= 1 || g->row < 0) {   // local command: no peer has to agree
+      s->pending.erase(s->pending.begin() + qi);
+      return first;
+    }
+    const int dom = g->row * 2 + first->lane;
+    bool seen = false;
+    for (size_t k = 0; k < qi; ++k) seen |= s->pending[k]->desc.group == g && s->pending[k]->lane == first->lane;
+    if (seen) continue;                          // this domain was already looked at through an older command
+    auto in_domain = [&](CommRequest* r) { return r->desc.group == g && r->lane == first->lane; };
+    size_t pick = SIZE_MAX;
+    if (g->idx == 0) {
+      // leader: the oldest normal command if there is one, else the newest prioritised one when the window has room
+      for (size_t k = qi; k < s->pending.size() && pick == SIZE_MAX; ++k)
+        if (in_domain(s->pending[k]) && !prioritised(s->pending[k])) pick = k;
+      if (pick == SIZE_MAX) {
+        size_t fl = 0;
+        for (CommRequest* r : s->inflight) fl += in_domain(r);
+        if (fl < kPrioWindow) {
+          for (size_t k = s->pending.size(); k-- > qi;)
+            if (in_domain(s->pending[k])) {
+              pick = ctx_->env.msg_priority_mode == 1 ? k : SIZE_MAX;
+              if (pick != SIZE_MAX) break;
+            }
+          if (pick == SIZE_MAX) pick = qi;       // mode 0: oldest first
+        }
+      }
+      if (pick == SIZE_MAX) continue;
+      const uint64_t n = c->order_head[dom].load(std::memory_order_relaxed);
+      // never lap a follower that still has to read the entry this one would overwrite
+      uint64_t slowest = n;
+      for (int m : g->members)
+        if (m != ctx_->rank) slowest = std::min(slowest, c->order_pos[dom][m].load(std::memory_order_acquire));
+      if (n - slowest >= kOrderLogDepth) continue;
+      c->order_log[dom][n % kOrderLogDepth].store(order_key(s->pending[pick]), std::memory_order_relaxed);
+      c->order_head[dom].store(n + 1, std::memory_order_release);
+    } else {
+      const uint64_t pos = c->order_pos[dom][ctx_->rank].load(std::memory_order_relaxed);
+      if (c->order_head[dom].load(std::memory_order_acquire) <= pos) continue;      // the leader has not decided yet
+      const uint64_t key = c->order_log[dom][pos % kOrderLogDepth].load(std::memory_order_relaxed);
+      for (size_t k = qi; k < s->pending.size() && pick == SIZE_MAX; ++k)
+        if (in_domain(s->pending[k]) && order_key(s->pending[k]) == key) pick = k;
+      if (pick == SIZE_MAX) continue;            // not started by this rank's program yet
+      c->order_pos[dom][ctx_->rank].store(pos + 1, std::memory_order_release);
+    }
+    CommRequest* r = s->pending[pick];
+    s->pending.erase(s->pending.begin() + pick);
+    if (prioritised(r)) s->inflight.push_back(r);
+    return r;
+  }
+  return nullptr;
+}
+
 void ProgressEngine::run(Server* s, int idx) {
   pin_thread(ctx_->env.server_affinity, idx);
   set_log_rank(ctx_->rank);
   uint64_t idle = 0;
   for (;;) {
     Command c;
-    if (!s->ring.pop(c)) {
-      if (++idle < 2000) {
+    bool got = false;
+    while (s->ring.pop(c)) {
+      got = true;
+      if (c.kind == Command::STOP) {
+        for (CommRequest* r : s->pending) exec(s, r);   // nothing may stay queued behind a shutdown
+        s->pending.clear();
+        return;
+      }
+      if (c.kind == Command::SUSPEND) {
+        s->parked.store(true, std::memory_order_release);
+        while (resume_gen_.load(std::memory_order_acquire) < c.arg) usleep(100);
+        s->parked.store(false, std::memory_order_release);
+        continue;
+      }
+      if (c.kind == Command::EXEC) s->pending.push_back(c.req);
+    }
+    bool launched = false;
+    while (CommRequest* r = choose(s)) {
+      exec(s, r);
+      launched = true;
+    }
+    if (got || launched) {
+      idle = 0;
+      continue;
+    }
+    // commands held back by the ordering rules keep the thread polling; an empty queue lets it back off
+    if (++idle < 20000 || !s->pending.empty()) {
 #if defined(__x86_64__)
-        __builtin_ia32_pause();
+      __builtin_ia32_pause();
 #endif
-      } else if (idle < 20000) {
+      if (!s->pending.empty() && (idle & 0xfff) == 0) {
         sched_yield();
-      } else {
-        usleep(50);
+        if (ctx_->boot && ctx_->boot->poisoned()) {      // a dead peer can never log / start the command: fail what waits
+          for (CommRequest* r : s->pending) {
+            r->error = "job poisoned while the command waited for its turn";
+            r->state.store(CommRequest::FAILED, std::memory_order_release);
+            s->completed.fetch_add(1, std::memory_order_release);
+          }
+          s->pending.clear();
+        }
       }
-      if (ctx_->boot && (idle & 0x3ff) == 0) ctx_->boot->heartbeat();
-      continue;
+    } else if (idle < 200000) {
+      sched_yield();
+    } else {
+      usleep(50);
     }
-    idle = 0;
-    if (c.kind == Command::STOP) return;
-    if (c.kind == Command::SUSPEND) {
-      s->parked.store(true, std::memory_order_release);
-      while (resume_gen_.load(std::memory_order_acquire) < c.arg) usleep(100);
-      s->parked.store(false, std::memory_order_release);
-      continue;
-    }
-    if (c.kind == Command::EXEC) {
-      try {
-        ctx_->backend->launch(*c.req);
-      } catch (const std::exception& e) {
-        // the error belongs to the caller of Wait / Test: keep it on the request and fail it (a LAUNCHED state would
-        // leave host / net waiters spinning for a completion that never comes)
-        fprintf(stderr, "(r%d) progress thread: %s\n", ctx_->rank, e.what());
-        if (ctx_->boot) ctx_->boot->poison(ctx_->rank);
-        c.req->error = e.what();
-        c.req->state.store(CommRequest::FAILED, std::memory_order_release);
-      }
-      launched_.fetch_add(1, std::memory_order_relaxed);
-      s->completed.fetch_add(1, std::memory_order_release);
-    }
+    if (ctx_->boot && (idle & 0x3ff) == 0) ctx_->boot->heartbeat();
   }
 }
 
@@ -477,6 +611,10 @@ ProcessGroup* RankContext::create_group_from_members(const std::vector<int>& mem
     g->seq[0] = g->seq[1] = g->ctl_seq = base;
     seq_hwm = std::max(seq_hwm, base);
   }
+  if (boot && boot->ctl() && g->row >= 0)          // the row's launch-order log continues where the previous group on it stopped
+    for (int l = 0; l < 2; ++l)
+      boot->ctl()->order_pos[g->row * 2 + l][rank].store(boot->ctl()->order_head[g->row * 2 + l].load(std::memory_order_acquire),
+                                                         std::memory_order_release);
   if (backend) backend->group_created(*g);
   return g;
 }
@@ -687,8 +825,13 @@ void context_init(RankContext* ctx) {
   // MLSL_CHECK_SINGLE_NODE=0 switches that rule off: the reference's default of 4 servers applies (host path).
   int ns = ctx->env.num_servers;
   if (ns < 0) {
-    if (ctx->backend->is_device() || ctx->world <= 1) {
+    if (ctx->world <= 1) {
       ns = 0;
+    } else if (ctx->backend->is_device()) {
+      // one process per GPU: ONE progress thread per rank launches the collectives on the communication streams - the
+      // API thread only records an event and pushes a ring entry (the reference's endpoint server, as a thread).  Ranks
+      // that share a GPU (loop-back tests) and inline-stream mode launch from the caller.
+      ns = ctx->backend->default_servers();
     } else if (!ctx->env.check_single_node) {
       ns = 4;
     } else {

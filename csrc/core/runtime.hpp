@@ -139,6 +139,8 @@ class Backend {
  public:
   virtual ~Backend() {}
   virtual const char* name() const = 0;
+  virtual bool peek_done(CommRequest&) { return true; }         // launched collective finished? (never consumes it)
+  virtual int default_servers() const { return 0; }              // progress threads when MLSL_NUM_SERVERS is unset
   virtual bool stream_ordered_wait() const { return false; }   // Wait only orders a stream (the host never blocks)
   virtual void harvest_device_time(CommRequest&) {}             // fold finished device timings into the request
   virtual bool is_device() const { return false; }
@@ -229,6 +231,8 @@ class ProgressEngine {
   void suspend();                     // park the servers (reference EPLIB_suspend/EPLIB_execute)
   void resume();
   uint64_t launched() const { return launched_.load(); }
+  // op uids of the most recently launched collectives (oldest first, at most 256): what order did the engine choose?
+  std::vector<int64_t> recent_launches();
 
  private:
   struct Server {
@@ -237,11 +241,19 @@ class ProgressEngine {
     std::atomic<uint64_t> submitted{0}, completed{0};
     std::atomic<bool> parked{false};
     std::mutex mu;                    // producers are API threads: serialise pushes (SPSC per ring)
+    // message prioritisation: commands taken off the ring but not launched yet, and what is in flight per (row, lane)
+    std::vector<CommRequest*> pending;
+    std::vector<CommRequest*> inflight;
   };
   void run(Server* s, int idx);
+  void exec(Server* s, CommRequest* r);
+  bool prioritised(const CommRequest* r) const;
+  CommRequest* choose(Server* s);     // next pending command to launch under the ordering rules (nullptr: none yet)
   RankContext* ctx_;
   std::vector<std::unique_ptr<Server>> servers_;
   std::atomic<uint64_t> launched_{0};
+  std::mutex recent_mu_;
+  std::vector<int64_t> recent_;
   std::atomic<uint64_t> suspend_gen_{0}, resume_gen_{0};   // a server stays parked while resume_gen_ < its SUSPEND's generation
 };
 

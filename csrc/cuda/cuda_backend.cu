@@ -186,6 +186,18 @@ class CudaBackend final : public Backend {
     if (auto* st = (CudaReqState*)r.backend_state) harvest(r, st, false);
   }
   bool stream_ordered_wait() const override { return stream_wait_; }
+  bool peek_done(CommRequest& r) override {
+    auto* st = (CudaReqState*)r.backend_state;
+    if (!st || !st->recorded) return true;
+    set_device();
+    cudaError_t e = cudaEventQuery(st->done);
+    if (e == cudaErrorNotReady) {
+      cudaGetLastError();
+      return false;
+    }
+    return true;
+  }
+  int default_servers() const override { return (inproc_ || inline_stream_ || ranks_per_device_ > 1) ? 0 : 1; }
   void ensure_events(CudaReqState* st) {
     if (st->done) return;
     st->ready = take_event();

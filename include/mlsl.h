@@ -226,6 +226,7 @@ const char* mlsl_last_error(void);                       /* message of the last 
 int mlsl_environment_set_stream(mlsl_environment env, void* cuda_stream);
 int mlsl_environment_get_stream(mlsl_environment env, void** cuda_stream);
 int mlsl_environment_set_wait_mode(mlsl_environment env, const char* mode);
+int mlsl_environment_get_launch_order(mlsl_environment env, long long* uids, size_t capacity, size_t* count);   /* [ext] */
 int mlsl_environment_set_tuning(mlsl_environment env, const char* key, long long value);      /* [ext] */
 int mlsl_environment_get_tuning(mlsl_environment env, const char* key, long long* value);     /* [ext] */
 int mlsl_environment_get_backend_name(mlsl_environment env, const char** name);

@@ -328,6 +328,9 @@ class Environment {
   void SetWaitMode(const char* mode);   // "host" | "stream"
   // [ext] device-path tuning knobs by name ("ar_channels", "mid_max_kb", ... or their MLSL_* environment names; the
   // list is printed at MLSL_LOG_LEVEL=1).  Every rank must apply the same change at the same point of the program.
+  // [ext] operation uids of the collectives the progress threads launched most recently, oldest first (what order did
+  // message prioritisation choose?).  Returns the number written (<= capacity).
+  size_t GetLaunchOrder(long long* uids, size_t capacity);
   void SetTuning(const char* key, long value);
   long GetTuning(const char* key);
   const char* GetBackendName();         // "host" | "cuda"

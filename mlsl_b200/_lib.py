@@ -110,6 +110,7 @@ def _declare(l):
         "mlsl_environment_get_stream": [H, P(c_void_p)],
         "mlsl_environment_set_wait_mode": [H, c_char_p],
         "mlsl_environment_set_tuning": [H, c_char_p, ctypes.c_longlong],
+        "mlsl_environment_get_launch_order": [H, ctypes.POINTER(ctypes.c_longlong), c_size_t, P(c_size_t)],
         "mlsl_environment_get_tuning": [H, c_char_p, ctypes.POINTER(ctypes.c_longlong)],
         "mlsl_environment_get_backend_name": [H, P(c_char_p)],
         "mlsl_environment_is_device_backend": [H, P(c_int)],

@@ -554,6 +554,13 @@ class MLSL(_Handle):
     def set_wait_mode(self, mode):
         self._call("mlsl_environment_set_wait_mode", mode.encode())
 
+    def get_launch_order(self, capacity=256):
+        """Operation uids of the most recently launched collectives, oldest first (progress threads only)."""
+        buf = (ctypes.c_longlong * capacity)()
+        n = c_size_t()
+        check(_lib.lib().mlsl_environment_get_launch_order(self.handle, buf, capacity, ctypes.byref(n)))
+        return [int(buf[i]) for i in range(n.value)]
+
     def set_tuning(self, key, value):
         """Device-path tuning knob by name (see MLSL_LOG_LEVEL=1 for the list); same change on every rank."""
         self._call("mlsl_environment_set_tuning", key.encode(), int(value))

@@ -226,6 +226,61 @@ def test_servers_priority_lane_and_suspend_resume(servers):
     assert run_ranks(2, body, env=env) == [True, True]
 
 
+def test_message_priority_newest_first_same_order_on_every_rank():
+    """MLSL_MSG_PRIORITY=1 with a progress thread: big gradient all-reduces that queue up go out newest first (the first
+    layers' gradients, produced last, overtake the bulk - reference eplib/allreduce_pr.c:76-79), small messages go at
+    once, and every rank launches the row's collectives in the SAME order (the leader's order log)."""
+    world, layers = 4, 6
+
+    def body(r, mlsl):
+        from mlsl_b200.api import DataType, OperationType
+        e = mlsl.env()
+        sess = e.create_session()
+        sess.set_global_minibatch_size(world)
+        dist = e.create_distribution(world, 1)
+        ops = []
+        for l in range(layers):
+            ri = sess.create_operation_reg_info(OperationType.CC)
+            ri.add_input(8, 1, DataType.FLOAT)
+            ri.add_output(8, 1, DataType.FLOAT)
+            ri.add_parameter_set(4096 if l != 2 else 16, 1, DataType.FLOAT, False)      # layer 2: a small message
+            ops.append(sess.get_operation(sess.add_operation(ri, dist)))
+        sess.commit()
+        grads = []
+        for op in ops:
+            ps = op.get_parameter_set(0)
+            g = mlsl.alloc_tensor(ps.get_local_kernel_count() * ps.get_kernel_size(), torch.float32)
+            g.fill_(r + 1.0)
+            grads.append((ps, g))
+        before = len(e.get_launch_order())
+        e.suspend_servers()                       # let the whole backward pass queue up, as a busy device would
+        for ps, g in reversed(grads):             # backward order: last layer first
+            ps.start_gradient_comm(g)
+        e.resume_servers()
+        for ps, g in grads:
+            ps.wait_gradient_comm()
+        order = e.get_launch_order()[before:]
+        ok = all(float(g[0]) == sum(range(1, world + 1)) for _, g in grads)
+        e.delete_session(sess)
+        e.delete_distribution(dist)
+        return ok, order
+
+    env = {"MLSL_NUM_SERVERS": "1", "MLSL_MSG_PRIORITY": "1", "MLSL_MSG_PRIORITY_THRESHOLD": "1000", "MLSL_MSG_PRIORITY_MODE": "1"}
+    outs = run_ranks(world, body, env=env)
+    assert all(ok for ok, _ in outs)
+    orders = [o for _, o in outs]
+    assert all(o == orders[0] for o in orders), orders            # identical on every rank
+    uids = orders[0]
+    assert len(uids) == layers
+    big = [u for u in uids if u != uids[0]] if False else uids
+    # the small message (layer 2, third from the top of the model) went first; among the big ones the newest queued =
+    # the FIRST layer's gradient (started last) leads, the last layer's (started first) trails
+    small_uid = sorted(uids)[2]
+    assert uids[0] == small_uid, uids
+    rest = [u for u in uids if u != small_uid]
+    assert rest[0] == min(rest) and rest[-1] == max(rest), uids
+
+
 def test_test_returns_pointer_again_after_completion():
     def body(r, mlsl):
         sess, dist, ops = _session_two_layers(mlsl, 2, 1, False, mb=4)

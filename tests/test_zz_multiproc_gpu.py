@@ -29,3 +29,19 @@ def test_one_rank_per_gpu(n):
     res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     tail = res.stdout[-6000:]
     assert res.returncode == 0 and "ALL PASSED" in res.stdout and "FAILED" not in res.stdout.replace("0 FAILED", ""), tail
+
+
+def test_message_priority_one_rank_per_gpu():
+    """MLSL_MSG_PRIORITY=1 on real GPUs: the progress threads launch queued gradient all-reduces newest first, in the
+    same order on every rank (tests/mp_priority_check.py)."""
+    n = 2 if _ngpus() < 4 else 4
+    if _ngpus() < n:
+        pytest.skip("needs %d GPUs, %d visible" % (n, _ngpus()))
+    env = dict(os.environ)
+    for k in ("CUDA_MODULE_LOADING", "MLSL_BACKEND", "MLSL_HEAP_SIZE_GB", "MLSL_WATCHDOG_SEC", "MLSL_STREAM_MODE"):
+        env.pop(k, None)
+    env["MLSL_MSG_PRIORITY"] = "1"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29633", os.path.join(ROOT, "tests", "mp_priority_check.py")]
+    res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and "ALL PASSED" in res.stdout, res.stdout[-4000:]
