@@ -29,6 +29,20 @@ struct BootSlot {
 
 constexpr size_t kGroupSlotBytes = 64;
 constexpr size_t kOrderLogDepth = 256;
+constexpr int kMaxGrowChunks = 24;
+
+// Device-heap expansion (reference eplib/memory.c:396-410 registers a further shared-memory region with every server):
+// a rank that outgrows its slab creates another physical chunk, maps it behind the slab in its own reserved address range,
+// and publishes (pid, fd, offset, size) here; a watcher thread of every peer imports the descriptor through
+// /proc/<pid>/fd/<fd>, maps the chunk at the same offset of ITS reservation for that rank and acknowledges.
+struct GrowRec {
+  std::atomic<uint64_t> gen;          // chunks published so far
+  int64_t pid;
+  struct {
+    int64_t fd;
+    uint64_t off, bytes;
+  } chunk[kMaxGrowChunks];
+};
 struct GroupSlot {
   std::atomic<uint64_t> seq[2];
   char data[2][kGroupSlotBytes];
@@ -51,6 +65,8 @@ struct alignas(64) BootCtl {
   // Launch-order log of a (signal row, lane): with message prioritisation on, the group's first member decides in which
   // order queued collectives go out (newest big gradient first) and publishes the decision here; the other members
   // replay it, so every rank launches the row's collectives in the same order (runtime.cpp: ProgressEngine).
+  alignas(64) GrowRec grow[kMaxHostRanks];
+  alignas(64) std::atomic<uint64_t> grow_ack[kMaxHostRanks][kMaxHostRanks];   // [owner][peer]: chunks of `owner` that `peer` has mapped
   alignas(64) std::atomic<uint64_t> order_head[kMaxGroupRows * 2];
   alignas(64) std::atomic<uint64_t> order_pos[kMaxGroupRows * 2][kMaxHostRanks];
   alignas(64) std::atomic<uint64_t> order_log[kMaxGroupRows * 2][kOrderLogDepth];

@@ -348,3 +348,25 @@ int mlsl_set_assert_throws(int on) { C_GUARD(mlslb::set_assert_throws(on != 0)) 
 int mlsl_cuda_available(int* available) { C_GUARD(*need(available) = mlslb::cuda_backend_available() ? 1 : 0) }
 
 }  // extern "C"
+
+// ---- torch.cuda.memory.CUDAPluggableAllocator entry points -------------------------------------------------------------
+// `with mlsl_b200.heap_pool():` routes the torch allocations made inside it (DDP / FSDP buckets, optimizer flats, activations
+// that are exchanged) to the symmetric heap of the calling rank, so collectives on those tensors are zero-copy - the GPU
+// answer to the reference's "stage only what is not in the shared heap" (src/comm_ep.cpp:363-566, EPLIB_memory_is_shmem).
+// The signatures are the ones torch expects: (size, device, stream).  A block freed after Finalize is simply dropped.
+extern "C" void* mlsl_heap_malloc(ssize_t size, int /*device*/, void* /*stream*/) {
+  try {
+    MLSL::Environment& e = MLSL::Environment::GetEnv();
+    if (!e.IsInitialized()) return nullptr;
+    return e.Alloc(size > 0 ? (size_t)size : 1, 512);
+  } catch (const std::exception&) {
+    return nullptr;
+  }
+}
+extern "C" void mlsl_heap_free(void* ptr, ssize_t /*size*/, int /*device*/, void* /*stream*/) {
+  try {
+    MLSL::Environment& e = MLSL::Environment::GetEnv();
+    if (ptr && e.IsInitialized()) e.Free(ptr);
+  } catch (const std::exception&) {
+  }
+}

@@ -92,6 +92,7 @@ EnvConfig parse_env() {
   gets(c.server_affinity, "MLSL_SERVER_AFFINITY", "EPLIB_SERVER_AFFINITY");
   geti(c.num_channels, "MLSL_NUM_CHANNELS");
   if (const char* v = ev("MLSL_HEAP_SIZE_GB", "EPLIB_SHM_SIZE_GB")) c.heap_size_gb = atof(v);
+  if (const char* v = ev("MLSL_HEAP_MAX_GB")) c.heap_max_gb = atof(v);
   getb(c.check_mem_size, "MLSL_CHECK_MEM_SIZE");
   getz(c.max_short_msg, "MLSL_MAX_SHORT_MSG_SIZE");
   getz(c.large_msg_mb, "MLSL_LARGE_MSG_SIZE_MB");
@@ -126,8 +127,8 @@ EnvConfig parse_env() {
 void print_env(const EnvConfig& c) {
   MLSLB_LOG(LOG_INFO, "MLSL_LOG_LEVEL=%d MLSL_STATS=%d MLSL_DUP_GROUP=%d MLSL_AUTO_CONFIG_TYPE=%d", c.log_level,
             (int)c.stats, (int)c.dup_group, c.auto_config);
-  MLSLB_LOG(LOG_INFO, "MLSL_BACKEND=%s MLSL_NUM_SERVERS=%d MLSL_NUM_CHANNELS=%d MLSL_HEAP_SIZE_GB=%.2f",
-            c.backend.c_str(), c.num_servers, c.num_channels, c.heap_size_gb);
+  MLSLB_LOG(LOG_INFO, "MLSL_BACKEND=%s MLSL_NUM_SERVERS=%d MLSL_NUM_CHANNELS=%d MLSL_HEAP_SIZE_GB=%.2f MLSL_HEAP_MAX_GB=%.2f",
+            c.backend.c_str(), c.num_servers, c.num_channels, c.heap_size_gb, c.heap_max_gb);
   MLSLB_LOG(LOG_INFO, "MLSL_MAX_SHORT_MSG_SIZE=%zu MLSL_LARGE_MSG_SIZE_MB=%zu MLSL_LARGE_MSG_CHUNKS=%d",
             c.max_short_msg, c.large_msg_mb, c.large_msg_chunks);
   MLSLB_LOG(LOG_INFO, "MLSL_MSG_PRIORITY=%d MLSL_MSG_PRIORITY_THRESHOLD=%zu MLSL_MSG_PRIORITY_MODE=%d",

@@ -67,12 +67,17 @@ struct EnvConfig {
   std::string server_affinity;   // MLSL_SERVER_AFFINITY: cpu list for progress threads
   int num_channels = 0;          // MLSL_NUM_CHANNELS (0=auto)
   double heap_size_gb = 4.0;     // MLSL_HEAP_SIZE_GB
+  double heap_max_gb = 0.0;      // MLSL_HEAP_MAX_GB: address range reserved per rank for heap growth (0 = 8 x MLSL_HEAP_SIZE_GB,
+                                 // at least 32 GiB); the device heap grows into it chunk by chunk when it runs full
   bool check_mem_size = false;   // MLSL_CHECK_MEM_SIZE
   size_t max_short_msg = 0;      // MLSL_MAX_SHORT_MSG_SIZE (elements): <= this -> single channel
   size_t large_msg_mb = 128;     // MLSL_LARGE_MSG_SIZE_MB
   int large_msg_chunks = 4;      // MLSL_LARGE_MSG_CHUNKS
-  int alltoall_split = 0;        // MLSL_ALLTOALL_SPLIT
-  int alltoallv_split = 0;       // MLSL_ALLTOALLV_SPLIT
+  // MLSL_ALLTOALL_SPLIT / MLSL_ALLTOALLV_SPLIT (reference src/comm_ep.cpp:1192,1270: split every pair message across all
+  // endpoints): >= 1 (and the default, -1) every pair message is spread over ALL channels, one pair after the other;
+  // 0 = the channels are dealt to the pairs, each pair message moves on its own channels, all pairs at once
+  int alltoall_split = -1;
+  int alltoallv_split = -1;
   bool msg_priority = false;     // MLSL_MSG_PRIORITY
   size_t msg_priority_threshold = 10000;  // MLSL_MSG_PRIORITY_THRESHOLD (bytes)
   int msg_priority_mode = 1;     // MLSL_MSG_PRIORITY_MODE (1 = newest first)

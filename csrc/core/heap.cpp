@@ -43,6 +43,22 @@ size_t SlabAllocator::alloc(size_t bytes, size_t align) {
   return start;
 }
 
+void SlabAllocator::extend(size_t bytes) {
+  if (!bytes) return;
+  std::lock_guard<std::mutex> g(mu_);
+  const size_t off = base_ + cap_;
+  cap_ += bytes;
+  // merge with a free block that ends where the new space starts
+  if (!free_.empty()) {
+    auto last = std::prev(free_.end());
+    if (last->first + last->second == off) {
+      last->second += bytes;
+      return;
+    }
+  }
+  free_[off] = bytes;
+}
+
 bool SlabAllocator::free(size_t offset) {
   std::lock_guard<std::mutex> g(mu_);
   auto it = live_.find(offset);

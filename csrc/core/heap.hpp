@@ -18,6 +18,7 @@ class SlabAllocator {
   void reset(size_t base_offset, size_t bytes);
   // returns offset or SIZE_MAX when the slab is exhausted
   size_t alloc(size_t bytes, size_t align);
+  void extend(size_t bytes);           // the slab grew by `bytes` at its end (device heap expansion)
   bool free(size_t offset);            // false if offset is not a live allocation
   size_t size_of(size_t offset) const; // 0 if unknown
   // find the live allocation containing [off, off+len); returns false if none

@@ -10,6 +10,7 @@
 //     stream, Wait() either blocks the host on the completion event or just orders the user's stream after it.
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
+#include <fcntl.h>
 #include <sched.h>
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -19,7 +20,9 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "core/log.hpp"
@@ -86,9 +89,12 @@ class CudaBackend final : public Backend {
       sweep_parked();
       off = heap_.alloc(bytes, std::max<size_t>(align, 256));
     }
+    if (off == SIZE_MAX && grow_heap(bytes + std::max<size_t>(align, 256))) off = heap_.alloc(bytes, std::max<size_t>(align, 256));
     MLSLB_ASSERT(off != SIZE_MAX,
-                 "symmetric device heap exhausted (%zu bytes requested, %zu of %zu in use): raise MLSL_HEAP_SIZE_GB",
-                 bytes, heap_.bytes_in_use(), heap_.capacity());
+                 "symmetric device heap exhausted (%zu bytes requested, %zu of %zu in use%s): raise MLSL_HEAP_SIZE_GB%s",
+                 bytes, heap_.bytes_in_use(), heap_.capacity(),
+                 vmm_.ok ? ", growth failed or the reserved range is full" : "; this slab cannot grow (CUDA IPC / in-process ranks)",
+                 vmm_.ok ? " / MLSL_HEAP_MAX_GB" : "");
     void* p = slab_ + off;
     ctx_->ptrcheck.add(p, bytes);
     return p;
@@ -243,6 +249,78 @@ class CudaBackend final : public Backend {
   }
 
   void launch(CommRequest& r) override;
+  // ---- device-heap expansion (reference eplib/memory.c:396-410, eplib/cqueue.c:1451-1510) ---------------------------------
+  // The slab of a VMM job sits at the start of a much larger reserved address range.  When Alloc runs out of room this rank
+  // backs the next part of ITS range with a new chunk (at least as big as the slab so far: sizes double), publishes the
+  // chunk's descriptor in the shared control block and waits until every peer's watcher thread has mapped it at the same
+  // offset of the range it reserved for this rank - only then can an offset inside the chunk reach a peer's kernel.
+  std::thread grow_watcher_;
+  std::atomic<bool> grow_stop_{false};
+  std::vector<uint64_t> grow_seen_;
+  std::mutex grow_mu_;
+  bool grow_heap(size_t need) {
+    if (!vmm_.ok || !ctx_->boot->ctl()) return false;
+    std::lock_guard<std::mutex> g(grow_mu_);
+    BootCtl* c = ctx_->boot->ctl();
+    GrowRec& rec = c->grow[ctx_->rank];
+    const uint64_t n = rec.gen.load(std::memory_order_relaxed);
+    if (n >= (uint64_t)kMaxGrowChunks) return false;
+    size_t add = std::max(need, vmm_.local_mapped - 0), off = 0, got = 0;
+    add = std::min(add, vmm_.reserved - vmm_.local_mapped);
+    if (add < need) return false;
+    set_device();
+    const int fd = vmm_slab_grow(vmm_, add, &off, &got);
+    if (fd < 0) return false;
+    rec.pid = (int64_t)getpid();
+    rec.chunk[n].fd = fd;             // stays open: the peers read it through /proc/<pid>/fd
+    rec.chunk[n].off = off;
+    rec.chunk[n].bytes = got;
+    rec.gen.store(n + 1, std::memory_order_release);
+    // wait for every peer (their watcher threads run independently of what their API threads are doing)
+    const uint64_t t0 = now_ns();
+    for (int p = 0; p < ctx_->world; ++p) {
+      if (p == ctx_->rank) continue;
+      while (c->grow_ack[ctx_->rank][p].load(std::memory_order_acquire) < n + 1) {
+        usleep(50);
+        if (ctx_->boot->poisoned() || now_ns() - t0 > 30000000000ull) {
+          MLSLB_LOG(LOG_ERROR, "heap growth: rank %d never mapped the new chunk", p);
+          return false;
+        }
+      }
+    }
+    heap_.extend(got);
+    slab_bytes_ = vmm_.local_mapped;
+    MLSLB_LOG(LOG_INFO, "device heap of rank %d grew by %.2f GiB to %.2f GiB", ctx_->rank, got / 1073741824.0, slab_bytes_ / 1073741824.0);
+    return true;
+  }
+  void grow_watch() {
+    BootCtl* c = ctx_->boot->ctl();
+    cudaSetDevice(device_);
+    while (!grow_stop_.load(std::memory_order_acquire)) {
+      bool any = false;
+      for (int p = 0; p < ctx_->world; ++p) {
+        if (p == ctx_->rank) continue;
+        const uint64_t g = c->grow[p].gen.load(std::memory_order_acquire);
+        while (grow_seen_[p] < g) {
+          const auto& ch = c->grow[p].chunk[grow_seen_[p]];
+          char path[64];
+          snprintf(path, sizeof(path), "/proc/%lld/fd/%lld", (long long)c->grow[p].pid, (long long)ch.fd);
+          const int fd = open(path, O_RDWR);
+          bool ok = fd >= 0 && vmm_slab_map_peer_chunk(vmm_, p, fd, ch.off, ch.bytes);
+          if (fd >= 0) close(fd);
+          if (!ok) {
+            MLSLB_LOG(LOG_ERROR, "heap growth: cannot map chunk %llu of rank %d (%s)", (unsigned long long)grow_seen_[p], p, path);
+            ctx_->boot->poison(ctx_->rank);
+            return;
+          }
+          grow_seen_[p]++;
+          c->grow_ack[p][ctx_->rank].store(grow_seen_[p], std::memory_order_release);
+          any = true;
+        }
+      }
+      if (!any) usleep(200);
+    }
+  }
   // Loop-back ranks (several ranks on ONE GPU: the single-GPU test mode): a kernel that spins on the device for a peer
   // that has not launched yet starves every host call that needs the device idle for a moment - a first kernel with a
   // bigger stack, cudaFree, cublasCreate, any allocation while a thread sits in a pageable copy (probe_blocking.cu) -
@@ -362,6 +440,11 @@ class CudaBackend final : public Backend {
       }
     };
     cudaDeviceSynchronize();
+    if (grow_watcher_.joinable()) {
+      quiet_barrier();                 // nobody is growing any more
+      grow_stop_.store(true, std::memory_order_release);
+      grow_watcher_.join();
+    }
     sweep_parked(true);
     for (int b = 0; b < kPipeBufs; ++b) {
       give_event(pipe_h2d_[b]);
@@ -601,7 +684,9 @@ void CudaBackend::init() {
     const char* mode = getenv("MLSL_SLAB");
     bool want_vmm = !inproc_ && b->size() > 1 && !(mode && !strcmp(mode, "ipc"));
     if (want_vmm) {
-      vmm_ = vmm_slab_create(b, device_, slab_bytes_, ctx_->env.use_nvls && b->size() <= kMaxDevRanks);
+      const double max_gb = ctx_->env.heap_max_gb > 0 ? ctx_->env.heap_max_gb : std::max(32.0, 8.0 * ctx_->env.heap_size_gb);
+      vmm_ = vmm_slab_create(b, device_, slab_bytes_, ctx_->env.use_nvls && b->size() <= kMaxDevRanks,
+                             (size_t)(max_gb * 1073741824.0));
       if (vmm_.ok) {
         slab_ = vmm_.local;
         slab_bytes_ = vmm_.bytes;
@@ -690,6 +775,10 @@ void CudaBackend::init() {
   // that spins for a peer dead-locks as soon as that peer's next kernel is falsely serialised behind it on one queue,
   // so unless told otherwise every collective runs in line on the caller's stream: one stream per rank, program order.
   if (!getenv("MLSL_STREAM_MODE") && ranks_per_device_ > 1) inline_stream_ = true;
+  if (vmm_.ok && b->ctl() && b->size() > 1) {
+    grow_seen_.assign((size_t)W, 0);
+    grow_watcher_ = std::thread([this] { grow_watch(); });
+  }
   b->barrier();
   MLSLB_LOG(LOG_DEBUG, "cuda backend up: device %d slab %p (%zu bytes) ranks/device %d", device_, (void*)slab_,
             slab_bytes_, ranks_per_device_);
@@ -742,7 +831,10 @@ DevComm CudaBackend::make_comm(const ProcessGroup& g, int lane) const {
   if (mc_ && g.size() == ctx_->world && g.size() >= nvls_min) {
     bool ident = true;
     for (int i = 0; i < g.size(); ++i) ident &= g.members[i] == i;
-    if (ident) dc.mc = mc_;
+    if (ident) {
+      dc.mc = mc_;
+      dc.mc_bytes = vmm_.bytes;      // the multicast object covers the initial slab only
+    }
   }
   return dc;
 }
@@ -1079,11 +1171,13 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
         plan.mc_mode = 2;
         plan.mc_bytes = n * es;
       }
+      if (d.kind == OpKind::ALLTOALL) plan.pairs_concurrent = ctx_->env.alltoall_split == 0;
+      if (d.kind == OpKind::ALLTOALLV || d.kind == OpKind::SENDRECV_LIST) plan.pairs_concurrent = ctx_->env.alltoallv_split == 0;
       // big messages: the copy engine (cp.async.bulk rings) moves the segments instead of the threads
       unsigned long long pulled = 0;
       for (int i = 0; i < plan.nseg; ++i) pulled += plan.seg[i].bytes;
       const long bk = ctx_->env.tune.bulk_copy_kb;
-      const bool bulk = bk > 0 && pulled >= ((unsigned long long)bk << 10);
+      const bool bulk = bk > 0 && pulled >= ((unsigned long long)bk << 10) && !plan.pairs_concurrent;   // the ring deals pieces itself
       MLSLB_CUDA(launch_pull_copy(dc, plan, pub_send, ro, ch, bulk, s));
       break;
     }

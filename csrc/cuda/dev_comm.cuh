@@ -38,6 +38,7 @@ struct DevComm {
   int* err;                   // host-mapped error word (0 = ok)
   char* slab[kMaxDevRanks];   // slab base of every member (group order) in MY address space
   char* mc;                   // multicast mapping of the slabs (NVLS) or nullptr
+  unsigned long long mc_bytes;   // the multicast object covers slab offsets [0, mc_bytes) (chunks the heap grew by are not in it)
   unsigned ll_off;            // byte offset of this row's low-latency arena inside every slab (0 = none)
   unsigned mid_off;           // byte offset of this row's mid-size flag-in-data arena (0 = none)
   unsigned mid_seq_off;       // byte offset of my launch counters of the mid kernel (one per CTA)

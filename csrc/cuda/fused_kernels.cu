@@ -24,10 +24,11 @@ __host__ __device__ __forceinline__ size_t quant_nblk4(size_t count) {
   const size_t nblk = (count + kQuantBlock - 1) / kQuantBlock;
   return (nblk + 3) & ~(size_t)3;
 }
-size_t allreduce_quant_stage_bytes(size_t count) {
+__host__ __device__ __forceinline__ size_t allreduce_quant_stage_bytes_dev(size_t count) {
   const size_t nb = quant_nblk4(count);
   return 2 * (ru256(nb * kQuantBlock) + ru256(nb * sizeof(float)));
 }
+size_t allreduce_quant_stage_bytes(size_t count) { return allreduce_quant_stage_bytes_dev(count); }
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, u
   const unsigned long long t = comm_begin(dc, pt, stage_off, stage_off, NoAux());
   const int P = dc.nranks, me = dc.me;
   if (threadIdx.x == 0) {
-    int sym = dc.mc != nullptr && !pt.failed;
+    int sym = dc.mc != nullptr && !pt.failed && stage_off + allreduce_quant_stage_bytes_dev(count) <= dc.mc_bytes;
     for (int p = 0; p < P; ++p) sym &= (pt.send[p] - dc.slab[p]) == (long long)stage_off;
     s_symmetric = sym;
   }

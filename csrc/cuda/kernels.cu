@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(kCommThreads) k_allreduce(DevComm dc, unsigned
       sym &= (pt.send[p] - dc.slab[p]) == (long long)send_off && (pt.recv[p] - dc.slab[p]) == (long long)recv_off;
     }
     s_aligned = (bits & 15ull) == 0;
-    s_symmetric = sym && dc.mc != nullptr && !pt.failed;
+    s_symmetric = sym && dc.mc != nullptr && !pt.failed && send_off + count * sizeof(T) <= dc.mc_bytes &&
+                  recv_off + count * sizeof(T) <= dc.mc_bytes;
   }
   __syncthreads();
   const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
@@ -596,7 +597,7 @@ __global__ void __launch_bounds__(kCommThreads) k_reduce_pull(DevComm dc, unsign
         sym &= (pt.send[p] - dc.slab[p]) == (long long)send_off;
       }
       s_aligned = (bits & 15ull) == 0;
-      s_symmetric = sym && dc.mc != nullptr && !pt.failed;
+      s_symmetric = sym && dc.mc != nullptr && !pt.failed && send_off + (base_elems + count) * sizeof(T) <= dc.mc_bytes;
     }
     __syncthreads();
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
@@ -720,6 +721,7 @@ __device__ __forceinline__ bool pull_copy_try_mc(const DevComm& dc, const PeerTa
     else sym &= (pt.recv[p] - dc.slab[p]) == (long long)recv_off;
   }
   const unsigned long long dst_off = plan.mc_mode == 1 ? send_off : recv_off + (unsigned long long)me * plan.mc_bytes;
+  if ((plan.mc_mode == 1 ? send_off + plan.mc_bytes : recv_off + (unsigned long long)P * plan.mc_bytes) > dc.mc_bytes) return false;
   const char* src = plan.mc_mode == 1 ? pt.send[me] : pt.send[me];
   if (!sym || ((dst_off | (unsigned long long)src | (plan.mc_mode == 2 ? plan.mc_bytes : 0ull)) & 15ull) != 0) return false;
   if (plan.mc_mode == 1 && me != plan.mc_root) return true;          // receivers only wait for the closing handshake
@@ -759,7 +761,14 @@ __global__ void __launch_bounds__(kCommThreads) k_pull_copy(DevComm dc, CopyPlan
     return;
   }
   constexpr int U = 4;
+  // pairs_concurrent: CTA c works on segment c mod nseg only, with the CTAs that share that residue as its sub-grid
+  const bool deal = plan.pairs_concurrent && (int)gridDim.x >= plan.nseg && plan.nseg > 1;
+  const int my_sg = deal ? (int)(blockIdx.x % plan.nseg) : -1;
+  const size_t sub_ctas = deal ? (gridDim.x - my_sg + plan.nseg - 1) / plan.nseg : gridDim.x;
+  const size_t stid = deal ? (size_t)(blockIdx.x / plan.nseg) * blockDim.x + threadIdx.x : gtid;
+  const size_t ssz = deal ? sub_ctas * blockDim.x : gsz;
   for (int sgi = 0; sgi < plan.nseg; ++sgi) {
+    if (deal && sgi != my_sg) continue;
     // rotate the segment order by rank so the peers are not all hammering the same source at the same time
     int sidx = sgi + me;
     while (sidx >= plan.nseg) sidx -= plan.nseg;
@@ -769,6 +778,7 @@ __global__ void __launch_bounds__(kCommThreads) k_pull_copy(DevComm dc, CopyPlan
     if (src == dst || sg.bytes == 0) continue;
     const bool aligned = ((((unsigned long long)src) | ((unsigned long long)dst)) & 15ull) == 0;
     size_t done = 0;
+    const size_t gtid = stid, gsz = ssz;       // this segment's sub-grid (shadows the whole-grid indices)
     if (aligned) {
       const size_t nvec = sg.bytes / 16;
       for (size_t b0 = gtid; b0 < nvec; b0 += gsz * U) {

@@ -24,6 +24,7 @@ struct CopyPlan {
                      // 1 = bcast (mc_root multimem.st's mc_bytes of its buffer), 2 = all-gather (everyone pushes its shard)
   int mc_root;
   unsigned long long mc_bytes;
+  int pairs_concurrent;   // 1: deal the channels to the segments (MLSL_ALLTOALL(V)_SPLIT=0), 0: every segment on all channels
   CopySeg seg[kMaxDevRanks];
   unsigned long long aux_out[kMaxDevRanks];   // word I publish to peer p in the opening handshake
 };

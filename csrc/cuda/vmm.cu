@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "core/bootstrap.hpp"
@@ -106,10 +107,14 @@ void vmm_slab_destroy(VmmSlab& s) {
   }
   for (size_t p = 0; p < s.peers.size(); ++p) {
     if (!s.peers[p]) continue;
-    g_drv.MemUnmap((CUdeviceptr)s.peers[p], s.bytes);
-    g_drv.MemAddressFree((CUdeviceptr)s.peers[p], s.bytes);
+    const size_t mapped = p < s.peer_mapped.size() && s.peer_mapped[p] ? s.peer_mapped[p] : s.bytes;
+    const size_t mine = s.peers[p] == s.local ? std::max(mapped, s.local_mapped) : mapped;
+    g_drv.MemUnmap((CUdeviceptr)s.peers[p], mine);
+    g_drv.MemAddressFree((CUdeviceptr)s.peers[p], s.reserved ? s.reserved : s.bytes);
     if (p < s.h_peers.size() && s.h_peers[p]) g_drv.MemRelease((CUmemGenericAllocationHandle)s.h_peers[p]);
   }
+  for (unsigned long long h : s.h_grown) g_drv.MemRelease((CUmemGenericAllocationHandle)h);
+  s.h_grown.clear();
   s.peers.clear();
   s.h_peers.clear();
   s.local = nullptr;
@@ -117,8 +122,60 @@ void vmm_slab_destroy(VmmSlab& s) {
   s.ok = false;
 }
 
-VmmSlab vmm_slab_create(Bootstrap* boot, int device, size_t bytes, bool want_multicast) {
+int vmm_slab_grow(VmmSlab& s, size_t add_bytes, size_t* off, size_t* got) {
+  if (!s.ok || !g_drv.loaded) return -1;
+  add_bytes = (add_bytes + s.gran - 1) / s.gran * s.gran;
+  if (s.local_mapped + add_bytes > s.reserved) return -1;
+  CUmemAllocationProp prop;
+  memset(&prop, 0, sizeof(prop));
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = s.device;
+  prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  CUmemGenericAllocationHandle h = 0;
+  if (g_drv.MemCreate(&h, add_bytes, &prop, 0) != CUDA_SUCCESS) return -1;
+  const CUdeviceptr va = (CUdeviceptr)(s.local + s.local_mapped);
+  CUmemAccessDesc acc;
+  memset(&acc, 0, sizeof(acc));
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = s.device;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  int fd = -1;
+  if (g_drv.MemMap(va, add_bytes, 0, h, 0) != CUDA_SUCCESS || g_drv.MemSetAccess(va, add_bytes, &acc, 1) != CUDA_SUCCESS ||
+      g_drv.MemExportToShareableHandle(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS) {
+    g_drv.MemRelease(h);
+    return -1;
+  }
+  s.h_grown.push_back(h);
+  *off = s.local_mapped;
+  *got = add_bytes;
+  s.local_mapped += add_bytes;
+  return fd;
+}
+
+bool vmm_slab_map_peer_chunk(VmmSlab& s, int peer, int fd, size_t off, size_t bytes) {
+  if (!s.ok || !g_drv.loaded || peer < 0 || peer >= (int)s.peers.size() || !s.peers[peer]) return false;
+  if (off + bytes > s.reserved) return false;
+  CUmemGenericAllocationHandle h = 0;
+  if (g_drv.MemImportFromShareableHandle(&h, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) != CUDA_SUCCESS) return false;
+  const CUdeviceptr va = (CUdeviceptr)(s.peers[peer] + off);
+  CUmemAccessDesc acc;
+  memset(&acc, 0, sizeof(acc));
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = s.device;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (g_drv.MemMap(va, bytes, 0, h, 0) != CUDA_SUCCESS || g_drv.MemSetAccess(va, bytes, &acc, 1) != CUDA_SUCCESS) {
+    g_drv.MemRelease(h);
+    return false;
+  }
+  s.h_grown.push_back(h);
+  s.peer_mapped[peer] = std::max(s.peer_mapped[peer], off + bytes);
+  return true;
+}
+
+VmmSlab vmm_slab_create(Bootstrap* boot, int device, size_t bytes, bool want_multicast, size_t reserve_bytes) {
   VmmSlab s;
+  s.device = device;
   const int W = boot->size(), me = boot->rank();
   s.peers.assign(W, nullptr);
   s.h_peers.assign(W, 0);
@@ -164,14 +221,19 @@ VmmSlab vmm_slab_create(Bootstrap* boot, int device, size_t bytes, bool want_mul
   if (gran == 0) gran = (size_t)2 << 20;
   bytes = (bytes + gran - 1) / gran * gran;
   s.bytes = bytes;
+  s.gran = gran;
+  s.reserved = std::max(bytes, (reserve_bytes + gran - 1) / gran * gran);
+  s.local_mapped = bytes;
+  s.peer_mapped.assign(W, 0);
   {
     CUmemGenericAllocationHandle h = 0;
     CUdeviceptr va = 0;
     DRV_TRY(g_drv.MemCreate(&h, bytes, &prop, 0), "cuMemCreate");
     s.h_local = h;
     s.h_peers[me] = h;
-    DRV_TRY(g_drv.MemAddressReserve(&va, bytes, gran, 0, 0), "cuMemAddressReserve");
+    DRV_TRY(g_drv.MemAddressReserve(&va, s.reserved, gran, 0, 0), "cuMemAddressReserve");
     s.peers[me] = (char*)va;
+    s.peer_mapped[me] = bytes;
     DRV_TRY(g_drv.MemMap(va, bytes, 0, h, 0), "cuMemMap");
     acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
     acc.location.id = device;
@@ -199,10 +261,11 @@ done:
     CUresult r = g_drv.MemImportFromShareableHandle(&h, (void*)(uintptr_t)fds[p], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
     if (r == CUDA_SUCCESS) {
       s.h_peers[p] = h;
-      r = g_drv.MemAddressReserve(&va, bytes, gran, 0, 0);
+      r = g_drv.MemAddressReserve(&va, s.reserved, gran, 0, 0);
     }
     if (r == CUDA_SUCCESS) {
       s.peers[p] = (char*)va;
+      s.peer_mapped[p] = bytes;
       r = g_drv.MemMap(va, bytes, 0, h, 0);
     }
     if (r == CUDA_SUCCESS) r = g_drv.MemSetAccess(va, bytes, &acc, 1);

@@ -20,7 +20,7 @@ from ._lib import MLSLError  # noqa: E402
 from .api import (CompressionType, DataType, GroupType, InprocWorld, MLSL, OperationType, OptimizerType, PhaseType,
                   ReductionType, cuda_available)
 from .comm import (Work, alloc_tensor, allgather, allgatherv, allreduce, alltoall, alltoallv, barrier, bcast, bind_thread_state, env, finalize,
-                   free_tensor, gather, init, is_device, is_initialized, rank, reduce, reduce_scatter, ring_shift, scatter, tensor_from_address,
+                   free_tensor, gather, heap_pool, init, is_device, is_initialized, rank, reduce, reduce_scatter, ring_shift, scatter, tensor_from_address,
                    world_distribution, world_size)
 
 __version__ = "2026.1"

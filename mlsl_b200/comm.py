@@ -234,6 +234,33 @@ def alloc_tensor(shape, dtype=torch.float32, zero=True):
     return t
 
 
+_HEAP_POOL = {}
+
+
+def heap_pool():
+    """Context manager: torch CUDA allocations made inside it come from this rank's symmetric heap (a torch.cuda.MemPool on a
+    CUDAPluggableAllocator that calls Environment::Alloc / Free), so collectives on them - DDP / FSDP buckets, the "mlsl"
+    torch.distributed backend, optimizer flats - run zero-copy instead of being staged through heap scratch.
+
+        with mlsl_b200.heap_pool():
+            model = DDP(model.cuda())            # gradient buckets live in the heap from now on
+    """
+    if not is_device():
+        import contextlib
+        return contextlib.nullcontext()
+    st = _state()
+    pool = st.get("heap_pool")
+    if pool is None:
+        from . import _lib
+        alloc = _HEAP_POOL.get("alloc")
+        if alloc is None:
+            alloc = torch.cuda.memory.CUDAPluggableAllocator(_lib.LIB_PATH, "mlsl_heap_malloc", "mlsl_heap_free")
+            _HEAP_POOL["alloc"] = alloc
+        pool = torch.cuda.MemPool(alloc.allocator())
+        st["heap_pool"] = pool
+    return torch.cuda.use_mem_pool(pool)
+
+
 def free_tensor(t):
     ptr = t.data_ptr()
     st = _state()

@@ -150,6 +150,18 @@ def main():
             check("sub-group allreduce %dx%d %s" % (D, M, grp), bool((t == float(sum(q + 1 for q in mem))).all().item()) and len(mem) == P)
             mlsl.free_tensor(t)
         env.delete_distribution(dist)
+    # ---- device-heap expansion: one allocation bigger than the whole initial heap (MLSL_HEAP_SIZE_GB=2); the new chunk is
+    #      mapped by every peer's watcher thread, then peers read / write it like any other heap memory ----------------------
+    if "VMM" in env.describe_backend():
+        nbig = int(2.25 * (1 << 30)) // 4
+        big = mlsl.alloc_tensor(nbig, torch.float32, zero=False)
+        big.fill_(float(r + 1))
+        mlsl.allreduce(big)
+        torch.cuda.synchronize()
+        want = float(W * (W + 1) // 2)
+        check("heap growth: all-reduce inside a 2.25 GiB allocation on a 2 GiB heap (%s)" % env.describe_backend().split(",")[2].strip(),
+              bool((big[:1 << 20] == want).all().item()) and bool((big[-(1 << 20):] == want).all().item()))
+        mlsl.free_tensor(big)
     mlsl.finalize()
     if r == 0:
         print("mp_gpu_check: %s" % ("ALL PASSED" if not fails else "FAILED: %s" % fails), flush=True)

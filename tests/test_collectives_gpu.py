@@ -172,6 +172,61 @@ def test_reduce_scatter_allgather(world):
         assert torch.equal(z, full)
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("n", [3331, 300000])
+def test_alltoall_split_knobs(split, n):
+    """MLSL_ALLTOALL_SPLIT / MLSL_ALLTOALLV_SPLIT (reference src/comm_ep.cpp:1192,1270): 1 = every pair message spread over
+    all channels, 0 = the channels are dealt to the pairs, all pairs moving at once.  Same result either way."""
+    world = 4
+
+    def body(r, mlsl):
+        a = mlsl.alloc_tensor(world * n, torch.float32)
+        a.copy_(torch.arange(world * n, dtype=torch.float32) + 1000000 * r)
+        out = mlsl.alltoall(a)
+        counts = [(p + r) % 3 * 1000 + 7 for p in range(world)]             # what I send to p
+        rcounts = [(r + p) % 3 * 1000 + 7 for p in range(world)]            # what p sends to me (same formula, symmetric)
+        v = mlsl.alltoallv(a[:sum(counts)], counts, rcounts)
+        torch.cuda.current_stream().synchronize()
+        return out.cpu(), v.cpu()
+
+    outs = _gpu(body, world, env={"MLSL_ALLTOALL_SPLIT": split, "MLSL_ALLTOALLV_SPLIT": split})
+    for r, (out, v) in enumerate(outs):
+        for p in range(world):
+            want = (torch.arange(world * n, dtype=torch.float32) + 1000000 * p)[r * n:(r + 1) * n]
+            assert torch.equal(out[p * n:(p + 1) * n], want), (split, r, p)
+        off = 0
+        for p in range(world):
+            pc = [(q + p) % 3 * 1000 + 7 for q in range(world)]             # p's send counts
+            so = sum(pc[:r])
+            cnt = pc[r]
+            want = (torch.arange(world * n, dtype=torch.float32) + 1000000 * p)[so:so + cnt]
+            assert torch.equal(v[off:off + cnt], want), (split, r, p)
+            off += cnt
+
+
+def test_heap_pool_makes_torch_allocations_zero_copy():
+    """`with mlsl.heap_pool():` - torch allocations come from the symmetric heap (pluggable allocator), so a collective on
+    them passes the pointer check that rejects foreign buffers (MLSL_POINTER_CHECK=1) and needs no staging."""
+    world, n = 2, 100000
+
+    def body(r, mlsl):
+        with mlsl.heap_pool():
+            x = torch.full((n,), float(r + 1), device="cuda")
+            y = torch.empty(n, device="cuda")
+        mlsl.allreduce(x, out=y)
+        foreign_rejected = False
+        try:
+            mlsl.allreduce(torch.ones(n, device="cuda"))
+        except mlsl.MLSLError:
+            foreign_rejected = True
+        torch.cuda.current_stream().synchronize()
+        ok = bool((y == 3.0).all().item())
+        del x, y
+        return ok, foreign_rejected
+
+    assert _gpu(body, world, env={"MLSL_POINTER_CHECK": "1"}) == [(True, True)] * world
+
+
 def test_bcast_reduce_gather_scatter_alltoall():
     world, n = 4, 3331
 
