@@ -397,6 +397,56 @@ std::vector<int> Bootstrap::allgather_fd(int fd) {
   return out;
 }
 
+bool Bootstrap::send_fd_to(int r, int fd, const uint64_t payload[3]) {
+  if (inproc_ || uds_fd_ < 0) return false;
+  sockaddr_un a;
+  memset(&a, 0, sizeof(a));
+  a.sun_family = AF_UNIX;
+  int n = snprintf(a.sun_path + 1, sizeof(a.sun_path) - 1, "mlslb_%d_%s_%d", (int)getuid(), key_.c_str(), r);
+  uint64_t buf[3] = {payload[0], payload[1], payload[2]};
+  iovec iov{buf, sizeof(buf)};
+  char cbuf[CMSG_SPACE(sizeof(int))];
+  memset(cbuf, 0, sizeof(cbuf));
+  msghdr m;
+  memset(&m, 0, sizeof(m));
+  m.msg_name = &a;
+  m.msg_namelen = (socklen_t)(offsetof(sockaddr_un, sun_path) + 1 + n);
+  m.msg_iov = &iov;
+  m.msg_iovlen = 1;
+  m.msg_control = cbuf;
+  m.msg_controllen = sizeof(cbuf);
+  cmsghdr* c = CMSG_FIRSTHDR(&m);
+  c->cmsg_level = SOL_SOCKET;
+  c->cmsg_type = SCM_RIGHTS;
+  c->cmsg_len = CMSG_LEN(sizeof(int));
+  memcpy(CMSG_DATA(c), &fd, sizeof(int));
+  ssize_t s;
+  do { s = sendmsg(uds_fd_, &m, 0); } while (s < 0 && (errno == EINTR || errno == EAGAIN));
+  return s == (ssize_t)sizeof(buf);
+}
+
+bool Bootstrap::try_recv_fd(int* fd, uint64_t payload[3]) {
+  if (inproc_ || uds_fd_ < 0) return false;
+  uint64_t buf[3] = {0, 0, 0};
+  iovec iov{buf, sizeof(buf)};
+  char cbuf[CMSG_SPACE(sizeof(int))];
+  msghdr m;
+  memset(&m, 0, sizeof(m));
+  m.msg_iov = &iov;
+  m.msg_iovlen = 1;
+  m.msg_control = cbuf;
+  m.msg_controllen = sizeof(cbuf);
+  ssize_t s = recvmsg(uds_fd_, &m, MSG_DONTWAIT);
+  if (s != (ssize_t)sizeof(buf)) return false;
+  cmsghdr* c = CMSG_FIRSTHDR(&m);
+  if (!c || c->cmsg_type != SCM_RIGHTS) return false;
+  memcpy(fd, CMSG_DATA(c), sizeof(int));
+  payload[0] = buf[0];
+  payload[1] = buf[1];
+  payload[2] = buf[2];
+  return true;
+}
+
 void Bootstrap::poison(int code) {
   if (tcp_) {
     tcp_->poison(code);

@@ -110,6 +110,10 @@ class Bootstrap {
   // File-descriptor exchange (multi-process only): every rank contributes one fd, receives world fds
   // (its own slot is a dup).  Used for CUDA VMM shareable handles.
   std::vector<int> allgather_fd(int fd);
+  // Point-to-point descriptor passing over the same sockets, any time after start-up (device-heap expansion): send one
+  // descriptor + 24 bytes to `rank`; poll for one (non-blocking, false when nothing is waiting).  Multi-process only.
+  bool send_fd_to(int rank, int fd, const uint64_t payload[3]);
+  bool try_recv_fd(int* fd, uint64_t payload[3]);
 
   // Fail-fast: mark the job poisoned / query it / beat.
   void poison(int code);

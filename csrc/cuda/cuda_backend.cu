@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <cerrno>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -272,10 +273,17 @@ class CudaBackend final : public Backend {
     const int fd = vmm_slab_grow(vmm_, add, &off, &got);
     if (fd < 0) return false;
     rec.pid = (int64_t)getpid();
-    rec.chunk[n].fd = fd;             // stays open: the peers read it through /proc/<pid>/fd
+    rec.chunk[n].fd = fd;
     rec.chunk[n].off = off;
     rec.chunk[n].bytes = got;
     rec.gen.store(n + 1, std::memory_order_release);
+    // hand the descriptor to every peer's watcher thread (SCM_RIGHTS over the bootstrap's sockets)
+    const uint64_t msg[3] = {(uint64_t)ctx_->rank, (uint64_t)off, (uint64_t)got};
+    for (int p = 0; p < ctx_->world; ++p)
+      if (p != ctx_->rank && !ctx_->boot->send_fd_to(p, fd, msg)) {
+        MLSLB_LOG(LOG_ERROR, "heap growth: cannot send the chunk descriptor to rank %d", p);
+        return false;
+      }
     // wait for every peer (their watcher threads run independently of what their API threads are doing)
     const uint64_t t0 = now_ns();
     for (int p = 0; p < ctx_->world; ++p) {
@@ -288,6 +296,7 @@ class CudaBackend final : public Backend {
         }
       }
     }
+    close(fd);                        // every peer holds its own duplicate now
     heap_.extend(got);
     slab_bytes_ = vmm_.local_mapped;
     MLSLB_LOG(LOG_INFO, "device heap of rank %d grew by %.2f GiB to %.2f GiB", ctx_->rank, got / 1073741824.0, slab_bytes_ / 1073741824.0);
@@ -298,25 +307,20 @@ class CudaBackend final : public Backend {
     cudaSetDevice(device_);
     while (!grow_stop_.load(std::memory_order_acquire)) {
       bool any = false;
-      for (int p = 0; p < ctx_->world; ++p) {
-        if (p == ctx_->rank) continue;
-        const uint64_t g = c->grow[p].gen.load(std::memory_order_acquire);
-        while (grow_seen_[p] < g) {
-          const auto& ch = c->grow[p].chunk[grow_seen_[p]];
-          char path[64];
-          snprintf(path, sizeof(path), "/proc/%lld/fd/%lld", (long long)c->grow[p].pid, (long long)ch.fd);
-          const int fd = open(path, O_RDWR);
-          bool ok = fd >= 0 && vmm_slab_map_peer_chunk(vmm_, p, fd, ch.off, ch.bytes);
-          if (fd >= 0) close(fd);
-          if (!ok) {
-            MLSLB_LOG(LOG_ERROR, "heap growth: cannot map chunk %llu of rank %d (%s)", (unsigned long long)grow_seen_[p], p, path);
-            ctx_->boot->poison(ctx_->rank);
-            return;
-          }
-          grow_seen_[p]++;
-          c->grow_ack[p][ctx_->rank].store(grow_seen_[p], std::memory_order_release);
-          any = true;
+      int fd = -1;
+      uint64_t msg[3];
+      while (ctx_->boot->try_recv_fd(&fd, msg)) {
+        const int p = (int)msg[0];
+        const bool ok = p >= 0 && p < ctx_->world && vmm_slab_map_peer_chunk(vmm_, p, fd, (size_t)msg[1], (size_t)msg[2]);
+        close(fd);
+        if (!ok) {
+          MLSLB_LOG(LOG_ERROR, "heap growth: cannot map the chunk rank %d added at offset %llu", p, (unsigned long long)msg[1]);
+          ctx_->boot->poison(ctx_->rank);
+          return;
         }
+        grow_seen_[p]++;
+        c->grow_ack[p][ctx_->rank].store(grow_seen_[p], std::memory_order_release);
+        any = true;
       }
       if (!any) usleep(200);
     }
@@ -1048,7 +1052,11 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
     case OpKind::FUSED_UPDATE: work = n * 4; break;
     default: break;   // gather-like: everything a rank pulls
   }
-  const int ch = pick_channels(work);
+  int ch = pick_channels(work);
+  // the *v exchanges move a different number of bytes on every rank, but the grid (= the channels that shake hands) has
+  // to be the same everywhere: a fixed grid for them
+  if (d.kind == OpKind::ALLTOALLV || d.kind == OpKind::SENDRECV_LIST)
+    ch = std::min(32, std::min(kMaxChannels, std::max(1, sm_count_ / std::max(1, ranks_per_device_))));
 
   switch (d.kind) {
     case OpKind::BARRIER: MLSLB_CUDA(launch_barrier(dc, s)); break;

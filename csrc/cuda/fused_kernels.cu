@@ -89,7 +89,11 @@ __global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, u
 
   // ---- phase 1: (x + residual) -> fp8 blocks in my staging area; residual <- quantisation error.  The only pass over
   //      the fp32 input: 4 + 4 bytes read, 4 + 1 written per element, one warp per 128-element block. --------------------
-  for (size_t b = c + (size_t)warp * C; b < nblk4; b += C * nwarp) {
+  //      Work is dealt by SUPERBLOCK: superblock sb belongs to channel sb % C in every phase and on every rank, so the
+  //      per-channel handshakes below order exactly the producers and consumers of each block.
+  for (size_t sb1 = c + (size_t)warp * C; sb1 < nsb; sb1 += C * nwarp)
+  for (int j = 0; j < 4; ++j) {
+    const size_t b = sb1 * 4 + j;
     const size_t e0 = b * kQuantBlock + (size_t)lane * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f), r = v;
     if (e0 + 3 < count) {
@@ -125,7 +129,8 @@ __global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, u
   const size_t slo = min(nsb, (size_t)me * sb_per), shi = min(nsb, slo + sb_per);
   const int sub = lane >> 3, l8 = lane & 7;                     // block inside the superblock, 16-byte piece inside the block
   const bool mcast = s_symmetric != 0;
-  for (size_t sb = slo + c + (size_t)warp * C; sb < shi; sb += C * nwarp) {
+  const size_t sbstart = slo + ((c + C - slo % C) % C);         // first superblock of my slice that belongs to this channel
+  for (size_t sb = sbstart + (size_t)warp * C; sb < shi; sb += C * nwarp) {
     const size_t b = sb * 4 + sub;
     float acc[16];
 #pragma unroll

@@ -52,6 +52,8 @@ def run_ranks(nranks, fn, backend="host", env=None, timeout=300, wait_mode=None)
 
     old = {}
     new = {"MLSL_BACKEND": backend}
+    if backend == "cuda":
+        new["MLSL_DEVICE"] = "0"       # loop-back ranks all live on GPU 0, also on a box with several GPUs
     new.update(env or {})
     for k, v in new.items():
         old[k] = os.environ.get(k)
