@@ -1,5 +1,4 @@
-"""CUDA twins of the pipeline- and expert-parallel tests (device tensors, loop-back ranks on one GPU).  Opt-in until their
-first hardware run: MLSL_TEST_STRATEGIES_GPU=1 pytest tests/test_zz_strategies_gpu.py -m gpu (docs/NEXT_STEPS.md 2.9)."""
+"""CUDA twins of the pipeline- and expert-parallel tests (device tensors, loop-back ranks on one GPU)."""
 import os
 import threading
 
@@ -8,8 +7,11 @@ import torch
 
 from conftest import run_ranks
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("MLSL_TEST_STRATEGIES_GPU") != "1",
-                                                  reason="opt-in: not yet run on hardware")]
+pytestmark = pytest.mark.gpu
+# pipeline and expert parallelism run here by default (validated on hardware in round 2); the transformer block is
+# torch-heavy (cuBLASLt workspaces, many first-use kernels per thread) and stays opt-in in loop-back mode - it runs one rank
+# per GPU in examples/ and tests/mp_gpu_check.py
+_opt_in = pytest.mark.skipif(os.environ.get("MLSL_TEST_STRATEGIES_GPU") != "1", reason="loop-back opt-in (torch-heavy)")
 _lock = threading.Lock()
 ENV = {"MLSL_HEAP_SIZE_GB": "0.5", "MLSL_WATCHDOG_SEC": "20"}
 
@@ -81,6 +83,7 @@ def test_expert_parallel_device():
         assert torch.allclose(gw2, w2.grad[r * El:(r + 1) * El], atol=1e-3, rtol=1e-2)
 
 
+@_opt_in
 def test_parallel_transformer_block_device():
     """bf16 block on the fused kernels' shapes (GEMM + reduce-scatter always; all-gather + GEMM with MLSL_AG_GEMM=1)."""
     from test_parallel_transformer import _full, _reference
