@@ -923,7 +923,8 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   // pull from / push to its own buffers).  Lets ncu profile the kernels on one GPU - under the profiler kernels
   // are serialised, so ranks that wait for each other can never be captured.
   const bool force_solo = ctx_->env.tune.force_kernel_solo != 0;
-  if (!g || g->size() <= 1 ? !((force_solo && g && g->row >= 0) || d.kind == OpKind::FUSED_UPDATE || d.kind == OpKind::GEMM_RS || d.kind == OpKind::AG_GEMM) : false) {
+  // (self groups have no signal row of their own: make_comm gives them the reserved last row)
+  if (!g || g->size() <= 1 ? !((force_solo && g) || d.kind == OpKind::FUSED_UPDATE || d.kind == OpKind::GEMM_RS || d.kind == OpKind::AG_GEMM) : false) {
     size_t bytes = 0;
     switch (d.kind) {
       case OpKind::ALLREDUCE: case OpKind::REDUCE: case OpKind::REDUCE_SCATTER: case OpKind::ALLGATHER:
