@@ -78,6 +78,8 @@ DistributionImpl::DistributionImpl(RankContext* c, ProcessGroup* data)
       modelGroup(c->self_group), replicaGroup(c->self_group) {}
 
 DistributionImpl::~DistributionImpl() {
+  for (auto& kv : compressed) delete kv.second;
+  compressed.clear();
   auto drop = [&](ProcessGroup* g) {
     if (!(g && g != ctx->global_group && g != ctx->self_group && g != ctx->world_group)) return;
     try {   // destructors must not throw: a poisoned / timed-out job is reported, not escalated to terminate()
@@ -622,6 +624,38 @@ CommReq* Distribution::AllReduceEx(void* sendBuffer, void* recvBuffer, size_t co
                                    GroupType gt, float scale, CompressionType compress) {
   auto d = SELF(DistributionImpl);
   check_count(count);
+  if (compress == CT_QUANTIZATION) {
+    // persistent per (buffers, count, ...): the error-feedback residual lives in the request's backend state
+    DistributionImpl::CompressKey key{sendBuffer, recvBuffer, count, (int)dt, (int)rt, (int)gt};
+    auto it = d->compressed.find(key);
+    if (it != d->compressed.end() && !it->second->active()) {
+      CommRequest* r = it->second;
+      r->desc.scale = scale;
+      d->ctx->register_request(r);
+      r->start(sendBuffer, recvBuffer);
+      return (CommReq*)r;
+    }
+    if (it == d->compressed.end()) {
+      if (d->compressed.size() >= 64) {          // bounded: drop idle entries (their residuals start from zero again)
+        for (auto e = d->compressed.begin(); e != d->compressed.end();)
+          if (!e->second->active()) {
+            delete e->second;
+            e = d->compressed.erase(e);
+          } else {
+            ++e;
+          }
+      }
+      CommRequest* r = d->make_request(mlslb::OpKind::ALLREDUCE, dt, gt);
+      r->one_shot = false;                       // Environment::Wait / Test leave it alive
+      r->desc.count = count;
+      r->desc.rop = to_redop(rt);
+      r->desc.scale = scale;
+      r->desc.compress = true;
+      d->compressed[key] = r;
+      return d->submit(r, sendBuffer, recvBuffer);
+    }
+    // same buffers started again while the previous run is still in flight: fall through to a one-shot request
+  }
   CommRequest* r = d->make_request(mlslb::OpKind::ALLREDUCE, dt, gt);
   r->desc.count = count;
   r->desc.rop = to_redop(rt);

@@ -5,6 +5,8 @@
 // comm buffers, and expose pack/unpack block descriptors plus Start/Wait/Test per tensor.  The requests it builds
 // are persistent CommRequests executed by the active backend (CUDA peer-memory kernels or host shared memory).
 #pragma once
+#include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -142,6 +144,19 @@ class DistributionImpl : public Distribution {
   ProcessGroup* dataGroup = nullptr;
   ProcessGroup* modelGroup = nullptr;
   ProcessGroup* replicaGroup = nullptr;
+  // Compressed (fp8) all-reduces of the Distribution API keep their request - and with it the error-feedback residual -
+  // per (buffers, count, reduction, group), as the reference keys its residual by the buffer address (quant/quant.c:153-167);
+  // a fresh one-shot request per call would quantise without ever compensating the error.
+  struct CompressKey {
+    void* send;
+    void* recv;
+    size_t count;
+    int dt, rt, gt;
+    bool operator<(const CompressKey& o) const {
+      return std::tie(send, recv, count, dt, rt, gt) < std::tie(o.send, o.recv, o.count, o.dt, o.rt, o.gt);
+    }
+  };
+  std::map<CompressKey, CommRequest*> compressed;
 };
 
 struct RegTensor {

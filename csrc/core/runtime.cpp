@@ -832,6 +832,10 @@ void context_init(RankContext* ctx) {
       // API thread only records an event and pushes a ring entry (the reference's endpoint server, as a thread).  Ranks
       // that share a GPU (loop-back tests) and inline-stream mode launch from the caller.
       ns = ctx->backend->default_servers();
+    } else if (ctx->boot->is_tcp()) {
+      // jobs that span nodes: Start() must not run a whole TCP collective on the caller (ranks that start collectives on
+      // overlapping groups in different orders would wait for each other): one progress thread, like the reference's servers
+      ns = 1;
     } else if (!ctx->env.check_single_node) {
       ns = 4;
     } else {

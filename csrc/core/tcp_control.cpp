@@ -15,6 +15,8 @@
 #include "log.hpp"
 
 namespace mlslb {
+constexpr uint64_t kMaxCtlPayload = (uint64_t)1 << 20;   // gather payloads are kBootSlotBytes-sized; 1 MiB is generous
+
 
 // ---- socket helpers ------------------------------------------------------------------------------------------------
 static bool resolve(const std::string& addr, int port, sockaddr_in* out) {
@@ -330,7 +332,8 @@ void TcpControl::server_accept_loop() {
       close(fd);
       continue;
     }
-    if (h.type != MSG_HELLO || (int)h.rank >= world_ || (int)h.nmembers != world_) {
+    // (compared as unsigned: a rank >= 2^31 must not turn into a negative index)
+    if (h.type != MSG_HELLO || (uint64_t)h.rank >= (uint64_t)world_ || (uint64_t)h.nmembers != (uint64_t)world_) {
       close(fd);
       continue;
     }
@@ -351,6 +354,7 @@ void TcpControl::server_client_loop(int fd, int peer_rank) {
     std::vector<char> payload;
     try {
       tcp_recv_all(fd, &h, sizeof(h));
+      if ((uint64_t)h.bytes > kMaxCtlPayload) throw std::runtime_error("control message too large");   // never trust a length from the wire
       payload.resize(h.bytes);
       if (h.bytes) tcp_recv_all(fd, payload.data(), h.bytes);
     } catch (const std::exception&) {
