@@ -36,8 +36,10 @@ else:   # mlslrun: the ranks share a job id, use a file store named after it
 
 torch.manual_seed(0)
 model = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.GELU(), torch.nn.Linear(256, 64)).to(dev)
-ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index] if dev.type == "cuda" else None,
-                                                bucket_cap_mb=0.05)
+import mlsl_b200  # noqa: E402
+with mlsl_b200.heap_pool():     # CUDA backend: DDP's gradient buckets are allocated in the symmetric heap -> zero-copy all-reduces
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index] if dev.type == "cuda" else None,
+                                                    bucket_cap_mb=0.05)
 opt = torch.optim.AdamW(ddp.parameters(), lr=1e-2)
 torch.manual_seed(100 + rank)
 x, y = torch.randn(32, 64, device=dev), torch.randn(32, 64, device=dev)

@@ -150,6 +150,25 @@ def main():
             check("sub-group allreduce %dx%d %s" % (D, M, grp), bool((t == float(sum(q + 1 for q in mem))).all().item()) and len(mem) == P)
             mlsl.free_tensor(t)
         env.delete_distribution(dist)
+    # ---- tcgen05 GEMMs fused with their collectives, one rank per GPU (k_gemm_rs2 on CTA pairs by default, k_ag_gemm) ----------
+    from mlsl_b200.ops.ag_gemm import allgather_gemm
+    from mlsl_b200.ops.gemm_rs import gemm_reduce_scatter
+    M, N, K = 256 * W, 512, 256
+    gen = torch.Generator().manual_seed(4242)
+    a_full = (torch.randn(W, M, K, generator=gen) * 0.25).to(torch.bfloat16)          # rank p multiplies a_full[p] @ w_full[p].T
+    w_full = (torch.randn(W, N, K, generator=gen) * 0.25).to(torch.bfloat16)
+    out = gemm_reduce_scatter(a_full[r].cuda(), w_full[r].cuda(), out_dtype=torch.float32, group="data")
+    ref = sum(a_full[p].float() @ w_full[p].float().t() for p in range(W))
+    torch.cuda.synchronize()
+    rows = M // W
+    err = (out.cpu() - ref[r * rows:(r + 1) * rows]).abs().max().item() / ref.abs().max().item()
+    check("gemm + reduce-scatter %dx%dx%d (rel err %.1e)" % (M, N, K, err), err < 2e-2)
+    xs = a_full[0][r * rows:(r + 1) * rows].contiguous().cuda()                        # row shard of ONE matrix
+    y, xg = allgather_gemm(xs, w_full[0].cuda(), out_dtype=torch.float32, group="data")
+    torch.cuda.synchronize()
+    ref2 = a_full[0].float() @ w_full[0].float().t()
+    err2 = (y.cpu() - ref2).abs().max().item() / ref2.abs().max().item()
+    check("all-gather + gemm %dx%dx%d (rel err %.1e)" % (M, N, K, err2), err2 < 2e-2 and torch.equal(xg.cpu(), a_full[0]))
     # ---- device-heap expansion: one allocation bigger than the whole initial heap (MLSL_HEAP_SIZE_GB=2); the new chunk is
     #      mapped by every peer's watcher thread, then peers read / write it like any other heap memory ----------------------
     if "VMM" in env.describe_backend():
