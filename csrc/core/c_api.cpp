@@ -90,6 +90,7 @@ int mlsl_activation_get_fm_size(mlsl_activation a, size_t* v) { C_GUARD(*need(v)
 int mlsl_activation_get_comm_buf(mlsl_activation a, void** v) { C_GUARD(*need(v) = H<Activation>(a)->GetCommBuf()) }
 int mlsl_activation_get_comm_buf_size(mlsl_activation a, size_t* v) { C_GUARD(*need(v) = H<Activation>(a)->GetCommBufSize()) }
 int mlsl_activation_start_comm(mlsl_activation a, void* buf) { C_GUARD(H<Activation>(a)->StartComm(buf)) }
+int mlsl_activation_start_comm_fused(mlsl_activation a, void* local, void* dst) { C_GUARD(H<Activation>(a)->StartCommFused(local, dst)) }
 int mlsl_activation_wait_comm(mlsl_activation a, void** v) { C_GUARD(*need(v) = H<Activation>(a)->WaitComm()) }
 int mlsl_activation_pack(mlsl_activation a, const void* local_buf, void* comm_buf) { C_GUARD(H<Activation>(a)->Pack(local_buf, comm_buf)) }
 int mlsl_activation_unpack(mlsl_activation a, const void* comm_buf, void* local_buf) { C_GUARD(H<Activation>(a)->Unpack(comm_buf, local_buf)) }

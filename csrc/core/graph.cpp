@@ -274,13 +274,68 @@ void ActivationImpl::start(void* buf) {
   st->leave(op->opIndex, kind, index, StatisticsImpl::START, needComm ? req : nullptr);
 }
 
+// [ext] Activation::StartCommFused(local, dst): the pack / exchange / unpack sequence in one call.  For the all-to-all
+// patterns (cases 4 and 5) on a backend with strided support this is ONE kernel: every member pulls the rectangle meant
+// for it straight out of each peer's unpacked tensor and writes it straight into its own unpacked `dst` (or, without `dst`,
+// packed into the receive region): no pack kernel, no unpack kernel, no packed send region.  Everywhere else
+// it is Pack + StartComm, and WaitComm unpacks into `dst` before it returns.
+void ActivationImpl::start_fused(void* local, void* dst) {
+  fusedDst = unpackDst = nullptr;
+  if (!needComm || !req || req->desc.kind == OpKind::BARRIER) return;
+  RankContext* ctx = op->session->ctx;
+  ProcessGroup* g = req->desc.group;
+  const bool a2a = (commCase == 4 || commCase == 5) && req->desc.kind == OpKind::ALLTOALL && peer && g &&
+                   packBlocks.size() == (size_t)g->size() && peer->unpackBlocks.size() == (size_t)g->size();
+  if (!(a2a && ctx->backend->supports_strided_alltoall() && g->size() > 1)) {
+    commBuf.allocate();
+    pack(local, commBuf.ptr, false);
+    unpackDst = dst;
+    start(commBuf.ptr);
+    return;
+  }
+  const size_t es = dtype_size(to_dtype(dataType));
+  const BlockImpl* mine = packBlocks[(size_t)g->idx];      // the block every peer holds for ME has this geometry in ITS tensor
+  CommDesc::Strided& sd = req->desc.strided;
+  sd.on = true;
+  sd.rows = mine->mbCount;
+  sd.row_bytes = mine->fmCount * mine->fmSize * es;
+  sd.src_off = (mine->mbOffset * localFmCount + mine->fmOffset) * mine->fmSize * es;
+  sd.src_stride = localFmCount * mine->fmSize * es;
+  sd.src_total = op->localMb * localFmCount * fmSize * es;
+  sd.dst_direct = dst != nullptr;
+  sd.dst_off.clear();
+  if (dst) {
+    sd.dst_stride = peer->localFmCount * peer->fmSize * es;
+    sd.dst_total = peer->op->localMb * peer->localFmCount * peer->fmSize * es;
+    for (BlockImpl* b : peer->unpackBlocks) sd.dst_off.push_back((b->mbOffset * peer->localFmCount + b->fmOffset) * b->fmSize * es);
+  } else {
+    commBuf.allocate();
+  }
+  fusedDst = dst;
+  StatisticsImpl* st = op->session->stats;
+  auto kind = isInput ? StatisticsImpl::INPUT_ACT : StatisticsImpl::OUTPUT_ACT;
+  st->enter(op->opIndex, kind, index, StatisticsImpl::START);
+  req->start(local, dst ? dst : (char*)commBuf.ptr + sendRegionBytes);
+  st->leave(op->opIndex, kind, index, StatisticsImpl::START, req);
+}
+
 void* ActivationImpl::wait() {
   StatisticsImpl* st = op->session->stats;
   auto kind = isInput ? StatisticsImpl::INPUT_ACT : StatisticsImpl::OUTPUT_ACT;
   st->enter(op->opIndex, kind, index, StatisticsImpl::WAIT);
   void* ret = nullptr;
   // the data we consume was sent by the PEER activation (reference src/mlsl_impl.cpp:366-386)
-  if (needComm && peer && peer->req && peer->req->desc.kind != OpKind::BARRIER) ret = peer->req->wait();
+  if (needComm && peer && peer->req && peer->req->desc.kind != OpKind::BARRIER) {
+    ret = peer->req->wait();
+    peer->req->desc.strided.on = false;             // the next plain StartComm of this request is a packed exchange again
+    if (peer->fusedDst) {
+      ret = peer->fusedDst;                         // the kernel wrote my unpacked tensor itself
+    } else if (peer->unpackDst && ret) {
+      pack(peer->unpackDst, ret, true);             // fallback of start_fused: unpack with MY block list
+      ret = peer->unpackDst;
+    }
+    peer->fusedDst = peer->unpackDst = nullptr;
+  }
   st->leave(op->opIndex, kind, index, StatisticsImpl::WAIT, needComm && peer ? peer->req : nullptr);
   return ret;
 }
@@ -560,6 +615,7 @@ void* Activation::GetCommBuf() { return SELF(ActivationImpl)->commBuf.ptr; }
 size_t Activation::GetCommBufSize() { return SELF(ActivationImpl)->commBuf.bytes; }
 void Activation::StartComm(void* buf) { SELF(ActivationImpl)->start(buf); }
 void* Activation::WaitComm() { return SELF(ActivationImpl)->wait(); }
+void Activation::StartCommFused(void* localBuf, void* localDst) { SELF(ActivationImpl)->start_fused(localBuf, localDst); }
 void Activation::Pack(const void* localBuf, void* commBuf) { SELF(ActivationImpl)->pack(localBuf, commBuf, false); }
 void Activation::Unpack(const void* commBuf, void* localBuf) { SELF(ActivationImpl)->pack(localBuf, const_cast<void*>(commBuf), true); }
 

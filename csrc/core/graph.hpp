@@ -71,6 +71,7 @@ class ActivationImpl : public Activation {
   void set_peer(ActivationImpl* other);
   void connect();                 // called on OUTPUT activations at Commit: choose the exchange pattern
   void start(void* buf);
+  void start_fused(void* local, void* dst);   // [ext] exchange straight from / into the unpacked tensors
   void* wait();
   void pack(const void* local, void* comm, bool unpack);
   std::string describe() const;
@@ -88,6 +89,8 @@ class ActivationImpl : public Activation {
   CommBuf commBuf;
   std::vector<BlockImpl*> packBlocks, unpackBlocks;
   int commCase = 0;
+  void* fusedDst = nullptr;        // start_fused(local, dst): the kernel wrote the consumer's tensor itself, WaitComm returns it
+  void* unpackDst = nullptr;       // start_fused fallback: WaitComm unpacks into it after the collective
   size_t msg_bytes() const;
 };
 

@@ -82,6 +82,17 @@ struct CommDesc {
   // fused all-gather + GEMM (OpKind::AG_GEMM): Y[M, N] = concat_rows(X_0..X_{P-1}) * W[N, K]^T; gemm.M/N/K, gemm.a = this
   // rank's shard X_r [M/P, K], gemm.w = W; `gathered` receives the full X [M, K] (kept for backward)
   void* gathered = nullptr;
+  // strided all-to-all (Activation::StartCommFused): every member pulls, from each peer's UNPACKED tensor,
+  // the rectangle that is meant for it - `rows` rows of `row_bytes`, `src_stride` apart, starting `src_off` into the peer's
+  // tensor (the geometry is the same on every member) - and writes it either packed into slot p of the receive region or,
+  // with `dst_direct`, straight into its own unpacked tensor at `dst_off[p]` with rows `dst_stride` apart.  No pack kernel,
+  // no unpack kernel, no trip of the payload through a packed send region.
+  struct Strided {
+    bool on = false, dst_direct = false;
+    size_t rows = 0, row_bytes = 0, src_off = 0, src_stride = 0, src_total = 0;
+    size_t dst_stride = 0, dst_total = 0;
+    std::vector<size_t> dst_off;
+  } strided;
 };
 
 class CommRequest {
@@ -139,6 +150,7 @@ class Backend {
  public:
   virtual ~Backend() {}
   virtual const char* name() const = 0;
+  virtual bool supports_strided_alltoall() const { return false; }
   virtual bool peek_done(CommRequest&) { return true; }         // launched collective finished? (never consumes it)
   virtual int default_servers() const { return 0; }              // progress threads when MLSL_NUM_SERVERS is unset
   virtual bool stream_ordered_wait() const { return false; }   // Wait only orders a stream (the host never blocks)

@@ -192,6 +192,7 @@ class CudaBackend final : public Backend {
   void harvest_device_time(CommRequest& r) override {
     if (auto* st = (CudaReqState*)r.backend_state) harvest(r, st, false);
   }
+  bool supports_strided_alltoall() const override { return true; }
   bool stream_ordered_wait() const override { return stream_wait_; }
   bool peek_done(CommRequest& r) override {
     auto* st = (CudaReqState*)r.backend_state;
@@ -1009,6 +1010,10 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
   if (d.kind == OpKind::SCATTER && me != (int)d.root) sbytes = 0;
   if (d.kind == OpKind::FUSED_UPDATE) rbytes = n * P * dtype_size(d.has_out_dtype ? d.out_dtype : d.dtype);
   if (d.kind == OpKind::AG_GEMM) rbytes = 0;   // Y and the gathered X are local: any device memory; the shard is staged if foreign
+  if (d.kind == OpKind::ALLTOALL && d.strided.on) {   // whole unpacked tensors are the buffers
+    sbytes = d.strided.src_total;
+    if (d.strided.dst_direct) rbytes = d.strided.dst_total;
+  }
   if (d.kind == OpKind::GEMM_RS) {
     sbytes = 0;   // A and W are only read by this rank's own TMA loads: any device memory will do
     rbytes = (size_t)d.gemm.M / P * d.gemm.N * (d.has_out_dtype && d.out_dtype == DType::F32 ? 4 : 2);
@@ -1151,6 +1156,18 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
           if (me != (int)d.root) add((int)d.root, 0, 0, n * es, 0);
           break;
         case OpKind::ALLTOALL:
+          if (d.strided.on) {
+            const CommDesc::Strided& sd = d.strided;
+            for (int p = 0; p < P; ++p) {
+              add(p, sd.src_off, sd.dst_direct ? sd.dst_off[(size_t)p] : (unsigned long long)p * n * es, sd.rows * sd.row_bytes, 0);
+              CopySeg& sg = plan.seg[plan.nseg - 1];
+              sg.rows = sd.rows;
+              sg.row_bytes = sd.row_bytes;
+              sg.src_stride = sd.src_stride;
+              sg.dst_stride = sd.dst_direct ? sd.dst_stride : sd.row_bytes;
+            }
+            break;
+          }
           for (int p = 0; p < P; ++p) add(p, (unsigned long long)me * n * es, (unsigned long long)p * n * es, n * es, 0);
           break;
         case OpKind::ALLTOALLV:
@@ -1186,7 +1203,8 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
       unsigned long long pulled = 0;
       for (int i = 0; i < plan.nseg; ++i) pulled += plan.seg[i].bytes;
       const long bk = ctx_->env.tune.bulk_copy_kb;
-      const bool bulk = bk > 0 && pulled >= ((unsigned long long)bk << 10) && !plan.pairs_concurrent;   // the ring deals pieces itself
+      const bool bulk = bk > 0 && pulled >= ((unsigned long long)bk << 10) && !plan.pairs_concurrent &&   // the ring deals pieces itself
+                        !(d.kind == OpKind::ALLTOALL && d.strided.on);                                  // rectangles: the threads copy
       MLSLB_CUDA(launch_pull_copy(dc, plan, pub_send, ro, ch, bulk, s));
       break;
     }

@@ -779,6 +779,38 @@ __global__ void __launch_bounds__(kCommThreads) k_pull_copy(DevComm dc, CopyPlan
     const bool aligned = ((((unsigned long long)src) | ((unsigned long long)dst)) & 15ull) == 0;
     size_t done = 0;
     const size_t gtid = stid, gsz = ssz;       // this segment's sub-grid (shadows the whole-grid indices)
+    if (sg.rows > 1) {
+      // strided rectangle (activation blocks pulled straight out of / into unpacked tensors)
+      const bool al2 = aligned && ((sg.row_bytes | sg.src_stride | sg.dst_stride) & 15ull) == 0;
+      if (al2) {
+        const size_t rv = sg.row_bytes / 16, nvec = sg.rows * rv;
+        for (size_t b0 = gtid; b0 < nvec; b0 += gsz * U) {
+          uint4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const size_t i = b0 + (size_t)u * gsz;
+            if (i < nvec) {
+              const size_t row = i / rv, c = i - row * rv;
+              v[u] = ld16(src + row * sg.src_stride + c * 16);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const size_t i = b0 + (size_t)u * gsz;
+            if (i < nvec) {
+              const size_t row = i / rv, c = i - row * rv;
+              st16(dst + row * sg.dst_stride + c * 16, v[u]);
+            }
+          }
+        }
+      } else {
+        for (size_t i = gtid; i < sg.bytes; i += gsz) {
+          const size_t row = i / sg.row_bytes, c = i - row * sg.row_bytes;
+          dst[row * sg.dst_stride + c] = src[row * sg.src_stride + c];
+        }
+      }
+      continue;
+    }
     if (aligned) {
       const size_t nvec = sg.bytes / 16;
       for (size_t b0 = gtid; b0 < nvec; b0 += gsz * U) {

@@ -16,6 +16,8 @@ struct CopySeg {
   int peer;
   int use_aux;
   unsigned long long src_off, dst_off, bytes;
+  // 2-D form (rows > 1): `rows` rows of `row_bytes` (bytes = rows * row_bytes), `src_stride` / `dst_stride` apart
+  unsigned long long rows, row_bytes, src_stride, dst_stride;
 };
 struct CopyPlan {
   int nseg;

@@ -88,6 +88,7 @@ int mlsl_activation_get_fm_size(mlsl_activation act, size_t* fm_size);
 int mlsl_activation_get_comm_buf(mlsl_activation act, void** comm_buf);
 int mlsl_activation_get_comm_buf_size(mlsl_activation act, size_t* size);
 int mlsl_activation_start_comm(mlsl_activation act, void* buffer);
+int mlsl_activation_start_comm_fused(mlsl_activation act, void* local_buf, void* local_dst);   /* [ext] */
 int mlsl_activation_wait_comm(mlsl_activation act, void** ret_buffer);
 
 /* ---- ParameterSet ------------------------------------------------------------------------------------- */

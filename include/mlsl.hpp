@@ -125,6 +125,10 @@ class Activation {
   size_t GetCommBufSize();
   void StartComm(void* buf);
   void* WaitComm();   // waits for the PEER activation's transfer; NULL when no communication is needed
+  // [ext] pack + exchange + unpack in one call: `localBuf` is the UNPACKED local tensor; with `localDst` the consumer's
+  // unpacked tensor is filled directly and the peer's WaitComm returns it.  For the all-to-all patterns on the CUDA backend
+  // this is one kernel that pulls the rectangles straight out of the peers' tensors (no pack / unpack kernels).
+  void StartCommFused(void* localBuf, void* localDst = nullptr);
   // [ext] device-side pack/unpack of a local (mb, fm, fmSize) tensor to/from the comm buffer (one kernel)
   void Pack(const void* localBuf, void* commBuf);
   void Unpack(const void* commBuf, void* localBuf);

@@ -191,6 +191,7 @@ def _declare(l):
         "mlsl_activation_get_comm_buf": [H, P(c_void_p)],
         "mlsl_activation_get_comm_buf_size": [H, P(c_size_t)],
         "mlsl_activation_start_comm": [H, c_void_p],
+        "mlsl_activation_start_comm_fused": [H, c_void_p, c_void_p],
         "mlsl_activation_wait_comm": [H, P(c_void_p)],
         "mlsl_activation_pack": [H, c_void_p, c_void_p],
         "mlsl_activation_unpack": [H, c_void_p, c_void_p],

@@ -121,6 +121,13 @@ class Activation(_Handle):
         _pre()
         self._call("mlsl_activation_start_comm", buffer_address(buf))
 
+    def start_comm_fused(self, local_buf, local_dst=None):
+        """Pack + exchange + unpack in one call from the UNPACKED local tensor; with `local_dst` the consumer's unpacked tensor
+        is filled directly (the peer's wait_comm returns its address).  All-to-all patterns on the CUDA backend: one kernel."""
+        _pre()
+        self._call("mlsl_activation_start_comm_fused", buffer_address(local_buf),
+                   buffer_address(local_dst) if local_dst is not None else None)
+
     def wait_comm(self):
         _pre()
         return self._get("mlsl_activation_wait_comm", c_void_p)

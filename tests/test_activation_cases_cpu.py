@@ -35,7 +35,13 @@ def test_activation_exchange_case(case, ptype, pdist, cdist):
     run_case(case, ptype, pdist, cdist, "host")
 
 
-def run_case(case, ptype, pdist, cdist, backend):
+@pytest.mark.parametrize("case,ptype,pdist,cdist", CASES, ids=["case%d" % c[0] for c in CASES])
+def test_activation_exchange_case_fused(case, ptype, pdist, cdist):
+    """Activation.start_comm_fused: the unpacked tensors go in and come out, no user-side pack / unpack loops."""
+    run_case(case, ptype, pdist, cdist, "host", fused=True)
+
+
+def run_case(case, ptype, pdist, cdist, backend, fused=False):
     dev = "cuda" if backend == "cuda" else "cpu"
 
     def body(r, mlsl):
@@ -70,18 +76,39 @@ def run_case(case, ptype, pdist, cdist, backend):
         p_fm, p_fo = oa.get_local_fm_count(), oa.get_global_fm_offset()
         c_fm, c_fo = ia.get_local_fm_count(), ia.get_global_fm_offset()
         # ---- forward: producer's output -> consumer's input
-        out = _f(p_off, p_mb, p_fo, p_fm).to(dev)
-        comm = view(oa.get_comm_buf(), oa.get_comm_buf_size())
-        Net.move_blocks(oa, comm, out, False)
-        oa.start_comm(comm)
-        got = ia.wait_comm()
-        inp = torch.zeros(c_mb * c_fm * FS, device=dev)
-        # the pointer WaitComm returns lies in the PRODUCER's request buffer; the unpack blocks say how much of it is ours
-        Net.move_blocks(ia, view(got, max(ia.get_comm_buf_size(), c_mb * c_fm * FS * 4)), inp, True)
+        if fused:
+            out = mlsl.alloc_tensor(p_mb * p_fm * FS, torch.float32)
+            out.copy_(_f(p_off, p_mb, p_fo, p_fm))
+            inp = mlsl.alloc_tensor(c_mb * c_fm * FS, torch.float32)
+            oa.start_comm_fused(out, inp)
+            got = ia.wait_comm()
+            assert got == inp.data_ptr()
+        else:
+            out = _f(p_off, p_mb, p_fo, p_fm).to(dev)
+            comm = view(oa.get_comm_buf(), oa.get_comm_buf_size())
+            Net.move_blocks(oa, comm, out, False)
+            oa.start_comm(comm)
+            got = ia.wait_comm()
+            inp = torch.zeros(c_mb * c_fm * FS, device=dev)
+            # the pointer WaitComm returns lies in the PRODUCER's request buffer; the unpack blocks say how much of it is ours
+            Net.move_blocks(ia, view(got, max(ia.get_comm_buf_size(), c_mb * c_fm * FS * 4)), inp, True)
         partial = dp.get_process_count(1) if ptype == "CC" else 1          # an OT_CC output is a partial sum per model rank
         fwd_ok = torch.equal(inp.cpu(), partial * _f(c_off, c_mb, c_fo, c_fm))
         # ---- backward: consumer's input gradient -> producer's output gradient
         bwd_ok = True
+        if fused and case != 2:
+            din = mlsl.alloc_tensor(c_mb * c_fm * FS, torch.float32)
+            din.copy_(_f(c_off, c_mb, c_fo, c_fm))
+            dout = mlsl.alloc_tensor(p_mb * p_fm * FS, torch.float32)
+            ia.start_comm_fused(din, dout)
+            back = oa.wait_comm()
+            bwd_ok = back == dout.data_ptr() and torch.equal(dout.cpu(), _f(p_off, p_mb, p_fo, p_fm))
+            res = (fwd_ok, bwd_ok, oa.get_pack_block_count(), ia.get_unpack_block_count())
+            e.delete_session(sess)
+            if dc is not dp:
+                e.delete_distribution(dc)
+            e.delete_distribution(dp)
+            return res
         din = _f(c_off, c_mb, c_fo, c_fm).to(dev)
         addr = ia.get_comm_buf()
         commi = view(addr, ia.get_comm_buf_size()) if addr else din
