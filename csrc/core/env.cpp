@@ -50,6 +50,7 @@ static const TuneDesc kTune[] = {
     {"nvtx", "MLSL_NVTX", &Tunables::nvtx, "NVTX ranges"},
     {"trace_launch", "MLSL_TRACE_LAUNCH", &Tunables::trace_launch, "stderr line per launch"},
     {"force_kernel_solo", "MLSL_FORCE_KERNEL_SOLO", &Tunables::force_kernel_solo, "1-rank groups run the peer kernels"},
+    {"quant_mx", "MLSL_QUANT_MX", &Tunables::quant_mx, "fp8 transport: ue8m0 scale per 32 elements (MX) instead of fp32 per 128"},
     {"dev_timestamps", "MLSL_DEV_TIMESTAMPS", &Tunables::dev_timestamps, "device timestamps in statistics / trace"},
     {"loopback_rendezvous_ms", "MLSL_LOOPBACK_RENDEZVOUS_MS", &Tunables::loopback_rendezvous_ms,
      "ranks sharing a GPU wait this long on the host for their peers before launching"},

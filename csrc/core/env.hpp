@@ -41,6 +41,8 @@ struct Tunables {
   long nvtx = 1;                // MLSL_NVTX: NVTX range per collective launch
   long trace_launch = 0;        // MLSL_TRACE_LAUNCH: one stderr line per kernel launch
   long force_kernel_solo = 0;   // MLSL_FORCE_KERNEL_SOLO: single-rank groups run the peer kernels against themselves
+  long quant_mx = 0;            // MLSL_QUANT_MX: fp8 transport with one ue8m0 (power-of-two) scale per 32 elements (MX) instead of
+                                // one fp32 scale per 128 - same wire size; host and device backends implement the same format
   long dev_timestamps = 1;      // MLSL_DEV_TIMESTAMPS: statistics / trace use device event timestamps
   long loopback_rendezvous_ms = 20;   // MLSL_LOOPBACK_RENDEZVOUS_MS: ranks sharing a GPU wait this long on the HOST for their
                                       // peers before launching a collective (0 = launch at once and spin on the device)

@@ -684,14 +684,19 @@ void HostBackend::exec_quantized_allreduce(CommRequest& r, const ProcessGroup& g
   float* s2 = (float*)(stage + 2 * qbytes + sbytes);
   const float* x = (const float*)S;
   float* y = (float*)R;
+  const bool mx = ctx_->env.tune.quant_mx != 0;          // four ue8m0 exponent bytes in place of the block's fp32 scale
+  auto block_scale = [&](const float* sc, size_t b, size_t i) {   // scale of element i of block b
+    return mx ? mx_scale_of(((const uint8_t*)(sc + b))[(i % kQuantBlock) / kMxBlock]) : sc[b];
+  };
   // step 1: x + residual -> fp8 blocks, residual update
   for (size_t b = 0; b < nblk; ++b) {
     size_t lo = b * kQuantBlock, hi = std::min(n, lo + kQuantBlock);
     float v[kQuantBlock];
     for (size_t i = lo; i < hi; ++i) v[i - lo] = x[i] + st->residual[i];
     for (size_t i = hi - lo; i < (size_t)kQuantBlock; ++i) v[i] = 0.f;
-    s1[b] = quant_block(v, q1 + lo);
-    for (size_t i = lo; i < hi; ++i) st->residual[i] = v[i - lo] - e4m3_to_f32(q1[i]) * s1[b];
+    if (mx) quant_block_mx(v, q1 + lo, (uint8_t*)(s1 + b));
+    else s1[b] = quant_block(v, q1 + lo);
+    for (size_t i = lo; i < hi; ++i) st->residual[i] = v[i - lo] - e4m3_to_f32(q1[i]) * block_scale(s1, b, i - lo);
   }
   mine->send_off = to_off(stage);
   auto sync = [&](int step) {
@@ -707,10 +712,11 @@ void HostBackend::exec_quantized_allreduce(CommRequest& r, const ProcessGroup& g
     for (int p = 0; p < P; ++p) {
       const char* ps = peer_ptr(g.members[p], pub(g.members[p], prow)->send_off);
       const uint8_t* pq = (const uint8_t*)ps + b * kQuantBlock;
-      float sc = ((const float*)(ps + qbytes))[b];
-      for (int i = 0; i < kQuantBlock; ++i) acc[i] += e4m3_to_f32(pq[i]) * sc;
+      const float* psc1 = (const float*)(ps + qbytes);
+      for (int i = 0; i < kQuantBlock; ++i) acc[i] += e4m3_to_f32(pq[i]) * block_scale(psc1, b, (size_t)i);
     }
-    s2[b] = quant_block(acc, q2 + b * kQuantBlock);
+    if (mx) quant_block_mx(acc, q2 + b * kQuantBlock, (uint8_t*)(s2 + b));
+    else s2[b] = quant_block(acc, q2 + b * kQuantBlock);
   }
   sync(2);
   // step 3: gather every slice, dequantise with the fused output scale
@@ -721,7 +727,7 @@ void HostBackend::exec_quantized_allreduce(CommRequest& r, const ProcessGroup& g
     size_t plo = std::min(nblk, (size_t)p * blk_per), phi = std::min(nblk, plo + blk_per);
     for (size_t b = plo; b < phi; ++b) {
       size_t lo = b * kQuantBlock, hi = std::min(n, lo + kQuantBlock);
-      for (size_t i = lo; i < hi; ++i) y[i] = e4m3_to_f32(pq[i]) * psc[b] * d.scale;
+      for (size_t i = lo; i < hi; ++i) y[i] = e4m3_to_f32(pq[i]) * block_scale(psc, b, i - lo) * d.scale;
     }
   }
   sync(3);

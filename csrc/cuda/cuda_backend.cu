@@ -1080,7 +1080,7 @@ void CudaBackend::launch_single(CommRequest& r, CudaReqState* st, cudaStream_t s
           st->residual_elems = n;
         }
         MLSLB_CUDA(launch_allreduce_quant(dc, so, ro, (unsigned long long)((char*)st->qstage - slab_), st->residual, n,
-                                          d.scale, quant_channels(n), s));
+                                          d.scale, quant_channels(n), ctx_->env.tune.quant_mx != 0, s));
       } else {
         // very large messages go out as pipelined chunks (reference MLSL_LARGE_MSG_SIZE_MB / _CHUNKS,
         // src/comm_ep.cpp:645-656) so a higher-priority collective can slip in between them

@@ -60,9 +60,23 @@ __device__ __forceinline__ float quant_warp_block(const float4& v, unsigned& pac
   return scale;
 }
 
+// MX flavour: biased exponent byte of the power-of-two scale of a sub-block with magnitude `amax` (same integer arithmetic as
+// mx_exp_of() in core/quant.hpp), and the scale / inverse scale it stands for
+__device__ __forceinline__ unsigned mx_exp_dev(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 0u;
+  const unsigned u = __float_as_uint(__fdiv_rn(amax, 448.0f));
+  const unsigned E = (u >> 23) & 0xffu, M = u & 0x7fffffu;
+  if (E == 0u) return 0u;
+  const unsigned eb = E + (M ? 1u : 0u);
+  return eb > 254u ? 254u : eb;
+}
+__device__ __forceinline__ float mx_scale_dev(unsigned eb) { return eb ? __uint_as_float(eb << 23) : 0.f; }
+__device__ __forceinline__ float mx_inv_dev(unsigned eb) { return eb ? __uint_as_float((254u - eb) << 23) : 0.f; }
+
 // The local phases (quantise / dequantise) are HBM bound, so unlike the pure NVLink kernels this one wants the whole
 // GPU: 1024-thread CTAs, up to one per SM.
 constexpr int kQuantThreads = 1024;
+template <bool kMx>
 __global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, unsigned long long send_off,
                                                                   unsigned long long recv_off,
                                                                   unsigned long long stage_off, float* residual,
@@ -106,9 +120,22 @@ __global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, u
     }
     v.x = __fadd_rn(v.x, r.x); v.y = __fadd_rn(v.y, r.y); v.z = __fadd_rn(v.z, r.z); v.w = __fadd_rn(v.w, r.w);
     unsigned packed;
-    const float sc = quant_warp_block(v, packed);
+    float sc;
+    if constexpr (kMx) {
+      // 32-element sub-block = 8 lanes: its own power-of-two scale, one exponent byte each
+      float am = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+      const unsigned eb = mx_exp_dev(am);
+      sc = mx_scale_dev(eb);
+      const float inv = mx_inv_dev(eb);
+      packed = eb ? pack_e4m3x4(__fmul_rn(v.x, inv), __fmul_rn(v.y, inv), __fmul_rn(v.z, inv), __fmul_rn(v.w, inv)) : 0u;
+      if ((lane & 7) == 0) *reinterpret_cast<unsigned char*>(mystage + qbytes + b * sizeof(float) + (lane >> 3)) = (unsigned char)eb;
+    } else {
+      sc = quant_warp_block(v, packed);
+      if (lane == 0) *reinterpret_cast<float*>(mystage + qbytes + b * sizeof(float)) = sc;
+    }
     *reinterpret_cast<unsigned*>(mystage + b * kQuantBlock + lane * 4) = packed;
-    if (lane == 0) *reinterpret_cast<float*>(mystage + qbytes + b * sizeof(float)) = sc;
     const float4 dq = unpack_e4m3x4(packed);
     r.x = __fsub_rn(v.x, __fmul_rn(dq.x, sc)); r.y = __fsub_rn(v.y, __fmul_rn(dq.y, sc));
     r.z = __fsub_rn(v.z, __fmul_rn(dq.z, sc)); r.w = __fsub_rn(v.w, __fmul_rn(dq.w, sc));
@@ -138,7 +165,13 @@ __global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, u
     for (int p = 0; p < P; ++p) {
       const char* ps = pt.send[p];
       const uint4 w = ld16(ps + b * kQuantBlock + l8 * 16);
-      const float sc = __ldcg(reinterpret_cast<const float*>(ps + qbytes + b * sizeof(float)));
+      float sc;
+      if constexpr (kMx) {
+        const unsigned ew = __ldcg(reinterpret_cast<const unsigned*>(ps + qbytes + b * sizeof(float)));
+        sc = mx_scale_dev((ew >> (8 * (l8 >> 1))) & 0xffu);          // my 16 elements sit in sub-block l8 / 2
+      } else {
+        sc = __ldcg(reinterpret_cast<const float*>(ps + qbytes + b * sizeof(float)));
+      }
       const unsigned ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -153,11 +186,28 @@ __global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, u
     float amax = 0.f;
 #pragma unroll
     for (int k = 0; k < 16; ++k) amax = fmaxf(amax, fabsf(acc[k]));
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     uint4 q = make_uint4(0u, 0u, 0u, 0u);
     float sc2 = 0.f;
-    if (amax > 0.f && isfinite(amax)) {
+    if constexpr (kMx) {
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));     // the lane pair that shares a 32-element sub-block
+      const unsigned eb = mx_exp_dev(amax);
+      const float inv = mx_inv_dev(eb);
+      if (eb) {
+        q.x = pack_e4m3x4(__fmul_rn(acc[0], inv), __fmul_rn(acc[1], inv), __fmul_rn(acc[2], inv), __fmul_rn(acc[3], inv));
+        q.y = pack_e4m3x4(__fmul_rn(acc[4], inv), __fmul_rn(acc[5], inv), __fmul_rn(acc[6], inv), __fmul_rn(acc[7], inv));
+        q.z = pack_e4m3x4(__fmul_rn(acc[8], inv), __fmul_rn(acc[9], inv), __fmul_rn(acc[10], inv), __fmul_rn(acc[11], inv));
+        q.w = pack_e4m3x4(__fmul_rn(acc[12], inv), __fmul_rn(acc[13], inv), __fmul_rn(acc[14], inv), __fmul_rn(acc[15], inv));
+      }
+      // the block's four exponent bytes, assembled on every lane of the 8-lane group (lanes 0, 2, 4, 6 hold them)
+      const int g0 = lane & ~7;
+      const unsigned ew = __shfl_sync(0xffffffffu, eb, g0) | (__shfl_sync(0xffffffffu, eb, g0 + 2) << 8) |
+                          (__shfl_sync(0xffffffffu, eb, g0 + 4) << 16) | (__shfl_sync(0xffffffffu, eb, g0 + 6) << 24);
+      sc2 = __uint_as_float(ew);                                    // travels in the fp32 scale slot of the block
+    } else {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    }
+    if (!kMx && amax > 0.f && isfinite(amax)) {
       sc2 = __fdiv_rn(amax, 448.0f);
       const float inv = __fdiv_rn(448.0f, amax);
       q.x = pack_e4m3x4(__fmul_rn(acc[0], inv), __fmul_rn(acc[1], inv), __fmul_rn(acc[2], inv), __fmul_rn(acc[3], inv));
@@ -193,7 +243,13 @@ __global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, u
   for (size_t sb = c + (size_t)warp * C; sb < nsb; sb += C * nwarp) {
     const size_t b = sb * 4 + sub;
     const uint4 w = *reinterpret_cast<const uint4*>(mystage + q2_off + b * kQuantBlock + l8 * 16);
-    const float sc = *reinterpret_cast<const float*>(mystage + s2_off + b * sizeof(float));
+    float sc;
+    if constexpr (kMx) {
+      const unsigned ew = *reinterpret_cast<const unsigned*>(mystage + s2_off + b * sizeof(float));
+      sc = mx_scale_dev((ew >> (8 * (l8 >> 1))) & 0xffu);
+    } else {
+      sc = *reinterpret_cast<const float*>(mystage + s2_off + b * sizeof(float));
+    }
     const unsigned ww[4] = {w.x, w.y, w.z, w.w};
     const size_t e0 = b * kQuantBlock + (size_t)l8 * 16;
 #pragma unroll
@@ -216,8 +272,9 @@ __global__ void __launch_bounds__(kQuantThreads) k_allreduce_quant(DevComm dc, u
 
 cudaError_t launch_allreduce_quant(const DevComm& dc, unsigned long long send_off, unsigned long long recv_off,
                                    unsigned long long stage_off, float* residual, size_t count, float scale,
-                                   int channels, cudaStream_t s) {
-  k_allreduce_quant<<<channels, kQuantThreads, 0, s>>>(dc, send_off, recv_off, stage_off, residual, count, scale);
+                                   int channels, bool mx, cudaStream_t s) {
+  if (mx) k_allreduce_quant<true><<<channels, kQuantThreads, 0, s>>>(dc, send_off, recv_off, stage_off, residual, count, scale);
+  else k_allreduce_quant<false><<<channels, kQuantThreads, 0, s>>>(dc, send_off, recv_off, stage_off, residual, count, scale);
   return cudaGetLastError();
 }
 

@@ -77,7 +77,7 @@ cudaError_t launch_pack_blocks(const PackPlan& plan, size_t local_fm_count, int 
 // K11 fused fp8 block-quantised all-reduce with error feedback (fp32 in/out)
 cudaError_t launch_allreduce_quant(const DevComm& dc, unsigned long long send_off, unsigned long long recv_off,
                                    unsigned long long stage_off, float* residual, size_t count, float scale,
-                                   int channels, cudaStream_t s);
+                                   int channels, bool mx, cudaStream_t s);
 size_t allreduce_quant_stage_bytes(size_t count);
 // fused distributed update: reduce-scatter + optimizer + all-gather in one kernel
 struct FusedUpdateArgs {

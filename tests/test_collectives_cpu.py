@@ -402,3 +402,35 @@ def test_compressed_allreduce_keeps_error_feedback_across_calls():
     err_mean = (outs.mean(0) - exact).abs().mean().item()
     assert err_first > 0
     assert err_mean < 0.35 * err_first, (err_first, err_mean)
+
+
+@pytest.mark.parametrize("mx", ["0", "1"])
+def test_compressed_allreduce_formats(mx):
+    """Both fp8 wire formats of the compressed all-reduce - one fp32 scale per 128 elements, or the MX layout (one ue8m0
+    power-of-two scale per 32 elements, MLSL_QUANT_MX=1) - stay within e4m3 precision of the exact sum, identically on every rank,
+    also when magnitudes differ by orders between neighbouring 32-element groups (where the finer MX scales help)."""
+    import torch
+    world, n = 4, 5000
+
+    def body(r, mlsl):
+        g = torch.Generator().manual_seed(11 + r)
+        x = torch.randn(n, generator=g)
+        x[::64] *= 1000.0                      # a few large entries per 128-block
+        y = torch.zeros(n)
+        mlsl.allreduce(x, out=y, compress=True)
+        return x, y
+
+    res = run_ranks(world, body, env={"MLSL_QUANT_MX": mx})
+    exact = sum(r[0] for r in res)
+    for _, y in res:
+        assert torch.equal(y, res[0][1])
+    err = (res[0][1] - exact).abs()
+    assert err.max() <= 0.07 * exact.abs().max()               # e4m3: 3 mantissa bits, two quantisation steps
+    small = torch.ones(n, dtype=torch.bool)
+    small[::64] = False                                          # the entries that share a scale with a 1000x larger neighbour
+    if mx == "1":                                                # MX: only the 32-group of the outlier is coarse
+        far = small.clone()
+        for k in range(0, n, 64):
+            far[k:k + 32] = False
+        assert err[far].max() < 0.5, err[far].max()              # ~N(0, 2) sums quantised at their own scale
+

@@ -266,8 +266,10 @@ def test_bcast_reduce_gather_scatter_alltoall():
     assert torch.equal(outs[3][2], torch.cat([_make(r, n, torch.float32) for r in range(world)]))
 
 
-def test_quantized_allreduce_fp8_matches_host_definition():
-    """The fused fp8 kernel must agree with the CPU definition of the format (csrc/core/quant.hpp) to rounding."""
+@pytest.mark.parametrize("mx", ["0", "1"])
+def test_quantized_allreduce_fp8_matches_host_definition(mx):
+    """The fused fp8 kernel must agree with the CPU definition of the format (csrc/core/quant.hpp) to rounding - with one fp32
+    scale per 128 elements and with the MX layout (MLSL_QUANT_MX=1: one ue8m0 power-of-two scale per 32 elements)."""
     world, n = 4, 70001
 
     def body(r, mlsl):
@@ -284,8 +286,8 @@ def test_quantized_allreduce_fp8_matches_host_definition():
         mlsl.allreduce(x, out=y, compress=True, scale=0.25)
         return y
 
-    dev = _gpu(body, world)
-    host = run_ranks(world, host_body, backend="host")
+    dev = _gpu(body, world, env={"MLSL_QUANT_MX": mx})
+    host = run_ranks(world, host_body, backend="host", env={"MLSL_QUANT_MX": mx})
     ref = (_ref_reduce([_make(r, n, torch.float32) * 3 for r in range(world)], "sum") * 0.25).float()
     for r in range(world):
         assert torch.equal(dev[r], dev[0])
@@ -490,3 +492,59 @@ def test_heap_tensor_explicit_free_then_recycled_address():
     for r, outs in enumerate(_gpu(body, 2)):
         for distinct, ysum, xval in outs:
             assert distinct and ysum == 3.0 and xval == float(r + 1)
+
+
+@pytest.mark.parametrize("wait_mode", ["host", "stream"])
+def test_statistics_carry_device_timed_durations(wait_mode, tmp_path):
+    """MLSL_STATS=1 on the device: an event pair around every kernel gives the duration of the collective ON THE DEVICE
+    (Statistics.get_device_comm_nanos); with stream-ordered waits that duration is what the comm counters carry.  The Chrome
+    trace (MLSL_TRACE_FILE) records it per request as `device_us`."""
+    import json
+    import os
+    world, n = 2, 1 << 20
+    trace = str(tmp_path / "trace")
+
+    def body(r, mlsl):
+        from mlsl_b200.api import DataType, OperationType
+        e = mlsl.env()
+        sess = e.create_session()
+        sess.set_global_minibatch_size(world)
+        dist = e.create_distribution(world, 1)
+        ri = sess.create_operation_reg_info(OperationType.CC)
+        ri.add_input(8, 1, DataType.FLOAT)
+        ri.add_output(8, 1, DataType.FLOAT)
+        ri.add_parameter_set(n, 1, DataType.FLOAT, False)
+        op = sess.get_operation(sess.add_operation(ri, dist))
+        sess.commit()
+        st = sess.get_stats()
+        iso = st.get_total_isolation_comm_cycles()
+        st.start()
+        ps = op.get_parameter_set(0)
+        g = mlsl.alloc_tensor(n, torch.float32)
+        g.fill_(1.0)
+        for _ in range(4):
+            ps.start_gradient_comm(g)
+            ps.wait_gradient_comm()
+            torch.cuda.current_stream().synchronize()
+        ps.start_gradient_comm(g)                 # the fifth run harvests the fourth in stream mode
+        ps.wait_gradient_comm()
+        torch.cuda.current_stream().synchronize()
+        st.stop()
+        res = (iso, st.get_device_comm_nanos(0), st.get_comm_nanos(0), float(g[0]))
+        st.print()
+        e.delete_session(sess)
+        e.delete_distribution(dist)
+        return res
+
+    outs = _gpu(body, world, wait_mode=wait_mode, env={"MLSL_STATS": "1", "MLSL_STATS_ITERS": "3", "MLSL_STATS_SKIP": "1",
+                                                       "MLSL_TRACE_FILE": trace})
+    for iso, dev_ns, comm_ns, v in outs:
+        assert v == 2.0 ** 5
+        assert iso > 0
+        assert dev_ns > 3 * 2000, dev_ns            # >= 3 harvested runs of a 4 MiB all-reduce, microseconds each
+        assert comm_ns >= (dev_ns if wait_mode == "stream" else 1)
+    tr = json.load(open(trace + ".0.json"))
+    evs = [ev for ev in tr["traceEvents"] if ev.get("ph") == "X" and ev["name"] == "AllReduce"]
+    assert evs and any(ev["args"].get("device_us", 0) > 0 for ev in evs)
+    if os.path.exists("mlsl_stats.log"):
+        os.remove("mlsl_stats.log")
