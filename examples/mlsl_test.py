@@ -226,6 +226,9 @@ def main():
         return 2
     cfg = (args + [0, 0, 0])[:4]
     if inproc <= 0:
+        if torch.cuda.is_available() and os.environ.get("MLSL_BACKEND") == "cuda":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))      # torchrun: one rank per GPU
+            torch.cuda.set_stream(torch.cuda.Stream())
         return Net(*cfg).run()
 
     def body(r):
