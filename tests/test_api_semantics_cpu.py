@@ -582,3 +582,24 @@ def test_out_of_order_starts_on_different_groups_need_servers():
     assert run_ranks(2, body, env={"MLSL_NUM_SERVERS": "2"}) == [(2.0, 4.0), (2.0, 4.0)]
     with pytest.raises(Exception, match="watchdog|poisoned"):
         run_ranks(2, body, env={"MLSL_NUM_SERVERS": "0", "MLSL_WATCHDOG_SEC": "3"})
+
+
+def test_tuning_knobs_roundtrip_and_unknown_key():
+    """Environment.set_tuning / get_tuning: by key or by environment-variable name; unknown keys are an error; the value read
+    from the environment at init is visible."""
+    def body(r, mlsl):
+        from mlsl_b200 import MLSLError
+        e = mlsl.env()
+        before = e.get_tuning("mid_max_kb")
+        e.set_tuning("mid_max_kb", 256)
+        by_env_name = e.get_tuning("MLSL_MID_MAX_KB")
+        e.set_tuning("MLSL_MID_MAX_KB", before)
+        try:
+            e.set_tuning("no_such_knob", 1)
+            unknown = False
+        except MLSLError as ex:
+            unknown = "unknown tuning key" in str(ex)
+        return before, by_env_name, e.get_tuning("mid_max_kb"), unknown, e.get_tuning("pipe_bufs")
+
+    for before, by_env, after, unknown, pipe in run_ranks(2, body, env={"MLSL_PIPE_BUFS": "6"}):
+        assert (before, by_env, after, unknown, pipe) == (1024, 256, 1024, True, 6)
