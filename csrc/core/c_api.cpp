@@ -141,6 +141,11 @@ int mlsl_distribution_all_reduce_ex(mlsl_distribution d, void* s, void* rv, size
                                     mlsl_group_type g, float scale, mlsl_compression_type c, mlsl_comm_req* r) {
   C_GUARD(*need(r) = U(H<Distribution>(d)->AllReduceEx(s, rv, n, DT(t), RT(op), GT(g), scale, (MLSL::CompressionType)(int)c)))
 }
+// [ext] AllReduceEx followed by Environment::Wait in one call (bindings: half the call overhead of the blocking form)
+int mlsl_distribution_all_reduce_ex_wait(mlsl_distribution d, mlsl_environment e, void* s, void* rv, size_t n, mlsl_data_type t,
+                                         mlsl_reduction_type op, mlsl_group_type g, float scale, mlsl_compression_type c) {
+  C_GUARD(H<Environment>(e)->Wait(H<Distribution>(d)->AllReduceEx(s, rv, n, DT(t), RT(op), GT(g), scale, (MLSL::CompressionType)(int)c)))
+}
 int mlsl_distribution_all_to_all(mlsl_distribution d, void* s, size_t n, void* rv, mlsl_data_type t, mlsl_group_type g, mlsl_comm_req* r) {
   C_GUARD(*need(r) = U(H<Distribution>(d)->AlltoAll(s, n, rv, DT(t), GT(g))))
 }

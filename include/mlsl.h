@@ -244,6 +244,9 @@ int mlsl_environment_create_distribution_from_ranks(mlsl_environment env, const 
 int mlsl_distribution_all_reduce_ex(mlsl_distribution dist, void* send_buffer, void* recv_buffer, size_t count,
                                     mlsl_data_type dtype, mlsl_reduction_type red_type, mlsl_group_type group_type,
                                     float scale, mlsl_compression_type compress, mlsl_comm_req* req);
+int mlsl_distribution_all_reduce_ex_wait(mlsl_distribution dist, mlsl_environment env, void* send_buffer, void* recv_buffer, size_t count,
+                                         mlsl_data_type data_type, mlsl_reduction_type red_type, mlsl_group_type group_type,
+                                         float scale, mlsl_compression_type compression);   /* [ext] start + wait */
 int mlsl_distribution_reduce_scatter_ex(mlsl_distribution dist, void* send_buffer, void* recv_buffer,
                                         size_t recv_count, mlsl_data_type dtype, mlsl_reduction_type red_type,
                                         mlsl_group_type group_type, float scale, mlsl_comm_req* req);

@@ -126,6 +126,7 @@ def _declare(l):
         "mlsl_distribution_reduce": [H, c_void_p, c_void_p, c_size_t, c_int, c_int, c_size_t, c_int, P(H)],
         "mlsl_distribution_all_reduce": [H, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, P(H)],
         "mlsl_distribution_all_reduce_ex": [H, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_float, c_int, P(H)],
+        "mlsl_distribution_all_reduce_ex_wait": [H, H, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_float, c_int],
         "mlsl_distribution_all_to_all": [H, c_void_p, c_size_t, c_void_p, c_int, c_int, P(H)],
         "mlsl_distribution_all_to_allv": [H, c_void_p, P(c_size_t), P(c_size_t), c_void_p, P(c_size_t), P(c_size_t), c_int, c_int, P(H)],
         "mlsl_distribution_send_recv_list": [H, c_void_p, P(c_size_t), P(c_size_t), c_void_p, P(c_size_t), P(c_size_t), c_int, c_int, P(H)],

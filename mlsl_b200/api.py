@@ -74,6 +74,9 @@ def _pre():
         _stream_hook()
 
 
+_FN = {}     # native entry points by name (resolved once)
+
+
 class _Handle:
     __slots__ = ("handle",)
 
@@ -202,7 +205,10 @@ class Distribution(_Handle):
     def _req(self, fname, *args):
         _pre()
         req = H()
-        check(getattr(_lib.lib(), fname)(self.handle, *args, ctypes.byref(req)))
+        fn = _FN.get(fname)
+        if fn is None:
+            fn = _FN[fname] = getattr(_lib.lib(), fname)      # ctypes attribute lookups are not free on a hot path
+        check(fn(self.handle, *args, ctypes.byref(req)))
         return req.value
 
     def bcast(self, buf, count, data_type, root_idx, group_type):
@@ -215,6 +221,16 @@ class Distribution(_Handle):
     def all_reduce(self, send_buf, recv_buf, count, data_type, red_type, group_type):
         return self._req("mlsl_distribution_all_reduce", buffer_address(send_buf), buffer_address(recv_buf), count,
                          data_type, red_type, group_type)
+
+    def all_reduce_blocking(self, env, send_buf, recv_buf, count, data_type, red_type, group_type, scale=1.0,
+                            compress=CompressionType.NONE):
+        """AllReduceEx + Environment::Wait in ONE native call (the tensor-level blocking path: half the binding overhead)."""
+        _pre()
+        fn = _FN.get("mlsl_distribution_all_reduce_ex_wait")
+        if fn is None:
+            fn = _FN["mlsl_distribution_all_reduce_ex_wait"] = _lib.lib().mlsl_distribution_all_reduce_ex_wait
+        check(fn(self.handle, env.handle, buffer_address(send_buf), buffer_address(recv_buf), count, data_type, red_type,
+                 group_type, scale, compress))
 
     def all_reduce_ex(self, send_buf, recv_buf, count, data_type, red_type, group_type, scale=1.0,
                       compress=CompressionType.NONE):

@@ -319,14 +319,25 @@ def _check_out(what, out, numel, dtype):
 def allreduce(tensor, op="sum", group="data", scale=1.0, compress=False, out=None, async_op=False, distribution=None):
     """All-reduce `tensor` (in place unless `out` is given).  `scale` and the optional fp8 `compress`ed transport are
     fused into the reduction kernel."""
-    _prep(tensor)
-    out = tensor if out is None else _check_out("allreduce", out, tensor.numel(), tensor.dtype)
-    _sync_stream()
+    st = _state()
+    e = st.get("env")
+    if e is None:
+        raise RuntimeError("mlsl_b200 is not initialised: call mlsl_b200.init() first")
+    if not tensor.is_contiguous() or (tensor.is_cuda and not st["device"]):
+        _prep(tensor)                                   # raises the descriptive error
+    n = tensor.numel()
+    if out is None:
+        out = tensor
+    elif out is not tensor:
+        _check_out("allreduce", out, n, tensor.dtype)
+    ct = CompressionType.QUANTIZATION if compress else CompressionType.NONE
+    d = distribution if distribution is not None else (st.get("world_dist") or world_distribution())
+    if not async_op:      # start + wait in one native call (the stream is bound to torch's current one inside)
+        d.all_reduce_blocking(e, tensor, out, n, mlsl_dtype(tensor.dtype), _op(op), _group(group), float(scale), ct)
+        return out
     req = _dist(distribution).all_reduce_ex(tensor, out, tensor.numel(), mlsl_dtype(tensor.dtype), _op(op),
-                                            _group(group), float(scale),
-                                            CompressionType.QUANTIZATION if compress else CompressionType.NONE)
-    w = Work(env(), req, out, (tensor, out))
-    return w if async_op else w.wait()
+                                            _group(group), float(scale), ct)
+    return Work(env(), req, out, (tensor, out))
 
 
 def reduce_scatter(tensor, out=None, op="sum", group="data", scale=1.0, async_op=False, distribution=None):
