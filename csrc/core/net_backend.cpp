@@ -27,6 +27,8 @@
 
 #include "log.hpp"
 #include "numeric.hpp"
+#include <functional>
+
 #include "quant.hpp"
 #include "runtime.hpp"
 #include "tcp_control.hpp"
@@ -39,6 +41,7 @@ struct Seg {
   int peer;      // global rank
   char* ptr;
   size_t bytes;
+  uint64_t tag = 0;   // 0: the tag of the exchange; chunked collectives give every chunk its own
 };
 
 constexpr size_t kOneShotBytes = 32 << 10;   // all-reduce up to this size: one exchange of whole vectors
@@ -120,70 +123,73 @@ class Mesh {
       }
   }
 
-  // Every entry of `sends` / `recvs` names a distinct peer.  Returns when all of them have completed.
-  void exchange(uint64_t tag, const std::vector<Seg>& sends, const std::vector<Seg>& recvs) {
+  // Returns when every send and receive has completed.  Plain collectives name every peer at most once per direction; the
+  // chunked ones post several messages per peer (own tag each): messages to one peer leave in list order, receives complete
+  // in the order the peer sent them.  `on_recv(i)` runs when recvs[i] is complete (inside the progress loop: the sockets keep
+  // flowing through the kernel's buffers while it computes) and may queue further sends with add_send().
+  using RecvFn = std::function<void(size_t)>;
+  void exchange(uint64_t tag, const std::vector<Seg>& sends, const std::vector<Seg>& recvs, const RecvFn* on_recv = nullptr) {
     std::lock_guard<std::mutex> g(mu_);
-    struct Out {
-      int peer;
-      WireHdr hdr;
-      size_t hdr_sent = 0, sent = 0;
-      const char* ptr;
-    };
-    std::vector<Out> outs;
-    for (const Seg& s : sends) {
-      Out o;
-      o.peer = s.peer;
-      o.hdr.tag = tag;
-      o.hdr.bytes = s.bytes;
-      o.ptr = s.ptr;
-      outs.push_back(o);
-    }
+    Xchg x;
+    x.tag = tag;
+    x.on_recv = on_recv;
+    struct Scope {
+      Mesh* m;
+      ~Scope() { m->cur_ = nullptr; }
+    } scope{this};
+    cur_ = &x;
+    for (const Seg& s : sends) x.outs.push_back(Out{s.peer, WireHdr{s.tag ? s.tag : tag, s.bytes}, 0, 0, s.ptr});
     // expected arrivals; something that came early is already parked
-    size_t pending_in = 0;
-    for (const Seg& r : recvs) {
+    std::vector<size_t> early;
+    std::vector<int> rpeers;
+    for (size_t i = 0; i < recvs.size(); ++i) {
+      const Seg& r = recvs[i];
+      const uint64_t t = r.tag ? r.tag : tag;
       Peer& P = peers_[r.peer];
-      auto it = P.parked.find(tag);
+      if (std::find(rpeers.begin(), rpeers.end(), r.peer) == rpeers.end()) rpeers.push_back(r.peer);
+      auto it = P.parked.find(t);
       if (it != P.parked.end()) {
         MLSLB_ASSERT(it->second.size() == r.bytes, "message of %zu bytes from rank %d where %zu were expected", it->second.size(),
                      r.peer, r.bytes);
         if (r.bytes) memcpy(r.ptr, it->second.data(), r.bytes);
         P.parked.erase(it);
+        early.push_back(i);
       } else {
-        MLSLB_ASSERT(P.expect.find(tag) == P.expect.end(), "two receives from rank %d in one exchange", r.peer);
-        P.expect[tag] = Expect{r.ptr, r.bytes, false};
-        ++pending_in;
+        MLSLB_ASSERT(P.expect.find(t) == P.expect.end(), "two receives from rank %d under one tag", r.peer);
+        P.expect[t] = Expect{r.ptr, r.bytes, i};
+        ++x.pending_in;
       }
     }
     // start with the next rank, not with rank 0: if everybody served the peers in index order, all first messages would
-    // converge on the same receiver
-    std::sort(outs.begin(), outs.end(), [&](const Out& a, const Out& b) {
+    // converge on the same receiver (stable: the messages of one peer keep their order)
+    std::stable_sort(x.outs.begin(), x.outs.end(), [&](const Out& a, const Out& b) {
       return (a.peer - rank_ + world_) % world_ < (b.peer - rank_ + world_) % world_;
     });
-    size_t pending_out = outs.size();
+    x.pending_out = x.outs.size();
+    blocked_.assign(world_, 0);
+    if (on_recv)
+      for (size_t i : early) (*on_recv)(i);
     const uint64_t t0 = now_ns();
     // first try without sleeping: small messages usually go out and come in at once
-    for (Out& o : outs) {
-      push(o.peer, o.hdr, o.hdr_sent, o.ptr, o.sent);
-      if (o.hdr_sent == sizeof(WireHdr) && o.sent == o.hdr.bytes) --pending_out;
-    }
-    for (int spin = 0; spin < 200 && pending_in; ++spin)
-      for (const Seg& r : recvs)
-        if (peers_[r.peer].expect.count(tag)) pending_in -= drain(r.peer, tag);
+    push_ready(x);
+    for (int spin = 0; spin < 200 && x.pending_in; ++spin)
+      for (int p : rpeers) {
+        x.pending_in -= drain(p);
+        if (x.fresh) push_ready(x);
+      }
     std::vector<pollfd> pfds;
-    while (pending_in || pending_out) {
+    while (x.pending_in || x.pending_out) {
+      push_ready(x);
+      if (!x.pending_in && !x.pending_out) break;
       pfds.clear();
       // always listen on every connection: a peer may already be sending for a later collective
       for (int p = 0; p < world_; ++p)
         if (fds_[p] >= 0) {
           const Peer& P = peers_[p];
           const bool idle_hold = P.held && !P.expect.count(P.hdr.tag);   // readable, but nobody to read for: don't spin
-          pfds.push_back(pollfd{fds_[p], (short)(idle_hold ? 0 : POLLIN), 0});
+          pfds.push_back(pollfd{fds_[p], (short)((idle_hold ? 0 : POLLIN) | (blocked_[p] ? POLLOUT : 0)), 0});
         }
-      for (Out& o : outs)
-        if (o.sent < o.hdr.bytes || o.hdr_sent < sizeof(WireHdr))
-          for (pollfd& pf : pfds)
-            if (pf.fd == fds_[o.peer]) pf.events |= POLLOUT;
-      int rc = poll(pfds.data(), (nfds_t)pfds.size(), 100);
+      int rc = poll(pfds.data(), (nfds_t)pfds.size(), x.paced ? (tokens_ < 1.0 ? 1 : 0) : 100);
       if (rc < 0 && errno != EINTR) MLSLB_ASSERT(false, "poll(): %s", strerror(errno));
       if (ctx_->boot->poisoned()) MLSLB_ASSERT(false, "job poisoned by rank %d during a network collective", (int)ctx_->boot->poisoned() - 1);
       const int wd = ctx_->env.watchdog_sec;
@@ -199,22 +205,40 @@ class Mesh {
         int peer = -1;
         for (int p = 0; p < world_; ++p)
           if (fds_[p] == pf.fd) peer = p;
-        if (pf.revents & POLLIN) pending_in -= drain(peer, tag);
-        if (pf.revents & POLLOUT)
-          for (Out& o : outs)
-            if (o.peer == peer && (o.hdr_sent < sizeof(WireHdr) || o.sent < o.hdr.bytes)) {
-              push(o.peer, o.hdr, o.hdr_sent, o.ptr, o.sent);
-              if (o.hdr_sent == sizeof(WireHdr) && o.sent == o.hdr.bytes) --pending_out;
-            }
+        if (pf.revents & POLLOUT) blocked_[peer] = 0;
+        if (pf.revents & POLLIN) x.pending_in -= drain(peer);
       }
     }
+  }
+
+  // Only inside an on_recv callback: one more message of the running exchange (e.g. the reduced chunk that can leave now).
+  void add_send(const Seg& s) {
+    MLSLB_ASSERT(cur_ != nullptr, "add_send() outside an exchange");
+    cur_->outs.push_back(Out{s.peer, WireHdr{s.tag ? s.tag : cur_->tag, s.bytes}, 0, 0, s.ptr});
+    ++cur_->pending_out;
+    cur_->fresh = true;
   }
 
  private:
   struct Expect {
     char* ptr;
     size_t bytes;
-    bool done;
+    size_t idx;     // position in the exchange's receive list
+  };
+  struct Out {
+    int peer;
+    WireHdr hdr;
+    size_t hdr_sent, sent;
+    const char* ptr;
+    bool done() const { return hdr_sent == sizeof(WireHdr) && sent == hdr.bytes; }
+  };
+  struct Xchg {     // the running exchange
+    uint64_t tag = 0;
+    std::vector<Out> outs;
+    size_t first_live = 0, pending_out = 0, pending_in = 0;
+    bool fresh = false;          // add_send() queued something since the last push
+    bool paced = false;          // link emulation: the last push ran out of tokens
+    const RecvFn* on_recv = nullptr;
   };
   struct Peer {
     // incoming parser
@@ -234,6 +258,34 @@ class Mesh {
     return v;
   }
 
+  // Send what the sockets take.  Per peer strictly in list order (the byte stream carries one message after the other); a
+  // peer whose socket is full is skipped until poll() reports it writable again.
+  void push_ready(Xchg& x) {
+    x.fresh = x.paced = false;
+    busy_.assign(world_, 0);
+    while (x.first_live < x.outs.size() && x.outs[x.first_live].done()) ++x.first_live;
+    for (size_t i = x.first_live; i < x.outs.size(); ++i) {
+      Out& o = x.outs[i];
+      if (o.done() || busy_[o.peer]) continue;
+      if (blocked_[o.peer]) {
+        busy_[o.peer] = 1;
+        continue;
+      }
+      paced_ = false;
+      quantum_left_ = 64 << 10;
+      push(o.peer, o.hdr, o.hdr_sent, o.ptr, o.sent);
+      if (o.done()) {
+        --x.pending_out;
+      } else if (paced_) {      // out of tokens or of its turn, not out of socket space: go on in a moment, nothing to poll for
+        x.paced = true;
+        busy_[o.peer] = 1;
+        if (tokens_ < 1.0) break;
+      } else {
+        busy_[o.peer] = blocked_[o.peer] = 1;
+      }
+    }
+  }
+
   void push(int peer, const WireHdr& h, size_t& hdr_sent, const char* ptr, size_t& sent) {
     const int fd = fds_[peer];
     while (hdr_sent < sizeof(WireHdr) || sent < h.bytes) {
@@ -241,7 +293,22 @@ class Mesh {
       iovec iov[2];
       int niov = 0;
       if (hdr_sent < sizeof(WireHdr)) iov[niov++] = iovec{(char*)&h + hdr_sent, sizeof(WireHdr) - hdr_sent};
-      if (sent < h.bytes) iov[niov++] = iovec{(char*)ptr + sent, (size_t)(h.bytes - sent)};
+      size_t pay = h.bytes - sent;
+      if (rate_Bps_ > 0) {      // link emulation: this rank's egress is paced by a token bucket (3 ms of burst)
+        const uint64_t now = now_ns();
+        tokens_ = std::min(rate_Bps_ * 3e-3, tokens_ + (double)(now - last_refill_ns_) * 1e-9 * rate_Bps_);
+        last_refill_ns_ = now;
+        if (tokens_ < 1.0) {
+          paced_ = true;
+          return;
+        }
+        if (quantum_left_ == 0) {    // the peers take turns, like sockets sharing one NIC
+          paced_ = true;
+          return;
+        }
+        pay = std::min({pay, (size_t)tokens_, quantum_left_});
+      }
+      if (pay) iov[niov++] = iovec{(char*)ptr + sent, pay};
       msghdr mh;
       memset(&mh, 0, sizeof(mh));
       mh.msg_iov = iov;
@@ -257,11 +324,15 @@ class Mesh {
         k -= h_part;
       }
       sent += k;
+      if (rate_Bps_ > 0) {
+        tokens_ -= (double)k;
+        quantum_left_ -= std::min(quantum_left_, k);
+      }
     }
   }
 
   // read what is available from `peer`; returns how many receives of the running exchange completed
-  size_t drain(int peer, uint64_t /*running_tag*/) {
+  size_t drain(int peer) {
     Peer& P = peers_[peer];
     const int fd = fds_[peer];
     size_t completed = 0;
@@ -312,18 +383,25 @@ class Mesh {
           MLSLB_ASSERT(it->second.bytes == P.hdr.bytes, "message of %llu bytes from rank %d where %zu were expected",
                        (unsigned long long)P.hdr.bytes, peer, it->second.bytes);
           if (P.hdr.bytes) memcpy(it->second.ptr, P.stash.data(), P.hdr.bytes);
+          const size_t idx = it->second.idx;
           P.expect.erase(it);
           ++completed;
+          if (cur_ && cur_->on_recv) (*cur_->on_recv)(idx);
         } else {
           P.parked[P.hdr.tag] = std::move(P.stash);
         }
         P.stash.clear();
+        P.hdr_got = 0;
+        P.dst = nullptr;
       } else {
-        P.expect.erase(P.hdr.tag);
+        auto it = P.expect.find(P.hdr.tag);
+        const size_t idx = it->second.idx;
+        P.expect.erase(it);
         ++completed;
+        P.hdr_got = 0;       // the parser is ready for the next message before the callback runs
+        P.dst = nullptr;
+        if (cur_ && cur_->on_recv) (*cur_->on_recv)(idx);
       }
-      P.hdr_got = 0;
-      P.dst = nullptr;
     }
   }
 
@@ -331,6 +409,14 @@ class Mesh {
   int rank_ = 0, world_ = 1;
   std::vector<int> fds_;
   std::vector<Peer> peers_;
+  std::vector<char> blocked_, busy_;   // per peer: socket full (wait for POLLOUT) / already served in this push pass
+  Xchg* cur_ = nullptr;
+  // MLSL_NET_EMULATE_GBIT=<x>: pace this rank's egress to x Gbit/s - what a collective does on a slower link than loop-back
+  // can be measured on one machine (bench / test knob, off by default)
+  double rate_Bps_ = getenv("MLSL_NET_EMULATE_GBIT") ? atof(getenv("MLSL_NET_EMULATE_GBIT")) * 1e9 / 8 : 0.0, tokens_ = 0.0;
+  uint64_t last_refill_ns_ = 0;
+  bool paced_ = false;
+  size_t quantum_left_ = 0;
   std::mutex mu_;
 };
 
@@ -472,6 +558,67 @@ void NetBackend::execute(CommRequest& r) {
     if (elems) host_reduce(d.dtype, dst, srcs, elems, d.rop, scale);
   };
 
+  // Large reductions travel in chunks: every slice is cut into K pieces with a tag each, a piece is reduced as soon as all
+  // members' copies of it are there (while the later pieces are still on the wire) and - all-reduce - its result leaves for
+  // the other members right away, so the reduction and the second exchange hide behind the first.  Pieces are reduced in
+  // member order like whole slices: the values do not depend on the chunking.
+  static const size_t chunk_bytes = std::max<size_t>(4096, (getenv("MLSL_NET_CHUNK_KB") ? (size_t)atol(getenv("MLSL_NET_CHUNK_KB")) : 512) << 10);
+  constexpr int kMaxChunks = 96;                       // two phases of tags fit the 8-bit step field (2 + 2 * 96 < 256)
+  auto chunk_elems = [&](size_t slice_elems) {         // elements per piece (0: not worth chunking)
+    if (slice_elems * dt < 2 * chunk_bytes) return (size_t)0;
+    size_t ce = std::max(chunk_bytes / dt, ceil_div(slice_elems, (size_t)kMaxChunks));
+    return (ce + 63) & ~(size_t)63;
+  };
+  // slice p of the send side starts at element s_lo(p) and has s_len(p) elements; mine is reduced into `out`; with
+  // `gather` the reduced pieces go to everybody (all-reduce: slice p of R starts at s_lo(p) too)
+  auto chunked_reduce = [&](size_t ce, size_t per, const std::function<size_t(int)>& s_lo, const std::function<size_t(int)>& s_len,
+                            char* out, bool gather) {
+    char* tmp = net_scratch((size_t)(P + 1) * per * dt);   // (+1: room for a staged output behind the slices)
+    auto clen = [&](int p, int c) {                    // length of piece c of slice p
+      const size_t L = s_len(p), b = (size_t)c * ce;
+      return b >= L ? (size_t)0 : std::min(ce, L - b);
+    };
+    const int Kall = (int)ceil_div(per, ce);
+    struct Meta {
+      int phase, p, c;
+    };
+    std::vector<Meta> meta;
+    std::vector<int> arrived(Kall, 0);
+    for (int p = 0; p < P; ++p) {
+      if (p == me) continue;
+      for (int c = 0; c < Kall; ++c) {
+        if (clen(p, c)) snd.push_back(Seg{peer(p), S + (s_lo(p) + (size_t)c * ce) * dt, clen(p, c) * dt, tag(2 + c)});
+        if (clen(me, c)) {
+          rcv.push_back(Seg{peer(p), tmp + ((size_t)p * per + (size_t)c * ce) * dt, clen(me, c) * dt, tag(2 + c)});
+          meta.push_back(Meta{0, p, c});
+        }
+      }
+      if (gather)
+        for (int c = 0; c < Kall; ++c)
+          if (clen(p, c)) {
+            rcv.push_back(Seg{peer(p), R + (s_lo(p) + (size_t)c * ce) * dt, clen(p, c) * dt, tag(2 + kMaxChunks + c)});
+            meta.push_back(Meta{1, p, c});
+          }
+    }
+    std::vector<const void*> srcs(P);
+    auto reduce_piece = [&](int c) {
+      const size_t off = (size_t)c * ce;
+      for (int p = 0; p < P; ++p)
+        srcs[p] = p == me ? (const void*)(S + (s_lo(me) + off) * dt) : (const void*)(tmp + ((size_t)p * per + off) * dt);
+      host_reduce(d.dtype, out + off * dt, srcs, clen(me, c), d.rop, d.scale);
+      if (gather)
+        for (int p = 0; p < P; ++p)
+          if (p != me) mesh_.add_send(Seg{peer(p), out + off * dt, clen(me, c) * dt, tag(2 + kMaxChunks + c)});
+    };
+    Mesh::RecvFn on_recv = [&](size_t i) {
+      const Meta& m = meta[i];
+      if (m.phase == 0 && ++arrived[m.c] == P - 1) reduce_piece(m.c);
+    };
+    mesh_.exchange(tag(0), snd, rcv, &on_recv);
+    snd.clear();
+    rcv.clear();
+  };
+
   switch (d.kind) {
     case OpKind::BARRIER:
       for (int p = 0; p < P; ++p)
@@ -573,6 +720,15 @@ void NetBackend::execute(CommRequest& r) {
       go(0);
       break;
     case OpKind::REDUCE_SCATTER: {
+      if (const size_t ce = chunk_elems(n)) {      // (the choice must not depend on the rank or on its buffers)
+        // in place the result lands on slice 0 of the send buffer, which a rank other than member 0 still has to send: only
+        // an output on the own slice or outside the send buffer can be written while the exchange runs - else it is staged
+        const bool out_safe = R == S + (size_t)me * n * dt || R + n * dt <= S || R >= S + (size_t)P * n * dt;
+        char* out = out_safe ? R : net_scratch((size_t)(P + 1) * n * dt) + (size_t)P * n * dt;
+        chunked_reduce(ce, n, [&](int p) { return (size_t)p * n; }, [&](int) { return n; }, out, false);
+        if (!out_safe) memcpy(R, out, n * dt);
+        break;
+      }
       char* tmp = net_scratch((size_t)P * n * dt);
       for (int p = 0; p < P; ++p)
         if (p != me) {
@@ -621,6 +777,10 @@ void NetBackend::execute(CommRequest& r) {
       const size_t per = ceil_div(n, (size_t)P);
       auto lo = [&](int p) { return std::min(n, (size_t)p * per); };
       auto len = [&](int p) { return std::min(n, lo(p) + per) - lo(p); };
+      if (const size_t ce = chunk_elems(per)) {
+        chunked_reduce(ce, per, lo, len, R + lo(me) * dt, true);
+        break;
+      }
       char* tmp = net_scratch((size_t)P * per * dt);
       for (int p = 0; p < P; ++p)
         if (p != me) {

@@ -25,7 +25,7 @@ def rows(out):
 
 
 def ours(op):
-    port = str(random.randrange(20000, 50000))
+    port = str(random.randrange(20000, 32000))       # below the ephemeral range
     env = dict(os.environ, MLSL_BENCH_OP=op, MLSL_BENCH_OUT_OF_PLACE="0")
     env.pop("MLSL_BACKEND", None)
     cmd = lambda i: [RUN, "-n", "1", "--bind", "none", "--nnodes", str(N), "--node-rank", str(i), "--master-addr", "127.0.0.1",

@@ -3,6 +3,23 @@ import sys
 
 import pytest
 
+
+def free_port():
+    """A TCP port for a rendezvous on 127.0.0.1: below the kernel's ephemeral range (a port that the outgoing connections of
+    an earlier job still hold would make rank 0's listen fail and its peers retry until they time out) and free right now."""
+    import random
+    import socket
+    rng = random.Random()
+    for _ in range(200):
+        port = rng.randrange(20000, 32000)
+        with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+            try:
+                s.bind(("127.0.0.1", port))
+                return port
+            except OSError:
+                continue
+    raise RuntimeError("no free port between 20000 and 32000")
+
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # loopback ranks share one GPU (see mlsl_b200/__init__.py)
 # Loop-back ranks are threads of ONE CUDA context.  With lazy module loading the first launch of any kernel (ours or
 # torch's) synchronises the context while holding its lock; if a peer rank's kernel is spinning for a third rank whose

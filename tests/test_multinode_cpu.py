@@ -2,11 +2,12 @@
 The "nodes" are groups of processes on this machine with torchrun's variables; inside a node the ranks meet in shared
 memory under a per-node job id, between nodes over gloo."""
 import os
-import random
 import subprocess
 import sys
 
 import pytest
+
+from conftest import free_port
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -14,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize("nnodes,per_node", [(2, 2), (3, 1), (1, 3), (2, 3)])
 def test_two_level_collectives_and_training(nnodes, per_node):
     world = nnodes * per_node
-    port = str(random.Random().randrange(20000, 50000))
+    port = str(free_port())
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r % per_node),

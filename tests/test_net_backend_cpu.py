@@ -1,19 +1,18 @@
 """The net backend (TCP control plane + TCP data mesh) on one machine playing several nodes: every "node" is its own
 mlslrun with --nnodes / --node-rank, exactly how a real multi-node job is started."""
 import os
-import random
 import subprocess
 import sys
 
 import pytest
 
-from conftest import ROOT
+from conftest import ROOT, free_port
 
 MLSLRUN = os.path.join(ROOT, "bin", "mlslrun")
 
 
 def _launch(nnodes, per_node, cmd, extra_env=None, timeout=240):
-    port = str(random.Random().randrange(20000, 50000))
+    port = str(free_port())
     env = dict(os.environ, MLSL_WATCHDOG_SEC="60")
     env.pop("MLSL_BACKEND", None)
     env.update(extra_env or {})
@@ -37,6 +36,17 @@ def test_random_collectives_and_fused_update_across_nodes(nnodes, per_node, seed
     rcs, out = _launch(nnodes, per_node, [sys.executable, os.path.join(ROOT, "tests", "net_worker.py"), str(seed)])
     assert all(rc == 0 for rc in rcs), out[-3000:]
     assert out.count("NET OK") == nnodes * per_node
+
+
+@pytest.mark.parametrize("nnodes,per_node", [(2, 2), (4, 1), (2, 1)])
+def test_reductions_in_pieces_are_exact(nnodes, per_node):
+    """Large reductions are cut into pieces that are reduced (and, all-reduce, passed on) while the rest is still on the wire;
+    4 KiB pieces here, so that every size class takes that path: in place, send -> recv, reduce-scatter onto slice 0 of its
+    own input."""
+    rcs, out = _launch(nnodes, per_node, [sys.executable, os.path.join(ROOT, "tests", "net_chunk_worker.py")],
+                       extra_env={"MLSL_NET_CHUNK_KB": "4"})
+    assert all(rc == 0 for rc in rcs), out[-3000:]
+    assert out.count("NET CHUNK OK") == nnodes * per_node
 
 
 def test_a_dying_rank_fails_the_whole_multi_node_job_fast():
