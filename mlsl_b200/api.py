@@ -88,11 +88,17 @@ class _Handle:
 
     def _get(self, fname, ctype=c_size_t, *args):
         out = ctype()
-        check(getattr(_lib.lib(), fname)(self.handle, *args, ctypes.byref(out)))
+        fn = _FN.get(fname)
+        if fn is None:
+            fn = _FN[fname] = getattr(_lib.lib(), fname)      # ctypes attribute lookups are not free on a hot path
+        check(fn(self.handle, *args, ctypes.byref(out)))
         return out.value
 
     def _call(self, fname, *args):
-        check(getattr(_lib.lib(), fname)(self.handle, *args))
+        fn = _FN.get(fname)
+        if fn is None:
+            fn = _FN[fname] = getattr(_lib.lib(), fname)
+        check(fn(self.handle, *args))
 
 
 def _getters(cls, prefix, names, ctype=c_size_t):
@@ -196,11 +202,24 @@ _getters(ParameterSet, "mlsl_parameter_set", ["data_type"], c_int)
 
 
 class Distribution(_Handle):
+    __slots__ = ("_shape",)       # (group type) -> (process count, process index): fixed for the life of a distribution
+
+    def _group_shape(self, group_type):
+        try:
+            return self._shape[group_type]
+        except AttributeError:
+            self._shape = {}
+        except KeyError:
+            pass
+        v = self._shape[group_type] = (self._get("mlsl_distribution_get_process_count", c_size_t, group_type),
+                                       self._get("mlsl_distribution_get_process_idx", c_size_t, group_type))
+        return v
+
     def get_process_count(self, group_type):
-        return self._get("mlsl_distribution_get_process_count", c_size_t, group_type)
+        return self._group_shape(group_type)[0]
 
     def get_process_idx(self, group_type):
-        return self._get("mlsl_distribution_get_process_idx", c_size_t, group_type)
+        return self._group_shape(group_type)[1]
 
     def _req(self, fname, *args):
         _pre()

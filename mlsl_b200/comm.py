@@ -296,6 +296,24 @@ def _dist(distribution):
     return distribution if distribution is not None else world_distribution()
 
 
+def _enter(tensor, distribution):
+    """Common prologue of the tensor-level collectives: (state, distribution) with one state lookup."""
+    st = _state()
+    if st.get("env") is None:
+        raise RuntimeError("mlsl_b200 is not initialised: call mlsl_b200.init() first")
+    if not tensor.is_contiguous() or (tensor.is_cuda and not st["device"]):
+        _prep(tensor)                                   # raises the descriptive error
+    return st, (distribution if distribution is not None else (st.get("world_dist") or world_distribution()))
+
+
+def _finish(st, req, result, keep, async_op):
+    e = st["env"]
+    if async_op:
+        return Work(e, req, result, keep)
+    e.wait(req)
+    return result
+
+
 def _group(group):
     if isinstance(group, str):
         if group not in _GROUPS:
@@ -342,35 +360,31 @@ def allreduce(tensor, op="sum", group="data", scale=1.0, compress=False, out=Non
 
 def reduce_scatter(tensor, out=None, op="sum", group="data", scale=1.0, async_op=False, distribution=None):
     """tensor: P*n elements; returns rank's n-element reduced shard."""
-    _prep(tensor)
-    d = _dist(distribution)
-    P = d.get_process_count(_group(group))
+    st, d = _enter(tensor, distribution)
+    g = _group(group)
+    P = d.get_process_count(g)
     if tensor.numel() % P:
         raise ValueError("reduce_scatter: %d elements cannot be split over %d ranks" % (tensor.numel(), P))
     n = tensor.numel() // P
     if out is None:
-        out = alloc_tensor((n,), tensor.dtype, zero=False) if is_device() else torch.empty(n, dtype=tensor.dtype)
+        out = alloc_tensor((n,), tensor.dtype, zero=False) if st["device"] else torch.empty(n, dtype=tensor.dtype)
     else:
         _check_out("reduce_scatter", out, n, tensor.dtype)
-    _sync_stream()
-    req = d.reduce_scatter(tensor, out, n, mlsl_dtype(tensor.dtype), _op(op), _group(group), float(scale))
-    w = Work(env(), req, out, (tensor, out))
-    return w if async_op else w.wait()
+    req = d.reduce_scatter(tensor, out, n, mlsl_dtype(tensor.dtype), _op(op), g, float(scale))
+    return _finish(st, req, out, (tensor, out), async_op)
 
 
 def allgather(tensor, out=None, group="data", async_op=False, distribution=None):
-    _prep(tensor)
-    d = _dist(distribution)
-    P = d.get_process_count(_group(group))
+    st, d = _enter(tensor, distribution)
+    g = _group(group)
+    n = tensor.numel()
+    P = d.get_process_count(g)
     if out is None:
-        out = (alloc_tensor((P * tensor.numel(),), tensor.dtype, zero=False) if is_device()
-               else torch.empty(P * tensor.numel(), dtype=tensor.dtype))
+        out = alloc_tensor((P * n,), tensor.dtype, zero=False) if st["device"] else torch.empty(P * n, dtype=tensor.dtype)
     else:
-        _check_out("allgather", out, P * tensor.numel(), tensor.dtype)
-    _sync_stream()
-    req = d.all_gather(tensor, tensor.numel(), out, mlsl_dtype(tensor.dtype), _group(group))
-    w = Work(env(), req, out, (tensor, out))
-    return w if async_op else w.wait()
+        _check_out("allgather", out, P * n, tensor.dtype)
+    req = d.all_gather(tensor, n, out, mlsl_dtype(tensor.dtype), g)
+    return _finish(st, req, out, (tensor, out), async_op)
 
 
 def allgatherv(tensor, recv_counts, out=None, group="data", async_op=False, distribution=None):
@@ -395,19 +409,17 @@ def allgatherv(tensor, recv_counts, out=None, group="data", async_op=False, dist
 
 
 def alltoall(tensor, out=None, group="data", async_op=False, distribution=None):
-    _prep(tensor)
-    d = _dist(distribution)
-    P = d.get_process_count(_group(group))
+    st, d = _enter(tensor, distribution)
+    g = _group(group)
+    P = d.get_process_count(g)
     if tensor.numel() % P:
         raise ValueError("alltoall: %d elements cannot be split over %d ranks" % (tensor.numel(), P))
     if out is None:
-        out = alloc_tensor(tuple(tensor.shape), tensor.dtype, zero=False) if is_device() else torch.empty_like(tensor)
+        out = alloc_tensor(tuple(tensor.shape), tensor.dtype, zero=False) if st["device"] else torch.empty_like(tensor)
     else:
         _check_out("alltoall", out, tensor.numel(), tensor.dtype)
-    _sync_stream()
-    req = d.all_to_all(tensor, tensor.numel() // P, out, mlsl_dtype(tensor.dtype), _group(group))
-    w = Work(env(), req, out, (tensor, out))
-    return w if async_op else w.wait()
+    req = d.all_to_all(tensor, tensor.numel() // P, out, mlsl_dtype(tensor.dtype), g)
+    return _finish(st, req, out, (tensor, out), async_op)
 
 
 def alltoallv(tensor, send_counts, recv_counts=None, out=None, group="data", async_op=False, distribution=None):
@@ -463,21 +475,17 @@ def ring_shift(tensor, shift=1, out=None, group="data", async_op=False, distribu
 
 
 def bcast(tensor, root=0, group="data", async_op=False, distribution=None):
-    _prep(tensor)
-    _sync_stream()
-    raw = _movable(tensor.view(-1))
-    req = _dist(distribution).bcast(raw, raw.numel(), mlsl_dtype(raw.dtype), root, _group(group))
-    w = Work(env(), req, tensor, (tensor, raw))
-    return w if async_op else w.wait()
+    st, d = _enter(tensor, distribution)
+    raw = tensor if (tensor.dim() == 1 and tensor.dtype in _TORCH2MLSL) else _movable(tensor.view(-1))
+    req = d.bcast(raw, raw.numel(), mlsl_dtype(raw.dtype), root, _group(group))
+    return _finish(st, req, tensor, (tensor, raw), async_op)
 
 
 def reduce(tensor, out=None, root=0, op="sum", group="data", async_op=False, distribution=None):
-    _prep(tensor)
+    st, d = _enter(tensor, distribution)
     out = tensor if out is None else _check_out("reduce", out, tensor.numel(), tensor.dtype)
-    _sync_stream()
-    req = _dist(distribution).reduce(tensor, out, tensor.numel(), mlsl_dtype(tensor.dtype), _op(op), root, _group(group))
-    w = Work(env(), req, out, (tensor, out))
-    return w if async_op else w.wait()
+    req = d.reduce(tensor, out, tensor.numel(), mlsl_dtype(tensor.dtype), _op(op), root, _group(group))
+    return _finish(st, req, out, (tensor, out), async_op)
 
 
 def gather(tensor, out=None, root=0, group="data", async_op=False, distribution=None):
