@@ -13,11 +13,14 @@
 // the same connection; an early message is parked until its collective asks for it.  Buffers are ordinary host memory.
 #include <fcntl.h>
 #include <poll.h>
+#include <sched.h>
+#include <sys/mman.h>
 #include <sys/socket.h>
 #include <sys/uio.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <cstring>
 #include <deque>
@@ -56,6 +59,37 @@ struct WireHdr {
   uint64_t tag, bytes;
 };
 
+// One direction of a same-node pair: a byte stream through shared memory with the semantics of the socket it replaces
+// (bounded, in order, the writer stalls when it is full).  Single producer, single consumer.
+struct ShmRing {
+  alignas(64) std::atomic<uint64_t> head;   // bytes written so far (producer)
+  alignas(64) std::atomic<uint64_t> tail;   // bytes read so far (consumer)
+  alignas(64) uint64_t cap;                 // power of two
+  alignas(64) char data[1];
+
+  size_t write(const char* p, size_t n) {
+    const uint64_t h = head.load(std::memory_order_relaxed), t = tail.load(std::memory_order_acquire);
+    n = std::min<size_t>(n, cap - (h - t));
+    if (!n) return 0;
+    const size_t o = h & (cap - 1), first = std::min<size_t>(n, cap - o);
+    memcpy(data + o, p, first);
+    if (n > first) memcpy(data, p + first, n - first);
+    head.store(h + n, std::memory_order_release);
+    return n;
+  }
+  size_t read(char* p, size_t n) {
+    const uint64_t t = tail.load(std::memory_order_relaxed), h = head.load(std::memory_order_acquire);
+    n = std::min<size_t>(n, h - t);
+    if (!n) return 0;
+    const size_t o = t & (cap - 1), first = std::min<size_t>(n, cap - o);
+    memcpy(p, data + o, first);
+    if (n > first) memcpy(p + first, data, n - first);
+    tail.store(t + n, std::memory_order_release);
+    return n;
+  }
+  bool readable() const { return head.load(std::memory_order_acquire) != tail.load(std::memory_order_relaxed); }
+};
+
 class Mesh {
  public:
   void init(RankContext* ctx) {
@@ -70,6 +104,7 @@ class Mesh {
     struct Addr {
       char ip[48];
       int port;
+      char node[80];     // which machine (and which launcher on it) the rank runs on: equal keys -> shared memory
     } mine, zero;
     memset(&zero, 0, sizeof(zero));
     mine = zero;
@@ -79,6 +114,7 @@ class Mesh {
     if (const char* v = getenv("MLSL_NET_ADDR")) my_ip = v;       // explicit address of this rank's interface
     snprintf(mine.ip, sizeof(mine.ip), "%s", my_ip.c_str());
     mine.port = port;
+    snprintf(mine.node, sizeof(mine.node), "%s", node_key().c_str());
     std::vector<Addr> all(world_);
     ctx->boot->allgather(&mine, all.data(), sizeof(Addr));
     // connect to every lower rank (the listen backlog completes the handshake even before the peer accepts) ...
@@ -107,6 +143,89 @@ class Mesh {
       fds_[who] = fd;
     }
     close(lfd);
+    // ranks of one node talk through shared memory: the lower rank of a pair creates the segment and names it over the
+    // socket, the higher one maps it and answers; a pair that cannot share it (containers with separate /dev/shm) stays on TCP
+    const char* use_shm = getenv("MLSL_NET_SHM");
+    if (!use_shm || atoi(use_shm) != 0) {
+      struct Offer {
+        uint32_t magic;
+        char name[60];
+      };
+      const size_t ring_bytes = ring_capacity();
+      const size_t seg_bytes = 2 * (offsetof(ShmRing, data) + ring_bytes);
+      auto ring_at = [&](char* base, int k) { return (ShmRing*)(base + (size_t)k * (offsetof(ShmRing, data) + ring_bytes)); };
+      std::vector<std::pair<int, std::string>> offered;
+      for (int p = rank_ + 1; p < world_; ++p) {
+        if (strcmp(all[p].node, mine.node) != 0) continue;
+        Offer o;
+        memset(&o, 0, sizeof(o));
+        o.magic = 0x4d53484d;
+        snprintf(o.name, sizeof(o.name), "/mlslb_n%08x_%d_%d_%d", (unsigned)std::hash<std::string>()(key), (int)getpid(), rank_, p);
+        int fd = shm_open(o.name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        char* base = nullptr;
+        if (fd >= 0 && ftruncate(fd, (off_t)seg_bytes) == 0) {
+          void* m = mmap(nullptr, seg_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+          if (m != MAP_FAILED) base = (char*)m;
+        }
+        if (fd >= 0) close(fd);
+        if (base) {
+          for (int k = 0; k < 2; ++k) {
+            ShmRing* r = ring_at(base, k);
+            r->head.store(0, std::memory_order_relaxed);
+            r->tail.store(0, std::memory_order_relaxed);
+            r->cap = ring_bytes;
+          }
+          std::atomic_thread_fence(std::memory_order_release);
+          peers_[p].tx = ring_at(base, 0);      // lower -> higher
+          peers_[p].rx = ring_at(base, 1);
+          peers_[p].seg = base;
+          peers_[p].seg_bytes = seg_bytes;
+        } else {
+          o.magic = 0;                          // tell the peer to stay on TCP
+        }
+        tcp_send_all(fds_[p], &o, sizeof(o));
+        offered.emplace_back(p, base ? std::string(o.name) : std::string());
+      }
+      for (int p = 0; p < rank_; ++p) {
+        if (strcmp(all[p].node, mine.node) != 0) continue;
+        Offer o;
+        tcp_recv_all(fds_[p], &o, sizeof(o));
+        uint32_t ok = 0;
+        if (o.magic == 0x4d53484d) {
+          o.name[sizeof(o.name) - 1] = 0;
+          int fd = shm_open(o.name, O_RDWR, 0600);
+          if (fd >= 0) {
+            void* m = mmap(nullptr, seg_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+            close(fd);
+            if (m != MAP_FAILED && ring_at((char*)m, 0)->cap == ring_bytes) {
+              peers_[p].rx = ring_at((char*)m, 0);
+              peers_[p].tx = ring_at((char*)m, 1);
+              peers_[p].seg = (char*)m;
+              peers_[p].seg_bytes = seg_bytes;
+              ok = 1;
+            } else if (m != MAP_FAILED) {
+              munmap(m, seg_bytes);
+            }
+          }
+        }
+        tcp_send_all(fds_[p], &ok, sizeof(ok));
+      }
+      for (auto& of : offered) {
+        uint32_t ok = 0;
+        tcp_recv_all(fds_[of.first], &ok, sizeof(ok));
+        if (!of.second.empty()) shm_unlink(of.second.c_str());     // both sides hold their mapping (or never will)
+        Peer& P = peers_[of.first];
+        if (!ok && P.seg) {
+          munmap(P.seg, P.seg_bytes);
+          P.seg = nullptr;
+          P.tx = P.rx = nullptr;
+        }
+      }
+      for (int p = 0; p < world_; ++p)
+        if (peers_[p].tx) {
+          shm_peers_.push_back(p);
+        }
+    }
     for (int p = 0; p < world_; ++p)
       if (fds_[p] >= 0) {
         int fl = fcntl_nonblock(fds_[p]);
@@ -115,12 +234,21 @@ class Mesh {
     ctx->boot->barrier();
   }
 
+  int shm_peer_count() const { return (int)shm_peers_.size(); }
+
   void shutdown_all() {
     for (int& fd : fds_)
       if (fd >= 0) {
         close(fd);
         fd = -1;
       }
+    for (Peer& P : peers_)
+      if (P.seg) {
+        munmap(P.seg, P.seg_bytes);
+        P.seg = nullptr;
+        P.tx = P.rx = nullptr;
+      }
+    shm_peers_.clear();
   }
 
   // Returns when every send and receive has completed.  Plain collectives name every peer at most once per direction; the
@@ -178,18 +306,40 @@ class Mesh {
         if (x.fresh) push_ready(x);
       }
     std::vector<pollfd> pfds;
+    uint64_t idle = 0;
     while (x.pending_in || x.pending_out) {
       push_ready(x);
+      // shared-memory peers have no descriptor to sleep on: look at their rings every round, and keep the rounds short while
+      // something is expected from / still has to go to one of them
+      bool shm_busy = x.shm_stall;
+      for (int p : shm_peers_) {
+        Peer& P = peers_[p];
+        if (P.expect.empty()) continue;
+        shm_busy = true;
+        if (P.rx->readable() && !(P.held && !P.expect.count(P.hdr.tag))) {
+          const size_t k = drain(p);
+          x.pending_in -= k;
+          if (k) idle = 0;
+        }
+      }
+      if (x.fresh) continue;
       if (!x.pending_in && !x.pending_out) break;
+      int timeout_ms = x.paced ? (tokens_ < 1.0 ? 1 : 0) : 100;
+      if (shm_busy) {
+        timeout_ms = 0;
+        if (++idle > 64) sched_yield();
+        if (idle > 20000) timeout_ms = 1;      // a slow peer: stop burning the core
+      }
       pfds.clear();
       // always listen on every connection: a peer may already be sending for a later collective
       for (int p = 0; p < world_; ++p)
         if (fds_[p] >= 0) {
           const Peer& P = peers_[p];
           const bool idle_hold = P.held && !P.expect.count(P.hdr.tag);   // readable, but nobody to read for: don't spin
+          if (P.rx) continue;                                           // (its socket is silent after the set-up)
           pfds.push_back(pollfd{fds_[p], (short)((idle_hold ? 0 : POLLIN) | (blocked_[p] ? POLLOUT : 0)), 0});
         }
-      int rc = poll(pfds.data(), (nfds_t)pfds.size(), x.paced ? (tokens_ < 1.0 ? 1 : 0) : 100);
+      int rc = poll(pfds.data(), (nfds_t)pfds.size(), timeout_ms);
       if (rc < 0 && errno != EINTR) MLSLB_ASSERT(false, "poll(): %s", strerror(errno));
       if (ctx_->boot->poisoned()) MLSLB_ASSERT(false, "job poisoned by rank %d during a network collective", (int)ctx_->boot->poisoned() - 1);
       const int wd = ctx_->env.watchdog_sec;
@@ -198,6 +348,7 @@ class Mesh {
         MLSLB_ASSERT(false, "watchdog: network collective (tag %llx) did not complete in %d s", (unsigned long long)tag, wd);
       }
       if (rc <= 0) continue;
+      idle = 0;
       for (pollfd& pf : pfds) {
         if (pf.revents & (POLLERR | POLLHUP | POLLNVAL)) {
           if (!(pf.revents & POLLIN)) MLSLB_ASSERT(false, "connection to a peer broke during a collective");
@@ -238,6 +389,7 @@ class Mesh {
     size_t first_live = 0, pending_out = 0, pending_in = 0;
     bool fresh = false;          // add_send() queued something since the last push
     bool paced = false;          // link emulation: the last push ran out of tokens
+    bool shm_stall = false;      // a shared-memory ring was full at the last push
     const RecvFn* on_recv = nullptr;
   };
   struct Peer {
@@ -250,9 +402,36 @@ class Mesh {
     bool held = false;                    // header read, large payload left in the socket until its receive is posted
     std::map<uint64_t, Expect> expect;    // tag -> waiting receive of the running exchange
     std::map<uint64_t, std::vector<char>> parked;
+    // same node: the byte streams of the pair run through shared memory instead of the socket
+    ShmRing *tx = nullptr, *rx = nullptr;
+    char* seg = nullptr;
+    size_t seg_bytes = 0;
   };
 
   static int fcntl_nonblock(int fd);
+  static size_t ring_capacity() {      // per direction of a same-node pair, rounded up to a power of two
+    size_t kb = getenv("MLSL_NET_SHM_RING_KB") ? (size_t)atol(getenv("MLSL_NET_SHM_RING_KB")) : 1024, cap = 4096;
+    while (cap < (kb << 10)) cap <<= 1;
+    return cap;
+  }
+  // Same key = same machine and same launcher: host name + boot id, plus the node rank the launcher gave (several "nodes" on
+  // one machine - the test set-up - stay separate).
+  static std::string node_key() {
+    char host[64] = "?";
+    gethostname(host, sizeof(host) - 1);
+    std::string k = host;
+    if (FILE* f = fopen("/proc/sys/kernel/random/boot_id", "r")) {
+      char id[48] = "";
+      if (fgets(id, sizeof(id), f)) k += std::string(":") + std::string(id).substr(0, 8);
+      fclose(f);
+    }
+    for (const char* name : {"MLSL_NODE_RANK", "GROUP_RANK"})
+      if (const char* v = getenv(name)) {
+        k += std::string(":") + v;
+        break;
+      }
+    return k;
+  }
   static size_t eager_bytes() {
     static const size_t v = getenv("MLSL_NET_EAGER_KB") ? (size_t)atol(getenv("MLSL_NET_EAGER_KB")) << 10 : kEagerBytes;
     return v;
@@ -261,7 +440,7 @@ class Mesh {
   // Send what the sockets take.  Per peer strictly in list order (the byte stream carries one message after the other); a
   // peer whose socket is full is skipped until poll() reports it writable again.
   void push_ready(Xchg& x) {
-    x.fresh = x.paced = false;
+    x.fresh = x.paced = x.shm_stall = false;
     busy_.assign(world_, 0);
     while (x.first_live < x.outs.size() && x.outs[x.first_live].done()) ++x.first_live;
     for (size_t i = x.first_live; i < x.outs.size(); ++i) {
@@ -280,6 +459,9 @@ class Mesh {
         x.paced = true;
         busy_[o.peer] = 1;
         if (tokens_ < 1.0) break;
+      } else if (peers_[o.peer].tx) {   // ring full: the reader is not there yet, look again in a moment (nothing to poll)
+        busy_[o.peer] = 1;
+        x.shm_stall = true;
       } else {
         busy_[o.peer] = blocked_[o.peer] = 1;
       }
@@ -287,6 +469,19 @@ class Mesh {
   }
 
   void push(int peer, const WireHdr& h, size_t& hdr_sent, const char* ptr, size_t& sent) {
+    if (ShmRing* ring = peers_[peer].tx) {
+      while (hdr_sent < sizeof(WireHdr)) {
+        const size_t k = ring->write((const char*)&h + hdr_sent, sizeof(WireHdr) - hdr_sent);
+        if (!k) return;
+        hdr_sent += k;
+      }
+      while (sent < h.bytes) {
+        const size_t k = ring->write(ptr + sent, h.bytes - sent);
+        if (!k) return;
+        sent += k;
+      }
+      return;
+    }
     const int fd = fds_[peer];
     while (hdr_sent < sizeof(WireHdr) || sent < h.bytes) {
       // header and payload leave in one call (one segment for small messages instead of a 16-byte packet of its own)
@@ -338,7 +533,9 @@ class Mesh {
     size_t completed = 0;
     for (;;) {
       if (P.hdr_got < sizeof(WireHdr)) {
-        ssize_t n = recv(fd, (char*)&P.hdr + P.hdr_got, sizeof(WireHdr) - P.hdr_got, 0);
+        ssize_t n = P.rx ? (ssize_t)P.rx->read((char*)&P.hdr + P.hdr_got, sizeof(WireHdr) - P.hdr_got)
+                         : recv(fd, (char*)&P.hdr + P.hdr_got, sizeof(WireHdr) - P.hdr_got, 0);
+        if (P.rx && n == 0) return completed;
         if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return completed;
         if (n < 0 && errno == EINTR) continue;
         MLSLB_ASSERT(n > 0, "rank %d closed its connection in the middle of a job", peer);
@@ -369,7 +566,8 @@ class Mesh {
         P.held = false;
       }
       while (P.got < P.hdr.bytes) {
-        ssize_t n = recv(fd, P.dst + P.got, P.hdr.bytes - P.got, 0);
+        ssize_t n = P.rx ? (ssize_t)P.rx->read(P.dst + P.got, P.hdr.bytes - P.got) : recv(fd, P.dst + P.got, P.hdr.bytes - P.got, 0);
+        if (P.rx && n == 0) return completed;
         if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return completed;
         if (n < 0 && errno == EINTR) continue;
         MLSLB_ASSERT(n > 0, "rank %d closed its connection in the middle of a message", peer);
@@ -410,6 +608,7 @@ class Mesh {
   std::vector<int> fds_;
   std::vector<Peer> peers_;
   std::vector<char> blocked_, busy_;   // per peer: socket full (wait for POLLOUT) / already served in this push pass
+  std::vector<int> shm_peers_;
   Xchg* cur_ = nullptr;
   // MLSL_NET_EMULATE_GBIT=<x>: pace this rank's egress to x Gbit/s - what a collective does on a slower link than loop-back
   // can be measured on one machine (bench / test knob, off by default)
@@ -487,7 +686,10 @@ class NetBackend final : public Backend {
     }
     mesh_.shutdown_all();
   }
-  std::string describe() const override { return "net backend (TCP mesh, " + std::to_string(ctx_->world) + " ranks)"; }
+  std::string describe() const override {
+    return "net backend (TCP mesh, " + std::to_string(ctx_->world) + " ranks, " + std::to_string(mesh_.shm_peer_count()) +
+           " same-node peers over shared memory)";
+  }
 
  private:
   RankContext* ctx_;

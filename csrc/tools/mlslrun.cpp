@@ -226,6 +226,8 @@ int main(int argc, char** argv) {
       setenv("WORLD_SIZE", buf, 1);
       setenv("MLSL_JOB_ID", job, 1);
       if (nnodes > 1) {
+        snprintf(buf, sizeof(buf), "%d", node_rank);
+        setenv("MLSL_NODE_RANK", buf, 1);          // the net backend: ranks of one node talk through shared memory
         setenv("MLSL_BACKEND", "net", 0);
         if (!master_addr.empty()) setenv("MLSL_MASTER_ADDR", master_addr.c_str(), 1);
         if (!master_port.empty()) setenv("MLSL_MASTER_PORT", master_port.c_str(), 1);

@@ -49,6 +49,18 @@ def main():
     x = vec(r, 300000, torch.float32)
     mlsl.allreduce(x, scale=1.0 / P)
     assert torch.equal(x, torch.stack([vec(q, 300000, torch.float32) for q in range(P)]).sum(0) / P)
+    # data movement (these take the same transports): all-gather, all-to-all, broadcast of a buffer larger than any ring
+    n = 70001
+    mine = vec(r, n, torch.float32)
+    got = mlsl.allgather(mine)
+    assert torch.equal(got, torch.cat([vec(q, n, torch.float32) for q in range(P)]))
+    a2a = mlsl.alltoall(torch.cat([vec(r * P + q, n, torch.int32) for q in range(P)]))
+    assert torch.equal(a2a, torch.cat([vec(q * P + r, n, torch.int32) for q in range(P)]))
+    b = vec(7, 300001, torch.float64) if r == P - 1 else torch.zeros(300001, dtype=torch.float64)
+    mlsl.bcast(b, root=P - 1)
+    assert torch.equal(b, vec(7, 300001, torch.float64))
+    if len(sys.argv) > 1 and sys.argv[1] == "describe":
+        print(mlsl.env().describe_backend(), flush=True)
     mlsl.barrier()
     mlsl.finalize()
     print("NET CHUNK OK rank %d of %d (%d checks)" % (r, P, checks + 1), flush=True)

@@ -38,6 +38,17 @@ def test_random_collectives_and_fused_update_across_nodes(nnodes, per_node, seed
     assert out.count("NET OK") == nnodes * per_node
 
 
+@pytest.mark.parametrize("shm,ring_kb,expect", [("1", "4", "1 same-node peers"), ("1", "1024", "1 same-node peers"), ("0", "1024", "0 same-node peers")])
+def test_same_node_ranks_talk_through_shared_memory(shm, ring_kb, expect):
+    """Two launchers = two nodes with two ranks each: the ranks of a node exchange through a shared-memory ring (4 KiB here:
+    every larger message wraps around and stalls the writer many times), the nodes over TCP; MLSL_NET_SHM=0 keeps everything
+    on the sockets.  Same collectives, same exact results."""
+    rcs, out = _launch(2, 2, [sys.executable, os.path.join(ROOT, "tests", "net_chunk_worker.py"), "describe"],
+                       extra_env={"MLSL_NET_SHM": shm, "MLSL_NET_SHM_RING_KB": ring_kb})
+    assert all(rc == 0 for rc in rcs), out[-3000:]
+    assert out.count("NET CHUNK OK") == 4 and out.count(expect) == 4, out[-3000:]
+
+
 @pytest.mark.parametrize("nnodes,per_node", [(2, 2), (4, 1), (2, 1)])
 def test_reductions_in_pieces_are_exact(nnodes, per_node):
     """Large reductions are cut into pieces that are reduced (and, all-reduce, passed on) while the rest is still on the wire;
