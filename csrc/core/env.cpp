@@ -116,6 +116,20 @@ EnvConfig parse_env() {
   if (const char* v = ev("MLSL_MASTER_PORT")) c.master_port = atoi(v);
   else if (const char* t = ev("MASTER_PORT")) c.master_port = atoi(t) + 1;   // torch's own store owns MASTER_PORT itself
   else c.master_port = 29571;
+  gets(c.dynamic_server, "MLSL_DYNAMIC_SERVER", "EPLIB_DYNAMIC_SERVER");
+  if (c.dynamic_server == "disable") c.num_servers = 0;
+  getz(c.thp_threshold_mb, "MLSL_THP_THRESHOLD_MB");
+  if (const char* v = ev("EPLIB_THP_THRESHOLD_MB")) if (!ev("MLSL_THP_THRESHOLD_MB")) c.thp_threshold_mb = (size_t)strtoull(v, nullptr, 10);
+  gets(c.hostname, "MLSL_HOSTNAME", "EPLIB_HOSTNAME");
+  geti(c.hostname_type, "MLSL_HOSTNAME_TYPE", "EPLIB_HOSTNAME_TYPE");
+  gets(c.iface_name, "MLSL_IFACE_NAME", "EPLIB_IFACE_NAME");
+  geti(c.iface_idx, "MLSL_IFACE_IDX", "EPLIB_IFACE_IDX");
+  if (c.job_id.empty()) gets(c.job_id, "EPLIB_UUID");     // the reference's shared-memory name key (eplib/env.c:373-407)
+  // knobs of the reference's server processes / MPI glue: accepted, nothing to configure
+  for (const char* name : {"MLSL_SERVER_CREATION_TYPE", "MLSL_SERVER_PREFIX", "MLSL_USE_COPY_THREADS", "MLSL_COPY_THREADS",
+                           "MLSL_COPY_THRESHOLD", "MLSL_MPI_VERSION_CHECK", "EPLIB_USE_ALLOCATOR", "EPLIB_USE_MEM_HOOKS",
+                           "EPLIB_STD_MPI_MODE", "EPLIB_MPI_THREAD_MULTIPLE", "EPLIB_ROOT"})
+    if (ev(name)) c.not_applicable += std::string(c.not_applicable.empty() ? "" : " ") + name;
   geti(c.stats_iters, "MLSL_STATS_ITERS");
   geti(c.stats_skip, "MLSL_STATS_SKIP");
   if (c.num_servers > 16) c.num_servers = 16;
@@ -135,6 +149,12 @@ void print_env(const EnvConfig& c) {
   MLSLB_LOG(LOG_INFO, "MLSL_NVLS=%d MLSL_WAIT_MODE=%s MLSL_WATCHDOG_SEC=%d MLSL_CHECK_SINGLE_NODE=%d",
             (int)c.use_nvls, c.wait_mode.c_str(), c.watchdog_sec, (int)c.check_single_node);
   MLSLB_LOG(LOG_INFO, "MLSL_ALLTOALL_SPLIT=%d MLSL_ALLTOALLV_SPLIT=%d", c.alltoall_split, c.alltoallv_split);
+  MLSLB_LOG(LOG_INFO, "MLSL_DYNAMIC_SERVER=%s (servers are progress threads) MLSL_SERVER_AFFINITY=%s MLSL_THP_THRESHOLD_MB=%zu",
+            c.dynamic_server.empty() ? "thread" : c.dynamic_server.c_str(), c.server_affinity.c_str(), c.thp_threshold_mb);
+  MLSLB_LOG(LOG_INFO, "MLSL_HOSTNAME=%s MLSL_HOSTNAME_TYPE=%d MLSL_IFACE_NAME=%s MLSL_IFACE_IDX=%d", c.hostname.c_str(), c.hostname_type,
+            c.iface_name.c_str(), c.iface_idx);
+  if (!c.not_applicable.empty())
+    MLSLB_LOG(LOG_INFO, "set but not applicable (no server processes, no MPI underneath): %s", c.not_applicable.c_str());
   for (const TuneDesc& d : kTune) MLSLB_LOG(LOG_INFO, "%s=%ld  (%s)", d.env, c.tune.*(d.field), d.help);
 }
 

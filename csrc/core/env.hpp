@@ -93,6 +93,16 @@ struct EnvConfig {
   int master_port = 0;                      // MLSL_MASTER_PORT, else MASTER_PORT + 1, else 29571
   int inproc_ranks = 0;          // MLSL_INPROC_RANKS: >0 -> N virtual ranks inside this process (tests/loopback)
   int stats_iters = 10, stats_skip = 4;  // isolation statistics iterations (reference: 10 / skip 4)
+  // MLSL_DYNAMIC_SERVER (reference src/comm_ep.cpp:1509-1531, eplib/env.c:62-81): process | thread | asyncthread | hybrid all
+  // mean progress THREADS here (there are no server processes); "disable" = no servers, collectives run on the caller
+  std::string dynamic_server;
+  size_t thp_threshold_mb = 128; // MLSL_THP_THRESHOLD_MB: host allocations from this size are 2 MiB aligned + MADV_HUGEPAGE
+                                 // (reference eplib/common.h:78-93)
+  // which address the rank's data connections use across nodes (reference eplib/server.c:228-330: MLSL_HOSTNAME,
+  // MLSL_HOSTNAME_TYPE 0 = as given by the launcher / 1 = name / 2 = IP, MLSL_IFACE_NAME prefix, MLSL_IFACE_IDX)
+  std::string hostname, iface_name;
+  int hostname_type = 0, iface_idx = -1;
+  std::string not_applicable;    // reference knobs that were set but have nothing to act on here (listed at INFO)
   Tunables tune;                 // device-path knobs (see below)
 };
 

@@ -1,5 +1,10 @@
 #include "heap.hpp"
 
+#include <sys/mman.h>
+
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.hpp"
 
 namespace mlslb {
@@ -96,6 +101,19 @@ bool SlabAllocator::contains(size_t off, size_t len) const {
   if (it == live_.begin()) return false;
   --it;
   return off >= it->first && off + len <= it->first + it->second;
+}
+
+void* aligned_host_alloc(size_t bytes, size_t align, size_t thp_bytes) {
+  constexpr size_t kTwoMb = (size_t)2 << 20;
+  align = std::max<size_t>(align ? align : 64, 64);
+  const bool thp = thp_bytes && bytes >= thp_bytes && kTwoMb % align == 0;
+  if (thp) align = kTwoMb;
+  void* p = nullptr;
+  if (posix_memalign(&p, align, round_up(std::max<size_t>(bytes, 1), 64)) != 0) return nullptr;
+#ifdef MADV_HUGEPAGE
+  if (thp && bytes >= kTwoMb) madvise(p, (bytes / kTwoMb) * kTwoMb, MADV_HUGEPAGE);     // the whole 2 MiB pages of the block
+#endif
+  return p;
 }
 
 }  // namespace mlslb

@@ -34,4 +34,8 @@ class SlabAllocator {
   size_t base_ = 0, cap_ = 0, in_use_ = 0;
 };
 
+// Host memory for user buffers outside a shared slab: cache-line aligned, and from `thp_bytes` on 2 MiB aligned and marked
+// for transparent huge pages (reference eplib/common.h:78-93, MLSL_THP_THRESHOLD_MB).  Freed with free().
+void* aligned_host_alloc(size_t bytes, size_t align, size_t thp_bytes);
+
 }  // namespace mlslb

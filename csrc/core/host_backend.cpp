@@ -17,6 +17,7 @@
 #include <map>
 #include <memory>
 
+#include "heap.hpp"
 #include "log.hpp"
 #include "numeric.hpp"
 #include <dlfcn.h>
@@ -196,8 +197,8 @@ class HostBackend final : public Backend {
     if (align == 0) align = 64;
     void* p = nullptr;
     if (inproc_) {
-      MLSLB_ASSERT(posix_memalign(&p, std::max<size_t>(align, 64), round_up(std::max<size_t>(bytes, 1), 64)) == 0,
-                   "host alloc of %zu bytes failed", bytes);
+      p = aligned_host_alloc(bytes, align, ctx_->env.thp_threshold_mb << 20);
+      MLSLB_ASSERT(p != nullptr, "host alloc of %zu bytes failed", bytes);
       std::lock_guard<std::mutex> g(mu_);
       inproc_live_[p] = bytes;
     } else {

@@ -28,6 +28,7 @@
 #include <memory>
 #include <mutex>
 
+#include "heap.hpp"
 #include "log.hpp"
 #include "numeric.hpp"
 #include <functional>
@@ -111,7 +112,20 @@ class Mesh {
     const std::string& key = ctx->boot->key();                  // "master:port"
     const size_t colon = key.rfind(':');
     std::string my_ip = tcp_local_address_towards(key.substr(0, colon), atoi(key.c_str() + colon + 1));
+    // the reference's ways to pick the interface (eplib/server.c:228-330), most explicit first
+    const EnvConfig& ec = ctx->env;
+    if (!ec.iface_name.empty() || ec.iface_idx >= 0) {
+      const std::string a = tcp_address_of_interface(ec.iface_name, ec.iface_idx);
+      MLSLB_ASSERT(!a.empty(), "no IPv4 interface matches MLSL_IFACE_NAME=%s / MLSL_IFACE_IDX=%d", ec.iface_name.c_str(), ec.iface_idx);
+      my_ip = a;
+    }
+    if (!ec.hostname.empty() && ec.hostname_type != 0) {
+      const std::string a = tcp_resolve_to_ip(ec.hostname);
+      MLSLB_ASSERT(!a.empty(), "MLSL_HOSTNAME=%s does not resolve", ec.hostname.c_str());
+      my_ip = a;
+    }
     if (const char* v = getenv("MLSL_NET_ADDR")) my_ip = v;       // explicit address of this rank's interface
+    my_ip_ = my_ip;
     snprintf(mine.ip, sizeof(mine.ip), "%s", my_ip.c_str());
     mine.port = port;
     snprintf(mine.node, sizeof(mine.node), "%s", node_key().c_str());
@@ -235,6 +249,7 @@ class Mesh {
   }
 
   int shm_peer_count() const { return (int)shm_peers_.size(); }
+  const std::string& address() const { return my_ip_; }
 
   void shutdown_all() {
     for (int& fd : fds_)
@@ -609,6 +624,7 @@ class Mesh {
   std::vector<Peer> peers_;
   std::vector<char> blocked_, busy_;   // per peer: socket full (wait for POLLOUT) / already served in this push pass
   std::vector<int> shm_peers_;
+  std::string my_ip_;
   Xchg* cur_ = nullptr;
   // MLSL_NET_EMULATE_GBIT=<x>: pace this rank's egress to x Gbit/s - what a collective does on a slower link than loop-back
   // can be measured on one machine (bench / test knob, off by default)
@@ -633,9 +649,8 @@ class NetBackend final : public Backend {
   explicit NetBackend(RankContext* ctx) : ctx_(ctx) { mesh_.init(ctx); }
   const char* name() const override { return "net"; }
   void* alloc(size_t bytes, size_t align) override {
-    void* p = nullptr;
-    MLSLB_ASSERT(posix_memalign(&p, std::max<size_t>(align ? align : 64, 64), round_up(std::max<size_t>(bytes, 1), 64)) == 0,
-                 "allocation of %zu bytes failed", bytes);
+    void* p = aligned_host_alloc(bytes, align, ctx_->env.thp_threshold_mb << 20);
+    MLSLB_ASSERT(p != nullptr, "allocation of %zu bytes failed", bytes);
     ctx_->ptrcheck.add(p, bytes);
     return p;
   }
@@ -688,7 +703,7 @@ class NetBackend final : public Backend {
   }
   std::string describe() const override {
     return "net backend (TCP mesh, " + std::to_string(ctx_->world) + " ranks, " + std::to_string(mesh_.shm_peer_count()) +
-           " same-node peers over shared memory)";
+           " same-node peers over shared memory" + (mesh_.address().empty() ? "" : ", data address " + mesh_.address()) + ")";
   }
 
  private:
@@ -760,7 +775,9 @@ void NetBackend::execute(CommRequest& r) {
     if (elems) host_reduce(d.dtype, dst, srcs, elems, d.rop, scale);
   };
 
-  // Large reductions travel in chunks: every slice is cut into K pieces with a tag each, a piece is reduced as soon as all
+  // Large reductions travel in chunks (the reference cuts messages of 128 MiB and more into epSize x MLSL_LARGE_MSG_CHUNKS
+  // independent non-blocking requests and raises the chunk count to 128 on Ethernet: reference src/comm_ep.cpp:96-97,649-653,
+  // src/mlsl.cpp:667; here the pieces additionally form a pipeline): every slice is cut into K pieces with a tag each, a piece is reduced as soon as all
   // members' copies of it are there (while the later pieces are still on the wire) and - all-reduce - its result leaves for
   // the other members right away, so the reduction and the second exchange hide behind the first.  Pieces are reduced in
   // member order like whole slices: the values do not depend on the chunking.

@@ -1,6 +1,8 @@
 #include "tcp_control.hpp"
 
 #include <arpa/inet.h>
+#include <ifaddrs.h>
+#include <net/if.h>
 #include <netdb.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
@@ -120,6 +122,31 @@ std::string tcp_local_address_towards(const std::string& addr, int port) {
   }
   close(fd);
   return out;
+}
+
+std::string tcp_address_of_interface(const std::string& prefix, int idx) {
+  ifaddrs* list = nullptr;
+  if (getifaddrs(&list) != 0) return "";
+  std::string out;
+  int seen = 0;
+  for (ifaddrs* ifa = list; ifa; ifa = ifa->ifa_next) {
+    if (!ifa->ifa_addr || ifa->ifa_addr->sa_family != AF_INET || (ifa->ifa_flags & IFF_LOOPBACK) || !(ifa->ifa_flags & IFF_UP)) continue;
+    const bool hit = !prefix.empty() ? strncmp(ifa->ifa_name, prefix.c_str(), prefix.size()) == 0 : seen == idx;
+    ++seen;
+    if (!hit) continue;
+    char buf[64];
+    if (inet_ntop(AF_INET, &((sockaddr_in*)ifa->ifa_addr)->sin_addr, buf, sizeof(buf))) out = buf;
+    break;
+  }
+  freeifaddrs(list);
+  return out;
+}
+
+std::string tcp_resolve_to_ip(const std::string& host) {
+  sockaddr_in sa;
+  char buf[64];
+  if (!resolve(host, 0, &sa) || !inet_ntop(AF_INET, &sa.sin_addr, buf, sizeof(buf))) return "";
+  return buf;
 }
 
 // ---- wire format -----------------------------------------------------------------------------------------------------

@@ -28,6 +28,10 @@ void tcp_send_all(int fd, const void* buf, size_t bytes);                       
 void tcp_recv_all(int fd, void* buf, size_t bytes);
 void tcp_tune(int fd);                                                                  // TCP_NODELAY, big buffers
 std::string tcp_local_address_towards(const std::string& addr, int port);              // my address on the route to addr
+// IPv4 address of the first non-loop-back interface whose name starts with `prefix`, or - empty prefix - of the idx-th one
+// ("" if none); and of a host name / dotted address
+std::string tcp_address_of_interface(const std::string& prefix, int idx);
+std::string tcp_resolve_to_ip(const std::string& host);
 
 class TcpControl {
  public:

@@ -75,6 +75,7 @@ def _pre():
 
 
 _FN = {}     # native entry points by name (resolved once)
+_INIT_COUNT = {}     # (environment handle, thread) -> init() calls not yet matched by finalize()
 
 
 class _Handle:
@@ -515,9 +516,23 @@ class MLSL(_Handle):
             except Exception:  # noqa: BLE001
                 use_cuda = False
             os.environ["MLSL_BACKEND"] = "cuda" if use_cuda else "host"
+        # init / finalize nest like in the reference's binding (reference include/mlsl/mlsl.py:680-703): only the first
+        # init and the matching last finalize reach the library
+        key = (self.handle, threading.get_ident())
+        n = _INIT_COUNT.get(key, 0)
+        if n > 0 and self.is_initialized():
+            _INIT_COUNT[key] = n + 1
+            return
+        _INIT_COUNT[key] = 1              # (a left-over count of a run that never finalized does not nest)
         self._call("mlsl_environment_init", None, None)
 
     def finalize(self):
+        key = (self.handle, threading.get_ident())
+        n = _INIT_COUNT.get(key, 0)
+        if n > 1:
+            _INIT_COUNT[key] = n - 1
+            return
+        _INIT_COUNT.pop(key, None)
         self._call("mlsl_environment_finalize")
 
     def is_initialized(self):
@@ -684,3 +699,30 @@ class InprocWorld:
 
     def __exit__(self, *a):
         self.close()
+
+
+_mlsl_obj = None
+
+
+def close():
+    """Finalize the environment that MLSL_ALLOW_REINIT=1 created at import (reference include/mlsl/mlsl.py:1216-1225)."""
+    global _mlsl_obj
+    if _mlsl_obj is not None:
+        n = _INIT_COUNT.get((_mlsl_obj.handle, threading.get_ident()), 0)
+        if n != 1:
+            raise RuntimeError("Unexpected reference count for the MLSL object: %d" % n)
+        _mlsl_obj.finalize()
+        _mlsl_obj = None
+
+
+def _auto_init():
+    # MLSL_ALLOW_REINIT=1: the module owns one initialisation for the life of the process, so that user code may call
+    # init() / finalize() any number of times (reference include/mlsl/mlsl.py:1227-1229)
+    import os
+    global _mlsl_obj
+    if os.getenv("MLSL_ALLOW_REINIT") == "1" and _mlsl_obj is None:
+        _mlsl_obj = MLSL()
+        _mlsl_obj.init()
+
+
+_auto_init()

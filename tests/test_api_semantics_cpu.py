@@ -97,7 +97,11 @@ def test_error_paths_raise():
             except MLSLError as ex:
                 assert "assertion" in str(ex).lower() or "null" in str(ex).lower(), str(ex)
 
-        expect(lambda: e.init(), "double init")
+        # the library itself refuses a second Init; the Python object counts init() / finalize() like the reference's binding
+        expect(lambda: e._call("mlsl_environment_init", None, None), "double init")
+        e.init()
+        e.finalize()
+        assert e.is_initialized()
         sess = e.create_session()
         expect(lambda: sess.set_global_minibatch_size(0), "zero minibatch")
         sess.set_global_minibatch_size(8)
@@ -603,3 +607,45 @@ def test_tuning_knobs_roundtrip_and_unknown_key():
 
     for before, by_env, after, unknown, pipe in run_ranks(2, body, env={"MLSL_PIPE_BUFS": "6"}):
         assert (before, by_env, after, unknown, pipe) == (1024, 256, 1024, True, 6)
+
+
+def _py(code, env):
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r)\n%s" % (ROOT, code)], env=e, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-3000:]
+    return r.stdout
+
+
+def test_reference_environment_knobs_are_recognised():
+    """Every variable of the reference's table is parsed: the ones about server processes / MPI have nothing to
+    configure here and are listed as such at INFO, MLSL_DYNAMIC_SERVER=disable means no progress threads, EPLIB_UUID names
+    the job, MLSL_THP_THRESHOLD_MB makes big host allocations 2 MiB aligned."""
+    out = _py("import os, torch, mlsl_b200 as mlsl\n"
+              "env = mlsl.init()\n"
+              "p = env.alloc(6 << 20, 64); q = env.alloc(1 << 20, 64)\n"
+              "print('ALIGN', p % (2 << 20), q % 64)\n"
+              "x = torch.ones(8); mlsl.allreduce(x); print('SUM', float(x.sum()))\n"
+              "env.free(p); env.free(q); mlsl.finalize()\n",
+              {"MLSL_BACKEND": "host", "MLSL_LOG_LEVEL": "1", "MLSL_DYNAMIC_SERVER": "disable", "MLSL_COPY_THREADS": "4",
+               "MLSL_SERVER_PREFIX": "numactl", "MLSL_MPI_VERSION_CHECK": "0", "MLSL_THP_THRESHOLD_MB": "4", "EPLIB_UUID": "job-77",
+               "MLSL_INPROC_RANKS": "0", "MLSL_NUM_SERVERS": "2"})
+    assert "MLSL_DYNAMIC_SERVER=disable" in out and "MLSL_THP_THRESHOLD_MB=4" in out, out[-2000:]
+    assert "MLSL_NUM_SERVERS=0" in out, out[-2000:]                   # "disable" wins over the server count
+    line = [l for l in out.splitlines() if "not applicable" in l]
+    assert line and all(k in line[0] for k in ("MLSL_COPY_THREADS", "MLSL_SERVER_PREFIX", "MLSL_MPI_VERSION_CHECK")), out[-2000:]
+    assert "SUM 8.0" in out and "ALIGN 0 0" in out, out[-2000:]
+
+
+def test_python_init_finalize_nest_and_allow_reinit():
+    """The reference's Python module counts init() / finalize() calls and, with MLSL_ALLOW_REINIT=1, holds one initialisation
+    of its own until close() (reference include/mlsl/mlsl.py:680-703,1216-1229)."""
+    code = ("import os\nfrom mlsl_b200 import api\n"
+            "e = api.MLSL(); print('AUTO', e.is_initialized())\n"
+            "e.init(); e.init(); e.finalize(); print('NESTED', e.is_initialized())\n"
+            "e.finalize(); print('OUTER', e.is_initialized())\n"
+            "api.close(); print('CLOSED', e.is_initialized())\n")
+    out = _py(code, {"MLSL_BACKEND": "host", "MLSL_ALLOW_REINIT": "1"})
+    assert "AUTO True" in out and "NESTED True" in out and "OUTER True" in out and "CLOSED False" in out, out
+    out = _py(code, {"MLSL_BACKEND": "host", "MLSL_ALLOW_REINIT": "0"})
+    assert "AUTO False" in out and "NESTED True" in out and "OUTER False" in out and "CLOSED False" in out, out

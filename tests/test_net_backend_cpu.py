@@ -60,6 +60,22 @@ def test_reductions_in_pieces_are_exact(nnodes, per_node):
     assert out.count("NET CHUNK OK") == nnodes * per_node
 
 
+def test_interface_selection_like_the_reference():
+    """MLSL_IFACE_NAME (prefix) / MLSL_IFACE_IDX pick the interface of the data connections (reference eplib/server.c:228-330)."""
+    psutil = pytest.importorskip("psutil")
+    import socket
+    nics = [(n, a.address) for n, addrs in psutil.net_if_addrs().items() for a in addrs
+            if a.family == socket.AF_INET and not a.address.startswith("127.")]
+    if not nics:
+        pytest.skip("no IPv4 interface besides loop-back")
+    name, ip = nics[0]
+    code = "import sys; sys.path.insert(0, %r); import mlsl_b200 as mlsl; e = mlsl.init(); print(e.describe_backend()); mlsl.barrier(); mlsl.finalize()" % ROOT
+    rcs, out = _launch(2, 1, [sys.executable, "-c", code], extra_env={"MLSL_IFACE_NAME": name[:3]})
+    assert all(rc == 0 for rc in rcs) and out.count("data address " + ip) == 2, out[-2000:]
+    rcs, out = _launch(2, 1, [sys.executable, "-c", code], extra_env={"MLSL_IFACE_NAME": "nosuchnic"}, timeout=100)
+    assert any(rc != 0 for rc in rcs) and "no IPv4 interface matches" in out, out[-2000:]
+
+
 def test_a_dying_rank_fails_the_whole_multi_node_job_fast():
     """One rank exits without finalizing: its control connection drops, rank 0's server poisons everyone, the surviving
     ranks leave their collective with an error instead of waiting for the watchdog."""
