@@ -434,3 +434,28 @@ def test_compressed_allreduce_formats(mx):
             far[k:k + 32] = False
         assert err[far].max() < 0.5, err[far].max()              # ~N(0, 2) sums quantised at their own scale
 
+
+
+@pytest.mark.parametrize("world", [16, 48])
+def test_many_ranks_world_and_subgroups(world):
+    """Well past the eight ranks of one GPU node: the host backend serves up to 64 ranks (kMaxHostRanks) - world-wide collectives
+    and the data / model groups of a (world / 4) x 4 distribution."""
+    def body(r, mlsl):
+        W = mlsl.world_size()
+        x = torch.full((1000,), float(r + 1))
+        mlsl.allreduce(x)
+        a = mlsl.alltoall(torch.arange(W * 3, dtype=torch.float32) + 1000 * r)
+        g = mlsl.allgather(torch.tensor([float(r)]))
+        e = mlsl.env()
+        d = e.create_distribution(W // 4, 4)
+        y = torch.ones(64)
+        mlsl.allreduce(y, group="model", distribution=d)
+        z = torch.ones(64)
+        mlsl.allreduce(z, group="data", distribution=d)
+        e.delete_distribution(d)
+        return float(x[0]), a.tolist(), float(g.sum()), float(y[0]), float(z[0])
+
+    for r, (x0, a, gsum, y0, z0) in enumerate(run_ranks(world, body)):
+        assert x0 == world * (world + 1) / 2 and gsum == world * (world - 1) / 2
+        assert a == [1000.0 * q + 3 * r + k for q in range(world) for k in range(3)]
+        assert (y0, z0) == (4.0, world / 4)
