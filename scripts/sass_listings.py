@@ -23,7 +23,8 @@ WANT = [
     ("k_barrier", r"k_barrier\("),
     ("k_pack_blocks", r"k_pack_blocks\("),
     ("k_scale_copy_f32", r"k_scale_copy<float>"),
-    ("k_allreduce_quant", r"k_allreduce_quant\("),
+    ("k_allreduce_quant", r"k_allreduce_quant<false>"),
+    ("k_allreduce_quant_mx", r"k_allreduce_quant<true>"),
     ("k_fused_update_f32_bf16", r"k_fused_update<float, __nv_bfloat16>"),
     ("k_fused_update_f32_f32", r"k_fused_update<float, float>"),
     ("k_gemm_rs", r"k_gemm_rs[<(]"),
@@ -44,7 +45,7 @@ def main():
                 with open(os.path.join(OUT, out + ".sass"), "w") as f:
                     text = "\n".join(re.sub(r"\s*/\* 0x[0-9a-f]{16} \*/\s*$", "", ln) for ln in body.split("\n\t\t.....")[0].splitlines() if ln.strip())
                     f.write("// %s\n// sm_100a, cuobjdump -sass mlsl_b200/lib/libmlsl_b200.so (encodings stripped)\n%s\n" % (name, text))
-                ops = re.findall(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", body)
+                ops = re.findall(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", body)
                 key = sorted({o.split(".")[0] for o in ops if o.startswith(("UTC", "LDTM", "UTMA", "UBLKCP", "LDGMC", "STGMC", "SYNCS", "UCGABAR"))})
                 print("%-36s %6d instructions  %s" % (out, len(ops), " ".join(key)))
                 break
