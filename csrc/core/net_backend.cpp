@@ -1033,13 +1033,19 @@ void NetBackend::execute(CommRequest& r) {
         }
       go(0);
       std::vector<float> gsum(n);
-      for (size_t i = 0; i < n; ++i) {
-        float a = 0.f;
-        for (int p = 0; p < P; ++p) {
-          const char* sp = (p == me ? S + (size_t)me * n * dt : tmp + (size_t)p * n * dt) + i * dt;
-          a += d.dtype == DType::F32 ? *(const float*)sp : bf16_to_f32(*(const uint16_t*)sp);
+      if (d.dtype == DType::F32) {            // the vectorised reduction (same member order as the loop below)
+        std::vector<const void*> srcs(P);
+        for (int p = 0; p < P; ++p) srcs[p] = p == me ? (const void*)(S + (size_t)me * n * dt) : (const void*)(tmp + (size_t)p * n * dt);
+        if (n) host_reduce(DType::F32, gsum.data(), srcs, n, RedOp::SUM, d.scale);
+      } else {
+        for (size_t i = 0; i < n; ++i) {
+          float a = 0.f;
+          for (int p = 0; p < P; ++p) {
+            const char* sp = (p == me ? S + (size_t)me * n * dt : tmp + (size_t)p * n * dt) + i * dt;
+            a += bf16_to_f32(*(const uint16_t*)sp);
+          }
+          gsum[i] = a * d.scale;
         }
-        gsum[i] = a * d.scale;
       }
       char* param = (char*)d.fused.param;
       host_optimizer_step(d.fused, pdt, param + (size_t)me * n * pdts, gsum.data(), n);
