@@ -41,11 +41,11 @@ TOOLS := bin/mlslrun
 ifndef NO_CUDA
 CUDA_EXAMPLES := bin/mlsl_example_cuda
 endif
-TESTS := $(CUDA_EXAMPLES) bin/libmlsl_quant_sample.so bin/quant_codec_check bin/mlsl_functional_test bin/cmlsl_smoke_test bin/cmlsl_functional_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
+TESTS := $(CUDA_EXAMPLES) bin/libmlsl_quant_sample.so bin/quant_codec_check bin/mlsl_functional_test bin/cmlsl_smoke_test bin/cmlsl_functional_test bin/cmlsl_eplib_test bin/mlsl_sample bin/mlsl_example bin/mlsl_allreduce_bench
 
 all: $(LIB) $(TOOLS) $(TESTS)
 
-$(BUILD)/%.o: csrc/%.cpp $(wildcard csrc/core/*.hpp) include/mlsl.hpp include/mlsl.h
+$(BUILD)/%.o: csrc/%.cpp $(wildcard csrc/core/*.hpp) include/mlsl.hpp include/mlsl.h include/eplib.h
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
@@ -99,7 +99,7 @@ install: all
 	cp $(LIB) $(PREFIX)/intel64/lib/
 	ln -sf libmlsl_b200.so $(PREFIX)/intel64/lib/libmlsl.so   # drop-in name: -lmlsl and the reference's Python binding find it
 	cp bin/mlslrun bin/libmlsl_quant_sample.so $(PREFIX)/intel64/bin/
-	cp include/mlsl.hpp include/mlsl.h $(PREFIX)/intel64/include/
+	cp include/mlsl.hpp include/mlsl.h include/eplib.h $(PREFIX)/intel64/include/
 	cp -r mlsl_b200 $(PREFIX)/python/ && rm -rf $(PREFIX)/python/mlsl_b200/__pycache__ $(PREFIX)/python/mlsl_b200/*/__pycache__
 	cp README.md DESIGN.md docs/*.md $(PREFIX)/doc/
 	cp examples/*.py csrc/tests/mlsl_example.cpp csrc/tests/mlsl_sample.cpp csrc/tests/mlsl_functional_test.cpp \

@@ -21,7 +21,7 @@ for g in 1 2 4; do for du in 0 1; do
   run "c   groups=$g dist_update=$du" bin/mlslrun -n 4 --timeout 120 bin/cmlsl_functional_test $g $du
   run "py  groups=$g dist_update=$du" bin/mlslrun -n 4 --timeout 120 python examples/mlsl_test.py $g $du
 done; done
-run "c   smoke + samples" bash -c "bin/mlslrun -n 3 bin/cmlsl_smoke_test && bin/mlslrun -n 2 bin/mlsl_sample && bin/mlslrun -n 4 bin/mlsl_example"
+run "c   smoke + samples" bash -c "bin/mlslrun -n 3 bin/cmlsl_smoke_test && bin/mlslrun -n 2 bin/mlsl_sample && bin/mlslrun -n 4 bin/mlsl_example && bin/mlslrun -n 2 bin/cmlsl_eplib_test /tmp/mlsl_matrix_eplib.bin"
 port=$((20000 + RANDOM % 20000))
 for g in 1 2 4; do
   run "net groups=$g dist_update=1 (2 nodes x 2 ranks over TCP)" bash -c "unset MLSL_BACKEND; (bin/mlslrun -n 2 --nnodes 2 --node-rank 1 --master-addr 127.0.0.1 --master-port $port --timeout 120 bin/mlsl_functional_test $g 1 > /dev/null 2>&1 &); bin/mlslrun -n 2 --nnodes 2 --node-rank 0 --master-addr 127.0.0.1 --master-port $port --timeout 120 bin/mlsl_functional_test $g 1"

@@ -337,6 +337,16 @@ def test_c_binding_and_sample_multiprocess():
         assert res.returncode == 0 and "FAILED" not in res.stdout, res.stdout[-2000:]
 
 
+@pytest.mark.parametrize("n,servers", [(1, "0"), (3, "0"), (4, "2")])
+def test_eplib_entry_points_from_c(n, servers, tmp_path):
+    """include/eplib.h: the reference's stand-alone endpoint library surface (init / teardown, the allocation family,
+    EPLIB_memory_is_shmem, suspend / execute, file reads on a progress thread) on this runtime (reference eplib/eplib.h)."""
+    env = dict(os.environ, MLSL_BACKEND="host", MLSL_HEAP_SIZE_GB="0.25", MLSL_NUM_SERVERS=servers)
+    res = subprocess.run([_bin("mlslrun"), "-n", str(n), "--timeout", "60", _bin("cmlsl_eplib_test"), str(tmp_path / "blob.bin")],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=120)
+    assert res.returncode == 0 and res.stdout.count("PASSED") == n and "FAILED" not in res.stdout, res.stdout[-2000:]
+
+
 def test_poison_makes_peers_fail_fast():
     """A rank that dies with a fatal signal poisons the shared control block: the survivor errors out at once instead
     of waiting for the watchdog (the reference can only _exit the failing process)."""
