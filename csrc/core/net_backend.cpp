@@ -332,10 +332,12 @@ class Mesh {
         if (P.expect.empty()) continue;
         shm_busy = true;
         if (P.rx->readable() && !(P.held && !P.expect.count(P.hdr.tag))) {
-          const size_t k = drain(p);
-          x.pending_in -= k;
-          if (k) idle = 0;
+          x.pending_in -= drain(p);
         }
+      }
+      if (io_progress_) {          // bytes moved through a ring (or a socket) since the last round: not idle
+        io_progress_ = false;
+        idle = 0;
       }
       if (x.fresh) continue;
       if (!x.pending_in && !x.pending_out) break;
@@ -489,11 +491,13 @@ class Mesh {
         const size_t k = ring->write((const char*)&h + hdr_sent, sizeof(WireHdr) - hdr_sent);
         if (!k) return;
         hdr_sent += k;
+        io_progress_ = true;
       }
       while (sent < h.bytes) {
         const size_t k = ring->write(ptr + sent, h.bytes - sent);
         if (!k) return;
         sent += k;
+        io_progress_ = true;
       }
       return;
     }
@@ -586,6 +590,7 @@ class Mesh {
         if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return completed;
         if (n < 0 && errno == EINTR) continue;
         MLSLB_ASSERT(n > 0, "rank %d closed its connection in the middle of a message", peer);
+        io_progress_ = true;
         P.got += (size_t)n;
       }
       // message complete
@@ -630,7 +635,7 @@ class Mesh {
   // can be measured on one machine (bench / test knob, off by default)
   double rate_Bps_ = getenv("MLSL_NET_EMULATE_GBIT") ? atof(getenv("MLSL_NET_EMULATE_GBIT")) * 1e9 / 8 : 0.0, tokens_ = 0.0;
   uint64_t last_refill_ns_ = 0;
-  bool paced_ = false;
+  bool paced_ = false, io_progress_ = false;
   size_t quantum_left_ = 0;
   std::mutex mu_;
 };
