@@ -341,11 +341,11 @@ class Mesh {
       }
       if (x.fresh) continue;
       if (!x.pending_in && !x.pending_out) break;
-      int timeout_ms = x.paced ? (tokens_ < 1.0 ? 1 : 0) : 100;
+      long timeout_us = x.paced ? (tokens_ < 1.0 ? 1000 : 0) : 100000;
       if (shm_busy) {
-        timeout_ms = 0;
+        timeout_us = 0;
         if (++idle > 64) sched_yield();
-        if (idle > 20000) timeout_ms = 1;      // a slow peer: stop burning the core
+        if (idle > 20000) timeout_us = 100;    // a slow peer: stop burning the core (the sockets still wake us at once)
       }
       pfds.clear();
       // always listen on every connection: a peer may already be sending for a later collective
@@ -356,7 +356,8 @@ class Mesh {
           if (P.rx) continue;                                           // (its socket is silent after the set-up)
           pfds.push_back(pollfd{fds_[p], (short)((idle_hold ? 0 : POLLIN) | (blocked_[p] ? POLLOUT : 0)), 0});
         }
-      int rc = poll(pfds.data(), (nfds_t)pfds.size(), timeout_ms);
+      timespec ts{timeout_us / 1000000, (timeout_us % 1000000) * 1000};
+      int rc = ppoll(pfds.data(), (nfds_t)pfds.size(), &ts, nullptr);
       if (rc < 0 && errno != EINTR) MLSLB_ASSERT(false, "poll(): %s", strerror(errno));
       if (ctx_->boot->poisoned()) MLSLB_ASSERT(false, "job poisoned by rank %d during a network collective", (int)ctx_->boot->poisoned() - 1);
       const int wd = ctx_->env.watchdog_sec;
