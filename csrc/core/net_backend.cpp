@@ -131,6 +131,16 @@ class Mesh {
     snprintf(mine.node, sizeof(mine.node), "%s", node_key().c_str());
     std::vector<Addr> all(world_);
     ctx->boot->allgather(&mine, all.data(), sizeof(Addr));
+    node_of_.assign(world_, 0);                                 // node index of every rank (order of first appearance)
+    {
+      std::vector<std::string> seen;
+      for (int p = 0; p < world_; ++p) {
+        all[p].node[sizeof(all[p].node) - 1] = 0;
+        auto it = std::find(seen.begin(), seen.end(), std::string(all[p].node));
+        node_of_[p] = (int)(it - seen.begin());
+        if (it == seen.end()) seen.push_back(all[p].node);
+      }
+    }
     // connect to every lower rank (the listen backlog completes the handshake even before the peer accepts) ...
     for (int p = 0; p < rank_; ++p) {
       int fd = tcp_connect_retry(all[p].ip, all[p].port, 60);
@@ -249,6 +259,7 @@ class Mesh {
   }
 
   int shm_peer_count() const { return (int)shm_peers_.size(); }
+  int node_of(int rank) const { return node_of_.empty() ? 0 : node_of_[rank]; }
   const std::string& address() const { return my_ip_; }
 
   void shutdown_all() {
@@ -629,7 +640,7 @@ class Mesh {
   std::vector<int> fds_;
   std::vector<Peer> peers_;
   std::vector<char> blocked_, busy_;   // per peer: socket full (wait for POLLOUT) / already served in this push pass
-  std::vector<int> shm_peers_;
+  std::vector<int> shm_peers_, node_of_;
   std::string my_ip_;
   Xchg* cur_ = nullptr;
   // MLSL_NET_EMULATE_GBIT=<x>: pace this rank's egress to x Gbit/s - what a collective does on a slower link than loop-back
@@ -717,6 +728,7 @@ class NetBackend final : public Backend {
   Mesh mesh_;
   void execute(CommRequest& r);
   void quantized_allreduce(CommRequest& r, const ProcessGroup& g);
+  bool hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
 };
 
 // Receive space for the slices of a reduction: grow-only and uninitialised (a fresh std::vector would zero-fill and
@@ -985,6 +997,7 @@ void NetBackend::execute(CommRequest& r) {
         break;
       }
       static const size_t one_shot = getenv("MLSL_NET_ONESHOT_KB") ? (size_t)atol(getenv("MLSL_NET_ONESHOT_KB")) << 10 : kOneShotBytes;
+      if (hierarchical_allreduce(r, g, tag)) break;
       if (n * dt <= one_shot) {
         // small message: everybody sends the whole vector to everybody and reduces locally in member order (bitwise
         // identical everywhere) - one exchange instead of two
@@ -1068,6 +1081,113 @@ void NetBackend::execute(CommRequest& r) {
       MLSLB_ASSERT(false, "%s is a device-only fused op", opkind_name(d.kind));
       break;
   }
+}
+
+// Two-level all-reduce for groups that have the same number L > 1 of members on each of N > 1 nodes: reduce-scatter among
+// the members of a node (shared-memory rings), all-reduce of the 1/L shard among the members with the same local index
+// (one per node, over the wire), all-gather inside the node.  A rank then sends 2 (n / L)(N - 1) / N bytes between nodes
+// instead of the 2 n (P - L) / P of the flat exchange - L times less on the link that is the slow one.  (The reference
+// leaves this to the MPI library underneath; Intel MPI's shm + fabric collectives are topology aware in the same way.)
+// Every element is reduced along one fixed chain (node members in member order, then nodes in order) by exactly one rank
+// and then copied, so all ranks end up with identical bits.  Returns false when the group / size does not qualify; the
+// decision only uses facts every member knows (who runs where, the count), so all members decide alike.
+bool NetBackend::hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag) {
+  static const long hier_kb = getenv("MLSL_NET_HIER_KB") ? atol(getenv("MLSL_NET_HIER_KB")) : 1024;   // < 0: never
+  const CommDesc& d = r.desc;
+  const size_t dt = dtype_size(d.dtype), n = d.count;
+  const int P = g.size(), me = g.idx;
+  if (hier_kb < 0 || n * dt < (size_t)hier_kb << 10) return false;
+  // who sits where
+  std::vector<int> nodes;                     // distinct node indices in member order
+  std::vector<std::vector<int>> on_node;      // member positions per node
+  for (int p = 0; p < P; ++p) {
+    const int nd = mesh_.node_of(g.members[p]);
+    size_t k = std::find(nodes.begin(), nodes.end(), nd) - nodes.begin();
+    if (k == nodes.size()) {
+      nodes.push_back(nd);
+      on_node.emplace_back();
+    }
+    on_node[k].push_back(p);
+  }
+  const int N = (int)nodes.size(), L = (int)on_node[0].size();
+  if (N < 2 || L < 2) return false;
+  for (auto& v : on_node)
+    if ((int)v.size() != L) return false;
+  if (n < (size_t)L * N) return false;
+  int my_node = 0, li = 0;
+  for (int k = 0; k < N; ++k)
+    for (int j = 0; j < L; ++j)
+      if (on_node[k][j] == me) {
+        my_node = k;
+        li = j;
+      }
+  char* S = (char*)r.send;
+  char* R = (char*)r.recv;
+  auto peer = [&](int p) { return g.members[p]; };
+  const size_t per_l = ceil_div(n, (size_t)L);                       // slice of local member j: [lo_l(j), lo_l(j) + len_l(j))
+  auto lo_l = [&](int j) { return std::min(n, (size_t)j * per_l); };
+  auto len_l = [&](int j) { return std::min(n, lo_l(j) + per_l) - lo_l(j); };
+  const size_t mine = len_l(li);
+  const size_t per_n = ceil_div(per_l, (size_t)N);                   // sub-slice of node k inside a shard
+  auto lo_n = [&](size_t shard_len, int k) { return std::min(shard_len, (size_t)k * per_n); };
+  auto len_n = [&](size_t shard_len, int k) { return std::min(shard_len, lo_n(shard_len, k) + per_n) - lo_n(shard_len, k); };
+  char* scratch = net_scratch(((size_t)L * per_l + per_l + (size_t)N * per_n) * dt);
+  char* tmpA = scratch;                                              // L slices received inside the node
+  char* shard = scratch + (size_t)L * per_l * dt;                    // my 1/L of the node's sum, then of the total
+  char* tmpB = shard + per_l * dt;                                   // N sub-slices received from the other nodes
+  std::vector<Seg> snd, rcv;
+  std::vector<const void*> srcs;
+  // A: reduce-scatter inside the node
+  for (int j = 0; j < L; ++j) {
+    if (j == li) continue;
+    const int p = on_node[my_node][j];
+    if (len_l(j)) snd.push_back(Seg{peer(p), S + lo_l(j) * dt, len_l(j) * dt});
+    if (mine) rcv.push_back(Seg{peer(p), tmpA + (size_t)j * per_l * dt, mine * dt});
+  }
+  mesh_.exchange(tag(200), snd, rcv);
+  snd.clear();
+  rcv.clear();
+  if (mine) {
+    srcs.assign(L, nullptr);
+    for (int j = 0; j < L; ++j) srcs[j] = j == li ? (const void*)(S + lo_l(li) * dt) : (const void*)(tmpA + (size_t)j * per_l * dt);
+    host_reduce(d.dtype, shard, srcs, mine, d.rop, 1.0f);
+  }
+  // B: all-reduce of the shard among the members with my local index, one per node: reduce-scatter + all-gather
+  const size_t sub = len_n(mine, my_node);
+  for (int k = 0; k < N; ++k) {
+    if (k == my_node) continue;
+    const int p = on_node[k][li];
+    if (len_n(mine, k)) snd.push_back(Seg{peer(p), shard + lo_n(mine, k) * dt, len_n(mine, k) * dt});
+    if (sub) rcv.push_back(Seg{peer(p), tmpB + (size_t)k * per_n * dt, sub * dt});
+  }
+  mesh_.exchange(tag(201), snd, rcv);
+  snd.clear();
+  rcv.clear();
+  if (sub) {
+    srcs.assign(N, nullptr);
+    for (int k = 0; k < N; ++k)
+      srcs[k] = k == my_node ? (const void*)(shard + lo_n(mine, my_node) * dt) : (const void*)(tmpB + (size_t)k * per_n * dt);
+    host_reduce(d.dtype, shard + lo_n(mine, my_node) * dt, srcs, sub, d.rop, d.scale);     // (element-wise: in place is fine)
+  }
+  for (int k = 0; k < N; ++k) {
+    if (k == my_node) continue;
+    const int p = on_node[k][li];
+    if (sub) snd.push_back(Seg{peer(p), shard + lo_n(mine, my_node) * dt, sub * dt});
+    if (len_n(mine, k)) rcv.push_back(Seg{peer(p), shard + lo_n(mine, k) * dt, len_n(mine, k) * dt});
+  }
+  mesh_.exchange(tag(202), snd, rcv);
+  snd.clear();
+  rcv.clear();
+  // C: all-gather inside the node, straight into the result
+  if (mine) memcpy(R + lo_l(li) * dt, shard, mine * dt);
+  for (int j = 0; j < L; ++j) {
+    if (j == li) continue;
+    const int p = on_node[my_node][j];
+    if (mine) snd.push_back(Seg{peer(p), shard, mine * dt});
+    if (len_l(j)) rcv.push_back(Seg{peer(p), R + lo_l(j) * dt, len_l(j) * dt});
+  }
+  mesh_.exchange(tag(203), snd, rcv);
+  return true;
 }
 
 // Quantised all-reduce (CT_QUANTIZATION) between nodes - where the reference's gradient compression matters most: the same

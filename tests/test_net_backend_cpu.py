@@ -49,13 +49,24 @@ def test_same_node_ranks_talk_through_shared_memory(shm, ring_kb, expect):
     assert out.count("NET CHUNK OK") == 4 and out.count(expect) == 4, out[-3000:]
 
 
+@pytest.mark.parametrize("nnodes,per_node,hier_kb", [(2, 2, "0"), (2, 3, "0"), (3, 2, "16"), (2, 2, "-1")])
+def test_two_level_allreduce_is_exact(nnodes, per_node, hier_kb):
+    """Groups with the same number of members on every node reduce inside the node first (shared memory), exchange 1/L of the
+    message between the nodes and gather inside the node again; MLSL_NET_HIER_KB = smallest message that goes that way
+    (-1: never).  Same exact results for every size / dtype / in place or not, also with 3 ranks per node or 3 nodes."""
+    rcs, out = _launch(nnodes, per_node, [sys.executable, os.path.join(ROOT, "tests", "net_chunk_worker.py")],
+                       extra_env={"MLSL_NET_HIER_KB": hier_kb})
+    assert all(rc == 0 for rc in rcs), out[-3000:]
+    assert out.count("NET CHUNK OK") == nnodes * per_node
+
+
 @pytest.mark.parametrize("nnodes,per_node", [(2, 2), (4, 1), (2, 1)])
 def test_reductions_in_pieces_are_exact(nnodes, per_node):
     """Large reductions are cut into pieces that are reduced (and, all-reduce, passed on) while the rest is still on the wire;
     4 KiB pieces here, so that every size class takes that path: in place, send -> recv, reduce-scatter onto slice 0 of its
     own input."""
     rcs, out = _launch(nnodes, per_node, [sys.executable, os.path.join(ROOT, "tests", "net_chunk_worker.py")],
-                       extra_env={"MLSL_NET_CHUNK_KB": "4"})
+                       extra_env={"MLSL_NET_CHUNK_KB": "4", "MLSL_NET_HIER_KB": "-1"})
     assert all(rc == 0 for rc in rcs), out[-3000:]
     assert out.count("NET CHUNK OK") == nnodes * per_node
 
