@@ -729,6 +729,37 @@ class NetBackend final : public Backend {
   void execute(CommRequest& r);
   void quantized_allreduce(CommRequest& r, const ProcessGroup& g);
   bool hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
+  bool hierarchical_gather_scatter(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
+  // Where the members of a group run: N nodes with L members each (member positions per node, in member order), and this
+  // rank's place.  false unless the group is regular (same L > 1 on each of N > 1 nodes).
+  struct NodeMap {
+    int N = 0, L = 0, my_node = 0, li = 0;
+    std::vector<std::vector<int>> on_node;
+  };
+  bool node_map(const ProcessGroup& g, NodeMap& m) const {
+    std::vector<int> nodes;
+    for (int p = 0; p < g.size(); ++p) {
+      const int nd = mesh_.node_of(g.members[p]);
+      size_t k = std::find(nodes.begin(), nodes.end(), nd) - nodes.begin();
+      if (k == nodes.size()) {
+        nodes.push_back(nd);
+        m.on_node.emplace_back();
+      }
+      m.on_node[k].push_back(p);
+    }
+    m.N = (int)nodes.size();
+    m.L = (int)m.on_node[0].size();
+    if (m.N < 2 || m.L < 2) return false;
+    for (auto& v : m.on_node)
+      if ((int)v.size() != m.L) return false;
+    for (int k = 0; k < m.N; ++k)
+      for (int j = 0; j < m.L; ++j)
+        if (m.on_node[k][j] == g.idx) {
+          m.my_node = k;
+          m.li = j;
+        }
+    return true;
+  }
 };
 
 // Receive space for the slices of a reduction: grow-only and uninitialised (a fresh std::vector would zero-fill and
@@ -899,6 +930,7 @@ void NetBackend::execute(CommRequest& r) {
     }
     case OpKind::ALLGATHER:
     case OpKind::ALLGATHERV: {
+      if (d.kind == OpKind::ALLGATHER && hierarchical_gather_scatter(r, g, tag)) break;
       std::vector<size_t> cnt(P, n), off(P, 0);
       if (d.kind == OpKind::ALLGATHERV) cnt.assign(d.recv_counts.begin(), d.recv_counts.end());
       for (int p = 1; p < P; ++p) off[p] = off[p - 1] + cnt[p - 1];
@@ -957,6 +989,7 @@ void NetBackend::execute(CommRequest& r) {
       go(0);
       break;
     case OpKind::REDUCE_SCATTER: {
+      if (hierarchical_gather_scatter(r, g, tag)) break;
       if (const size_t ce = chunk_elems(n)) {      // (the choice must not depend on the rank or on its buffers)
         // in place the result lands on slice 0 of the send buffer, which a rank other than member 0 still has to send: only
         // an output on the own slice or outside the send buffer can be written while the exchange runs - else it is staged
@@ -1095,32 +1128,11 @@ bool NetBackend::hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, c
   static const long hier_kb = getenv("MLSL_NET_HIER_KB") ? atol(getenv("MLSL_NET_HIER_KB")) : 1024;   // < 0: never
   const CommDesc& d = r.desc;
   const size_t dt = dtype_size(d.dtype), n = d.count;
-  const int P = g.size(), me = g.idx;
   if (hier_kb < 0 || n * dt < (size_t)hier_kb << 10) return false;
-  // who sits where
-  std::vector<int> nodes;                     // distinct node indices in member order
-  std::vector<std::vector<int>> on_node;      // member positions per node
-  for (int p = 0; p < P; ++p) {
-    const int nd = mesh_.node_of(g.members[p]);
-    size_t k = std::find(nodes.begin(), nodes.end(), nd) - nodes.begin();
-    if (k == nodes.size()) {
-      nodes.push_back(nd);
-      on_node.emplace_back();
-    }
-    on_node[k].push_back(p);
-  }
-  const int N = (int)nodes.size(), L = (int)on_node[0].size();
-  if (N < 2 || L < 2) return false;
-  for (auto& v : on_node)
-    if ((int)v.size() != L) return false;
-  if (n < (size_t)L * N) return false;
-  int my_node = 0, li = 0;
-  for (int k = 0; k < N; ++k)
-    for (int j = 0; j < L; ++j)
-      if (on_node[k][j] == me) {
-        my_node = k;
-        li = j;
-      }
+  NodeMap nm;
+  if (!node_map(g, nm) || n < (size_t)nm.L * nm.N) return false;
+  const int N = nm.N, L = nm.L, my_node = nm.my_node, li = nm.li;
+  const std::vector<std::vector<int>>& on_node = nm.on_node;
   char* S = (char*)r.send;
   char* R = (char*)r.recv;
   auto peer = [&](int p) { return g.members[p]; };
@@ -1188,6 +1200,89 @@ bool NetBackend::hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, c
   }
   mesh_.exchange(tag(203), snd, rcv);
   return true;
+}
+
+// The same two levels for all-gather and reduce-scatter (the pair behind the distributed weight update): between nodes only
+// the members with the same local index talk, (N - 1) n bytes per rank instead of (P - L) n; the node-local step moves the N
+// blocks every member holds / needs through shared memory (packed into one message per local peer).
+bool NetBackend::hierarchical_gather_scatter(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag) {
+  static const long hier_kb = getenv("MLSL_NET_HIER_KB") ? atol(getenv("MLSL_NET_HIER_KB")) : 1024;
+  const CommDesc& d = r.desc;
+  const size_t dt = dtype_size(d.dtype), n = d.count;      // n = elements of ONE block (per member)
+  const int P = g.size();
+  if (hier_kb < 0 || (size_t)P * n * dt < (size_t)hier_kb << 10 || n == 0) return false;
+  NodeMap nm;
+  if (!node_map(g, nm)) return false;
+  const int N = nm.N, L = nm.L, my_node = nm.my_node, li = nm.li;
+  char* S = (char*)r.send;
+  char* R = (char*)r.recv;
+  auto peer = [&](int p) { return g.members[p]; };
+  const size_t blk = n * dt;
+  std::vector<Seg> snd, rcv;
+  if (d.kind == OpKind::ALLGATHER) {
+    // between nodes: my block goes to the members with my local index, theirs arrive at their places in R
+    if (R + (size_t)g.idx * blk != S) memmove(R + (size_t)g.idx * blk, S, blk);
+    for (int k = 0; k < N; ++k) {
+      if (k == my_node) continue;
+      const int p = nm.on_node[k][li];
+      snd.push_back(Seg{peer(p), R + (size_t)g.idx * blk, blk});
+      rcv.push_back(Seg{peer(p), R + (size_t)p * blk, blk});
+    }
+    mesh_.exchange(tag(204), snd, rcv);
+    snd.clear();
+    rcv.clear();
+    // inside the node: everybody passes on the N blocks of its column, packed [node 0 .. node N-1]
+    char* scratch = net_scratch((size_t)L * N * blk);
+    char* mine = scratch + (size_t)li * N * blk;
+    for (int k = 0; k < N; ++k) memcpy(mine + (size_t)k * blk, R + (size_t)nm.on_node[k][li] * blk, blk);
+    for (int j = 0; j < L; ++j) {
+      if (j == li) continue;
+      const int p = nm.on_node[my_node][j];
+      snd.push_back(Seg{peer(p), mine, (size_t)N * blk});
+      rcv.push_back(Seg{peer(p), scratch + (size_t)j * N * blk, (size_t)N * blk});
+    }
+    mesh_.exchange(tag(205), snd, rcv);
+    for (int j = 0; j < L; ++j)
+      if (j != li)
+        for (int k = 0; k < N; ++k) memcpy(R + (size_t)nm.on_node[k][j] * blk, scratch + ((size_t)j * N + k) * blk, blk);
+    return true;
+  }
+  if (d.kind == OpKind::REDUCE_SCATTER) {
+    // inside the node: local member j collects, from every local member, the blocks meant for column j (packed by node) and
+    // adds them up - N partial sums per rank
+    char* scratch = net_scratch(((size_t)L * N + (size_t)L * N + N + N) * blk);
+    char* out_pack = scratch;                                   // [j][k]: what I send to local member j
+    char* in_pack = scratch + (size_t)L * N * blk;              // [j][k]: what local member j sent me
+    char* partial = in_pack + (size_t)L * N * blk;              // [k]: node-local sum of the block for member on_node[k][li]
+    char* from_nodes = partial + (size_t)N * blk;               // [k]: partial sums for ME from the other nodes
+    for (int j = 0; j < L; ++j)
+      for (int k = 0; k < N; ++k) memcpy(out_pack + ((size_t)j * N + k) * blk, S + (size_t)nm.on_node[k][j] * blk, blk);
+    for (int j = 0; j < L; ++j) {
+      if (j == li) continue;
+      const int p = nm.on_node[my_node][j];
+      snd.push_back(Seg{peer(p), out_pack + (size_t)j * N * blk, (size_t)N * blk});
+      rcv.push_back(Seg{peer(p), in_pack + (size_t)j * N * blk, (size_t)N * blk});
+    }
+    mesh_.exchange(tag(204), snd, rcv);
+    snd.clear();
+    rcv.clear();
+    std::vector<const void*> srcs(L);
+    for (int j = 0; j < L; ++j) srcs[j] = j == li ? (const void*)(out_pack + (size_t)li * N * blk) : (const void*)(in_pack + (size_t)j * N * blk);
+    host_reduce(d.dtype, partial, srcs, (size_t)N * n, d.rop, 1.0f);
+    // between nodes: the partial sum for each member of my column goes to that member; add what arrives for me
+    for (int k = 0; k < N; ++k) {
+      if (k == my_node) continue;
+      const int p = nm.on_node[k][li];
+      snd.push_back(Seg{peer(p), partial + (size_t)k * blk, blk});
+      rcv.push_back(Seg{peer(p), from_nodes + (size_t)k * blk, blk});
+    }
+    mesh_.exchange(tag(205), snd, rcv);
+    std::vector<const void*> parts(N);
+    for (int k = 0; k < N; ++k) parts[k] = k == my_node ? (const void*)(partial + (size_t)my_node * blk) : (const void*)(from_nodes + (size_t)k * blk);
+    host_reduce(d.dtype, R, parts, n, d.rop, d.scale);
+    return true;
+  }
+  return false;
 }
 
 // Quantised all-reduce (CT_QUANTIZATION) between nodes - where the reference's gradient compression matters most: the same

@@ -31,9 +31,12 @@ def test_cpp_functional_test_across_nodes(nnodes, per_node, args):
     assert out.count("0 FAILED") == nnodes * per_node and ": FAILED" not in out
 
 
-@pytest.mark.parametrize("nnodes,per_node,seed", [(2, 2, 3), (3, 2, 4), (2, 1, 7)])
-def test_random_collectives_and_fused_update_across_nodes(nnodes, per_node, seed):
-    rcs, out = _launch(nnodes, per_node, [sys.executable, os.path.join(ROOT, "tests", "net_worker.py"), str(seed)])
+@pytest.mark.parametrize("nnodes,per_node,seed,hier_kb", [(2, 2, 3, "1024"), (3, 2, 4, "1024"), (2, 1, 7, "1024"), (2, 2, 5, "0"), (2, 3, 6, "0")])
+def test_random_collectives_and_fused_update_across_nodes(nnodes, per_node, seed, hier_kb):
+    """(hier_kb 0: every all-reduce / all-gather / reduce-scatter over a group with several members per node takes the
+    two-level route, whatever its size - sub-groups of the randomised programs included)"""
+    rcs, out = _launch(nnodes, per_node, [sys.executable, os.path.join(ROOT, "tests", "net_worker.py"), str(seed)],
+                       extra_env={"MLSL_NET_HIER_KB": hier_kb})
     assert all(rc == 0 for rc in rcs), out[-3000:]
     assert out.count("NET OK") == nnodes * per_node
 
