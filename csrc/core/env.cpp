@@ -130,6 +130,15 @@ EnvConfig parse_env() {
                            "MLSL_COPY_THRESHOLD", "MLSL_MPI_VERSION_CHECK", "EPLIB_USE_ALLOCATOR", "EPLIB_USE_MEM_HOOKS",
                            "EPLIB_STD_MPI_MODE", "EPLIB_MPI_THREAD_MULTIPLE", "EPLIB_ROOT"})
     if (ev(name)) c.not_applicable += std::string(c.not_applicable.empty() ? "" : " ") + name;
+  gets(c.net_addr, "MLSL_NET_ADDR");
+  if (const char* v = ev("MLSL_NET_EAGER_KB")) c.net_eager_kb = atol(v);
+  if (const char* v = ev("MLSL_NET_ONESHOT_KB")) c.net_oneshot_kb = atol(v);
+  if (const char* v = ev("MLSL_NET_CHUNK_KB")) c.net_chunk_kb = atol(v);
+  if (const char* v = ev("MLSL_NET_HIER_KB")) c.net_hier_kb = atol(v);
+  getb(c.net_shm, "MLSL_NET_SHM");
+  if (const char* v = ev("MLSL_NET_SHM_RING_KB")) c.net_shm_ring_kb = atol(v);
+  if (const char* v = ev("MLSL_NET_EMULATE_GBIT")) c.net_emulate_gbit = atof(v);
+  gets(c.node_rank, "MLSL_NODE_RANK", "GROUP_RANK");
   geti(c.stats_iters, "MLSL_STATS_ITERS");
   geti(c.stats_skip, "MLSL_STATS_SKIP");
   if (c.num_servers > 16) c.num_servers = 16;
@@ -153,6 +162,9 @@ void print_env(const EnvConfig& c) {
             c.dynamic_server.empty() ? "thread" : c.dynamic_server.c_str(), c.server_affinity.c_str(), c.thp_threshold_mb);
   MLSLB_LOG(LOG_INFO, "MLSL_HOSTNAME=%s MLSL_HOSTNAME_TYPE=%d MLSL_IFACE_NAME=%s MLSL_IFACE_IDX=%d", c.hostname.c_str(), c.hostname_type,
             c.iface_name.c_str(), c.iface_idx);
+  MLSLB_LOG(LOG_INFO, "MLSL_NET_ADDR=%s MLSL_NET_EAGER_KB=%ld MLSL_NET_ONESHOT_KB=%ld MLSL_NET_CHUNK_KB=%ld MLSL_NET_HIER_KB=%ld MLSL_NET_SHM=%d "
+            "MLSL_NET_SHM_RING_KB=%ld MLSL_NET_EMULATE_GBIT=%g MLSL_NODE_RANK=%s", c.net_addr.c_str(), c.net_eager_kb, c.net_oneshot_kb,
+            c.net_chunk_kb, c.net_hier_kb, (int)c.net_shm, c.net_shm_ring_kb, c.net_emulate_gbit, c.node_rank.c_str());
   if (!c.not_applicable.empty())
     MLSLB_LOG(LOG_INFO, "set but not applicable (no server processes, no MPI underneath): %s", c.not_applicable.c_str());
   for (const TuneDesc& d : kTune) MLSLB_LOG(LOG_INFO, "%s=%ld  (%s)", d.env, c.tune.*(d.field), d.help);

@@ -103,6 +103,16 @@ struct EnvConfig {
   std::string hostname, iface_name;
   int hostname_type = 0, iface_idx = -1;
   std::string not_applicable;    // reference knobs that were set but have nothing to act on here (listed at INFO)
+  // ---- net backend (csrc/core/net_backend.cpp) ----
+  std::string net_addr;          // MLSL_NET_ADDR: explicit address of this rank's data connections
+  long net_eager_kb = 32;        // MLSL_NET_EAGER_KB: an early message up to this size is parked, a larger one stays in the socket
+  long net_oneshot_kb = 32;      // MLSL_NET_ONESHOT_KB: all-reduce up to this size = one exchange of whole vectors
+  long net_chunk_kb = 512;       // MLSL_NET_CHUNK_KB: reductions of slices >= 2x this travel in pieces of this size
+  long net_hier_kb = 1024;       // MLSL_NET_HIER_KB: two-level all-reduce / all-gather / reduce-scatter from this size (-1 never)
+  bool net_shm = true;           // MLSL_NET_SHM: same-node ranks exchange through shared-memory rings
+  long net_shm_ring_kb = 1024;   // MLSL_NET_SHM_RING_KB: ring size per direction of a same-node pair
+  double net_emulate_gbit = 0;   // MLSL_NET_EMULATE_GBIT: pace every rank's TCP egress (bench / test knob)
+  std::string node_rank;         // MLSL_NODE_RANK / GROUP_RANK: which launcher ("node") on this machine the rank belongs to
   Tunables tune;                 // device-path knobs (see below)
 };
 

@@ -124,11 +124,13 @@ class Mesh {
       MLSLB_ASSERT(!a.empty(), "MLSL_HOSTNAME=%s does not resolve", ec.hostname.c_str());
       my_ip = a;
     }
-    if (const char* v = getenv("MLSL_NET_ADDR")) my_ip = v;       // explicit address of this rank's interface
+    if (!ec.net_addr.empty()) my_ip = ec.net_addr;                // explicit address of this rank's interface
     my_ip_ = my_ip;
     snprintf(mine.ip, sizeof(mine.ip), "%s", my_ip.c_str());
     mine.port = port;
-    snprintf(mine.node, sizeof(mine.node), "%s", node_key().c_str());
+    snprintf(mine.node, sizeof(mine.node), "%s", node_key(ec.node_rank).c_str());
+    eager_bytes_ = (size_t)std::max(0l, ec.net_eager_kb) << 10;
+    rate_Bps_ = ec.net_emulate_gbit * 1e9 / 8;
     std::vector<Addr> all(world_);
     ctx->boot->allgather(&mine, all.data(), sizeof(Addr));
     node_of_.assign(world_, 0);                                 // node index of every rank (order of first appearance)
@@ -169,13 +171,12 @@ class Mesh {
     close(lfd);
     // ranks of one node talk through shared memory: the lower rank of a pair creates the segment and names it over the
     // socket, the higher one maps it and answers; a pair that cannot share it (containers with separate /dev/shm) stays on TCP
-    const char* use_shm = getenv("MLSL_NET_SHM");
-    if (!use_shm || atoi(use_shm) != 0) {
+    if (ec.net_shm) {
       struct Offer {
         uint32_t magic;
         char name[60];
       };
-      const size_t ring_bytes = ring_capacity();
+      const size_t ring_bytes = ring_capacity(ec.net_shm_ring_kb);
       const size_t seg_bytes = 2 * (offsetof(ShmRing, data) + ring_bytes);
       auto ring_at = [&](char* base, int k) { return (ShmRing*)(base + (size_t)k * (offsetof(ShmRing, data) + ring_bytes)); };
       std::vector<std::pair<int, std::string>> offered;
@@ -438,14 +439,14 @@ class Mesh {
   };
 
   static int fcntl_nonblock(int fd);
-  static size_t ring_capacity() {      // per direction of a same-node pair, rounded up to a power of two
-    size_t kb = getenv("MLSL_NET_SHM_RING_KB") ? (size_t)atol(getenv("MLSL_NET_SHM_RING_KB")) : 1024, cap = 4096;
-    while (cap < (kb << 10)) cap <<= 1;
+  static size_t ring_capacity(long kb) {      // per direction of a same-node pair, rounded up to a power of two
+    size_t cap = 4096;
+    while (cap < ((size_t)std::max(4l, kb) << 10)) cap <<= 1;
     return cap;
   }
   // Same key = same machine and same launcher: host name + boot id, plus the node rank the launcher gave (several "nodes" on
   // one machine - the test set-up - stay separate).
-  static std::string node_key() {
+  static std::string node_key(const std::string& node_rank) {
     char host[64] = "?";
     gethostname(host, sizeof(host) - 1);
     std::string k = host;
@@ -454,17 +455,10 @@ class Mesh {
       if (fgets(id, sizeof(id), f)) k += std::string(":") + std::string(id).substr(0, 8);
       fclose(f);
     }
-    for (const char* name : {"MLSL_NODE_RANK", "GROUP_RANK"})
-      if (const char* v = getenv(name)) {
-        k += std::string(":") + v;
-        break;
-      }
+    if (!node_rank.empty()) k += ":" + node_rank;
     return k;
   }
-  static size_t eager_bytes() {
-    static const size_t v = getenv("MLSL_NET_EAGER_KB") ? (size_t)atol(getenv("MLSL_NET_EAGER_KB")) << 10 : kEagerBytes;
-    return v;
-  }
+  size_t eager_bytes() const { return eager_bytes_; }
 
   // Send what the sockets take.  Per peer strictly in list order (the byte stream carries one message after the other); a
   // peer whose socket is full is skipped until poll() reports it writable again.
@@ -645,7 +639,8 @@ class Mesh {
   Xchg* cur_ = nullptr;
   // MLSL_NET_EMULATE_GBIT=<x>: pace this rank's egress to x Gbit/s - what a collective does on a slower link than loop-back
   // can be measured on one machine (bench / test knob, off by default)
-  double rate_Bps_ = getenv("MLSL_NET_EMULATE_GBIT") ? atof(getenv("MLSL_NET_EMULATE_GBIT")) * 1e9 / 8 : 0.0, tokens_ = 0.0;
+  double rate_Bps_ = 0.0, tokens_ = 0.0;
+  size_t eager_bytes_ = kEagerBytes;
   uint64_t last_refill_ns_ = 0;
   bool paced_ = false, io_progress_ = false;
   size_t quantum_left_ = 0;
@@ -830,7 +825,7 @@ void NetBackend::execute(CommRequest& r) {
   // members' copies of it are there (while the later pieces are still on the wire) and - all-reduce - its result leaves for
   // the other members right away, so the reduction and the second exchange hide behind the first.  Pieces are reduced in
   // member order like whole slices: the values do not depend on the chunking.
-  static const size_t chunk_bytes = std::max<size_t>(4096, (getenv("MLSL_NET_CHUNK_KB") ? (size_t)atol(getenv("MLSL_NET_CHUNK_KB")) : 512) << 10);
+  const size_t chunk_bytes = std::max<size_t>(4096, (size_t)std::max(0l, ctx_->env.net_chunk_kb) << 10);
   constexpr int kMaxChunks = 96;                       // two phases of tags fit the 8-bit step field (2 + 2 * 96 < 256)
   auto chunk_elems = [&](size_t slice_elems) {         // elements per piece (0: not worth chunking)
     if (slice_elems * dt < 2 * chunk_bytes) return (size_t)0;
@@ -1029,7 +1024,7 @@ void NetBackend::execute(CommRequest& r) {
         quantized_allreduce(r, g);
         break;
       }
-      static const size_t one_shot = getenv("MLSL_NET_ONESHOT_KB") ? (size_t)atol(getenv("MLSL_NET_ONESHOT_KB")) << 10 : kOneShotBytes;
+      const size_t one_shot = (size_t)std::max(0l, ctx_->env.net_oneshot_kb) << 10;
       if (hierarchical_allreduce(r, g, tag)) break;
       if (n * dt <= one_shot) {
         // small message: everybody sends the whole vector to everybody and reduces locally in member order (bitwise
@@ -1125,7 +1120,7 @@ void NetBackend::execute(CommRequest& r) {
 // and then copied, so all ranks end up with identical bits.  Returns false when the group / size does not qualify; the
 // decision only uses facts every member knows (who runs where, the count), so all members decide alike.
 bool NetBackend::hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag) {
-  static const long hier_kb = getenv("MLSL_NET_HIER_KB") ? atol(getenv("MLSL_NET_HIER_KB")) : 1024;   // < 0: never
+  const long hier_kb = ctx_->env.net_hier_kb;   // < 0: never
   const CommDesc& d = r.desc;
   const size_t dt = dtype_size(d.dtype), n = d.count;
   if (hier_kb < 0 || n * dt < (size_t)hier_kb << 10) return false;
@@ -1206,7 +1201,7 @@ bool NetBackend::hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, c
 // the members with the same local index talk, (N - 1) n bytes per rank instead of (P - L) n; the node-local step moves the N
 // blocks every member holds / needs through shared memory (packed into one message per local peer).
 bool NetBackend::hierarchical_gather_scatter(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag) {
-  static const long hier_kb = getenv("MLSL_NET_HIER_KB") ? atol(getenv("MLSL_NET_HIER_KB")) : 1024;
+  const long hier_kb = ctx_->env.net_hier_kb;
   const CommDesc& d = r.desc;
   const size_t dt = dtype_size(d.dtype), n = d.count;      // n = elements of ONE block (per member)
   const int P = g.size();
