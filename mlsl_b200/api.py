@@ -203,7 +203,8 @@ _getters(ParameterSet, "mlsl_parameter_set", ["data_type"], c_int)
 
 
 class Distribution(_Handle):
-    __slots__ = ("_shape",)       # (group type) -> (process count, process index): fixed for the life of a distribution
+    # instances keep a __dict__ (like before); `_shape` caches (group type) -> (process count, process index), which are
+    # fixed for the life of a distribution
 
     def _group_shape(self, group_type):
         try:
