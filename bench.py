@@ -359,7 +359,8 @@ def run_ours(args):
         "config": {"model": "allreduce fp32 SUM, %d MiB per rank, out of place, fused 1/N scale" % (S >> 20),
                    "global_batch": None, "seq_len": None, "parallelism": "dp%d" % world, "message_bytes": S,
                    "l2": "inputs (1 GiB) larger than L2, no flush needed",
-                   "warmup_steps_run": warm + extra + 4,      # `warmup` = the W asked for; clocks settle over ~0.4 s more of the same step "transport": "fp8" if args.compress else "fp32",
+                   # `warmup` = the W asked for; the clocks settle over ~0.4 s more of the same step before the timed region
+                   "warmup_steps_run": warm + extra + 4, "transport": "fp8" if args.compress else "fp32",
                    "api": "mlsl_b200.allreduce -> Distribution::AllReduceEx -> Environment::Wait",
                    "backend": env.get_backend_name(), "backend_detail": describe, "stream_mode": os.environ.get("MLSL_STREAM_MODE"),
                    "kernel": ("k_scale_copy" if world == 1 else ("k_allreduce_quant" if args.compress else
