@@ -18,6 +18,7 @@ import torch.distributed as dist
 from torch.distributed import ReduceOp
 
 from . import comm
+from .api import GroupType
 
 BACKEND_NAME = "mlsl"
 _NATIVE_RED = {ReduceOp.SUM: "sum", ReduceOp.MIN: "min", ReduceOp.MAX: "max"}
@@ -102,10 +103,12 @@ def _flatten(x):
 
 
 class MLSLProcessGroup(dist.ProcessGroup):
-    def __init__(self, rank, size, distribution, owns_distribution, owns_library):
+    def __init__(self, rank, size, distribution, owns_distribution, owns_library, store=None, ranks=None):
         super().__init__(rank, size)
         self._d, self._owns_d, self._owns_lib = distribution, owns_distribution, owns_library
         self._state = comm._state()   # collectives may be issued from autograd's threads (DDP hooks)
+        self._store, self._ranks = store, list(ranks) if ranks is not None else list(range(size))
+        self._pairs = {}              # peer (group rank) -> (two-member distribution, my index in it)
 
     # ---- plumbing -------------------------------------------------------------------------------------------
     def getBackendName(self):
@@ -345,16 +348,61 @@ class MLSLProcessGroup(dist.ProcessGroup):
                 comm.barrier(group="data", distribution=self._d)
             return self._done([], None)
 
-    def send(self, tensors, dstRank, tag):
-        raise NotImplementedError("mlsl backend: point-to-point send/recv is not provided (use all_to_all_single with "
-                                  "split sizes, or comm.ring_shift)")
+    # ---- point to point -------------------------------------------------------------------------------------
+    # A pair of ranks that exchanges messages gets a two-member distribution of its own the first time it does (created by
+    # the two members only, the group's store is the rendezvous - like new_group); a send and the matching recv are then ONE
+    # SendRecvList operation on it, so messages between a pair match in program order (tags are not consulted), both calls
+    # complete together (rendezvous semantics), and batch_isend_irecv maps every (send, recv) couple of a pair to the same
+    # operation on both sides.
+    def _pair(self, peer):
+        me = self.rank()
+        if peer == me or not 0 <= peer < self.size():
+            raise ValueError("mlsl backend: invalid peer rank %d for rank %d of %d" % (peer, me, self.size()))
+        ent = self._pairs.get(peer)
+        if ent is None:
+            env = comm.env()
+            lo, hi = min(me, peer), max(me, peer)
+            key = "mlsl_p2p/%d_%d/%%d" % (lo, hi)
+            rows, mark = env.get_group_state()
+            self._store.set(key % me, struct.pack("<QQ", rows, mark))
+            peer_rows, peer_mark = struct.unpack("<QQ", self._store.get(key % peer))
+            d = env.create_distribution_from_ranks([self._ranks[lo], self._ranks[hi]], rows | peer_rows, max(mark, peer_mark))
+            ent = self._pairs[peer] = (d, 0 if me == lo else 1)
+        return ent
 
-    recv = recv_anysource = send
+    def _p2p(self, tensor, peer, sending):
+        with comm.use_state(self._state):
+            if self._store is None:
+                raise NotImplementedError("mlsl backend: this process group was made without a store: no point-to-point")
+            d, idx = self._pair(peer)
+            c, back = self._staged(tensor)
+            raw = c.view(-1) if c.dtype in comm._TORCH2MLSL else c.view(-1).view(torch.uint8)
+            n = raw.numel()
+            mine = [0, 0]
+            mine[1 - idx] = n
+            sc, rc = (mine, [0, 0]) if sending else ([0, 0], mine)
+            comm._sync_stream()
+            req = d.send_recv_list(raw, sc, [0, 0], raw, rc, [0, 0], comm.mlsl_dtype(raw.dtype), GroupType.DATA)
+            return self._done([comm.Work(comm.env(), req, None, (raw, c))], [tensor], [None if sending else back])
+
+    def send(self, tensors, dstRank, tag):
+        return self._p2p(tensors[0], dstRank, True)
+
+    def recv(self, tensors, srcRank, tag):
+        return self._p2p(tensors[0], srcRank, False)
+
+    def recv_anysource(self, tensors, tag):
+        raise NotImplementedError("mlsl backend: recv from any source is not provided (every message is a rendezvous of a pair)")
 
     # ---- lifetime -------------------------------------------------------------------------------------------
     def shutdown(self):
         """Called by torch.distributed.destroy_process_group (newest group first, the same order on every rank)."""
         with comm.use_state(self._state):
+            if comm.is_initialized():
+                me = self.rank()                          # collective over the pair: one global order of the pairs
+                for peer in sorted(self._pairs, key=lambda q: (min(me, q), max(me, q))):
+                    comm.env().delete_distribution(self._pairs[peer][0])
+            self._pairs = {}
             if self._d is not None and self._owns_d and comm.is_initialized():
                 comm.env().delete_distribution(self._d)   # collective over the members
             self._d = None
@@ -379,14 +427,14 @@ def _create(opts, pg_options=None):
         raise RuntimeError("mlsl backend: torch rank %d is library process %d - launch both from the same RANK/"
                            "WORLD_SIZE (mlslrun or torchrun)" % (ranks[rank], env.get_process_idx()))
     if ranks == list(range(world)):
-        return MLSLProcessGroup(rank, size, comm.world_distribution(), False, owns_lib)
+        return MLSLProcessGroup(rank, size, comm.world_distribution(), False, owns_lib, opts.store, ranks)
     rows, mark = env.get_group_state()
     opts.store.set("mlsl_group_state/%d" % rank, struct.pack("<QQ", rows, mark))
     for r in range(size):
         peer_rows, peer_mark = struct.unpack("<QQ", opts.store.get("mlsl_group_state/%d" % r))
         rows |= peer_rows
         mark = max(mark, peer_mark)
-    return MLSLProcessGroup(rank, size, env.create_distribution_from_ranks(ranks, rows, mark), True, owns_lib)
+    return MLSLProcessGroup(rank, size, env.create_distribution_from_ranks(ranks, rows, mark), True, owns_lib, opts.store, ranks)
 
 
 def compressed_allreduce_hook(process_group, bucket):

@@ -125,6 +125,37 @@ if world >= 4:
     if rank in lists[0]:
         dist.destroy_process_group(groups[0])
 
+# point to point: a send and its recv are one operation of a two-member distribution made on first use
+if world > 1:
+    up, down = (rank + 1) % world, (rank - 1) % world
+    for dtype, n in ((torch.float32, 1000), (torch.int64, 77), (torch.bfloat16, 4099)):
+        out, got = inp(rank, n, dtype), torch.zeros(n, dtype=dtype, device=DEV)
+        if rank % 2 == 0:                       # even ranks talk first: every message is a rendezvous of its two ranks
+            dist.send(out, dst=up)
+            dist.recv(got, src=down)
+        else:
+            dist.recv(got, src=down)
+            dist.send(out, dst=up)
+        check("send/recv ring %s" % dtype, got, inp(down, n, dtype))
+    # both directions of a pair in one batch (pipeline schedules): the couple maps to the same operation on both sides
+    if world % 2 == 0:
+        mate = rank ^ 1
+        a, b = inp(rank, 513), torch.zeros(513, device=DEV)
+        base = torch.zeros(64, 2, device=DEV)
+        ops = [dist.P2POp(dist.isend, a, mate), dist.P2POp(dist.irecv, b, mate)]
+        if rank > mate:
+            ops.reverse()                       # the higher rank lists its recv first: pairs match in program order
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        check("batch_isend_irecv", b, inp(mate, 513))
+        if rank < mate:
+            dist.send(inp(rank, 64), dst=mate)
+        else:
+            dist.recv(base[:, 1], src=mate)     # strided destination
+            check("recv into a strided view", base[:, 1], inp(mate, 64))
+            check("recv strided untouched column", base[:, 0], torch.zeros(64, device=DEV))
+    dist.barrier()
+
 # DistributedDataParallel end to end: parameters broadcast from rank 0, gradients averaged
 torch.manual_seed(1234 + rank)
 model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4)).to(DEV)
