@@ -29,7 +29,7 @@ def build(model, batch, seq):
         m = resnet50().cuda().to(memory_format=torch.channels_last)
         x = torch.randn(batch, 3, 224, 224, device="cuda").to(memory_format=torch.channels_last)
         y = torch.randint(0, 1000, (batch,), device="cuda")
-        return m, (x, y), batch, "images/s", lambda out, y: torch.nn.functional.cross_entropy(out, y)
+        return m, (x, y), batch, "images/s", lambda out, y: torch.nn.functional.cross_entropy(out.float(), y)
     if model in ("bert-large", "bert-small"):
         cfg = BertConfig() if model == "bert-large" else BertConfig(layers=4, hidden=512, heads=8, ffn=2048)
         m = BertEncoderModel(cfg).cuda()
@@ -55,6 +55,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--bucket-mb", type=float, default=64)
     ap.add_argument("--optimizer", default=None)
+    ap.add_argument("--param-dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="bf16: parameters AND gradients in bf16 (half the gradient bytes on the wire; the fused sharded optimizer "
+                         "keeps fp32 master weights and moments for its shard), no autocast")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -63,7 +66,14 @@ def main():
     torch.manual_seed(1234)
     model, (x, y), units, unit_name, loss_fn = build(args.model, batch, args.seq)
     nparam = sum(p.numel() for p in model.parameters())
-    amp = torch.autocast("cuda", dtype=torch.bfloat16)
+    if args.param_dtype == "bf16":
+        import contextlib
+        model = model.to(torch.bfloat16)
+        if x.is_floating_point():
+            x = x.to(torch.bfloat16)
+        amp = contextlib.nullcontext()
+    else:
+        amp = torch.autocast("cuda", dtype=torch.bfloat16)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     if args.impl == "mlsl":
@@ -115,7 +125,8 @@ def main():
         print(json.dumps({"model": args.model, "impl": args.impl, "mode": args.mode if args.impl == "mlsl" else "nccl-ddp",
                           "compress": args.compress, "n_gpus": world, "per_gpu_batch": batch, "params_M": round(nparam / 1e6, 1),
                           "ms_per_step": round(ms, 3), "throughput": round(units * world / (ms * 1e-3), 1),
-                          "unit": unit_name, "optimizer": kind, "loss": round(float(loss), 4), "dtype": "bf16 autocast, fp32 params/grads"}))
+                          "unit": unit_name, "optimizer": kind, "loss": round(float(loss), 4),
+                          "dtype": "bf16 params/grads" if args.param_dtype == "bf16" else "bf16 autocast, fp32 params/grads"}))
     if args.impl == "mlsl":
         opt.close()
         import mlsl_b200 as mlsl
