@@ -39,10 +39,10 @@ def _reference(world, steps, kind, kw):
     return torch.cat([p.detach().reshape(-1) for p in m.parameters()])
 
 
-def _train(world, steps, kind, mode, backend, kw, bucket_mb=0.004, compress=False, model_zero_grad=False):
+def _train(world, steps, kind, mode, backend, kw, bucket_mb=0.004, compress=False, model_zero_grad=False, dtype=torch.float32):
     def body(r, mlsl):
         dev = "cuda" if backend == "cuda" else "cpu"
-        m = _model().to(dev)
+        m = _model(dtype).to(dev)
         okw = dict(lr=kw["lr"], weight_decay=kw.get("weight_decay", 0.0), optimizer=kind, mode=mode, bucket_mb=bucket_mb,
                    compress=compress)
         if kind == "sgd":
@@ -55,7 +55,7 @@ def _train(world, steps, kind, mode, backend, kw, bucket_mb=0.004, compress=Fals
             else:
                 opt.zero_grad()
             x, y = _batch(r, s)
-            torch.nn.functional.mse_loss(m(x.to(dev)), y.to(dev)).backward()
+            torch.nn.functional.mse_loss(m(x.to(dev).to(dtype)).float(), y.to(dev)).backward()
             opt.step()
         if backend == "cuda":
             torch.cuda.current_stream().synchronize()
@@ -77,6 +77,20 @@ def test_distributed_optimizer_cpu(mode, kind, kw):
     for o in outs:
         assert torch.allclose(o, ref, rtol=2e-4, atol=2e-5), (o - ref).abs().max()
         assert torch.equal(o, outs[0])
+
+
+@pytest.mark.parametrize("mode,kind,kw", [("fused", "adamw", dict(lr=0.01, weight_decay=0.02)),
+                                          ("fused", "sgd", dict(lr=0.05, momentum=0.9, weight_decay=0.01)),
+                                          ("allreduce", "sgd", dict(lr=0.05, momentum=0.9, weight_decay=0.01))])
+def test_bf16_parameters_and_gradients(mode, kind, kw):
+    """bf16 parameters: the gradient buckets travel in bf16 (half the bytes); the fused sharded optimizer keeps fp32 master
+    weights and moments for its shard, so the result tracks the fp32 reference to bf16 resolution and replicas stay identical."""
+    world, steps = 2, 4
+    outs = _train(world, steps, kind, mode, "host", kw, dtype=torch.bfloat16)
+    ref = _reference(world, steps, kind, kw)
+    for o in outs:
+        assert torch.equal(o, outs[0])
+        assert torch.allclose(o, ref, rtol=0.05, atol=0.02), (o - ref).abs().max()
 
 
 @pytest.mark.parametrize("mode", ["fused", "allreduce"])
