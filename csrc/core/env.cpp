@@ -165,6 +165,7 @@ void print_env(const EnvConfig& c) {
   MLSLB_LOG(LOG_INFO, "MLSL_NET_ADDR=%s MLSL_NET_EAGER_KB=%ld MLSL_NET_ONESHOT_KB=%ld MLSL_NET_CHUNK_KB=%ld MLSL_NET_HIER_KB=%ld MLSL_NET_SHM=%d "
             "MLSL_NET_SHM_RING_KB=%ld MLSL_NET_EMULATE_GBIT=%g MLSL_NODE_RANK=%s", c.net_addr.c_str(), c.net_eager_kb, c.net_oneshot_kb,
             c.net_chunk_kb, c.net_hier_kb, (int)c.net_shm, c.net_shm_ring_kb, c.net_emulate_gbit, c.node_rank.c_str());
+  MLSLB_LOG(LOG_INFO, "MLSL_JOB_TOKEN=%s", getenv("MLSL_JOB_TOKEN") ? "(set)" : "(not set)");
   if (!c.not_applicable.empty())
     MLSLB_LOG(LOG_INFO, "set but not applicable (no server processes, no MPI underneath): %s", c.not_applicable.c_str());
   for (const TuneDesc& d : kTune) MLSLB_LOG(LOG_INFO, "%s=%ld  (%s)", d.env, c.tune.*(d.field), d.help);

@@ -59,6 +59,10 @@ constexpr size_t kBcastSplitBytes = 128 << 10;   // broadcast from this size on:
 struct WireHdr {
   uint64_t tag, bytes;
 };
+struct MeshHello {           // first frame of a data connection
+  uint32_t rank, pad;
+  uint64_t token;
+};
 
 // One direction of a same-node pair: a byte stream through shared memory with the semantics of the socket it replaces
 // (bounded, in order, the writer stalls when it is full).  Single producer, single consumer.
@@ -146,7 +150,7 @@ class Mesh {
     // connect to every lower rank (the listen backlog completes the handshake even before the peer accepts) ...
     for (int p = 0; p < rank_; ++p) {
       int fd = tcp_connect_retry(all[p].ip, all[p].port, 60);
-      uint32_t me = (uint32_t)rank_;
+      MeshHello me{(uint32_t)rank_, 0, tcp_job_token()};
       try {
         tcp_send_all(fd, &me, sizeof(me));
       } catch (const Error& e) {
@@ -155,18 +159,32 @@ class Mesh {
       fds_[p] = fd;
     }
     // ... and accept every higher one
-    for (int k = rank_ + 1; k < world_; ++k) {
+    for (int accepted = 0; accepted < world_ - 1 - rank_;) {
+      pollfd pl{lfd, POLLIN, 0};
+      const int pr = poll(&pl, 1, 120000);
+      MLSLB_ASSERT(pr > 0, "data mesh: %d of the %d higher ranks never connected", world_ - 1 - rank_ - accepted, world_ - 1 - rank_);
       int fd = accept4(lfd, nullptr, nullptr, SOCK_CLOEXEC);
       MLSLB_ASSERT(fd >= 0, "accept(): %s", strerror(errno));
       tcp_tune(fd);
-      uint32_t who = 0;
+      MeshHello who{0, 0, 0};
+      bool ok = true;
       try {
+        timeval tv{10, 0};                                       // a stray that never speaks must not stall the job
+        setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
         tcp_recv_all(fd, &who, sizeof(who));
-      } catch (const Error& e) {
-        MLSLB_ASSERT(false, "data mesh: a peer connected and vanished: %s", e.what());
+        timeval none{0, 0};
+        setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &none, sizeof(none));
+      } catch (const Error&) {
+        ok = false;
       }
-      MLSLB_ASSERT((int)who > rank_ && (int)who < world_ && fds_[who] < 0, "unexpected peer %u on the data mesh", who);
-      fds_[who] = fd;
+      // somebody who is not a higher rank of THIS job (another job on a recycled port, a scanner): turn it away, keep waiting
+      if (!ok || who.token != tcp_job_token() || (int)who.rank <= rank_ || (int)who.rank >= world_ || fds_[who.rank] >= 0) {
+        MLSLB_LOG(LOG_ERROR, "data mesh: turned away a connection (claims rank %u)", who.rank);
+        close(fd);
+        continue;
+      }
+      fds_[who.rank] = fd;
+      ++accepted;
     }
     close(lfd);
     // ranks of one node talk through shared memory: the lower rank of a pair creates the segment and names it over the

@@ -10,6 +10,7 @@
 #include <unistd.h>
 
 #include <cerrno>
+#include <cstdlib>
 #include <cstring>
 #include <tuple>
 
@@ -142,6 +143,16 @@ std::string tcp_address_of_interface(const std::string& prefix, int idx) {
   return out;
 }
 
+uint64_t tcp_job_token() {
+  static const uint64_t token = [] {
+    const char* v = getenv("MLSL_JOB_TOKEN");
+    uint64_t h = 1469598103934665603ull;                       // FNV-1a
+    for (const char* c = (v && *v) ? v : "mlsl-b200"; *c; ++c) h = (h ^ (uint8_t)*c) * 1099511628211ull;
+    return h ? h : 1;
+  }();
+  return token;
+}
+
 std::string tcp_resolve_to_ip(const std::string& host) {
   sockaddr_in sa;
   char buf[64];
@@ -208,6 +219,7 @@ TcpControl::TcpControl(const std::string& master_addr, int master_port, int rank
   h.type = MSG_HELLO;
   h.rank = (uint32_t)rank;
   h.nmembers = (uint32_t)world;
+  h.key = tcp_job_token();
   tcp_send_all(sock_, &h, sizeof(h));
   rx_ = std::thread([this] { rx_loop(); });
 }
@@ -360,7 +372,10 @@ void TcpControl::server_accept_loop() {
       continue;
     }
     // (compared as unsigned: a rank >= 2^31 must not turn into a negative index)
-    if (h.type != MSG_HELLO || (uint64_t)h.rank >= (uint64_t)world_ || (uint64_t)h.nmembers != (uint64_t)world_) {
+    if (h.type != MSG_HELLO || (uint64_t)h.rank >= (uint64_t)world_ || (uint64_t)h.nmembers != (uint64_t)world_ ||
+        h.key != tcp_job_token()) {
+      if (h.type == MSG_HELLO && h.key != tcp_job_token())
+        MLSLB_LOG(LOG_ERROR, "control server: turned away a connection that claims rank %u with another job token (MLSL_JOB_TOKEN)", h.rank);
       close(fd);
       continue;
     }

@@ -32,6 +32,10 @@ std::string tcp_local_address_towards(const std::string& addr, int port);       
 // ("" if none); and of a host name / dotted address
 std::string tcp_address_of_interface(const std::string& prefix, int idx);
 std::string tcp_resolve_to_ip(const std::string& host);
+// What every connection of a job has to present in its first frame: a hash of MLSL_JOB_TOKEN (a fixed value when the variable
+// is not set).  `mlslrun --hosts` hands every node the same random token; it keeps strays - another job that was given the
+// same port, a port scanner - from being taken for a member (it is not a defence against someone who can read the environment).
+uint64_t tcp_job_token();
 
 class TcpControl {
  public:

@@ -69,7 +69,19 @@ static int run_hosts(const std::vector<std::string>& hosts, const std::string& r
   if (master_port.empty()) {
     timeval tv;
     gettimeofday(&tv, nullptr);
-    master_port = std::to_string(20000 + (int)((tv.tv_usec ^ getpid()) % 30000));
+    master_port = std::to_string(20000 + (int)((tv.tv_usec ^ getpid()) % 12000));     // below the ephemeral range
+  }
+  if (!getenv("MLSL_JOB_TOKEN")) {          // every node of this job presents the same token when it connects (forwarded below)
+    unsigned long long r = 0;
+    if (FILE* f = fopen("/dev/urandom", "rb")) {
+      if (fread(&r, sizeof(r), 1, f) != 1) r = 0;
+      fclose(f);
+    }
+    timeval tv;
+    gettimeofday(&tv, nullptr);
+    char tok[40];
+    snprintf(tok, sizeof(tok), "%016llx", r ^ ((unsigned long long)tv.tv_usec << 20) ^ (unsigned long long)getpid());
+    setenv("MLSL_JOB_TOKEN", tok, 1);
   }
   std::vector<std::string> rsh_argv;   // the remote shell command may carry its own options
   {

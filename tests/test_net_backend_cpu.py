@@ -90,6 +90,25 @@ def test_interface_selection_like_the_reference():
     assert any(rc != 0 for rc in rcs) and "no IPv4 interface matches" in out, out[-2000:]
 
 
+def test_job_token_in_the_first_frame_of_every_connection():
+    """Control and data connections present a hash of MLSL_JOB_TOKEN: with the same token on every node the job runs; a node
+    that was given another one is turned away by the control server (and says so) instead of being taken for a member."""
+    code = ("import sys; sys.path.insert(0, %r); import torch, mlsl_b200 as mlsl; mlsl.init(); x = torch.ones(4); mlsl.allreduce(x); "
+            "print('TOKEN OK %%d' %% int(x[0]), flush=True); mlsl.finalize()") % ROOT
+    rcs, out = _launch(2, 2, [sys.executable, "-c", code], extra_env={"MLSL_JOB_TOKEN": "s3cret"})
+    assert all(rc == 0 for rc in rcs) and out.count("TOKEN OK 4") == 4, out[-2000:]
+    port = str(free_port())
+    env = dict(os.environ, MLSL_WATCHDOG_SEC="10")
+    env.pop("MLSL_BACKEND", None)
+    cmd = lambda i: [MLSLRUN, "-n", "1", "--nnodes", "2", "--node-rank", str(i), "--master-addr", "127.0.0.1", "--master-port", port,
+                     "--timeout", "25", sys.executable, "-c", code]
+    procs = [subprocess.Popen(cmd(i), cwd=ROOT, env=dict(env, MLSL_JOB_TOKEN="job-%d" % i), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for i in range(2)]
+    outs = [p.communicate(timeout=90)[0] for p in procs]
+    assert all(p.returncode != 0 for p in procs) and "TOKEN OK" not in "".join(outs)
+    assert "another job token" in outs[0], outs[0][-2000:]
+
+
 def test_a_dying_rank_fails_the_whole_multi_node_job_fast():
     """One rank exits without finalizing: its control connection drops, rank 0's server poisons everyone, the surviving
     ranks leave their collective with an error instead of waiting for the watchdog."""
