@@ -105,7 +105,6 @@ class Mesh {
     peers_.resize(world_);
     if (world_ == 1) return;
     int port = 0;
-    int lfd = tcp_listen("*", 0, world_ + 8, &port);
     struct Addr {
       char ip[48];
       int port;
@@ -129,6 +128,9 @@ class Mesh {
       my_ip = a;
     }
     if (!ec.net_addr.empty()) my_ip = ec.net_addr;                // explicit address of this rank's interface
+    // an interface that was asked for by name / address is also the only one the data port listens on
+    const bool chosen = !ec.net_addr.empty() || !ec.iface_name.empty() || ec.iface_idx >= 0 || (!ec.hostname.empty() && ec.hostname_type != 0);
+    int lfd = tcp_listen(chosen ? my_ip.c_str() : "*", 0, world_ + 8, &port);
     my_ip_ = my_ip;
     snprintf(mine.ip, sizeof(mine.ip), "%s", my_ip.c_str());
     mine.port = port;
