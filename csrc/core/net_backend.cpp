@@ -743,6 +743,8 @@ class NetBackend final : public Backend {
   Mesh mesh_;
   void execute(CommRequest& r);
   void quantized_allreduce(CommRequest& r, const ProcessGroup& g);
+  void quantized_exchange(const float* x, float* y, size_t n, const std::vector<int>& ranks, int me, std::vector<float>& residual,
+                          float scale, const std::function<uint64_t(int)>& tag, int step0);
   bool hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
   bool hierarchical_gather_scatter(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
   // Where the members of a group run: N nodes with L members each (member positions per node, in member order), and this
@@ -780,6 +782,17 @@ class NetBackend final : public Backend {
 // Receive space for the slices of a reduction: grow-only and uninitialised (a fresh std::vector would zero-fill and
 // page-fault the whole message size on every call).
 static char* net_scratch(size_t bytes) {
+  thread_local std::unique_ptr<char[]> buf;
+  thread_local size_t cap = 0;
+  if (bytes > cap) {
+    cap = bytes + bytes / 4;
+    buf.reset(new char[cap]);
+  }
+  return buf.get();
+}
+
+// (the quantised exchange has its own: it runs inside the two-level all-reduce, whose shard lives in the scratch above)
+static char* net_scratch_q(size_t bytes) {
   thread_local std::unique_ptr<char[]> buf;
   thread_local size_t cap = 0;
   if (bytes > cap) {
@@ -1041,6 +1054,7 @@ void NetBackend::execute(CommRequest& r) {
     }
     case OpKind::ALLREDUCE: {
       if (d.compress && d.dtype == DType::F32 && d.rop == RedOp::SUM) {
+        if (hierarchical_allreduce(r, g, tag)) break;     // exact inside the node, quantised between the nodes
         quantized_allreduce(r, g);
         break;
       }
@@ -1179,7 +1193,16 @@ bool NetBackend::hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, c
     for (int j = 0; j < L; ++j) srcs[j] = j == li ? (const void*)(S + lo_l(li) * dt) : (const void*)(tmpA + (size_t)j * per_l * dt);
     host_reduce(d.dtype, shard, srcs, mine, d.rop, 1.0f);
   }
-  // B: all-reduce of the shard among the members with my local index, one per node: reduce-scatter + all-gather
+  // B: all-reduce of the shard among the members with my local index, one per node
+  if (d.compress && d.dtype == DType::F32 && d.rop == RedOp::SUM) {
+    // gradient compression where it pays - on the wire between nodes: block-scaled fp8 with error feedback for the shard
+    // (the node-local sums before and the copies after are exact); the residual belongs to the request as in the flat form
+    if (!r.backend_state) r.backend_state = new NetReqState();
+    NetReqState* st = (NetReqState*)r.backend_state;
+    std::vector<int> column(N);
+    for (int k = 0; k < N; ++k) column[k] = peer(on_node[k][li]);
+    if (mine) quantized_exchange((const float*)shard, (float*)shard, mine, column, my_node, st->residual, d.scale, tag, 201);
+  } else {
   const size_t sub = len_n(mine, my_node);
   for (int k = 0; k < N; ++k) {
     if (k == my_node) continue;
@@ -1205,6 +1228,7 @@ bool NetBackend::hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, c
   mesh_.exchange(tag(202), snd, rcv);
   snd.clear();
   rcv.clear();
+  }
   // C: all-gather inside the node, straight into the result
   if (mine) memcpy(R + lo_l(li) * dt, shard, mine * dt);
   for (int j = 0; j < L; ++j) {
@@ -1307,11 +1331,21 @@ bool NetBackend::hierarchical_gather_scatter(CommRequest& r, const ProcessGroup&
 // because every block is dequantised from the one requantised copy its owner produced.
 void NetBackend::quantized_allreduce(CommRequest& r, const ProcessGroup& g) {
   const CommDesc& d = r.desc;
-  const size_t n = d.count;
-  const int P = g.size(), me = g.idx;
   if (!r.backend_state) r.backend_state = new NetReqState();
   NetReqState* st = (NetReqState*)r.backend_state;
-  if (st->residual.size() != n) st->residual.assign(n, 0.f);
+  auto tag = [&](int step) {
+    return ((uint64_t)(uint8_t)g.row << 56) | ((uint64_t)(r.lane & 0xff) << 48) | ((r.group_seq & 0xffffffffffull) << 8) |
+           (uint64_t)(step & 0xff);
+  };
+  quantized_exchange((const float*)r.send, (float*)r.recv, d.count, g.members, g.idx, st->residual, d.scale, tag, 0);
+}
+
+// x (+ the residual of earlier rounds) -> fp8 blocks -> every member's range summed by its owner and requantised once ->
+// y = dequantised sum * scale, among `ranks` (global ranks, this one at position `me`); two exchanges under tag(step0), tag(step0 + 1)
+void NetBackend::quantized_exchange(const float* x, float* y, size_t n, const std::vector<int>& ranks, int me, std::vector<float>& residual,
+                                    float scale, const std::function<uint64_t(int)>& tag, int step0) {
+  const int P = (int)ranks.size();
+  if (residual.size() != n) residual.assign(n, 0.f);
   const size_t nblk = ceil_div(n, (size_t)kQuantBlock), blk_per = ceil_div(nblk, (size_t)P);
   auto blo = [&](int p) { return std::min(nblk, (size_t)p * blk_per); };
   auto bcnt = [&](int p) { return std::min(nblk, blo(p) + blk_per) - blo(p); };
@@ -1319,35 +1353,29 @@ void NetBackend::quantized_allreduce(CommRequest& r, const ProcessGroup& g) {
   auto qof = [&](char* base, int p) { return (uint8_t*)(base + (size_t)p * chunk); };
   auto sof = [&](char* base, int p) { return (float*)(base + (size_t)p * chunk + bcnt(p) * kQuantBlock); };
   // scratch: outgoing chunks by owner | incoming chunks of my range by source | requantised ranges by owner
-  char* out = net_scratch(3 * (size_t)P * chunk);
+  char* out = net_scratch_q(3 * (size_t)P * chunk);
   char* in = out + (size_t)P * chunk;
   char* red = in + (size_t)P * chunk;
-  const float* x = (const float*)r.send;
-  float* y = (float*)r.recv;
   // step 1: x + residual -> fp8 blocks laid out per owner, residual update
   for (int p = 0; p < P; ++p)
     for (size_t k = 0; k < bcnt(p); ++k) {
       const size_t b = blo(p) + k, lo = b * kQuantBlock, hi = std::min(n, lo + kQuantBlock);
       float v[kQuantBlock];
-      for (size_t i = lo; i < hi; ++i) v[i - lo] = x[i] + st->residual[i];
+      for (size_t i = lo; i < hi; ++i) v[i - lo] = x[i] + residual[i];
       for (size_t i = hi - lo; i < (size_t)kQuantBlock; ++i) v[i] = 0.f;
       uint8_t* q = qof(out, p) + k * kQuantBlock;
       const float sc = quant_block(v, q);
       sof(out, p)[k] = sc;
-      for (size_t i = lo; i < hi; ++i) st->residual[i] = v[i - lo] - e4m3_to_f32(q[i - lo]) * sc;
+      for (size_t i = lo; i < hi; ++i) residual[i] = v[i - lo] - e4m3_to_f32(q[i - lo]) * sc;
     }
-  auto tag = [&](int step) {
-    return ((uint64_t)(uint8_t)g.row << 56) | ((uint64_t)(r.lane & 0xff) << 48) | ((r.group_seq & 0xffffffffffull) << 8) |
-           (uint64_t)(step & 0xff);
-  };
   std::vector<Seg> snd, rcv;
   const size_t mine_bytes = bcnt(me) * kQuantBlockBytes;
   for (int p = 0; p < P; ++p)
     if (p != me) {
-      if (bcnt(p)) snd.push_back(Seg{g.members[p], out + (size_t)p * chunk, bcnt(p) * kQuantBlockBytes});
-      if (mine_bytes) rcv.push_back(Seg{g.members[p], in + (size_t)p * chunk, mine_bytes});
+      if (bcnt(p)) snd.push_back(Seg{ranks[p], out + (size_t)p * chunk, bcnt(p) * kQuantBlockBytes});
+      if (mine_bytes) rcv.push_back(Seg{ranks[p], in + (size_t)p * chunk, mine_bytes});
     }
-  mesh_.exchange(tag(0), snd, rcv);
+  mesh_.exchange(tag(step0), snd, rcv);
   snd.clear();
   rcv.clear();
   // step 2: my blocks - dequantise and add in member order, requantise once
@@ -1364,17 +1392,17 @@ void NetBackend::quantized_allreduce(CommRequest& r, const ProcessGroup& g) {
   }
   for (int p = 0; p < P; ++p)
     if (p != me) {
-      if (mine_bytes) snd.push_back(Seg{g.members[p], red + (size_t)me * chunk, mine_bytes});
-      if (bcnt(p)) rcv.push_back(Seg{g.members[p], red + (size_t)p * chunk, bcnt(p) * kQuantBlockBytes});
+      if (mine_bytes) snd.push_back(Seg{ranks[p], red + (size_t)me * chunk, mine_bytes});
+      if (bcnt(p)) rcv.push_back(Seg{ranks[p], red + (size_t)p * chunk, bcnt(p) * kQuantBlockBytes});
     }
-  mesh_.exchange(tag(1), snd, rcv);
+  mesh_.exchange(tag(step0 + 1), snd, rcv);
   // step 3: every range from its owner's requantised copy, output scale fused
   for (int p = 0; p < P; ++p)
     for (size_t k = 0; k < bcnt(p); ++k) {
       const size_t b = blo(p) + k, lo = b * kQuantBlock, hi = std::min(n, lo + kQuantBlock);
       const uint8_t* q = qof(red, p) + k * kQuantBlock;
       const float sc = sof(red, p)[k];
-      for (size_t i = lo; i < hi; ++i) y[i] = e4m3_to_f32(q[i - lo]) * sc * d.scale;   // same order as the host edition
+      for (size_t i = lo; i < hi; ++i) y[i] = e4m3_to_f32(q[i - lo]) * sc * scale;   // same order as the host edition
     }
 }
 
