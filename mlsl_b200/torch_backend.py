@@ -9,7 +9,8 @@ underneath had to be patched (Intel Caffe, reference README.md).  Here the PyTor
 maps to the world distribution, `new_group(ranks)` to a distribution created by its members only (the torch store is the
 rendezvous, Environment::CreateDistributionFromRanks), and every collective is one call into `mlsl_b200.comm`, so on the
 CUDA backend it is stream-ordered like ProcessGroupNCCL (`Work.wait()` orders the current stream, it does not block the
-host).  Point-to-point send/recv is not part of the library (the reference has none either, src/comm.hpp:212-248).
+host).  send / recv between two ranks are one SendRecvList operation (the op the reference declares but never wires up,
+src/comm.hpp:212-248) on a two-member distribution made for the pair on first use.
 """
 import struct
 
