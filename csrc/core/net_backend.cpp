@@ -747,6 +747,7 @@ class NetBackend final : public Backend {
                           float scale, const std::function<uint64_t(int)>& tag, int step0);
   bool hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
   bool hierarchical_gather_scatter(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
+  bool hierarchical_bcast(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
   // Where the members of a group run: N nodes with L members each (member positions per node, in member order), and this
   // rank's place.  false unless the group is regular (same L > 1 on each of N > 1 nodes).
   struct NodeMap {
@@ -926,6 +927,7 @@ void NetBackend::execute(CommRequest& r) {
       break;
     case OpKind::BCAST: {
       const int root = (int)d.root;
+      if (hierarchical_bcast(r, g, tag)) break;
       if (n * dt < kBcastSplitBytes || P < 3) {   // small: the root sends the whole buffer to everybody
         if (me == root) {
           for (int p = 0; p < P; ++p)
@@ -1322,6 +1324,65 @@ bool NetBackend::hierarchical_gather_scatter(CommRequest& r, const ProcessGroup&
     return true;
   }
   return false;
+}
+
+// Broadcast in two levels: the root's column (the members with its local index, one per node) gets the buffer over the wire -
+// scatter + all-gather among them from three nodes on, so the root's link carries the message once - and every column member
+// hands it to the other members of its node through shared memory.  One copy of the message enters each node.
+bool NetBackend::hierarchical_bcast(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag) {
+  const long hier_kb = ctx_->env.net_hier_kb;
+  const CommDesc& d = r.desc;
+  const size_t bytes = d.count * dtype_size(d.dtype);
+  if (hier_kb < 0 || bytes < (size_t)hier_kb << 10 || bytes < 64) return false;
+  NodeMap nm;
+  if (!node_map(g, nm)) return false;
+  const int N = nm.N, L = nm.L, my_node = nm.my_node, li = nm.li, root = (int)d.root;
+  int root_node = 0, root_li = 0;
+  for (int k = 0; k < N; ++k)
+    for (int j = 0; j < L; ++j)
+      if (nm.on_node[k][j] == root) {
+        root_node = k;
+        root_li = j;
+      }
+  char* R = (char*)r.recv;
+  auto peer = [&](int p) { return g.members[p]; };
+  std::vector<Seg> snd, rcv;
+  if (li == root_li) {                                   // the column of the root: between nodes
+    if (N == 2) {
+      if (my_node == root_node) snd.push_back(Seg{peer(nm.on_node[1 - my_node][li]), R, bytes});
+      else rcv.push_back(Seg{peer(root), R, bytes});
+      mesh_.exchange(tag(206), snd, rcv);
+    } else {
+      const size_t per = ceil_div(bytes, (size_t)N);
+      auto lo = [&](int k) { return std::min(bytes, (size_t)k * per); };
+      auto len = [&](int k) { return std::min(bytes, lo(k) + per) - lo(k); };
+      if (my_node == root_node) {
+        for (int k = 0; k < N; ++k)
+          if (k != my_node && len(k)) snd.push_back(Seg{peer(nm.on_node[k][li]), R + lo(k), len(k)});
+      } else if (len(my_node)) {
+        rcv.push_back(Seg{peer(root), R + lo(my_node), len(my_node)});
+      }
+      mesh_.exchange(tag(206), snd, rcv);
+      snd.clear();
+      rcv.clear();
+      for (int k = 0; k < N; ++k) {
+        if (k == my_node) continue;
+        const int p = nm.on_node[k][li];
+        if (k != root_node && len(my_node)) snd.push_back(Seg{peer(p), R + lo(my_node), len(my_node)});
+        if (my_node != root_node && len(k)) rcv.push_back(Seg{peer(p), R + lo(k), len(k)});
+      }
+      mesh_.exchange(tag(207), snd, rcv);
+    }
+    snd.clear();
+    rcv.clear();
+    for (int j = 0; j < L; ++j)                           // inside the node
+      if (j != li) snd.push_back(Seg{peer(nm.on_node[my_node][j]), R, bytes});
+    mesh_.exchange(tag(208), snd, rcv);
+  } else {
+    rcv.push_back(Seg{peer(nm.on_node[my_node][root_li]), R, bytes});
+    mesh_.exchange(tag(208), snd, rcv);
+  }
+  return true;
 }
 
 // Quantised all-reduce (CT_QUANTIZATION) between nodes - where the reference's gradient compression matters most: the same
