@@ -166,6 +166,11 @@ void print_env(const EnvConfig& c) {
             "MLSL_NET_SHM_RING_KB=%ld MLSL_NET_EMULATE_GBIT=%g MLSL_NODE_RANK=%s", c.net_addr.c_str(), c.net_eager_kb, c.net_oneshot_kb,
             c.net_chunk_kb, c.net_hier_kb, (int)c.net_shm, c.net_shm_ring_kb, c.net_emulate_gbit, c.node_rank.c_str());
   MLSLB_LOG(LOG_INFO, "MLSL_JOB_TOKEN=%s", getenv("MLSL_JOB_TOKEN") ? "(set)" : "(not set)");
+  // read where they are used, once, at start-up (device selection and slab / stream set-up of the CUDA backend, logging, tracing)
+  auto shown = [](const char* name) { const char* v = getenv(name); return v ? v : "(unset)"; };
+  MLSLB_LOG(LOG_INFO, "MLSL_DEVICE=%s MLSL_SLAB=%s MLSL_STREAM_MODE=%s MLSL_RANKS_PER_DEVICE=%s MLSL_ASSERT_MODE=%s MLSL_SIG_HANDLERS=%s "
+            "MLSL_TRACE_FILE=%s", shown("MLSL_DEVICE"), shown("MLSL_SLAB"), shown("MLSL_STREAM_MODE"), shown("MLSL_RANKS_PER_DEVICE"),
+            shown("MLSL_ASSERT_MODE"), shown("MLSL_SIG_HANDLERS"), shown("MLSL_TRACE_FILE"));
   if (!c.not_applicable.empty())
     MLSLB_LOG(LOG_INFO, "set but not applicable (no server processes, no MPI underneath): %s", c.not_applicable.c_str());
   for (const TuneDesc& d : kTune) MLSLB_LOG(LOG_INFO, "%s=%ld  (%s)", d.env, c.tune.*(d.field), d.help);
