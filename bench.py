@@ -358,7 +358,8 @@ def run_ours(args):
         "busbw_per_gpu_GBps": round(busbw, 3), "algbw_GBps": round(algbw, 3), "roofline": roofline(world, S, ms, nvls),
         "config": {"model": "allreduce fp32 SUM, %d MiB per rank, out of place, fused 1/N scale" % (S >> 20),
                    "global_batch": None, "seq_len": None, "parallelism": "dp%d" % world, "message_bytes": S,
-                   "l2": "inputs (1 GiB) larger than L2, no flush needed",
+                   "l2": ("inputs (%d MiB per buffer) larger than the 126 MB L2, no flush needed" % (S >> 20) if S > (126 << 20) else
+                          "send + receive buffers of %d MiB each against a 126 MB L2, NO flush between iterations" % (S >> 20)),
                    # `warmup` = the W asked for; the clocks settle over ~0.4 s more of the same step before the timed region
                    "warmup_steps_run": warm + extra + 4, "transport": "fp8" if args.compress else "fp32",
                    "api": "mlsl_b200.allreduce -> Distribution::AllReduceEx -> Environment::Wait",
