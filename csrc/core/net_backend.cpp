@@ -748,6 +748,11 @@ class NetBackend final : public Backend {
   bool hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
   bool hierarchical_gather_scatter(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
   bool hierarchical_bcast(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
+  struct NodeMap;
+  void hier_allgather(const NodeMap& nm, const ProcessGroup& g, const std::function<uint64_t(int)>& tag, int step0, const char* S, char* R,
+                      size_t blk);
+  void hier_reduce_scatter(const NodeMap& nm, const ProcessGroup& g, const std::function<uint64_t(int)>& tag, int step0, DType dtype, RedOp rop,
+                           const char* S, char* R, size_t n, float scale);
   // Where the members of a group run: N nodes with L members each (member positions per node, in member order), and this
   // rank's place.  false unless the group is regular (same L > 1 on each of N > 1 nodes).
   struct NodeMap {
@@ -1108,6 +1113,20 @@ void NetBackend::execute(CommRequest& r) {
       const DType pdt = d.has_out_dtype ? d.out_dtype : d.dtype;
       MLSLB_ASSERT(pdt == DType::F32 || pdt == DType::BF16, "fused update: parameter dtype must be f32/bf16");
       const size_t pdts = dtype_size(pdt);
+      {
+        // groups with several members per node: the same reduce-scatter -> shared optimizer step -> all-gather, each in two
+        // levels (fp32 gradients; bf16 ones keep the flat form, whose sum is accumulated in fp32)
+        NodeMap nm;
+        const long hier_kb = ctx_->env.net_hier_kb;
+        if (d.dtype == DType::F32 && hier_kb >= 0 && (size_t)P * n * dt >= (size_t)hier_kb << 10 && n && node_map(g, nm)) {
+          std::vector<float> gsum(n);
+          hier_reduce_scatter(nm, g, tag, 204, DType::F32, RedOp::SUM, S, (char*)gsum.data(), n, d.scale);
+          char* param = (char*)d.fused.param;
+          host_optimizer_step(d.fused, pdt, param + (size_t)me * n * pdts, gsum.data(), n);
+          hier_allgather(nm, g, tag, 209, param + (size_t)me * n * pdts, param, n * pdts);
+          break;
+        }
+      }
       char* tmp = net_scratch((size_t)P * n * dt);
       for (int p = 0; p < P; ++p)
         if (p != me) {
@@ -1250,80 +1269,90 @@ bool NetBackend::hierarchical_gather_scatter(CommRequest& r, const ProcessGroup&
   const long hier_kb = ctx_->env.net_hier_kb;
   const CommDesc& d = r.desc;
   const size_t dt = dtype_size(d.dtype), n = d.count;      // n = elements of ONE block (per member)
-  const int P = g.size();
-  if (hier_kb < 0 || (size_t)P * n * dt < (size_t)hier_kb << 10 || n == 0) return false;
+  if (hier_kb < 0 || (size_t)g.size() * n * dt < (size_t)hier_kb << 10 || n == 0) return false;
   NodeMap nm;
   if (!node_map(g, nm)) return false;
-  const int N = nm.N, L = nm.L, my_node = nm.my_node, li = nm.li;
-  char* S = (char*)r.send;
-  char* R = (char*)r.recv;
-  auto peer = [&](int p) { return g.members[p]; };
-  const size_t blk = n * dt;
-  std::vector<Seg> snd, rcv;
   if (d.kind == OpKind::ALLGATHER) {
-    // between nodes: my block goes to the members with my local index, theirs arrive at their places in R
-    if (R + (size_t)g.idx * blk != S) memmove(R + (size_t)g.idx * blk, S, blk);
-    for (int k = 0; k < N; ++k) {
-      if (k == my_node) continue;
-      const int p = nm.on_node[k][li];
-      snd.push_back(Seg{peer(p), R + (size_t)g.idx * blk, blk});
-      rcv.push_back(Seg{peer(p), R + (size_t)p * blk, blk});
-    }
-    mesh_.exchange(tag(204), snd, rcv);
-    snd.clear();
-    rcv.clear();
-    // inside the node: everybody passes on the N blocks of its column, packed [node 0 .. node N-1]
-    char* scratch = net_scratch((size_t)L * N * blk);
-    char* mine = scratch + (size_t)li * N * blk;
-    for (int k = 0; k < N; ++k) memcpy(mine + (size_t)k * blk, R + (size_t)nm.on_node[k][li] * blk, blk);
-    for (int j = 0; j < L; ++j) {
-      if (j == li) continue;
-      const int p = nm.on_node[my_node][j];
-      snd.push_back(Seg{peer(p), mine, (size_t)N * blk});
-      rcv.push_back(Seg{peer(p), scratch + (size_t)j * N * blk, (size_t)N * blk});
-    }
-    mesh_.exchange(tag(205), snd, rcv);
-    for (int j = 0; j < L; ++j)
-      if (j != li)
-        for (int k = 0; k < N; ++k) memcpy(R + (size_t)nm.on_node[k][j] * blk, scratch + ((size_t)j * N + k) * blk, blk);
+    hier_allgather(nm, g, tag, 204, (const char*)r.send, (char*)r.recv, n * dt);
     return true;
   }
   if (d.kind == OpKind::REDUCE_SCATTER) {
-    // inside the node: local member j collects, from every local member, the blocks meant for column j (packed by node) and
-    // adds them up - N partial sums per rank
-    char* scratch = net_scratch(((size_t)L * N + (size_t)L * N + N + N) * blk);
-    char* out_pack = scratch;                                   // [j][k]: what I send to local member j
-    char* in_pack = scratch + (size_t)L * N * blk;              // [j][k]: what local member j sent me
-    char* partial = in_pack + (size_t)L * N * blk;              // [k]: node-local sum of the block for member on_node[k][li]
-    char* from_nodes = partial + (size_t)N * blk;               // [k]: partial sums for ME from the other nodes
-    for (int j = 0; j < L; ++j)
-      for (int k = 0; k < N; ++k) memcpy(out_pack + ((size_t)j * N + k) * blk, S + (size_t)nm.on_node[k][j] * blk, blk);
-    for (int j = 0; j < L; ++j) {
-      if (j == li) continue;
-      const int p = nm.on_node[my_node][j];
-      snd.push_back(Seg{peer(p), out_pack + (size_t)j * N * blk, (size_t)N * blk});
-      rcv.push_back(Seg{peer(p), in_pack + (size_t)j * N * blk, (size_t)N * blk});
-    }
-    mesh_.exchange(tag(204), snd, rcv);
-    snd.clear();
-    rcv.clear();
-    std::vector<const void*> srcs(L);
-    for (int j = 0; j < L; ++j) srcs[j] = j == li ? (const void*)(out_pack + (size_t)li * N * blk) : (const void*)(in_pack + (size_t)j * N * blk);
-    host_reduce(d.dtype, partial, srcs, (size_t)N * n, d.rop, 1.0f);
-    // between nodes: the partial sum for each member of my column goes to that member; add what arrives for me
-    for (int k = 0; k < N; ++k) {
-      if (k == my_node) continue;
-      const int p = nm.on_node[k][li];
-      snd.push_back(Seg{peer(p), partial + (size_t)k * blk, blk});
-      rcv.push_back(Seg{peer(p), from_nodes + (size_t)k * blk, blk});
-    }
-    mesh_.exchange(tag(205), snd, rcv);
-    std::vector<const void*> parts(N);
-    for (int k = 0; k < N; ++k) parts[k] = k == my_node ? (const void*)(partial + (size_t)my_node * blk) : (const void*)(from_nodes + (size_t)k * blk);
-    host_reduce(d.dtype, R, parts, n, d.rop, d.scale);
+    hier_reduce_scatter(nm, g, tag, 204, d.dtype, d.rop, (const char*)r.send, (char*)r.recv, n, d.scale);
     return true;
   }
   return false;
+}
+
+// between nodes: my block goes to the members with my local index, theirs arrive at their places in R; inside the node:
+// everybody passes on the N blocks of its column, packed [node 0 .. node N-1]          (tags step0, step0 + 1)
+void NetBackend::hier_allgather(const NodeMap& nm, const ProcessGroup& g, const std::function<uint64_t(int)>& tag, int step0, const char* S,
+                                char* R, size_t blk) {
+  const int N = nm.N, L = nm.L, my_node = nm.my_node, li = nm.li;
+  auto peer = [&](int p) { return g.members[p]; };
+  std::vector<Seg> snd, rcv;
+  if (R + (size_t)g.idx * blk != S) memmove(R + (size_t)g.idx * blk, S, blk);
+  for (int k = 0; k < N; ++k) {
+    if (k == my_node) continue;
+    const int p = nm.on_node[k][li];
+    snd.push_back(Seg{peer(p), R + (size_t)g.idx * blk, blk});
+    rcv.push_back(Seg{peer(p), R + (size_t)p * blk, blk});
+  }
+  mesh_.exchange(tag(step0), snd, rcv);
+  snd.clear();
+  rcv.clear();
+  char* scratch = net_scratch((size_t)L * N * blk);
+  char* mine = scratch + (size_t)li * N * blk;
+  for (int k = 0; k < N; ++k) memcpy(mine + (size_t)k * blk, R + (size_t)nm.on_node[k][li] * blk, blk);
+  for (int j = 0; j < L; ++j) {
+    if (j == li) continue;
+    const int p = nm.on_node[my_node][j];
+    snd.push_back(Seg{peer(p), mine, (size_t)N * blk});
+    rcv.push_back(Seg{peer(p), scratch + (size_t)j * N * blk, (size_t)N * blk});
+  }
+  mesh_.exchange(tag(step0 + 1), snd, rcv);
+  for (int j = 0; j < L; ++j)
+    if (j != li)
+      for (int k = 0; k < N; ++k) memcpy(R + (size_t)nm.on_node[k][j] * blk, scratch + ((size_t)j * N + k) * blk, blk);
+}
+
+// inside the node: local member j collects, from every local member, the blocks meant for column j (packed by node) and adds
+// them up - N partial sums per rank; between nodes: the partial sum for each member of my column goes to that member, which
+// adds what arrives (scale applied there)                                            (tags step0, step0 + 1)
+void NetBackend::hier_reduce_scatter(const NodeMap& nm, const ProcessGroup& g, const std::function<uint64_t(int)>& tag, int step0, DType dtype,
+                                     RedOp rop, const char* S, char* R, size_t n, float scale) {
+  const int N = nm.N, L = nm.L, my_node = nm.my_node, li = nm.li;
+  const size_t blk = n * dtype_size(dtype);
+  auto peer = [&](int p) { return g.members[p]; };
+  std::vector<Seg> snd, rcv;
+  char* scratch = net_scratch(((size_t)L * N + (size_t)L * N + N + N) * blk);
+  char* out_pack = scratch;                                   // [j][k]: what I send to local member j
+  char* in_pack = scratch + (size_t)L * N * blk;              // [j][k]: what local member j sent me
+  char* partial = in_pack + (size_t)L * N * blk;              // [k]: node-local sum of the block for member on_node[k][li]
+  char* from_nodes = partial + (size_t)N * blk;               // [k]: partial sums for ME from the other nodes
+  for (int j = 0; j < L; ++j)
+    for (int k = 0; k < N; ++k) memcpy(out_pack + ((size_t)j * N + k) * blk, S + (size_t)nm.on_node[k][j] * blk, blk);
+  for (int j = 0; j < L; ++j) {
+    if (j == li) continue;
+    const int p = nm.on_node[my_node][j];
+    snd.push_back(Seg{peer(p), out_pack + (size_t)j * N * blk, (size_t)N * blk});
+    rcv.push_back(Seg{peer(p), in_pack + (size_t)j * N * blk, (size_t)N * blk});
+  }
+  mesh_.exchange(tag(step0), snd, rcv);
+  snd.clear();
+  rcv.clear();
+  std::vector<const void*> srcs(L);
+  for (int j = 0; j < L; ++j) srcs[j] = j == li ? (const void*)(out_pack + (size_t)li * N * blk) : (const void*)(in_pack + (size_t)j * N * blk);
+  host_reduce(dtype, partial, srcs, (size_t)N * n, rop, 1.0f);
+  for (int k = 0; k < N; ++k) {
+    if (k == my_node) continue;
+    const int p = nm.on_node[k][li];
+    snd.push_back(Seg{peer(p), partial + (size_t)k * blk, blk});
+    rcv.push_back(Seg{peer(p), from_nodes + (size_t)k * blk, blk});
+  }
+  mesh_.exchange(tag(step0 + 1), snd, rcv);
+  std::vector<const void*> parts(N);
+  for (int k = 0; k < N; ++k) parts[k] = k == my_node ? (const void*)(partial + (size_t)my_node * blk) : (const void*)(from_nodes + (size_t)k * blk);
+  host_reduce(dtype, R, parts, n, rop, scale);
 }
 
 // Broadcast in two levels: the root's column (the members with its local index, one per node) gets the buffer over the wire -
