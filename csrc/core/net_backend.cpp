@@ -749,6 +749,8 @@ class NetBackend final : public Backend {
   bool hierarchical_gather_scatter(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
   bool hierarchical_bcast(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag);
   struct NodeMap;
+  void hierarchical_allreduce_pipelined(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag, const NodeMap& nm,
+                                        size_t piece_bytes);
   void hier_allgather(const NodeMap& nm, const ProcessGroup& g, const std::function<uint64_t(int)>& tag, int step0, const char* S, char* R,
                       size_t blk);
   void hier_reduce_scatter(const NodeMap& nm, const ProcessGroup& g, const std::function<uint64_t(int)>& tag, int step0, DType dtype, RedOp rop,
@@ -1193,6 +1195,12 @@ bool NetBackend::hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, c
   const size_t per_n = ceil_div(per_l, (size_t)N);                   // sub-slice of node k inside a shard
   auto lo_n = [&](size_t shard_len, int k) { return std::min(shard_len, (size_t)k * per_n); };
   auto len_n = [&](size_t shard_len, int k) { return std::min(shard_len, lo_n(shard_len, k) + per_n) - lo_n(shard_len, k); };
+  const bool quant = d.compress && d.dtype == DType::F32 && d.rop == RedOp::SUM;
+  const size_t piece_bytes = std::max<size_t>(4096, (size_t)std::max(0l, ctx_->env.net_chunk_kb) << 10);
+  if (!quant && per_l * dt >= 2 * piece_bytes && ctx_->env.net_hier_pipeline) {
+    hierarchical_allreduce_pipelined(r, g, tag, nm, piece_bytes);
+    return true;
+  }
   char* scratch = net_scratch(((size_t)L * per_l + per_l + (size_t)N * per_n) * dt);
   char* tmpA = scratch;                                              // L slices received inside the node
   char* shard = scratch + (size_t)L * per_l * dt;                    // my 1/L of the node's sum, then of the total
@@ -1260,6 +1268,128 @@ bool NetBackend::hierarchical_allreduce(CommRequest& r, const ProcessGroup& g, c
   }
   mesh_.exchange(tag(203), snd, rcv);
   return true;
+}
+
+// The two-level all-reduce cut into pieces: the shard (1/L of the message) is divided into up to 48 pieces, and every piece
+// runs through the four steps on its own - node-local reduce-scatter, reduce-scatter among the nodes, all-gather among the
+// nodes, node-local all-gather - driven by the arrivals inside ONE exchange: when the L - 1 local copies of a piece are there
+// it is summed and its sub-slices leave for the other nodes, when their N - 1 copies of my sub-slice are there it is summed
+// (scale applied) and passed around, and when a piece is complete it goes to the local members.  The shared-memory steps of
+// later pieces run while earlier pieces are on the wire.  Same chains of additions as the one-piece form: same bits.
+void NetBackend::hierarchical_allreduce_pipelined(CommRequest& r, const ProcessGroup& g, const std::function<uint64_t(int)>& tag,
+                                                  const NodeMap& nm, size_t piece_bytes) {
+  const CommDesc& d = r.desc;
+  const size_t dt = dtype_size(d.dtype), n = d.count;
+  const int N = nm.N, L = nm.L, my_node = nm.my_node, li = nm.li;
+  char* S = (char*)r.send;
+  char* R = (char*)r.recv;
+  auto peer = [&](int p) { return g.members[p]; };
+  constexpr int kMaxPieces = 16;                                      // (four steps x 16 tags fit the 8-bit step field with room to spare)
+  const size_t per_l = ceil_div(n, (size_t)L);
+  auto lo_l = [&](int j) { return std::min(n, (size_t)j * per_l); };
+  auto len_l = [&](int j) { return std::min(n, lo_l(j) + per_l) - lo_l(j); };
+  size_t ce = std::max(piece_bytes / dt, ceil_div(per_l, (size_t)kMaxPieces));
+  ce = (ce + 63) & ~(size_t)63;
+  const int K = (int)ceil_div(per_l, ce);
+  auto plen = [&](int j, int c) {                                      // length of piece c inside slice j
+    const size_t Lj = len_l(j), b = (size_t)c * ce;
+    return b >= Lj ? (size_t)0 : std::min(ce, Lj - b);
+  };
+  const size_t per_n = ceil_div(ce, (size_t)N);                       // sub-slice of node k inside a piece
+  auto slo = [&](size_t m, int k) { return std::min(m, (size_t)k * per_n); };
+  auto slen = [&](size_t m, int k) { return std::min(m, slo(m, k) + per_n) - slo(m, k); };
+  auto step = [&](int phase, int c) { return 2 + phase * kMaxPieces + c; };
+  char* scratch = net_scratch(((size_t)L * per_l + per_l + (size_t)K * N * per_n) * dt);
+  char* tmpA = scratch;                                               // [j]: local member j's copy of my slice
+  char* shard = scratch + (size_t)L * per_l * dt;                     // my slice: node sum, then total
+  char* tmpB = shard + per_l * dt;                                    // [c][k]: node k's copy of my sub-slice of piece c
+  struct Meta {
+    int phase, c;
+  };
+  std::vector<Seg> snd, rcv;
+  std::vector<Meta> meta;
+  std::vector<int> gotA(K, 0), gotB1(K, 0), gotB2(K, 0), needB1(K, 0), needB2(K, 0);
+  for (int c = 0; c < K; ++c) {
+    const size_t m = plen(li, c);
+    // step 0 (inside the node): piece c of everybody's slice
+    for (int j = 0; j < L; ++j) {
+      if (j == li) continue;
+      const int p = nm.on_node[my_node][j];
+      if (plen(j, c)) snd.push_back(Seg{peer(p), S + (lo_l(j) + (size_t)c * ce) * dt, plen(j, c) * dt, tag(step(0, c))});
+      if (m) {
+        rcv.push_back(Seg{peer(p), tmpA + ((size_t)j * per_l + (size_t)c * ce) * dt, m * dt, tag(step(0, c))});
+        meta.push_back(Meta{0, c});
+      }
+    }
+    if (!m) continue;
+    for (int k = 0; k < N; ++k) {
+      if (k == my_node) continue;
+      const int p = nm.on_node[k][li];
+      if (slen(m, my_node)) {                                          // step 1: their copies of my sub-slice
+        rcv.push_back(Seg{peer(p), tmpB + ((size_t)c * N + k) * per_n * dt, slen(m, my_node) * dt, tag(step(1, c))});
+        meta.push_back(Meta{1, c});
+        ++needB1[c];
+      }
+      if (slen(m, k)) {                                                // step 2: their finished sub-slices
+        rcv.push_back(Seg{peer(p), shard + ((size_t)c * ce + slo(m, k)) * dt, slen(m, k) * dt, tag(step(2, c))});
+        meta.push_back(Meta{2, c});
+        ++needB2[c];
+      }
+    }
+  }
+  for (int j = 0; j < L; ++j) {                                        // step 3 (inside the node): finished pieces of the others
+    if (j == li) continue;
+    const int p = nm.on_node[my_node][j];
+    for (int c = 0; c < K; ++c)
+      if (plen(j, c)) {
+        rcv.push_back(Seg{peer(p), R + (lo_l(j) + (size_t)c * ce) * dt, plen(j, c) * dt, tag(step(3, c))});
+        meta.push_back(Meta{3, c});
+      }
+  }
+  std::vector<const void*> srcs;
+  std::vector<char> localDone(K, 0), subDone(K, 0), pieceDone(K, 0);
+  // One rule for every arrival: a piece moves on as far as its inputs allow (an arrival can run ahead of the step before it -
+  // the other nodes may be faster with piece c than this node's members - so every step checks the one before it too).
+  auto advance = [&](int c) {
+    const size_t m = plen(li, c), off = (size_t)c * ce;
+    if (!localDone[c] && gotA[c] == L - 1) {                          // the node's copies of piece c of my slice are here
+      srcs.assign(L, nullptr);
+      for (int j = 0; j < L; ++j)
+        srcs[j] = j == li ? (const void*)(S + (lo_l(li) + off) * dt) : (const void*)(tmpA + ((size_t)j * per_l + off) * dt);
+      host_reduce(d.dtype, shard + off * dt, srcs, m, d.rop, 1.0f);
+      for (int k = 0; k < N; ++k)
+        if (k != my_node && slen(m, k))
+          mesh_.add_send(Seg{peer(nm.on_node[k][li]), shard + (off + slo(m, k)) * dt, slen(m, k) * dt, tag(step(1, c))});
+      localDone[c] = 1;
+    }
+    if (localDone[c] && !subDone[c] && gotB1[c] == needB1[c]) {       // every node's copy of my sub-slice of piece c is here
+      const size_t sub = slen(m, my_node);
+      if (sub) {
+        srcs.assign(N, nullptr);
+        for (int k = 0; k < N; ++k)
+          srcs[k] = k == my_node ? (const void*)(shard + (off + slo(m, my_node)) * dt) : (const void*)(tmpB + ((size_t)c * N + k) * per_n * dt);
+        host_reduce(d.dtype, shard + (off + slo(m, my_node)) * dt, srcs, sub, d.rop, d.scale);     // (element-wise: in place is fine)
+        for (int k = 0; k < N; ++k)
+          if (k != my_node) mesh_.add_send(Seg{peer(nm.on_node[k][li]), shard + (off + slo(m, my_node)) * dt, sub * dt, tag(step(2, c))});
+      }
+      subDone[c] = 1;
+    }
+    if (subDone[c] && !pieceDone[c] && gotB2[c] == needB2[c]) {       // piece c of my shard is final: to the result, to the node
+      memcpy(R + (lo_l(li) + off) * dt, shard + off * dt, m * dt);
+      for (int j = 0; j < L; ++j)
+        if (j != li) mesh_.add_send(Seg{peer(nm.on_node[my_node][j]), shard + off * dt, m * dt, tag(step(3, c))});
+      pieceDone[c] = 1;
+    }
+  };
+  Mesh::RecvFn on_recv = [&](size_t i) {
+    const Meta& mt = meta[i];
+    if (mt.phase == 0) ++gotA[mt.c];
+    else if (mt.phase == 1) ++gotB1[mt.c];
+    else if (mt.phase == 2) ++gotB2[mt.c];
+    else return;
+    advance(mt.c);
+  };
+  mesh_.exchange(tag(0), snd, rcv, &on_recv);
 }
 
 // The same two levels for all-gather and reduce-scatter (the pair behind the distributed weight update): between nodes only

@@ -52,13 +52,15 @@ def test_same_node_ranks_talk_through_shared_memory(shm, ring_kb, expect):
     assert out.count("NET CHUNK OK") == 4 and out.count(expect) == 4, out[-3000:]
 
 
-@pytest.mark.parametrize("nnodes,per_node,hier_kb", [(2, 2, "0"), (2, 3, "0"), (3, 2, "16"), (2, 2, "-1")])
-def test_two_level_allreduce_is_exact(nnodes, per_node, hier_kb):
+@pytest.mark.parametrize("nnodes,per_node,hier_kb,chunk_kb", [(2, 2, "0", "512"), (2, 3, "0", "4"), (3, 2, "16", "4"), (2, 2, "0", "4"),
+                                                               (2, 2, "-1", "512")])
+def test_two_level_allreduce_is_exact(nnodes, per_node, hier_kb, chunk_kb):
     """Groups with the same number of members on every node reduce inside the node first (shared memory), exchange 1/L of the
     message between the nodes and gather inside the node again; MLSL_NET_HIER_KB = smallest message that goes that way
-    (-1: never).  Same exact results for every size / dtype / in place or not, also with 3 ranks per node or 3 nodes."""
+    (-1: never); with 4 KiB pieces the all-reduce runs as a pipeline of pieces through its four steps.  Same exact results for
+    every size / dtype / in place or not, also with 3 ranks per node or 3 nodes."""
     rcs, out = _launch(nnodes, per_node, [sys.executable, os.path.join(ROOT, "tests", "net_chunk_worker.py")],
-                       extra_env={"MLSL_NET_HIER_KB": hier_kb})
+                       extra_env={"MLSL_NET_HIER_KB": hier_kb, "MLSL_NET_CHUNK_KB": chunk_kb})
     assert all(rc == 0 for rc in rcs), out[-3000:]
     assert out.count("NET CHUNK OK") == nnodes * per_node
 
