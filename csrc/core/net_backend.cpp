@@ -11,6 +11,12 @@
 //   all-reduce     : reduce-scatter + all-gather              fused update : reduce-scatter + optimizer + all-gather
 // Messages carry a tag (signal row, lane, sequence number, step), so collectives of different groups may be in flight on
 // the same connection; an early message is parked until its collective asks for it.  Buffers are ordinary host memory.
+//
+// On top of that (round 2): an exchange may carry several tagged messages per peer and run a callback per arrival, which may
+// queue further sends - large reductions travel as a pipeline of pieces; ranks of one node talk through shared-memory byte
+// rings instead of their socket (same stream semantics); groups with several members per node run all-reduce, all-gather,
+// reduce-scatter, broadcast and the fused update in two levels (node-local step, 1/L of the bytes between nodes, node-local
+// step), the compressed all-reduce with fp8 only on the wire between nodes.
 #include <fcntl.h>
 #include <poll.h>
 #include <sched.h>
