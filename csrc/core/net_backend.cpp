@@ -61,6 +61,7 @@ constexpr size_t kOneShotBytes = 32 << 10;   // all-reduce up to this size: one 
 // queued behind the held message on that connection.
 constexpr size_t kEagerBytes = 32 << 10;
 constexpr size_t kBcastSplitBytes = 128 << 10;   // broadcast from this size on: scatter + all-gather
+constexpr int kTreeMinRanks = 4;                 // small broadcasts and barriers of this many members take log P steps
 
 struct WireHdr {
   uint64_t tag, bytes;
@@ -355,6 +356,7 @@ class Mesh {
     push_ready(x);
     for (int spin = 0; spin < 200 && x.pending_in; ++spin)
       for (int p : rpeers) {
+        if (peers_[p].expect.empty()) continue;      // everything of this peer is in: no system call for it
         x.pending_in -= drain(p);
         if (x.fresh) push_ready(x);
       }
@@ -652,6 +654,9 @@ class Mesh {
         P.dst = nullptr;
         if (cur_ && cur_->on_recv) (*cur_->on_recv)(idx);
       }
+      // nothing else is expected from this peer now: what it sends next belongs to a later collective and is read then
+      // (saves the receive call that would only report an empty socket)
+      if (P.expect.empty()) return completed;
     }
   }
 
@@ -931,6 +936,17 @@ void NetBackend::execute(CommRequest& r) {
 
   switch (d.kind) {
     case OpKind::BARRIER:
+      if (P >= kTreeMinRanks) {
+        // dissemination: in round k everybody signals the member 2^k places ahead and waits for the one 2^k places behind;
+        // after ceil(log2 P) rounds every member has (transitively) heard from every other - log P messages per rank
+        // instead of P - 1
+        for (int k = 0, dist = 1; dist < P; ++k, dist <<= 1) {
+          snd.push_back(Seg{peer((me + dist) % P), nullptr, 0});
+          rcv.push_back(Seg{peer((me - dist + P) % P), nullptr, 0});
+          go(k);
+        }
+        break;
+      }
       for (int p = 0; p < P; ++p)
         if (p != me) {
           snd.push_back(Seg{peer(p), nullptr, 0});
@@ -941,6 +957,24 @@ void NetBackend::execute(CommRequest& r) {
     case OpKind::BCAST: {
       const int root = (int)d.root;
       if (hierarchical_bcast(r, g, tag)) break;
+      if (n * dt < kBcastSplitBytes && P >= kTreeMinRanks) {
+        // small, four members or more: binomial tree.  Member v (counted from the root) gets the buffer from v minus its
+        // lowest set bit and passes it to v + 2^k for every 2^k below that bit, farthest first: the root's connection
+        // carries log2 P copies instead of P - 1 and the copies of one level travel at the same time
+        const int v = (me - root + P) % P;
+        int low = 1;
+        if (v) {
+          while (!(v & low)) low <<= 1;
+          rcv.push_back(Seg{peer((v - low + root) % P), R, n * dt, tag(1)});
+          go(0);
+        } else {
+          while (low < P) low <<= 1;
+        }
+        for (int b = low >> 1; b >= 1; b >>= 1)
+          if (v + b < P) snd.push_back(Seg{peer((v + b + root) % P), R, n * dt, tag(1)});
+        if (!snd.empty()) go(0);
+        break;
+      }
       if (n * dt < kBcastSplitBytes || P < 3) {   // small: the root sends the whole buffer to everybody
         if (me == root) {
           for (int p = 0; p < P; ++p)

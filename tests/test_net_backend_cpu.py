@@ -76,6 +76,17 @@ def test_reductions_in_pieces_are_exact(nnodes, per_node):
     assert out.count("NET CHUNK OK") == nnodes * per_node
 
 
+@pytest.mark.parametrize("nnodes,per_node", [(4, 1), (5, 1), (3, 2), (7, 1)])
+def test_small_broadcasts_and_barriers_take_log_p_steps(nnodes, per_node):
+    """From four members on a small broadcast runs down a binomial tree and the barrier is a dissemination barrier: every
+    root, member counts that are not a power of two, queued broadcasts, and a barrier that holds everybody until the last
+    member arrives."""
+    rcs, out = _launch(nnodes, per_node, [sys.executable, os.path.join(ROOT, "tests", "net_tree_worker.py")],
+                       extra_env={"MLSL_NET_HIER_KB": "-1"})
+    assert all(rc == 0 for rc in rcs), out[-3000:]
+    assert out.count("NET TREE OK") == nnodes * per_node
+
+
 def test_interface_selection_like_the_reference():
     """MLSL_IFACE_NAME (prefix) / MLSL_IFACE_IDX pick the interface of the data connections (reference eplib/server.c:228-330)."""
     psutil = pytest.importorskip("psutil")
