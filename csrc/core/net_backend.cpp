@@ -460,6 +460,8 @@ class Mesh {
     bool held = false;                    // header read, large payload left in the socket until its receive is posted
     std::map<uint64_t, Expect> expect;    // tag -> waiting receive of the running exchange
     std::map<uint64_t, std::vector<char>> parked;
+    std::vector<char> ra;                 // read-ahead of the socket (sock_read)
+    size_t ra_lo = 0, ra_hi = 0;
     // same node: the byte streams of the pair run through shared memory instead of the socket
     ShmRing *tx = nullptr, *rx = nullptr;
     char* seg = nullptr;
@@ -579,6 +581,28 @@ class Mesh {
     }
   }
 
+  // recv() with read-ahead: a short read (a header, a small payload) fetches up to kReadAhead bytes from the socket in one
+  // system call and serves what follows from there - header and payload of a small message cost one call instead of two,
+  // several small messages one; long reads go straight to their destination.  Same return convention as recv().
+  static constexpr size_t kReadAhead = 16 << 10;
+  ssize_t sock_read(Peer& P, int fd, char* dst, size_t want) {
+    if (P.ra_lo < P.ra_hi) {
+      const size_t k = std::min(want, P.ra_hi - P.ra_lo);
+      memcpy(dst, P.ra.data() + P.ra_lo, k);
+      P.ra_lo += k;
+      return (ssize_t)k;
+    }
+    if (want >= kReadAhead / 2) return recv(fd, dst, want, 0);
+    if (P.ra.empty()) P.ra.resize(kReadAhead);
+    const ssize_t n = recv(fd, P.ra.data(), kReadAhead, 0);
+    if (n <= 0) return n;
+    const size_t k = std::min(want, (size_t)n);
+    memcpy(dst, P.ra.data(), k);
+    P.ra_lo = k;
+    P.ra_hi = (size_t)n;
+    return (ssize_t)k;
+  }
+
   // read what is available from `peer`; returns how many receives of the running exchange completed
   size_t drain(int peer) {
     Peer& P = peers_[peer];
@@ -587,7 +611,7 @@ class Mesh {
     for (;;) {
       if (P.hdr_got < sizeof(WireHdr)) {
         ssize_t n = P.rx ? (ssize_t)P.rx->read((char*)&P.hdr + P.hdr_got, sizeof(WireHdr) - P.hdr_got)
-                         : recv(fd, (char*)&P.hdr + P.hdr_got, sizeof(WireHdr) - P.hdr_got, 0);
+                         : sock_read(P, fd, (char*)&P.hdr + P.hdr_got, sizeof(WireHdr) - P.hdr_got);
         if (P.rx && n == 0) return completed;
         if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return completed;
         if (n < 0 && errno == EINTR) continue;
@@ -619,7 +643,7 @@ class Mesh {
         P.held = false;
       }
       while (P.got < P.hdr.bytes) {
-        ssize_t n = P.rx ? (ssize_t)P.rx->read(P.dst + P.got, P.hdr.bytes - P.got) : recv(fd, P.dst + P.got, P.hdr.bytes - P.got, 0);
+        ssize_t n = P.rx ? (ssize_t)P.rx->read(P.dst + P.got, P.hdr.bytes - P.got) : sock_read(P, fd, P.dst + P.got, P.hdr.bytes - P.got);
         if (P.rx && n == 0) return completed;
         if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) return completed;
         if (n < 0 && errno == EINTR) continue;
@@ -963,16 +987,24 @@ void NetBackend::execute(CommRequest& r) {
         // carries log2 P copies instead of P - 1 and the copies of one level travel at the same time
         const int v = (me - root + P) % P;
         int low = 1;
-        if (v) {
+        if (v)
           while (!(v & low)) low <<= 1;
-          rcv.push_back(Seg{peer((v - low + root) % P), R, n * dt, tag(1)});
-          go(0);
-        } else {
+        else
           while (low < P) low <<= 1;
-        }
+        std::vector<Seg> kids;
         for (int b = low >> 1; b >= 1; b >>= 1)
-          if (v + b < P) snd.push_back(Seg{peer((v + b + root) % P), R, n * dt, tag(1)});
-        if (!snd.empty()) go(0);
+          if (v + b < P) kids.push_back(Seg{peer((v + b + root) % P), R, n * dt, tag(1)});
+        if (v) {      // one exchange: the copies for the children are queued the moment the parent's message is complete
+          rcv.push_back(Seg{peer((v - low + root) % P), R, n * dt, tag(1)});
+          Mesh::RecvFn forward = [&](size_t) {
+            for (const Seg& k : kids) mesh_.add_send(k);
+          };
+          mesh_.exchange(tag(0), snd, rcv, &forward);
+          rcv.clear();
+        } else {
+          snd = kids;
+          go(0);
+        }
         break;
       }
       if (n * dt < kBcastSplitBytes || P < 3) {   // small: the root sends the whole buffer to everybody
