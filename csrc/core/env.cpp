@@ -137,6 +137,7 @@ EnvConfig parse_env() {
   if (const char* v = ev("MLSL_NET_HIER_KB")) c.net_hier_kb = atol(v);
   getb(c.net_shm, "MLSL_NET_SHM");
   getb(c.net_hier_pipeline, "MLSL_NET_HIER_PIPELINE");
+  if (const char* v = ev("MLSL_NET_SOCKBUF_KB")) c.net_sockbuf_kb = atol(v);
   if (const char* v = ev("MLSL_NET_SHM_RING_KB")) c.net_shm_ring_kb = atol(v);
   if (const char* v = ev("MLSL_NET_EMULATE_GBIT")) c.net_emulate_gbit = atof(v);
   gets(c.node_rank, "MLSL_NODE_RANK", "GROUP_RANK");
@@ -164,8 +165,9 @@ void print_env(const EnvConfig& c) {
   MLSLB_LOG(LOG_INFO, "MLSL_HOSTNAME=%s MLSL_HOSTNAME_TYPE=%d MLSL_IFACE_NAME=%s MLSL_IFACE_IDX=%d", c.hostname.c_str(), c.hostname_type,
             c.iface_name.c_str(), c.iface_idx);
   MLSLB_LOG(LOG_INFO, "MLSL_NET_ADDR=%s MLSL_NET_EAGER_KB=%ld MLSL_NET_ONESHOT_KB=%ld MLSL_NET_CHUNK_KB=%ld MLSL_NET_HIER_KB=%ld MLSL_NET_HIER_PIPELINE=%d MLSL_NET_SHM=%d "
-            "MLSL_NET_SHM_RING_KB=%ld MLSL_NET_EMULATE_GBIT=%g MLSL_NODE_RANK=%s", c.net_addr.c_str(), c.net_eager_kb, c.net_oneshot_kb,
-            c.net_chunk_kb, c.net_hier_kb, (int)c.net_hier_pipeline, (int)c.net_shm, c.net_shm_ring_kb, c.net_emulate_gbit, c.node_rank.c_str());
+            "MLSL_NET_SHM_RING_KB=%ld MLSL_NET_EMULATE_GBIT=%g MLSL_NODE_RANK=%s MLSL_NET_SOCKBUF_KB=%ld", c.net_addr.c_str(), c.net_eager_kb, c.net_oneshot_kb,
+            c.net_chunk_kb, c.net_hier_kb, (int)c.net_hier_pipeline, (int)c.net_shm, c.net_shm_ring_kb, c.net_emulate_gbit, c.node_rank.c_str(),
+            c.net_sockbuf_kb);
   MLSLB_LOG(LOG_INFO, "MLSL_JOB_TOKEN=%s", getenv("MLSL_JOB_TOKEN") ? "(set)" : "(not set)");
   // read where they are used, once, at start-up (device selection and slab / stream set-up of the CUDA backend, logging, tracing)
   auto shown = [](const char* name) { const char* v = getenv(name); return v ? v : "(unset)"; };

@@ -159,6 +159,7 @@ class Mesh {
     // connect to every lower rank (the listen backlog completes the handshake even before the peer accepts) ...
     for (int p = 0; p < rank_; ++p) {
       int fd = tcp_connect_retry(all[p].ip, all[p].port, 60);
+      tcp_tune(fd, ctx->env.net_sockbuf_kb);
       MeshHello me{(uint32_t)rank_, 0, tcp_job_token()};
       try {
         tcp_send_all(fd, &me, sizeof(me));
@@ -174,7 +175,7 @@ class Mesh {
       MLSLB_ASSERT(pr > 0, "data mesh: %d of the %d higher ranks never connected", world_ - 1 - rank_ - accepted, world_ - 1 - rank_);
       int fd = accept4(lfd, nullptr, nullptr, SOCK_CLOEXEC);
       MLSLB_ASSERT(fd >= 0, "accept(): %s", strerror(errno));
-      tcp_tune(fd);
+      tcp_tune(fd, ctx->env.net_sockbuf_kb);
       MeshHello who{0, 0, 0};
       bool ok = true;
       try {

@@ -26,7 +26,7 @@ int tcp_listen(const std::string& addr, int port, int backlog, int* bound_port);
 int tcp_connect_retry(const std::string& addr, int port, int timeout_sec);              // retries until the peer listens
 void tcp_send_all(int fd, const void* buf, size_t bytes);                               // throws mlslb::Error
 void tcp_recv_all(int fd, void* buf, size_t bytes);
-void tcp_tune(int fd);                                                                  // TCP_NODELAY, big buffers
+void tcp_tune(int fd, long sockbuf_kb = 0);                                                                  // TCP_NODELAY; fixed socket buffers of that size if > 0
 std::string tcp_local_address_towards(const std::string& addr, int port);              // my address on the route to addr
 // IPv4 address of the first non-loop-back interface whose name starts with `prefix`, or - empty prefix - of the idx-th one
 // ("" if none); and of a host name / dotted address
