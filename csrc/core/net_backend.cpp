@@ -1190,12 +1190,20 @@ void NetBackend::execute(CommRequest& r) {
       const size_t pdts = dtype_size(pdt);
       {
         // groups with several members per node: the same reduce-scatter -> shared optimizer step -> all-gather, each in two
-        // levels (fp32 gradients; bf16 ones keep the flat form, whose sum is accumulated in fp32)
+        // levels.  bf16 gradients are widened first: the sums are fp32 on both levels like in the flat form, and the wire
+        // between the nodes still carries fewer bytes (fp32 partial sums of 1/L of the slices instead of every bf16 slice)
         NodeMap nm;
         const long hier_kb = ctx_->env.net_hier_kb;
-        if (d.dtype == DType::F32 && hier_kb >= 0 && (size_t)P * n * dt >= (size_t)hier_kb << 10 && n && node_map(g, nm)) {
-          std::vector<float> gsum(n);
-          hier_reduce_scatter(nm, g, tag, 204, DType::F32, RedOp::SUM, S, (char*)gsum.data(), n, d.scale);
+        if (hier_kb >= 0 && (size_t)P * n * dt >= (size_t)hier_kb << 10 && n && node_map(g, nm)) {
+          std::vector<float> gsum(n), wide;
+          const char* grads = S;
+          if (d.dtype == DType::BF16) {
+            wide.resize((size_t)P * n);
+            const uint16_t* h = (const uint16_t*)S;
+            for (size_t i = 0; i < (size_t)P * n; ++i) wide[i] = bf16_to_f32(h[i]);
+            grads = (const char*)wide.data();
+          }
+          hier_reduce_scatter(nm, g, tag, 204, DType::F32, RedOp::SUM, grads, (char*)gsum.data(), n, d.scale);
           char* param = (char*)d.fused.param;
           host_optimizer_step(d.fused, pdt, param + (size_t)me * n * pdts, gsum.data(), n);
           hier_allgather(nm, g, tag, 209, param + (size_t)me * n * pdts, param, n * pdts);
