@@ -120,6 +120,10 @@ asan: bin/mlslrun bin/libmlsl_quant_sample.so
 	cd /tmp/mlsl_asan && MLSL_BACKEND=host ./ftest 2 1 0 1 --inproc 4 | tail -1
 	cd /tmp/mlsl_asan && MLSL_BACKEND=host MLSL_TEST_QUANT_LIB=$(CURDIR)/bin/libmlsl_quant_sample.so ./ftest 1 0 0 0 1 --inproc 4 | tail -1
 	cd /tmp/mlsl_asan && MLSL_BACKEND=host MLSL_HEAP_SIZE_GB=0.2 $(CURDIR)/bin/mlslrun -n 4 ./ftest 2 1 | grep -c "0 FAILED"
+	# net backend (tree broadcast, dissemination barrier, read-ahead reads, shared-memory rings): two launchers playing two nodes
+	cd /tmp/mlsl_asan && ($(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 1 --master-addr 127.0.0.1 --master-port 29879 ./ftest 2 1 > node1.out 2>&1 &) ; \
+	  $(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 0 --master-addr 127.0.0.1 --master-port 29879 ./ftest 2 1 | grep -c "0 FAILED" ; \
+	  ! grep -q "AddressSanitizer\|runtime error" node1.out
 
 clean:
 	rm -rf $(BUILD) $(LIB) bin _install
