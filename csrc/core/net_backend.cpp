@@ -790,7 +790,7 @@ class NetBackend final : public Backend {
   void hier_allgather(const NodeMap& nm, const ProcessGroup& g, const std::function<uint64_t(int)>& tag, int step0, const char* S, char* R,
                       size_t blk);
   void hier_reduce_scatter(const NodeMap& nm, const ProcessGroup& g, const std::function<uint64_t(int)>& tag, int step0, DType dtype, RedOp rop,
-                           const char* S, char* R, size_t n, float scale);
+                           const char* S, char* R, size_t n, float scale, int step_end = 256);
   // Where the members of a group run: N nodes with L members each (member positions per node, in member order), and this
   // rank's place.  false unless the group is regular (same L > 1 on each of N > 1 nodes).
   struct NodeMap {
@@ -1203,7 +1203,7 @@ void NetBackend::execute(CommRequest& r) {
             for (size_t i = 0; i < (size_t)P * n; ++i) wide[i] = bf16_to_f32(h[i]);
             grads = (const char*)wide.data();
           }
-          hier_reduce_scatter(nm, g, tag, 204, DType::F32, RedOp::SUM, grads, (char*)gsum.data(), n, d.scale);
+          hier_reduce_scatter(nm, g, tag, 100, DType::F32, RedOp::SUM, grads, (char*)gsum.data(), n, d.scale, 209);
           char* param = (char*)d.fused.param;
           host_optimizer_step(d.fused, pdt, param + (size_t)me * n * pdts, gsum.data(), n);
           hier_allgather(nm, g, tag, 209, param + (size_t)me * n * pdts, param, n * pdts);
@@ -1488,7 +1488,7 @@ bool NetBackend::hierarchical_gather_scatter(CommRequest& r, const ProcessGroup&
     return true;
   }
   if (d.kind == OpKind::REDUCE_SCATTER) {
-    hier_reduce_scatter(nm, g, tag, 204, d.dtype, d.rop, (const char*)r.send, (char*)r.recv, n, d.scale);
+    hier_reduce_scatter(nm, g, tag, 100, d.dtype, d.rop, (const char*)r.send, (char*)r.recv, n, d.scale);
     return true;
   }
   return false;
@@ -1502,6 +1502,52 @@ void NetBackend::hier_allgather(const NodeMap& nm, const ProcessGroup& g, const 
   auto peer = [&](int p) { return g.members[p]; };
   std::vector<Seg> snd, rcv;
   if (R + (size_t)g.idx * blk != S) memmove(R + (size_t)g.idx * blk, S, blk);
+  // From two pieces per block on, both levels run inside ONE exchange: a piece that arrives from another node is handed to
+  // the local members straight from its place in R (and lands in its place in theirs: no packing on either side), so the
+  // shared-memory step of early pieces runs while later ones are on the wire.  Tags: piece c of the wire step = step0 + c,
+  // piece c of node k's block inside the node = step0 + k C + c (column peers and local peers are different ranks).
+  // (a quarter of the reductions' piece: nothing is computed between the two levels, so finer pieces only shorten the ramp)
+  const size_t piece_bytes = std::max<size_t>(4096, (size_t)std::max(0l, ctx_->env.net_chunk_kb) << 8);
+  const int tags = 255 - step0;
+  if (ctx_->env.net_hier_pipeline && N > 1 && L > 1 && N <= tags && blk >= 2 * piece_bytes) {
+    const int C = (int)std::min<size_t>(ceil_div(blk, piece_bytes), (size_t)std::min(16, tags / N));
+    const size_t ce = (ceil_div(blk, (size_t)C) + 63) & ~(size_t)63;
+    auto plo = [&](int c) { return std::min(blk, (size_t)c * ce); };
+    auto plen = [&](int c) { return std::min(blk, plo(c) + ce) - plo(c); };
+    struct Meta {
+      int k, c;      // k < 0: from a local member, nothing to pass on
+    };
+    std::vector<Meta> meta;
+    for (int c = 0; c < C; ++c) {
+      if (!plen(c)) continue;
+      char* mine = R + (size_t)g.idx * blk + plo(c);
+      for (int k = 0; k < N; ++k) {
+        if (k == my_node) continue;
+        const int p = nm.on_node[k][li];
+        snd.push_back(Seg{peer(p), mine, plen(c), tag(step0 + c)});
+        rcv.push_back(Seg{peer(p), R + (size_t)p * blk + plo(c), plen(c), tag(step0 + c)});
+        meta.push_back(Meta{k, c});
+      }
+      for (int j = 0; j < L; ++j) {
+        if (j == li) continue;
+        const int p = nm.on_node[my_node][j];
+        snd.push_back(Seg{peer(p), mine, plen(c), tag(step0 + my_node * C + c)});
+        for (int k = 0; k < N; ++k) {
+          rcv.push_back(Seg{peer(p), R + (size_t)nm.on_node[k][j] * blk + plo(c), plen(c), tag(step0 + k * C + c)});
+          meta.push_back(Meta{-1, c});
+        }
+      }
+    }
+    Mesh::RecvFn on_recv = [&](size_t i) {
+      const Meta& mt = meta[i];
+      if (mt.k < 0) return;
+      char* src = R + (size_t)nm.on_node[mt.k][li] * blk + plo(mt.c);
+      for (int j = 0; j < L; ++j)
+        if (j != li) mesh_.add_send(Seg{peer(nm.on_node[my_node][j]), src, plen(mt.c), tag(step0 + mt.k * C + mt.c)});
+    };
+    mesh_.exchange(tag(step0), snd, rcv, &on_recv);
+    return;
+  }
   for (int k = 0; k < N; ++k) {
     if (k == my_node) continue;
     const int p = nm.on_node[k][li];
@@ -1530,11 +1576,84 @@ void NetBackend::hier_allgather(const NodeMap& nm, const ProcessGroup& g, const 
 // them up - N partial sums per rank; between nodes: the partial sum for each member of my column goes to that member, which
 // adds what arrives (scale applied there)                                            (tags step0, step0 + 1)
 void NetBackend::hier_reduce_scatter(const NodeMap& nm, const ProcessGroup& g, const std::function<uint64_t(int)>& tag, int step0, DType dtype,
-                                     RedOp rop, const char* S, char* R, size_t n, float scale) {
+                                     RedOp rop, const char* S, char* R, size_t n, float scale, int step_end) {
   const int N = nm.N, L = nm.L, my_node = nm.my_node, li = nm.li;
-  const size_t blk = n * dtype_size(dtype);
+  const size_t dt = dtype_size(dtype), blk = n * dt;
   auto peer = [&](int p) { return g.members[p]; };
   std::vector<Seg> snd, rcv;
+  // From two pieces per block on, both levels run inside ONE exchange.  The blocks leave for the local members straight from
+  // the input (no packing); when the L - 1 local copies of piece c of the block for node k's member of my column are here it
+  // is summed and leaves for that member (k = my node: it stays), and when the N - 1 partial sums of piece c of MY block are
+  // here the piece is finished (scale applied) - the node-local additions of later pieces run while earlier partial sums are
+  // on the wire.  Same chains of additions as the two-exchange form below: same bits.
+  // Tags [step0, step_end): piece c inside the node = step0 + k C + c, between the nodes = step0 + c (different peers).
+  const size_t piece_bytes = std::max<size_t>(4096, (size_t)std::max(0l, ctx_->env.net_chunk_kb) << 10);
+  const int tags = std::min(step_end, 256) - step0;
+  if (ctx_->env.net_hier_pipeline && N > 1 && L > 1 && N <= tags && blk >= 2 * piece_bytes) {
+    const int C = (int)std::min<size_t>(ceil_div(blk, piece_bytes), (size_t)std::min(16, tags / N));
+    const size_t ce = (ceil_div(n, (size_t)C) + 63) & ~(size_t)63;                  // elements per piece
+    auto plo = [&](int c) { return std::min(n, (size_t)c * ce); };
+    auto plen = [&](int c) { return std::min(n, plo(c) + ce) - plo(c); };
+    const size_t P = (size_t)N * L;
+    const bool alias = R < S + P * blk && S < R + blk;                             // in place: the input is still being sent
+    char* scratch = net_scratch(((size_t)L * N + N + N + 1) * blk);
+    char* in_pack = scratch;                                   // [j][k]: local member j's copy of the block for on_node[k][li]
+    char* partial = in_pack + (size_t)L * N * blk;             // [k]: the node's sum of that block
+    char* from_nodes = partial + (size_t)N * blk;              // [k]: node k's sum of MY block
+    char* out = alias ? from_nodes + (size_t)N * blk : R;
+    struct Meta {
+      int wire, k, c;
+    };
+    std::vector<Meta> meta;
+    std::vector<int> got_local((size_t)N * C, 0), got_wire(C, 0);
+    std::vector<char> local_done((size_t)N * C, 0), done(C, 0);
+    for (int c = 0; c < C; ++c) {
+      if (!plen(c)) continue;
+      for (int kk = 1; kk <= N; ++kk) {                        // the blocks that have to cross the wire first, my node's last
+        const int k = (my_node + kk) % N;
+        for (int j = 0; j < L; ++j) {
+          if (j == li) continue;
+          const int p = nm.on_node[my_node][j];
+          snd.push_back(Seg{peer(p), const_cast<char*>(S) + (size_t)nm.on_node[k][j] * blk + plo(c) * dt, plen(c) * dt, tag(step0 + k * C + c)});
+          rcv.push_back(Seg{peer(p), in_pack + ((size_t)j * N + k) * blk + plo(c) * dt, plen(c) * dt, tag(step0 + k * C + c)});
+          meta.push_back(Meta{0, k, c});
+        }
+        if (k != my_node) {
+          rcv.push_back(Seg{peer(nm.on_node[k][li]), from_nodes + (size_t)k * blk + plo(c) * dt, plen(c) * dt, tag(step0 + c)});
+          meta.push_back(Meta{1, k, c});
+        }
+      }
+    }
+    std::vector<const void*> srcs;
+    auto finish = [&](int c) {
+      if (done[c] || !local_done[(size_t)my_node * C + c] || got_wire[c] != N - 1) return;
+      srcs.assign(N, nullptr);
+      for (int k = 0; k < N; ++k) srcs[k] = (k == my_node ? partial : from_nodes) + (size_t)k * blk + plo(c) * dt;
+      host_reduce(dtype, out + plo(c) * dt, srcs, plen(c), rop, scale);
+      done[c] = 1;
+    };
+    Mesh::RecvFn on_recv = [&](size_t i) {
+      const Meta& mt = meta[i];
+      const int c = mt.c, k = mt.k;
+      if (mt.wire) {
+        ++got_wire[c];
+        finish(c);
+        return;
+      }
+      if (++got_local[(size_t)k * C + c] != L - 1) return;
+      srcs.assign(L, nullptr);
+      for (int j = 0; j < L; ++j)
+        srcs[j] = j == li ? (const void*)(S + (size_t)nm.on_node[k][li] * blk + plo(c) * dt)
+                          : (const void*)(in_pack + ((size_t)j * N + k) * blk + plo(c) * dt);
+      host_reduce(dtype, partial + (size_t)k * blk + plo(c) * dt, srcs, plen(c), rop, 1.0f);
+      local_done[(size_t)k * C + c] = 1;
+      if (k != my_node) mesh_.add_send(Seg{peer(nm.on_node[k][li]), partial + (size_t)k * blk + plo(c) * dt, plen(c) * dt, tag(step0 + c)});
+      else finish(c);
+    };
+    mesh_.exchange(tag(step0), snd, rcv, &on_recv);
+    if (alias) memcpy(R, out, blk);
+    return;
+  }
   char* scratch = net_scratch(((size_t)L * N + (size_t)L * N + N + N) * blk);
   char* out_pack = scratch;                                   // [j][k]: what I send to local member j
   char* in_pack = scratch + (size_t)L * N * blk;              // [j][k]: what local member j sent me

@@ -55,6 +55,11 @@ def main():
     mine = vec(r, n, torch.float32)
     got = mlsl.allgather(mine)
     assert torch.equal(got, torch.cat([vec(q, n, torch.float32) for q in range(P)]))
+    for m, dtype in ((9, torch.int32), (4099, torch.float64), (300003, torch.bfloat16)):   # in place: my block sits where it belongs
+        full = torch.zeros(P * m, dtype=dtype)
+        full[r * m:(r + 1) * m] = vec(r, m, dtype)
+        mlsl.allgather(full[r * m:(r + 1) * m], out=full)
+        assert torch.equal(full, torch.cat([vec(q, m, dtype) for q in range(P)])), ("allgather in place", m, dtype)
     a2a = mlsl.alltoall(torch.cat([vec(r * P + q, n, torch.int32) for q in range(P)]))
     assert torch.equal(a2a, torch.cat([vec(q * P + r, n, torch.int32) for q in range(P)]))
     b = vec(7, 300001, torch.float64) if r == P - 1 else torch.zeros(300001, dtype=torch.float64)
