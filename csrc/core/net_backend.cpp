@@ -1587,7 +1587,8 @@ void NetBackend::hier_reduce_scatter(const NodeMap& nm, const ProcessGroup& g, c
   // here the piece is finished (scale applied) - the node-local additions of later pieces run while earlier partial sums are
   // on the wire.  Same chains of additions as the two-exchange form below: same bits.
   // Tags [step0, step_end): piece c inside the node = step0 + k C + c, between the nodes = step0 + c (different peers).
-  const size_t piece_bytes = std::max<size_t>(4096, (size_t)std::max(0l, ctx_->env.net_chunk_kb) << 10);
+  // (pieces of MLSL_NET_CHUNK_KB / 4 like the all-gather: 4 MiB on 2 x 4 ranks 4.3 -> 3.2 ms, larger sizes unchanged)
+  const size_t piece_bytes = std::max<size_t>(4096, (size_t)std::max(0l, ctx_->env.net_chunk_kb) << 8);
   const int tags = std::min(step_end, 256) - step0;
   if (ctx_->env.net_hier_pipeline && N > 1 && L > 1 && N <= tags && blk >= 2 * piece_bytes) {
     const int C = (int)std::min<size_t>(ceil_div(blk, piece_bytes), (size_t)std::min(16, tags / N));
@@ -1706,6 +1707,43 @@ bool NetBackend::hierarchical_bcast(CommRequest& r, const ProcessGroup& g, const
   char* R = (char*)r.recv;
   auto peer = [&](int p) { return g.members[p]; };
   std::vector<Seg> snd, rcv;
+  // Two nodes, two pieces or more: one exchange on every rank - the root feeds the other node's column member and its own
+  // node piece by piece, the column member passes every piece on to its node when it arrives (shared memory while the next
+  // piece is on the wire), the others receive the pieces in place.                  (tags: wire 210 + c, inside a node 230 + c)
+  const size_t piece_bytes = std::max<size_t>(4096, (size_t)std::max(0l, ctx_->env.net_chunk_kb) << 8);
+  if (N == 2 && ctx_->env.net_hier_pipeline && bytes >= 2 * piece_bytes) {
+    const int C = (int)std::min<size_t>(ceil_div(bytes, piece_bytes), 16);
+    const size_t ce = (ceil_div(bytes, (size_t)C) + 63) & ~(size_t)63;
+    auto plo = [&](int c) { return std::min(bytes, (size_t)c * ce); };
+    auto plen = [&](int c) { return std::min(bytes, plo(c) + ce) - plo(c); };
+    auto to_node = [&](int c, bool queued) {
+      for (int j = 0; j < L; ++j) {
+        if (j == li) continue;
+        const Seg sg{peer(nm.on_node[my_node][j]), R + plo(c), plen(c), tag(230 + c)};
+        if (queued) mesh_.add_send(sg);
+        else snd.push_back(sg);
+      }
+    };
+    for (int c = 0; c < C; ++c) {
+      if (!plen(c)) continue;
+      if (li != root_li) {
+        rcv.push_back(Seg{peer(nm.on_node[my_node][root_li]), R + plo(c), plen(c), tag(230 + c)});
+      } else if (my_node == root_node) {
+        snd.push_back(Seg{peer(nm.on_node[1 - my_node][li]), R + plo(c), plen(c), tag(210 + c)});
+        to_node(c, false);
+      } else {
+        rcv.push_back(Seg{peer(root), R + plo(c), plen(c), tag(210 + c)});
+      }
+    }
+    std::vector<int> piece_of;                             // receive index -> piece (empty pieces are not posted)
+    for (int c = 0; c < C; ++c)
+      if (plen(c)) piece_of.push_back(c);
+    Mesh::RecvFn on_recv = [&](size_t i) {
+      if (li == root_li && my_node != root_node) to_node(piece_of[i], true);
+    };
+    mesh_.exchange(tag(206), snd, rcv, &on_recv);
+    return true;
+  }
   if (li == root_li) {                                   // the column of the root: between nodes
     if (N == 2) {
       if (my_node == root_node) snd.push_back(Seg{peer(nm.on_node[1 - my_node][li]), R, bytes});
