@@ -1744,6 +1744,54 @@ bool NetBackend::hierarchical_bcast(CommRequest& r, const ProcessGroup& g, const
     mesh_.exchange(tag(206), snd, rcv, &on_recv);
     return true;
   }
+  // Three nodes and more: the same scatter + all-gather among the root's column, slice by slice inside one exchange - a
+  // column member passes its own slice on to the other column members the moment it has it, and every slice (its own, the
+  // root's, the others') goes to its node when it arrives.                    (tags: wire 210 + slice, inside a node 230 + slice)
+  if (N >= 3 && N <= 16 && ctx_->env.net_hier_pipeline && bytes >= 2 * piece_bytes) {
+    const size_t per = (ceil_div(bytes, (size_t)N) + 63) & ~(size_t)63;
+    auto lo = [&](int k) { return std::min(bytes, (size_t)k * per); };
+    auto len = [&](int k) { return std::min(bytes, lo(k) + per) - lo(k); };
+    const bool column = li == root_li, is_root = column && my_node == root_node;
+    std::vector<int> slice_of;                             // receive index -> slice
+    auto to_node = [&](int sl, bool queued) {
+      for (int j = 0; j < L; ++j) {
+        if (j == li) continue;
+        const Seg sg{peer(nm.on_node[my_node][j]), R + lo(sl), len(sl), tag(230 + sl)};
+        if (queued) mesh_.add_send(sg);
+        else snd.push_back(sg);
+      }
+    };
+    auto expect = [&](int from, int sl, int step) {
+      if (!len(sl)) return;
+      rcv.push_back(Seg{peer(from), R + lo(sl), len(sl), tag(step + sl)});
+      slice_of.push_back(sl);
+    };
+    if (!column) {
+      for (int sl = 0; sl < N; ++sl) expect(nm.on_node[my_node][root_li], sl, 230);
+    } else if (is_root) {
+      for (int k = 0; k < N; ++k)
+        if (k != my_node && len(k)) snd.push_back(Seg{peer(nm.on_node[k][li]), R + lo(k), len(k), tag(210 + k)});
+      for (int k = 0; k < N; ++k)
+        if (k != my_node && len(my_node)) snd.push_back(Seg{peer(nm.on_node[k][li]), R + lo(my_node), len(my_node), tag(210 + my_node)});
+      for (int sl = 0; sl < N; ++sl)
+        if (len(sl)) to_node(sl, false);
+    } else {
+      expect(root, my_node, 210);
+      expect(root, root_node, 210);
+      for (int k = 0; k < N; ++k)
+        if (k != my_node && k != root_node) expect(nm.on_node[k][li], k, 210);
+    }
+    Mesh::RecvFn on_recv = [&](size_t i) {
+      if (!column || is_root) return;
+      const int sl = slice_of[i];
+      if (sl == my_node)
+        for (int k = 0; k < N; ++k)
+          if (k != my_node && k != root_node) mesh_.add_send(Seg{peer(nm.on_node[k][li]), R + lo(sl), len(sl), tag(210 + sl)});
+      to_node(sl, true);
+    };
+    mesh_.exchange(tag(206), snd, rcv, &on_recv);
+    return true;
+  }
   if (li == root_li) {                                   // the column of the root: between nodes
     if (N == 2) {
       if (my_node == root_node) snd.push_back(Seg{peer(nm.on_node[1 - my_node][li]), R, bytes});

@@ -65,6 +65,11 @@ def main():
     b = vec(7, 300001, torch.float64) if r == P - 1 else torch.zeros(300001, dtype=torch.float64)
     mlsl.bcast(b, root=P - 1)
     assert torch.equal(b, vec(7, 300001, torch.float64))
+    for root in range(P):                                   # every root: a different column / node feeds the others
+        m = 100003 + root
+        b = vec(root, m, torch.float32) if r == root else torch.zeros(m)
+        mlsl.bcast(b, root=root)
+        assert torch.equal(b, vec(root, m, torch.float32)), ("bcast", root)
     if len(sys.argv) > 1 and sys.argv[1] == "describe":
         print(mlsl.env().describe_backend(), flush=True)
     mlsl.barrier()
