@@ -124,6 +124,10 @@ asan: bin/mlslrun bin/libmlsl_quant_sample.so
 	cd /tmp/mlsl_asan && ($(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 1 --master-addr 127.0.0.1 --master-port 29879 ./ftest 2 1 > node1.out 2>&1 &) ; \
 	  $(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 0 --master-addr 127.0.0.1 --master-port 29879 ./ftest 2 1 | grep -c "0 FAILED" ; \
 	  ! grep -q "AddressSanitizer\|runtime error" node1.out
+	# ... and with every two-level collective on its piece-by-piece route (4 KiB pieces)
+	cd /tmp/mlsl_asan && export MLSL_NET_HIER_KB=0 MLSL_NET_CHUNK_KB=4 && ($(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 1 --master-addr 127.0.0.1 --master-port 29881 ./ftest 2 1 > node1p.out 2>&1 &) ; \
+	  $(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 0 --master-addr 127.0.0.1 --master-port 29881 ./ftest 2 1 | grep -c "0 FAILED" ; \
+	  ! grep -q "AddressSanitizer\|runtime error" node1p.out
 
 clean:
 	rm -rf $(BUILD) $(LIB) bin _install
