@@ -90,6 +90,11 @@ tsan: bin/mlslrun
 	# net backend (control server, receiver thread, TCP mesh): two launchers playing two nodes
 	cd /tmp/mlsl_tsan && (TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" $(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 1 --master-addr 127.0.0.1 --master-port 29877 ./ftest 2 1 > node1.out 2>&1 &) ; \
 	  TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" $(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 0 --master-addr 127.0.0.1 --master-port 29877 ./ftest 2 1 | grep -c "0 FAILED"
+	# ... and with every two-level collective on its piece-by-piece route (4 KiB pieces)
+	cd /tmp/mlsl_tsan && export MLSL_NET_HIER_KB=0 MLSL_NET_CHUNK_KB=4 TSAN_OPTIONS="halt_on_error=1 report_signal_unsafe=0" && \
+	  ($(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 1 --master-addr 127.0.0.1 --master-port 29883 ./ftest 2 1 > node1p.out 2>&1 &) ; \
+	  $(CURDIR)/bin/mlslrun -n 2 --nnodes 2 --node-rank 0 --master-addr 127.0.0.1 --master-port 29883 ./ftest 2 1 | grep -c "0 FAILED" ; \
+	  ! grep -q "ThreadSanitizer" node1p.out
 
 # make install PREFIX=/opt/mlsl_b200: the layout of the reference's package (intel64/{bin,lib,include}, doc, examples,
 # the environment script), plus the Python package
