@@ -16,7 +16,10 @@
 // queue further sends - large reductions travel as a pipeline of pieces; ranks of one node talk through shared-memory byte
 // rings instead of their socket (same stream semantics); groups with several members per node run all-reduce, all-gather,
 // reduce-scatter, broadcast and the fused update in two levels (node-local step, 1/L of the bytes between nodes, node-local
-// step), the compressed all-reduce with fp8 only on the wire between nodes.
+// step), the compressed all-reduce with fp8 only on the wire between nodes.  Each of those two-level collectives is ONE
+// exchange from two pieces per block on: what arrives on one level is reduced / passed on to the other level inside the
+// arrival callback, so shared-memory work of early pieces overlaps the wire time of later ones (MLSL_NET_HIER_PIPELINE=0:
+// the levels as separate exchanges).
 #include <fcntl.h>
 #include <poll.h>
 #include <sched.h>
