@@ -110,7 +110,7 @@ struct EnvConfig {
   long net_chunk_kb = 512;       // MLSL_NET_CHUNK_KB: reductions of slices >= 2x this travel in pieces of this size
   long net_hier_kb = 1024;       // MLSL_NET_HIER_KB: two-level all-reduce / all-gather / reduce-scatter from this size (-1 never)
   long net_sockbuf_kb = 0;       // MLSL_NET_SOCKBUF_KB: fixed send / receive buffers of the data sockets (0: kernel auto-tuning)
-  bool net_hier_pipeline = true; // MLSL_NET_HIER_PIPELINE: the two-level all-reduce runs piece by piece (MLSL_NET_CHUNK_KB)
+  bool net_hier_pipeline = true; // MLSL_NET_HIER_PIPELINE: the two-level collectives run piece by piece inside one exchange (MLSL_NET_CHUNK_KB)
   bool net_shm = true;           // MLSL_NET_SHM: same-node ranks exchange through shared-memory rings
   long net_shm_ring_kb = 1024;   // MLSL_NET_SHM_RING_KB: ring size per direction of a same-node pair
   double net_emulate_gbit = 0;   // MLSL_NET_EMULATE_GBIT: pace every rank's TCP egress (bench / test knob)
